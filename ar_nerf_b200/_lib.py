@@ -1,0 +1,116 @@
+"""ctypes loader for libarnerf.so (the C ABI declared in include/arnerf.h).
+
+There is NO fallback: if the CUDA library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarnerf.so")
+
+P = C.c_void_p
+I = C.c_int
+L = C.c_int64
+F = C.c_float
+
+
+class Levels(C.Structure):
+    _fields_ = [("scale_host", P), ("res_host", P), ("size_host", P), ("offset_host", P)]
+
+
+class FieldWs(C.Structure):
+    _fields_ = [("feat", P), ("hid", P), ("h", P), ("in32", P), ("hid1", P), ("hid2", P)]
+
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/arnerf.h one to one
+SIGNATURES = {
+    "arn_version": [],
+    "arn_last_error": [],
+    "arn_launch_count": [],
+    "arn_ray_aabb_intersect": [P, P, L, P, P, I, I, P, P, P, P],
+    "arn_ray_sphere_intersect": [P, P, L, P, P, I, I, P, P, P, P],
+    "arn_ray_aabb_near": [P, P, L, P, P, F, P, P],
+    "arn_morton3d": [P, L, P, P],
+    "arn_morton3d_invert": [P, L, P, P],
+    "arn_packbits": [P, I, F, P, L, P],
+    "arn_march_train_count": [P, P, P, L, P, I, I, F, F, P, I, P, P, P],
+    "arn_march_train_emit": [P, P, P, L, P, I, I, F, F, P, I, P, P, P, P, P, L, P],
+    "arn_march_train_count_ex": [P, P, P, L, P, I, I, F, F, P, I, P, P, P, P],
+    "arn_march_train_emit_ex": [P, P, P, L, P, I, I, F, F, P, I, P, P, P, P, P, P, L, P],
+    "arn_march_test": [P, P, P, P, L, P, I, I, F, F, I, I, P, P, P, P, P, P],
+    "arn_composite_train_fw": [P, P, P, P, P, L, L, F, P, P, P, P, P, P],
+    "arn_composite_train_bw": [P, P, P, P, P, P, P, P, P, P, P, P, P, L, L, F, P, P, P],
+    "arn_composite_test_fw": [P, P, P, P, P, L, I, F, P, P, P, P, P],
+    "arn_distortion_fw": [P, P, P, P, L, L, P, P, P, P],
+    "arn_distortion_bw": [P, P, P, P, P, P, P, L, L, P, P],
+    "arn_march_train_bw": [P, P, P, P, L, P, P, P],
+    "arn_hashgrid_geometry": [I, I, F, I, P, P, P, P],
+    "arn_cast_f32_to_f16": [P, P, L, P],
+    "arn_field_fw": [P, P, L, P, P, Levels, P, P, I, FieldWs, P, P, P],
+    "arn_field_bw": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
+    "arn_field_fw_simt": [P, P, L, P, P, Levels, P, P, I, FieldWs, P, P, P],
+    "arn_field_bw_simt": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
+    "arn_hash_encode_fw": [P, L, P, P, Levels, P, P, P],
+    "arn_hash_encode_bw": [P, L, P, P, Levels, P, P, P, P, P],
+    "arn_sh4": [P, L, P, P],
+    "arn_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, I, P],
+}
+_RESTYPES = {"arn_last_error": C.c_char_p, "arn_launch_count": C.c_int64}
+
+_lib = None
+
+
+def lib():
+    """Load libarnerf.so once.  Raises RuntimeError when it has not been built (python __graft_entry__.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C ar_nerf_b200/csrc` (or __graft_entry__.build()). "
+                "ar_nerf_b200 has no CPU / PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = l
+    return _lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point; raise RuntimeError(arn_last_error()) on failure."""
+    l = lib()
+    rc = getattr(l, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {l.arn_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib().arn_launch_count())
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def check_tensor(t, name, dtype=None, ndim=None, last=None):
+    """Reference behaviour (include/utils.h:4-6: CUDA + contiguous) plus dtype/shape validation."""
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+    if last is not None and t.shape[-1] != last:
+        raise RuntimeError(f"{name} must have last dim {last}, got shape {tuple(t.shape)}")
+    return t

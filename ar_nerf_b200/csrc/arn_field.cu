@@ -1,0 +1,554 @@
+// libarnerf.so -- the field: multiresolution hash grid + density MLP + SH-4 + colour MLP (replaces tiny-cuda-nn as
+// used by models/networks.py:37-78,95-108,133-165).  Numeric contract: fp16 operands, fp32 accumulate.
+//
+// This file holds the hash-grid encode/backward, SH-4, parameter cast and Adam kernels plus the CUDA-core ("simt")
+// MLP kernels.  The simt MLP follows the oracle's operation order exactly (k-ascending fmaf), which makes the whole
+// forward bit-comparable with oracle/oracle_field.c; the tensor-core MLP (arn_mlp_tc.cu) is validated against it.
+#include "arn_common.cuh"
+#include "arn_field.cuh"
+
+namespace arn {
+
+// ------------------------------------------------------------------------------------------------ parameter cast
+__global__ void __launch_bounds__(256) cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n && ((uintptr_t)(src + i) & 15) == 0 && ((uintptr_t)(dst + i) & 7) == 0) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(dst + i) = o;
+    } else {
+        for (int k = 0; k < 4 && i + k < n; k++) dst[i + k] = __float2half_rn(src[i + k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ hash grid
+// Forward, one thread per (sample, level) -- SURVEY Appendix A.3.
+__global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __restrict__ xyzs, int64_t n, Aabb box,
+                                                             const __grid_constant__ LevelTable tbl,
+                                                             const __half2* __restrict__ table, __half2* __restrict__ feat) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (i >= n) return;
+    float w[3]; uint32_t g[3];
+    level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
+    const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
+        const float2 v = __half22float2(table[off + grid_index(size, res, p)]);
+        acc0 = __fmaf_rn(wt, v.x, acc0); acc1 = __fmaf_rn(wt, v.y, acc1);
+    }
+    feat[i * ARN_N_LEVELS + l] = __floats2half2_rn(acc0, acc1);
+}
+
+// Backward into the table, one thread per (sample, level): vector red.global.add.v2.f32 per corner.
+__global__ void __launch_bounds__(256) hash_encode_bw_kernel(const float* __restrict__ xyzs, int64_t n, Aabb box,
+                                                             const __grid_constant__ LevelTable tbl,
+                                                             const float2* __restrict__ dfeat, float2* __restrict__ table_grad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (i >= n) return;
+    const float2 d = dfeat[i * ARN_N_LEVELS + l];
+    if (d.x == 0.0f && d.y == 0.0f) return;
+    float w[3]; uint32_t g[3];
+    level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
+    const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
+        atomicAdd(table_grad + off + grid_index(size, res, p), make_float2(wt * d.x, wt * d.y));
+    }
+}
+
+// dL/dxyz through the trilinear weights (render_surface_normal, rendering.py:301-313): one thread per sample.
+__global__ void __launch_bounds__(256) hash_encode_dx_kernel(const float* __restrict__ xyzs, int64_t n, Aabb box,
+                                                             const __grid_constant__ LevelTable tbl,
+                                                             const __half2* __restrict__ table, const float2* __restrict__ dfeat,
+                                                             float* __restrict__ dL_dxyzs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gx[3] = {0.f, 0.f, 0.f};
+    for (int l = 0; l < ARN_N_LEVELS; l++) {
+        float w[3]; uint32_t g[3];
+        level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
+        const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
+        const float2 d = dfeat[i * ARN_N_LEVELS + l];
+        for (int c = 0; c < 8; c++) {
+            uint32_t p[3]; corner_weight(c, w, g, p);
+            const float2 t = __half22float2(table[off + grid_index(size, res, p)]);
+            const float v = t.x * d.x + t.y * d.y;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float wd = 1.0f;
+#pragma unroll
+                for (int e = 0; e < 3; e++) if (e != k) wd *= (c & (1 << e)) ? w[e] : 1.0f - w[e];
+                gx[k] += ((c & (1 << k)) ? 1.0f : -1.0f) * wd * v * tbl.scale[l];
+            }
+        }
+    }
+    // chain through x01 = (x - min) / (max - min)
+    dL_dxyzs[3 * i] = gx[0] / (box.mx[0] - box.mn[0]);
+    dL_dxyzs[3 * i + 1] = gx[1] / (box.mx[1] - box.mn[1]);
+    dL_dxyzs[3 * i + 2] = gx[2] / (box.mx[2] - box.mn[2]);
+}
+
+// ------------------------------------------------------------------------------------------------ SH-4
+__global__ void __launch_bounds__(256) sh4_kernel(const float* __restrict__ dirs, int64_t n, __half* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float sh[16];
+    sh4_eval(dirs + 3 * i, sh);
+    __half2* o = reinterpret_cast<__half2*>(out + 16 * i);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = __floats2half2_rn(sh[2 * k], sh[2 * k + 1]);
+}
+
+// ------------------------------------------------------------------------------------------------ simt MLPs
+// Weights live in shared memory TRANSPOSED ([k][j], j contiguous) so a 128-bit load yields 8 output neurons of one
+// input; every thread of a warp reads the same address (broadcast, conflict-free).  One thread per sample.
+template <int J, int K>
+__device__ __forceinline__ void load_wt(const __half* __restrict__ W, __half* sW) {  // W [J][K] -> sW [K][J]
+    for (int e = threadIdx.x; e < J * K; e += blockDim.x) { const int j = e / K, k = e % K; sW[k * J + j] = W[e]; }
+}
+// acc[j] = sum_k W[j][k] x[k], k ascending (same order as the oracle's matvec)
+template <int J, int K>
+__device__ __forceinline__ void matvec(const __half* sWt, const __half* x, float* acc) {
+#pragma unroll
+    for (int j = 0; j < J; j++) acc[j] = 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+        const float xk = __half2float(x[k]);
+        const uint4* row = reinterpret_cast<const uint4*>(sWt + k * J);
+#pragma unroll
+        for (int j8 = 0; j8 < J / 8; j8++) {
+            const uint4 q = row[j8];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float2 wv = __half22float2(h2[u]);
+                acc[j8 * 8 + 2 * u] = __fmaf_rn(wv.x, xk, acc[j8 * 8 + 2 * u]);
+                acc[j8 * 8 + 2 * u + 1] = __fmaf_rn(wv.y, xk, acc[j8 * 8 + 2 * u + 1]);
+            }
+        }
+    }
+}
+// dx[k] = sum_j W[j][k] g[j], j ascending; weights in ORIGINAL layout sW [J][K] (k contiguous)
+template <int J, int K>
+__device__ __forceinline__ void matvec_t(const __half* sW, const __half* g, float* dx) {
+#pragma unroll
+    for (int k = 0; k < K; k++) dx[k] = 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < J; j++) {
+        const float gj = __half2float(g[j]);
+        const uint4* row = reinterpret_cast<const uint4*>(sW + j * K);
+#pragma unroll
+        for (int k8 = 0; k8 < K / 8; k8++) {
+            const uint4 q = row[k8];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float2 wv = __half22float2(h2[u]);
+                dx[k8 * 8 + 2 * u] = __fmaf_rn(wv.x, gj, dx[k8 * 8 + 2 * u]);
+                dx[k8 * 8 + 2 * u + 1] = __fmaf_rn(wv.y, gj, dx[k8 * 8 + 2 * u + 1]);
+            }
+        }
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ void load_row(const __half* __restrict__ src, __half* dst) {  // NV halves, 16-byte chunks
+#pragma unroll
+    for (int q = 0; q < NV / 8; q++) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(src)[q];
+}
+template <int NV>
+__device__ __forceinline__ void store_row(__half* __restrict__ dst, const __half* src) {
+#pragma unroll
+    for (int q = 0; q < NV / 8; q++) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(src)[q];
+}
+
+// Density net 32 -> 64 (ReLU) -> 16 ; sigma = exp(h0)
+__global__ void __launch_bounds__(128) density_mlp_fw_simt_kernel(const __half* __restrict__ feat, int64_t n, const __half* __restrict__ Wd,
+                                                                  __half* __restrict__ hid, float* __restrict__ h, float* __restrict__ sigmas) {
+    __shared__ __align__(16) __half sW1[32 * 64];
+    __shared__ __align__(16) __half sW2[64 * 16];
+    load_wt<64, 32>(Wd, sW1); load_wt<16, 64>(Wd + 2048, sW2);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    __align__(16) __half x[32]; load_row<32>(feat + 32 * i, x);
+    float acc[64];
+    matvec<64, 32>(sW1, x, acc);
+    __align__(16) __half hv[64];
+#pragma unroll
+    for (int j = 0; j < 64; j++) hv[j] = __float2half_rn(fmaxf(acc[j], 0.0f));
+    store_row<64>(hid + 64 * i, hv);
+    float o[16];
+    matvec<16, 64>(sW2, hv, o);
+#pragma unroll
+    for (int q = 0; q < 4; q++) reinterpret_cast<float4*>(h + 16 * i)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    sigmas[i] = expf(o[0]);
+}
+
+// Colour net 32 -> 64 -> 64 (ReLU) -> 16 ; input [sh16 | fp16(h16)] ; Sigmoid / None on the first 3 outputs
+__global__ void __launch_bounds__(128) rgb_mlp_fw_simt_kernel(const float* __restrict__ dirs, const float* __restrict__ h, int64_t n,
+                                                              const __half* __restrict__ Wc, int rgb_act, __half* __restrict__ in32,
+                                                              __half* __restrict__ hid1, __half* __restrict__ hid2, float* __restrict__ rgbs) {
+    __shared__ __align__(16) __half sW1[32 * 64];
+    __shared__ __align__(16) __half sW2[64 * 64];
+    __shared__ __align__(16) __half sW3[64 * 16];
+    load_wt<64, 32>(Wc, sW1); load_wt<64, 64>(Wc + 2048, sW2); load_wt<16, 64>(Wc + 2048 + 4096, sW3);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    __align__(16) __half x[32];
+    {
+        float sh[16]; sh4_eval(dirs + 3 * i, sh);
+#pragma unroll
+        for (int k = 0; k < 16; k++) { x[k] = __float2half_rn(sh[k]); x[16 + k] = __float2half_rn(h[16 * i + k]); }
+    }
+    store_row<32>(in32 + 32 * i, x);
+    float acc[64];
+    __align__(16) __half a1[64], a2[64];
+    matvec<64, 32>(sW1, x, acc);
+#pragma unroll
+    for (int j = 0; j < 64; j++) a1[j] = __float2half_rn(fmaxf(acc[j], 0.0f));
+    store_row<64>(hid1 + 64 * i, a1);
+    matvec<64, 64>(sW2, a1, acc);
+#pragma unroll
+    for (int j = 0; j < 64; j++) a2[j] = __float2half_rn(fmaxf(acc[j], 0.0f));
+    store_row<64>(hid2 + 64 * i, a2);
+    float o[16];
+    matvec<16, 64>(sW3, a2, o);
+#pragma unroll
+    for (int j = 0; j < 3; j++) rgbs[3 * i + j] = rgb_act ? 1.0f / (1.0f + expf(-o[j])) : o[j];
+}
+
+// Backward of both nets (oracle_field.c orc_field_mlp_bw).  Persistent CTAs of 128 threads walk 128-sample tiles.
+// Per tile: each thread runs its sample's dgrad chain (bit-identical order with the oracle), stages (g, x) pairs of
+// every layer in shared memory, then the CTA accumulates its share of the five weight gradients in registers;
+// one atomicAdd per weight per CTA at the end.
+template <int J, int K>
+__device__ __forceinline__ void wgrad_tile(const __half* sG, const __half* sX, int rows, float* acc) {
+    // thread t owns elements e = t + 128*i  (j = e / K, k = e % K); sG [128][64], sX [128][64]
+    constexpr int PER = J * K / 128;
+    for (int s = 0; s < rows; s++) {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int e = threadIdx.x + 128 * i; const int j = e / K, k = e % K;
+            acc[i] = __fmaf_rn(__half2float(sG[s * 64 + j]), __half2float(sX[s * 64 + k]), acc[i]);
+        }
+    }
+}
+template <int J, int K>
+__device__ __forceinline__ void wgrad_flush(const float* acc, float scale, float* __restrict__ dW) {
+    constexpr int PER = J * K / 128;
+#pragma unroll
+    for (int i = 0; i < PER; i++) atomicAdd(dW + threadIdx.x + 128 * i, acc[i] * scale);
+}
+
+__global__ void __launch_bounds__(128) field_mlp_bw_simt_kernel(int64_t n, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
+                                                                const float* __restrict__ rgbs, const float* __restrict__ h,
+                                                                const __half* __restrict__ feat, const __half* __restrict__ hid,
+                                                                const __half* __restrict__ in32, const __half* __restrict__ hid1,
+                                                                const __half* __restrict__ hid2, const __half* __restrict__ Wd,
+                                                                const __half* __restrict__ Wc, int rgb_act, float loss_scale,
+                                                                float* __restrict__ dWd, float* __restrict__ dWc, float* __restrict__ dfeat) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* sWc1 = reinterpret_cast<__half*>(smem_raw);  // [64][32]
+    __half* sWc2 = sWc1 + 2048;                          // [64][64]
+    __half* sWc3 = sWc2 + 4096;                          // [16][64]
+    __half* sWd1 = sWc3 + 1024;                          // [64][32]
+    __half* sWd2 = sWd1 + 2048;                          // [16][64]
+    __half* sG = sWd2 + 1024;                            // [128][64]
+    __half* sX = sG + 128 * 64;                          // [128][64]
+    const bool has_rgb = Wc != nullptr;
+    for (int e = threadIdx.x; e < 3072; e += 128) sWd1[e] = Wd[e];  // sWd1|sWd2 contiguous, same layout as params
+    if (has_rgb) for (int e = threadIdx.x; e < 7168; e += 128) sWc1[e] = Wc[e];
+    __syncthreads();
+    float aC1[16], aC2[32], aC3[8], aD1[16], aD2[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { aC1[i] = 0.f; aD1[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 32; i++) aC2[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { aC3[i] = 0.f; aD2[i] = 0.f; }
+    const float inv_scale = 1.0f / loss_scale;
+    const int64_t n_tiles = (n + 127) / 128;
+    __half* myG = sG + threadIdx.x * 64; __half* myX = sX + threadIdx.x * 64;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * 128 + threadIdx.x;
+        const bool valid = i < n;
+        const int rows = (int)min((int64_t)128, n - tile * 128);
+        float t[64];
+        __align__(16) __half g64[64];
+        // ---- colour branch
+        if (has_rgb) {
+            // output layer
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float g = 0.0f;
+                if (valid && j < 3 && dL_drgbs) {
+                    const float y = rgbs[3 * i + j];
+                    g = dL_drgbs[3 * i + j] * (rgb_act ? y * (1.0f - y) : 1.0f);
+                }
+                g64[j] = __float2half_rn(g * loss_scale);
+            }
+            if (valid) { store_row<16>(myG, g64); load_row<64>(hid2 + 64 * i, myX); }
+            __syncthreads();
+            wgrad_tile<16, 64>(sG, sX, rows, aC3);
+            __syncthreads();
+            if (valid) {
+                matvec_t<16, 64>(sWc3, g64, t);
+#pragma unroll
+                for (int k = 0; k < 64; k++) g64[k] = __float2half_rn(__half2float(myX[k]) > 0.0f ? t[k] : 0.0f);
+            }
+            __syncthreads();
+            if (valid) { store_row<64>(myG, g64); load_row<64>(hid1 + 64 * i, myX); }
+            __syncthreads();
+            wgrad_tile<64, 64>(sG, sX, rows, aC2);
+            __syncthreads();
+            if (valid) {
+                matvec_t<64, 64>(sWc2, g64, t);
+#pragma unroll
+                for (int k = 0; k < 64; k++) g64[k] = __float2half_rn(__half2float(myX[k]) > 0.0f ? t[k] : 0.0f);
+            }
+            __syncthreads();
+            if (valid) { store_row<64>(myG, g64); load_row<32>(in32 + 32 * i, myX); }
+            __syncthreads();
+            wgrad_tile<64, 32>(sG, sX, rows, aC1);
+            __syncthreads();
+            if (valid) matvec_t<64, 32>(sWc1, g64, t);  // t[16..31] = scaled dL/dh from the colour branch
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; k++) t[k] = 0.0f;
+        }
+        // ---- density branch: dL/dh0 += dL/dsigma * exp(clamp(h0,-15,15))   (custom_functions.py:170-173)
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float g = t[16 + j];
+                if (j == 0 && dL_dsigmas) g += (dL_dsigmas[i] * expf(fminf(fmaxf(h[16 * i], -15.0f), 15.0f))) * loss_scale;
+                g64[j] = __float2half_rn(g);
+            }
+            store_row<16>(myG, g64); load_row<64>(hid + 64 * i, myX);
+        }
+        __syncthreads();
+        wgrad_tile<16, 64>(sG, sX, rows, aD2);
+        __syncthreads();
+        if (valid) {
+            matvec_t<16, 64>(sWd2, g64, t);
+#pragma unroll
+            for (int k = 0; k < 64; k++) g64[k] = __float2half_rn(__half2float(myX[k]) > 0.0f ? t[k] : 0.0f);
+        }
+        __syncthreads();
+        if (valid) { store_row<64>(myG, g64); load_row<32>(feat + 32 * i, myX); }
+        __syncthreads();
+        wgrad_tile<64, 32>(sG, sX, rows, aD1);
+        __syncthreads();
+        if (valid) {
+            matvec_t<64, 32>(sWd1, g64, t);
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                reinterpret_cast<float4*>(dfeat + 32 * i)[q] =
+                    make_float4(t[4 * q] * inv_scale, t[4 * q + 1] * inv_scale, t[4 * q + 2] * inv_scale, t[4 * q + 3] * inv_scale);
+        }
+    }
+    if (has_rgb) {
+        wgrad_flush<64, 32>(aC1, inv_scale, dWc); wgrad_flush<64, 64>(aC2, inv_scale, dWc + 2048);
+        wgrad_flush<16, 64>(aC3, inv_scale, dWc + 2048 + 4096);
+    }
+    wgrad_flush<64, 32>(aD1, inv_scale, dWd); wgrad_flush<16, 64>(aD2, inv_scale, dWd + 2048);
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam / apex FusedAdam (adam_w_mode=False, wd=0) update, fused with grad un-scale, fp16 refresh, zeroing.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                   __half* __restrict__ p16, int64_t n, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2_sqrt, float inv_gs, int zero_grad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gr = g[i] * inv_gs;
+    if (zero_grad) g[i] = 0.0f;
+    if (gr == 0.0f && m[i] == 0.0f && v[i] == 0.0f) return;  // untouched hash entry: the update is exactly zero
+    const float mi = b1 * m[i] + (1.0f - b1) * gr;
+    const float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float np = p[i] - (lr / bc1) * (mi / denom);
+    p[i] = np;
+    if (p16) p16[i] = __float2half_rn(np);
+}
+
+}  // namespace arn
+
+using namespace arn;
+
+// ================================================================================================ C ABI
+extern "C" ARN_API int arn_hashgrid_geometry(int n_levels, int base_resolution, float per_level_scale, int log2_hashmap_size,
+                                     float* scale_host, uint32_t* res_host, uint32_t* size_host, uint32_t* offset_host) {
+    ARN_REQUIRE(n_levels >= 1 && n_levels <= 32 && base_resolution >= 1 && log2_hashmap_size >= 1 && log2_hashmap_size <= 31, "bad configuration");
+    ARN_REQUIRE(scale_host && res_host && size_host && offset_host, "null pointer");
+    // tiny-cuda-nn grid.h: scale = exp2f(l * log2f(b)) * N_min - 1 ; res = ceilf(scale) + 1 ; entries = min(roundup8(res^3), 2^T)
+    const float log2_pls = log2f(per_level_scale);
+    uint32_t offset = 0;
+    for (int l = 0; l < n_levels; l++) {
+        const float scale = exp2f((float)l * log2_pls) * (float)base_resolution - 1.0f;
+        const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+        const uint32_t max_params = 0xffffffffu / 2u;
+        uint32_t params = max_params;
+        if ((double)res * res * res < (double)max_params) params = res * res * res;
+        params = (params + 7u) / 8u * 8u;
+        const uint32_t cap = 1u << log2_hashmap_size;
+        if (params > cap) params = cap;
+        scale_host[l] = scale; res_host[l] = res; size_host[l] = params; offset_host[l] = offset;
+        offset += params;
+    }
+    offset_host[n_levels] = offset;
+    return ARN_OK;
+}
+
+extern "C" ARN_API int arn_cast_f32_to_f16(const float* src, void* dst_f16, int64_t n, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(src && dst_f16, "null pointer");
+    cast_f32_f16_kernel<<<ceil_div((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst_f16, n);
+    return check_launch("cast_f32_to_f16");
+}
+
+namespace arn {
+int make_levels(const arn_levels_t& lv, LevelTable& t) {
+    if (!lv.scale_host || !lv.res_host || !lv.size_host || !lv.offset_host) { set_error("levels: null host table"); return ARN_E_INVALID; }
+    for (int l = 0; l < ARN_N_LEVELS; l++) {
+        t.scale[l] = lv.scale_host[l]; t.res[l] = lv.res_host[l]; t.size[l] = lv.size_host[l]; t.offset[l] = lv.offset_host[l];
+        if (t.size[l] == 0) { set_error("levels: empty level"); return ARN_E_INVALID; }
+    }
+    return ARN_OK;
+}
+int make_box(const float* mn, const float* mx, Aabb& b) {
+    if (!mn || !mx) { set_error("aabb: null host pointer"); return ARN_E_INVALID; }
+    for (int k = 0; k < 3; k++) { b.mn[k] = mn[k]; b.mx[k] = mx[k]; }
+    return ARN_OK;
+}
+}  // namespace arn
+
+extern "C" ARN_API int arn_hash_encode_fw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                                  arn_levels_t levels, const void* table_f16, void* feat_f16, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(xyzs && table_f16 && feat_f16, "null pointer");
+    LevelTable t; Aabb b;
+    if (int e = make_levels(levels, t)) return e;
+    if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
+    dim3 grid(ceil_div(n, 256), ARN_N_LEVELS);
+    hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, b, t, (const __half2*)table_f16, (__half2*)feat_f16);
+    return check_launch("hash_encode_fw");
+}
+
+extern "C" ARN_API int arn_hash_encode_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                                  arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad,
+                                  float* dL_dxyzs, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(xyzs && dfeat, "null pointer");
+    LevelTable t; Aabb b;
+    if (int e = make_levels(levels, t)) return e;
+    if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (table_grad) {
+        dim3 grid(ceil_div(n, 256), ARN_N_LEVELS);
+        hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, b, t, (const float2*)dfeat, (float2*)table_grad);
+        if (int e = check_launch("hash_encode_bw")) return e;
+    }
+    if (dL_dxyzs) {
+        ARN_REQUIRE(table_f16, "dL_dxyzs needs the table");
+        hash_encode_dx_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xyzs, n, b, t, (const __half2*)table_f16, (const float2*)dfeat, dL_dxyzs);
+        if (int e = check_launch("hash_encode_dx")) return e;
+    }
+    return ARN_OK;
+}
+
+extern "C" ARN_API int arn_sh4(const float* dirs, int64_t n, void* out_f16, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(dirs && out_f16, "null pointer");
+    sh4_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dirs, n, (__half*)out_f16);
+    return check_launch("sh4");
+}
+
+extern "C" ARN_API int arn_field_fw_simt(const float* xyzs, const float* dirs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                                 arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act,
+                                 arn_field_ws_t ws, float* sigmas, float* rgbs, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(xyzs && params_xyz_f16 && ws.feat && ws.hid && ws.h && sigmas, "null pointer");
+    const bool with_rgb = dirs != nullptr;
+    if (with_rgb) ARN_REQUIRE(params_rgb_f16 && ws.in32 && ws.hid1 && ws.hid2 && rgbs, "null pointer (colour branch)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const __half* pxyz = (const __half*)params_xyz_f16;
+    if (int e = arn_hash_encode_fw(xyzs, n, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, stream)) return e;
+    density_mlp_fw_simt_kernel<<<ceil_div(n, 128), 128, 0, st>>>((const __half*)ws.feat, n, pxyz, (__half*)ws.hid, ws.h, sigmas);
+    if (int e = check_launch("density_mlp_fw_simt")) return e;
+    if (with_rgb) {
+        rgb_mlp_fw_simt_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dirs, ws.h, n, (const __half*)params_rgb_f16, rgb_act, (__half*)ws.in32,
+                                                                (__half*)ws.hid1, (__half*)ws.hid2, rgbs);
+        if (int e = check_launch("rgb_mlp_fw_simt")) return e;
+    }
+    return ARN_OK;
+}
+
+extern "C" ARN_API int arn_field_bw_simt(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host, arn_levels_t levels,
+                                 const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
+                                 const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
+                                 float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream) {
+    (void)sigmas;
+    ARN_REQUIRE(n >= 0 && loss_scale > 0, "bad size / loss_scale");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(xyzs && params_xyz_f16 && ws.feat && ws.hid && ws.h && dfeat_scratch && grad_params_xyz, "null pointer");
+    const bool with_rgb = params_rgb_f16 != nullptr && dL_drgbs != nullptr;
+    if (with_rgb) ARN_REQUIRE(ws.in32 && ws.hid1 && ws.hid2 && rgbs && grad_params_rgb, "null pointer (colour branch)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const __half* pxyz = (const __half*)params_xyz_f16;
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    const int smem = (7168 + 3072 + 2 * 128 * 64) * (int)sizeof(__half);  // 53,248 B
+    static bool attr_set = false;
+    if (!attr_set) { ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+    const int64_t n_tiles = (n + 127) / 128;
+    const int grid = (int)min((int64_t)n_sm * 4, n_tiles);
+    field_mlp_bw_simt_kernel<<<grid, 128, smem, st>>>(n, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, ws.h, (const __half*)ws.feat,
+                                                     (const __half*)ws.hid, (const __half*)ws.in32, (const __half*)ws.hid1,
+                                                     (const __half*)ws.hid2, pxyz, with_rgb ? (const __half*)params_rgb_f16 : nullptr,
+                                                     rgb_act, loss_scale, grad_params_xyz, grad_params_rgb, dfeat_scratch);
+    if (int e = check_launch("field_mlp_bw_simt")) return e;
+    return arn_hash_encode_bw(xyzs, n, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
+                              grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, stream);
+}
+
+extern "C" ARN_API int arn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* dst_f16, int64_t n, float lr,
+                             float beta1, float beta2, float eps, int step, float inv_grad_scale, int zero_grad, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0 && step >= 1, "bad size / step");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "null pointer");
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    adam_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (__half*)dst_f16, n, lr, beta1, beta2,
+                                                                  eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad);
+    return check_launch("adam_step");
+}
+
+// Public entry points.  The tensor-core implementation (arn_mlp_tc.cu) takes over once it is parity-green against
+// the simt path; until then both names run the simt kernels.
+extern "C" ARN_API int arn_field_fw(const float* xyzs, const float* dirs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                                    arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act,
+                                    arn_field_ws_t ws, float* sigmas, float* rgbs, arn_stream_t stream) {
+    return arn_field_fw_simt(xyzs, dirs, n, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs, stream);
+}
+extern "C" ARN_API int arn_field_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host, arn_levels_t levels,
+                                    const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
+                                    const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
+                                    float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream) {
+    return arn_field_bw_simt(xyzs, n, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs,
+                             dL_dsigmas, dL_drgbs, loss_scale, dfeat_scratch, grad_params_xyz, grad_params_rgb, dL_dxyzs, stream);
+}

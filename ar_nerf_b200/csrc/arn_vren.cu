@@ -1,0 +1,713 @@
+// libarnerf.so -- kernels replacing the reference's `vren` extension (models/csrc/*.cu), hand-written for sm_100a.
+// Compiled with -fmad=false: every fused multiply-add on a bit-exact path is explicit (arn_march_core.h).
+//
+//   intersection   one thread per ray, fused near clamp for the single-box case used by render()
+//   march (train)  pass 1: one thread per ray counts samples (bit-exact with raymarching.cu:184-234) and records the
+//                  sample parameters t into a caller-provided scratch; a single-CTA scan lays rays out canonically;
+//                  pass 2 is then embarrassingly parallel: one thread per SAMPLE, coalesced stores, no re-march.
+//   march (test)   one thread per alive ray, zero-fills its own padding (no memset launches)
+//   compositing    one warp per ray: multiplicative/additive warp scans, ballot for early termination
+#include "arn_common.cuh"
+#include "arn_march_core.h"
+
+namespace arn {
+
+// ---------------------------------------------------------------------------------------------- intersection
+// intersection.cu:5-22
+__device__ __forceinline__ float2 slab_test(const float* o, const float* inv, const float* c, const float* h) {
+    float t1 = -INFINITY, t2 = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float tmin = __fmul_rn(__fsub_rn(__fsub_rn(c[k], h[k]), o[k]), inv[k]);
+        const float tmax = __fmul_rn(__fsub_rn(__fadd_rn(c[k], h[k]), o[k]), inv[k]);
+        const float a = fminf(tmin, tmax), b = fmaxf(tmin, tmax);
+        t1 = (k == 0) ? a : fmaxf(t1, a);
+        t2 = (k == 0) ? b : fminf(t2, b);
+    }
+    if (t1 > t2) return make_float2(-1.0f, -1.0f);
+    return make_float2(t1, t2);
+}
+
+// intersection.cu:103-121 ; dot() contracted as FMUL x, FFMA y, FFMA z (reference SASS)
+__device__ __forceinline__ float2 sphere_test(const float* o, const float* d, const float* c, float radius) {
+    const float cx = __fsub_rn(o[0], c[0]), cy = __fsub_rn(o[1], c[1]), cz = __fsub_rn(o[2], c[2]);
+    const float a = __fmaf_rn(d[2], d[2], __fmaf_rn(d[1], d[1], __fmul_rn(d[0], d[0])));
+    const float half_b = __fmaf_rn(d[2], cz, __fmaf_rn(d[1], cy, __fmul_rn(d[0], cx)));
+    const float cc = __fmaf_rn(-radius, radius, __fmaf_rn(cz, cz, __fmaf_rn(cy, cy, __fmul_rn(cx, cx))));
+    const float disc = __fmaf_rn(half_b, half_b, -__fmul_rn(a, cc));
+    if (disc < 0) return make_float2(-1.0f, -1.0f);
+    const float sq = __fsqrt_rn(disc);
+    return make_float2(__fdiv_rn(__fsub_rn(-half_b, sq), a), __fdiv_rn(__fadd_rn(-half_b, sq), a));
+}
+
+template <bool SPHERE>
+__global__ void __launch_bounds__(256) intersect_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                        int64_t n_rays, const float* __restrict__ centers,
+                                                        const float* __restrict__ extents, int n_prims, int max_hits,
+                                                        int32_t* __restrict__ hit_cnt, float* __restrict__ hits_t,
+                                                        int64_t* __restrict__ hits_idx) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
+    const float d[3] = {rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]};
+    const float inv[3] = {__fdiv_rn(1.0f, d[0]), __fdiv_rn(1.0f, d[1]), __fdiv_rn(1.0f, d[2])};
+    float* ht = hits_t + r * max_hits * 2;
+    int64_t* hi = hits_idx + r * max_hits;
+    for (int k = 0; k < max_hits; k++) { ht[2 * k] = -1.0f; ht[2 * k + 1] = -1.0f; hi[k] = -1; }
+    int cnt = 0;
+    for (int v = 0; v < n_prims; v++) {
+        const float c[3] = {centers[3 * v], centers[3 * v + 1], centers[3 * v + 2]};
+        float2 tt;
+        if (SPHERE) tt = sphere_test(o, d, c, extents[v]);
+        else { const float h[3] = {extents[3 * v], extents[3 * v + 1], extents[3 * v + 2]}; tt = slab_test(o, inv, c, h); }
+        if (tt.y > 0) {  // intersection.cu:49-55
+            if (cnt < max_hits) { ht[2 * cnt] = fmaxf(tt.x, 0.0f); ht[2 * cnt + 1] = tt.y; hi[cnt] = v; }
+            cnt++;
+        }
+    }
+    hit_cnt[r] = cnt;
+    // near -> far on t1, ascending with the -1 fills (what torch::sort does at intersection.cu:95-97)
+    for (int i = 1; i < max_hits; i++) {
+        const float a0 = ht[2 * i], a1 = ht[2 * i + 1]; const int64_t ai = hi[i];
+        int j = i - 1;
+        while (j >= 0 && ht[2 * j] > a0) { ht[2 * j + 2] = ht[2 * j]; ht[2 * j + 3] = ht[2 * j + 1]; hi[j + 1] = hi[j]; j--; }
+        ht[2 * j + 2] = a0; ht[2 * j + 3] = a1; hi[j + 1] = ai;
+    }
+}
+
+// rendering.py:29-31 fused: single box, max_hits 1, near clamp.
+__global__ void __launch_bounds__(256) aabb_near_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                        int64_t n_rays, float cx, float cy, float cz, float hx, float hy,
+                                                        float hz, float near, float2* __restrict__ hits_t) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
+    const float inv[3] = {__fdiv_rn(1.0f, rays_d[3 * r]), __fdiv_rn(1.0f, rays_d[3 * r + 1]), __fdiv_rn(1.0f, rays_d[3 * r + 2])};
+    const float c[3] = {cx, cy, cz}, h[3] = {hx, hy, hz};
+    const float2 tt = slab_test(o, inv, c, h);
+    float2 out = make_float2(-1.0f, -1.0f);
+    if (tt.y > 0) {
+        out.x = fmaxf(tt.x, 0.0f); out.y = tt.y;
+        if (out.x >= 0 && out.x < near) out.x = near;
+    }
+    hits_t[r] = out;
+}
+
+// ---------------------------------------------------------------------------------------------- grid utilities
+__global__ void __launch_bounds__(256) morton3d_kernel(const int32_t* __restrict__ coords, int64_t n, int32_t* __restrict__ indices) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    indices[i] = (int32_t)arn_morton3d((uint32_t)coords[3 * i], (uint32_t)coords[3 * i + 1], (uint32_t)coords[3 * i + 2]);
+}
+__global__ void __launch_bounds__(256) morton3d_invert_kernel(const int32_t* __restrict__ indices, int64_t n, int32_t* __restrict__ coords) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t ind = indices[i];
+    coords[3 * i + 0] = (int32_t)arn_morton3d_invert((uint32_t)(ind >> 0));
+    coords[3 * i + 1] = (int32_t)arn_morton3d_invert((uint32_t)(ind >> 1));
+    coords[3 * i + 2] = (int32_t)arn_morton3d_invert((uint32_t)(ind >> 2));
+}
+
+// raymarching.cu:122-141.  One thread packs 4 output bytes from 32 consecutive cells (128-bit loads for f32),
+// so a warp reads 4 KB contiguous and writes 128 B contiguous.
+template <typename T>
+__global__ void __launch_bounds__(256) packbits_kernel(const T* __restrict__ grid, float thr, uint8_t* __restrict__ bits, int64_t n_bytes) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // word index (4 bytes)
+    const int64_t b0 = w * 4;
+    if (b0 >= n_bytes) return;
+    uint32_t word = 0;
+    const int nb = (int)min((int64_t)4, n_bytes - b0);
+    for (int b = 0; b < nb; b++) {
+        uint32_t byte = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) byte |= ((float)grid[(b0 + b) * 8 + i] > thr) ? (1u << i) : 0u;
+        word |= byte << (8 * b);
+    }
+    if (nb == 4 && ((uintptr_t)(bits + b0) & 3) == 0) *reinterpret_cast<uint32_t*>(bits + b0) = word;
+    else for (int b = 0; b < nb; b++) bits[b0 + b] = (uint8_t)(word >> (8 * b));
+}
+// double: compared in double precision against (double)thr, as the reference's template does (scalar_t > float)
+__global__ void __launch_bounds__(256) packbits_f64_kernel(const double* __restrict__ grid, float thr, uint8_t* __restrict__ bits, int64_t n_bytes) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_bytes) return;
+    uint32_t byte = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) byte |= (grid[n * 8 + i] > (double)thr) ? (1u << i) : 0u;
+    bits[n] = (uint8_t)byte;
+}
+
+// ---------------------------------------------------------------------------------------------- march (train)
+// Pass 1 (raymarching.cu:184-234).  Counts go to rays_a[r][2]; if t_scratch != nullptr the parameter t of sample i
+// of ray r is recorded at t_scratch[r*max_samples + i] so that pass 2 needs no second march.
+__global__ void __launch_bounds__(128) march_train_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                                const float* __restrict__ hits_t, int64_t n_rays,
+                                                                const uint8_t* __restrict__ bitfield, ArnMarchConsts c,
+                                                                const float* __restrict__ noise, int64_t* __restrict__ rays_a,
+                                                                float* __restrict__ t_scratch) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
+    const float t1 = arn_jitter_start(c, hits_t[2 * r], noise[r]);
+    const float t2 = hits_t[2 * r + 1];
+    float* rec = t_scratch ? t_scratch + r * c.max_samples : nullptr;
+    float t = t1; int N = 0;
+    while (0 <= t && t < t2 && N < c.max_samples) {
+        float x, y, z, dt;
+        if (arn_march_eval(c, ray, bitfield, t, x, y, z, dt)) {
+            if (rec) rec[N] = t;
+            t = __fadd_rn(t, dt); N++;
+        }
+    }
+    rays_a[3 * r + 2] = N;
+}
+
+// Exclusive scan of the counts: rays_a[r] = (r, start, N); counter = (total, n_rays).  Single CTA, chunked.
+__global__ void __launch_bounds__(1024) rays_scan_kernel(int64_t* __restrict__ rays_a, int64_t n_rays, int32_t* __restrict__ counter) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t carry_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_rays; base += blockDim.x) {
+        const int64_t r = base + threadIdx.x;
+        const int64_t v = r < n_rays ? rays_a[3 * r + 2] : 0;
+        int64_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int64_t s = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, s, o); if (lane >= o) s += u; }
+            warp_sums[lane] = s;  // inclusive over warps
+        }
+        __syncthreads();
+        const int64_t carry = carry_s;
+        const int64_t start = carry + (wid ? warp_sums[wid - 1] : 0) + inc - v;
+        if (r < n_rays) { rays_a[3 * r] = r; rays_a[3 * r + 1] = start; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int64_t tot = carry_s;
+        counter[0] = (int32_t)(tot > 0x7fffffff ? 0x7fffffff : tot);
+        counter[1] = (int32_t)(n_rays > 0x7fffffff ? 0x7fffffff : n_rays);
+    }
+}
+
+// Pass 2, parallel form: one thread per sample.  The ray of sample s is found by binary search over the starts.
+__global__ void __launch_bounds__(256) march_train_emit_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                               int64_t n_rays, ArnMarchConsts c, const int64_t* __restrict__ rays_a,
+                                                               const float* __restrict__ t_scratch, int64_t total,
+                                                               float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                               float* __restrict__ deltas, float* __restrict__ ts) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    // largest r with start[r] <= s and N[r] > 0 : starts are non-decreasing, so search the last start <= s
+    int64_t lo = 0, hi = n_rays - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (rays_a[3 * mid + 1] <= s) lo = mid; else hi = mid - 1;
+    }
+    const int64_t r = lo;  // rays with N == 0 share their start with the next ray; "last start <= s" skips them
+    const int i = (int)(s - rays_a[3 * r + 1]);
+    const float t = t_scratch[r * c.max_samples + i];
+    const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    xyzs[3 * s] = __fmaf_rn(dx, t, ox); xyzs[3 * s + 1] = __fmaf_rn(dy, t, oy); xyzs[3 * s + 2] = __fmaf_rn(dz, t, oz);
+    dirs[3 * s] = dx; dirs[3 * s + 1] = dy; dirs[3 * s + 2] = dz;
+    ts[s] = t; deltas[s] = arn_calc_dt(c, t);
+}
+
+// Pass 2, re-march form (raymarching.cu:236-279), used when the caller gives no t scratch.
+__global__ void __launch_bounds__(128) march_train_remarch_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                                  const float* __restrict__ hits_t, int64_t n_rays,
+                                                                  const uint8_t* __restrict__ bitfield, ArnMarchConsts c,
+                                                                  const float* __restrict__ noise, const int64_t* __restrict__ rays_a,
+                                                                  float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                                  float* __restrict__ deltas, float* __restrict__ ts) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
+    const float t1 = arn_jitter_start(c, hits_t[2 * r], noise[r]);
+    const float t2 = hits_t[2 * r + 1];
+    const int64_t start = rays_a[3 * r + 1]; const int N = (int)rays_a[3 * r + 2];
+    float t = t1; int samples = 0;
+    while (t < t2 && samples < N) {
+        float x, y, z, dt;
+        if (arn_march_eval(c, ray, bitfield, t, x, y, z, dt)) {
+            const int64_t s = start + samples;
+            xyzs[3 * s] = x; xyzs[3 * s + 1] = y; xyzs[3 * s + 2] = z;
+            dirs[3 * s] = ray.dx; dirs[3 * s + 1] = ray.dy; dirs[3 * s + 2] = ray.dz;
+            ts[s] = t; deltas[s] = dt;
+            t = __fadd_rn(t, dt); samples++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- march (test)
+// raymarching.cu:335-404
+__global__ void __launch_bounds__(128) march_test_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                         float* __restrict__ hits_t, const int64_t* __restrict__ alive,
+                                                         int64_t n_alive, const uint8_t* __restrict__ bitfield, ArnMarchConsts c,
+                                                         int S, float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                         float* __restrict__ deltas, float* __restrict__ ts, int32_t* __restrict__ n_eff) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int64_t r = alive[n];
+    const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
+    float t = hits_t[2 * r]; const float t2 = hits_t[2 * r + 1];
+    int s = 0;
+    float t_resume = t; bool moved = false;
+    while (t < t2 && s < S) {
+        float x, y, z, dt;
+        if (arn_march_eval(c, ray, bitfield, t, x, y, z, dt)) {
+            const int64_t o = n * S + s;
+            xyzs[3 * o] = x; xyzs[3 * o + 1] = y; xyzs[3 * o + 2] = z;
+            dirs[3 * o] = ray.dx; dirs[3 * o + 1] = ray.dy; dirs[3 * o + 2] = ray.dz;
+            ts[o] = t; deltas[o] = dt;
+            t = __fadd_rn(t, dt);
+            t_resume = t; moved = true;  // raymarching.cu:386: only an occupied step moves the resume point
+            s++;
+        }
+    }
+    if (moved) hits_t[2 * r] = t_resume;
+    n_eff[n] = s;
+    for (int k = s; k < S; k++) {  // zero padding (the reference memsets the whole buffers, :421-426)
+        const int64_t o = n * S + k;
+        xyzs[3 * o] = 0.f; xyzs[3 * o + 1] = 0.f; xyzs[3 * o + 2] = 0.f;
+        dirs[3 * o] = 0.f; dirs[3 * o + 1] = 0.f; dirs[3 * o + 2] = 0.f;
+        ts[o] = 0.f; deltas[o] = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- compositing
+// alpha = 1 - __expf(-sigma*delta): SASS of the reference is FMUL s*d ; FMUL -1.44269502 ; MUFU.EX2 (volumerendering.cu:27)
+__device__ __forceinline__ float alpha_of(float sigma, float delta) {
+    return __fsub_rn(1.0f, __expf(-sigma * delta));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_incl_sum(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(kFull, v, o); if (lane >= o) v += u; }
+    return v;
+}
+__device__ __forceinline__ float warp_incl_prod(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(kFull, v, o); if (lane >= o) v *= u; }
+    return v;
+}
+
+// volumerendering.cu:5-44, one warp per rays_a row.
+__global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                 const float* __restrict__ deltas, const float* __restrict__ ts,
+                                                                 const int64_t* __restrict__ rays_a, int64_t n_rays, float T_thr,
+                                                                 int64_t* __restrict__ total_samples, float* __restrict__ opacity,
+                                                                 float* __restrict__ depth, float* __restrict__ rgb, float* __restrict__ ws) {
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= n_rays) return;
+    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1]; const int N = (int)rays_a[3 * n + 2];
+    float T = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
+    int64_t samples = N; bool done = false;
+    int base = 0;
+    for (; base < N && !done; base += 32) {
+        const int i = base + lane; const bool in = i < N; const int64_t s = start + i;
+        const float a = in ? alpha_of(sigmas[s], deltas[s]) : 0.0f;
+        const float incl = warp_incl_prod(__fsub_rn(1.0f, a), lane);
+        float excl = __shfl_up_sync(kFull, incl, 1); if (lane == 0) excl = 1.0f;
+        const float T_before = T * excl, T_after = T * incl;
+        const unsigned term = __ballot_sync(kFull, in && (T_after <= T_thr));
+        const int last = term ? __ffs(term) - 1 : 31;  // the terminating sample still contributes (:37-40)
+        const bool use = in && lane <= last;
+        const float w = use ? a * T_before : 0.0f;
+        if (in) ws[s] = w;
+        float cr = 0.f, cg = 0.f, cb = 0.f, ct = 0.f;
+        if (use) { cr = rgbs[3 * s]; cg = rgbs[3 * s + 1]; cb = rgbs[3 * s + 2]; ct = ts[s]; }
+        acc_r += warp_sum(w * cr); acc_g += warp_sum(w * cg); acc_b += warp_sum(w * cb);
+        acc_d += warp_sum(w * ct); acc_o += warp_sum(w);
+        if (term) { done = true; samples = base + last; }  // break happens before samples++ (:40-41)
+        T = __shfl_sync(kFull, T_after, 31);
+    }
+    for (int i = base + lane; i < N; i += 32) ws[start + i] = 0.0f;  // after termination (reference: zero-init, :59)
+    if (lane == 0) {
+        opacity[ray_idx] = acc_o; depth[ray_idx] = acc_d;
+        rgb[3 * ray_idx] = acc_r; rgb[3 * ray_idx + 1] = acc_g; rgb[3 * ray_idx + 2] = acc_b;
+        total_samples[ray_idx] = samples;
+    }
+}
+
+// volumerendering.cu:86-150, one warp per row.  The reference's in-kernel serial thrust scan of dL_dws*ws (:118-121)
+// becomes a warp reduction (total) plus a running warp scan.
+__global__ void __launch_bounds__(256) composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __restrict__ dL_ddepth,
+                                                                 const float* __restrict__ dL_drgb, const float* __restrict__ dL_dws,
+                                                                 const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                 const float* __restrict__ ws, const float* __restrict__ deltas,
+                                                                 const float* __restrict__ ts, const int64_t* __restrict__ rays_a,
+                                                                 const float* __restrict__ opacity, const float* __restrict__ depth,
+                                                                 const float* __restrict__ rgb, int64_t n_rays, float T_thr,
+                                                                 float* __restrict__ dL_dsigmas, float* __restrict__ dL_drgbs) {
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= n_rays) return;
+    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1]; const int N = (int)rays_a[3 * n + 2];
+    if (N <= 0) return;
+    const float R = rgb[3 * ray_idx], G = rgb[3 * ray_idx + 1], B = rgb[3 * ray_idx + 2];
+    const float O = opacity[ray_idx], D = depth[ray_idx];
+    const float gR = dL_drgb[3 * ray_idx], gG = dL_drgb[3 * ray_idx + 1], gB = dL_drgb[3 * ray_idx + 2];
+    const float gO = dL_dopacity[ray_idx], gD = dL_ddepth[ray_idx];
+    float ww_total = 0.0f;
+    if (dL_dws) {
+        float p = 0.0f;
+        for (int i = lane; i < N; i += 32) p += dL_dws[start + i] * ws[start + i];
+        ww_total = warp_sum(p);
+    }
+    float T = 1.0f, r = 0.f, g = 0.f, b = 0.f, d = 0.f, ww = 0.f;
+    bool done = false; int base = 0;
+    for (; base < N && !done; base += 32) {
+        const int i = base + lane; const bool in = i < N; const int64_t s = start + i;
+        float sg = 0.f, dl = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, ct = 0.f, gw = 0.f, wsv = 0.f;
+        if (in) {
+            sg = sigmas[s]; dl = deltas[s]; cr = rgbs[3 * s]; cg = rgbs[3 * s + 1]; cb = rgbs[3 * s + 2]; ct = ts[s];
+            if (dL_dws) { gw = dL_dws[s]; wsv = ws[s]; }
+        }
+        const float a = in ? alpha_of(sg, dl) : 0.0f;
+        const float incl = warp_incl_prod(__fsub_rn(1.0f, a), lane);
+        float excl = __shfl_up_sync(kFull, incl, 1); if (lane == 0) excl = 1.0f;
+        const float T_before = T * excl, T_after = T * incl;
+        const unsigned term = __ballot_sync(kFull, in && (T_after <= T_thr));
+        const int last = term ? __ffs(term) - 1 : 31;
+        const bool use = in && lane <= last;
+        const float w = use ? a * T_before : 0.0f;
+        const float pr = r + warp_incl_sum(w * cr, lane), pg = g + warp_incl_sum(w * cg, lane);
+        const float pb = b + warp_incl_sum(w * cb, lane), pd = d + warp_incl_sum(w * ct, lane);
+        const float pww = ww + warp_incl_sum(gw * wsv, lane);
+        if (in) {
+            float o_r = 0.f, o_g = 0.f, o_b = 0.f, o_s = 0.f;
+            if (use) {
+                o_r = gR * w; o_g = gG * w; o_b = gB * w;
+                o_s = dl * (gR * (cr * T_after - (R - pr)) + gG * (cg * T_after - (G - pg)) + gB * (cb * T_after - (B - pb)) +
+                            gO * (1.0f - O) + gD * (ct * T_after - (D - pd)) + T_after * gw - (ww_total - pww));
+            }
+            dL_drgbs[3 * s] = o_r; dL_drgbs[3 * s + 1] = o_g; dL_drgbs[3 * s + 2] = o_b;
+            dL_dsigmas[s] = o_s;
+        }
+        if (term) done = true;
+        T = __shfl_sync(kFull, T_after, 31);
+        r = __shfl_sync(kFull, pr, 31); g = __shfl_sync(kFull, pg, 31); b = __shfl_sync(kFull, pb, 31);
+        d = __shfl_sync(kFull, pd, 31); ww = __shfl_sync(kFull, pww, 31);
+    }
+    for (int i = base + lane; i < N; i += 32) {  // zero-init in the reference (:171-172)
+        const int64_t s = start + i;
+        dL_drgbs[3 * s] = 0.f; dL_drgbs[3 * s + 1] = 0.f; dL_drgbs[3 * s + 2] = 0.f; dL_dsigmas[s] = 0.f;
+    }
+}
+
+// volumerendering.cu:204-248.  Chunks are short (S <= 64, usually 1..8): one thread per alive ray, registers for the
+// running sums, one read-modify-write of the per-ray outputs at the end.
+__global__ void __launch_bounds__(256) composite_test_fw_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                const float* __restrict__ deltas, const float* __restrict__ ts,
+                                                                int64_t* __restrict__ alive, int64_t n_alive, int S, float T_thr,
+                                                                const int32_t* __restrict__ n_eff, float* __restrict__ opacity,
+                                                                float* __restrict__ depth, float* __restrict__ rgb) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int ne = n_eff[n];
+    if (ne == 0) { alive[n] = -1; return; }
+    const int64_t r = alive[n];
+    float O = opacity[r];
+    float T = __fsub_rn(1.0f, O);
+    float cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2], D = depth[r];
+    for (int s = 0; s < ne; s++) {
+        const int64_t o = n * S + s;
+        const float a = alpha_of(sigmas[o], deltas[o]);
+        const float w = __fmul_rn(a, T);
+        cr = __fmaf_rn(w, rgbs[3 * o], cr); cg = __fmaf_rn(w, rgbs[3 * o + 1], cg); cb = __fmaf_rn(w, rgbs[3 * o + 2], cb);
+        D = __fmaf_rn(w, ts[o], D);
+        O = __fadd_rn(O, w);
+        T = __fmul_rn(T, __fsub_rn(1.0f, a));
+        if (T <= T_thr) { alive[n] = -1; break; }
+    }
+    opacity[r] = O; depth[r] = D; rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+}
+
+// ---------------------------------------------------------------------------------------------- distortion loss
+// losses.cu:7-59,62-107: one warp per row; inclusive scans kept for the backward, loss reduced in the same pass.
+__global__ void __launch_bounds__(256) distortion_fw_kernel(const float* __restrict__ ws, const float* __restrict__ deltas,
+                                                            const float* __restrict__ ts, const int64_t* __restrict__ rays_a,
+                                                            int64_t n_rays, float* __restrict__ loss, float* __restrict__ wsi,
+                                                            float* __restrict__ wtsi) {
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= n_rays) return;
+    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1]; const int N = (int)rays_a[3 * n + 2];
+    float cw = 0.f, cwt = 0.f, acc = 0.f;
+    for (int base = 0; base < N; base += 32) {
+        const int i = base + lane; const bool in = i < N; const int64_t s = start + i;
+        const float w = in ? ws[s] : 0.f, t = in ? ts[s] : 0.f, dl = in ? deltas[s] : 0.f;
+        const float wt = w * t;
+        const float wi = cw + warp_incl_sum(w, lane), wti = cwt + warp_incl_sum(wt, lane);
+        const float we = wi - w, wte = wti - wt;
+        if (in) { wsi[s] = wi; wtsi[s] = wti; }
+        acc += in ? (2.0f * (wti * we - wi * wte) + (1.0f / 3.0f) * w * w * dl) : 0.f;
+        cw = __shfl_sync(kFull, wi, 31); cwt = __shfl_sync(kFull, wti, 31);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) loss[ray_idx] = acc;
+}
+
+// losses.cu:110-140 -- every sample is independent given the scans: one thread per sample of a row's segment.
+__global__ void __launch_bounds__(256) distortion_bw_kernel(const float* __restrict__ dL_dloss, const float* __restrict__ wsi,
+                                                            const float* __restrict__ wtsi, const float* __restrict__ ws,
+                                                            const float* __restrict__ deltas, const float* __restrict__ ts,
+                                                            const int64_t* __restrict__ rays_a, int64_t n_rays, float* __restrict__ dL_dws) {
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= n_rays) return;
+    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1]; const int N = (int)rays_a[3 * n + 2];
+    if (N <= 0) return;
+    const int64_t end = start + N - 1;
+    const float ws_sum = wsi[end], wts_sum = wtsi[end], gl = dL_dloss[ray_idx];
+    for (int64_t s = start + lane; s <= end; s += 32) {
+        float v = gl * 2.0f * ((s == start ? 0.0f : (ts[s] * wsi[s - 1] - wtsi[s - 1])) +
+                               (wts_sum - wtsi[s] - ts[s] * (ws_sum - wsi[s])));
+        v += gl * (2.0f / 3.0f) * ws[s] * deltas[s];
+        dL_dws[s] = v;
+    }
+}
+
+// custom_functions.py:104-112 (torch_scatter.segment_csr): one warp per row.
+__global__ void __launch_bounds__(256) march_train_bw_kernel(const float* __restrict__ dL_dxyzs, const float* __restrict__ dL_ddirs,
+                                                             const float* __restrict__ ts, const int64_t* __restrict__ rays_a,
+                                                             int64_t n_rays, float* __restrict__ dL_do, float* __restrict__ dL_dd) {
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= n_rays) return;
+    const int64_t start = rays_a[3 * n + 1]; const int N = (int)rays_a[3 * n + 2];
+    float o[3] = {0, 0, 0}, d[3] = {0, 0, 0};
+    for (int i = lane; i < N; i += 32) {
+        const int64_t s = start + i; const float t = ts[s];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float gx = dL_dxyzs[3 * s + k];
+            o[k] += gx; d[k] += gx * t + (dL_ddirs ? dL_ddirs[3 * s + k] : 0.0f);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { o[k] = warp_sum(o[k]); d[k] = warp_sum(d[k]); }
+    if (lane == 0) {
+        for (int k = 0; k < 3; k++) { dL_do[3 * n + k] = o[k]; dL_dd[3 * n + k] = d[k]; }  // segment_csr is by row
+    }
+}
+
+}  // namespace arn
+
+using namespace arn;
+
+// ================================================================================================ C ABI
+extern "C" ARN_API int arn_ray_aabb_intersect(const float* rays_o, const float* rays_d, int64_t n_rays, const float* centers,
+                                      const float* half_sizes, int n_voxels, int max_hits, int32_t* hit_cnt, float* hits_t,
+                                      int64_t* hits_idx, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0 && n_voxels >= 0 && max_hits >= 1, "bad sizes");
+    if (n_rays == 0) return ARN_OK;
+    ARN_REQUIRE(rays_o && rays_d && centers && half_sizes && hit_cnt && hits_t && hits_idx, "null pointer");
+    intersect_kernel<false><<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, centers, half_sizes,
+                                                                                    n_voxels, max_hits, hit_cnt, hits_t, hits_idx);
+    return check_launch("ray_aabb_intersect");
+}
+
+extern "C" ARN_API int arn_ray_sphere_intersect(const float* rays_o, const float* rays_d, int64_t n_rays, const float* centers,
+                                        const float* radii, int n_spheres, int max_hits, int32_t* hit_cnt, float* hits_t,
+                                        int64_t* hits_idx, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0 && n_spheres >= 0 && max_hits >= 1, "bad sizes");
+    if (n_rays == 0) return ARN_OK;
+    ARN_REQUIRE(rays_o && rays_d && centers && radii && hit_cnt && hits_t && hits_idx, "null pointer");
+    intersect_kernel<true><<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, centers, radii,
+                                                                                   n_spheres, max_hits, hit_cnt, hits_t, hits_idx);
+    return check_launch("ray_sphere_intersect");
+}
+
+extern "C" ARN_API int arn_ray_aabb_near(const float* rays_o, const float* rays_d, int64_t n_rays, const float* center_host,
+                                 const float* half_size_host, float near, float* hits_t, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0, "bad sizes");
+    if (n_rays == 0) return ARN_OK;
+    ARN_REQUIRE(rays_o && rays_d && center_host && half_size_host && hits_t, "null pointer");
+    float ch[6];  // the box is 24 bytes of module state: passed from the host so it travels as kernel arguments
+    for (int k = 0; k < 3; k++) { ch[k] = center_host[k]; ch[3 + k] = half_size_host[k]; }
+    aabb_near_kernel<<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, ch[0], ch[1], ch[2], ch[3],
+                                                                            ch[4], ch[5], near, reinterpret_cast<float2*>(hits_t));
+    return check_launch("ray_aabb_near");
+}
+
+extern "C" ARN_API int arn_morton3d(const int32_t* coords, int64_t n, int32_t* indices, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(coords && indices, "null pointer");
+    morton3d_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(coords, n, indices);
+    return check_launch("morton3d");
+}
+extern "C" ARN_API int arn_morton3d_invert(const int32_t* indices, int64_t n, int32_t* coords, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(coords && indices, "null pointer");
+    morton3d_invert_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(indices, n, coords);
+    return check_launch("morton3d_invert");
+}
+extern "C" ARN_API int arn_packbits(const void* density_grid, int grid_dtype, float threshold, uint8_t* density_bitfield,
+                            int64_t n_bytes, arn_stream_t stream) {
+    ARN_REQUIRE(n_bytes >= 0, "bad size");
+    if (n_bytes == 0) return ARN_OK;
+    ARN_REQUIRE(density_grid && density_bitfield, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t words = (n_bytes + 3) / 4;
+    if (grid_dtype == 0) packbits_kernel<float><<<ceil_div(words, 256), 256, 0, st>>>((const float*)density_grid, threshold, density_bitfield, n_bytes);
+    else if (grid_dtype == 1) packbits_kernel<__half><<<ceil_div(words, 256), 256, 0, st>>>((const __half*)density_grid, threshold, density_bitfield, n_bytes);
+    else if (grid_dtype == 2) packbits_f64_kernel<<<ceil_div(n_bytes, 256), 256, 0, st>>>((const double*)density_grid, threshold, density_bitfield, n_bytes);
+    else { set_error("arn_packbits: grid_dtype must be 0 (f32), 1 (f16) or 2 (f64)"); return ARN_E_INVALID; }
+    return check_launch("packbits");
+}
+
+static int check_march_cfg(int cascades, int grid_size, int max_samples) {
+    if (cascades < 1 || cascades > 16) { set_error("march: cascades out of range [1,16]"); return ARN_E_INVALID; }
+    if (grid_size < 1 || grid_size > 1024) { set_error("march: grid_size out of range [1,1024]"); return ARN_E_INVALID; }
+    if (max_samples < 1) { set_error("march: max_samples must be >= 1"); return ARN_E_INVALID; }
+    return ARN_OK;
+}
+
+// t_scratch is carried through a second entry point so the published signature stays the reference's argument list.
+extern "C" ARN_API int arn_march_train_count_ex(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                                        const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                                        float exp_step_factor, const float* noise, int max_samples, int64_t* rays_a,
+                                        int32_t* counter, float* t_scratch, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0, "bad size");
+    ARN_REQUIRE(counter, "null counter");
+    if (int e = check_march_cfg(cascades, grid_size, max_samples)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rays == 0) { ARN_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int32_t), st)); return ARN_OK; }
+    ARN_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && noise && rays_a, "null pointer");
+    const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
+    march_train_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch);
+    if (int e = check_launch("march_train_count")) return e;
+    rays_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, counter);
+    return check_launch("rays_scan");
+}
+extern "C" ARN_API int arn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                                     const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                                     float exp_step_factor, const float* noise, int max_samples, int64_t* rays_a,
+                                     int32_t* counter, arn_stream_t stream) {
+    return arn_march_train_count_ex(rays_o, rays_d, hits_t, n_rays, density_bitfield, cascades, grid_size, scale,
+                                    exp_step_factor, noise, max_samples, rays_a, counter, nullptr, stream);
+}
+
+extern "C" ARN_API int arn_march_train_emit_ex(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                                       const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                                       float exp_step_factor, const float* noise, int max_samples, const int64_t* rays_a,
+                                       const float* t_scratch, float* xyzs, float* dirs, float* deltas, float* ts,
+                                       int64_t capacity, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0 && capacity >= 0, "bad size");
+    if (int e = check_march_cfg(cascades, grid_size, max_samples)) return e;
+    if (n_rays == 0 || capacity == 0) return ARN_OK;
+    ARN_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && noise && rays_a && xyzs && dirs && deltas && ts, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
+    if (t_scratch) {
+        march_train_emit_kernel<<<ceil_div(capacity, 256), 256, 0, st>>>(rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, xyzs, dirs, deltas, ts);
+        return check_launch("march_train_emit");
+    }
+    march_train_remarch_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, xyzs, dirs, deltas, ts);
+    return check_launch("march_train_remarch");
+}
+extern "C" ARN_API int arn_march_train_emit(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                                    const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                                    float exp_step_factor, const float* noise, int max_samples, const int64_t* rays_a,
+                                    float* xyzs, float* dirs, float* deltas, float* ts, int64_t capacity, arn_stream_t stream) {
+    return arn_march_train_emit_ex(rays_o, rays_d, hits_t, n_rays, density_bitfield, cascades, grid_size, scale, exp_step_factor,
+                                   noise, max_samples, rays_a, nullptr, xyzs, dirs, deltas, ts, capacity, stream);
+}
+
+extern "C" ARN_API int arn_march_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_indices,
+                              int64_t n_alive, const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                              float exp_step_factor, int n_samples, int max_samples, float* xyzs, float* dirs, float* deltas,
+                              float* ts, int32_t* n_eff_samples, arn_stream_t stream) {
+    ARN_REQUIRE(n_alive >= 0 && n_samples >= 1, "bad size");
+    if (int e = check_march_cfg(cascades, grid_size, max_samples)) return e;
+    if (n_alive == 0) return ARN_OK;
+    ARN_REQUIRE(rays_o && rays_d && hits_t && alive_indices && density_bitfield && xyzs && dirs && deltas && ts && n_eff_samples, "null pointer");
+    // raymarching.cu:370,399: the test kernel passes `cascades` where calc_dt expects `scale`
+    const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, (float)cascades, exp_step_factor, max_samples);
+    march_test_kernel<<<ceil_div(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, alive_indices, n_alive,
+                                                                              density_bitfield, c, n_samples, xyzs, dirs, deltas, ts, n_eff_samples);
+    return check_launch("march_test");
+}
+
+extern "C" ARN_API int arn_composite_train_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                                      const int64_t* rays_a, int64_t n_rays, int64_t n_samples, float T_threshold,
+                                      int64_t* total_samples, float* opacity, float* depth, float* rgb, float* ws, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0 && n_samples >= 0, "bad size");
+    if (n_rays == 0) return ARN_OK;
+    ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "null pointer");
+    ARN_REQUIRE(n_samples == 0 || (sigmas && rgbs && deltas && ts && ws), "null pointer");
+    composite_train_fw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
+                                                                                          total_samples, opacity, depth, rgb, ws);
+    return check_launch("composite_train_fw");
+}
+
+extern "C" ARN_API int arn_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drgb, const float* dL_dws,
+                                      const float* sigmas, const float* rgbs, const float* ws, const float* deltas, const float* ts,
+                                      const int64_t* rays_a, const float* opacity, const float* depth, const float* rgb,
+                                      int64_t n_rays, int64_t n_samples, float T_threshold, float* dL_dsigmas, float* dL_drgbs,
+                                      arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0 && n_samples >= 0, "bad size");
+    if (n_rays == 0 || n_samples == 0) return ARN_OK;
+    ARN_REQUIRE(dL_dopacity && dL_ddepth && dL_drgb && sigmas && rgbs && ws && deltas && ts && rays_a && opacity && depth && rgb && dL_dsigmas && dL_drgbs,
+                "null pointer");
+    composite_train_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws,
+                                                                                          deltas, ts, rays_a, opacity, depth, rgb, n_rays,
+                                                                                          T_threshold, dL_dsigmas, dL_drgbs);
+    return check_launch("composite_train_bw");
+}
+
+extern "C" ARN_API int arn_composite_test_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                                     int64_t* alive_indices, int64_t n_alive, int n_samples, float T_threshold,
+                                     const int32_t* n_eff_samples, float* opacity, float* depth, float* rgb, arn_stream_t stream) {
+    ARN_REQUIRE(n_alive >= 0 && n_samples >= 1, "bad size");
+    if (n_alive == 0) return ARN_OK;
+    ARN_REQUIRE(sigmas && rgbs && deltas && ts && alive_indices && n_eff_samples && opacity && depth && rgb, "null pointer");
+    composite_test_fw_kernel<<<ceil_div(n_alive, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, alive_indices, n_alive, n_samples,
+                                                                                     T_threshold, n_eff_samples, opacity, depth, rgb);
+    return check_launch("composite_test_fw");
+}
+
+extern "C" ARN_API int arn_distortion_fw(const float* ws, const float* deltas, const float* ts, const int64_t* rays_a, int64_t n_rays,
+                                 int64_t n_samples, float* loss, float* ws_inclusive_scan, float* wts_inclusive_scan, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0 && n_samples >= 0, "bad size");
+    if (n_rays == 0) return ARN_OK;
+    ARN_REQUIRE(rays_a && loss, "null pointer");
+    ARN_REQUIRE(n_samples == 0 || (ws && deltas && ts && ws_inclusive_scan && wts_inclusive_scan), "null pointer");
+    distortion_fw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(ws, deltas, ts, rays_a, n_rays, loss, ws_inclusive_scan, wts_inclusive_scan);
+    return check_launch("distortion_fw");
+}
+extern "C" ARN_API int arn_distortion_bw(const float* dL_dloss, const float* ws_inclusive_scan, const float* wts_inclusive_scan, const float* ws,
+                                 const float* deltas, const float* ts, const int64_t* rays_a, int64_t n_rays, int64_t n_samples,
+                                 float* dL_dws, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0 && n_samples >= 0, "bad size");
+    if (n_rays == 0 || n_samples == 0) return ARN_OK;
+    ARN_REQUIRE(dL_dloss && ws_inclusive_scan && wts_inclusive_scan && ws && deltas && ts && rays_a && dL_dws, "null pointer");
+    distortion_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dloss, ws_inclusive_scan, wts_inclusive_scan, ws, deltas, ts,
+                                                                                     rays_a, n_rays, dL_dws);
+    return check_launch("distortion_bw");
+}
+extern "C" ARN_API int arn_march_train_bw(const float* dL_dxyzs, const float* dL_ddirs, const float* ts, const int64_t* rays_a, int64_t n_rays,
+                                  float* dL_drays_o, float* dL_drays_d, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0, "bad size");
+    if (n_rays == 0) return ARN_OK;
+    ARN_REQUIRE(dL_dxyzs && ts && rays_a && dL_drays_o && dL_drays_d, "null pointer");
+    march_train_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dxyzs, dL_ddirs, ts, rays_a, n_rays, dL_drays_o, dL_drays_d);
+    return check_launch("march_train_bw");
+}

@@ -1,0 +1,192 @@
+"""NGP field of the reference (models/networks.py:12-281): same constructor, attributes, buffers, state-dict keys and
+methods, evaluated by libarnerf.so (no tinycudann)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+from einops import rearrange
+from torch import nn
+
+from . import vren
+from .custom_functions import TruncExp
+from .field import Encoding, FieldFunction, FieldState, HashGeometry, Network, NetworkWithInputEncoding
+
+NEAR_DISTANCE = 0.01  # models/rendering.py:10 (imported from there by the reference; defined here to avoid the cycle)
+
+
+class _Tonemapper(nn.Module):
+    """tcnn.Network 1 -> 64 (ReLU) -> 1, Sigmoid (networks.py:80-93, HDR-NeRF mode only).  Secondary branch of the
+    reference, kept as plain torch ops; params follow tiny-cuda-nn's layout (input padded to 16)."""
+
+    def __init__(self, seed):
+        super().__init__()
+        gen = torch.Generator().manual_seed(seed)
+        bound1, bound2 = (6.0 / (16 + 64)) ** 0.5, (6.0 / (64 + 16)) ** 0.5
+        p = torch.cat([(torch.rand(64 * 16, generator=gen) * 2 - 1) * bound1, (torch.rand(16 * 64, generator=gen) * 2 - 1) * bound2])
+        self.params = nn.Parameter(p)
+
+    def forward(self, x):
+        w1 = self.params[:1024].view(64, 16).half().float(); w2 = self.params[1024:].view(16, 64).half().float()
+        hid = torch.relu(x.float() @ w1[:, :1].T).half().float()
+        return torch.sigmoid(hid @ w2[:1].T)
+
+
+class NGP(nn.Module):
+    def __init__(self, scale, rgb_act='Sigmoid', use_raw_HDR=False):
+        super().__init__()
+        self.rgb_act = rgb_act
+        self.use_raw_HDR = use_raw_HDR
+
+        # scene bounding box (networks.py:19-24)
+        self.scale = scale
+        self.register_buffer('center', torch.zeros(1, 3))
+        self.register_buffer('xyz_min', -torch.ones(1, 3) * scale)
+        self.register_buffer('xyz_max', torch.ones(1, 3) * scale)
+        self.register_buffer('half_size', (self.xyz_max - self.xyz_min) / 2)
+
+        # each density grid covers [-2^(k-1), 2^(k-1)]^3 for k in [0, C-1] (networks.py:26-30)
+        self.cascades = max(1 + int(np.ceil(np.log2(2 * scale))), 1)
+        self.grid_size = 128
+        self.register_buffer('density_bitfield', torch.zeros(self.cascades * self.grid_size ** 3 // 8, dtype=torch.uint8))
+
+        # networks.py:33-35
+        L = 16; Fdim = 2; log2_T = 19; N_min = 16
+        b = np.exp(np.log(2048 * scale / N_min) / (L - 1))
+        print(f'GridEncoding: Nmin={N_min} b={b:.5f} F={Fdim} T=2^{log2_T} L={L}')
+
+        self.geometry = HashGeometry(L, N_min, float(np.float32(b)), log2_T)
+        self.xyz_encoder = NetworkWithInputEncoding(self.geometry)
+        self.dir_encoder = Encoding()
+        self.rgb_net = Network()
+        self.field_state = FieldState(self.geometry, self.xyz_min[0].tolist(), self.xyz_max[0].tolist(), rgb_act)
+        self.field_impl = ""  # "" = production kernels, "_simt" = CUDA-core cross-check path (tests)
+
+        if self.rgb_act == 'None' and not self.use_raw_HDR:  # rgb_net output is log-radiance (networks.py:80-93)
+            for i in range(3):
+                setattr(self, f'tonemapper_net_{i}', _Tonemapper(4242 + i))
+
+    # -------------------------------------------------------------------------------------------- host copies
+    def host_box(self):
+        """(center, half_size) of the single scene box as python floats, cached (no device sync per render call)."""
+        key = (self.center._version, self.half_size._version, self.center.data_ptr())
+        if getattr(self, '_host_box_key', None) != key:
+            self._host_box = (self.center[0].tolist(), self.half_size[0].tolist())
+            self._host_box_key = key
+            self.field_state.set_box(self.xyz_min[0].tolist(), self.xyz_max[0].tolist())
+        return self._host_box
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._host_box_key = None
+
+    # -------------------------------------------------------------------------------------------- field
+    def density(self, x, return_feat=False):
+        """networks.py:95-108.  x (N,3) in [-scale, scale] -> sigmas (N) [, h (N,16)]."""
+        self.host_box()
+        sigmas, _, h = FieldFunction.apply(x, None, self.xyz_encoder.params, None, self.field_state, self.field_impl)
+        if return_feat:
+            return sigmas, h
+        return sigmas
+
+    def log_radiance_to_rgb(self, log_radiances, **kwargs):
+        """networks.py:110-131."""
+        log_exposure = torch.log(kwargs['exposure']) if 'exposure' in kwargs else 0
+        out = []
+        for i in range(3):
+            inp = log_radiances[:, i:i + 1] + log_exposure
+            out += [getattr(self, f'tonemapper_net_{i}')(inp)]
+        return torch.cat(out, 1)
+
+    def forward(self, x, d, **kwargs):
+        """networks.py:133-165.  x (N,3), d (N,3) -> sigmas (N), rgbs (N,3)."""
+        self.host_box()
+        sigmas, rgbs, _ = FieldFunction.apply(x, d, self.xyz_encoder.params, self.rgb_net.params, self.field_state,
+                                              self.field_impl)
+        if self.use_raw_HDR:
+            rgbs = F.leaky_relu(rgbs) if not kwargs.get('output_radiance', False) else torch.relu(rgbs)
+        elif self.rgb_act == 'None':
+            if kwargs.get('output_radiance', False):
+                rgbs = TruncExp.apply(torch.clamp(rgbs, 0, 20))
+            else:
+                rgbs = self.log_radiance_to_rgb(rgbs, **kwargs)
+        return sigmas, rgbs
+
+    # -------------------------------------------------------------------------------------------- occupancy grid
+    def init_density_grid(self):
+        """Registers `density_grid` (C,G^3) and `grid_coords` (G^3,3) exactly as train.py:79-82 does on the model."""
+        G = self.grid_size
+        dev = self.density_bitfield.device
+        if not hasattr(self, 'density_grid'):
+            self.register_buffer('density_grid', torch.zeros(self.cascades, G ** 3, device=dev))
+        if not hasattr(self, 'grid_coords'):
+            r = torch.arange(G, dtype=torch.int32, device=dev)
+            zz, yy, xx = torch.meshgrid(r, r, r, indexing='ij')
+            self.register_buffer('grid_coords', torch.stack([xx, yy, zz], -1).reshape(-1, 3).contiguous())
+
+    @torch.no_grad()
+    def get_all_cells(self):
+        """networks.py:167-179."""
+        indices = vren.morton3D(self.grid_coords).long()
+        return [(indices, self.grid_coords)] * self.cascades
+
+    @torch.no_grad()
+    def sample_uniform_and_occupied_cells(self, M, density_threshold):
+        """networks.py:181-207 (same torch RNG calls in the same order)."""
+        cells = []
+        for c in range(self.cascades):
+            coords1 = torch.randint(self.grid_size, (M, 3), dtype=torch.int32, device=self.density_grid.device)
+            indices1 = vren.morton3D(coords1).long()
+            indices2 = torch.nonzero(self.density_grid[c] > density_threshold)[:, 0]
+            if len(indices2) > 0:
+                rand_idx = torch.randint(len(indices2), (M,), device=self.density_grid.device)
+                indices2 = indices2[rand_idx]
+            coords2 = vren.morton3D_invert(indices2.int())
+            cells += [(torch.cat([indices1, indices2]), torch.cat([coords1, coords2]))]
+        return cells
+
+    @torch.no_grad()
+    def mark_invisible_cells(self, K, poses, img_wh, chunk=64 ** 3):
+        """networks.py:209-250."""
+        N_cams = poses.shape[0]
+        self.count_grid = torch.zeros_like(self.density_grid)
+        w2c_R = rearrange(poses[:, :3, :3], 'n a b -> n b a')
+        w2c_T = -w2c_R @ poses[:, :3, 3:]
+        cells = self.get_all_cells()
+        for c in range(self.cascades):
+            indices, coords = cells[c]
+            for i in range(0, len(indices), chunk):
+                xyzs = coords[i:i + chunk] / (self.grid_size - 1) * 2 - 1
+                s = min(2 ** (c - 1), self.scale)
+                half_grid_size = s / self.grid_size
+                xyzs_w = (xyzs * (s - half_grid_size)).T
+                xyzs_c = w2c_R @ xyzs_w + w2c_T
+                uvd = K @ xyzs_c
+                uv = uvd[:, :2] / uvd[:, 2:]
+                in_image = (uvd[:, 2] >= 0) & (uv[:, 0] >= 0) & (uv[:, 0] < img_wh[0]) & (uv[:, 1] >= 0) & (uv[:, 1] < img_wh[1])
+                covered_by_cam = (uvd[:, 2] >= NEAR_DISTANCE) & in_image
+                self.count_grid[c, indices[i:i + chunk]] = count = covered_by_cam.sum(0) / N_cams
+                too_near_to_cam = (uvd[:, 2] < NEAR_DISTANCE) & in_image
+                too_near_to_any_cam = too_near_to_cam.any(0)
+                valid_mask = (count > 0) & (~too_near_to_any_cam)
+                self.density_grid[c, indices[i:i + chunk]] = torch.where(valid_mask, 0., -1.)
+
+    @torch.no_grad()
+    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):
+        """networks.py:252-281."""
+        density_grid_tmp = torch.zeros_like(self.density_grid)
+        if warmup:
+            cells = self.get_all_cells()
+        else:
+            cells = self.sample_uniform_and_occupied_cells(self.grid_size ** 3 // 4, density_threshold)
+        for c in range(self.cascades):
+            indices, coords = cells[c]
+            s = min(2 ** (c - 1), self.scale)
+            half_grid_size = s / self.grid_size
+            xyzs_w = (coords / (self.grid_size - 1) * 2 - 1) * (s - half_grid_size)
+            xyzs_w += (torch.rand_like(xyzs_w) * 2 - 1) * half_grid_size
+            density_grid_tmp[c, indices] = self.density(xyzs_w)
+        if erode:
+            decay = torch.clamp(decay ** (1 / self.count_grid), 0.1, 0.95)
+        self.density_grid = torch.where(self.density_grid < 0, self.density_grid,
+                                        torch.maximum(self.density_grid * decay, density_grid_tmp))
+        mean_density = self.density_grid[self.density_grid > 0].mean().item()
+        vren.packbits(self.density_grid, min(mean_density, density_threshold), self.density_bitfield)

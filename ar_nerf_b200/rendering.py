@@ -1,0 +1,205 @@
+"""Render API of the reference (models/rendering.py:13-54,162-319), kept verbatim at the call boundary:
+`render(model, rays_o, rays_d, **kwargs) -> dict` with the same kwargs and result keys, so train.py:84-109,
+show_gui.py:94 and insert/main.py:126,645 can call it unchanged.  The kernels underneath are libarnerf.so."""
+import torch
+import torch.nn.functional as F
+from einops import rearrange
+
+from . import vren
+from .custom_functions import RayAABBIntersector, RayMarcher, VolumeRenderer
+
+MAX_SAMPLES = 1024    # rendering.py:9
+NEAR_DISTANCE = 0.01  # rendering.py:10
+
+
+# ---- the two helpers rendering.py pulls from insert/insert_utils.py (:18-19, :102-147) without open3d/matplotlib (Q13)
+def normalize_eps(vec, eps=1e-6):
+    return vec / (torch.norm(vec, dim=-1, keepdim=True) + eps)
+
+
+def get_SH_val(shec, dirs, clamp_postive=False):
+    """insert_utils.py:142-147 with SH_functions_torch (:102-131): order-3 real SH (9 terms), shec (9,3) -> (x,3)."""
+    x, y, z = dirs[..., 0], dirs[..., 1], dirs[..., 2]
+    dir_shs = torch.stack([
+        0.2820947918 * torch.ones_like(x),
+        0.4886025119 * y, 0.4886025119 * z, 0.4886025119 * x,
+        1.0925484306 * x * y, 1.0925484306 * y * z, 0.3153915653 * (3.0 * z ** 2 - 1),
+        1.0925484306 * x * z, 0.5462742153 * (x ** 2 - y ** 2)], dim=-1)
+    vals = torch.matmul(dir_shs.unsqueeze(-2), shec).squeeze(-2)
+    if clamp_postive:
+        vals = F.relu(vals)
+    return vals
+
+
+def _intersect(model, rays_o, rays_d):
+    """rendering.py:29-31.  Single scene box: fused slab test + near clamp; otherwise the general path."""
+    if model.center.shape[0] == 1 and hasattr(model, 'host_box'):
+        center, half_size = model.host_box()
+        return vren.ray_aabb_near(rays_o.float(), rays_d.float(), center, half_size, NEAR_DISTANCE)
+    _, hits_t, _ = RayAABBIntersector.apply(rays_o, rays_d, model.center, model.half_size, 1)
+    hits_t[(hits_t[:, 0, 0] >= 0) & (hits_t[:, 0, 0] < NEAR_DISTANCE), 0, 0] = NEAR_DISTANCE
+    return hits_t
+
+
+@torch.amp.autocast('cuda')
+def render(model, rays_o, rays_d, **kwargs):
+    """
+    Render rays by
+    1. Compute the intersection of the rays with the scene bounding box
+    2. Follow the process in @render_func (different for train/test)
+
+    Inputs:
+        model: NGP
+        rays_o: (N_rays, 3) ray origins
+        rays_d: (N_rays, 3) ray directions
+
+    Outputs:
+        result: dictionary containing final rgb and depth
+    """
+    rays_o = rays_o.contiguous(); rays_d = rays_d.contiguous()
+    hits_t = _intersect(model, rays_o, rays_d)
+
+    if kwargs.get('test_time', False):
+        render_func = __render_rays_test
+    else:
+        render_func = __render_rays_train
+
+    mesh_depth_map = kwargs.get('mesh_depth_map', None)
+    if mesh_depth_map is not None:  # flattened (rendering.py:38-44)
+        valid_depth = mesh_depth_map >= 1e-6
+        hits_t_s = hits_t[valid_depth]
+        update_min = torch.min(hits_t_s[:, 0, 1], mesh_depth_map[valid_depth])
+        update_min = torch.max(update_min, hits_t_s[:, 0, 0])
+        hits_t[valid_depth, 0, 1] = update_min
+
+    results = render_func(model, rays_o, rays_d, hits_t, **kwargs)
+    for k, v in results.items():
+        if kwargs.get('to_cpu', False):
+            v = v.cpu()
+            if kwargs.get('to_numpy', False):
+                v = v.numpy()
+        results[k] = v
+    return results
+
+
+@torch.no_grad()
+def __render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
+    """rendering.py:162-253: iterative march / evaluate / composite with alive-ray compaction (schedule kept, Q10)."""
+    exp_step_factor = kwargs.get('exp_step_factor', 0.)
+    results = {}
+
+    N_rays = len(rays_o)
+    device = rays_o.device
+    opacity = torch.zeros(N_rays, device=device)
+    depth = torch.zeros(N_rays, device=device)
+    rgb = torch.zeros(N_rays, 3, device=device)
+
+    samples = total_samples = 0
+    alive_indices = torch.arange(N_rays, device=device)
+    min_samples = 1 if exp_step_factor == 0 else 4
+    hits_t2 = hits_t[:, 0]  # (R,2) view, marched in place
+
+    while samples < kwargs.get('max_samples', MAX_SAMPLES):
+        N_alive = len(alive_indices)
+        if N_alive == 0: break
+
+        N_samples = max(min(N_rays // N_alive, 64), min_samples)
+        samples += N_samples
+
+        xyzs, dirs, deltas, ts, N_eff_samples = \
+            vren.raymarching_test(rays_o, rays_d, hits_t2, alive_indices, model.density_bitfield, model.cascades,
+                                  model.scale, exp_step_factor, model.grid_size, MAX_SAMPLES, N_samples)
+        total_samples += N_eff_samples.sum()
+        xyzs = rearrange(xyzs, 'n1 n2 c -> (n1 n2) c')
+        dirs = rearrange(dirs, 'n1 n2 c -> (n1 n2) c')
+        valid_mask = ~torch.all(dirs == 0, dim=1)
+        if valid_mask.sum() == 0: break
+
+        sigmas = torch.zeros(len(xyzs), device=device)
+        rgbs = torch.zeros(len(xyzs), 3, device=device)
+
+        xyzs = xyzs[valid_mask]; dirs = dirs[valid_mask]
+        pts_num = xyzs.shape[0]
+        val_batch_size = kwargs.get('val_batch_size', pts_num)
+        sigma_bat_res = []; rgb_bat_res = []
+        for i in range(0, pts_num, val_batch_size):
+            sigma_bat, rgb_bat = model(xyzs[i:i + val_batch_size], dirs[i:i + val_batch_size], **kwargs)
+            sigma_bat_res.append(sigma_bat)
+            rgb_bat_res.append(rgb_bat)
+        sigmas[valid_mask] = torch.concat(sigma_bat_res, 0)
+        rgbs[valid_mask] = torch.concat(rgb_bat_res, 0).float()
+
+        sigmas = rearrange(sigmas, '(n1 n2) -> n1 n2', n2=N_samples)
+        rgbs = rearrange(rgbs, '(n1 n2) c -> n1 n2 c', n2=N_samples)
+
+        vren.composite_test_fw(sigmas, rgbs, deltas, ts, hits_t2, alive_indices, kwargs.get('T_threshold', 1e-4),
+                               N_eff_samples, opacity, depth, rgb)
+        alive_indices = alive_indices[alive_indices >= 0]  # remove converged rays
+
+    results['opacity'] = opacity
+    results['depth'] = depth
+    results['rgb'] = rgb
+    results['total_samples'] = total_samples  # total samples for all rays
+
+    rgb_bg = torch.zeros(3, device=device)
+    SH_bkg = kwargs.get('SH_bkg', None)
+    if SH_bkg is not None:
+        rgb_bg = get_SH_val(SH_bkg, rays_d, clamp_postive=True)
+    IM_bkg = kwargs.get('IM_bkg', None)
+    if IM_bkg is not None:
+        rgb_bg = IM_bkg
+    if kwargs.get('blend_bkg', True):
+        results['rgb'] += rgb_bg * rearrange(1 - opacity, 'n -> n 1')
+    return results
+
+
+def __render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):
+    """rendering.py:255-298: march -> field -> composite, background blend (Q9)."""
+    exp_step_factor = kwargs.get('exp_step_factor', 0.)
+    results = {}
+
+    (rays_a, xyzs, dirs, results['deltas'], results['ts'], results['rm_samples']) = \
+        RayMarcher.apply(rays_o, rays_d, hits_t[:, 0], model.density_bitfield, model.cascades, model.scale,
+                         exp_step_factor, model.grid_size, MAX_SAMPLES, kwargs.get('noise', None))
+
+    for k, v in kwargs.items():  # supply additional inputs, repeated per ray
+        if isinstance(v, torch.Tensor) and k != 'noise':
+            kwargs[k] = torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0)
+    sigmas, rgbs = model(xyzs, dirs, **kwargs)
+
+    (results['vr_samples'], results['opacity'], results['depth'], results['rgb'], results['ws']) = \
+        VolumeRenderer.apply(sigmas, rgbs.contiguous(), results['deltas'], results['ts'], rays_a,
+                             kwargs.get('T_threshold', 1e-4))
+    results['rays_a'] = rays_a
+
+    if kwargs.get('random_bg', False):
+        rgb_bg = torch.rand(3, device=rays_o.device)
+    else:
+        if exp_step_factor == 0:  # synthetic
+            rgb_bg = torch.ones(3, device=rays_o.device)
+        else:  # real
+            rgb_bg = torch.zeros(3, device=rays_o.device)
+
+    results['rgb'] = results['rgb'] + rgb_bg * rearrange(1 - results['opacity'], 'n -> n 1')
+    del rgb_bg
+    return results
+
+
+@torch.enable_grad()
+def render_surface_normal(model, pts, **kwargs):
+    """rendering.py:300-313: normals = -normalize(d sigma / d x)."""
+    H, W, _ = pts.shape
+    pts_grad = pts.reshape(-1, 3).detach().clone().requires_grad_(True)
+    sigmas = model.density(pts_grad)
+    normals = torch.autograd.grad(sigmas, pts_grad, torch.ones_like(sigmas))[0]
+    normals = normals.reshape(H, W, 3).nan_to_num(0.0, 1.0, -1.0).detach()
+    normals = -normalize_eps(normals)
+    return normals
+
+
+@torch.no_grad()
+def render_surface_rgb(model, pts, rays_d, **kwargs):
+    """rendering.py:315-319."""
+    H, W, _ = pts.shape
+    sigmas, rgbs = model(pts.reshape(-1, 3), rays_d.reshape(-1, 3), **kwargs)
+    return rgbs.reshape(H, W, 3)

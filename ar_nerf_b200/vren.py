@@ -1,0 +1,224 @@
+"""`vren`-shaped module: the 12 functions of the reference's pybind11 extension (models/csrc/binding.cpp:234-250),
+same names, argument order, return values and error behaviour, running on libarnerf.so (sm_100a) through ctypes.
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * raymarching_train returns exactly-sized outputs in canonical ray order (rays_a[r] = (r, start, N)); the
+    reference returns worst-case buffers in a scheduling-dependent order and the caller slices by counter[0].
+  * kernels run on torch's current stream, not the legacy default stream.
+"""
+import torch
+
+from . import _lib
+from ._lib import F, I, L, call, check_tensor, ptr, stream
+
+_DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.float64: 2}
+_T_SCRATCH = {}
+_T_SCRATCH_LIMIT = 8 << 30  # bytes; larger requests fall back to the re-march emit
+
+
+def _t_scratch(device, n):
+    buf = _T_SCRATCH.get(device)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(n, dtype=torch.float32, device=device)
+        _T_SCRATCH[device] = buf
+    return buf
+
+
+def ray_aabb_intersect(rays_o, rays_d, centers, half_sizes, max_hits):
+    """binding.cpp:4-17 -> intersection.cu:59-100.  Returns (hit_cnt (R) i32, hits_t (R,max_hits,2), hits_voxel_idx (R,max_hits) i64)."""
+    for t, n in ((rays_o, "rays_o"), (rays_d, "rays_d"), (centers, "centers"), (half_sizes, "half_sizes")):
+        check_tensor(t, n, torch.float32, 2, 3)
+    R, V = rays_o.shape[0], centers.shape[0]
+    dev = rays_o.device
+    hit_cnt = torch.empty(R, dtype=torch.int32, device=dev)
+    hits_t = torch.empty(R, max_hits, 2, dtype=torch.float32, device=dev)
+    hits_idx = torch.empty(R, max_hits, dtype=torch.int64, device=dev)
+    call("arn_ray_aabb_intersect", ptr(rays_o), ptr(rays_d), R, ptr(centers), ptr(half_sizes), V, int(max_hits),
+         ptr(hit_cnt), ptr(hits_t), ptr(hits_idx), stream())
+    return [hit_cnt, hits_t, hits_idx]
+
+
+def ray_sphere_intersect(rays_o, rays_d, centers, radii, max_hits):
+    """binding.cpp:19-32 -> intersection.cu:156-197."""
+    for t, n in ((rays_o, "rays_o"), (rays_d, "rays_d"), (centers, "centers")):
+        check_tensor(t, n, torch.float32, 2, 3)
+    check_tensor(radii, "radii", torch.float32, 1)
+    R, V = rays_o.shape[0], centers.shape[0]
+    dev = rays_o.device
+    hit_cnt = torch.empty(R, dtype=torch.int32, device=dev)
+    hits_t = torch.empty(R, max_hits, 2, dtype=torch.float32, device=dev)
+    hits_idx = torch.empty(R, max_hits, dtype=torch.int64, device=dev)
+    call("arn_ray_sphere_intersect", ptr(rays_o), ptr(rays_d), R, ptr(centers), ptr(radii), V, int(max_hits),
+         ptr(hit_cnt), ptr(hits_t), ptr(hits_idx), stream())
+    return [hit_cnt, hits_t, hits_idx]
+
+
+def ray_aabb_near(rays_o, rays_d, center_host, half_size_host, near):
+    """Fused rendering.py:29-31 (single box, max_hits=1, near clamp).  center/half_size are 3-float host sequences."""
+    check_tensor(rays_o, "rays_o", torch.float32, 2, 3); check_tensor(rays_d, "rays_d", torch.float32, 2, 3)
+    R = rays_o.shape[0]
+    hits_t = torch.empty(R, 1, 2, dtype=torch.float32, device=rays_o.device)
+    c = (F * 3)(*[float(v) for v in center_host]); h = (F * 3)(*[float(v) for v in half_size_host])
+    call("arn_ray_aabb_near", ptr(rays_o), ptr(rays_d), R, c, h, float(near), ptr(hits_t), stream())
+    return hits_t
+
+
+def morton3D(coords):
+    """binding.cpp:46-50 -> raymarching.cu:72-88."""
+    check_tensor(coords, "coords", torch.int32, 2, 3)
+    out = torch.empty(coords.shape[0], dtype=torch.int32, device=coords.device)
+    call("arn_morton3d", ptr(coords), coords.shape[0], ptr(out), stream())
+    return out
+
+
+def morton3D_invert(indices):
+    """binding.cpp:53-57 -> raymarching.cu:103-119."""
+    check_tensor(indices, "indices", torch.int32, 1)
+    out = torch.empty(indices.shape[0], 3, dtype=torch.int32, device=indices.device)
+    call("arn_morton3d_invert", ptr(indices), indices.shape[0], ptr(out), stream())
+    return out
+
+
+def packbits(density_grid, density_threshold, density_bitfield):
+    """binding.cpp:34-43 -> raymarching.cu:143-162.  In place on density_bitfield (uint8, C*G^3/8)."""
+    check_tensor(density_grid, "density_grid"); check_tensor(density_bitfield, "density_bitfield", torch.uint8)
+    if density_grid.dtype not in _DTYPE_CODE:
+        raise RuntimeError(f'"packbits_cu" not implemented for \'{density_grid.dtype}\'')
+    n_bytes = density_bitfield.numel()
+    if density_grid.numel() < 8 * n_bytes:
+        raise RuntimeError("density_grid must hold 8 cells per bitfield byte")
+    call("arn_packbits", ptr(density_grid), _DTYPE_CODE[density_grid.dtype], float(density_threshold),
+         ptr(density_bitfield), n_bytes, stream())
+
+
+def raymarching_train(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size,
+                      max_samples):
+    """binding.cpp:60-81 -> raymarching.cu:283-332.  Returns [rays_a, xyzs, dirs, deltas, ts, counter]."""
+    check_tensor(rays_o, "rays_o", torch.float32, 2, 3); check_tensor(rays_d, "rays_d", torch.float32, 2, 3)
+    check_tensor(hits_t, "hits_t", torch.float32, 2, 2); check_tensor(density_bitfield, "density_bitfield", torch.uint8)
+    check_tensor(noise, "noise", torch.float32, 1)
+    R = rays_o.shape[0]
+    dev = rays_o.device
+    if density_bitfield.numel() < cascades * grid_size ** 3 // 8:
+        raise RuntimeError("density_bitfield smaller than cascades*grid_size^3/8")
+    rays_a = torch.empty(R, 3, dtype=torch.int64, device=dev)
+    counter = torch.empty(2, dtype=torch.int32, device=dev)
+    scratch_n = R * max_samples
+    t_scratch = _t_scratch(dev, scratch_n) if 0 < scratch_n * 4 <= _T_SCRATCH_LIMIT else None
+    cfg = (ptr(density_bitfield), int(cascades), int(grid_size), float(scale), float(exp_step_factor), ptr(noise),
+           int(max_samples))
+    call("arn_march_train_count_ex", ptr(rays_o), ptr(rays_d), ptr(hits_t), R, *cfg, ptr(rays_a), ptr(counter),
+         ptr(t_scratch), stream())
+    total = int(counter[0].item()) if R > 0 else 0  # the one host sync the reference has too (custom_functions.py:91-96)
+    xyzs = torch.empty(total, 3, dtype=torch.float32, device=dev)
+    dirs = torch.empty(total, 3, dtype=torch.float32, device=dev)
+    deltas = torch.empty(total, dtype=torch.float32, device=dev)
+    ts = torch.empty(total, dtype=torch.float32, device=dev)
+    call("arn_march_train_emit_ex", ptr(rays_o), ptr(rays_d), ptr(hits_t), R, *cfg, ptr(rays_a), ptr(t_scratch),
+         ptr(xyzs), ptr(dirs), ptr(deltas), ptr(ts), total, stream())
+    return [rays_a, xyzs, dirs, deltas, ts, counter]
+
+
+def raymarching_test(rays_o, rays_d, hits_t, alive_indices, density_bitfield, cascades, scale, exp_step_factor,
+                     grid_size, max_samples, N_samples):
+    """binding.cpp:84-106 -> raymarching.cu:407-454.  hits_t (R,2) updated in place.  Returns [xyzs, dirs, deltas, ts, N_eff]."""
+    check_tensor(rays_o, "rays_o", torch.float32, 2, 3); check_tensor(rays_d, "rays_d", torch.float32, 2, 3)
+    check_tensor(hits_t, "hits_t", torch.float32, 2, 2); check_tensor(alive_indices, "alive_indices", torch.int64, 1)
+    check_tensor(density_bitfield, "density_bitfield", torch.uint8)
+    n, S, dev = alive_indices.shape[0], int(N_samples), rays_o.device
+    xyzs = torch.empty(n, S, 3, dtype=torch.float32, device=dev)
+    dirs = torch.empty(n, S, 3, dtype=torch.float32, device=dev)
+    deltas = torch.empty(n, S, dtype=torch.float32, device=dev)
+    ts = torch.empty(n, S, dtype=torch.float32, device=dev)
+    n_eff = torch.empty(n, dtype=torch.int32, device=dev)
+    call("arn_march_test", ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_indices), n, ptr(density_bitfield),
+         int(cascades), int(grid_size), float(scale), float(exp_step_factor), S, int(max_samples),
+         ptr(xyzs), ptr(dirs), ptr(deltas), ptr(ts), ptr(n_eff), stream())
+    return [xyzs, dirs, deltas, ts, n_eff]
+
+
+def composite_train_fw(sigmas, rgbs, deltas, ts, rays_a, T_threshold):
+    """binding.cpp:109-126 -> volumerendering.cu:47-83.  Returns [total_samples (R) i64, opacity, depth, rgb, ws]."""
+    check_tensor(sigmas, "sigmas", torch.float32, 1); check_tensor(rgbs, "rgbs", torch.float32, 2, 3)
+    check_tensor(deltas, "deltas", torch.float32, 1); check_tensor(ts, "ts", torch.float32, 1)
+    check_tensor(rays_a, "rays_a", torch.int64, 2, 3)
+    R, N, dev = rays_a.shape[0], sigmas.shape[0], sigmas.device
+    total = torch.empty(R, dtype=torch.int64, device=dev)
+    opacity = torch.empty(R, dtype=torch.float32, device=dev)
+    depth = torch.empty(R, dtype=torch.float32, device=dev)
+    rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    ws = torch.empty(N, dtype=torch.float32, device=dev)
+    call("arn_composite_train_fw", ptr(sigmas), ptr(rgbs), ptr(deltas), ptr(ts), ptr(rays_a), R, N, float(T_threshold),
+         ptr(total), ptr(opacity), ptr(depth), ptr(rgb), ptr(ws), stream())
+    return [total, opacity, depth, rgb, ws]
+
+
+def composite_train_bw(dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws, deltas, ts, rays_a, opacity, depth,
+                       rgb, T_threshold):
+    """binding.cpp:129-163 -> volumerendering.cu:153-201.  dL_dws may be None.  Returns [dL_dsigmas, dL_drgbs]."""
+    for t, n in ((dL_dopacity, "dL_dopacity"), (dL_ddepth, "dL_ddepth"), (sigmas, "sigmas"), (ws, "ws"),
+                 (deltas, "deltas"), (ts, "ts"), (opacity, "opacity"), (depth, "depth")):
+        check_tensor(t, n, torch.float32, 1)
+    check_tensor(dL_drgb, "dL_drgb", torch.float32, 2, 3); check_tensor(rgbs, "rgbs", torch.float32, 2, 3)
+    check_tensor(rgb, "rgb", torch.float32, 2, 3); check_tensor(rays_a, "rays_a", torch.int64, 2, 3)
+    if dL_dws is not None:
+        check_tensor(dL_dws, "dL_dws", torch.float32, 1)
+    R, N, dev = rays_a.shape[0], sigmas.shape[0], sigmas.device
+    dsig = torch.empty(N, dtype=torch.float32, device=dev)
+    drgbs = torch.empty(N, 3, dtype=torch.float32, device=dev)
+    call("arn_composite_train_bw", ptr(dL_dopacity), ptr(dL_ddepth), ptr(dL_drgb), ptr(dL_dws), ptr(sigmas), ptr(rgbs),
+         ptr(ws), ptr(deltas), ptr(ts), ptr(rays_a), ptr(opacity), ptr(depth), ptr(rgb), R, N, float(T_threshold),
+         ptr(dsig), ptr(drgbs), stream())
+    return [dsig, drgbs]
+
+
+def composite_test_fw(sigmas, rgbs, deltas, ts, hits_t, alive_indices, T_threshold, N_eff_samples, opacity, depth, rgb):
+    """binding.cpp:166-194 -> volumerendering.cu:251-284.  In place on alive_indices / opacity / depth / rgb."""
+    check_tensor(sigmas, "sigmas", torch.float32, 2); check_tensor(rgbs, "rgbs", torch.float32, 3, 3)
+    check_tensor(deltas, "deltas", torch.float32, 2); check_tensor(ts, "ts", torch.float32, 2)
+    check_tensor(hits_t, "hits_t")  # accepted and unused, as in the reference kernel
+    check_tensor(alive_indices, "alive_indices", torch.int64, 1); check_tensor(N_eff_samples, "N_eff_samples", torch.int32, 1)
+    check_tensor(opacity, "opacity", torch.float32, 1); check_tensor(depth, "depth", torch.float32, 1)
+    check_tensor(rgb, "rgb", torch.float32, 2, 3)
+    n, S = sigmas.shape
+    call("arn_composite_test_fw", ptr(sigmas), ptr(rgbs), ptr(deltas), ptr(ts), ptr(alive_indices), n, S,
+         float(T_threshold), ptr(N_eff_samples), ptr(opacity), ptr(depth), ptr(rgb), stream())
+
+
+def distortion_loss_fw(ws, deltas, ts, rays_a):
+    """binding.cpp:197-209 -> losses.cu:62-107.  Returns [loss (R), ws_inclusive_scan (N), wts_inclusive_scan (N)]."""
+    for t, n in ((ws, "ws"), (deltas, "deltas"), (ts, "ts")):
+        check_tensor(t, n, torch.float32, 1)
+    check_tensor(rays_a, "rays_a", torch.int64, 2, 3)
+    R, N, dev = rays_a.shape[0], ws.shape[0], ws.device
+    loss = torch.zeros(R, dtype=torch.float32, device=dev)
+    wsi = torch.zeros(N, dtype=torch.float32, device=dev)
+    wtsi = torch.zeros(N, dtype=torch.float32, device=dev)
+    call("arn_distortion_fw", ptr(ws), ptr(deltas), ptr(ts), ptr(rays_a), R, N, ptr(loss), ptr(wsi), ptr(wtsi), stream())
+    return [loss, wsi, wtsi]
+
+
+def distortion_loss_bw(dL_dloss, ws_inclusive_scan, wts_inclusive_scan, ws, deltas, ts, rays_a):
+    """binding.cpp:212-231 -> losses.cu:143-181.  Returns dL_dws (N)."""
+    for t, n in ((dL_dloss, "dL_dloss"), (ws_inclusive_scan, "ws_inclusive_scan"), (wts_inclusive_scan, "wts_inclusive_scan"),
+                 (ws, "ws"), (deltas, "deltas"), (ts, "ts")):
+        check_tensor(t, n, torch.float32, 1)
+    check_tensor(rays_a, "rays_a", torch.int64, 2, 3)
+    R, N = rays_a.shape[0], ws.shape[0]
+    out = torch.zeros(N, dtype=torch.float32, device=ws.device)
+    call("arn_distortion_bw", ptr(dL_dloss), ptr(ws_inclusive_scan), ptr(wts_inclusive_scan), ptr(ws), ptr(deltas),
+         ptr(ts), ptr(rays_a), R, N, ptr(out), stream())
+    return out
+
+
+def segment_sums(dL_dxyzs, dL_ddirs, ts, rays_a):
+    """Per-row sums for RayMarcher.backward (replaces torch_scatter.segment_csr, custom_functions.py:104-112)."""
+    check_tensor(dL_dxyzs, "dL_dxyzs", torch.float32, 2, 3); check_tensor(ts, "ts", torch.float32, 1)
+    check_tensor(rays_a, "rays_a", torch.int64, 2, 3)
+    if dL_ddirs is not None:
+        check_tensor(dL_ddirs, "dL_ddirs", torch.float32, 2, 3)
+    R = rays_a.shape[0]
+    d_o = torch.empty(R, 3, dtype=torch.float32, device=ts.device)
+    d_d = torch.empty(R, 3, dtype=torch.float32, device=ts.device)
+    call("arn_march_train_bw", ptr(dL_dxyzs), ptr(dL_ddirs), ptr(ts), ptr(rays_a), R, ptr(d_o), ptr(d_d), stream())
+    return d_o, d_d

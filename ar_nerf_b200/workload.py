@@ -1,0 +1,141 @@
+"""Synthetic workloads of SURVEY.md section 8(d): W1 Lego-shaped scene (scale 0.5, 1 cascade, 128^3), W2 800x800 test
+frame, W3 unbounded scene (scale 16, 6 cascades).  Everything is generated with CPU generators from fixed seeds so the
+CPU oracle and the GPU see identical inputs.  Ray conventions follow datasets/ray_utils.py:8-70 (un-normalised
+directions) and datasets/nerf.py:27-73 (800x800, camera_angle_x 0.6911112, poses rescaled to radius 1.5)."""
+import math
+
+import numpy as np
+import torch
+
+IMG_WH = (800, 800)
+CAMERA_ANGLE_X = 0.6911112
+DENSITY_THRESHOLD = 0.01 * 1024 / 3 ** 0.5  # train.py:176
+
+
+def intrinsics(w=800, h=800):
+    fx = fy = 0.5 * 800 / math.tan(0.5 * CAMERA_ANGLE_X) * (w / 800)
+    return torch.tensor([[fx, 0, w / 2], [0, fy, h / 2], [0, 0, 1]], dtype=torch.float32)
+
+
+def ray_directions(h, w, K):
+    """datasets/ray_utils.py:8-43 (pixel centres, un-normalised, flattened)."""
+    v, u = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing='ij')
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    return torch.stack([(u - cx + 0.5) / fx, (v - cy + 0.5) / fy, torch.ones_like(u)], -1).reshape(-1, 3)
+
+
+def get_rays(directions, c2w):
+    """datasets/ray_utils.py:46-70."""
+    if c2w.ndim == 2:
+        rays_d = directions @ c2w[:, :3].T
+    else:
+        rays_d = (directions[:, None, :] @ c2w[..., :3].transpose(1, 2))[:, 0]
+    rays_o = c2w[..., 3].expand_as(rays_d)
+    return rays_o.contiguous(), rays_d.contiguous()
+
+
+def look_at_poses(n, radius, seed, upper_only=True, inward=True):
+    """n camera-to-world matrices [right down front] on a sphere of `radius`, looking at the origin."""
+    g = np.random.default_rng(seed)
+    poses = []
+    for _ in range(n):
+        z = g.uniform(0.1, 0.9) if upper_only else g.uniform(-0.9, 0.9)
+        phi = g.uniform(0, 2 * math.pi)
+        r = math.sqrt(1 - z * z)
+        pos = radius * np.array([r * math.cos(phi), r * math.sin(phi), z])
+        front = -pos / np.linalg.norm(pos)
+        up = np.array([0.0, 0.0, 1.0])
+        right = np.cross(front, up); right /= np.linalg.norm(right)
+        down = np.cross(front, right)
+        poses.append(np.stack([right, down, front, pos], 1))
+    return torch.tensor(np.stack(poses), dtype=torch.float32)
+
+
+def lego_boxes():
+    """Axis-aligned boxes (lo, hi in [-0.5,0.5]^3) imitating the Lego bulldozer: base plate, body, cabin, arm, bucket.
+    Together they fill about 5 % of the 128^3 cells."""
+    return [((-0.34, -0.20, -0.30), (0.34, 0.20, -0.22)),   # base plate / tracks
+            ((-0.24, -0.15, -0.22), (0.14, 0.15, 0.00)),    # body
+            ((-0.18, -0.11, 0.00), (0.02, 0.11, 0.15)),     # cabin
+            ((0.14, -0.04, -0.16), (0.36, 0.04, -0.06)),    # arm
+            ((0.30, -0.19, -0.24), (0.42, 0.19, -0.02))]    # bucket
+
+
+def occupancy_from_boxes(boxes, cascades=1, grid_size=128, scale=0.5, shell=None, seed=0):
+    """density_grid (C, G^3) in MORTON order: 10 inside a box, 0 outside; optional sparse random shell (fraction) in
+    cascades >= 2 for the unbounded workload W3."""
+    G = grid_size
+    r = np.arange(G)
+    zz, yy, xx = np.meshgrid(r, r, r, indexing='ij')
+    x, y, z = xx.reshape(-1).astype(np.uint32), yy.reshape(-1).astype(np.uint32), zz.reshape(-1).astype(np.uint32)
+
+    def expand(v):
+        v = (v * np.uint32(0x00010001)) & np.uint32(0xFF0000FF)
+        v = (v * np.uint32(0x00000101)) & np.uint32(0x0F00F00F)
+        v = (v * np.uint32(0x00000011)) & np.uint32(0xC30C30C3)
+        v = (v * np.uint32(0x00000005)) & np.uint32(0x49249249)
+        return v
+    morton = (expand(x) | (expand(y) << np.uint32(1)) | (expand(z) << np.uint32(2))).astype(np.int64)
+    grid = np.zeros((cascades, G ** 3), np.float32)
+    g = np.random.default_rng(seed)
+    for c in range(cascades):
+        s = min(2.0 ** (c - 1), scale)  # half extent of cascade c (networks.py:224)
+        cx = ((x.astype(np.float32) + 0.5) / G * 2 - 1) * s
+        cy = ((y.astype(np.float32) + 0.5) / G * 2 - 1) * s
+        cz = ((z.astype(np.float32) + 0.5) / G * 2 - 1) * s
+        inside = np.zeros(G ** 3, bool)
+        for lo, hi in boxes:
+            inside |= (cx >= lo[0]) & (cx <= hi[0]) & (cy >= lo[1]) & (cy <= hi[1]) & (cz >= lo[2]) & (cz <= hi[2])
+        if shell is not None and c >= 2:
+            inside |= g.random(G ** 3) < shell
+        grid[c, morton[inside]] = 10.0
+    return torch.from_numpy(grid)
+
+
+def pack_bitfield(density_grid, threshold=DENSITY_THRESHOLD):
+    """numpy restatement of packbits (raymarching.cu:122-141) for building inputs on the host."""
+    bits = (density_grid.reshape(-1).numpy() > threshold)
+    return torch.from_numpy(np.packbits(bits, bitorder='little'))
+
+
+class Workload:
+    """Holds poses / directions / occupancy of one synthetic scene and draws seeded train batches (datasets/base.py:22-36)."""
+
+    def __init__(self, kind='W1', n_poses=100, seed=0):
+        self.kind = kind
+        self.K = intrinsics()
+        self.directions = ray_directions(IMG_WH[1], IMG_WH[0], self.K)
+        if kind == 'W1':
+            self.scale, self.exp_step_factor = 0.5, 0.0
+            self.poses = look_at_poses(n_poses, 1.5, seed)
+            self.cascades = 1
+            self.density_grid = occupancy_from_boxes(lego_boxes(), 1, 128, 0.5)
+        elif kind == 'W3':
+            self.scale, self.exp_step_factor = 16.0, 1 / 256
+            self.poses = look_at_poses(n_poses, 1.0, seed, upper_only=False)
+            self.cascades = 6
+            self.density_grid = occupancy_from_boxes(lego_boxes(), 6, 128, 16.0, shell=0.01, seed=seed)
+        else:
+            raise ValueError(kind)
+        self.bitfield = pack_bitfield(self.density_grid)
+        self.test_pose = look_at_poses(1, 1.5 if kind == 'W1' else 1.0, seed + 12345)[0]
+
+    def train_batch(self, step, batch_size=8192, seed=0):
+        """Returns (rays_o, rays_d, rgb_target, noise) on the CPU, all float32."""
+        g = torch.Generator().manual_seed(seed * 1000003 + step)
+        img_idxs = torch.randint(len(self.poses), (batch_size,), generator=g)
+        pix_idxs = torch.randint(self.directions.shape[0], (batch_size,), generator=g)
+        rays_o, rays_d = get_rays(self.directions[pix_idxs], self.poses[img_idxs])
+        rgb = torch.rand(batch_size, 3, generator=g)
+        noise = torch.rand(batch_size, generator=g)
+        return rays_o, rays_d, rgb, noise
+
+    def test_frame(self, h=800, w=800):
+        K = intrinsics(w, h)
+        return get_rays(ray_directions(h, w, K), self.test_pose)
+
+    def install(self, model):
+        """Copies the occupancy into an NGP (density_grid, density_bitfield)."""
+        model.init_density_grid()
+        model.density_grid.copy_(self.density_grid.to(model.density_grid.device))
+        model.density_bitfield.copy_(self.bitfield.to(model.density_bitfield.device))

@@ -1,0 +1,226 @@
+/*
+ * include/arnerf.h -- C ABI of libarnerf.so, the B200 (sm_100a) implementation of the AR-NeRF rendering hot path.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one function of the reference's pybind11 module `vren`
+ * (models/csrc/binding.cpp:234-250) or one tiny-cuda-nn call site of models/networks.py, and is what a
+ * maintainer's FFI stub binds (see INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the library never allocates persistent device memory: all buffers (including scratch) come from the caller;
+ *   - every kernel is launched on the `stream` argument (a cudaStream_t passed as void*), never on the legacy stream,
+ *     so calls are CUDA-graph capturable and re-entrant;
+ *   - return value: 0 on success, negative ARN_E_* otherwise; arn_last_error() returns a thread-local message;
+ *   - outputs are written completely by the kernels (no pre-zeroing by the caller is needed) unless stated.
+ *   - "in place" tensors keep the reference's in-place semantics: density_bitfield, hits_t (test march),
+ *     alive_indices, opacity/depth/rgb (test compositing).
+ */
+#ifndef ARNERF_H_
+#define ARNERF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARN_VERSION 100 /* round 1 */
+
+#define ARN_OK 0
+#define ARN_E_INVALID (-1) /* bad argument (null pointer, negative size, unsupported configuration) */
+#define ARN_E_CUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+
+typedef void* arn_stream_t; /* cudaStream_t */
+
+int arn_version(void);
+const char* arn_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
+int64_t arn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Ray / box and ray / sphere intersection.
+ * Replaces vren.ray_aabb_intersect   (binding.cpp:4-17   -> intersection.cu:59-100, kernel :25-56)
+ *          vren.ray_sphere_intersect (binding.cpp:19-32  -> intersection.cu:156-197, kernel :124-153).
+ * hit_cnt (R) i32, hits_t (R,max_hits,2) f32, hits_idx (R,max_hits) i64; unfilled slots are -1 and, exactly as the
+ * reference's torch::sort on t1 leaves them, come FIRST.  One thread per ray loops over the voxels (deterministic).
+ * ---------------------------------------------------------------------------------------------------------- */
+int arn_ray_aabb_intersect(const float* rays_o, const float* rays_d, int64_t n_rays,
+                           const float* centers, const float* half_sizes, int n_voxels, int max_hits,
+                           int32_t* hit_cnt, float* hits_t, int64_t* hits_idx, arn_stream_t stream);
+int arn_ray_sphere_intersect(const float* rays_o, const float* rays_d, int64_t n_rays,
+                             const float* centers, const float* radii, int n_spheres, int max_hits,
+                             int32_t* hit_cnt, float* hits_t, int64_t* hits_idx, arn_stream_t stream);
+/* Fused fast path used by render(): single box, max_hits = 1, plus the near-plane clamp of rendering.py:29-31
+ * (0 <= t1 < near  ->  t1 = near).  hits_t (R,1,2).  Pass near < 0 to skip the clamp. */
+int arn_ray_aabb_near(const float* rays_o, const float* rays_d, int64_t n_rays, const float* center_host,
+                      const float* half_size_host, float near, float* hits_t, arn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Occupancy-grid utilities.
+ * Replaces vren.morton3D (binding.cpp:46-50 -> raymarching.cu:72-88), vren.morton3D_invert (:53-57 -> :103-119),
+ *          vren.packbits (:34-43 -> raymarching.cu:143-162, kernel :122-141).
+ * grid_dtype: 0 = float32, 1 = float16, 2 = float64 (the reference dispatches on the same three).
+ * ---------------------------------------------------------------------------------------------------------- */
+int arn_morton3d(const int32_t* coords, int64_t n, int32_t* indices, arn_stream_t stream);
+int arn_morton3d_invert(const int32_t* indices, int64_t n, int32_t* coords, arn_stream_t stream);
+int arn_packbits(const void* density_grid, int grid_dtype, float threshold, uint8_t* density_bitfield,
+                 int64_t n_bytes, arn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training ray march.  Replaces vren.raymarching_train (binding.cpp:60-81 -> raymarching.cu:283-332, kernel :166-280).
+ * The reference's one kernel (count, two atomics, re-march into worst-case R*max_samples buffers) is split:
+ *   arn_march_train_count : per-ray sample counts (bit-exact with the reference's pass 1), then an exclusive scan:
+ *                           rays_a[r] = (r, start[r], N[r]) (i64, canonical order) and counter = (total, n_rays).
+ *   arn_march_train_emit  : re-march into EXACTLY-sized outputs (caller reads counter[0] to size them).
+ * hits_t is (R,2).  Sample values are bit-exact with the reference's for the same ray.
+ * ---------------------------------------------------------------------------------------------------------- */
+int arn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                          const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                          float exp_step_factor, const float* noise, int max_samples,
+                          int64_t* rays_a, int32_t* counter, arn_stream_t stream);
+int arn_march_train_emit(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                         const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                         float exp_step_factor, const float* noise, int max_samples, const int64_t* rays_a,
+                         float* xyzs, float* dirs, float* deltas, float* ts, int64_t capacity, arn_stream_t stream);
+/* Same pair with a caller-provided scratch t_scratch (n_rays * max_samples floats, NOT zeroed, only the marched
+ * prefix of each row is touched): pass 1 records each sample's t, so pass 2 is one thread per sample (coalesced
+ * stores, no second march).  t_scratch == NULL falls back to the re-march of the plain entry points. */
+int arn_march_train_count_ex(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                             const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                             float exp_step_factor, const float* noise, int max_samples,
+                             int64_t* rays_a, int32_t* counter, float* t_scratch, arn_stream_t stream);
+int arn_march_train_emit_ex(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                            const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                            float exp_step_factor, const float* noise, int max_samples, const int64_t* rays_a,
+                            const float* t_scratch, float* xyzs, float* dirs, float* deltas, float* ts,
+                            int64_t capacity, arn_stream_t stream);
+
+/* Test-time march.  Replaces vren.raymarching_test (binding.cpp:84-106 -> raymarching.cu:407-454, kernel :335-404).
+ * hits_t (R,2) is updated in place at [r][0]; outputs are padded (n_alive, N_samples, .) and zero-filled past
+ * N_eff_samples[n] by the kernel.  Keeps the reference's use of `cascades` as calc_dt's scale (raymarching.cu:370). */
+int arn_march_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_indices,
+                   int64_t n_alive, const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                   float exp_step_factor, int n_samples, int max_samples,
+                   float* xyzs, float* dirs, float* deltas, float* ts, int32_t* n_eff_samples, arn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Compositing.  Replaces vren.composite_train_fw (binding.cpp:109-126 -> volumerendering.cu:47-83, kernel :5-44),
+ *               vren.composite_train_bw (:129-163 -> :153-201, kernel :86-150),
+ *               vren.composite_test_fw  (:166-194 -> :251-284, kernel :204-248).
+ * One warp per ray, warp-segmented product/sum scans, early termination at T <= T_threshold.
+ * dL_dws may be NULL (no gradient reaches ws).  n_samples = sigmas.numel().
+ * ---------------------------------------------------------------------------------------------------------- */
+int arn_composite_train_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                           const int64_t* rays_a, int64_t n_rays, int64_t n_samples, float T_threshold,
+                           int64_t* total_samples, float* opacity, float* depth, float* rgb, float* ws,
+                           arn_stream_t stream);
+int arn_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drgb, const float* dL_dws,
+                           const float* sigmas, const float* rgbs, const float* ws, const float* deltas,
+                           const float* ts, const int64_t* rays_a, const float* opacity, const float* depth,
+                           const float* rgb, int64_t n_rays, int64_t n_samples, float T_threshold,
+                           float* dL_dsigmas, float* dL_drgbs, arn_stream_t stream);
+int arn_composite_test_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                          int64_t* alive_indices, int64_t n_alive, int n_samples, float T_threshold,
+                          const int32_t* n_eff_samples, float* opacity, float* depth, float* rgb, arn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Distortion loss.  Replaces vren.distortion_loss_fw (binding.cpp:197-209 -> losses.cu:62-107) and
+ *                   vren.distortion_loss_bw (:212-231 -> losses.cu:143-181).
+ * ---------------------------------------------------------------------------------------------------------- */
+int arn_distortion_fw(const float* ws, const float* deltas, const float* ts, const int64_t* rays_a, int64_t n_rays,
+                      int64_t n_samples, float* loss, float* ws_inclusive_scan, float* wts_inclusive_scan,
+                      arn_stream_t stream);
+int arn_distortion_bw(const float* dL_dloss, const float* ws_inclusive_scan, const float* wts_inclusive_scan,
+                      const float* ws, const float* deltas, const float* ts, const int64_t* rays_a, int64_t n_rays,
+                      int64_t n_samples, float* dL_dws, arn_stream_t stream);
+
+/* Per-ray segment sums used by RayMarcher.backward (replaces torch_scatter.segment_csr, custom_functions.py:104-112):
+ * dL_drays_o[r] = sum_s dL_dxyzs[s], dL_drays_d[r] = sum_s (dL_dxyzs[s]*ts[s] + dL_ddirs[s]).  dL_ddirs may be NULL. */
+int arn_march_train_bw(const float* dL_dxyzs, const float* dL_ddirs, const float* ts, const int64_t* rays_a,
+                       int64_t n_rays, float* dL_drays_o, float* dL_drays_d, arn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Field: multiresolution hash grid (L=16, F=2) + density MLP 32-64-16 + SH-4 + colour MLP 32-64-64-16.
+ * Replaces the tiny-cuda-nn modules built in models/networks.py:37-78 and evaluated in :95-108 / :133-165.
+ * Numeric contract ("fp16 operands, fp32 accumulate") is stated in DESIGN.md and oracle/oracle_field.c.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define ARN_N_LEVELS 16
+#define ARN_DENSITY_MLP_PARAMS 3072 /* 64*32 + 16*64            (networks.py:37-57)  */
+#define ARN_RGB_MLP_PARAMS 7168     /* 64*32 + 64*64 + 16*64    (networks.py:68-78)  */
+
+/* HOST function: level table in strict float32 (tiny-cuda-nn grid.h rule).
+ * scale/res/size have n_levels entries, offset has n_levels+1 (offset[n_levels] = total entries). */
+int arn_hashgrid_geometry(int n_levels, int base_resolution, float per_level_scale, int log2_hashmap_size,
+                          float* scale_host, uint32_t* res_host, uint32_t* size_host, uint32_t* offset_host);
+
+/* fp32 master parameters -> fp16 working copy (tiny-cuda-nn casts every forward).  n elements. */
+int arn_cast_f32_to_f16(const float* src, void* dst_f16, int64_t n, arn_stream_t stream);
+
+/* Level table passed by value to the field kernels (all HOST pointers, ARN_N_LEVELS entries; offset has +1). */
+typedef struct {
+    const float* scale_host;
+    const uint32_t* res_host;
+    const uint32_t* size_host;
+    const uint32_t* offset_host;
+} arn_levels_t;
+
+/* Workspace layout of one field evaluation over n samples (all device buffers owned by the caller).
+ *   feat  (n,32) f16   encoded features                      hid   (n,64) f16   density hidden layer
+ *   h     (n,16) f32   density-net output (h[:,0] = log sigma)
+ *   in32  (n,32) f16   colour-net input [sh16 | h16]         hid1, hid2 (n,64) f16  colour hidden layers
+ * For a density-only evaluation (NGP.density) dirs, in32, hid1, hid2, rgbs and params_rgb_f16 are NULL. */
+typedef struct {
+    void* feat; void* hid; float* h; void* in32; void* hid1; void* hid2;
+} arn_field_ws_t;
+
+/* Forward.  xyzs (n,3) world coordinates, normalised inside with (x - xyz_min)/(xyz_max - xyz_min) (networks.py:104);
+ * dirs (n,3) un-normalised (normalised inside, networks.py:144).  params_xyz_f16 = [3072 MLP | table], params_rgb_f16
+ * = 7168, both already cast.  rgb_act: 1 = Sigmoid, 0 = None.  sigmas (n) f32 = exp(h0); rgbs (n,3) f32. */
+int arn_field_fw(const float* xyzs, const float* dirs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                 arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act,
+                 arn_field_ws_t ws, float* sigmas, float* rgbs, arn_stream_t stream);
+
+/* Backward.  dL_dsigmas (n) / dL_drgbs (n,3) f32 (either may be NULL = zero).  grad_params_xyz (3072 + 2*entries) f32
+ * and grad_params_rgb (7168) f32 are ACCUMULATED INTO (caller zeroes them).  dL_dxyzs (n,3) f32 optional (NULL to
+ * skip): gradient w.r.t. the world coordinates (needed by render_surface_normal, rendering.py:301-313).
+ * dfeat_scratch (n,32) f32 is scratch. */
+int arn_field_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                 arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act,
+                 arn_field_ws_t ws, const float* sigmas, const float* rgbs, const float* dL_dsigmas,
+                 const float* dL_drgbs, float loss_scale, float* dfeat_scratch, float* grad_params_xyz,
+                 float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream);
+
+/* CUDA-core ("simt") implementation of the same two calls: operation order identical to oracle/oracle_field.c, kept
+ * as the on-device cross-check of the tensor-core path (tests only; same arguments as arn_field_fw / arn_field_bw). */
+int arn_field_fw_simt(const float* xyzs, const float* dirs, int64_t n, const float* xyz_min_host,
+                      const float* xyz_max_host, arn_levels_t levels, const void* params_xyz_f16,
+                      const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws, float* sigmas, float* rgbs,
+                      arn_stream_t stream);
+int arn_field_bw_simt(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                      arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act,
+                      arn_field_ws_t ws, const float* sigmas, const float* rgbs, const float* dL_dsigmas,
+                      const float* dL_drgbs, float loss_scale, float* dfeat_scratch, float* grad_params_xyz,
+                      float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream);
+
+/* Stand-alone pieces of the field (exported for parity tests and for the hash-encode GB/s measurement). */
+int arn_hash_encode_fw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                       arn_levels_t levels, const void* table_f16, void* feat_f16, arn_stream_t stream);
+int arn_hash_encode_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                       arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad,
+                       float* dL_dxyzs, arn_stream_t stream);
+int arn_sh4(const float* dirs, int64_t n, void* out_f16, arn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimizer step.  Replaces apex FusedAdam(lr, betas=(0.9,0.999), eps=1e-15, weight_decay=0) (train.py:146).
+ * One fused pass: Adam update of the fp32 master, optional un-scaling of the gradient by inv_grad_scale, refresh of
+ * the fp16 working copy (dst_f16 may be NULL), and zeroing of the gradient for the next step (zero_grad != 0).
+ * step is the 1-based step count (bias correction as torch.optim.Adam).
+ * ---------------------------------------------------------------------------------------------------------- */
+int arn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* dst_f16, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int step, float inv_grad_scale, int zero_grad,
+                  arn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARNERF_H_ */

@@ -1,0 +1,79 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/arnerf.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "arnerf.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(arn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_reference_surface():
+    syms = declared_symbols()
+    # one entry per function of the reference's pybind module (binding.cpp:234-250) ...
+    for s in ["arn_ray_aabb_intersect", "arn_ray_sphere_intersect", "arn_morton3d", "arn_morton3d_invert", "arn_packbits",
+              "arn_march_train_count", "arn_march_train_emit", "arn_march_test", "arn_composite_train_fw", "arn_composite_train_bw",
+              "arn_composite_test_fw", "arn_distortion_fw", "arn_distortion_bw",
+              # ... plus the tiny-cuda-nn / apex / torch_scatter replacements
+              "arn_field_fw", "arn_field_bw", "arn_hash_encode_fw", "arn_hash_encode_bw", "arn_sh4", "arn_adam_step",
+              "arn_march_train_bw", "arn_hashgrid_geometry", "arn_version", "arn_last_error"]:
+        assert s in syms, s
+
+
+def test_library_exports_every_declared_symbol():
+    from ar_nerf_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "libarnerf.so not built: run python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/arnerf.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in ar_nerf_b200/_lib.py"
+    assert _lib.lib().arn_version() == 100
+    assert _lib.lib().arn_last_error() == b""
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected before any CUDA call: negative sizes / null pointers -> ARN_E_INVALID + message."""
+    from ar_nerf_b200 import _lib
+    l = _lib.lib()
+    assert l.arn_morton3d(None, -1, None, None) == -1 and b"bad size" in l.arn_last_error()
+    assert l.arn_packbits(None, 0, 0.0, None, 8, None) == -1 and b"null pointer" in l.arn_last_error()
+    with pytest.raises(RuntimeError, match="arn_march_test failed"):
+        _lib.call("arn_march_test", None, None, None, None, 4, None, 1, 128, 0.5, 0.0, 0, 1024, None, None, None, None, None, None)
+
+
+def test_geometry_matches_oracle():
+    import oracle
+    from ar_nerf_b200.field import HashGeometry
+    for scale in (0.5, 1.0, 2.0, 8.0, 16.0):
+        b = float(np.float32(np.exp(np.log(2048 * scale / 16) / 15)))
+        a, o = HashGeometry(per_level_scale=b), oracle.HashGeometry(per_level_scale=b)
+        assert np.array_equal(a.res, o.res) and np.array_equal(a.size, o.size) and np.array_equal(a.offset, o.offset)
+        assert np.array_equal(a.scale.view(np.uint32), o.scale.view(np.uint32))
+
+
+def test_product_never_imports_the_oracle():
+    """The product path must not route through oracle/ (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "ar_nerf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src and "oracle/_ref" not in src and "dlopen" not in src, f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from ar_nerf_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libarnerf.so")
+    with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
+        _lib.lib()

@@ -1,0 +1,503 @@
+"""Parity tests proper (-m gpu): every libarnerf.so entry point, called through the C ABI (ctypes, ar_nerf_b200.vren),
+against the CPU oracle on the same seeded inputs and -- when oracle/_ref/vren*.so travelled to the box -- against the
+UNMODIFIED reference kernels themselves.
+
+Bar (BASELINE.json north_star): bit-exact for occupancy bits, morton codes, sample counts, indices and sample values;
+1e-4 relative for rgb / opacity / depth / ws and gradients.  "Relative" is taken against max(|ref|, 1e-2 * max|ref|)
+per tensor (REL_FLOOR below): an element-wise relative bound on values that are themselves rounding noise around zero
+would be meaningless."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import refvren
+from conftest import near_clamp, scene_hits
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+REL_FLOOR = 1e-2
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def T(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).to(dev())
+    return t if dtype is None else t.to(dtype)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_rel(got, ref, rtol=RTOL, what=""):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    if ref.size == 0:
+        return
+    denom = np.maximum(np.abs(ref), REL_FLOOR * np.abs(ref).max())
+    err = np.abs(got - ref) / np.maximum(denom, 1e-30)
+    assert err.max() <= rtol, f"{what}: max rel err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)} (ref {ref.flat[err.argmax()]:.6e}, got {got.flat[err.argmax()]:.6e})"
+
+
+@pytest.fixture(scope="module")
+def vren():
+    from ar_nerf_b200 import vren as v
+    return v
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refvren.load()  # None when oracle/_ref was not built
+
+
+def workload(kind, w1, w3):
+    return w1 if kind == "W1" else w3
+
+
+# ------------------------------------------------------------------------------------------------ grid utilities
+def test_morton_and_packbits(vren, ref):
+    rng = np.random.default_rng(0)
+    c = rng.integers(0, 1024, (100003, 3)).astype(np.int32)
+    idx = vren.morton3D(T(c))
+    assert np.array_equal(N(idx), oracle.morton3D(c))
+    assert np.array_equal(N(vren.morton3D_invert(idx)), c)
+    for dt in (torch.float32, torch.float16, torch.float64):
+        g = (rng.random(128 ** 3 // 4 + 24) * 12).astype(np.float16).astype(np.float32)  # representable in all three dtypes
+        g[::5] = 5.912 if dt != torch.float16 else np.float32(np.float16(5.912))
+        thr = 5.912
+        b = torch.zeros(g.size // 8, dtype=torch.uint8, device=dev())
+        vren.packbits(T(g, dt), thr, b)
+        want = np.zeros(g.size // 8, np.uint8)
+        oracle.packbits(T(g, dt).float().cpu().numpy() if dt != torch.float64 else g, thr, want)
+        if dt == torch.float64:  # compared in double against (double)thr
+            want = np.packbits(g.astype(np.float64) > np.float64(np.float32(thr)), bitorder='little')
+        assert np.array_equal(N(b), want), dt
+        if ref is not None:
+            b2 = torch.zeros_like(b); ref.packbits(T(g, dt), thr, b2)
+            assert torch.equal(b, b2), dt
+    if ref is not None:
+        assert torch.equal(idx, ref.morton3D(T(c)))
+        assert torch.equal(vren.morton3D_invert(idx), ref.morton3D_invert(idx))
+
+
+# ------------------------------------------------------------------------------------------------ intersections
+@pytest.mark.parametrize("kind", ["W1", "W3"])
+def test_ray_aabb(kind, w1, w3, vren, ref):
+    w = workload(kind, w1, w3)
+    ro, rd, _, _ = w.train_batch(0, 8192)
+    ro[:4] = torch.tensor([[0, 0, -2.0], [0.01, 0.02, 0.03], [3, 3, 3], [0.1, -2, 0.05]]) * (1 if kind == "W1" else 4)
+    rd[:4] = torch.tensor([[0, 0, 1.0], [0.3, -0.2, 0.9], [1, 0, 0], [0, 1, 0]])
+    center = np.zeros((1, 3), np.float32); half = np.full((1, 3), w.scale, np.float32)
+    cnt, ht, hi = vren.ray_aabb_intersect(T(ro), T(rd), T(center), T(half), 1)
+    ocnt, oht, ohi = oracle.ray_aabb_intersect(ro.numpy(), rd.numpy(), center, half, 1)
+    assert np.array_equal(N(cnt), ocnt) and np.array_equal(bits(N(ht)), bits(oht)) and np.array_equal(N(hi), ohi)
+    fused = vren.ray_aabb_near(T(ro), T(rd), [0, 0, 0], [w.scale] * 3, 0.01)
+    assert np.array_equal(bits(N(fused)[:, 0]), bits(near_clamp(oht)))
+    # several voxels
+    g = torch.Generator().manual_seed(3)
+    vc = ((torch.rand(8, 3, generator=g) - 0.5) * w.scale).numpy(); vh = np.full((8, 3), 0.2 * w.scale, np.float32)
+    cnt8, ht8, hi8 = vren.ray_aabb_intersect(T(ro), T(rd), T(vc), T(vh), 4)
+    ocnt8, oht8, ohi8 = oracle.ray_aabb_intersect(ro.numpy(), rd.numpy(), vc, vh, 4)
+    assert np.array_equal(N(cnt8), ocnt8) and np.array_equal(bits(N(ht8)), bits(oht8)) and np.array_equal(N(hi8), ohi8)
+    scnt, sht, shi = vren.ray_sphere_intersect(T(ro), T(rd), T(vc), T(vh[:, 0].copy()), 4)
+    oscnt, osht, oshi = oracle.ray_sphere_intersect(ro.numpy(), rd.numpy(), vc, vh[:, 0].copy(), 4)
+    assert np.array_equal(N(scnt), oscnt) and np.array_equal(N(shi), oshi)
+    np.testing.assert_allclose(N(sht), osht, rtol=1e-5, atol=1e-6)
+    if ref is not None:
+        rc, rt, ri = ref.ray_aabb_intersect(T(ro), T(rd), T(center), T(half), 1)
+        assert torch.equal(cnt, rc) and torch.equal(ht.view(torch.int32), rt.view(torch.int32)) and torch.equal(hi, ri)
+        rc, rt, ri = ref.ray_aabb_intersect(T(ro), T(rd), T(vc), T(vh), 4)
+        full = rc <= 4
+        assert torch.equal(cnt8, rc) and torch.equal(ht8[full].view(torch.int32), rt[full].view(torch.int32))
+        rc, rt, ri = ref.ray_sphere_intersect(T(ro), T(rd), T(vc), T(vh[:, 0].copy()), 4)
+        full = rc <= 4
+        assert torch.equal(scnt, rc)
+        assert torch.equal(sht[full].view(torch.int32), rt[full].view(torch.int32)), "sphere hits not bit-identical"
+
+
+# ------------------------------------------------------------------------------------------------ marching
+@pytest.mark.parametrize("kind,n_rays", [("W1", 8192), ("W3", 8192), ("W1", 1), ("W1", 33)])
+def test_march_train_bit_exact(kind, n_rays, w1, w3, vren, ref):
+    w = workload(kind, w1, w3)
+    ro, rd, _, noise = w.train_batch(1, n_rays)
+    ht = scene_hits(w, ro.numpy(), rd.numpy())
+    cfg = (w.cascades, w.scale, w.exp_step_factor)
+    out = vren.raymarching_train(T(ro), T(rd), T(ht), T(w.bitfield), *cfg, T(noise), 128, 1024)
+    rays_a, xyzs, dirs, deltas, ts, counter = [N(t) for t in out]
+    o_ra, o_x, o_d, o_dl, o_ts, o_c = oracle.raymarching_train(ro.numpy(), rd.numpy(), ht, w.bitfield.numpy(), *cfg, noise.numpy(), 128, 1024)
+    assert np.array_equal(rays_a, o_ra) and np.array_equal(counter, o_c)
+    for a, b in ((xyzs, o_x), (dirs, o_d), (deltas, o_dl), (ts, o_ts)):
+        assert np.array_equal(bits(a), bits(b))
+    # the re-march emit (no t scratch) gives the same bytes
+    from ar_nerf_b200 import vren as v
+    lim = v._T_SCRATCH_LIMIT
+    try:
+        v._T_SCRATCH_LIMIT = 0
+        out2 = vren.raymarching_train(T(ro), T(rd), T(ht), T(w.bitfield), *cfg, T(noise), 128, 1024)
+    finally:
+        v._T_SCRATCH_LIMIT = lim
+    for a, b in zip(out, out2):
+        assert torch.equal(a, b)
+    if ref is not None:
+        r_out = ref.raymarching_train(T(ro), T(rd), T(ht), T(w.bitfield), *cfg, T(noise), 128, 1024)
+        n, rx, rdirs, rdl, rts, total = refvren.canonical_train(r_out)
+        assert total == counter[0] and np.array_equal(n, rays_a[:, 2])
+        for a, b in ((xyzs, rx), (dirs, rdirs), (deltas, rdl), (ts, rts)):
+            assert np.array_equal(bits(a), bits(b))
+
+
+def test_march_train_edge_cases(vren):
+    """Empty batch, all rays missing, empty occupancy, full occupancy (max_samples cap)."""
+    z = torch.zeros(0, 3, device=dev())
+    bf = torch.zeros(128 ** 3 // 8, dtype=torch.uint8, device=dev())
+    out = vren.raymarching_train(z, z, torch.zeros(0, 2, device=dev()), bf, 1, 0.5, 0.0, torch.zeros(0, device=dev()), 128, 1024)
+    assert out[0].shape == (0, 3) and out[1].shape == (0, 3) and int(out[5][0]) == 0
+    ro = torch.tensor([[0, 0, -2.0]] * 64, device=dev()); rd = torch.tensor([[0, 0, 1.0]] * 64, device=dev())
+    miss = torch.full((64, 2), -1.0, device=dev())
+    out = vren.raymarching_train(ro, rd, miss, bf, 1, 0.5, 0.0, torch.rand(64, device=dev()), 128, 1024)
+    assert int(out[5][0]) == 0 and (out[0][:, 2] == 0).all() and (out[0][:, 0] == torch.arange(64, device=dev())).all()
+    hit = torch.tensor([[1.5, 2.5]] * 64, device=dev())
+    out = vren.raymarching_train(ro, rd, hit, bf, 1, 0.5, 0.0, torch.rand(64, device=dev()), 128, 1024)
+    assert int(out[5][0]) == 0
+    full = torch.full_like(bf, 255)
+    noise = torch.rand(64, device=dev())
+    out = vren.raymarching_train(ro, rd, hit, full, 1, 0.5, 0.0, noise, 128, 1024)
+    o = oracle.raymarching_train(N(ro), N(rd), N(hit), N(full), 1, 0.5, 0.0, N(noise), 128, 1024)
+    assert np.array_equal(N(out[0]), o[0]) and np.array_equal(bits(N(out[4])), bits(o[4])) and N(out[0])[:, 2].max() <= 1024
+    # max_samples cap reached
+    out = vren.raymarching_train(ro, rd, hit, full, 1, 0.5, 0.0, noise, 128, 100)
+    o = oracle.raymarching_train(N(ro), N(rd), N(hit), N(full), 1, 0.5, 0.0, N(noise), 128, 100)
+    assert (out[0][:, 2] == 100).all() and np.array_equal(bits(N(out[4])), bits(o[4]))
+    with pytest.raises(RuntimeError):
+        vren.raymarching_train(ro.cpu(), rd, hit, full, 1, 0.5, 0.0, noise, 128, 100)
+    with pytest.raises(RuntimeError):
+        vren.raymarching_train(ro, rd, hit, full, 0, 0.5, 0.0, noise, 128, 100)
+
+
+@pytest.mark.parametrize("kind", ["W1", "W3"])
+def test_march_test_bit_exact(kind, w1, w3, vren, ref):
+    w = workload(kind, w1, w3)
+    ro, rd, _, _ = w.train_batch(2, 4096)
+    ht = scene_hits(w, ro.numpy(), rd.numpy())
+    cfg = (w.cascades, w.scale, w.exp_step_factor)
+    h_gpu, h_orc = T(ht), ht.copy()
+    h_ref = T(ht) if ref is not None else None
+    alive = np.arange(len(ro), dtype=np.int64)
+    for S in (1, 2, 4, 64, 64):
+        g = vren.raymarching_test(T(ro), T(rd), h_gpu, T(alive), T(w.bitfield), *cfg, 128, 1024, S)
+        o = oracle.raymarching_test(ro.numpy(), rd.numpy(), h_orc, alive, w.bitfield.numpy(), *cfg, 128, 1024, S)
+        for a, b in zip(g, o):
+            a = N(a)
+            assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
+        assert np.array_equal(bits(N(h_gpu)), bits(h_orc))
+        if ref is not None:
+            r = ref.raymarching_test(T(ro), T(rd), h_ref, T(alive), T(w.bitfield), *cfg, 128, 1024, S)
+            for a, b in zip(g, r):
+                assert torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b)
+            assert torch.equal(h_gpu.view(torch.int32), h_ref.view(torch.int32))
+        alive = alive[o[4] > 0][::2].copy() if S == 4 else alive[o[4] > 0]  # also exercise a ragged alive list
+
+
+# ------------------------------------------------------------------------------------------------ compositing
+def _comp_inputs(w, seed, n_rays=8192, sigma_max=60.0):
+    ro, rd, _, noise = w.train_batch(seed, n_rays)
+    ht = scene_hits(w, ro.numpy(), rd.numpy())
+    o = oracle.raymarching_train(ro.numpy(), rd.numpy(), ht, w.bitfield.numpy(), w.cascades, w.scale, w.exp_step_factor, noise.numpy(), 128, 1024)
+    rays_a, _, _, deltas, ts, _ = o
+    g = np.random.default_rng(seed)
+    sig = (g.random(len(ts)) * sigma_max).astype(np.float32); rgbs = g.random((len(ts), 3)).astype(np.float32)
+    return rays_a, deltas, ts, sig, rgbs, g
+
+
+@pytest.mark.parametrize("kind,thr,sigma_max", [("W1", 1e-4, 60.0), ("W1", 1e-2, 400.0), ("W3", 1e-4, 30.0), ("W1", 0.0, 5.0)])
+def test_composite_train_fw_bw(kind, thr, sigma_max, w1, w3, vren, ref):
+    w = workload(kind, w1, w3)
+    rays_a, deltas, ts, sig, rgbs, g = _comp_inputs(w, 4, sigma_max=sigma_max)
+    R, Ns = len(rays_a), len(ts)
+    total, opacity, depth, rgb, ws = vren.composite_train_fw(T(sig), T(rgbs), T(deltas), T(ts), T(rays_a), thr)
+    o_total, o_op, o_dp, o_rgb, o_ws = oracle.composite_train_fw(sig, rgbs, deltas, ts, rays_a, thr)
+    same = N(total) == o_total  # the T<=thr break can move by one sample between exp implementations
+    assert same.mean() >= 0.995, same.mean()
+    keep = np.repeat(same, rays_a[:, 2])
+    assert_rel(N(opacity)[same], o_op[same], what="opacity"); assert_rel(N(depth)[same], o_dp[same], what="depth")
+    assert_rel(N(rgb)[same], o_rgb[same], what="rgb"); assert_rel(N(ws)[keep], o_ws[keep], what="ws")
+    gO, gD, gC = g.standard_normal(R).astype(np.float32), g.standard_normal(R).astype(np.float32), g.standard_normal((R, 3)).astype(np.float32)
+    for gW in (g.standard_normal(Ns).astype(np.float32), None):
+        dsig, drgbs = vren.composite_train_bw(T(gO), T(gD), T(gC), None if gW is None else T(gW), T(sig), T(rgbs), T(o_ws), T(deltas), T(ts),
+                                              T(rays_a), T(o_op), T(o_dp), T(o_rgb), thr)
+        o_dsig, o_drgbs = oracle.composite_train_bw(gO, gD, gC, np.zeros(Ns, np.float32) if gW is None else gW, sig, rgbs, o_ws, deltas, ts,
+                                                    rays_a, o_op, o_dp, o_rgb, thr)
+        assert_rel(N(drgbs)[keep], o_drgbs[keep], what="dL_drgbs"); assert_rel(N(dsig)[keep], o_dsig[keep], what="dL_dsigmas")
+    if ref is not None:
+        r_total, r_op, r_dp, r_rgb, r_ws = ref.composite_train_fw(T(sig), T(rgbs), T(deltas), T(ts), T(rays_a), thr)
+        same = N(total) == N(r_total)
+        assert same.mean() >= 0.999, same.mean()
+        keep = np.repeat(same, rays_a[:, 2])
+        assert_rel(N(opacity)[same], N(r_op)[same], what="opacity/ref"); assert_rel(N(depth)[same], N(r_dp)[same], what="depth/ref")
+        assert_rel(N(rgb)[same], N(r_rgb)[same], what="rgb/ref"); assert_rel(N(ws)[keep], N(r_ws)[keep], what="ws/ref")
+        gW = g.standard_normal(Ns).astype(np.float32)
+        dsig, drgbs = vren.composite_train_bw(T(gO), T(gD), T(gC), T(gW), T(sig), T(rgbs), r_ws, T(deltas), T(ts), T(rays_a), r_op, r_dp, r_rgb, thr)
+        r_dsig, r_drgbs = ref.composite_train_bw(T(gO), T(gD), T(gC), T(gW), T(sig), T(rgbs), r_ws, T(deltas), T(ts), T(rays_a), r_op, r_dp, r_rgb, thr)
+        bw_same = np.repeat(N(total) == N(r_total), rays_a[:, 2])
+        assert_rel(N(drgbs)[bw_same], N(r_drgbs)[bw_same], what="dL_drgbs/ref"); assert_rel(N(dsig)[bw_same], N(r_dsig)[bw_same], what="dL_dsigmas/ref")
+
+
+def test_composite_permuted_rows_and_empty(vren):
+    """rays_a rows in arbitrary order (the reference's atomics produce that); outputs are indexed by ray_idx."""
+    g = np.random.default_rng(1)
+    n = g.integers(0, 70, 500); n[::3] = 0
+    start = np.concatenate([[0], np.cumsum(n)[:-1]])
+    rays_a = np.stack([np.arange(500), start, n], 1).astype(np.int64)
+    perm = g.permutation(500)
+    Ns = int(n.sum())
+    sig = (g.random(Ns) * 50).astype(np.float32); rgbs = g.random((Ns, 3)).astype(np.float32)
+    deltas = np.full(Ns, 0.01, np.float32); ts = g.random(Ns).astype(np.float32)
+    a = vren.composite_train_fw(T(sig), T(rgbs), T(deltas), T(ts), T(rays_a), 1e-4)
+    b = vren.composite_train_fw(T(sig), T(rgbs), T(deltas), T(ts), T(rays_a[perm]), 1e-4)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    e = torch.zeros(0, device=dev())
+    out = vren.composite_train_fw(e, torch.zeros(0, 3, device=dev()), e, e, T(np.stack([np.arange(4), np.zeros(4), np.zeros(4)], 1).astype(np.int64)), 1e-4)
+    assert (out[1] == 0).all() and (out[3] == 0).all() and (out[0] == 0).all()
+
+
+@pytest.mark.parametrize("S", [1, 4, 64])
+def test_composite_test_fw(S, vren, ref):
+    g = np.random.default_rng(S)
+    R, n = 5000, 3000
+    alive = np.sort(g.choice(R, n, replace=False)).astype(np.int64)
+    neff = g.integers(0, S + 1, n).astype(np.int32)
+    sig = (g.random((n, S)) * 200).astype(np.float32); rgbs = g.random((n, S, 3)).astype(np.float32)
+    deltas = np.full((n, S), 0.01, np.float32); ts = g.random((n, S)).astype(np.float32)
+    op0 = (g.random(R) * 0.9).astype(np.float32); dp0 = g.random(R).astype(np.float32); rgb0 = g.random((R, 3)).astype(np.float32)
+    a_g, op_g, dp_g, rgb_g = T(alive), T(op0), T(dp0), T(rgb0)
+    vren.composite_test_fw(T(sig), T(rgbs), T(deltas), T(ts), torch.zeros(R, 2, device=dev()), a_g, 1e-2, T(neff), op_g, dp_g, rgb_g)
+    a_o, op_o, dp_o, rgb_o = alive.copy(), op0.copy(), dp0.copy(), rgb0.copy()
+    oracle.composite_test_fw(sig, rgbs, deltas, ts, None, a_o, 1e-2, neff, op_o, dp_o, rgb_o)
+    assert (N(a_g) == a_o).mean() > 0.998
+    assert_rel(N(op_g), op_o, what="opacity"); assert_rel(N(dp_g), dp_o, what="depth"); assert_rel(N(rgb_g), rgb_o, what="rgb")
+    if ref is not None:
+        a_r, op_r, dp_r, rgb_r = T(alive), T(op0), T(dp0), T(rgb0)
+        ref.composite_test_fw(T(sig), T(rgbs), T(deltas), T(ts), torch.zeros(R, 2, device=dev()), a_r, 1e-2, T(neff), op_r, dp_r, rgb_r)
+        assert torch.equal(a_g, a_r)
+        assert_rel(N(op_g), N(op_r), rtol=1e-6, what="opacity/ref"); assert_rel(N(rgb_g), N(rgb_r), rtol=1e-6, what="rgb/ref")
+
+
+def test_distortion_loss(w1, vren, ref):
+    rays_a, deltas, ts, sig, rgbs, g = _comp_inputs(w1, 6, n_rays=4096)
+    _, _, _, _, ws = oracle.composite_train_fw(sig, rgbs, deltas, ts, rays_a, 1e-4)
+    loss, wsi, wtsi = vren.distortion_loss_fw(T(ws), T(deltas), T(ts), T(rays_a))
+    o_loss, o_wsi, o_wtsi = oracle.distortion_loss_fw(ws, deltas, ts, rays_a)
+    assert_rel(N(wsi), o_wsi, what="ws scan"); assert_rel(N(wtsi), o_wtsi, what="wts scan")
+    assert_rel(N(loss), o_loss, rtol=2e-3, what="distortion loss")  # difference of large prefix products in fp32
+    gl = g.standard_normal(len(rays_a)).astype(np.float32)
+    dws = vren.distortion_loss_bw(T(gl), T(o_wsi), T(o_wtsi), T(ws), T(deltas), T(ts), T(rays_a))
+    assert_rel(N(dws), oracle.distortion_loss_bw(gl, o_wsi, o_wtsi, ws, deltas, ts, rays_a), what="dL_dws")
+    if ref is not None:
+        r_loss, r_wsi, r_wtsi = ref.distortion_loss_fw(T(ws), T(deltas), T(ts), T(rays_a))
+        assert_rel(N(wsi), N(r_wsi), what="ws scan/ref"); assert_rel(N(loss), N(r_loss), rtol=2e-3, what="loss/ref")
+        assert_rel(N(dws), N(ref.distortion_loss_bw(T(gl), T(o_wsi), T(o_wtsi), T(ws), T(deltas), T(ts), T(rays_a))), what="dL_dws/ref")
+
+
+# ------------------------------------------------------------------------------------------------ field
+def _field_setup(scale, n, seed, table_amp=0.5):
+    from ar_nerf_b200.networks import NGP
+    model = NGP(scale).to(dev())
+    rng = np.random.default_rng(seed)
+    geo = oracle.HashGeometry(per_level_scale=model.geometry.per_level_scale)
+    assert np.array_equal(geo.res, model.geometry.res) and np.array_equal(geo.offset, model.geometry.offset)
+    assert np.array_equal(geo.scale.view(np.uint32), model.geometry.scale.view(np.uint32))
+    x = ((rng.random((n, 3)) * 2 - 1) * scale).astype(np.float32)
+    x[:6] = np.array([[-1, -1, -1], [1, 1, 1], [0, 0, 0], [1, -1, 1], [0.999999, 0.5, -0.25], [-1, 1, 0]], np.float32) * scale
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    pxyz = np.concatenate([(rng.random(3072) * 2 - 1) * 0.3, (rng.random(2 * geo.total) * 2 - 1) * table_amp]).astype(np.float32)
+    prgb = ((rng.random(7168) * 2 - 1) * 0.3).astype(np.float32)
+    with torch.no_grad():
+        model.xyz_encoder.params.copy_(T(pxyz)); model.rgb_net.params.copy_(T(prgb))
+    mn, mx = np.full(3, -scale, np.float32), np.full(3, scale, np.float32)
+    x01 = (x - mn) / (mx - mn)
+    return model, geo, x, x01, d, pxyz, prgb
+
+
+@pytest.mark.parametrize("impl", ["_simt", ""])
+@pytest.mark.parametrize("scale,n", [(0.5, 20000), (16.0, 5000), (0.5, 1), (0.5, 129)])
+def test_field_forward(impl, scale, n, vren):
+    from ar_nerf_b200.field import FieldFunction
+    model, geo, x, x01, d, pxyz, prgb = _field_setup(scale, n, 3)
+    model.field_impl = impl
+    with torch.no_grad():
+        sig, rgb = model(T(x), T(d))
+        sig2, h = model.density(T(x), return_feat=True)
+    ctx = oracle.field_fw(x01, d, geo, pxyz, prgb)
+    assert torch.equal(sig, sig2)
+    if impl == "_simt":  # same operation order as the oracle: features, hidden activations and h are bit-identical
+        assert np.array_equal(N(h).view(np.uint32), ctx["h"].view(np.uint32))
+    assert_rel(N(h), ctx["h"], rtol=2e-3 if impl == "" else 1e-6, what="h")
+    assert_rel(N(sig), ctx["sigma"], rtol=5e-3 if impl == "" else 1e-5, what="sigma")
+    np.testing.assert_allclose(N(rgb), ctx["rgb"], atol=2e-3 if impl == "" else 1e-6)
+
+
+@pytest.mark.parametrize("impl", ["_simt", ""])
+def test_field_backward(impl, vren):
+    model, geo, x, x01, d, pxyz, prgb = _field_setup(0.5, 30000, 5)
+    model.field_impl = impl
+    rng = np.random.default_rng(11)
+    gs = (rng.standard_normal(len(x)) * 1e-2).astype(np.float32); gc = (rng.standard_normal((len(x), 3)) * 1e-2).astype(np.float32)
+    xt = T(x).requires_grad_(True)
+    sig, rgb = model(xt, T(d))
+    ((sig * T(gs)).sum() + (rgb * T(gc)).sum()).backward()
+    ctx = oracle.field_fw(x01, d, geo, pxyz, prgb)
+    o_gx, o_gc, o_dx, o_dfeat = oracle.field_bw(ctx, geo, gs, gc, loss_scale=128.0, want_dx=True)
+    tol = 1e-4 if impl == "_simt" else 2e-3
+    assert_rel(N(model.rgb_net.params.grad), o_gc, rtol=tol, what="colour MLP grad")
+    assert_rel(N(model.xyz_encoder.params.grad)[:3072], o_gx[:3072], rtol=tol, what="density MLP grad")
+    assert_rel(N(model.xyz_encoder.params.grad)[3072:], o_gx[3072:], rtol=tol, what="hash table grad")
+    assert_rel(N(xt.grad), o_dx / (2 * 0.5), rtol=max(tol, 1e-3), what="dL/dxyz")
+
+
+def test_hash_encode_linearity_full_size(vren):
+    """Size-independent property at BASELINE size (2^19-entry levels, 500k samples): the encoding is linear in the table,
+    so doubling the table doubles every feature exactly (powers of two are exact in fp16/fp32)."""
+    from ar_nerf_b200 import _lib
+    from ar_nerf_b200.field import HashGeometry
+    geo = HashGeometry(per_level_scale=float(np.float32(np.exp(np.log(2048 * 0.5 / 16) / 15))))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 500_000
+    x = torch.rand(n, 3, device=dev(), generator=g) - 0.5
+    table = (torch.rand(geo.total * 2, device=dev(), generator=g) - 0.5).half()
+    mn = (_lib.F * 3)(-0.5, -0.5, -0.5); mx = (_lib.F * 3)(0.5, 0.5, 0.5)
+    f1 = torch.empty(n, 32, dtype=torch.float16, device=dev()); f2 = torch.empty_like(f1)
+    _lib.call("arn_hash_encode_fw", x.data_ptr(), n, mn, mx, geo.c_levels, table.data_ptr(), f1.data_ptr(), _lib.stream())
+    t2 = table * 2
+    _lib.call("arn_hash_encode_fw", x.data_ptr(), n, mn, mx, geo.c_levels, t2.data_ptr(), f2.data_ptr(), _lib.stream())
+    big = f1.abs() > 1e-3  # away from fp16 subnormals
+    assert torch.equal((f1 * 2)[big], f2[big])
+    # backward: sum of the table gradient equals sum of dfeat (trilinear weights sum to one), level by level
+    dfeat = torch.randn(n, 32, device=dev(), generator=g)
+    tg = torch.zeros(geo.total * 2, device=dev())
+    _lib.call("arn_hash_encode_bw", x.data_ptr(), n, mn, mx, geo.c_levels, table.data_ptr(), dfeat.data_ptr(), tg.data_ptr(), None, _lib.stream())
+    for l in (0, 5, 15):
+        a = tg[2 * int(geo.offset[l]):2 * int(geo.offset[l + 1])].double().sum().item()
+        b = dfeat[:, 2 * l:2 * l + 2].double().sum().item()
+        assert abs(a - b) <= 1e-3 * max(1.0, dfeat[:, 2 * l:2 * l + 2].abs().double().sum().item() ** 0.5 * 10), (l, a, b)
+
+
+def test_adam_step_vs_torch(vren):
+    from ar_nerf_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n = 100_003
+    p = torch.randn(n, device=dev(), generator=g); p_ref = p.clone().requires_grad_(True)
+    m = torch.zeros(n, device=dev()); v = torch.zeros(n, device=dev()); p16 = torch.empty(n, dtype=torch.float16, device=dev())
+    opt = torch.optim.Adam([p_ref], lr=1e-2, eps=1e-15)
+    for step in range(1, 4):
+        grad = torch.randn(n, device=dev(), generator=g) * (torch.rand(n, device=dev(), generator=g) > 0.5)
+        gbuf = grad.clone() * 128
+        _lib.call("arn_adam_step", p.data_ptr(), gbuf.data_ptr(), m.data_ptr(), v.data_ptr(), p16.data_ptr(), n, 1e-2, 0.9, 0.999, 1e-15, step,
+                  1.0 / 128, 1, _lib.stream())
+        p_ref.grad = grad.clone(); opt.step()
+        assert (gbuf == 0).all()
+        np.testing.assert_allclose(N(p), N(p_ref), rtol=2e-5, atol=1e-6)
+        assert torch.equal(p16, p.half())
+
+
+# ------------------------------------------------------------------------------------------------ render() end to end
+def _oracle_render_train(w, model_params, ro, rd, noise, thr=1e-4):
+    pxyz, prgb, geo = model_params
+    ht = scene_hits(w, ro, rd)
+    rays_a, xyzs, dirs, deltas, ts, _ = oracle.raymarching_train(ro, rd, ht, w.bitfield.numpy(), w.cascades, w.scale, w.exp_step_factor, noise, 128, 1024)
+    mn, mx = np.full(3, -w.scale, np.float32), np.full(3, w.scale, np.float32)
+    ctx = oracle.field_fw((xyzs - mn) / (mx - mn), dirs, geo, pxyz, prgb)
+    total, opacity, depth, rgb, ws = oracle.composite_train_fw(ctx["sigma"], ctx["rgb"], deltas, ts, rays_a, thr)
+    return dict(rays_a=rays_a, xyzs=xyzs, deltas=deltas, ts=ts, ctx=ctx, total=total, opacity=opacity, depth=depth, rgb=rgb, ws=ws)
+
+
+@pytest.mark.parametrize("kind,impl", [("W1", "_simt"), ("W1", ""), ("W3", "")])
+def test_render_train_end_to_end(kind, impl, w1, w3):
+    """rendering.render(train) + NeRFLoss + backward against the oracle pipeline on identical rays / weights / noise."""
+    from ar_nerf_b200.losses import NeRFLoss
+    from ar_nerf_b200.rendering import render
+    w = workload(kind, w1, w3)
+    model, geo, _, _, _, pxyz, prgb = _field_setup(w.scale, 8, 21, table_amp=2.0 if kind == "W1" else 1.0)
+    model.field_impl = impl
+    w.install(model)
+    ro, rd, target, noise = w.train_batch(7, 4096)
+    res = render(model, T(ro), T(rd), test_time=False, exp_step_factor=w.exp_step_factor, noise=T(noise))
+    o = _oracle_render_train(w, (pxyz, prgb, geo), ro.numpy(), rd.numpy(), noise.numpy())
+    assert np.array_equal(N(res["rays_a"]), o["rays_a"]) and int(res["rm_samples"]) == len(o["ts"])
+    assert np.array_equal(bits(N(res["ts"])), bits(o["ts"])) and np.array_equal(bits(N(res["deltas"])), bits(o["deltas"]))
+    bg = 1.0 if w.exp_step_factor == 0 else 0.0
+    o_rgb = o["rgb"] + bg * (1 - o["opacity"])[:, None]
+    tol = 1e-4 if impl == "_simt" else 2e-3
+    assert_rel(N(res["opacity"]), o["opacity"], rtol=tol, what="opacity"); assert_rel(N(res["depth"]), o["depth"], rtol=tol, what="depth")
+    assert_rel(N(res["rgb"]), o_rgb, rtol=tol, what="rgb"); assert_rel(N(res["ws"]), o["ws"], rtol=tol, what="ws")
+    # loss + backward
+    loss_d = NeRFLoss(30, 'raw', w.scale, 0.0, lambda_distortion=0.0)(res, {"rgb": T(target)})
+    sum(l.mean() for l in loss_d.values()).backward()
+    # oracle backward: dL/d(rgb,opacity) by autograd on the tiny per-ray loss, then the oracle's composite/field backward
+    rgb_t = torch.tensor(o_rgb, requires_grad=True); op_t = torch.tensor(o["opacity"], requires_grad=True)
+    l = (((rgb_t - target) / (rgb_t.detach() + 1e-3)) ** 2).mean() + (1e-3 * (-(op_t + 1e-10) * torch.log(op_t + 1e-10))).mean()
+    l.backward()
+    g_rgb = rgb_t.grad.numpy(); g_op = op_t.grad.numpy() - bg * g_rgb.sum(1)
+    dsig, drgbs = oracle.composite_train_bw(g_op, np.zeros_like(g_op), g_rgb, np.zeros(len(o["ts"]), np.float32), o["ctx"]["sigma"], o["ctx"]["rgb"],
+                                            o["ws"], o["deltas"], o["ts"], o["rays_a"], o["opacity"], o["depth"], o["rgb"], 1e-4)
+    o_gx, o_gc, _, _ = oracle.field_bw(o["ctx"], geo, dsig, drgbs, loss_scale=128.0)
+    gtol = 1e-3 if impl == "_simt" else 5e-3
+    assert_rel(N(model.rgb_net.params.grad), o_gc, rtol=gtol, what="colour MLP grad")
+    assert_rel(N(model.xyz_encoder.params.grad)[:3072], o_gx[:3072], rtol=gtol, what="density MLP grad")
+    assert_rel(N(model.xyz_encoder.params.grad)[3072:], o_gx[3072:], rtol=gtol, what="hash table grad")
+
+
+def test_render_test_end_to_end(w1):
+    """rendering.render(test_time=True): the iterative march/composite loop against the same loop driven by the oracle."""
+    from ar_nerf_b200.rendering import render
+    w = w1
+    model, geo, _, _, _, pxyz, prgb = _field_setup(w.scale, 8, 22, table_amp=4.0)
+    model.field_impl = "_simt"
+    w.install(model)
+    ro, rd = w.test_frame(100, 100)
+    res = render(model, T(ro), T(rd), test_time=True, T_threshold=1e-2, max_samples=100)
+    ro_n, rd_n = ro.numpy(), rd.numpy()
+    hits = scene_hits(w, ro_n, rd_n)
+    R = len(ro_n)
+    opacity, depth, rgb = np.zeros(R, np.float32), np.zeros(R, np.float32), np.zeros((R, 3), np.float32)
+    alive = np.arange(R, dtype=np.int64); samples = 0; total = 0
+    mn, mx = np.full(3, -w.scale, np.float32), np.full(3, w.scale, np.float32)
+    while samples < 100 and len(alive):
+        S = max(min(R // len(alive), 64), 1); samples += S
+        x, d, dl, t, neff = oracle.raymarching_test(ro_n, rd_n, hits, alive, w.bitfield.numpy(), 1, 0.5, 0.0, 128, 1024, S)
+        total += int(neff.sum())
+        valid = ~np.all(d.reshape(-1, 3) == 0, 1)
+        if valid.sum() == 0:
+            break
+        ctx = oracle.field_fw((x.reshape(-1, 3)[valid] - mn) / (mx - mn), d.reshape(-1, 3)[valid], geo, pxyz, prgb)
+        sig = np.zeros(len(valid), np.float32); col = np.zeros((len(valid), 3), np.float32)
+        sig[valid] = ctx["sigma"]; col[valid] = ctx["rgb"]
+        oracle.composite_test_fw(sig.reshape(-1, S), col.reshape(-1, S, 3), dl, t, None, alive, 1e-2, neff, opacity, depth, rgb)
+        alive = alive[alive >= 0]
+    assert int(res["total_samples"]) == total
+    assert_rel(N(res["opacity"]), opacity, rtol=1e-4, what="opacity"); assert_rel(N(res["depth"]), depth, rtol=1e-4, what="depth")
+    assert_rel(N(res["rgb"]), rgb, rtol=1e-4, what="rgb")
+
+
+def test_density_grid_update_bits(w1):
+    """update_density_grid (networks.py:253-281): given the same density values the packed bits are bit-exact."""
+    from ar_nerf_b200.networks import NGP
+    torch.manual_seed(0)
+    model = NGP(0.5).to(dev())
+    w1.install(model)
+    model.update_density_grid(5.912, warmup=True)
+    dg = N(model.density_grid)
+    thr = min(float(dg[dg > 0].mean()), 5.912)
+    want = np.zeros(model.density_bitfield.numel(), np.uint8)
+    oracle.packbits(dg, thr, want)
+    assert np.array_equal(N(model.density_bitfield), want)
+    model.update_density_grid(5.912, warmup=False)
+    assert model.density_grid.shape == (1, 128 ** 3)

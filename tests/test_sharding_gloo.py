@@ -1,0 +1,41 @@
+"""world_size-2 gloo test of the N>1 host logic (ray sharding, gradient sum, frame gather) on CPU tensors."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ar_nerf_b200.sharding import allreduce_grads, gather_frame, shard_bounds, shard_rays
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (0, 1, 7, 8192, 640000, 640001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    rays_o = torch.rand(1001, 3, generator=g); rays_d = torch.rand(1001, 3, generator=g)
+    o, d = shard_rays(rays_o, rays_d, rank, world)
+    lo, hi = shard_bounds(1001, rank, world)
+    assert torch.equal(o, rays_o[lo:hi]) and torch.equal(d, rays_d[lo:hi])
+    # per-rank "gradient" = sum of its rays; the all-reduced sum equals the single-process gradient
+    grad = [o.sum(0).clone(), d.sum(0).clone()]
+    allreduce_grads(grad, world)
+    assert torch.allclose(grad[0], rays_o.sum(0), atol=1e-4) and torch.allclose(grad[1], rays_d.sum(0), atol=1e-4)
+    frame = gather_frame(o * 2, 1001, rank, world)
+    if rank == 0:
+        assert torch.equal(frame, rays_o * 2)
+    else:
+        assert frame is None
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo():
+    mp.spawn(_worker, args=(2, 29533), nprocs=2, join=True)
