@@ -79,12 +79,30 @@ def lib():
     return _lib
 
 
+# Optional per-entry-point device timing (bench.py's instrumented pass): when TIMING is a dict, every call is
+# bracketed by CUDA events on the launching stream and (start, end) pairs are appended under the entry-point name.
+TIMING = None
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise RuntimeError(arn_last_error()) on failure."""
     l = lib()
-    rc = getattr(l, name)(*args)
+    if TIMING is not None and torch.cuda.is_available():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(l, name)(*args)
+        e1.record()
+        TIMING.setdefault(name, []).append((e0, e1))
+    else:
+        rc = getattr(l, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {l.arn_last_error().decode()}")
+
+
+def timing_summary():
+    """{entry point: (calls, total ms)} for the pairs collected since TIMING was set; synchronises."""
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (TIMING or {}).items()}
 
 
 def launch_count():

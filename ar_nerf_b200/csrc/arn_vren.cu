@@ -28,12 +28,12 @@ __device__ __forceinline__ float2 slab_test(const float* o, const float* inv, co
     return make_float2(t1, t2);
 }
 
-// intersection.cu:103-121 ; dot() contracted as FMUL x, FFMA y, FFMA z (reference SASS)
+// intersection.cu:103-121 ; dot(a,b) is contracted by nvcc as fma(a.z,b.z, fma(a.x,b.x, a.y*b.y)) (reference SASS)
 __device__ __forceinline__ float2 sphere_test(const float* o, const float* d, const float* c, float radius) {
     const float cx = __fsub_rn(o[0], c[0]), cy = __fsub_rn(o[1], c[1]), cz = __fsub_rn(o[2], c[2]);
-    const float a = __fmaf_rn(d[2], d[2], __fmaf_rn(d[1], d[1], __fmul_rn(d[0], d[0])));
-    const float half_b = __fmaf_rn(d[2], cz, __fmaf_rn(d[1], cy, __fmul_rn(d[0], cx)));
-    const float cc = __fmaf_rn(-radius, radius, __fmaf_rn(cz, cz, __fmaf_rn(cy, cy, __fmul_rn(cx, cx))));
+    const float a = __fmaf_rn(d[2], d[2], __fmaf_rn(d[0], d[0], __fmul_rn(d[1], d[1])));
+    const float half_b = __fmaf_rn(d[2], cz, __fmaf_rn(d[0], cx, __fmul_rn(d[1], cy)));
+    const float cc = __fmaf_rn(-radius, radius, __fmaf_rn(cz, cz, __fmaf_rn(cx, cx, __fmul_rn(cy, cy))));
     const float disc = __fmaf_rn(half_b, half_b, -__fmul_rn(a, cc));
     if (disc < 0) return make_float2(-1.0f, -1.0f);
     const float sq = __fsqrt_rn(disc);

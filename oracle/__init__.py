@@ -209,7 +209,7 @@ def hash_encode_fw(x01, geo, table16):
 
 def hash_encode_bw(x01, geo, table16, dfeat, want_table_grad=True, want_dx=False):
     x01 = _f32(x01); dfeat = _f32(dfeat); N = len(x01)
-    tg = np.zeros((geo.total, 2), np.float32) if want_table_grad else None
+    tg = np.zeros((geo.total, 2), np.float64) if want_table_grad else None
     dx = np.zeros((N, 3), np.float32) if want_dx else None
     lib().orc_hash_encode_bw(i64(N), _p(x01), _p(geo.scale), _p(geo.res), _p(geo.size), _p(geo.offset),
                              _p(table16), _p(dfeat), _p(tg), _p(dx))
@@ -252,7 +252,7 @@ def field_fw(x01, dirs, geo, params_xyz, params_rgb, rgb_act=1):
 def field_bw(ctx, geo, dL_dsigma, dL_drgb, loss_scale=128.0, want_dx=False):
     """Returns (grad_params_xyz fp32 flat, grad_params_rgb fp32, dL/dx01 or None)."""
     N = len(ctx["feat"])
-    dWd = np.zeros(3072, np.float32); dWc = np.zeros(7168, np.float32); dfeat = np.zeros((N, 32), np.float32)
+    dWd = np.zeros(3072, np.float64); dWc = np.zeros(7168, np.float64); dfeat = np.zeros((N, 32), np.float32)
     lib().orc_field_mlp_bw(i64(N), _p(_f32(dL_dsigma)), _p(_f32(dL_drgb)), _p(ctx["rgb"]), _p(ctx["h"]),
                            _p(ctx["feat"]), _p(ctx["hid"]), _p(ctx["in32"]), _p(ctx["hid1"]), _p(ctx["hid2"]),
                            _p(ctx["Wd"]), _p(ctx["Wc"]), i32(ctx["rgb_act"]), f(loss_scale), _p(dWd), _p(dWc), _p(dfeat))

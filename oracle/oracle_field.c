@@ -88,10 +88,12 @@ void orc_hash_encode_fw(int64_t n, const float* x01, const float* tbl_scale, con
     }
 }
 
-/* Backward of the encoding: table_grad (total_entries,2) fp32 += weight * dfeat ; optional dL/dx01 (N,3). */
+/* Backward of the encoding: table_grad (total_entries,2) += weight * dfeat ; optional dL/dx01 (N,3).
+ * The oracle accumulates in DOUBLE so that it is the order-independent reference for the (order-dependent) fp32
+ * atomics of the GPU kernel. */
 void orc_hash_encode_bw(int64_t n, const float* x01, const float* tbl_scale, const uint32_t* tbl_res,
                         const uint32_t* tbl_size, const uint32_t* tbl_offset, const f16* table, const float* dfeat,
-                        float* table_grad, float* dx01) {
+                        double* table_grad, float* dx01) {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; i++) {
         float gx[3] = {0, 0, 0};
@@ -111,9 +113,9 @@ void orc_hash_encode_bw(int64_t n, const float* x01, const float* tbl_scale, con
                 const uint32_t idx = tbl_offset[l] + grid_index(tbl_size[l], tbl_res[l], p);
                 if (table_grad) {
 #pragma omp atomic
-                    table_grad[2 * (size_t)idx] += wt * d0;
+                    table_grad[2 * (size_t)idx] += (double)(wt * d0);
 #pragma omp atomic
-                    table_grad[2 * (size_t)idx + 1] += wt * d1;
+                    table_grad[2 * (size_t)idx + 1] += (double)(wt * d1);
                 }
                 if (dx01) {
                     const float v = (float)table[2 * (size_t)idx] * d0 + (float)table[2 * (size_t)idx + 1] * d1;
@@ -210,19 +212,19 @@ void orc_rgb_mlp_fw(int64_t n, const f16* sh, const float* h, const f16* Wc, int
 }
 
 /* Backward of both nets.  Inputs dL_dsigma (N), dL_drgb (N,3) fp32 (unscaled).
- * Outputs: dWc (7168) fp32 +=, dWd (3072) fp32 += (both already divided by loss_scale),
+ * Outputs: dWc (7168) double +=, dWd (3072) double += (both already divided by loss_scale),
  *          dfeat (N,32) fp32 = dL/dfeat (unscaled) for the encoding backward. */
 void orc_field_mlp_bw(int64_t n, const float* dL_dsigma, const float* dL_drgb, const float* rgb, const float* h,
                       const f16* feat, const f16* hid, const f16* in32, const f16* hid1, const f16* hid2,
                       const f16* Wd, const f16* Wc, int rgb_act, float loss_scale,
-                      float* dWd, float* dWc, float* dfeat) {
+                      double* dWd, double* dWc, float* dfeat) {
     const f16* Wc1 = Wc; const f16* Wc2 = Wc + 2048; const f16* Wc3 = Wc + 2048 + 4096;
     const f16* Wd1 = Wd; const f16* Wd2 = Wd + 2048;
     const float inv_scale = 1.0f / loss_scale;
 #pragma omp parallel
     {
-        float* lWc = (float*)calloc(7168, sizeof(float));
-        float* lWd = (float*)calloc(3072, sizeof(float));
+        double* lWc = (double*)calloc(7168, sizeof(double)); /* double: order-independent reference sums */
+        double* lWd = (double*)calloc(3072, sizeof(double));
 #pragma omp for schedule(static)
         for (int64_t i = 0; i < n; i++) {
             f16 g3[16], g2[64], g1[64], gh[16], gd[64];
@@ -264,8 +266,8 @@ void orc_field_mlp_bw(int64_t n, const float* dL_dsigma, const float* dL_drgb, c
         }
 #pragma omp critical
         {
-            for (int k = 0; k < 7168; k++) dWc[k] += lWc[k] * inv_scale;
-            for (int k = 0; k < 3072; k++) dWd[k] += lWd[k] * inv_scale;
+            for (int k = 0; k < 7168; k++) dWc[k] += lWc[k] * (double)inv_scale;
+            for (int k = 0; k < 3072; k++) dWd[k] += lWd[k] * (double)inv_scale;
         }
         free(lWc); free(lWd);
     }

@@ -278,7 +278,7 @@ void orc_ray_aabb_intersect(int n_rays, const float* rays_o, const float* rays_d
 }
 
 /* intersection.cu:103-153,156-197.  Unused by the reference's callers; kept for API completeness.
- * dot() contraction order follows the SASS (FMUL x ; FFMA y ; FFMA z). */
+ * dot() contraction order follows the SASS: fma(a.z,b.z, fma(a.x,b.x, a.y*b.y)). */
 void orc_ray_sphere_intersect(int n_rays, const float* rays_o, const float* rays_d, int n_sph, const float* centers,
                               const float* radii, int max_hits, int32_t* hit_cnt, float* hits_t, int64_t* hits_idx) {
     for (int r = 0; r < n_rays; r++) {
@@ -289,9 +289,9 @@ void orc_ray_sphere_intersect(int n_rays, const float* rays_o, const float* rays
         for (int s = 0; s < n_sph; s++) {
             const float* c = centers + 3 * s;
             const float co[3] = {o[0] - c[0], o[1] - c[1], o[2] - c[2]};
-            const float a = fmaf(d[2], d[2], fmaf(d[1], d[1], d[0] * d[0]));
-            const float half_b = fmaf(d[2], co[2], fmaf(d[1], co[1], d[0] * co[0]));
-            const float cc = fmaf(-radii[s], radii[s], fmaf(co[2], co[2], fmaf(co[1], co[1], co[0] * co[0])));
+            const float a = fmaf(d[2], d[2], fmaf(d[0], d[0], d[1] * d[1]));
+            const float half_b = fmaf(d[2], co[2], fmaf(d[0], co[0], d[1] * co[1]));
+            const float cc = fmaf(-radii[s], radii[s], fmaf(co[2], co[2], fmaf(co[0], co[0], co[1] * co[1])));
             const float disc = fmaf(half_b, half_b, -(a * cc));
             float t1 = -1.0f, t2 = -1.0f;
             if (!(disc < 0)) { const float sq = sqrtf(disc); t1 = (-half_b - sq) / a; t2 = (-half_b + sq) / a; }
