@@ -29,6 +29,8 @@ SIGNATURES = {
     "arn_version": [],
     "arn_last_error": [],
     "arn_launch_count": [],
+    "arn_profile_enable": [I],
+    "arn_profile_report": [C.c_char_p, I],
     "arn_ray_aabb_intersect": [P, P, L, P, P, I, I, P, P, P, P],
     "arn_ray_sphere_intersect": [P, P, L, P, P, I, I, P, P, P, P],
     "arn_ray_aabb_near": [P, P, L, P, P, F, P, P],
@@ -107,6 +109,21 @@ def timing_summary():
 
 def launch_count():
     return int(lib().arn_launch_count())
+
+
+def profile_enable(on=True):
+    call("arn_profile_enable", 1 if on else 0)
+
+
+def profile_report():
+    """{kernel: (calls, total device ms)} since the last report (CUDA events inside libarnerf.so)."""
+    buf = C.create_string_buffer(1 << 16)
+    call("arn_profile_report", buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, calls, ms = line.split()
+        out[name] = (int(calls), float(ms))
+    return out
 
 
 def stream():

@@ -14,6 +14,14 @@ namespace arn {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Optional per-kernel device timing (bench.py): when enabled, every launch is bracketed by CUDA events on its own
+// stream.  Not capturable into a CUDA graph (the caller keeps it off during capture).
+struct LaunchTimer {
+    LaunchTimer(const char* name, cudaStream_t st);
+    ~LaunchTimer();
+    const char* name_; cudaStream_t st_; void* slot_;
+};
+
 inline int check_launch(const char* what) {
     count_launch();
     cudaError_t e = cudaGetLastError();
@@ -27,6 +35,12 @@ constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 }  // namespace arn
+
+#define ARN_LAUNCH(name, st, ...)                 \
+    do {                                          \
+        arn::LaunchTimer lt__((name), (st));      \
+        __VA_ARGS__;                              \
+    } while (0)
 
 #define ARN_REQUIRE(cond, msg)                                            \
     do {                                                                  \

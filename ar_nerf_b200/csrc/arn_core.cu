@@ -1,6 +1,10 @@
 // Error string, version and launch counter of libarnerf.so.
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <stdarg.h>
+#include <string>
+#include <vector>
 
 #include "arn_common.cuh"
 
@@ -14,7 +18,56 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-kernel timing
+struct TimedLaunch { const char* name; cudaEvent_t e0, e1; };
+static std::atomic<int> g_profile{0};
+static std::mutex g_profile_mu;
+static std::vector<TimedLaunch> g_timed;
+
+LaunchTimer::LaunchTimer(const char* name, cudaStream_t st) : name_(name), st_(st), slot_(nullptr) {
+    if (!g_profile.load(std::memory_order_relaxed)) return;
+    TimedLaunch* t = new TimedLaunch{name, nullptr, nullptr};
+    if (cudaEventCreate(&t->e0) != cudaSuccess || cudaEventCreate(&t->e1) != cudaSuccess) { delete t; return; }
+    cudaEventRecord(t->e0, st);
+    slot_ = t;
+}
+LaunchTimer::~LaunchTimer() {
+    if (!slot_) return;
+    TimedLaunch* t = (TimedLaunch*)slot_;
+    cudaEventRecord(t->e1, st_);
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    g_timed.push_back(*t);
+    delete t;
+}
 }  // namespace arn
+
+extern "C" ARN_API int arn_profile_enable(int on) {
+    arn::g_profile.store(on ? 1 : 0);
+    return ARN_OK;
+}
+// Writes "kernel calls total_ms\n" lines (device time from CUDA events) for every launch since the last report, then
+// clears the log.  Synchronises on the recorded events.
+extern "C" ARN_API int arn_profile_report(char* buf, int cap) {
+    if (!buf || cap <= 0) { arn::set_error("arn_profile_report: bad buffer"); return ARN_E_INVALID; }
+    std::lock_guard<std::mutex> lk(arn::g_profile_mu);
+    std::map<std::string, std::pair<int, double>> agg;
+    for (auto& t : arn::g_timed) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+            auto& a = agg[t.name]; a.first += 1; a.second += ms;
+        }
+        cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
+    }
+    arn::g_timed.clear();
+    int off = 0; buf[0] = 0;
+    for (auto& kv : agg) {
+        int n = snprintf(buf + off, cap - off, "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        if (n < 0 || n >= cap - off) break;
+        off += n;
+    }
+    return ARN_OK;
+}
 
 extern "C" ARN_API int arn_version(void) { return ARN_VERSION; }
 extern "C" ARN_API const char* arn_last_error(void) { return arn::g_err; }

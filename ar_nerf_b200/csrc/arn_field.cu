@@ -413,7 +413,7 @@ extern "C" ARN_API int arn_cast_f32_to_f16(const float* src, void* dst_f16, int6
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(src && dst_f16, "null pointer");
-    cast_f32_f16_kernel<<<ceil_div((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst_f16, n);
+    ARN_LAUNCH("cast_f32_f16_kernel", (cudaStream_t)stream, cast_f32_f16_kernel<<<ceil_div((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst_f16, n));
     return check_launch("cast_f32_to_f16");
 }
 
@@ -442,7 +442,7 @@ extern "C" ARN_API int arn_hash_encode_fw(const float* xyzs, int64_t n, const fl
     if (int e = make_levels(levels, t)) return e;
     if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
     dim3 grid(ceil_div(n, 256), ARN_N_LEVELS);
-    hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, b, t, (const __half2*)table_f16, (__half2*)feat_f16);
+    ARN_LAUNCH("hash_encode_fw_kernel", (cudaStream_t)stream, hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, b, t, (const __half2*)table_f16, (__half2*)feat_f16));
     return check_launch("hash_encode_fw");
 }
 
@@ -458,12 +458,12 @@ extern "C" ARN_API int arn_hash_encode_bw(const float* xyzs, int64_t n, const fl
     cudaStream_t st = (cudaStream_t)stream;
     if (table_grad) {
         dim3 grid(ceil_div(n, 256), ARN_N_LEVELS);
-        hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, b, t, (const float2*)dfeat, (float2*)table_grad);
+        ARN_LAUNCH("hash_encode_bw_kernel", st, hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, b, t, (const float2*)dfeat, (float2*)table_grad));
         if (int e = check_launch("hash_encode_bw")) return e;
     }
     if (dL_dxyzs) {
         ARN_REQUIRE(table_f16, "dL_dxyzs needs the table");
-        hash_encode_dx_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xyzs, n, b, t, (const __half2*)table_f16, (const float2*)dfeat, dL_dxyzs);
+        ARN_LAUNCH("hash_encode_dx_kernel", st, hash_encode_dx_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xyzs, n, b, t, (const __half2*)table_f16, (const float2*)dfeat, dL_dxyzs));
         if (int e = check_launch("hash_encode_dx")) return e;
     }
     return ARN_OK;
@@ -473,7 +473,7 @@ extern "C" ARN_API int arn_sh4(const float* dirs, int64_t n, void* out_f16, arn_
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(dirs && out_f16, "null pointer");
-    sh4_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dirs, n, (__half*)out_f16);
+    ARN_LAUNCH("sh4_kernel", (cudaStream_t)stream, sh4_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dirs, n, (__half*)out_f16));
     return check_launch("sh4");
 }
 
@@ -488,11 +488,11 @@ extern "C" ARN_API int arn_field_fw_simt(const float* xyzs, const float* dirs, i
     cudaStream_t st = (cudaStream_t)stream;
     const __half* pxyz = (const __half*)params_xyz_f16;
     if (int e = arn_hash_encode_fw(xyzs, n, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, stream)) return e;
-    density_mlp_fw_simt_kernel<<<ceil_div(n, 128), 128, 0, st>>>((const __half*)ws.feat, n, pxyz, (__half*)ws.hid, ws.h, sigmas);
+    ARN_LAUNCH("density_mlp_fw_simt_kernel", st, density_mlp_fw_simt_kernel<<<ceil_div(n, 128), 128, 0, st>>>((const __half*)ws.feat, n, pxyz, (__half*)ws.hid, ws.h, sigmas));
     if (int e = check_launch("density_mlp_fw_simt")) return e;
     if (with_rgb) {
-        rgb_mlp_fw_simt_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dirs, ws.h, n, (const __half*)params_rgb_f16, rgb_act, (__half*)ws.in32,
-                                                                (__half*)ws.hid1, (__half*)ws.hid2, rgbs);
+        ARN_LAUNCH("rgb_mlp_fw_simt_kernel", st, rgb_mlp_fw_simt_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dirs, ws.h, n, (const __half*)params_rgb_f16, rgb_act, (__half*)ws.in32,
+                                                                (__half*)ws.hid1, (__half*)ws.hid2, rgbs));
         if (int e = check_launch("rgb_mlp_fw_simt")) return e;
     }
     return ARN_OK;
@@ -517,10 +517,10 @@ extern "C" ARN_API int arn_field_bw_simt(const float* xyzs, int64_t n, const flo
     if (!attr_set) { ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
     const int64_t n_tiles = (n + 127) / 128;
     const int grid = (int)min((int64_t)n_sm * 4, n_tiles);
-    field_mlp_bw_simt_kernel<<<grid, 128, smem, st>>>(n, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, ws.h, (const __half*)ws.feat,
+    ARN_LAUNCH("field_mlp_bw_simt_kernel", (cudaStream_t)stream, field_mlp_bw_simt_kernel<<<grid, 128, smem, st>>>(n, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, ws.h, (const __half*)ws.feat,
                                                      (const __half*)ws.hid, (const __half*)ws.in32, (const __half*)ws.hid1,
                                                      (const __half*)ws.hid2, pxyz, with_rgb ? (const __half*)params_rgb_f16 : nullptr,
-                                                     rgb_act, loss_scale, grad_params_xyz, grad_params_rgb, dfeat_scratch);
+                                                     rgb_act, loss_scale, grad_params_xyz, grad_params_rgb, dfeat_scratch));
     if (int e = check_launch("field_mlp_bw_simt")) return e;
     return arn_hash_encode_bw(xyzs, n, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
                               grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, stream);
@@ -533,8 +533,8 @@ extern "C" ARN_API int arn_adam_step(float* params, float* grads, float* exp_avg
     ARN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "null pointer");
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-    adam_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (__half*)dst_f16, n, lr, beta1, beta2,
-                                                                  eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad);
+    ARN_LAUNCH("adam_kernel", (cudaStream_t)stream, adam_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (__half*)dst_f16, n, lr, beta1, beta2,
+                                                                  eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad));
     return check_launch("adam_step");
 }
 

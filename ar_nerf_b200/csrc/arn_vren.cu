@@ -517,8 +517,8 @@ extern "C" ARN_API int arn_ray_aabb_intersect(const float* rays_o, const float* 
     ARN_REQUIRE(n_rays >= 0 && n_voxels >= 0 && max_hits >= 1, "bad sizes");
     if (n_rays == 0) return ARN_OK;
     ARN_REQUIRE(rays_o && rays_d && centers && half_sizes && hit_cnt && hits_t && hits_idx, "null pointer");
-    intersect_kernel<false><<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, centers, half_sizes,
-                                                                                    n_voxels, max_hits, hit_cnt, hits_t, hits_idx);
+    ARN_LAUNCH("intersect_kernel", (cudaStream_t)stream, intersect_kernel<false><<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, centers, half_sizes,
+                                                                                    n_voxels, max_hits, hit_cnt, hits_t, hits_idx));
     return check_launch("ray_aabb_intersect");
 }
 
@@ -528,8 +528,8 @@ extern "C" ARN_API int arn_ray_sphere_intersect(const float* rays_o, const float
     ARN_REQUIRE(n_rays >= 0 && n_spheres >= 0 && max_hits >= 1, "bad sizes");
     if (n_rays == 0) return ARN_OK;
     ARN_REQUIRE(rays_o && rays_d && centers && radii && hit_cnt && hits_t && hits_idx, "null pointer");
-    intersect_kernel<true><<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, centers, radii,
-                                                                                   n_spheres, max_hits, hit_cnt, hits_t, hits_idx);
+    ARN_LAUNCH("intersect_kernel", (cudaStream_t)stream, intersect_kernel<true><<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, centers, radii,
+                                                                                   n_spheres, max_hits, hit_cnt, hits_t, hits_idx));
     return check_launch("ray_sphere_intersect");
 }
 
@@ -540,8 +540,8 @@ extern "C" ARN_API int arn_ray_aabb_near(const float* rays_o, const float* rays_
     ARN_REQUIRE(rays_o && rays_d && center_host && half_size_host && hits_t, "null pointer");
     float ch[6];  // the box is 24 bytes of module state: passed from the host so it travels as kernel arguments
     for (int k = 0; k < 3; k++) { ch[k] = center_host[k]; ch[3 + k] = half_size_host[k]; }
-    aabb_near_kernel<<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, ch[0], ch[1], ch[2], ch[3],
-                                                                            ch[4], ch[5], near, reinterpret_cast<float2*>(hits_t));
+    ARN_LAUNCH("aabb_near_kernel", (cudaStream_t)stream, aabb_near_kernel<<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, ch[0], ch[1], ch[2], ch[3],
+                                                                            ch[4], ch[5], near, reinterpret_cast<float2*>(hits_t)));
     return check_launch("ray_aabb_near");
 }
 
@@ -549,14 +549,14 @@ extern "C" ARN_API int arn_morton3d(const int32_t* coords, int64_t n, int32_t* i
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(coords && indices, "null pointer");
-    morton3d_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(coords, n, indices);
+    ARN_LAUNCH("morton3d_kernel", (cudaStream_t)stream, morton3d_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(coords, n, indices));
     return check_launch("morton3d");
 }
 extern "C" ARN_API int arn_morton3d_invert(const int32_t* indices, int64_t n, int32_t* coords, arn_stream_t stream) {
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(coords && indices, "null pointer");
-    morton3d_invert_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(indices, n, coords);
+    ARN_LAUNCH("morton3d_invert_kernel", (cudaStream_t)stream, morton3d_invert_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(indices, n, coords));
     return check_launch("morton3d_invert");
 }
 extern "C" ARN_API int arn_packbits(const void* density_grid, int grid_dtype, float threshold, uint8_t* density_bitfield,
@@ -566,9 +566,9 @@ extern "C" ARN_API int arn_packbits(const void* density_grid, int grid_dtype, fl
     ARN_REQUIRE(density_grid && density_bitfield, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t words = (n_bytes + 3) / 4;
-    if (grid_dtype == 0) packbits_kernel<float><<<ceil_div(words, 256), 256, 0, st>>>((const float*)density_grid, threshold, density_bitfield, n_bytes);
-    else if (grid_dtype == 1) packbits_kernel<__half><<<ceil_div(words, 256), 256, 0, st>>>((const __half*)density_grid, threshold, density_bitfield, n_bytes);
-    else if (grid_dtype == 2) packbits_f64_kernel<<<ceil_div(n_bytes, 256), 256, 0, st>>>((const double*)density_grid, threshold, density_bitfield, n_bytes);
+    if (grid_dtype == 0) ARN_LAUNCH("packbits_kernel", st, packbits_kernel<float><<<ceil_div(words, 256), 256, 0, st>>>((const float*)density_grid, threshold, density_bitfield, n_bytes));
+    else if (grid_dtype == 1) ARN_LAUNCH("packbits_kernel", st, packbits_kernel<__half><<<ceil_div(words, 256), 256, 0, st>>>((const __half*)density_grid, threshold, density_bitfield, n_bytes));
+    else if (grid_dtype == 2) ARN_LAUNCH("packbits_f64_kernel", st, packbits_f64_kernel<<<ceil_div(n_bytes, 256), 256, 0, st>>>((const double*)density_grid, threshold, density_bitfield, n_bytes));
     else { set_error("arn_packbits: grid_dtype must be 0 (f32), 1 (f16) or 2 (f64)"); return ARN_E_INVALID; }
     return check_launch("packbits");
 }
@@ -592,9 +592,9 @@ extern "C" ARN_API int arn_march_train_count_ex(const float* rays_o, const float
     if (n_rays == 0) { ARN_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int32_t), st)); return ARN_OK; }
     ARN_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && noise && rays_a, "null pointer");
     const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
-    march_train_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch);
+    ARN_LAUNCH("march_train_count_kernel", st, march_train_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch));
     if (int e = check_launch("march_train_count")) return e;
-    rays_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, counter);
+    ARN_LAUNCH("rays_scan_kernel", st, rays_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, counter));
     return check_launch("rays_scan");
 }
 extern "C" ARN_API int arn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
@@ -617,10 +617,10 @@ extern "C" ARN_API int arn_march_train_emit_ex(const float* rays_o, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
     if (t_scratch) {
-        march_train_emit_kernel<<<ceil_div(capacity, 256), 256, 0, st>>>(rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, xyzs, dirs, deltas, ts);
+        ARN_LAUNCH("march_train_emit_kernel", st, march_train_emit_kernel<<<ceil_div(capacity, 256), 256, 0, st>>>(rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, xyzs, dirs, deltas, ts));
         return check_launch("march_train_emit");
     }
-    march_train_remarch_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, xyzs, dirs, deltas, ts);
+    ARN_LAUNCH("march_train_remarch_kernel", st, march_train_remarch_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, xyzs, dirs, deltas, ts));
     return check_launch("march_train_remarch");
 }
 extern "C" ARN_API int arn_march_train_emit(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
@@ -641,8 +641,8 @@ extern "C" ARN_API int arn_march_test(const float* rays_o, const float* rays_d, 
     ARN_REQUIRE(rays_o && rays_d && hits_t && alive_indices && density_bitfield && xyzs && dirs && deltas && ts && n_eff_samples, "null pointer");
     // raymarching.cu:370,399: the test kernel passes `cascades` where calc_dt expects `scale`
     const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, (float)cascades, exp_step_factor, max_samples);
-    march_test_kernel<<<ceil_div(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, alive_indices, n_alive,
-                                                                              density_bitfield, c, n_samples, xyzs, dirs, deltas, ts, n_eff_samples);
+    ARN_LAUNCH("march_test_kernel", (cudaStream_t)stream, march_test_kernel<<<ceil_div(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, alive_indices, n_alive,
+                                                                              density_bitfield, c, n_samples, xyzs, dirs, deltas, ts, n_eff_samples));
     return check_launch("march_test");
 }
 
@@ -653,8 +653,8 @@ extern "C" ARN_API int arn_composite_train_fw(const float* sigmas, const float* 
     if (n_rays == 0) return ARN_OK;
     ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "null pointer");
     ARN_REQUIRE(n_samples == 0 || (sigmas && rgbs && deltas && ts && ws), "null pointer");
-    composite_train_fw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
-                                                                                          total_samples, opacity, depth, rgb, ws);
+    ARN_LAUNCH("composite_train_fw_kernel", (cudaStream_t)stream, composite_train_fw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
+                                                                                          total_samples, opacity, depth, rgb, ws));
     return check_launch("composite_train_fw");
 }
 
@@ -667,9 +667,9 @@ extern "C" ARN_API int arn_composite_train_bw(const float* dL_dopacity, const fl
     if (n_rays == 0 || n_samples == 0) return ARN_OK;
     ARN_REQUIRE(dL_dopacity && dL_ddepth && dL_drgb && sigmas && rgbs && ws && deltas && ts && rays_a && opacity && depth && rgb && dL_dsigmas && dL_drgbs,
                 "null pointer");
-    composite_train_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws,
+    ARN_LAUNCH("composite_train_bw_kernel", (cudaStream_t)stream, composite_train_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws,
                                                                                           deltas, ts, rays_a, opacity, depth, rgb, n_rays,
-                                                                                          T_threshold, dL_dsigmas, dL_drgbs);
+                                                                                          T_threshold, dL_dsigmas, dL_drgbs));
     return check_launch("composite_train_bw");
 }
 
@@ -679,8 +679,8 @@ extern "C" ARN_API int arn_composite_test_fw(const float* sigmas, const float* r
     ARN_REQUIRE(n_alive >= 0 && n_samples >= 1, "bad size");
     if (n_alive == 0) return ARN_OK;
     ARN_REQUIRE(sigmas && rgbs && deltas && ts && alive_indices && n_eff_samples && opacity && depth && rgb, "null pointer");
-    composite_test_fw_kernel<<<ceil_div(n_alive, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, alive_indices, n_alive, n_samples,
-                                                                                     T_threshold, n_eff_samples, opacity, depth, rgb);
+    ARN_LAUNCH("composite_test_fw_kernel", (cudaStream_t)stream, composite_test_fw_kernel<<<ceil_div(n_alive, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, alive_indices, n_alive, n_samples,
+                                                                                     T_threshold, n_eff_samples, opacity, depth, rgb));
     return check_launch("composite_test_fw");
 }
 
@@ -690,7 +690,7 @@ extern "C" ARN_API int arn_distortion_fw(const float* ws, const float* deltas, c
     if (n_rays == 0) return ARN_OK;
     ARN_REQUIRE(rays_a && loss, "null pointer");
     ARN_REQUIRE(n_samples == 0 || (ws && deltas && ts && ws_inclusive_scan && wts_inclusive_scan), "null pointer");
-    distortion_fw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(ws, deltas, ts, rays_a, n_rays, loss, ws_inclusive_scan, wts_inclusive_scan);
+    ARN_LAUNCH("distortion_fw_kernel", (cudaStream_t)stream, distortion_fw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(ws, deltas, ts, rays_a, n_rays, loss, ws_inclusive_scan, wts_inclusive_scan));
     return check_launch("distortion_fw");
 }
 extern "C" ARN_API int arn_distortion_bw(const float* dL_dloss, const float* ws_inclusive_scan, const float* wts_inclusive_scan, const float* ws,
@@ -699,8 +699,8 @@ extern "C" ARN_API int arn_distortion_bw(const float* dL_dloss, const float* ws_
     ARN_REQUIRE(n_rays >= 0 && n_samples >= 0, "bad size");
     if (n_rays == 0 || n_samples == 0) return ARN_OK;
     ARN_REQUIRE(dL_dloss && ws_inclusive_scan && wts_inclusive_scan && ws && deltas && ts && rays_a && dL_dws, "null pointer");
-    distortion_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dloss, ws_inclusive_scan, wts_inclusive_scan, ws, deltas, ts,
-                                                                                     rays_a, n_rays, dL_dws);
+    ARN_LAUNCH("distortion_bw_kernel", (cudaStream_t)stream, distortion_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dloss, ws_inclusive_scan, wts_inclusive_scan, ws, deltas, ts,
+                                                                                     rays_a, n_rays, dL_dws));
     return check_launch("distortion_bw");
 }
 extern "C" ARN_API int arn_march_train_bw(const float* dL_dxyzs, const float* dL_ddirs, const float* ts, const int64_t* rays_a, int64_t n_rays,
@@ -708,6 +708,6 @@ extern "C" ARN_API int arn_march_train_bw(const float* dL_dxyzs, const float* dL
     ARN_REQUIRE(n_rays >= 0, "bad size");
     if (n_rays == 0) return ARN_OK;
     ARN_REQUIRE(dL_dxyzs && ts && rays_a && dL_drays_o && dL_drays_d, "null pointer");
-    march_train_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dxyzs, dL_ddirs, ts, rays_a, n_rays, dL_drays_o, dL_drays_d);
+    ARN_LAUNCH("march_train_bw_kernel", (cudaStream_t)stream, march_train_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dxyzs, dL_ddirs, ts, rays_a, n_rays, dL_drays_o, dL_drays_d));
     return check_launch("march_train_bw");
 }

@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- training throughput of the NeRF rendering hot path on the Lego-shaped synthetic workload
+(BASELINE.json configs[1]: 8192 rays/step, scale 0.5, 1 cascade, 128^3 grid, hash grid L=16 T=2^19, random init).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one full training pass over one batch of 8192 rays per GPU: density-grid update when due (every 16
+steps) -> ray/box -> march -> hash grid + MLPs -> composite -> loss -> backward -> gradient all-reduce (N > 1) ->
+Adam.  Prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the CPU restatement of the same
+step (oracle/, all host threads) -- the reference's CUDA extension has no CPU path."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 8192
+WORKLOAD = "W1 Lego-shaped synthetic scene (scale 0.5, 1 cascade, 128^3 occupancy ~6% full, 800x800 pinhole cameras at radius 1.5), " \
+           "NGP hash grid L=16 F=2 T=2^19 + 64-wide MLPs at random init, 8192 rays/step/GPU, fw+bw+Adam"
+N_BATCHES = 16  # distinct pre-generated batches, cycled
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        out = self.proc.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU reference
+def oracle_train_step(w, geo, state, rays_o, rays_d, target, noise):
+    """One full training step of the path on the CPU oracle (march -> field -> composite -> loss -> backward -> Adam)."""
+    import numpy as np
+    import torch
+
+    import oracle
+    pxyz, prgb, m, v, step = state["pxyz"], state["prgb"], state["m"], state["v"], state["step"] + 1
+    s = w.scale
+    _, ht, _ = oracle.ray_aabb_intersect(rays_o, rays_d, np.zeros((1, 3), np.float32), np.full((1, 3), s, np.float32), 1)
+    ht = ht[:, 0].copy(); near = (ht[:, 0] >= 0) & (ht[:, 0] < 0.01); ht[near, 0] = 0.01
+    rays_a, xyzs, dirs, deltas, ts, _ = oracle.raymarching_train(rays_o, rays_d, ht, w.bitfield.numpy(), w.cascades, s, w.exp_step_factor,
+                                                                 noise, 128, 1024)
+    ctx = oracle.field_fw((xyzs + s) / (2 * s), dirs, geo, pxyz, prgb)
+    _, opacity, depth, rgb, ws = oracle.composite_train_fw(ctx["sigma"], ctx["rgb"], deltas, ts, rays_a, 1e-4)
+    bg = 1.0 if w.exp_step_factor == 0 else 0.0
+    rgb_t = torch.tensor(rgb + bg * (1 - opacity)[:, None], requires_grad=True); op_t = torch.tensor(opacity, requires_grad=True)
+    tgt = torch.as_tensor(target)
+    loss = (((rgb_t - tgt) / (rgb_t.detach() + 1e-3)) ** 2).mean() + (1e-3 * (-(op_t + 1e-10) * torch.log(op_t + 1e-10))).mean()
+    loss.backward()
+    g_rgb = rgb_t.grad.numpy(); g_op = op_t.grad.numpy() - bg * g_rgb.sum(1)
+    dsig, drgbs = oracle.composite_train_bw(g_op, np.zeros_like(g_op), g_rgb, np.zeros(len(ts), np.float32), ctx["sigma"], ctx["rgb"], ws,
+                                            deltas, ts, rays_a, opacity, depth, rgb, 1e-4)
+    gx, gc, _, _ = oracle.field_bw(ctx, geo, dsig, drgbs)
+    for p, g, k in ((pxyz, gx, "x"), (prgb, gc, "c")):  # Adam(lr 1e-2, eps 1e-15), train.py:146
+        g = g.astype(np.float32)
+        m[k] = 0.9 * m[k] + 0.1 * g; v[k] = 0.999 * v[k] + 0.001 * g * g
+        p -= (1e-2 / (1 - 0.9 ** step)) * m[k] / (np.sqrt(v[k]) / np.sqrt(1 - 0.999 ** step) + 1e-15)
+    state["step"] = step
+    return float(loss.detach()), len(ts)
+
+
+def cpu_reference(n_rays, steps, warmup):
+    """Times the oracle step on `n_rays`-ray samples of the workload.  Returns (Mrays/s, cores, seconds per step)."""
+    import numpy as np
+
+    import oracle
+    from ar_nerf_b200.workload import Workload
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    import torch
+    torch.set_num_threads(cores)
+    w = Workload("W1")
+    b = float(np.float32(np.exp(np.log(2048 * w.scale / 16) / 15)))
+    geo = oracle.HashGeometry(per_level_scale=b)
+    rng = np.random.default_rng(1337)
+    pxyz = np.concatenate([(rng.random(3072) * 2 - 1) * 0.25, (rng.random(2 * geo.total) * 2 - 1) * 1e-4]).astype(np.float32)
+    prgb = ((rng.random(7168) * 2 - 1) * 0.25).astype(np.float32)
+    state = dict(pxyz=pxyz, prgb=prgb, step=0, m={"x": np.zeros_like(pxyz), "c": np.zeros_like(prgb)},
+                 v={"x": np.zeros_like(pxyz), "c": np.zeros_like(prgb)})
+    times = []
+    for i in range(warmup + steps):
+        ro, rd, tgt, noise = [t.numpy() for t in w.train_batch(i, n_rays)]
+        t0 = time.perf_counter()
+        oracle_train_step(w, geo, state, ro, rd, tgt, noise)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_rays / sec / 1e6, cores, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_rays = 2048
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 2))
+    mrays, cores, sec = cpu_reference(sample_rays, steps, warmup)
+    sample = f"{steps} timed steps of {sample_rays} rays (1/4 of the 8192-ray batch) each, oracle/ C port with OpenMP on {cores} threads"
+    line = {"impl": "reference", "metric": "train_Mrays_per_s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from ar_nerf_b200 import _lib
+    from ar_nerf_b200.networks import NGP
+    from ar_nerf_b200.rendering import render
+    from ar_nerf_b200.trainer import NGPTrainer
+    from ar_nerf_b200.workload import Workload
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libarnerf.so has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    w = Workload("W1")
+    model = NGP(w.scale).to(dev)
+    w.install(model)
+    trainer = NGPTrainer(model)
+    # per-rank batches (weak scaling: every GPU marches its own 8192 rays); pinned host copies feed the e2e leg
+    host = [w.train_batch(i, BATCH, seed=rank) for i in range(N_BATCHES)]
+    pinned = [[t.pin_memory() for t in b[:3]] for b in host]
+    resident = [[t.to(dev) for t in b[:3]] for b in host]
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """W warm-up steps are done by the caller; times `steps` calls of fn(i) with CUDA events, max over ranks."""
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    samples_seen = []
+
+    def step_resident(i):
+        ro, rd, tgt = resident[i % N_BATCHES]
+        _, res = trainer.train_step(ro, rd, tgt)
+        samples_seen.append(res["rm_samples"])
+
+    def step_e2e(i):
+        ro, rd, tgt = [t.to(dev, non_blocking=True) for t in pinned[i % N_BATCHES]]
+        loss, _ = trainer.train_step(ro, rd, tgt)
+        return float(loss.item())  # device -> host read of the step's result
+
+    for i in range(args.warmup):
+        step_resident(i)
+    samples_seen.clear()
+    clocks = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    clk = clocks.stop() if clocks else None
+    n_samples = float(torch.stack([s.float() for s in samples_seen]).mean().item())
+    value = world * BATCH * args.steps / (ms_total * 1e-3) / 1e6
+
+    if args.train_only:
+        if rank == 0:
+            print(json.dumps({"metric": "train_Mrays_per_s", "value": value, "ms_per_step": ms_total / args.steps, "train_only": True}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3) / 1e6
+
+    # instrumented pass (not part of `value`): device time of every libarnerf.so kernel over the same steps
+    _lib.profile_enable(True)
+    timed(step_resident, args.steps)
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+
+    hbm, tf_burst, tf_sus, peak_src = read_peaks()
+    # algorithmic bytes / flops per launch (DESIGN.md "Kernels"): N = marched samples of the step
+    N = n_samples
+    model_bytes = {"hash_encode_fw_kernel": 588.0 * N, "hash_encode_bw_kernel": 588.0 * N,
+                   "composite_train_fw_kernel": 28.0 * N + 20 * BATCH, "composite_train_bw_kernel": 60.0 * N,
+                   "march_train_emit_kernel": 36.0 * N, "adam_kernel": 34.0 * (11448112 + 7168) / 2}
+    model_flops = {"field_mlp_bw_simt_kernel": 40960.0 * N, "density_mlp_fw_simt_kernel": 2 * 3072.0 * N, "rgb_mlp_fw_simt_kernel": 2 * 7168.0 * N,
+                   "field_mlp_bw_tc_kernel": 40960.0 * N, "field_fw_tc_kernel": 20480.0 * N}
+    per_step = {k: ms / args.steps for k, (c, ms) in prof.items()}
+    top = max(per_step, key=per_step.get) if per_step else None
+    roof = None
+    if top is not None:
+        calls, ms = prof[top]
+        per_launch_s = ms / calls * 1e-3
+        if top in model_flops:
+            ach = model_flops[top] / per_launch_s / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
+                    "peak_source": peak_src + " (sustained bf16)", "ms_per_launch": per_launch_s * 1e3}
+        else:
+            ach = model_bytes.get(top, 0.0) / per_launch_s / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                    "peak_source": peak_src, "ms_per_launch": per_launch_s * 1e3}
+    hash_gbs = None
+    if "hash_encode_fw_kernel" in prof:
+        c, ms = prof["hash_encode_fw_kernel"]
+        hash_gbs = 588.0 * N / (ms / c * 1e-3) / 1e9
+
+    # 800x800 test frame (configs[2]); row bands sharded across ranks, gathered on rank 0
+    from ar_nerf_b200.sharding import gather_frame, shard_rays
+    fro, frd = w.test_frame(800, 800)
+    fro, frd = shard_rays(fro, frd, rank, world)
+    fro, frd = fro.to(dev), frd.to(dev)
+
+    def frame(i):
+        r = render(model, fro, frd, test_time=True, T_threshold=1e-4)
+        gather_frame(torch.cat([r["rgb"], r["depth"][:, None], r["opacity"][:, None]], 1), 640000, rank, world)
+
+    frame(0)
+    n_frames = 3
+    fps = n_frames / (timed(frame, n_frames) * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        mrays, cores, sec = cpu_reference(2048, 3, 1)
+        cpu = {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port",
+               "sample": f"3 timed oracle steps of 2048 rays (1/4 batch), {sec:.2f} s each, OpenMP on {cores} threads"}
+
+    if rank == 0:
+        line = {"metric": "train_Mrays_per_s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": BATCH, "samples_per_step_per_gpu": N,
+                           "parallelism": f"dp{world} (rays sharded, NCCL all-reduce of hash-table + MLP gradients)",
+                           "l2_policy": "no explicit flush: one step streams ~350 MB (fp32 master + Adam moments + gradients 206 MB, activations ~140 MB) > 126 MB L2",
+                           "grid_update": "every 16 steps inside the timed region (warm-up form: all 128^3 cells)"},
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": BATCH * 36, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "frames_per_s_800x800": fps, "hash_encode_GBps": hash_gbs,
+                "kernel_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-only", action="store_true", help="profiling runs: skip the e2e, test-frame and CPU legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,11 @@ int arn_version(void);
 const char* arn_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
 int64_t arn_launch_count(void);
+/* Per-kernel device timing for bench.py's roofline numbers: while enabled, every kernel launch of this library is
+ * bracketed by CUDA events on its launch stream.  arn_profile_report synchronises, writes one "kernel calls total_ms"
+ * line per kernel into buf_host and clears the log.  Keep it disabled during CUDA-graph capture. */
+int arn_profile_enable(int on);
+int arn_profile_report(char* buf_host, int capacity);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Ray / box and ray / sphere intersection.
