@@ -61,9 +61,16 @@ def lego_boxes():
             ((0.30, -0.19, -0.24), (0.42, 0.19, -0.02))]    # bucket
 
 
+INSIDE_DENSITY = 1.0e4   # occupied cells: stays above the 5.912 threshold for ~145 decayed updates (0.95^k)
+OUTSIDE_DENSITY = -1.0   # empty cells are "invisible" cells (networks.py:247-250): update_density_grid never revives them
+
+
 def occupancy_from_boxes(boxes, cascades=1, grid_size=128, scale=0.5, shell=None, seed=0):
-    """density_grid (C, G^3) in MORTON order: 10 inside a box, 0 outside; optional sparse random shell (fraction) in
-    cascades >= 2 for the unbounded workload W3."""
+    """density_grid (C, G^3) in MORTON order: INSIDE_DENSITY inside a box, OUTSIDE_DENSITY outside; optional sparse
+    random shell (fraction) in cascades >= 2 for the unbounded workload W3.  With these two values the reference's own
+    update rule (networks.py:270-281: frozen cells < 0, EMA-max with decay 0.95, threshold min(mean, 5.912)) keeps the
+    packed occupancy exactly the boxes for a whole benchmark run, so the workload is stationary while the density-grid
+    update still executes (and is paid for) every 16 steps."""
     G = grid_size
     r = np.arange(G)
     zz, yy, xx = np.meshgrid(r, r, r, indexing='ij')
@@ -76,7 +83,7 @@ def occupancy_from_boxes(boxes, cascades=1, grid_size=128, scale=0.5, shell=None
         v = (v * np.uint32(0x00000005)) & np.uint32(0x49249249)
         return v
     morton = (expand(x) | (expand(y) << np.uint32(1)) | (expand(z) << np.uint32(2))).astype(np.int64)
-    grid = np.zeros((cascades, G ** 3), np.float32)
+    grid = np.full((cascades, G ** 3), OUTSIDE_DENSITY, np.float32)
     g = np.random.default_rng(seed)
     for c in range(cascades):
         s = min(2.0 ** (c - 1), scale)  # half extent of cascade c (networks.py:224)
@@ -88,7 +95,7 @@ def occupancy_from_boxes(boxes, cascades=1, grid_size=128, scale=0.5, shell=None
             inside |= (cx >= lo[0]) & (cx <= hi[0]) & (cy >= lo[1]) & (cy <= hi[1]) & (cz >= lo[2]) & (cz <= hi[2])
         if shell is not None and c >= 2:
             inside |= g.random(G ** 3) < shell
-        grid[c, morton[inside]] = 10.0
+        grid[c, morton[inside]] = INSIDE_DENSITY
     return torch.from_numpy(grid)
 
 

@@ -246,7 +246,9 @@ def test_composite_train_fw_bw(kind, thr, sigma_max, w1, w3, vren, ref):
                                               T(rays_a), T(o_op), T(o_dp), T(o_rgb), thr)
         o_dsig, o_drgbs = oracle.composite_train_bw(gO, gD, gC, np.zeros(Ns, np.float32) if gW is None else gW, sig, rgbs, o_ws, deltas, ts,
                                                     rays_a, o_op, o_dp, o_rgb, thr)
-        assert_rel(N(drgbs)[keep], o_drgbs[keep], what="dL_drgbs"); assert_rel(N(dsig)[keep], o_dsig[keep], what="dL_dsigmas")
+        # dL_drgbs = g * w inherits the absolute rounding floor of w (alpha = 1 - exp cancels against 1.0)
+        assert_rel(N(drgbs)[keep], o_drgbs[keep], what="dL_drgbs", atol=ALPHA_ATOL * float(np.abs(gC).max()))
+        assert_rel(N(dsig)[keep], o_dsig[keep], what="dL_dsigmas", atol=ALPHA_ATOL * float(np.abs(gC).max()) * float(deltas.max()))
     if ref is not None:
         r_total, r_op, r_dp, r_rgb, r_ws = ref.composite_train_fw(T(sig), T(rgbs), T(deltas), T(ts), T(rays_a), thr)
         same = N(total) == N(r_total)
