@@ -21,7 +21,7 @@ class Levels(C.Structure):
 
 
 class FieldWs(C.Structure):
-    _fields_ = [("feat", P), ("hid", P), ("h", P), ("in32", P), ("hid1", P), ("hid2", P)]
+    _fields_ = [("feat", P), ("hid", P), ("h", P), ("in32", P), ("hid1", P), ("hid2", P), ("wimg", P)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/arnerf.h one to one
@@ -53,6 +53,8 @@ SIGNATURES = {
     "arn_field_fw": [P, P, L, P, P, Levels, P, P, I, FieldWs, P, P, P],
     "arn_field_bw": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
     "arn_field_fw_simt": [P, P, L, P, P, Levels, P, P, I, FieldWs, P, P, P],
+    "arn_field_fw_tc": [P, P, L, P, P, Levels, P, P, I, FieldWs, P, P, P],
+    "arn_field_bw_tc": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
     "arn_field_bw_simt": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
     "arn_hash_encode_fw": [P, L, P, P, Levels, P, P, P],
     "arn_hash_encode_bw": [P, L, P, P, Levels, P, P, P, P, P],

@@ -538,17 +538,20 @@ extern "C" ARN_API int arn_adam_step(float* params, float* grads, float* exp_avg
     return check_launch("adam_step");
 }
 
-// Public entry points.  The tensor-core implementation (arn_mlp_tc.cu) takes over once it is parity-green against
-// the simt path; until then both names run the simt kernels.
+// Public entry points: the tensor-core kernels (arn_mlp_tc.cu).
+extern "C" int arn_field_fw_tc(const float*, const float*, int64_t, const float*, const float*, arn_levels_t, const void*, const void*, int,
+                               arn_field_ws_t, float*, float*, arn_stream_t);
+extern "C" int arn_field_bw_tc(const float*, int64_t, const float*, const float*, arn_levels_t, const void*, const void*, int, arn_field_ws_t,
+                               const float*, const float*, const float*, const float*, float, float*, float*, float*, float*, arn_stream_t);
 extern "C" ARN_API int arn_field_fw(const float* xyzs, const float* dirs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
                                     arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act,
                                     arn_field_ws_t ws, float* sigmas, float* rgbs, arn_stream_t stream) {
-    return arn_field_fw_simt(xyzs, dirs, n, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs, stream);
+    return arn_field_fw_tc(xyzs, dirs, n, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs, stream);
 }
 extern "C" ARN_API int arn_field_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host, arn_levels_t levels,
                                     const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
                                     const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
                                     float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream) {
-    return arn_field_bw_simt(xyzs, n, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs,
-                             dL_dsigmas, dL_drgbs, loss_scale, dfeat_scratch, grad_params_xyz, grad_params_rgb, dL_dxyzs, stream);
+    return arn_field_bw_tc(xyzs, n, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs,
+                           dL_dsigmas, dL_drgbs, loss_scale, dfeat_scratch, grad_params_xyz, grad_params_rgb, dL_dxyzs, stream);
 }

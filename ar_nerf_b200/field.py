@@ -123,14 +123,15 @@ class FieldState:
 
 def _workspace(n, device, with_rgb):
     e = lambda *s, dt=torch.float16: torch.empty(*s, dtype=dt, device=device)
-    ws = dict(feat=e(n, 32), hid=e(n, 64), h=e(n, 16, dt=torch.float32))
+    ws = dict(feat=e(n, 32), hid=e(n, 64), h=e(n, 16, dt=torch.float32), wimg=torch.empty(20480, dtype=torch.uint8, device=device))
     if with_rgb:
         ws.update(in32=e(n, 32), hid1=e(n, 64), hid2=e(n, 64))
     return ws
 
 
 def _c_ws(ws):
-    return FieldWs(ptr(ws["feat"]), ptr(ws["hid"]), ptr(ws["h"]), ptr(ws.get("in32")), ptr(ws.get("hid1")), ptr(ws.get("hid2")))
+    return FieldWs(ptr(ws["feat"]), ptr(ws["hid"]), ptr(ws["h"]), ptr(ws.get("in32")), ptr(ws.get("hid1")), ptr(ws.get("hid2")),
+                   ptr(ws["wimg"]))
 
 
 class FieldFunction(torch.autograd.Function):

@@ -176,6 +176,7 @@ typedef struct {
  * For a density-only evaluation (NGP.density) dirs, in32, hid1, hid2, rgbs and params_rgb_f16 are NULL. */
 typedef struct {
     void* feat; void* hid; float* h; void* in32; void* hid1; void* hid2;
+    void* wimg; /* 20480 B scratch: the MLP weights as swizzled tcgen05 operand tiles (rebuilt every forward) */
 } arn_field_ws_t;
 
 /* Forward.  xyzs (n,3) world coordinates, normalised inside with (x - xyz_min)/(xyz_max - xyz_min) (networks.py:104);
@@ -194,6 +195,18 @@ int arn_field_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const 
                  arn_field_ws_t ws, const float* sigmas, const float* rgbs, const float* dL_dsigmas,
                  const float* dL_drgbs, float loss_scale, float* dfeat_scratch, float* grad_params_xyz,
                  float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream);
+
+/* Tensor-core implementation behind arn_field_fw / arn_field_bw (tcgen05 + TMEM, weights by bulk TMA copy). */
+int arn_field_fw_tc(const float* xyzs, const float* dirs, int64_t n, const float* xyz_min_host,
+                    const float* xyz_max_host, arn_levels_t levels, const void* params_xyz_f16,
+                    const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws, float* sigmas, float* rgbs,
+                    arn_stream_t stream);
+
+int arn_field_bw_tc(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                    arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act,
+                    arn_field_ws_t ws, const float* sigmas, const float* rgbs, const float* dL_dsigmas,
+                    const float* dL_drgbs, float loss_scale, float* dfeat_scratch, float* grad_params_xyz,
+                    float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream);
 
 /* CUDA-core ("simt") implementation of the same two calls: operation order identical to oracle/oracle_field.c, kept
  * as the on-device cross-check of the tensor-core path (tests only; same arguments as arn_field_fw / arn_field_bw). */

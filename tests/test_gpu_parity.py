@@ -354,7 +354,9 @@ def test_field_forward(impl, scale, n, vren):
     assert torch.equal(sig, sig2)
     if impl == "_simt":  # same operation order as the oracle: features, hidden activations and h are bit-identical
         assert np.array_equal(N(h).view(np.uint32), ctx["h"].view(np.uint32))
-    assert_rel(N(h), ctx["h"], rtol=2e-3 if impl == "" else 1e-6, what="h")
+    # tensor-core path: accumulation order differs inside the MMA and a hidden activation may flip one fp16 ulp, which moves
+    # h by ~1e-4 absolute whatever its size -> measured against max|h| (floor=1.0)
+    assert_rel(N(h), ctx["h"], rtol=2e-3 if impl == "" else 1e-6, floor=1.0 if impl == "" else REL_FLOOR, what="h")
     assert_rel(N(sig), ctx["sigma"], rtol=5e-3 if impl == "" else 1e-5, what="sigma")
     np.testing.assert_allclose(N(rgb), ctx["rgb"], atol=2e-3 if impl == "" else 1e-6)
 

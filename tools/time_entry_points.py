@@ -31,12 +31,13 @@ def main():
         _, res = tr.train_step(*batches[i][:3], noise=batches[i][3], update_grid=False)
     e1.record(); torch.cuda.synchronize()
     print(f"train step (no grid update, not instrumented): {e0.elapsed_time(e1) / 5:.3f} ms, samples/step {int(res['rm_samples'])}")
-    _lib.TIMING = {}
+    _lib.profile_enable(True)
     for i in range(3, 8):
         tr.train_step(*batches[i][:3], noise=batches[i][3], update_grid=False)
-    s = _lib.timing_summary(); _lib.TIMING = None
+    s = _lib.profile_report(); _lib.profile_enable(False)
     for k, (n, ms) in sorted(s.items(), key=lambda kv: -kv[1][1]):
-        print(f"  {k:28s} calls/step {n / 5:5.1f}  ms/step {ms / 5:8.4f}")
+        print(f"  {k:30s} launches/step {n / 5:5.1f}  us/step {ms / 5 * 1e3:9.2f}")
+    print(f"  kernel total us/step {sum(ms for _, ms in s.values()) / 5 * 1e3:.1f}")
     _lib.TIMING = {}
     model.update_density_grid(5.912, warmup=True)
     s = _lib.timing_summary(); _lib.TIMING = None
