@@ -24,6 +24,21 @@ class FieldWs(C.Structure):
     _fields_ = [("feat", P), ("hid", P), ("h", P), ("in32", P), ("hid1", P), ("hid2", P), ("wimg", P)]
 
 
+class TrainCfg(C.Structure):
+    """Mirror of arn_train_t (include/arnerf.h) -- field order and types must match exactly."""
+    _fields_ = [("rays_o", P), ("rays_d", P), ("rgb_target", P), ("noise", P), ("n_rays", L),
+                ("density_bitfield", P), ("cascades", I), ("grid_size", I), ("scale", F), ("exp_step_factor", F), ("max_samples", I),
+                ("T_threshold", F), ("near", F),
+                ("center_host", P), ("half_size_host", P), ("xyz_min_host", P), ("xyz_max_host", P),
+                ("levels", Levels), ("params_xyz_f16", P), ("params_rgb_f16", P), ("rgb_act", I),
+                ("bg_host", P), ("lambda_opacity", F), ("lambda_depth", F), ("grad_scale", F), ("loss_scale", F),
+                ("hits_t", P), ("rays_a", P), ("counter", P), ("t_scratch", P), ("total_samples", P),
+                ("opacity", P), ("depth", P), ("rgb", P), ("rgb_final", P), ("dL_dopacity", P), ("dL_ddepth", P), ("dL_drgb", P),
+                ("capacity", L), ("xyzs", P), ("dirs", P), ("deltas", P), ("ts", P), ("sigmas", P), ("rgbs", P), ("ws_out", P),
+                ("dL_dsigmas", P), ("dL_drgbs", P), ("dfeat", P), ("ws", FieldWs),
+                ("grad_xyz", P), ("grad_rgb", P), ("loss_out", P)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/arnerf.h one to one
 SIGNATURES = {
     "arn_version": [],
@@ -55,6 +70,13 @@ SIGNATURES = {
     "arn_field_fw_simt": [P, P, L, P, P, Levels, P, P, I, FieldWs, P, P, P],
     "arn_field_fw_tc": [P, P, L, P, P, Levels, P, P, I, FieldWs, P, P, P],
     "arn_field_bw_tc": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
+    "arn_field_fw_tc_dyn": [P, P, L, P, P, P, Levels, P, P, I, FieldWs, P, P, P],
+    "arn_field_bw_tc_dyn": [P, L, P, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
+    "arn_hash_encode_fw_dyn": [P, L, P, P, P, Levels, P, P, P],
+    "arn_hash_encode_bw_dyn": [P, L, P, P, P, Levels, P, P, P, P, P],
+    "arn_march_train_emit_dyn": [P, P, L, I, I, F, F, I, P, P, P, P, P, P, P, L, P],
+    "arn_nerf_loss": [P, P, P, P, L, P, F, F, F, F, P, P, P, P, P, P],
+    "arn_train_fwbw": [C.POINTER(TrainCfg), P],
     "arn_field_bw_simt": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
     "arn_hash_encode_fw": [P, L, P, P, Levels, P, P, P],
     "arn_hash_encode_bw": [P, L, P, P, Levels, P, P, P, P, P],

@@ -24,12 +24,12 @@ __global__ void __launch_bounds__(256) cast_f32_f16_kernel(const float* __restri
 
 // ------------------------------------------------------------------------------------------------ hash grid
 // Forward, one thread per (sample, level) -- SURVEY Appendix A.3.
-__global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __restrict__ xyzs, int64_t n, Aabb box,
+__global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                              const __grid_constant__ LevelTable tbl,
                                                              const __half2* __restrict__ table, __half2* __restrict__ feat) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = min(n, (int64_t)*n_dev);
     const int l = blockIdx.y;
-    if (i >= n) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float w[3]; uint32_t g[3];
     level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
     const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
@@ -41,17 +41,18 @@ __global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __rest
         acc0 = __fmaf_rn(wt, v.x, acc0); acc1 = __fmaf_rn(wt, v.y, acc1);
     }
     feat[i * ARN_N_LEVELS + l] = __floats2half2_rn(acc0, acc1);
+    }
 }
 
 // Backward into the table, one thread per (sample, level): vector red.global.add.v2.f32 per corner.
-__global__ void __launch_bounds__(256) hash_encode_bw_kernel(const float* __restrict__ xyzs, int64_t n, Aabb box,
+__global__ void __launch_bounds__(256) hash_encode_bw_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                              const __grid_constant__ LevelTable tbl,
                                                              const float2* __restrict__ dfeat, float2* __restrict__ table_grad) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = min(n, (int64_t)*n_dev);
     const int l = blockIdx.y;
-    if (i >= n) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float2 d = dfeat[i * ARN_N_LEVELS + l];
-    if (d.x == 0.0f && d.y == 0.0f) return;
+    if (d.x == 0.0f && d.y == 0.0f) continue;
     float w[3]; uint32_t g[3];
     level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
     const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(256) hash_encode_bw_kernel(const float* __rest
     for (int c = 0; c < 8; c++) {
         uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
         atomicAdd(table_grad + off + grid_index(size, res, p), make_float2(wt * d.x, wt * d.y));
+    }
     }
 }
 
@@ -433,22 +435,37 @@ int make_box(const float* mn, const float* mx, Aabb& b) {
 }
 }  // namespace arn
 
-extern "C" ARN_API int arn_hash_encode_fw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
-                                  arn_levels_t levels, const void* table_f16, void* feat_f16, arn_stream_t stream) {
+extern "C" int arn_hash_encode_bw_dyn(const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const float*, float*,
+                                      float*, arn_stream_t);
+namespace arn {
+// n is the count (n_dev == nullptr) or the capacity with the real count read on the device from *n_dev (fused step).
+inline int sample_grid(int64_t n, const int32_t* n_dev) { return n_dev ? (int)min((int64_t)148 * 8, (n + 255) / 256) : ceil_div(n, 256); }
+}
+extern "C" ARN_API int arn_hash_encode_fw_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                                      arn_levels_t levels, const void* table_f16, void* feat_f16, arn_stream_t stream) {
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(xyzs && table_f16 && feat_f16, "null pointer");
     LevelTable t; Aabb b;
     if (int e = make_levels(levels, t)) return e;
     if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
-    dim3 grid(ceil_div(n, 256), ARN_N_LEVELS);
-    ARN_LAUNCH("hash_encode_fw_kernel", (cudaStream_t)stream, hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, b, t, (const __half2*)table_f16, (__half2*)feat_f16));
+    dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS);
+    ARN_LAUNCH("hash_encode_fw_kernel", (cudaStream_t)stream, hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, n_dev, b, t, (const __half2*)table_f16, (__half2*)feat_f16));
     return check_launch("hash_encode_fw");
+}
+extern "C" ARN_API int arn_hash_encode_fw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
+                                  arn_levels_t levels, const void* table_f16, void* feat_f16, arn_stream_t stream) {
+    return arn_hash_encode_fw_dyn(xyzs, n, nullptr, xyz_min_host, xyz_max_host, levels, table_f16, feat_f16, stream);
 }
 
 extern "C" ARN_API int arn_hash_encode_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
                                   arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad,
                                   float* dL_dxyzs, arn_stream_t stream) {
+    return arn_hash_encode_bw_dyn(xyzs, n, nullptr, xyz_min_host, xyz_max_host, levels, table_f16, dfeat, table_grad, dL_dxyzs, stream);
+}
+extern "C" ARN_API int arn_hash_encode_bw_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                                      arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad,
+                                      float* dL_dxyzs, arn_stream_t stream) {
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(xyzs && dfeat, "null pointer");
@@ -457,12 +474,12 @@ extern "C" ARN_API int arn_hash_encode_bw(const float* xyzs, int64_t n, const fl
     if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     if (table_grad) {
-        dim3 grid(ceil_div(n, 256), ARN_N_LEVELS);
-        ARN_LAUNCH("hash_encode_bw_kernel", st, hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, b, t, (const float2*)dfeat, (float2*)table_grad));
+        dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS);
+        ARN_LAUNCH("hash_encode_bw_kernel", st, hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad));
         if (int e = check_launch("hash_encode_bw")) return e;
     }
     if (dL_dxyzs) {
-        ARN_REQUIRE(table_f16, "dL_dxyzs needs the table");
+        ARN_REQUIRE(table_f16 && !n_dev, "dL_dxyzs needs the table and a host-side count");
         ARN_LAUNCH("hash_encode_dx_kernel", st, hash_encode_dx_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xyzs, n, b, t, (const __half2*)table_f16, (const float2*)dfeat, dL_dxyzs));
         if (int e = check_launch("hash_encode_dx")) return e;
     }
@@ -554,4 +571,101 @@ extern "C" ARN_API int arn_field_bw(const float* xyzs, int64_t n, const float* x
                                     float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream) {
     return arn_field_bw_tc(xyzs, n, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs,
                            dL_dsigmas, dL_drgbs, loss_scale, dfeat_scratch, grad_params_xyz, grad_params_rgb, dL_dxyzs, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Hash-grid backward, run-aggregating form.  Samples arrive ordered along their rays, so at the coarse levels dozens of
+// consecutive samples fall into the same cell and hit the same 8 table entries.  One thread walks a segment of SEG
+// consecutive samples of ONE level, keeps the 8 corner gradients of the current cell in registers and issues the
+// red.global.add.v2.f32 only when the cell changes.  Lane%16 = level: a half-warp reads one full 128-byte dfeat row per step.
+namespace arn {
+constexpr int kBwSeg = 32;
+__global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
+                                                                  const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
+                                                                  float2* __restrict__ table_grad, int level0, int nlevels) {
+    if (n_dev) n = min(n, (int64_t)*n_dev);
+    const int l = (threadIdx.x & 15);
+    const int64_t n_seg = (n + kBwSeg - 1) / kBwSeg;
+    const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
+    const float scale = tbl.scale[l];
+    const bool active = l >= level0 && l < level0 + nlevels;
+    for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; seg < n_seg; seg += ((int64_t)gridDim.x * blockDim.x) >> 4) {
+        if (!active) continue;
+        const int64_t i0 = seg * kBwSeg, i1 = min(n, i0 + kBwSeg);
+        uint32_t cg[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+        float2 acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[c] = make_float2(0.f, 0.f);
+        bool dirty = false;
+        for (int64_t i = i0; i < i1; i++) {
+            const float2 d = dfeat[i * ARN_N_LEVELS + l];
+            float w[3]; uint32_t g[3];
+            level_position(xyzs + 3 * i, box, scale, w, g);
+            if (g[0] != cg[0] || g[1] != cg[1] || g[2] != cg[2]) {
+                if (dirty) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const uint32_t p[3] = {cg[0] + (c & 1), cg[1] + ((c >> 1) & 1), cg[2] + ((c >> 2) & 1)};
+                        atomicAdd(table_grad + off + grid_index(size, res, p), acc[c]);
+                        acc[c] = make_float2(0.f, 0.f);
+                    }
+                    dirty = false;
+                }
+                cg[0] = g[0]; cg[1] = g[1]; cg[2] = g[2];
+            }
+            if (d.x != 0.0f || d.y != 0.0f) {
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
+                    acc[c].x += wt * d.x; acc[c].y += wt * d.y;
+                }
+                dirty = true;
+            }
+        }
+        if (dirty) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint32_t p[3] = {cg[0] + (c & 1), cg[1] + ((c >> 1) & 1), cg[2] + ((c >> 2) & 1)};
+                atomicAdd(table_grad + off + grid_index(size, res, p), acc[c]);
+            }
+        }
+    }
+}
+
+// level-range form of the per-(sample, level) kernel, for the split below and for diagnostics
+__global__ void __launch_bounds__(256) hash_encode_bw_range_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
+                                                                   const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
+                                                                   float2* __restrict__ table_grad, int level0) {
+    if (n_dev) n = min(n, (int64_t)*n_dev);
+    const int l = blockIdx.y + level0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 d = dfeat[i * ARN_N_LEVELS + l];
+        if (d.x == 0.0f && d.y == 0.0f) continue;
+        float w[3]; uint32_t g[3];
+        level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
+        const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
+            atomicAdd(table_grad + off + grid_index(size, res, p), make_float2(wt * d.x, wt * d.y));
+        }
+    }
+}
+}  // namespace arn
+
+// Diagnostics entry (tools/): mode 0 = per-(sample,level) kernel on levels [level0, level0+nlevels), mode 1 = run-aggregating kernel.
+extern "C" ARN_API int arn_dbg_hash_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host, arn_levels_t levels,
+                                       const float* dfeat, float* table_grad, int level0, int nlevels, int mode, arn_stream_t stream) {
+    LevelTable t; Aabb b;
+    if (int e = make_levels(levels, t)) return e;
+    if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) {
+        dim3 grid(ceil_div(n, 256), nlevels);
+        ARN_LAUNCH("hash_encode_bw_range_kernel", st, hash_encode_bw_range_kernel<<<grid, 256, 0, st>>>(xyzs, n, nullptr, b, t, (const float2*)dfeat, (float2*)table_grad, level0));
+    } else {
+        const int64_t threads = ((n + kBwSeg - 1) / kBwSeg) * 16;
+        ARN_LAUNCH("hash_encode_bw_runs_kernel", st, hash_encode_bw_runs_kernel<<<ceil_div(threads, 256), 256, 0, st>>>(xyzs, n, nullptr, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels));
+    }
+    return check_launch("dbg_hash_bw");
 }

@@ -58,13 +58,14 @@ constexpr int kFwSmemTile64 = 128 * 128;   // 128 rows x 64 halves
 constexpr int kFwSmemBytes = kWimgBytes + kFwSmemTile32 + kFwSmemTile64 + 1024;  // + alignment slack
 
 __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __restrict__ feat, const float* __restrict__ dirs, int64_t n,
-                                                              const uint8_t* __restrict__ wimg, int rgb_act, int with_rgb,
+                                                              const int32_t* __restrict__ n_dev, const uint8_t* __restrict__ wimg, int rgb_act, int with_rgb,
                                                               __half* __restrict__ hid, float* __restrict__ h, float* __restrict__ sigmas,
                                                               __half* __restrict__ in32, __half* __restrict__ hid1, __half* __restrict__ hid2,
                                                               float* __restrict__ rgbs) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
+    if (n_dev) n = min(n, (int64_t)*n_dev);  // fused step: the sample count lives on the device
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzled tiles need 1024-byte alignment
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sW = base, sT32 = base + kWimgBytes, sT64 = sT32 + kFwSmemTile32;
@@ -190,9 +191,23 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
 
 using namespace arn;
 
+extern "C" int arn_field_fw_tc_dyn(const float*, const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const void*,
+                                   int, arn_field_ws_t, float*, float*, arn_stream_t);
+extern "C" int arn_field_bw_tc_dyn(const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const void*, int,
+                                   arn_field_ws_t, const float*, const float*, const float*, const float*, float, float*, float*, float*, float*, arn_stream_t);
+extern "C" int arn_hash_encode_fw_dyn(const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, void*, arn_stream_t);
+extern "C" int arn_hash_encode_bw_dyn(const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const float*, float*,
+                                      float*, arn_stream_t);
+
 extern "C" ARN_API int arn_field_fw_tc(const float* xyzs, const float* dirs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
                                        arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act,
                                        arn_field_ws_t ws, float* sigmas, float* rgbs, arn_stream_t stream) {
+    return arn_field_fw_tc_dyn(xyzs, dirs, n, nullptr, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs, stream);
+}
+// n_dev != NULL: n is the capacity of the buffers and the sample count is read on the device (fused training step).
+extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs, int64_t n, const int32_t* n_dev, const float* xyz_min_host,
+                                           const float* xyz_max_host, arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16,
+                                           int rgb_act, arn_field_ws_t ws, float* sigmas, float* rgbs, arn_stream_t stream) {
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(xyzs && params_xyz_f16 && ws.feat && ws.hid && ws.h && ws.wimg && sigmas, "null pointer");
@@ -200,7 +215,7 @@ extern "C" ARN_API int arn_field_fw_tc(const float* xyzs, const float* dirs, int
     if (with_rgb) ARN_REQUIRE(params_rgb_f16 && ws.in32 && ws.hid1 && ws.hid2 && rgbs, "null pointer (colour branch)");
     cudaStream_t st = (cudaStream_t)stream;
     const __half* pxyz = (const __half*)params_xyz_f16;
-    if (int e = arn_hash_encode_fw(xyzs, n, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, stream)) return e;
+    if (int e = arn_hash_encode_fw_dyn(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, stream)) return e;
     ARN_LAUNCH("pack_mlp_weights_kernel", st, pack_mlp_weights_kernel<<<5, 256, 0, st>>>(pxyz, (const __half*)params_rgb_f16, (uint8_t*)ws.wimg));
     if (int e = check_launch("pack_mlp_weights")) return e;
     static int n_sm = 0;
@@ -211,7 +226,7 @@ extern "C" ARN_API int arn_field_fw_tc(const float* xyzs, const float* dirs, int
     const int64_t n_tiles = (n + 127) / 128;
     const int grid = (int)(n_tiles < (int64_t)n_sm * 4 ? n_tiles : (int64_t)n_sm * 4);
     ARN_LAUNCH("field_mlp_fw_tc_kernel", st, field_mlp_fw_tc_kernel<<<grid, 128, kFwSmemBytes, st>>>(
-        (const __half*)ws.feat, dirs, n, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, (__half*)ws.hid, ws.h, sigmas,
+        (const __half*)ws.feat, dirs, n, n_dev, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, (__half*)ws.hid, ws.h, sigmas,
         (__half*)ws.in32, (__half*)ws.hid1, (__half*)ws.hid2, rgbs));
     return check_launch("field_mlp_fw_tc");
 }
@@ -261,7 +276,7 @@ __device__ __forceinline__ void epilogue_mask64(uint32_t taddr, const uint8_t* x
     }
 }
 
-__global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
+__global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const int32_t* __restrict__ n_dev, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
                                                               const float* __restrict__ rgbs, const float* __restrict__ h,
                                                               const __half* __restrict__ feat, const __half* __restrict__ hid,
                                                               const __half* __restrict__ in32, const __half* __restrict__ hid1,
@@ -271,6 +286,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const f
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
+    if (n_dev) n = min(n, (int64_t)*n_dev);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sW = base, sGa = base + kWimgBytes, sGb = sGa + kFwSmemTile64, sX = sGb + kFwSmemTile64;
@@ -426,6 +442,13 @@ extern "C" ARN_API int arn_field_bw_tc(const float* xyzs, int64_t n, const float
                                        const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
                                        const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
                                        float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream) {
+    return arn_field_bw_tc_dyn(xyzs, n, nullptr, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs, dL_dsigmas,
+                               dL_drgbs, loss_scale, dfeat_scratch, grad_params_xyz, grad_params_rgb, dL_dxyzs, stream);
+}
+extern "C" ARN_API int arn_field_bw_tc_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                                           arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
+                                           const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
+                                           float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream) {
     (void)sigmas;
     ARN_REQUIRE(n >= 0 && loss_scale > 0, "bad size / loss_scale");
     if (n == 0) return ARN_OK;
@@ -446,10 +469,10 @@ extern "C" ARN_API int arn_field_bw_tc(const float* xyzs, int64_t n, const float
     const int64_t n_tiles = (n + 127) / 128;
     const int grid = (int)(n_tiles < (int64_t)n_sm * 2 ? n_tiles : (int64_t)n_sm * 2);
     ARN_LAUNCH("field_mlp_bw_tc_kernel", st, arn::field_mlp_bw_tc_kernel<<<grid, 128, arn::kBwSmemBytes, st>>>(
-        n, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, ws.h, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32,
+        n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, ws.h, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32,
         (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, grad_params_xyz,
         grad_params_rgb, dfeat_scratch));
     if (int e = check_launch("field_mlp_bw_tc")) return e;
-    return arn_hash_encode_bw(xyzs, n, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
-                              grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, stream);
+    return arn_hash_encode_bw_dyn(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
+                                  grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, stream);
 }

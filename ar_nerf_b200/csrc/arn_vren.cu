@@ -201,10 +201,11 @@ __global__ void __launch_bounds__(1024) rays_scan_kernel(int64_t* __restrict__ r
 __global__ void __launch_bounds__(256) march_train_emit_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                                int64_t n_rays, ArnMarchConsts c, const int64_t* __restrict__ rays_a,
                                                                const float* __restrict__ t_scratch, int64_t total,
+                                                               const int32_t* __restrict__ total_dev,
                                                                float* __restrict__ xyzs, float* __restrict__ dirs,
                                                                float* __restrict__ deltas, float* __restrict__ ts) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= total) return;
+    if (total_dev) total = min(total, (int64_t)*total_dev);  // device-side count (fused step): `total` is the capacity
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (int64_t)gridDim.x * blockDim.x) {
     // largest r with start[r] <= s and N[r] > 0 : starts are non-decreasing, so search the last start <= s
     int64_t lo = 0, hi = n_rays - 1;
     while (lo < hi) {
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(256) march_train_emit_kernel(const float* __re
     xyzs[3 * s] = __fmaf_rn(dx, t, ox); xyzs[3 * s + 1] = __fmaf_rn(dy, t, oy); xyzs[3 * s + 2] = __fmaf_rn(dz, t, oz);
     dirs[3 * s] = dx; dirs[3 * s + 1] = dy; dirs[3 * s + 2] = dz;
     ts[s] = t; deltas[s] = arn_calc_dt(c, t);
+    }
 }
 
 // Pass 2, re-march form (raymarching.cu:236-279), used when the caller gives no t scratch.
@@ -617,12 +619,28 @@ extern "C" ARN_API int arn_march_train_emit_ex(const float* rays_o, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
     if (t_scratch) {
-        ARN_LAUNCH("march_train_emit_kernel", st, march_train_emit_kernel<<<ceil_div(capacity, 256), 256, 0, st>>>(rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, xyzs, dirs, deltas, ts));
+        ARN_LAUNCH("march_train_emit_kernel", st, march_train_emit_kernel<<<ceil_div(capacity, 256), 256, 0, st>>>(rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, nullptr, xyzs, dirs, deltas, ts));
         return check_launch("march_train_emit");
     }
     ARN_LAUNCH("march_train_remarch_kernel", st, march_train_remarch_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, xyzs, dirs, deltas, ts));
     return check_launch("march_train_remarch");
 }
+// Device-count form used by the fused training step: `capacity` bounds the outputs, the real count is counter[0].
+extern "C" ARN_API int arn_march_train_emit_dyn(const float* rays_o, const float* rays_d, int64_t n_rays, int cascades, int grid_size, float scale,
+                                                float exp_step_factor, int max_samples, const int64_t* rays_a, const float* t_scratch,
+                                                const int32_t* counter, float* xyzs, float* dirs, float* deltas, float* ts, int64_t capacity,
+                                                arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0 && capacity >= 0, "bad size");
+    if (int e = check_march_cfg(cascades, grid_size, max_samples)) return e;
+    if (n_rays == 0 || capacity == 0) return ARN_OK;
+    ARN_REQUIRE(rays_o && rays_d && rays_a && t_scratch && counter && xyzs && dirs && deltas && ts, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
+    const int grid = (int)min((int64_t)148 * 16, (capacity + 255) / 256);
+    ARN_LAUNCH("march_train_emit_kernel", st, march_train_emit_kernel<<<grid, 256, 0, st>>>(rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, counter, xyzs, dirs, deltas, ts));
+    return check_launch("march_train_emit_dyn");
+}
+
 extern "C" ARN_API int arn_march_train_emit(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
                                     const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
                                     float exp_step_factor, const float* noise, int max_samples, const int64_t* rays_a,

@@ -5,15 +5,16 @@ hash-table + MLP gradients are summed with one NCCL all-reduce per step (SURVEY 
 Step = density-grid update every 16 steps (train.py:175-178) -> render(train) -> NeRFLoss -> backward ->
 gradient all-reduce -> fused Adam (lr 1e-2, eps 1e-15, train.py:146) with fp16 working-copy refresh.
 """
+import ctypes as C
 import math
 
 import torch
 import torch.distributed as dist
 
 from . import _lib
-from ._lib import call, ptr, stream
+from ._lib import FieldWs, TrainCfg, call, ptr, stream
 from .losses import NeRFLoss
-from .rendering import MAX_SAMPLES, render
+from .rendering import MAX_SAMPLES, NEAR_DISTANCE, render
 
 
 class FusedAdam:
@@ -40,11 +41,41 @@ class FusedAdam:
                 cache.mark_fresh(p)
 
 
+class _FusedWorkspace:
+    """Device buffers of the fused step (arn_train_fwbw), allocated once: per-ray tensors for `n_rays`, per-sample
+    tensors for `capacity` samples (n_rays * max_samples can never overflow)."""
+
+    def __init__(self, n_rays, capacity, device):
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+        h = lambda *s: torch.empty(*s, dtype=torch.float16, device=device)
+        R, N = n_rays, capacity
+        self.n_rays, self.capacity = R, N
+        self.hits_t, self.rays_a = f(R, 1, 2), torch.empty(R, 3, dtype=torch.int64, device=device)
+        self.counter = torch.zeros(2, dtype=torch.int32, device=device)
+        self.t_scratch = f(R * MAX_SAMPLES)
+        self.total_samples = torch.empty(R, dtype=torch.int64, device=device)
+        self.opacity, self.depth, self.rgb, self.rgb_final = f(R), f(R), f(R, 3), f(R, 3)
+        self.dL_dopacity, self.dL_ddepth, self.dL_drgb = f(R), f(R), f(R, 3)
+        self.xyzs, self.dirs, self.deltas, self.ts = f(N, 3), f(N, 3), f(N), f(N)
+        self.sigmas, self.rgbs, self.ws_out = f(N), f(N, 3), f(N)
+        self.dL_dsigmas, self.dL_drgbs, self.dfeat = f(N), f(N, 3), f(N, 32)
+        self.feat, self.hid, self.h = h(N, 32), h(N, 64), f(N, 16)
+        self.in32, self.hid1, self.hid2 = h(N, 32), h(N, 64), h(N, 64)
+        self.wimg = torch.empty(20480, dtype=torch.uint8, device=device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=device)
+
+
 class NGPTrainer:
     def __init__(self, model, lr=1e-2, num_epochs=30, steps_per_epoch=1000, loss_func='raw', depth_loss_w=0.0,
-                 distortion_loss_w=0.0, exp_step_factor=None, random_bg=False, grad_scale=128.0,
-                 update_interval=16, warmup_steps=256):
+                 distortion_loss_w=0.0, exp_step_factor=None, random_bg=False, grad_scale=1.0,
+                 update_interval=16, warmup_steps=256, fused=True, sample_capacity=None):
         self.model = model
+        # the fused native step covers the default training configuration (train.py defaults: 'raw' loss, no distortion
+        # loss, fixed background); anything else runs the eager render() + autograd path
+        self.fused = fused and loss_func == 'raw' and distortion_loss_w == 0 and not random_bg and model.rgb_act == 'Sigmoid'
+        self.loss_func, self.depth_loss_w = loss_func, depth_loss_w
+        self.sample_capacity = sample_capacity
+        self._ws = None
         self.exp_step_factor = (1 / 256 if model.scale > 0.5 else 0.0) if exp_step_factor is None else exp_step_factor
         self.random_bg = random_bg
         self.loss = NeRFLoss(num_epochs, loss_func, model.scale, depth_loss_w, lambda_distortion=distortion_loss_w)
@@ -63,10 +94,53 @@ class NGPTrainer:
         eta_min = self.base_lr / 30
         return eta_min + (self.base_lr - eta_min) * (1 + math.cos(math.pi * e / self.num_epochs)) / 2
 
+    def _fused_fwbw(self, rays_o, rays_d, rgb_target, noise):
+        m, st = self.model, self.model.field_state
+        R, dev = rays_o.shape[0], rays_o.device
+        if self._ws is None or self._ws.n_rays != R:
+            self._ws = _FusedWorkspace(R, self.sample_capacity or R * MAX_SAMPLES, dev)
+        w = self._ws
+        center, half = m.host_box()
+        if noise is None:
+            noise = torch.rand(R, device=dev)  # the draw RayMarcher.forward makes (custom_functions.py:83)
+        self._keep = (rays_o.contiguous().float(), rays_d.contiguous().float(), rgb_target.contiguous().float(), noise.contiguous().float())
+        ro, rd, tgt, nz = self._keep
+        bgv = 1.0 if self.exp_step_factor == 0 else 0.0
+        self._host = ((C.c_float * 3)(*center), (C.c_float * 3)(*half), (C.c_float * 3)(bgv, bgv, bgv))
+        p16x = st.cache_xyz.get(m.xyz_encoder.params); p16c = st.cache_rgb.get(m.rgb_net.params)
+        cast = lambda a: C.cast(a, C.c_void_p)
+        cfg = TrainCfg(
+            ptr(ro), ptr(rd), ptr(tgt), ptr(nz), R,
+            ptr(m.density_bitfield), m.cascades, m.grid_size, float(m.scale), float(self.exp_step_factor), MAX_SAMPLES, 1e-4, NEAR_DISTANCE,
+            cast(self._host[0]), cast(self._host[1]), cast(st.mn), cast(st.mx),
+            st.geometry.c_levels, ptr(p16x), ptr(p16c), st.rgb_act,
+            cast(self._host[2]), float(self.loss.lambda_opacity), float(self.depth_loss_w), float(self.grad_scale), float(st.loss_scale),
+            ptr(w.hits_t), ptr(w.rays_a), ptr(w.counter), ptr(w.t_scratch), ptr(w.total_samples),
+            ptr(w.opacity), ptr(w.depth), ptr(w.rgb), ptr(w.rgb_final), ptr(w.dL_dopacity), ptr(w.dL_ddepth), ptr(w.dL_drgb),
+            w.capacity, ptr(w.xyzs), ptr(w.dirs), ptr(w.deltas), ptr(w.ts), ptr(w.sigmas), ptr(w.rgbs), ptr(w.ws_out),
+            ptr(w.dL_dsigmas), ptr(w.dL_drgbs), ptr(w.dfeat),
+            FieldWs(ptr(w.feat), ptr(w.hid), ptr(w.h), ptr(w.in32), ptr(w.hid1), ptr(w.hid2), ptr(w.wimg)),
+            ptr(m.xyz_encoder.params.grad), ptr(m.rgb_net.params.grad), ptr(w.loss))
+        call("arn_train_fwbw", C.byref(cfg), stream())
+        # views into the reused workspace (valid until the next step); per-sample buffers hold counter[0] samples
+        results = {'rgb': w.rgb_final, 'opacity': w.opacity, 'depth': w.depth, 'rm_samples': w.counter[0].clone(),
+                   'rays_a': w.rays_a, 'total_samples_per_ray': w.total_samples, 'ts_buf': w.ts, 'deltas_buf': w.deltas,
+                   'ws_buf': w.ws_out}
+        return w.loss[0].clone(), results
+
     def train_step(self, rays_o, rays_d, rgb_target, noise=None, update_grid=True):
         m = self.model
         if update_grid and self.global_step % self.update_interval == 0:
             m.update_density_grid(0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=self.global_step < self.warmup_steps)
+        if self.fused:
+            loss, results = self._fused_fwbw(rays_o, rays_d, rgb_target, noise)
+            if self.world > 1:
+                for p, _, _, _ in self.opt.items:
+                    dist.all_reduce(p.grad)
+            self.opt.lr = self.lr_at(self.global_step)
+            self.opt.step(inv_grad_scale=1.0 / (self.grad_scale * self.world))
+            self.global_step += 1
+            return loss, results
         kwargs = {'test_time': False, 'random_bg': self.random_bg, 'exp_step_factor': self.exp_step_factor}
         if noise is not None:
             kwargs['noise'] = noise

@@ -229,6 +229,61 @@ int arn_hash_encode_bw(const float* xyzs, int64_t n, const float* xyz_min_host, 
 int arn_sh4(const float* dirs, int64_t n, void* out_f16, arn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Fused training step (forward + loss + backward of one batch of rays in ONE host call, no host synchronisation).
+ * Replaces, for the trainer, the Python sequence of train.py:174-198 / rendering.py:255-298 / losses.py:63-82:
+ *   render(train) -> NeRFLoss('raw' rgb + opacity entropy [+ depth]) -> backward.
+ * The marched sample count never leaves the device: per-sample buffers are sized by `capacity` (n_rays*max_samples is
+ * always enough) and the kernels read the count from counter[0].  Gradients are ACCUMULATED into grad_xyz / grad_rgb;
+ * the caller all-reduces them (N > 1) and calls arn_adam_step.  Results match the eager path (tests/test_gpu_parity.py).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    /* batch (device) */
+    const float* rays_o; const float* rays_d; const float* rgb_target; const float* noise; int64_t n_rays;
+    /* scene / model */
+    const uint8_t* density_bitfield; int cascades; int grid_size; float scale; float exp_step_factor; int max_samples;
+    float T_threshold; float near;
+    const float* center_host; const float* half_size_host; const float* xyz_min_host; const float* xyz_max_host;
+    arn_levels_t levels; const void* params_xyz_f16; const void* params_rgb_f16; int rgb_act;
+    /* loss (losses.py:41-82, 'raw') and scaling */
+    const float* bg_host; float lambda_opacity; float lambda_depth; float grad_scale; float loss_scale;
+    /* workspace (device), per ray */
+    float* hits_t; int64_t* rays_a; int32_t* counter; float* t_scratch; int64_t* total_samples;
+    float* opacity; float* depth; float* rgb; float* rgb_final; float* dL_dopacity; float* dL_ddepth; float* dL_drgb;
+    /* workspace (device), per sample, `capacity` entries */
+    int64_t capacity; float* xyzs; float* dirs; float* deltas; float* ts; float* sigmas; float* rgbs; float* ws_out;
+    float* dL_dsigmas; float* dL_drgbs; float* dfeat; arn_field_ws_t ws;
+    /* outputs */
+    float* grad_xyz; float* grad_rgb; float* loss_out;
+} arn_train_t;
+int arn_train_fwbw(const arn_train_t* cfg_host, arn_stream_t stream);
+/* The loss kernel on its own (per-ray rgb/opacity/depth -> scalar loss + gradients; bg_host = 3 floats). */
+int arn_nerf_loss(const float* rgb, const float* opacity, const float* depth, const float* target, int64_t n_rays,
+                  const float* bg_host, float lambda_opacity, float lambda_depth, float grid_scale, float grad_scale,
+                  float* rgb_out, float* dL_drgb, float* dL_dopacity, float* dL_ddepth, float* loss_out,
+                  arn_stream_t stream);
+/* Device-count forms (n = capacity, real count read from *n_dev) of the per-sample entry points. */
+int arn_march_train_emit_dyn(const float* rays_o, const float* rays_d, int64_t n_rays, int cascades, int grid_size,
+                             float scale, float exp_step_factor, int max_samples, const int64_t* rays_a,
+                             const float* t_scratch, const int32_t* counter, float* xyzs, float* dirs, float* deltas,
+                             float* ts, int64_t capacity, arn_stream_t stream);
+int arn_hash_encode_fw_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host,
+                           const float* xyz_max_host, arn_levels_t levels, const void* table_f16, void* feat_f16,
+                           arn_stream_t stream);
+int arn_hash_encode_bw_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host,
+                           const float* xyz_max_host, arn_levels_t levels, const void* table_f16, const float* dfeat,
+                           float* table_grad, float* dL_dxyzs, arn_stream_t stream);
+int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs, int64_t n, const int32_t* n_dev, const float* xyz_min_host,
+                        const float* xyz_max_host, arn_levels_t levels, const void* params_xyz_f16,
+                        const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws, float* sigmas, float* rgbs,
+                        arn_stream_t stream);
+int arn_field_bw_tc_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host,
+                        const float* xyz_max_host, arn_levels_t levels, const void* params_xyz_f16,
+                        const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws, const float* sigmas,
+                        const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
+                        float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs,
+                        arn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Optimizer step.  Replaces apex FusedAdam(lr, betas=(0.9,0.999), eps=1e-15, weight_decay=0) (train.py:146).
  * One fused pass: Adam update of the fp32 master, optional un-scaling of the gradient by inv_grad_scale, refresh of
  * the fp16 working copy (dst_f16 may be NULL), and zeroing of the gradient for the next step (zero_grad != 0).

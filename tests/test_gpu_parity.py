@@ -476,6 +476,61 @@ def test_render_train_end_to_end(kind, impl, w1, w3):
     assert_rel(N(model.xyz_encoder.params.grad)[3072:], o_gx[3072:], rtol=gtol, floor=1.0, what="hash table grad")
 
 
+@pytest.mark.parametrize("kind", ["W1", "W3"])
+def test_fused_train_step_matches_eager(kind, w1, w3):
+    """arn_train_fwbw (one native call, device-side sample count) against render() + NeRFLoss + autograd on the same batch:
+    identical samples (bit-exact), same loss and gradients; then one Adam step keeps both models in lockstep."""
+    from ar_nerf_b200.trainer import NGPTrainer
+    w = workload(kind, w1, w3)
+    model_a, *_ = _field_setup(w.scale, 8, 31, table_amp=1.0)
+    model_b, *_ = _field_setup(w.scale, 8, 31, table_amp=1.0)  # same seed -> same parameters
+    w.install(model_a); w.install(model_b)
+    assert torch.equal(model_a.xyz_encoder.params, model_b.xyz_encoder.params)
+    ta = NGPTrainer(model_a, fused=True); tb = NGPTrainer(model_b, fused=False)
+    assert ta.fused and not tb.fused
+    ro, rd, target, noise = [T(t) for t in w.train_batch(9, 4096)]
+    loss_a, res_a = ta._fused_fwbw(ro, rd, target, noise)
+    from ar_nerf_b200.rendering import render
+    res_b = render(model_b, ro, rd, test_time=False, exp_step_factor=w.exp_step_factor, noise=noise)
+    loss_b = sum(l.mean() for l in tb.loss(res_b, {"rgb": target}).values())
+    loss_b.backward()
+    n = int(res_a["rm_samples"])
+    assert n == int(res_b["rm_samples"]) and torch.equal(res_a["rays_a"], res_b["rays_a"])
+    assert torch.equal(res_a["ts_buf"][:n], res_b["ts"]) and torch.equal(res_a["deltas_buf"][:n], res_b["deltas"])
+    assert_rel(N(res_a["rgb"]), N(res_b["rgb"]), rtol=1e-5, what="rgb"); assert_rel(N(res_a["opacity"]), N(res_b["opacity"]), rtol=1e-5, what="opacity")
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * abs(float(loss_b))
+    for pa, pb, name in ((model_a.xyz_encoder.params, model_b.xyz_encoder.params, "xyz"), (model_a.rgb_net.params, model_b.rgb_net.params, "rgb")):
+        assert_rel(N(pa.grad), N(pb.grad), rtol=2e-4, floor=1.0, what=f"grad {name}")
+    # full steps (with Adam) stay in lockstep
+    for step in range(3):
+        b = [T(t) for t in w.train_batch(20 + step, 4096)]
+        la, _ = ta.train_step(*b[:3], noise=b[3], update_grid=False)
+        lb, _ = tb.train_step(*b[:3], noise=b[3], update_grid=False)
+        assert abs(float(la) - float(lb)) <= 2e-3 * abs(float(lb)), (step, float(la), float(lb))
+
+
+def test_nerf_loss_kernel_vs_autograd():
+    from ar_nerf_b200 import _lib
+    from ar_nerf_b200.losses import NeRFLoss
+    g = torch.Generator(device="cuda").manual_seed(3)
+    R = 5000
+    rgb = torch.rand(R, 3, device=dev(), generator=g) * 0.7; op = torch.rand(R, device=dev(), generator=g); op[::7] = 0
+    depth = torch.rand(R, device=dev(), generator=g) * 2; tgt = torch.rand(R, 3, device=dev(), generator=g)
+    for bgv, ld in ((1.0, 0.0), (0.0, 0.01)):
+        bg = (_lib.F * 3)(bgv, bgv, bgv)
+        outs = [torch.empty(R, 3, device=dev()), torch.empty(R, 3, device=dev()), torch.empty(R, device=dev()), torch.empty(R, device=dev()), torch.zeros(1, device=dev())]
+        _lib.call("arn_nerf_loss", rgb.data_ptr(), op.data_ptr(), depth.data_ptr(), tgt.data_ptr(), R, bg, 1e-3, ld, 0.5, 2.0,
+                  *[o.data_ptr() for o in outs], _lib.stream())
+        r_, o_, d_ = rgb.clone().requires_grad_(True), op.clone().requires_grad_(True), depth.clone().requires_grad_(True)
+        final = r_ + bgv * (1 - o_)[:, None]
+        loss = sum(l.mean() for l in NeRFLoss(30, 'raw', 0.5, ld, lambda_distortion=0)({"rgb": final, "opacity": o_, "depth": d_}, {"rgb": tgt}).values())
+        (loss * 2.0).backward()
+        assert abs(float(outs[4]) - float(loss)) <= 1e-5 * abs(float(loss))
+        assert_rel(N(outs[0]), N(final), rtol=1e-6, what="rgb_final")
+        assert_rel(N(outs[1]), N(r_.grad), rtol=1e-4, what="dL_drgb"); assert_rel(N(outs[2]), N(o_.grad), rtol=1e-4, what="dL_dopacity")
+        assert_rel(N(outs[3]), N(d_.grad), rtol=1e-4, what="dL_ddepth")
+
+
 def test_render_test_end_to_end(w1):
     """rendering.render(test_time=True): the iterative march/composite loop against the same loop driven by the oracle."""
     from ar_nerf_b200.rendering import render
