@@ -44,6 +44,7 @@ SIGNATURES = {
     "arn_version": [],
     "arn_last_error": [],
     "arn_launch_count": [],
+    "arn_set_tunable": [C.c_char_p, I],
     "arn_profile_enable": [I],
     "arn_profile_report": [C.c_char_p, I],
     "arn_ray_aabb_intersect": [P, P, L, P, P, I, I, P, P, P, P],
@@ -133,6 +134,11 @@ def timing_summary():
 
 def launch_count():
     return int(lib().arn_launch_count())
+
+
+def set_tunable(name, value):
+    """Select a kernel variant (include/arnerf.h: arn_set_tunable); all variants compute the same results."""
+    call("arn_set_tunable", name.encode(), int(value))
 
 
 def profile_enable(on=True):

@@ -22,6 +22,10 @@ struct LaunchTimer {
     const char* name_; cudaStream_t st_; void* slot_;
 };
 
+// Kernel-variant switches for A/B measurements (arn_set_tunable): every variant computes the same results.
+enum Tunable { kTunMarchWarp = 0, kTunHashBwMode, kTunAdamVec, kTunCount };
+int tunable(Tunable t);
+
 inline int check_launch(const char* what) {
     count_launch();
     cudaError_t e = cudaGetLastError();

@@ -3,6 +3,7 @@
 #include <map>
 #include <mutex>
 #include <stdarg.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -18,6 +19,11 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- kernel-variant switches
+static std::atomic<int> g_tun[kTunCount] = {{1}, {32}, {1}};
+static const char* const g_tun_names[kTunCount] = {"march_warp", "hash_bw_mode", "adam_vec"};
+int tunable(Tunable t) { return g_tun[t].load(std::memory_order_relaxed); }
 
 // ---- per-kernel timing
 struct TimedLaunch { const char* name; cudaEvent_t e0, e1; };
@@ -67,6 +73,13 @@ extern "C" ARN_API int arn_profile_report(char* buf, int cap) {
         off += n;
     }
     return ARN_OK;
+}
+
+extern "C" ARN_API int arn_set_tunable(const char* name, int value) {
+    for (int i = 0; name && i < arn::kTunCount; i++)
+        if (!strcmp(name, arn::g_tun_names[i])) { arn::g_tun[i].store(value); return ARN_OK; }
+    arn::set_error("arn_set_tunable: unknown tunable '%s'", name ? name : "(null)");
+    return ARN_E_INVALID;
 }
 
 extern "C" ARN_API int arn_version(void) { return ARN_VERSION; }

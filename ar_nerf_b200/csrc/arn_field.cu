@@ -96,6 +96,82 @@ __global__ void __launch_bounds__(256) hash_encode_dx_kernel(const float* __rest
     dL_dxyzs[3 * i + 2] = gx[2] / (box.mx[2] - box.mn[2]);
 }
 
+// Hash-grid backward, run-aggregating form.  Samples arrive ordered along their rays, so at the coarse and middle levels
+// several consecutive samples fall into the same cell and hit the same 8 table entries.  One thread walks a segment of
+// SEG consecutive samples of ONE level, keeps the 8 corner gradients of the current cell in registers and issues the
+// red.global.add.v2.f32 only when the cell changes.  lane % 16 = level: a half-warp reads one full 128-byte dfeat row
+// per step and the xyz loads are broadcasts.  (Sums are re-associated relative to the per-sample kernel: same tolerance.)
+template <int SEG>
+__global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
+                                                                  const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
+                                                                  float2* __restrict__ table_grad, int level0, int nlevels) {
+    if (n_dev) n = min(n, (int64_t)*n_dev);
+    const int l = (threadIdx.x & 15);
+    const int64_t n_seg = (n + SEG - 1) / SEG;
+    const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
+    const float scale = tbl.scale[l];
+    const bool active = l >= level0 && l < level0 + nlevels;
+    for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; seg < n_seg; seg += ((int64_t)gridDim.x * blockDim.x) >> 4) {
+        if (!active) continue;
+        const int64_t i0 = seg * SEG, i1 = min(n, i0 + SEG);
+        uint32_t cg[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+        float2 acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[c] = make_float2(0.f, 0.f);
+        bool dirty = false;
+        for (int64_t i = i0; i < i1; i++) {
+            const float2 d = dfeat[i * ARN_N_LEVELS + l];
+            float w[3]; uint32_t g[3];
+            level_position(xyzs + 3 * i, box, scale, w, g);
+            if (g[0] != cg[0] || g[1] != cg[1] || g[2] != cg[2]) {
+                if (dirty) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const uint32_t p[3] = {cg[0] + (c & 1), cg[1] + ((c >> 1) & 1), cg[2] + ((c >> 2) & 1)};
+                        atomicAdd(table_grad + off + grid_index(size, res, p), acc[c]);
+                        acc[c] = make_float2(0.f, 0.f);
+                    }
+                    dirty = false;
+                }
+                cg[0] = g[0]; cg[1] = g[1]; cg[2] = g[2];
+            }
+            if (d.x != 0.0f || d.y != 0.0f) {
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
+                    acc[c].x += wt * d.x; acc[c].y += wt * d.y;
+                }
+                dirty = true;
+            }
+        }
+        if (dirty) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint32_t p[3] = {cg[0] + (c & 1), cg[1] + ((c >> 1) & 1), cg[2] + ((c >> 2) & 1)};
+                atomicAdd(table_grad + off + grid_index(size, res, p), acc[c]);
+            }
+        }
+    }
+}
+
+template <int SEG>
+static int launch_hash_bw_runs(const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
+                               float* table_grad, int level0, int nlevels, cudaStream_t st) {
+    const int64_t threads = ((n + SEG - 1) / SEG) * 16;
+    const int grid = (int)min((int64_t)148 * 8, (threads + 255) / 256);
+    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, hash_encode_bw_runs_kernel<SEG><<<grid, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels));
+    return check_launch("hash_encode_bw_runs");
+}
+static int hash_bw_runs(int seg, const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
+                        float* table_grad, int level0, int nlevels, cudaStream_t st) {
+    switch (seg) {
+        case 8: return launch_hash_bw_runs<8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, st);
+        case 16: return launch_hash_bw_runs<16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, st);
+        case 64: return launch_hash_bw_runs<64>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, st);
+        default: return launch_hash_bw_runs<32>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, st);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ SH-4
 __global__ void __launch_bounds__(256) sh4_kernel(const float* __restrict__ dirs, int64_t n, __half* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,6 +459,42 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
     if (p16) p16[i] = __float2half_rn(np);
 }
 
+// 128-bit form: one thread updates 4 consecutive parameters (float4 loads/stores of p, g, m, v; 64-bit store of the fp16
+// copy).  Same arithmetic per element as adam_kernel.  Requires 16-byte aligned pointers (8 for p16) and n % 4 == 0.
+__global__ void __launch_bounds__(256) adam_vec4_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                                                        uint2* __restrict__ p16, int64_t n4, float lr, float b1, float b2, float eps,
+                                                        float bc1, float bc2_sqrt, float inv_gs, int zero_grad) {
+    const float step_size = lr / bc1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 g4 = g[i]; const float4 m4 = m[i]; const float4 v4 = v[i];
+        if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float gr[4] = {g4.x * inv_gs, g4.y * inv_gs, g4.z * inv_gs, g4.w * inv_gs};
+        const float mo[4] = {m4.x, m4.y, m4.z, m4.w}, vo[4] = {v4.x, v4.y, v4.z, v4.w};
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) any |= !(gr[k] == 0.0f && mo[k] == 0.0f && vo[k] == 0.0f);
+        if (!any) continue;  // four untouched hash entries: the update is exactly zero
+        const float4 p4 = p[i];
+        float pn[4] = {p4.x, p4.y, p4.z, p4.w}, mn[4], vn[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            mn[k] = mo[k]; vn[k] = vo[k];
+            if (gr[k] == 0.0f && mo[k] == 0.0f && vo[k] == 0.0f) continue;
+            mn[k] = b1 * mo[k] + (1.0f - b1) * gr[k];
+            vn[k] = b2 * vo[k] + (1.0f - b2) * gr[k] * gr[k];
+            const float denom = sqrtf(vn[k]) / bc2_sqrt + eps;
+            pn[k] = pn[k] - step_size * (mn[k] / denom);
+        }
+        m[i] = make_float4(mn[0], mn[1], mn[2], mn[3]); v[i] = make_float4(vn[0], vn[1], vn[2], vn[3]);
+        p[i] = make_float4(pn[0], pn[1], pn[2], pn[3]);
+        if (p16) {
+            const __half2 a = __floats2half2_rn(pn[0], pn[1]), b = __floats2half2_rn(pn[2], pn[3]);
+            uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+            p16[i] = o;
+        }
+    }
+}
+
 }  // namespace arn
 
 using namespace arn;
@@ -474,9 +586,14 @@ extern "C" ARN_API int arn_hash_encode_bw_dyn(const float* xyzs, int64_t n, cons
     if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     if (table_grad) {
-        dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS);
-        ARN_LAUNCH("hash_encode_bw_kernel", st, hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad));
-        if (int e = check_launch("hash_encode_bw")) return e;
+        const int mode = tunable(kTunHashBwMode);  // 0: one reduction per (sample, level, corner); else: run-aggregating, segment length
+        if (mode) {
+            if (int e = hash_bw_runs(mode, xyzs, n, n_dev, b, t, dfeat, table_grad, 0, ARN_N_LEVELS, st)) return e;
+        } else {
+            dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS);
+            ARN_LAUNCH("hash_encode_bw_kernel", st, hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad));
+            if (int e = check_launch("hash_encode_bw")) return e;
+        }
     }
     if (dL_dxyzs) {
         ARN_REQUIRE(table_f16 && !n_dev, "dL_dxyzs needs the table and a host-side count");
@@ -550,8 +667,17 @@ extern "C" ARN_API int arn_adam_step(float* params, float* grads, float* exp_avg
     ARN_REQUIRE(params && grads && exp_avg && exp_avg_sq, "null pointer");
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-    ARN_LAUNCH("adam_kernel", (cudaStream_t)stream, adam_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (__half*)dst_f16, n, lr, beta1, beta2,
-                                                                  eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0 && ((uintptr_t)dst_f16 & 7) == 0;
+    if (tunable(kTunAdamVec) && aligned && n % 4 == 0 && n >= 4096) {
+        const int64_t n4 = n / 4;
+        const int grid = (int)min((int64_t)148 * 16, (n4 + 255) / 256);
+        ARN_LAUNCH("adam_vec4_kernel", st, adam_vec4_kernel<<<grid, 256, 0, st>>>((float4*)params, (float4*)grads, (float4*)exp_avg, (float4*)exp_avg_sq, (uint2*)dst_f16, n4,
+                                                                                  lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad));
+    } else {
+        ARN_LAUNCH("adam_kernel", st, adam_kernel<<<ceil_div(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)dst_f16, n, lr, beta1, beta2,
+                                                                                     eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad));
+    }
     return check_launch("adam_step");
 }
 
@@ -574,65 +700,8 @@ extern "C" ARN_API int arn_field_bw(const float* xyzs, int64_t n, const float* x
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Hash-grid backward, run-aggregating form.  Samples arrive ordered along their rays, so at the coarse levels dozens of
-// consecutive samples fall into the same cell and hit the same 8 table entries.  One thread walks a segment of SEG
-// consecutive samples of ONE level, keeps the 8 corner gradients of the current cell in registers and issues the
-// red.global.add.v2.f32 only when the cell changes.  Lane%16 = level: a half-warp reads one full 128-byte dfeat row per step.
 namespace arn {
-constexpr int kBwSeg = 32;
-__global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
-                                                                  const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
-                                                                  float2* __restrict__ table_grad, int level0, int nlevels) {
-    if (n_dev) n = min(n, (int64_t)*n_dev);
-    const int l = (threadIdx.x & 15);
-    const int64_t n_seg = (n + kBwSeg - 1) / kBwSeg;
-    const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
-    const float scale = tbl.scale[l];
-    const bool active = l >= level0 && l < level0 + nlevels;
-    for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; seg < n_seg; seg += ((int64_t)gridDim.x * blockDim.x) >> 4) {
-        if (!active) continue;
-        const int64_t i0 = seg * kBwSeg, i1 = min(n, i0 + kBwSeg);
-        uint32_t cg[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
-        float2 acc[8];
-#pragma unroll
-        for (int c = 0; c < 8; c++) acc[c] = make_float2(0.f, 0.f);
-        bool dirty = false;
-        for (int64_t i = i0; i < i1; i++) {
-            const float2 d = dfeat[i * ARN_N_LEVELS + l];
-            float w[3]; uint32_t g[3];
-            level_position(xyzs + 3 * i, box, scale, w, g);
-            if (g[0] != cg[0] || g[1] != cg[1] || g[2] != cg[2]) {
-                if (dirty) {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        const uint32_t p[3] = {cg[0] + (c & 1), cg[1] + ((c >> 1) & 1), cg[2] + ((c >> 2) & 1)};
-                        atomicAdd(table_grad + off + grid_index(size, res, p), acc[c]);
-                        acc[c] = make_float2(0.f, 0.f);
-                    }
-                    dirty = false;
-                }
-                cg[0] = g[0]; cg[1] = g[1]; cg[2] = g[2];
-            }
-            if (d.x != 0.0f || d.y != 0.0f) {
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
-                    acc[c].x += wt * d.x; acc[c].y += wt * d.y;
-                }
-                dirty = true;
-            }
-        }
-        if (dirty) {
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const uint32_t p[3] = {cg[0] + (c & 1), cg[1] + ((c >> 1) & 1), cg[2] + ((c >> 2) & 1)};
-                atomicAdd(table_grad + off + grid_index(size, res, p), acc[c]);
-            }
-        }
-    }
-}
-
-// level-range form of the per-(sample, level) kernel, for the split below and for diagnostics
+// level-range form of the per-(sample, level) kernel, for diagnostics
 __global__ void __launch_bounds__(256) hash_encode_bw_range_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                                    const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
                                                                    float2* __restrict__ table_grad, int level0) {
@@ -653,7 +722,8 @@ __global__ void __launch_bounds__(256) hash_encode_bw_range_kernel(const float* 
 }
 }  // namespace arn
 
-// Diagnostics entry (tools/): mode 0 = per-(sample,level) kernel on levels [level0, level0+nlevels), mode 1 = run-aggregating kernel.
+// Diagnostics entry (tools/): mode 0 = per-(sample,level) kernel on levels [level0, level0+nlevels), mode = 8/16/32/64 = run-aggregating
+// kernel with that segment length.
 extern "C" ARN_API int arn_dbg_hash_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host, arn_levels_t levels,
                                        const float* dfeat, float* table_grad, int level0, int nlevels, int mode, arn_stream_t stream) {
     LevelTable t; Aabb b;
@@ -663,9 +733,7 @@ extern "C" ARN_API int arn_dbg_hash_bw(const float* xyzs, int64_t n, const float
     if (mode == 0) {
         dim3 grid(ceil_div(n, 256), nlevels);
         ARN_LAUNCH("hash_encode_bw_range_kernel", st, hash_encode_bw_range_kernel<<<grid, 256, 0, st>>>(xyzs, n, nullptr, b, t, (const float2*)dfeat, (float2*)table_grad, level0));
-    } else {
-        const int64_t threads = ((n + kBwSeg - 1) / kBwSeg) * 16;
-        ARN_LAUNCH("hash_encode_bw_runs_kernel", st, hash_encode_bw_runs_kernel<<<ceil_div(threads, 256), 256, 0, st>>>(xyzs, n, nullptr, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels));
+        return check_launch("dbg_hash_bw");
     }
-    return check_launch("dbg_hash_bw");
+    return hash_bw_runs(mode, xyzs, n, nullptr, b, t, dfeat, table_grad, level0, nlevels, st);
 }

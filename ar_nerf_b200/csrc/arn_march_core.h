@@ -113,11 +113,10 @@ ARN_HD float arn_jitter_start(const ArnMarchConsts& c, float t1, float noise) {
     return t1;
 }
 
-// One evaluation of the loop body at parameter t (raymarching.cu:205-232).
-// Occupied: returns true, t unchanged (caller records the sample and does t += dt).
-// Empty:    returns false, t advanced by the reference's do/while skip.
-ARN_HD bool arn_march_eval(const ArnMarchConsts& c, const ArnRay& r, const uint8_t* __restrict__ bitfield, float& t,
-                           float& x, float& y, float& z, float& dt) {
+// One probe of the loop body at parameter t (raymarching.cu:205-229): position, step, occupancy of the cell that holds
+// o + t*d and -- for an empty cell -- the parameter t_target up to which the reference's skip loop advances.
+ARN_HD bool arn_march_probe(const ArnMarchConsts& c, const ArnRay& r, const uint8_t* __restrict__ bitfield, float t,
+                            float& x, float& y, float& z, float& dt, float& t_target) {
     x = ARN_FMA(r.dx, t, r.ox); y = ARN_FMA(r.dy, t, r.oy); z = ARN_FMA(r.dz, t, r.oz);
     dt = arn_calc_dt(c, t);
     // mip_from_pos (:19-23) / mip_from_dt (:29-32)
@@ -137,13 +136,39 @@ ARN_HD bool arn_march_eval(const ArnMarchConsts& c, const ArnRay& r, const uint8
     // :219-220
     const uint32_t idx = (uint32_t)mip * c.grid_size3 + arn_morton3d((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
     const bool occ = (bitfield[idx >> 3] >> (idx & 7u)) & 1u;
-    if (occ) return true;
+    if (occ) { t_target = t; return true; }
     // :225-227
     const float tx = ARN_MUL(ARN_FMA(mip_bound, ARN_FMA(ARN_MUL(ARN_FMA(r.sx, 0.5f, ARN_ADD((float)nx, 0.5f)), c.Ginv), 2.0f, -1.0f), -x), r.dxi);
     const float ty = ARN_MUL(ARN_FMA(mip_bound, ARN_FMA(ARN_MUL(ARN_FMA(r.sy, 0.5f, ARN_ADD((float)ny, 0.5f)), c.Ginv), 2.0f, -1.0f), -y), r.dyi);
     const float tz = ARN_MUL(ARN_FMA(mip_bound, ARN_FMA(ARN_MUL(ARN_FMA(r.sz, 0.5f, ARN_ADD((float)nz, 0.5f)), c.Ginv), 2.0f, -1.0f), -z), r.dzi);
-    // :229-232
-    const float t_target = ARN_ADD(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    // :229
+    t_target = ARN_ADD(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    return false;
+}
+
+// One evaluation of the loop body at parameter t (raymarching.cu:205-232).
+// Occupied: returns true, t unchanged (caller records the sample and does t += dt).
+// Empty:    returns false, t advanced by the reference's do/while skip (:230-232).
+ARN_HD bool arn_march_eval(const ArnMarchConsts& c, const ArnRay& r, const uint8_t* __restrict__ bitfield, float& t,
+                           float& x, float& y, float& z, float& dt) {
+    float t_target;
+    if (arn_march_probe(c, r, bitfield, t, x, y, z, dt, t_target)) return true;
     do { t = ARN_ADD(t, arn_calc_dt(c, t)); } while (t < t_target);
     return false;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Window form of the train march (warp-cooperative kernel, arn_vren.cu).
+//
+// Every advance of the reference loop -- the occupied step `t += dt` and each turn of the skip loop -- is the same map
+// t -> t + calc_dt(t), so the parameters the loop can ever visit form ONE chain t_0 = t1, t_{k+1} = t_k + calc_dt(t_k)
+// that does not depend on the occupancy grid; the grid only selects WHICH chain points are visited:
+//   visit k, occupied  -> sample, next visit k+1
+//   visit k, empty     -> next visit = first k' > k with t_{k'} >= t_target(k)
+// A warp therefore takes 32 consecutive chain points at a time (lane j builds t_{k0+j} by j sequential steps, so every
+// value is the reference's own rounding sequence), probes all 32 cells at once, turns the rule above into a "next"
+// pointer per lane (binary search over the monotone chain), finds the visited lanes by pointer doubling from the first
+// lane, and compacts the occupied visited lanes with ballot/popc.  A skip that leaves the window is carried into the
+// next window as `pending` (chain points below it are passed over).  Counts and sample parameters are bit-identical
+// with the one-thread-per-ray loop; tests/test_host_march.py runs a lane-by-lane host emulation of exactly this
+// procedure (tests/host_march_harness.cpp) against the oracle.

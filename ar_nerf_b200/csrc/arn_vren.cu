@@ -161,37 +161,117 @@ __global__ void __launch_bounds__(128) march_train_count_kernel(const float* __r
     rays_a[3 * r + 2] = N;
 }
 
-// Exclusive scan of the counts: rays_a[r] = (r, start, N); counter = (total, n_rays).  Single CTA, chunked.
+// Pass 1, warp-cooperative form (arn_march_core.h, "Window form"): one WARP per ray, 32 chain points per turn,
+// ballot/popc compaction of the occupied visited points into t_scratch.  Same counts and t values as the kernel above.
+template <bool CONST_DT>
+__global__ void __launch_bounds__(256) march_train_count_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                                     const float* __restrict__ hits_t, int64_t n_rays,
+                                                                     const uint8_t* __restrict__ bitfield, ArnMarchConsts c,
+                                                                     const float* __restrict__ noise, int64_t* __restrict__ rays_a,
+                                                                     float* __restrict__ t_scratch) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;  // warp-uniform
+    const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
+    const float t1 = arn_jitter_start(c, hits_t[2 * r], noise[r]);
+    const float t2 = hits_t[2 * r + 1];
+    float* rec = t_scratch ? t_scratch + r * c.max_samples : nullptr;
+    int N = 0;
+    if (0 <= t1 && t1 < t2) {
+        float base = t1;            // chain point of lane 0
+        float pending = -INFINITY;  // skip target carried over from the previous window
+        for (;;) {
+            // lane j <- j steps along the chain from `base`
+            float t = base;
+#pragma unroll
+            for (int j = 0; j < 31; j++) {
+                const float tn = __fadd_rn(t, CONST_DT ? c.dt_lo : arn_calc_dt(c, t));
+                if (lane > j) t = tn;
+            }
+            float x, y, z, dt, tgt;
+            const bool occ = arn_march_probe(c, ray, bitfield, t, x, y, z, dt, tgt);
+            const unsigned valid = __ballot_sync(kFull, t < t2);  // a prefix: the chain is increasing
+            const unsigned occm = __ballot_sync(kFull, occ);
+            const int s0 = __popc(__ballot_sync(kFull, t < pending));  // first lane not passed over by the carried skip
+            // next visit after this lane: first k > lane with t_k >= tgt (32: beyond the window); occupied: lane + 1
+            int lo = lane + 1, hi = 32;
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (lo + hi) >> 1;
+                const float tv = __shfl_sync(kFull, t, mid & 31);
+                if (lo < hi) { if (tv < tgt) lo = mid + 1; else hi = mid; }
+            }
+            int R = occ ? lane + 1 : lo;
+            // lanes reachable from s0 along the next pointers (pointer doubling)
+            unsigned M = 1u << lane;
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const unsigned Mo = __shfl_sync(kFull, M, R & 31);
+                const int Ro = __shfl_sync(kFull, R, R & 31);
+                if (R < 32) { M |= Mo; R = Ro; }
+            }
+            const unsigned vis = s0 < 32 ? __shfl_sync(kFull, M, s0 & 31) : 0u;
+            unsigned emit = vis & occm & valid;
+            const int rem = c.max_samples - N;
+            bool done = valid != kFull;
+            if (__popc(emit) >= rem) {  // the sample budget ends the march inside this window
+                done = true;
+                const int rank_all = __popc(emit & ((1u << lane) - 1u));
+                emit = __ballot_sync(kFull, ((emit >> lane) & 1u) && rank_all < rem);
+            }
+            if (rec && ((emit >> lane) & 1u)) rec[N + __popc(emit & ((1u << lane) - 1u))] = t;
+            N += __popc(emit);
+            if (done) break;
+            // carry: the last visited lane either is lane 31 and occupied, or is empty with a target beyond the window
+            if (vis) {
+                const int last = 31 - __clz(vis);
+                pending = __shfl_sync(kFull, occ ? -INFINITY : tgt, last);
+            }
+            const float t31 = __shfl_sync(kFull, t, 31);
+            base = __fadd_rn(t31, CONST_DT ? c.dt_lo : arn_calc_dt(c, t31));
+        }
+    }
+    if (lane == 0) rays_a[3 * r + 2] = N;
+}
+
+// Exclusive scan of the counts: rays_a[r] = (r, start, N); counter = (total, n_rays).  Single CTA: thread i owns the
+// K = ceil(n_rays/1024) consecutive rays [i*K, (i+1)*K) (K independent loads in flight), one block scan of the
+// per-thread totals, one pass of stores.
 __global__ void __launch_bounds__(1024) rays_scan_kernel(int64_t* __restrict__ rays_a, int64_t n_rays, int32_t* __restrict__ counter) {
     __shared__ int64_t warp_sums[32];
-    __shared__ int64_t carry_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    const int64_t K = (n_rays + blockDim.x - 1) / blockDim.x;
+    const int64_t r0 = min(n_rays, (int64_t)threadIdx.x * K), r1 = min(n_rays, r0 + K);
+    int64_t mine = 0;
+    if (K <= 8) {
+        int64_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (r0 + k < r1) ? rays_a[3 * (r0 + k) + 2] : 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) mine += v[k];
+    } else {
+        for (int64_t r = r0; r < r1; r++) mine += rays_a[3 * r + 2];
+    }
+    int64_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) warp_sums[wid] = inc;
     __syncthreads();
-    for (int64_t base = 0; base < n_rays; base += blockDim.x) {
-        const int64_t r = base + threadIdx.x;
-        const int64_t v = r < n_rays ? rays_a[3 * r + 2] : 0;
-        int64_t inc = v;
+    if (wid == 0) {
+        int64_t s = warp_sums[lane];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += u; }
-        if (lane == 31) warp_sums[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            int64_t s = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, s, o); if (lane >= o) s += u; }
-            warp_sums[lane] = s;  // inclusive over warps
-        }
-        __syncthreads();
-        const int64_t carry = carry_s;
-        const int64_t start = carry + (wid ? warp_sums[wid - 1] : 0) + inc - v;
-        if (r < n_rays) { rays_a[3 * r] = r; rays_a[3 * r + 1] = start; }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + warp_sums[31];
-        __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, s, o); if (lane >= o) s += u; }
+        warp_sums[lane] = s;  // inclusive over warps
+    }
+    __syncthreads();
+    int64_t start = (wid ? warp_sums[wid - 1] : 0) + inc - mine;
+    for (int64_t r = r0; r < r1; r++) {
+        const int64_t nr = rays_a[3 * r + 2];
+        rays_a[3 * r] = r; rays_a[3 * r + 1] = start;
+        start += nr;
     }
     if (threadIdx.x == 0) {
-        const int64_t tot = carry_s;
+        const int64_t tot = warp_sums[31];
         counter[0] = (int32_t)(tot > 0x7fffffff ? 0x7fffffff : tot);
         counter[1] = (int32_t)(n_rays > 0x7fffffff ? 0x7fffffff : n_rays);
     }
@@ -594,7 +674,13 @@ extern "C" ARN_API int arn_march_train_count_ex(const float* rays_o, const float
     if (n_rays == 0) { ARN_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int32_t), st)); return ARN_OK; }
     ARN_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && noise && rays_a, "null pointer");
     const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
-    ARN_LAUNCH("march_train_count_kernel", st, march_train_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch));
+    if (!tunable(kTunMarchWarp)) {
+        ARN_LAUNCH("march_train_count_kernel", st, march_train_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch));
+    } else if (exp_step_factor == 0.0f && c.dt_hi >= 0.0f) {  // calc_dt is the constant dt_lo
+        ARN_LAUNCH("march_train_count_warp_kernel", st, march_train_count_warp_kernel<true><<<ceil_div(n_rays * 32, 256), 256, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch));
+    } else {
+        ARN_LAUNCH("march_train_count_warp_kernel", st, march_train_count_warp_kernel<false><<<ceil_div(n_rays * 32, 256), 256, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch));
+    }
     if (int e = check_launch("march_train_count")) return e;
     ARN_LAUNCH("rays_scan_kernel", st, rays_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, counter));
     return check_launch("rays_scan");

@@ -39,6 +39,11 @@ int64_t arn_launch_count(void);
 /* Per-kernel device timing for bench.py's roofline numbers: while enabled, every kernel launch of this library is
  * bracketed by CUDA events on its launch stream.  arn_profile_report synchronises, writes one "kernel calls total_ms"
  * line per kernel into buf_host and clears the log.  Keep it disabled during CUDA-graph capture. */
+/* Kernel-variant switch for A/B measurements and for the tests that hold the variants to each other; every variant of
+ * a kernel computes the same results.  Names: "march_warp" (1 = warp-per-ray window march, 0 = thread-per-ray loop),
+ * "hash_bw_mode" (8/16/32/64 = run-aggregating hash-grid backward with that segment length, 0 = one reduction per
+ * sample and corner), "adam_vec" (1 = 128-bit Adam kernel). */
+int arn_set_tunable(const char* name, int value);
 int arn_profile_enable(int on);
 int arn_profile_report(char* buf_host, int capacity);
 

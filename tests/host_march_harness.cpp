@@ -42,3 +42,65 @@ extern "C" void h_march_test(int n_alive, const float* o, const float* d, float*
 }
 
 extern "C" int h_frexp_exponent(float x) { return arn_frexp_exponent(x); }
+
+// Lane-by-lane emulation of march_train_count_warp_kernel (arn_vren.cu): same window procedure, the warp primitives
+// (ballot, shfl) replaced by loops over 32-entry arrays.
+static inline int popc32(uint32_t v) { return __builtin_popcount(v); }
+extern "C" void h_march_train_window(int n_rays, const float* o, const float* d, const float* hits_t, const uint8_t* bits, int cascades,
+                                     int grid, float scale, float esf, const float* noise, int max_samples, int32_t* counts,
+                                     float* t_rec /* n_rays*max_samples */) {
+    const ArnMarchConsts c = arn_march_consts(cascades, grid, scale, scale, esf, max_samples);
+    for (int r = 0; r < n_rays; r++) {
+        const ArnRay ray = arn_load_ray(o + 3 * r, d + 3 * r);
+        const float t1 = arn_jitter_start(c, hits_t[2 * r], noise[r]);
+        const float t2 = hits_t[2 * r + 1];
+        float* rec = t_rec + (size_t)r * max_samples;
+        int N = 0;
+        if (0 <= t1 && t1 < t2) {
+            float base = t1, pending = -INFINITY;
+            for (;;) {
+                float t[32], tgt[32]; bool occ[32]; int R[32]; uint32_t M[32];
+                t[0] = base;
+                for (int j = 1; j < 32; j++) t[j] = ARN_ADD(t[j - 1], arn_calc_dt(c, t[j - 1]));
+                uint32_t valid = 0, occm = 0; int s0 = 0;
+                for (int l = 0; l < 32; l++) {
+                    float x, y, z, dt;
+                    occ[l] = arn_march_probe(c, ray, bits, t[l], x, y, z, dt, tgt[l]);
+                    if (t[l] < t2) valid |= 1u << l;
+                    if (occ[l]) occm |= 1u << l;
+                    if (t[l] < pending) s0++;
+                }
+                for (int l = 0; l < 32; l++) {
+                    int lo = l + 1, hi = 32;
+                    for (int it = 0; it < 5; it++) {
+                        const int mid = (lo + hi) >> 1;
+                        const float tv = t[mid & 31];
+                        if (lo < hi) { if (tv < tgt[l]) lo = mid + 1; else hi = mid; }
+                    }
+                    R[l] = occ[l] ? l + 1 : lo; M[l] = 1u << l;
+                }
+                for (int it = 0; it < 5; it++) {
+                    uint32_t Mo[32]; int Ro[32];
+                    for (int l = 0; l < 32; l++) { Mo[l] = M[R[l] & 31]; Ro[l] = R[R[l] & 31]; }
+                    for (int l = 0; l < 32; l++) if (R[l] < 32) { M[l] |= Mo[l]; R[l] = Ro[l]; }
+                }
+                const uint32_t vis = s0 < 32 ? M[s0 & 31] : 0u;
+                uint32_t emit = vis & occm & valid;
+                const int rem = max_samples - N;
+                bool done = valid != 0xffffffffu;
+                if (popc32(emit) >= rem) {
+                    done = true;
+                    uint32_t e2 = 0;
+                    for (int l = 0; l < 32; l++) if (((emit >> l) & 1u) && popc32(emit & ((1u << l) - 1u)) < rem) e2 |= 1u << l;
+                    emit = e2;
+                }
+                for (int l = 0; l < 32; l++) if ((emit >> l) & 1u) rec[N + popc32(emit & ((1u << l) - 1u))] = t[l];
+                N += popc32(emit);
+                if (done) break;
+                if (vis) { const int last = 31 - __builtin_clz(vis); pending = occ[last] ? -INFINITY : tgt[last]; }
+                base = ARN_ADD(t[31], arn_calc_dt(c, t[31]));
+            }
+        }
+        counts[r] = N;
+    }
+}

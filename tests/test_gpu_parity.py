@@ -154,6 +154,15 @@ def test_march_train_bit_exact(kind, n_rays, w1, w3, vren, ref):
         v._T_SCRATCH_LIMIT = lim
     for a, b in zip(out, out2):
         assert torch.equal(a, b)
+    # the thread-per-ray count kernel (the warp-window kernel is the default) gives the same bytes
+    from ar_nerf_b200 import _lib
+    try:
+        _lib.set_tunable("march_warp", 0)
+        out3 = vren.raymarching_train(T(ro), T(rd), T(ht), T(w.bitfield), *cfg, T(noise), 128, 1024)
+    finally:
+        _lib.set_tunable("march_warp", 1)
+    for a, b in zip(out, out3):
+        assert torch.equal(a, b)
     if ref is not None:
         r_out = ref.raymarching_train(T(ro), T(rd), T(ht), T(w.bitfield), *cfg, T(noise), 128, 1024)
         n, rx, rdirs, rdl, rts, total = refvren.canonical_train(r_out)
@@ -406,10 +415,53 @@ def test_hash_encode_linearity_full_size(vren):
         assert abs(a - b) <= 1e-3 * max(1.0, dfeat[:, 2 * l:2 * l + 2].abs().double().sum().item() ** 0.5 * 10), (l, a, b)
 
 
+@pytest.mark.parametrize("kind", ["W1", "W3"])
+def test_hash_backward_variants_agree(kind, w1, w3, vren):
+    """Run-aggregating hash-grid backward (segment lengths 8..64) against the one-reduction-per-corner kernel on marched
+    samples (consecutive samples of a ray share cells, which is what the aggregation exploits) and against the oracle."""
+    from ar_nerf_b200 import _lib
+    from ar_nerf_b200.field import HashGeometry
+    w = workload(kind, w1, w3)
+    ro, rd, _, noise = w.train_batch(4, 2048)
+    ht = scene_hits(w, ro.numpy(), rd.numpy())
+    out = vren.raymarching_train(T(ro), T(rd), T(ht), T(w.bitfield), w.cascades, w.scale, w.exp_step_factor, T(noise), 128, 1024)
+    xyzs = out[1]; n = xyzs.shape[0]
+    geo = HashGeometry(per_level_scale=float(np.float32(np.exp(np.log(2048 * w.scale / 16) / 15))))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dfeat = torch.randn(n, 32, device=dev(), generator=g)
+    dfeat[::5] = 0  # untouched samples (terminated rays) are skipped
+    mn = (_lib.F * 3)(*[-w.scale] * 3); mx = (_lib.F * 3)(*[w.scale] * 3)
+    res = {}
+    try:
+        for mode in (0, 8, 16, 32, 64):
+            _lib.set_tunable("hash_bw_mode", mode)
+            tg = torch.zeros(geo.total * 2, device=dev())
+            _lib.call("arn_hash_encode_bw", xyzs.data_ptr(), n, mn, mx, geo.c_levels, None, dfeat.data_ptr(), tg.data_ptr(), None, _lib.stream())
+            res[mode] = N(tg)
+    finally:
+        _lib.set_tunable("hash_bw_mode", 32)
+    x01 = (N(xyzs) - np.float32(-w.scale)) / (np.float32(w.scale) - np.float32(-w.scale))
+    o_geo = oracle.HashGeometry(per_level_scale=geo.per_level_scale)
+    o_tg, _ = oracle.hash_encode_bw(x01.astype(np.float32), o_geo, np.zeros(geo.total * 2, np.float16), N(dfeat))
+    for mode in (8, 16, 32, 64):
+        assert_rel(res[mode], res[0], rtol=1e-5, floor=1.0, what=f"hash bw runs seg {mode} vs per-sample")
+        assert_rel(res[mode], o_tg.reshape(-1), rtol=RTOL, floor=1.0, what=f"hash bw runs seg {mode} vs oracle")
+
+
 def test_adam_step_vs_torch(vren):
     from ar_nerf_b200 import _lib
     g = torch.Generator(device="cuda").manual_seed(1)
-    n = 100_003
+    _adam_case(g, 100_003)   # odd size: scalar kernel
+    _adam_case(g, 400_000)   # 128-bit kernel
+    try:
+        _lib.set_tunable("adam_vec", 0)
+        _adam_case(g, 400_000)
+    finally:
+        _lib.set_tunable("adam_vec", 1)
+
+
+def _adam_case(g, n):
+    from ar_nerf_b200 import _lib
     p = torch.randn(n, device=dev(), generator=g); p_ref = p.clone().requires_grad_(True)
     m = torch.zeros(n, device=dev()); v = torch.zeros(n, device=dev())
     p16 = p.half()  # the working copy starts as a full cast; Adam only rewrites entries whose value changed

@@ -45,6 +45,16 @@ def test_train_march_bit_exact(harness, kind, w1, w3):
     assert np.array_equal(counts, rays_a[:, 2].astype(np.int32))
     got = np.concatenate([rec[r, :counts[r]] for r in range(len(ro))])
     assert np.array_equal(got.view(np.uint32), ts.view(np.uint32))
+    # the warp-window procedure of march_train_count_warp_kernel, emulated lane by lane on the host
+    for max_samples in (1024, 37):
+        if max_samples != 1024:
+            rays_a, xyzs, dirs, deltas, ts, counter = oracle.raymarching_train(ro, rd, ht, bits, w.cascades, w.scale, w.exp_step_factor, noise, 128, max_samples)
+        counts = np.zeros(len(ro), np.int32); rec = np.zeros((len(ro), max_samples), np.float32)
+        harness.h_march_train_window(len(ro), _p(ro), _p(rd), _p(ht), _p(bits), w.cascades, 128, C.c_float(w.scale), C.c_float(w.exp_step_factor),
+                                     _p(noise), max_samples, _p(counts), _p(rec))
+        assert np.array_equal(counts, rays_a[:, 2].astype(np.int32))
+        got = np.concatenate([rec[r, :counts[r]] for r in range(len(ro))])
+        assert np.array_equal(got.view(np.uint32), ts.view(np.uint32))
 
 
 @pytest.mark.parametrize("kind", ["W1", "W3"])
