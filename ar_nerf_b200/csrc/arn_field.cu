@@ -459,38 +459,54 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
     if (p16) p16[i] = __float2half_rn(np);
 }
 
-// 128-bit form: one thread updates 4 consecutive parameters (float4 loads/stores of p, g, m, v; 64-bit store of the fp16
-// copy).  Same arithmetic per element as adam_kernel.  Requires 16-byte aligned pointers (8 for p16) and n % 4 == 0.
+// 128-bit form: one thread updates 2 x 4 consecutive parameters per turn; all eight 128-bit loads (p, g, m, v of both
+// groups) are issued before the first use, so a warp keeps 4 KB in flight (the scalar kernel is latency-bound: two
+// dependent DRAM round trips per element).  m, v and the fp32 master are streamed (read once, written once per step:
+// ld/st .cs), the gradient and the fp16 copy keep the default policy -- the hash kernels of the next step hit them in L2.
+// Same arithmetic per element as adam_kernel.  Requires 16-byte aligned pointers (8 for p16) and n % 4 == 0.
+__device__ __forceinline__ void adam_update4(float4& p4, const float4& g4, float4& m4, float4& v4, float lr_bc1, float b1, float b2, float eps,
+                                             float bc2_sqrt, float inv_gs) {
+    float pn[4] = {p4.x, p4.y, p4.z, p4.w}, mn[4] = {m4.x, m4.y, m4.z, m4.w}, vn[4] = {v4.x, v4.y, v4.z, v4.w};
+    const float gr[4] = {g4.x * inv_gs, g4.y * inv_gs, g4.z * inv_gs, g4.w * inv_gs};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (gr[k] == 0.0f && mn[k] == 0.0f && vn[k] == 0.0f) continue;  // untouched hash entry: the update is exactly zero
+        mn[k] = b1 * mn[k] + (1.0f - b1) * gr[k];
+        vn[k] = b2 * vn[k] + (1.0f - b2) * gr[k] * gr[k];
+        const float denom = sqrtf(vn[k]) / bc2_sqrt + eps;
+        pn[k] = pn[k] - lr_bc1 * (mn[k] / denom);
+    }
+    p4 = make_float4(pn[0], pn[1], pn[2], pn[3]); m4 = make_float4(mn[0], mn[1], mn[2], mn[3]); v4 = make_float4(vn[0], vn[1], vn[2], vn[3]);
+}
+__device__ __forceinline__ bool all_zero4(const float4& a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f && a.w == 0.0f; }
+__device__ __forceinline__ uint2 pack_half4(const float4& a) {
+    const __half2 lo = __floats2half2_rn(a.x, a.y), hi = __floats2half2_rn(a.z, a.w);
+    uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    return o;
+}
 __global__ void __launch_bounds__(256) adam_vec4_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
                                                         uint2* __restrict__ p16, int64_t n4, float lr, float b1, float b2, float eps,
                                                         float bc1, float bc2_sqrt, float inv_gs, int zero_grad) {
-    const float step_size = lr / bc1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 g4 = g[i]; const float4 m4 = m[i]; const float4 v4 = v[i];
-        if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float gr[4] = {g4.x * inv_gs, g4.y * inv_gs, g4.z * inv_gs, g4.w * inv_gs};
-        const float mo[4] = {m4.x, m4.y, m4.z, m4.w}, vo[4] = {v4.x, v4.y, v4.z, v4.w};
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < 4; k++) any |= !(gr[k] == 0.0f && mo[k] == 0.0f && vo[k] == 0.0f);
-        if (!any) continue;  // four untouched hash entries: the update is exactly zero
-        const float4 p4 = p[i];
-        float pn[4] = {p4.x, p4.y, p4.z, p4.w}, mn[4], vn[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            mn[k] = mo[k]; vn[k] = vo[k];
-            if (gr[k] == 0.0f && mo[k] == 0.0f && vo[k] == 0.0f) continue;
-            mn[k] = b1 * mo[k] + (1.0f - b1) * gr[k];
-            vn[k] = b2 * vo[k] + (1.0f - b2) * gr[k] * gr[k];
-            const float denom = sqrtf(vn[k]) / bc2_sqrt + eps;
-            pn[k] = pn[k] - step_size * (mn[k] / denom);
+    const float lr_bc1 = lr / bc1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+        const int64_t j = i + stride;
+        const bool two = j < n4;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 ga = g[i], ma = __ldcs(m + i), va = __ldcs(v + i), pa = __ldcs(p + i);
+        float4 gb = z, mb = z, vb = z, pb = z;
+        if (two) { gb = g[j]; mb = __ldcs(m + j); vb = __ldcs(v + j); pb = __ldcs(p + j); }
+        if (!(all_zero4(ga) && all_zero4(ma) && all_zero4(va))) {
+            if (zero_grad && !all_zero4(ga)) g[i] = z;
+            adam_update4(pa, ga, ma, va, lr_bc1, b1, b2, eps, bc2_sqrt, inv_gs);
+            __stcs(m + i, ma); __stcs(v + i, va); __stcs(p + i, pa);
+            if (p16) p16[i] = pack_half4(pa);
         }
-        m[i] = make_float4(mn[0], mn[1], mn[2], mn[3]); v[i] = make_float4(vn[0], vn[1], vn[2], vn[3]);
-        p[i] = make_float4(pn[0], pn[1], pn[2], pn[3]);
-        if (p16) {
-            const __half2 a = __floats2half2_rn(pn[0], pn[1]), b = __floats2half2_rn(pn[2], pn[3]);
-            uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
-            p16[i] = o;
+        if (two && !(all_zero4(gb) && all_zero4(mb) && all_zero4(vb))) {
+            if (zero_grad && !all_zero4(gb)) g[j] = z;
+            adam_update4(pb, gb, mb, vb, lr_bc1, b1, b2, eps, bc2_sqrt, inv_gs);
+            __stcs(m + j, mb); __stcs(v + j, vb); __stcs(p + j, pb);
+            if (p16) p16[j] = pack_half4(pb);
         }
     }
 }

@@ -335,13 +335,47 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     const uint64_t wD1 = smem_desc<64>(sW + kWimgD1), wD2 = smem_desc<128>(sW + kWimgD2);
     const uint64_t wC1 = smem_desc<64>(sW + kWimgC1), wC2 = smem_desc<128>(sW + kWimgC2), wC3 = smem_desc<128>(sW + kWimgC3);
 
+    // Global -> register prefetch: the activation row a layer needs is requested one layer ahead (and the first layer's
+    // inputs of the NEXT tile during the last layer), so its DRAM/L2 latency overlaps the MMA round trip and the epilogue
+    // instead of being exposed five times per tile.
+    auto fetch_row128 = [&](uint4* r, const __half* src, bool ok) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) r[c] = ok ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
+    };
+    auto fetch_row64 = [&](uint4* r, const __half* src, bool ok) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) r[c] = ok ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
+    };
+    auto put_row128 = [&](const uint4* r) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(pX + swz<128>(tid, c)) = r[c];
+    };
+    auto put_row64 = [&](const uint4* r) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(pX + swz<64>(tid, c)) = r[c];
+    };
+
     const int64_t n_tiles = (n + 127) / 128;
+    uint4 xr[8];                  // prefetched activation row
+    float pre_y[3], pre_g[3];     // prefetched rgbs / dL_drgbs of this thread's sample
+    {
+        const int64_t i = (int64_t)blockIdx.x * 128 + tid;
+        const bool valid = blockIdx.x < n_tiles && i < n;
+        if (with_rgb) {
+            fetch_row128(xr, hid2 + 64 * i, valid);
+#pragma unroll
+            for (int j = 0; j < 3; j++) { pre_y[j] = valid ? rgbs[3 * i + j] : 0.0f; pre_g[j] = (valid && dL_drgbs) ? dL_drgbs[3 * i + j] : 0.0f; }
+        } else {
+            fetch_row128(xr, hid + 64 * i, valid);
+        }
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
         float tcol[16];  // scaled dL/dh from the colour branch
 #pragma unroll
         for (int j = 0; j < 16; j++) tcol[j] = 0.0f;
+        float pre_ds = 0.0f, pre_h0 = 0.0f;
         if (with_rgb) {
             // ---- colour output layer: g3 (16) -> Ga (RB32), X = hid2
             {
@@ -351,33 +385,34 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                 if (valid && dL_drgbs) {
                     float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        const float y = rgbs[3 * i + j];
-                        g[j] = dL_drgbs[3 * i + j] * (rgb_act ? y * (1.0f - y) : 1.0f) * loss_scale;
-                    }
+                    for (int j = 0; j < 3; j++) g[j] = pre_g[j] * (rgb_act ? pre_y[j] * (1.0f - pre_y[j]) : 1.0f) * loss_scale;
                     o[0] = pack2(g[0], g[1]); o[1] = pack2(g[2], 0.0f);
                 }
                 *reinterpret_cast<uint4*>(pGa + swz<32>(tid, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<uint4*>(pGa + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
-                stage_row<128>(pX, tid, hid2 + 64 * i, valid);
+                put_row128(xr);
             }
+            fetch_row128(xr, hid1 + 64 * i, valid);
+            if (valid && dL_dsigmas) { pre_ds = dL_dsigmas[i]; pre_h0 = h[16 * i]; }
             layer(dGa32, 32, dX128, 128, wC3, 128, 64, 16, kColC3);
             epilogue_mask64(trow + kColR, pX, pGb, tid);              // g2 -> Gb
             fence_before_sync(); __syncthreads();                     // everyone has read its X row before it is replaced
-            stage_row<128>(pX, tid, hid1 + 64 * i, valid);
+            put_row128(xr);
+            fetch_row64(xr, in32 + 32 * i, valid);
             layer(dGb128, 128, dX128, 128, wC2, 128, 64, 64, kColC2);
             epilogue_mask64(trow + kColR, pX, pGa, tid);              // g1 -> Ga
             fence_before_sync(); __syncthreads();
-            stage_row<64>(pX, tid, in32 + 32 * i, valid);
+            put_row64(xr);
+            fetch_row128(xr, hid + 64 * i, valid);
             layer(dGa128, 128, dX64, 64, wC1, 64, 32, 64, kColC1);
             {   // R[:, 16:32] = scaled dL/dh from the colour branch
                 tmem_ld16(trow + kColR + 16, tcol); tmem_ld_wait();
             }
-        }
+        } else if (valid && dL_dsigmas) { pre_ds = dL_dsigmas[i]; pre_h0 = h[16 * i]; }
         // ---- density output layer: gh (16) -> Gb (RB32), X = hid
         {
             float g0 = tcol[0];
-            if (valid && dL_dsigmas) g0 += (dL_dsigmas[i] * expf(fminf(fmaxf(h[16 * i], -15.0f), 15.0f))) * loss_scale;
+            if (valid && dL_dsigmas) g0 += (pre_ds * expf(fminf(fmaxf(pre_h0, -15.0f), 15.0f))) * loss_scale;
             uint32_t o[8];
             o[0] = pack2(g0, tcol[1]);
 #pragma unroll
@@ -389,12 +424,24 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
             fence_before_sync(); __syncthreads();                     // previous layer's tiles are free
             *reinterpret_cast<uint4*>(pGb + swz<32>(tid, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<uint4*>(pGb + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
-            stage_row<128>(pX, tid, hid + 64 * i, valid);
+            put_row128(xr);
         }
+        fetch_row64(xr, feat + 32 * i, valid);
         layer(dGb32, 32, dX128, 128, wD2, 128, 64, 16, kColD2);
         epilogue_mask64(trow + kColR, pX, pGa, tid);                  // gd -> Ga
         fence_before_sync(); __syncthreads();
-        stage_row<64>(pX, tid, feat + 32 * i, valid);
+        put_row64(xr);
+        {   // first-layer inputs of this CTA's next tile
+            const int64_t in = (tile + gridDim.x) * 128 + tid;
+            const bool vn = tile + gridDim.x < n_tiles && in < n;
+            if (with_rgb) {
+                fetch_row128(xr, hid2 + 64 * in, vn);
+#pragma unroll
+                for (int j = 0; j < 3; j++) { pre_y[j] = vn ? rgbs[3 * in + j] : 0.0f; pre_g[j] = (vn && dL_drgbs) ? dL_drgbs[3 * in + j] : 0.0f; }
+            } else {
+                fetch_row128(xr, hid + 64 * in, vn);
+            }
+        }
         layer(dGa128, 128, dX64, 64, wD1, 64, 32, 64, kColD1);
         {
             float v[32];
