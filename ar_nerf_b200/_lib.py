@@ -20,6 +20,9 @@ class Levels(C.Structure):
     _fields_ = [("scale_host", P), ("res_host", P), ("size_host", P), ("offset_host", P)]
 
 
+FIELD_SCRATCH_BYTES = 20480 + 512 * 10240 * 4  # ARN_FIELD_SCRATCH_BYTES (include/arnerf.h)
+
+
 class FieldWs(C.Structure):
     _fields_ = [("feat", P), ("hid", P), ("h", P), ("in32", P), ("hid1", P), ("hid2", P), ("wimg", P)]
 
@@ -32,7 +35,7 @@ class TrainCfg(C.Structure):
                 ("center_host", P), ("half_size_host", P), ("xyz_min_host", P), ("xyz_max_host", P),
                 ("levels", Levels), ("params_xyz_f16", P), ("params_rgb_f16", P), ("rgb_act", I),
                 ("bg_host", P), ("lambda_opacity", F), ("lambda_depth", F), ("grad_scale", F), ("loss_scale", F),
-                ("hits_t", P), ("rays_a", P), ("counter", P), ("t_scratch", P), ("total_samples", P),
+                ("hits_t", P), ("rays_a", P), ("counter", P), ("t_scratch", P), ("count_scratch", P), ("total_samples", P),
                 ("opacity", P), ("depth", P), ("rgb", P), ("rgb_final", P), ("dL_dopacity", P), ("dL_ddepth", P), ("dL_drgb", P),
                 ("capacity", L), ("xyzs", P), ("dirs", P), ("deltas", P), ("ts", P), ("sigmas", P), ("rgbs", P), ("ws_out", P),
                 ("dL_dsigmas", P), ("dL_drgbs", P), ("dfeat", P), ("ws", FieldWs),
@@ -55,7 +58,7 @@ SIGNATURES = {
     "arn_packbits": [P, I, F, P, L, P],
     "arn_march_train_count": [P, P, P, L, P, I, I, F, F, P, I, P, P, P],
     "arn_march_train_emit": [P, P, P, L, P, I, I, F, F, P, I, P, P, P, P, P, L, P],
-    "arn_march_train_count_ex": [P, P, P, L, P, I, I, F, F, P, I, P, P, P, P],
+    "arn_march_train_count_ex": [P, P, P, L, P, I, I, F, F, P, I, P, P, P, P, P],
     "arn_march_train_emit_ex": [P, P, P, L, P, I, I, F, F, P, I, P, P, P, P, P, P, L, P],
     "arn_march_test": [P, P, P, P, L, P, I, I, F, F, I, I, P, P, P, P, P, P],
     "arn_composite_train_fw": [P, P, P, P, P, L, L, F, P, P, P, P, P, P],

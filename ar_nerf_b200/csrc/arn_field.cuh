@@ -15,6 +15,11 @@ struct Aabb { float mn[3], mx[3]; };
 
 int make_levels(const arn_levels_t& lv, LevelTable& t);
 int make_box(const float* mn, const float* mx, Aabb& b);
+// arn_field_bw_tc_dyn with the option of reusing the weight image already in ws.wimg (arn_mlp_tc.cu)
+int field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                     arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
+                     const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
+                     float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, bool pack_weights, arn_stream_t stream);
 
 // tiny-cuda-nn grid.h grid_index
 __device__ __forceinline__ uint32_t grid_index(uint32_t hashmap_size, uint32_t res, const uint32_t p[3]) {

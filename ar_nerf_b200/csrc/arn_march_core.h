@@ -42,6 +42,7 @@ struct ArnMarchConsts {
     float G;        // (float)grid_size
     float Gm1;      // G - 1
     float Ginv;     // 1 / G (IEEE)
+    float mip0_bound_inv;  // 1 / min(0.5, scale) (IEEE): mip_bound_inv of cascade 0
 };
 
 // dt_scale: `scale` for the train kernel, `(float)cascades` for the test kernel (reference quirk, raymarching.cu:370).
@@ -56,6 +57,7 @@ ARN_HD ArnMarchConsts arn_march_consts(int cascades, int grid_size, float scale,
     c.dt_hi = ARN_DIV(ARN_MUL(dt_scale, ARN_SQRT3 * 2), c.G);
     c.Gm1 = ARN_ADD(c.G, -1.0f);
     c.Ginv = ARN_DIV(1.0f, c.G);
+    c.mip0_bound_inv = ARN_DIV(1.0f, fminf(0.5f, scale));
     return c;
 }
 
@@ -81,6 +83,16 @@ ARN_HD uint32_t arn_expand_bits(uint32_t v) {  // raymarching.cu:35-42
 }
 ARN_HD uint32_t arn_morton3d(uint32_t x, uint32_t y, uint32_t z) {  // :44-50
     return arn_expand_bits(x) | (arn_expand_bits(y) << 1) | (arn_expand_bits(z) << 2);
+}
+// Same value for v < 256 (the first step of arn_expand_bits is then the identity): grids up to 256^3.
+ARN_HD uint32_t arn_expand_bits8(uint32_t v) {
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+ARN_HD uint32_t arn_morton3d_8(uint32_t x, uint32_t y, uint32_t z) {
+    return arn_expand_bits8(x) | (arn_expand_bits8(y) << 1) | (arn_expand_bits8(z) << 2);
 }
 ARN_HD uint32_t arn_morton3d_invert(uint32_t x) {  // :52-60
     x = x & 0x49249249u;
@@ -115,26 +127,35 @@ ARN_HD float arn_jitter_start(const ArnMarchConsts& c, float t1, float noise) {
 
 // One probe of the loop body at parameter t (raymarching.cu:205-229): position, step, occupancy of the cell that holds
 // o + t*d and -- for an empty cell -- the parameter t_target up to which the reference's skip loop advances.
+// ONE_CASCADE / SMALL_GRID are compile-time shortcuts with identical results: cascades == 1 makes both mip clamps
+// return 0 whatever the position, grid_size <= 256 makes the first morton step the identity.
+#if defined(__cplusplus)
+template <bool ONE_CASCADE = false, bool SMALL_GRID = false>
+#endif
 ARN_HD bool arn_march_probe(const ArnMarchConsts& c, const ArnRay& r, const uint8_t* __restrict__ bitfield, float t,
                             float& x, float& y, float& z, float& dt, float& t_target) {
     x = ARN_FMA(r.dx, t, r.ox); y = ARN_FMA(r.dy, t, r.oy); z = ARN_FMA(r.dz, t, r.oz);
     dt = arn_calc_dt(c, t);
     // mip_from_pos (:19-23) / mip_from_dt (:29-32)
-    const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-    int mp = arn_frexp_exponent(mx) + 1; mp = mp < 0 ? 0 : mp; mp = mp > c.cascades - 1 ? c.cascades - 1 : mp;
-    int md = arn_frexp_exponent(ARN_MUL(dt, c.G)); md = md < 0 ? 0 : md; md = md > c.cascades - 1 ? c.cascades - 1 : md;
-    const int mip = mp > md ? mp : md;
+    int mip = 0;
+    if (!ONE_CASCADE) {
+        const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+        int mp = arn_frexp_exponent(mx) + 1; mp = mp < 0 ? 0 : mp; mp = mp > c.cascades - 1 ? c.cascades - 1 : mp;
+        int md = arn_frexp_exponent(ARN_MUL(dt, c.G)); md = md < 0 ? 0 : md; md = md > c.cascades - 1 ? c.cascades - 1 : md;
+        mip = mp > md ? mp : md;
+    }
     // :211-212  mip_bound = min(2^(mip-1), scale) ; exact power of two built from its exponent bits
     union { uint32_t u; float f; } p2; p2.u = (uint32_t)(127 + mip - 1) << 23;
     const float mip_bound = fminf(p2.f, c.scale);
-    const float mip_bound_inv = ARN_DIV(1.0f, mip_bound);
+    const float mip_bound_inv = ONE_CASCADE ? c.mip0_bound_inv : ARN_DIV(1.0f, mip_bound);
     // :215-217
     const float fx = fmaxf(0.0f, fminf(ARN_MUL(ARN_MUL(0.5f, ARN_FMA(x, mip_bound_inv, 1.0f)), c.G), c.Gm1));
     const float fy = fmaxf(0.0f, fminf(ARN_MUL(ARN_MUL(0.5f, ARN_FMA(y, mip_bound_inv, 1.0f)), c.G), c.Gm1));
     const float fz = fmaxf(0.0f, fminf(ARN_MUL(ARN_MUL(0.5f, ARN_FMA(z, mip_bound_inv, 1.0f)), c.G), c.Gm1));
     const int nx = arn_f2i(fx), ny = arn_f2i(fy), nz = arn_f2i(fz);
     // :219-220
-    const uint32_t idx = (uint32_t)mip * c.grid_size3 + arn_morton3d((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    const uint32_t idx = (uint32_t)mip * c.grid_size3 + (SMALL_GRID ? arn_morton3d_8((uint32_t)nx, (uint32_t)ny, (uint32_t)nz)
+                                                                    : arn_morton3d((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
     const bool occ = (bitfield[idx >> 3] >> (idx & 7u)) & 1u;
     if (occ) { t_target = t; return true; }
     // :225-227
@@ -152,7 +173,7 @@ ARN_HD bool arn_march_probe(const ArnMarchConsts& c, const ArnRay& r, const uint
 ARN_HD bool arn_march_eval(const ArnMarchConsts& c, const ArnRay& r, const uint8_t* __restrict__ bitfield, float& t,
                            float& x, float& y, float& z, float& dt) {
     float t_target;
-    if (arn_march_probe(c, r, bitfield, t, x, y, z, dt, t_target)) return true;
+    if (arn_march_probe<false, false>(c, r, bitfield, t, x, y, z, dt, t_target)) return true;
     do { t = ARN_ADD(t, arn_calc_dt(c, t)); } while (t < t_target);
     return false;
 }

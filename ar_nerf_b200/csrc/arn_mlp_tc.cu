@@ -89,29 +89,44 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
     uint32_t phase = 0;
 
     // issue one layer: D[tmem cols] = A (128 x K) * W^T, K = 16 * ksteps; then commit
-    auto issue = [&](uint32_t dcol, uint64_t a, uint64_t b, uint32_t idesc, int ksteps) {
+    auto issue_only = [&](uint32_t dcol, uint64_t a, uint64_t b, uint32_t idesc, int ksteps) {
         fence_before_sync(); fence_async_smem(); __syncthreads();
         if (tid == 0) {
             fence_after_sync();
             for (int k = 0; k < ksteps; k++) mma_f16(tmem + dcol, desc_advance(a, 32 * k), desc_advance(b, 32 * k), idesc, k > 0);
             mma_commit(bar_mma);
         }
+    };
+    auto wait_mma = [&]() {
         mbar_wait(bar_mma, phase); phase ^= 1;
         fence_after_sync();
     };
+    auto issue = [&](uint32_t dcol, uint64_t a, uint64_t b, uint32_t idesc, int ksteps) { issue_only(dcol, a, b, idesc, ksteps); wait_mma(); };
 
+    // The tile's only global inputs (feature row, ray direction) are requested one tile ahead, between the issue of the
+    // previous tile's last MMA and its completion (ptxas cannot hoist them above that bar.sync; see the backward kernel).
     const int64_t n_tiles = (n + 127) / 128;
+    uint4 fr[4]; float dr[3] = {1.0f, 0.0f, 0.0f};
+    auto fetch_inputs = [&](int64_t t) {
+        const int64_t i = t * 128 + tid;
+        const bool ok = t < n_tiles && i < n;
+#pragma unroll
+        for (int c = 0; c < 4; c++) fr[c] = ok ? __ldg(reinterpret_cast<const uint4*>(feat + 32 * i) + c) : make_uint4(0, 0, 0, 0);
+        if (with_rgb) {
+            dr[0] = ok ? dirs[3 * i] : 1.0f; dr[1] = ok ? dirs[3 * i + 1] : 0.0f; dr[2] = ok ? dirs[3 * i + 2] : 0.0f;
+        }
+    };
+    fetch_inputs(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
         // ---- density layer 1: A = feat row (32 halves)
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (valid) v = reinterpret_cast<const uint4*>(feat + 32 * i)[c];
-            *reinterpret_cast<uint4*>(pT32 + swz<64>(tid, c)) = v;
-        }
-        issue(0, aT32, bD1, kI64, 2);
+        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(pT32 + swz<64>(tid, c)) = fr[c];
+        const float dcur[3] = {dr[0], dr[1], dr[2]};
+        issue_only(0, aT32, bD1, kI64, 2);
+        if (!with_rgb) fetch_inputs(tile + gridDim.x);
+        wait_mma();
         {
             uint32_t o[32];
             epilogue_row_f16<4, true>(trow + 0, o);
@@ -134,8 +149,7 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
             }
             if (with_rgb) {  // colour-net input row [sh16 | fp16(h16)]
                 float sh[16];
-                const float d0[3] = {1.0f, 0.0f, 0.0f};
-                sh4_eval(valid ? dirs + 3 * i : d0, sh);
+                sh4_eval(dcur, sh);
                 uint32_t o[16];
 #pragma unroll
                 for (int j = 0; j < 8; j++) { o[j] = pack2(sh[2 * j], sh[2 * j + 1]); o[8 + j] = pack2(hv[2 * j], hv[2 * j + 1]); }
@@ -173,7 +187,9 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
             }
         }
         // ---- colour layer 3 -> rgb
-        issue(0, aT64, bC3, kI16, 4);
+        issue_only(0, aT64, bC3, kI16, 4);
+        fetch_inputs(tile + gridDim.x);
+        wait_mma();
         {
             float ov[16];
             tmem_ld16(trow + 0, ov); tmem_ld_wait();
@@ -244,6 +260,8 @@ using namespace tc;
 // fp16 and writes the next G tile.  Rounding points are those of the simt kernel / oracle (fp16 G, fp32 accumulate).
 // TMEM map: [0,64) R | [64,80) dWc3^T | [80,144) dWc2 | [144,176) dWc1 | [176,192) dWd2^T | [192,224) dWd1   (256 allocated)
 constexpr int kBwSmemBytes = kWimgBytes + 3 * kFwSmemTile64 + 1024;
+constexpr int kWgradFloats = 7168 + 3072;  // one slab of per-CTA weight gradients
+constexpr int kMaxBwCtas = ARN_FIELD_SCRATCH_SLABS;
 constexpr uint32_t kColR = 0, kColC3 = 64, kColC2 = 80, kColC1 = 144, kColD2 = 176, kColD1 = 192;
 
 template <int RB>
@@ -282,7 +300,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                                                               const __half* __restrict__ in32, const __half* __restrict__ hid1,
                                                               const __half* __restrict__ hid2, const uint8_t* __restrict__ wimg, int rgb_act,
                                                               int with_rgb, float loss_scale, float* __restrict__ dWd, float* __restrict__ dWc,
-                                                              float* __restrict__ dfeat) {
+                                                              float* __restrict__ dfeat, float* __restrict__ wpart) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
@@ -326,6 +344,8 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                 mma_f16(tmem + kColR, desc_advance(g_desc, 32 * k), desc_advance(w_desc, 16 * rbw * k), di, k > 0);
             mma_commit(bar_mma);
         }
+    };
+    auto layer_wait = [&]() {
         mbar_wait(bar_mma, phase); phase ^= 1;
         fence_after_sync();
     };
@@ -338,6 +358,10 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     // Global -> register prefetch: the activation row a layer needs is requested one layer ahead (and the first layer's
     // inputs of the NEXT tile during the last layer), so its DRAM/L2 latency overlaps the MMA round trip and the epilogue
     // instead of being exposed five times per tile.
+    // The consumer of a prefetched row must come BEFORE the next prefetch is issued: loads retire through in-order
+    // scoreboards, so a use placed after younger loads waits for those as well (seen in ncu as long-scoreboard stalls on
+    // the first use).  ptxas hoists loads to the top of a basic block, so every fetch sits between layer() -- whose
+    // bar.sync it cannot cross -- and layer_wait(), after the previous row has gone to shared memory.
     auto fetch_row128 = [&](uint4* r, const __half* src, bool ok) {
 #pragma unroll
         for (int c = 0; c < 8; c++) r[c] = ok ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
@@ -356,7 +380,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     };
 
     const int64_t n_tiles = (n + 127) / 128;
-    uint4 xr[8];                  // prefetched activation row
+    uint4 xr[8], xs[4];           // prefetched activation rows (128-byte / 64-byte)
     float pre_y[3], pre_g[3];     // prefetched rgbs / dL_drgbs of this thread's sample
     {
         const int64_t i = (int64_t)blockIdx.x * 128 + tid;
@@ -392,19 +416,22 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                 *reinterpret_cast<uint4*>(pGa + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
                 put_row128(xr);
             }
+            layer(dGa32, 32, dX128, 128, wC3, 128, 64, 16, kColC3);
             fetch_row128(xr, hid1 + 64 * i, valid);
             if (valid && dL_dsigmas) { pre_ds = dL_dsigmas[i]; pre_h0 = h[16 * i]; }
-            layer(dGa32, 32, dX128, 128, wC3, 128, 64, 16, kColC3);
+            layer_wait();
             epilogue_mask64(trow + kColR, pX, pGb, tid);              // g2 -> Gb
             fence_before_sync(); __syncthreads();                     // everyone has read its X row before it is replaced
             put_row128(xr);
-            fetch_row64(xr, in32 + 32 * i, valid);
             layer(dGb128, 128, dX128, 128, wC2, 128, 64, 64, kColC2);
+            fetch_row64(xs, in32 + 32 * i, valid);
+            layer_wait();
             epilogue_mask64(trow + kColR, pX, pGa, tid);              // g1 -> Ga
             fence_before_sync(); __syncthreads();
-            put_row64(xr);
-            fetch_row128(xr, hid + 64 * i, valid);
+            put_row64(xs);
             layer(dGa128, 128, dX64, 64, wC1, 64, 32, 64, kColC1);
+            fetch_row128(xr, hid + 64 * i, valid);
+            layer_wait();
             {   // R[:, 16:32] = scaled dL/dh from the colour branch
                 tmem_ld16(trow + kColR + 16, tcol); tmem_ld_wait();
             }
@@ -426,12 +453,9 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
             *reinterpret_cast<uint4*>(pGb + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
             put_row128(xr);
         }
-        fetch_row64(xr, feat + 32 * i, valid);
         layer(dGb32, 32, dX128, 128, wD2, 128, 64, 16, kColD2);
-        epilogue_mask64(trow + kColR, pX, pGa, tid);                  // gd -> Ga
-        fence_before_sync(); __syncthreads();
-        put_row64(xr);
-        {   // first-layer inputs of this CTA's next tile
+        fetch_row64(xs, feat + 32 * i, valid);
+        {   // first-layer inputs of this CTA's next tile (xr is free: its row went to shared memory before this layer)
             const int64_t in = (tile + gridDim.x) * 128 + tid;
             const bool vn = tile + gridDim.x < n_tiles && in < n;
             if (with_rgb) {
@@ -442,7 +466,12 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                 fetch_row128(xr, hid + 64 * in, vn);
             }
         }
+        layer_wait();
+        epilogue_mask64(trow + kColR, pX, pGa, tid);                  // gd -> Ga
+        fence_before_sync(); __syncthreads();
+        put_row64(xs);
         layer(dGa128, 128, dX64, 64, wD1, 64, 32, 64, kColD1);
+        layer_wait();
         {
             float v[32];
             tmem_ld16(trow + kColR, v); tmem_ld16(trow + kColR + 16, v + 16); tmem_ld_wait();
@@ -456,31 +485,62 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
         acc = 1;
     }
 
-    // ---- flush the weight gradients: M=64 accumulators live in lanes 0-15 of each warp's quadrant (row = 16*warp + lane)
+    // ---- flush the weight gradients: M=64 accumulators live in lanes 0-15 of each warp's quadrant (row = 16*warp + lane).
+    // Every CTA writes its five accumulators as one 10240-float slab of `wpart` (parameter order: colour 7168 | density
+    // 3072) with plain stores; wgrad_reduce_kernel then sums the slabs in a fixed order.  (296 CTAs reducing onto the same
+    // 10240 addresses with atomics serialised in L2 and cost 28 % of this kernel; the slab sum is also deterministic.)
     fence_before_sync(); __syncthreads(); fence_after_sync();
-    if (acc) {
+    {
+        float* slab = wpart + (size_t)blockIdx.x * kWgradFloats;
         const int m = 16 * warp + lane;
         const bool own = lane < 16;
-        auto flush = [&](uint32_t col, int ncols, float* dst, int ld_row, int ld_col) {
+        auto flush = [&](uint32_t col, int ncols, float* dst, int ld_row, int ld_col, bool live) {
             for (int c0 = 0; c0 < ncols; c0 += 16) {
                 float v[16];
-                tmem_ld16(trow + col + c0, v); tmem_ld_wait();
-                if (own) {
+                if (live) { tmem_ld16(trow + col + c0, v); tmem_ld_wait(); }
+                else {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) atomicAdd(dst + m * ld_row + (c0 + j) * ld_col, v[j] * inv_scale);
+                    for (int j = 0; j < 16; j++) v[j] = 0.0f;
+                }
+                if (own) {
+                    if (ld_col == 1) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            *reinterpret_cast<float4*>(dst + m * ld_row + c0 + 4 * q) =
+                                make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale, v[4 * q + 3] * inv_scale);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) dst[m * ld_row + (c0 + j) * ld_col] = v[j] * inv_scale;
+                    }
                 }
             }
         };
-        if (with_rgb) {
-            flush(kColC3, 16, dWc + 6144, 1, 64);   // accumulator is [in][out]: dW3[out][in] = acc[in][out]
-            flush(kColC2, 64, dWc + 2048, 64, 1);
-            flush(kColC1, 32, dWc, 32, 1);
-        }
-        flush(kColD2, 16, dWd + 2048, 1, 64);
-        flush(kColD1, 32, dWd, 32, 1);
+        const bool live_c = acc && with_rgb, live_d = acc != 0;
+        flush(kColC3, 16, slab + 6144, 1, 64, live_c);   // accumulator is [in][out]: dW3[out][in] = acc[in][out]
+        flush(kColC2, 64, slab + 2048, 64, 1, live_c);
+        flush(kColC1, 32, slab, 32, 1, live_c);
+        flush(kColD2, 16, slab + 7168 + 2048, 1, 64, live_d);
+        flush(kColD1, 32, slab + 7168, 32, 1, live_d);
     }
     fence_before_sync(); __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// grad += sum over the CTAs' slabs, in slab order (deterministic).  One thread per weight; 10240 weights.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ wpart, int n_slabs, int with_rgb,
+                                                           float* __restrict__ dWd, float* __restrict__ dWc) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= kWgradFloats) return;
+    if (e < 7168 && !with_rgb) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 3 < n_slabs; k += 4) {
+        s0 += wpart[(size_t)k * kWgradFloats + e]; s1 += wpart[(size_t)(k + 1) * kWgradFloats + e];
+        s2 += wpart[(size_t)(k + 2) * kWgradFloats + e]; s3 += wpart[(size_t)(k + 3) * kWgradFloats + e];
+    }
+    for (; k < n_slabs; k++) s0 += wpart[(size_t)k * kWgradFloats + e];
+    const float sum = (s0 + s1) + (s2 + s3);
+    if (e < 7168) dWc[e] += sum; else dWd[e - 7168] += sum;
 }
 
 }  // namespace arn
@@ -496,6 +556,14 @@ extern "C" ARN_API int arn_field_bw_tc_dyn(const float* xyzs, int64_t n, const i
                                            arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
                                            const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
                                            float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, arn_stream_t stream) {
+    return arn::field_bw_tc_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, params_xyz_f16, params_rgb_f16, rgb_act, ws, sigmas, rgbs, dL_dsigmas,
+                                 dL_drgbs, loss_scale, dfeat_scratch, grad_params_xyz, grad_params_rgb, dL_dxyzs, true, stream);
+}
+// pack_weights = false: ws.wimg still holds the weight image the forward of the same parameters built (fused training step).
+int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                          arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
+                          const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
+                          float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, bool pack_weights, arn_stream_t stream) {
     (void)sigmas;
     ARN_REQUIRE(n >= 0 && loss_scale > 0, "bad size / loss_scale");
     if (n == 0) return ARN_OK;
@@ -506,20 +574,26 @@ extern "C" ARN_API int arn_field_bw_tc_dyn(const float* xyzs, int64_t n, const i
     const __half* pxyz = (const __half*)params_xyz_f16;
     // the weight image may have been built by a forward with different parameters only if the caller changed them in
     // between; rebuilding it here keeps the call self-contained (5 tiny blocks)
-    ARN_LAUNCH("pack_mlp_weights_kernel", st, arn::pack_mlp_weights_kernel<<<5, 256, 0, st>>>(pxyz, with_rgb ? (const __half*)params_rgb_f16 : nullptr, (uint8_t*)ws.wimg));
-    if (int e = check_launch("pack_mlp_weights")) return e;
+    if (pack_weights) {
+        ARN_LAUNCH("pack_mlp_weights_kernel", st, arn::pack_mlp_weights_kernel<<<5, 256, 0, st>>>(pxyz, with_rgb ? (const __half*)params_rgb_f16 : nullptr, (uint8_t*)ws.wimg));
+        if (int e = check_launch("pack_mlp_weights")) return e;
+    }
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0; ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         ARN_CUDA(cudaFuncSetAttribute(arn::field_mlp_bw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, arn::kBwSmemBytes));
     }
     const int64_t n_tiles = (n + 127) / 128;
-    const int grid = (int)(n_tiles < (int64_t)n_sm * 2 ? n_tiles : (int64_t)n_sm * 2);
+    int grid = (int)(n_tiles < (int64_t)n_sm * 2 ? n_tiles : (int64_t)n_sm * 2);
+    if (grid > arn::kMaxBwCtas) grid = arn::kMaxBwCtas;
+    float* wpart = reinterpret_cast<float*>((uint8_t*)ws.wimg + arn::kWimgBytes);  // slabs follow the weight image in the scratch
     ARN_LAUNCH("field_mlp_bw_tc_kernel", st, arn::field_mlp_bw_tc_kernel<<<grid, 128, arn::kBwSmemBytes, st>>>(
         n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, ws.h, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32,
         (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, grad_params_xyz,
-        grad_params_rgb, dfeat_scratch));
+        grad_params_rgb, dfeat_scratch, wpart));
     if (int e = check_launch("field_mlp_bw_tc")) return e;
+    ARN_LAUNCH("wgrad_reduce_kernel", st, arn::wgrad_reduce_kernel<<<arn::kWgradFloats / 256, 256, 0, st>>>(wpart, grid, with_rgb ? 1 : 0, grad_params_xyz, grad_params_rgb));
+    if (int e = check_launch("wgrad_reduce")) return e;
     return arn_hash_encode_bw_dyn(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
                                   grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, stream);
 }

@@ -5,6 +5,7 @@
 //   composite backward -> MLP + hash-grid backward (gradients accumulated into the caller's buffers).
 // The optimizer (arn_adam_step) is a separate call so that the caller can all-reduce the gradients in between.
 #include "arn_common.cuh"
+#include "arn_field.cuh"
 
 namespace arn {
 
@@ -66,7 +67,7 @@ using namespace arn;
 extern "C" {
 int arn_ray_aabb_near(const float*, const float*, int64_t, const float*, const float*, float, float*, arn_stream_t);
 int arn_march_train_count_ex(const float*, const float*, const float*, int64_t, const uint8_t*, int, int, float, float, const float*, int, int64_t*,
-                             int32_t*, float*, arn_stream_t);
+                             int32_t*, float*, int32_t*, arn_stream_t);
 int arn_march_train_emit_dyn(const float*, const float*, int64_t, int, int, float, float, int, const int64_t*, const float*, const int32_t*, float*,
                              float*, float*, float*, int64_t, arn_stream_t);
 int arn_field_fw_tc_dyn(const float*, const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const void*, int,
@@ -95,7 +96,7 @@ extern "C" ARN_API int arn_train_fwbw(const arn_train_t* c, arn_stream_t stream)
     const int64_t R = c->n_rays;
     if (int e = arn_ray_aabb_near(c->rays_o, c->rays_d, R, c->center_host, c->half_size_host, c->near, c->hits_t, stream)) return e;
     if (int e = arn_march_train_count_ex(c->rays_o, c->rays_d, c->hits_t, R, c->density_bitfield, c->cascades, c->grid_size, c->scale,
-                                         c->exp_step_factor, c->noise, c->max_samples, c->rays_a, c->counter, c->t_scratch, stream)) return e;
+                                         c->exp_step_factor, c->noise, c->max_samples, c->rays_a, c->counter, c->t_scratch, c->count_scratch, stream)) return e;
     if (int e = arn_march_train_emit_dyn(c->rays_o, c->rays_d, R, c->cascades, c->grid_size, c->scale, c->exp_step_factor, c->max_samples, c->rays_a,
                                          c->t_scratch, c->counter, c->xyzs, c->dirs, c->deltas, c->ts, c->capacity, stream)) return e;
     if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
@@ -106,7 +107,7 @@ extern "C" ARN_API int arn_train_fwbw(const arn_train_t* c, arn_stream_t stream)
                               c->rgb_final, c->dL_drgb, c->dL_dopacity, c->dL_ddepth, c->loss_out, stream)) return e;
     if (int e = arn_composite_train_bw(c->dL_dopacity, c->dL_ddepth, c->dL_drgb, nullptr, c->sigmas, c->rgbs, c->ws_out, c->deltas, c->ts, c->rays_a,
                                        c->opacity, c->depth, c->rgb, R, c->capacity, c->T_threshold, c->dL_dsigmas, c->dL_drgbs, stream)) return e;
-    return arn_field_bw_tc_dyn(c->xyzs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16, c->params_rgb_f16,
-                               c->rgb_act, c->ws, c->sigmas, c->rgbs, c->dL_dsigmas, c->dL_drgbs, c->loss_scale, c->dfeat, c->grad_xyz, c->grad_rgb,
-                               nullptr, stream);
+    return field_bw_tc_impl(c->xyzs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16, c->params_rgb_f16,
+                            c->rgb_act, c->ws, c->sigmas, c->rgbs, c->dL_dsigmas, c->dL_drgbs, c->loss_scale, c->dfeat, c->grad_xyz, c->grad_rgb,
+                            nullptr, /*pack_weights=*/false, stream);
 }

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128) march_train_count_kernel(const float* __r
                                                                 const float* __restrict__ hits_t, int64_t n_rays,
                                                                 const uint8_t* __restrict__ bitfield, ArnMarchConsts c,
                                                                 const float* __restrict__ noise, int64_t* __restrict__ rays_a,
-                                                                float* __restrict__ t_scratch) {
+                                                                float* __restrict__ t_scratch, int32_t* __restrict__ counts) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rays) return;
     const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
@@ -158,17 +158,18 @@ __global__ void __launch_bounds__(128) march_train_count_kernel(const float* __r
             t = __fadd_rn(t, dt); N++;
         }
     }
-    rays_a[3 * r + 2] = N;
+    if (counts) counts[r] = N; else rays_a[3 * r + 2] = N;
 }
 
 // Pass 1, warp-cooperative form (arn_march_core.h, "Window form"): one WARP per ray, 32 chain points per turn,
 // ballot/popc compaction of the occupied visited points into t_scratch.  Same counts and t values as the kernel above.
-template <bool CONST_DT>
+// CONST_DT: exp_step_factor == 0 (calc_dt is the constant dt_lo).  FAST: cascades == 1 and grid_size <= 256.
+template <bool CONST_DT, bool FAST>
 __global__ void __launch_bounds__(256) march_train_count_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                                      const float* __restrict__ hits_t, int64_t n_rays,
                                                                      const uint8_t* __restrict__ bitfield, ArnMarchConsts c,
                                                                      const float* __restrict__ noise, int64_t* __restrict__ rays_a,
-                                                                     float* __restrict__ t_scratch) {
+                                                                     float* __restrict__ t_scratch, int32_t* __restrict__ counts) {
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_rays) return;  // warp-uniform
@@ -178,18 +179,17 @@ __global__ void __launch_bounds__(256) march_train_count_warp_kernel(const float
     float* rec = t_scratch ? t_scratch + r * c.max_samples : nullptr;
     int N = 0;
     if (0 <= t1 && t1 < t2) {
-        float base = t1;            // chain point of lane 0
+        // lane j <- j steps along the chain from t1; afterwards every lane advances 32 steps per window
+        float t = t1;
+#pragma unroll
+        for (int j = 0; j < 31; j++) {
+            const float tn = __fadd_rn(t, CONST_DT ? c.dt_lo : arn_calc_dt(c, t));
+            if (lane > j) t = tn;
+        }
         float pending = -INFINITY;  // skip target carried over from the previous window
         for (;;) {
-            // lane j <- j steps along the chain from `base`
-            float t = base;
-#pragma unroll
-            for (int j = 0; j < 31; j++) {
-                const float tn = __fadd_rn(t, CONST_DT ? c.dt_lo : arn_calc_dt(c, t));
-                if (lane > j) t = tn;
-            }
             float x, y, z, dt, tgt;
-            const bool occ = arn_march_probe(c, ray, bitfield, t, x, y, z, dt, tgt);
+            const bool occ = arn_march_probe<FAST, FAST>(c, ray, bitfield, t, x, y, z, dt, tgt);
             const unsigned valid = __ballot_sync(kFull, t < t2);  // a prefix: the chain is increasing
             const unsigned occm = __ballot_sync(kFull, occ);
             const int s0 = __popc(__ballot_sync(kFull, t < pending));  // first lane not passed over by the carried skip
@@ -227,11 +227,61 @@ __global__ void __launch_bounds__(256) march_train_count_warp_kernel(const float
                 const int last = 31 - __clz(vis);
                 pending = __shfl_sync(kFull, occ ? -INFINITY : tgt, last);
             }
-            const float t31 = __shfl_sync(kFull, t, 31);
-            base = __fadd_rn(t31, CONST_DT ? c.dt_lo : arn_calc_dt(c, t31));
+#pragma unroll
+            for (int k = 0; k < 32; k++) t = __fadd_rn(t, CONST_DT ? c.dt_lo : arn_calc_dt(c, t));
         }
     }
-    if (lane == 0) rays_a[3 * r + 2] = N;
+    if (lane == 0) {
+        if (counts) counts[r] = N; else rays_a[3 * r + 2] = N;
+    }
+}
+
+// Exclusive scan of compact per-ray counts -> rays_a[r] = (r, start, N), counter = (total, n_rays).  One CTA per 1024
+// rays: it sums the counts of all earlier rays (coalesced 4-byte loads), scans its own 1024 and writes its rays_a rows
+// as 3072 consecutive 8-byte stores.  (A single CTA walking the 24-byte rows of rays_a is bound by one SM's
+// sector throughput: 20 us for 8192 rays.)
+__global__ void __launch_bounds__(1024) rays_scan_compact_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* __restrict__ rays_a,
+                                                                 int32_t* __restrict__ counter) {
+    __shared__ int64_t warp_pre[32], warp_inc[32];
+    __shared__ int64_t s_start[1024];
+    __shared__ int32_t s_cnt[1024];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t r_base = (int64_t)blockIdx.x * 1024, r = r_base + threadIdx.x;
+    int64_t pre = 0;
+    for (int64_t i = threadIdx.x; i < r_base; i += 1024) pre += counts[i];
+    const int32_t mine = r < n_rays ? counts[r] : 0;
+    int64_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += u; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(kFull, pre, o);
+    if (lane == 31) warp_inc[wid] = inc;
+    if (lane == 0) warp_pre[wid] = pre;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t s = warp_inc[lane], p = warp_pre[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, s, o); if (lane >= o) s += u; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(kFull, p, o);
+        warp_inc[lane] = s;  // inclusive over warps
+        warp_pre[lane] = p;  // every entry: total of the earlier blocks
+    }
+    __syncthreads();
+    const int64_t before = warp_pre[0];
+    s_start[threadIdx.x] = before + (wid ? warp_inc[wid - 1] : 0) + inc - mine;
+    s_cnt[threadIdx.x] = mine;
+    __syncthreads();
+    const int64_t rows = min((int64_t)1024, n_rays - r_base);
+    for (int64_t e = threadIdx.x; e < 3 * rows; e += 1024) {
+        const int ray = (int)(e / 3), f = (int)(e % 3);
+        rays_a[3 * r_base + e] = f == 0 ? r_base + ray : (f == 1 ? s_start[ray] : (int64_t)s_cnt[ray]);
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        const int64_t tot = before + warp_inc[31];
+        counter[0] = (int32_t)(tot > 0x7fffffff ? 0x7fffffff : tot);
+        counter[1] = (int32_t)(n_rays > 0x7fffffff ? 0x7fffffff : n_rays);
+    }
 }
 
 // Exclusive scan of the counts: rays_a[r] = (r, start, N); counter = (total, n_rays).  Single CTA: thread i owns the
@@ -662,11 +712,12 @@ static int check_march_cfg(int cascades, int grid_size, int max_samples) {
     return ARN_OK;
 }
 
-// t_scratch is carried through a second entry point so the published signature stays the reference's argument list.
+// t_scratch / count_scratch are carried through a second entry point so the published signature stays the reference's
+// argument list.  count_scratch (n_rays i32, optional): compact per-ray counts for the multi-CTA scan.
 extern "C" ARN_API int arn_march_train_count_ex(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
                                         const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
                                         float exp_step_factor, const float* noise, int max_samples, int64_t* rays_a,
-                                        int32_t* counter, float* t_scratch, arn_stream_t stream) {
+                                        int32_t* counter, float* t_scratch, int32_t* count_scratch, arn_stream_t stream) {
     ARN_REQUIRE(n_rays >= 0, "bad size");
     ARN_REQUIRE(counter, "null counter");
     if (int e = check_march_cfg(cascades, grid_size, max_samples)) return e;
@@ -675,14 +726,21 @@ extern "C" ARN_API int arn_march_train_count_ex(const float* rays_o, const float
     ARN_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && noise && rays_a, "null pointer");
     const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
     if (!tunable(kTunMarchWarp)) {
-        ARN_LAUNCH("march_train_count_kernel", st, march_train_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch));
-    } else if (exp_step_factor == 0.0f && c.dt_hi >= 0.0f) {  // calc_dt is the constant dt_lo
-        ARN_LAUNCH("march_train_count_warp_kernel", st, march_train_count_warp_kernel<true><<<ceil_div(n_rays * 32, 256), 256, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch));
+        ARN_LAUNCH("march_train_count_kernel", st, march_train_count_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch, count_scratch));
     } else {
-        ARN_LAUNCH("march_train_count_warp_kernel", st, march_train_count_warp_kernel<false><<<ceil_div(n_rays * 32, 256), 256, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch));
+        const bool const_dt = exp_step_factor == 0.0f && c.dt_hi >= 0.0f;  // calc_dt is the constant dt_lo
+        const bool fast = cascades == 1 && grid_size <= 256;
+        const int grid = ceil_div(n_rays * 32, 256);
+#define ARN_MARCH_WARP(CD, FA) ARN_LAUNCH("march_train_count_warp_kernel", st, (march_train_count_warp_kernel<CD, FA><<<grid, 256, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch, count_scratch)))
+        if (const_dt && fast) ARN_MARCH_WARP(true, true);
+        else if (const_dt) ARN_MARCH_WARP(true, false);
+        else if (fast) ARN_MARCH_WARP(false, true);
+        else ARN_MARCH_WARP(false, false);
+#undef ARN_MARCH_WARP
     }
     if (int e = check_launch("march_train_count")) return e;
-    ARN_LAUNCH("rays_scan_kernel", st, rays_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, counter));
+    if (count_scratch) ARN_LAUNCH("rays_scan_compact_kernel", st, rays_scan_compact_kernel<<<ceil_div(n_rays, 1024), 1024, 0, st>>>(count_scratch, n_rays, rays_a, counter));
+    else ARN_LAUNCH("rays_scan_kernel", st, rays_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, counter));
     return check_launch("rays_scan");
 }
 extern "C" ARN_API int arn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
@@ -690,7 +748,7 @@ extern "C" ARN_API int arn_march_train_count(const float* rays_o, const float* r
                                      float exp_step_factor, const float* noise, int max_samples, int64_t* rays_a,
                                      int32_t* counter, arn_stream_t stream) {
     return arn_march_train_count_ex(rays_o, rays_d, hits_t, n_rays, density_bitfield, cascades, grid_size, scale,
-                                    exp_step_factor, noise, max_samples, rays_a, counter, nullptr, stream);
+                                    exp_step_factor, noise, max_samples, rays_a, counter, nullptr, nullptr, stream);
 }
 
 extern "C" ARN_API int arn_march_train_emit_ex(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,

@@ -14,7 +14,7 @@ from torch import nn
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
-from ._lib import FieldWs, Levels, call, ptr, stream
+from ._lib import FIELD_SCRATCH_BYTES, FieldWs, Levels, call, ptr, stream
 
 N_LEVELS = 16
 DENSITY_MLP_PARAMS = 3072
@@ -123,7 +123,7 @@ class FieldState:
 
 def _workspace(n, device, with_rgb):
     e = lambda *s, dt=torch.float16: torch.empty(*s, dtype=dt, device=device)
-    ws = dict(feat=e(n, 32), hid=e(n, 64), h=e(n, 16, dt=torch.float32), wimg=torch.empty(20480, dtype=torch.uint8, device=device))
+    ws = dict(feat=e(n, 32), hid=e(n, 64), h=e(n, 16, dt=torch.float32), wimg=torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device))
     if with_rgb:
         ws.update(in32=e(n, 32), hid1=e(n, 64), hid2=e(n, 64))
     return ws

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from ._lib import FieldWs, TrainCfg, call, ptr, stream
+from ._lib import FIELD_SCRATCH_BYTES, FieldWs, TrainCfg, call, ptr, stream
 from .losses import NeRFLoss
 from .rendering import MAX_SAMPLES, NEAR_DISTANCE, render
 
@@ -53,6 +53,7 @@ class _FusedWorkspace:
         self.hits_t, self.rays_a = f(R, 1, 2), torch.empty(R, 3, dtype=torch.int64, device=device)
         self.counter = torch.zeros(2, dtype=torch.int32, device=device)
         self.t_scratch = f(R * MAX_SAMPLES)
+        self.count_scratch = torch.empty(R, dtype=torch.int32, device=device)
         self.total_samples = torch.empty(R, dtype=torch.int64, device=device)
         self.opacity, self.depth, self.rgb, self.rgb_final = f(R), f(R), f(R, 3), f(R, 3)
         self.dL_dopacity, self.dL_ddepth, self.dL_drgb = f(R), f(R), f(R, 3)
@@ -61,7 +62,7 @@ class _FusedWorkspace:
         self.dL_dsigmas, self.dL_drgbs, self.dfeat = f(N), f(N, 3), f(N, 32)
         self.feat, self.hid, self.h = h(N, 32), h(N, 64), f(N, 16)
         self.in32, self.hid1, self.hid2 = h(N, 32), h(N, 64), h(N, 64)
-        self.wimg = torch.empty(20480, dtype=torch.uint8, device=device)
+        self.wimg = torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=device)
 
 
@@ -115,7 +116,7 @@ class NGPTrainer:
             cast(self._host[0]), cast(self._host[1]), cast(st.mn), cast(st.mx),
             st.geometry.c_levels, ptr(p16x), ptr(p16c), st.rgb_act,
             cast(self._host[2]), float(self.loss.lambda_opacity), float(self.depth_loss_w), float(self.grad_scale), float(st.loss_scale),
-            ptr(w.hits_t), ptr(w.rays_a), ptr(w.counter), ptr(w.t_scratch), ptr(w.total_samples),
+            ptr(w.hits_t), ptr(w.rays_a), ptr(w.counter), ptr(w.t_scratch), ptr(w.count_scratch), ptr(w.total_samples),
             ptr(w.opacity), ptr(w.depth), ptr(w.rgb), ptr(w.rgb_final), ptr(w.dL_dopacity), ptr(w.dL_ddepth), ptr(w.dL_drgb),
             w.capacity, ptr(w.xyzs), ptr(w.dirs), ptr(w.deltas), ptr(w.ts), ptr(w.sigmas), ptr(w.rgbs), ptr(w.ws_out),
             ptr(w.dL_dsigmas), ptr(w.dL_drgbs), ptr(w.dfeat),

@@ -16,6 +16,9 @@ _T_SCRATCH = {}
 _T_SCRATCH_LIMIT = 8 << 30  # bytes; larger requests fall back to the re-march emit
 
 
+_COMPACT_SCAN = True  # tests flip it to cover the single-CTA scan over the rays_a rows
+
+
 def _t_scratch(device, n):
     buf = _T_SCRATCH.get(device)
     if buf is None or buf.numel() < n:
@@ -107,8 +110,9 @@ def raymarching_train(rays_o, rays_d, hits_t, density_bitfield, cascades, scale,
     t_scratch = _t_scratch(dev, scratch_n) if 0 < scratch_n * 4 <= _T_SCRATCH_LIMIT else None
     cfg = (ptr(density_bitfield), int(cascades), int(grid_size), float(scale), float(exp_step_factor), ptr(noise),
            int(max_samples))
+    count_scratch = torch.empty(R, dtype=torch.int32, device=dev) if _COMPACT_SCAN else None
     call("arn_march_train_count_ex", ptr(rays_o), ptr(rays_d), ptr(hits_t), R, *cfg, ptr(rays_a), ptr(counter),
-         ptr(t_scratch), stream())
+         ptr(t_scratch), ptr(count_scratch), stream())
     total = int(counter[0].item()) if R > 0 else 0  # the one host sync the reference has too (custom_functions.py:91-96)
     xyzs = torch.empty(total, 3, dtype=torch.float32, device=dev)
     dirs = torch.empty(total, 3, dtype=torch.float32, device=dev)

@@ -98,7 +98,8 @@ int arn_march_train_emit(const float* rays_o, const float* rays_d, const float* 
 int arn_march_train_count_ex(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
                              const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
                              float exp_step_factor, const float* noise, int max_samples,
-                             int64_t* rays_a, int32_t* counter, float* t_scratch, arn_stream_t stream);
+                             int64_t* rays_a, int32_t* counter, float* t_scratch, int32_t* count_scratch,
+                             arn_stream_t stream);
 int arn_march_train_emit_ex(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
                             const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
                             float exp_step_factor, const float* noise, int max_samples, const int64_t* rays_a,
@@ -179,9 +180,13 @@ typedef struct {
  *   h     (n,16) f32   density-net output (h[:,0] = log sigma)
  *   in32  (n,32) f16   colour-net input [sh16 | h16]         hid1, hid2 (n,64) f16  colour hidden layers
  * For a density-only evaluation (NGP.density) dirs, in32, hid1, hid2, rgbs and params_rgb_f16 are NULL. */
+#define ARN_FIELD_SCRATCH_SLABS 512
+#define ARN_FIELD_SCRATCH_BYTES (20480 + ARN_FIELD_SCRATCH_SLABS * 10240 * 4)
 typedef struct {
     void* feat; void* hid; float* h; void* in32; void* hid1; void* hid2;
-    void* wimg; /* 20480 B scratch: the MLP weights as swizzled tcgen05 operand tiles (rebuilt every forward) */
+    /* ARN_FIELD_SCRATCH_BYTES of scratch: [0, 20480) the MLP weights as swizzled tcgen05 operand tiles (rebuilt every
+     * call), then one 10240-float slab of weight gradients per backward CTA, summed in slab order after the kernel. */
+    void* wimg;
 } arn_field_ws_t;
 
 /* Forward.  xyzs (n,3) world coordinates, normalised inside with (x - xyz_min)/(xyz_max - xyz_min) (networks.py:104);
@@ -252,7 +257,7 @@ typedef struct {
     /* loss (losses.py:41-82, 'raw') and scaling */
     const float* bg_host; float lambda_opacity; float lambda_depth; float grad_scale; float loss_scale;
     /* workspace (device), per ray */
-    float* hits_t; int64_t* rays_a; int32_t* counter; float* t_scratch; int64_t* total_samples;
+    float* hits_t; int64_t* rays_a; int32_t* counter; float* t_scratch; int32_t* count_scratch; int64_t* total_samples;
     float* opacity; float* depth; float* rgb; float* rgb_final; float* dL_dopacity; float* dL_ddepth; float* dL_drgb;
     /* workspace (device), per sample, `capacity` entries */
     int64_t capacity; float* xyzs; float* dirs; float* deltas; float* ts; float* sigmas; float* rgbs; float* ws_out;

@@ -57,15 +57,18 @@ extern "C" void h_march_train_window(int n_rays, const float* o, const float* d,
         float* rec = t_rec + (size_t)r * max_samples;
         int N = 0;
         if (0 <= t1 && t1 < t2) {
-            float base = t1, pending = -INFINITY;
+            float pending = -INFINITY;
+            float t[32];
+            t[0] = t1;
+            for (int j = 1; j < 32; j++) t[j] = ARN_ADD(t[j - 1], arn_calc_dt(c, t[j - 1]));
+            const bool fast = cascades == 1 && grid <= 256;
             for (;;) {
-                float t[32], tgt[32]; bool occ[32]; int R[32]; uint32_t M[32];
-                t[0] = base;
-                for (int j = 1; j < 32; j++) t[j] = ARN_ADD(t[j - 1], arn_calc_dt(c, t[j - 1]));
+                float tgt[32]; bool occ[32]; int R[32]; uint32_t M[32];
                 uint32_t valid = 0, occm = 0; int s0 = 0;
                 for (int l = 0; l < 32; l++) {
                     float x, y, z, dt;
-                    occ[l] = arn_march_probe(c, ray, bits, t[l], x, y, z, dt, tgt[l]);
+                    occ[l] = fast ? arn_march_probe<true, true>(c, ray, bits, t[l], x, y, z, dt, tgt[l])
+                                  : arn_march_probe<false, false>(c, ray, bits, t[l], x, y, z, dt, tgt[l]);
                     if (t[l] < t2) valid |= 1u << l;
                     if (occ[l]) occm |= 1u << l;
                     if (t[l] < pending) s0++;
@@ -98,7 +101,8 @@ extern "C" void h_march_train_window(int n_rays, const float* o, const float* d,
                 N += popc32(emit);
                 if (done) break;
                 if (vis) { const int last = 31 - __builtin_clz(vis); pending = occ[last] ? -INFINITY : tgt[last]; }
-                base = ARN_ADD(t[31], arn_calc_dt(c, t[31]));
+                for (int l = 0; l < 32; l++)
+                    for (int k = 0; k < 32; k++) t[l] = ARN_ADD(t[l], arn_calc_dt(c, t[l]));
             }
         }
         counts[r] = N;

@@ -163,6 +163,14 @@ def test_march_train_bit_exact(kind, n_rays, w1, w3, vren, ref):
         _lib.set_tunable("march_warp", 1)
     for a, b in zip(out, out3):
         assert torch.equal(a, b)
+    # the single-CTA scan over the rays_a rows (no compact count scratch: the plain reference-signature entry point)
+    try:
+        v._COMPACT_SCAN = False
+        out4 = vren.raymarching_train(T(ro), T(rd), T(ht), T(w.bitfield), *cfg, T(noise), 128, 1024)
+    finally:
+        v._COMPACT_SCAN = True
+    for a, b in zip(out, out4):
+        assert torch.equal(a, b)
     if ref is not None:
         r_out = ref.raymarching_train(T(ro), T(rd), T(ht), T(w.bitfield), *cfg, T(noise), 128, 1024)
         n, rx, rdirs, rdl, rts, total = refvren.canonical_train(r_out)
@@ -444,7 +452,7 @@ def test_hash_backward_variants_agree(kind, w1, w3, vren):
     o_geo = oracle.HashGeometry(per_level_scale=geo.per_level_scale)
     o_tg, _ = oracle.hash_encode_bw(x01.astype(np.float32), o_geo, np.zeros(geo.total * 2, np.float16), N(dfeat))
     for mode in (8, 16, 32, 64):
-        assert_rel(res[mode], res[0], rtol=1e-5, floor=1.0, what=f"hash bw runs seg {mode} vs per-sample")
+        assert_rel(res[mode], res[0], rtol=5e-5, floor=1.0, what=f"hash bw runs seg {mode} vs per-sample")
         assert_rel(res[mode], o_tg.reshape(-1), rtol=RTOL, floor=1.0, what=f"hash bw runs seg {mode} vs oracle")
 
 
