@@ -32,13 +32,18 @@ __global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __rest
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float w[3]; uint32_t g[3];
     level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
-    const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
+    uint32_t idx[8]; float wt[8];
+    corner_indices(tbl.mode[l], tbl.size[l], tbl.res[l], g, idx);
+    corner_weights(w, wt);
+    const __half2* lvl = table + tbl.offset[l];
+    __half2 tv[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) tv[c] = lvl[idx[c]];  // eight independent gathers in flight
     float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-        uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
-        const float2 v = __half22float2(table[off + grid_index(size, res, p)]);
-        acc0 = __fmaf_rn(wt, v.x, acc0); acc1 = __fmaf_rn(wt, v.y, acc1);
+        const float2 v = __half22float2(tv[c]);
+        acc0 = __fmaf_rn(wt[c], v.x, acc0); acc1 = __fmaf_rn(wt[c], v.y, acc1);
     }
     feat[i * ARN_N_LEVELS + l] = __floats2half2_rn(acc0, acc1);
     }
@@ -55,12 +60,12 @@ __global__ void __launch_bounds__(256) hash_encode_bw_kernel(const float* __rest
     if (d.x == 0.0f && d.y == 0.0f) continue;
     float w[3]; uint32_t g[3];
     level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
-    const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
+    uint32_t idx[8]; float wt[8];
+    corner_indices(tbl.mode[l], tbl.size[l], tbl.res[l], g, idx);
+    corner_weights(w, wt);
+    float2* lvl = table_grad + tbl.offset[l];
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
-        atomicAdd(table_grad + off + grid_index(size, res, p), make_float2(wt * d.x, wt * d.y));
-    }
+    for (int c = 0; c < 8; c++) atomicAdd(lvl + idx[c], make_float2(wt[c] * d.x, wt[c] * d.y));
     }
 }
 
@@ -108,7 +113,8 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
     if (n_dev) n = min(n, (int64_t)*n_dev);
     const int l = (threadIdx.x & 15);
     const int64_t n_seg = (n + SEG - 1) / SEG;
-    const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
+    const uint32_t size = tbl.size[l], res = tbl.res[l], mode = tbl.mode[l];
+    float2* lvl = table_grad + tbl.offset[l];
     const float scale = tbl.scale[l];
     const bool active = l >= level0 && l < level0 + nlevels;
     for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; seg < n_seg; seg += ((int64_t)gridDim.x * blockDim.x) >> 4) {
@@ -119,38 +125,29 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
 #pragma unroll
         for (int c = 0; c < 8; c++) acc[c] = make_float2(0.f, 0.f);
         bool dirty = false;
+        auto flush = [&]() {
+            uint32_t idx[8];
+            corner_indices(mode, size, res, cg, idx);
+#pragma unroll
+            for (int c = 0; c < 8; c++) { atomicAdd(lvl + idx[c], acc[c]); acc[c] = make_float2(0.f, 0.f); }
+        };
         for (int64_t i = i0; i < i1; i++) {
             const float2 d = dfeat[i * ARN_N_LEVELS + l];
             float w[3]; uint32_t g[3];
             level_position(xyzs + 3 * i, box, scale, w, g);
             if (g[0] != cg[0] || g[1] != cg[1] || g[2] != cg[2]) {
-                if (dirty) {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        const uint32_t p[3] = {cg[0] + (c & 1), cg[1] + ((c >> 1) & 1), cg[2] + ((c >> 2) & 1)};
-                        atomicAdd(table_grad + off + grid_index(size, res, p), acc[c]);
-                        acc[c] = make_float2(0.f, 0.f);
-                    }
-                    dirty = false;
-                }
+                if (dirty) { flush(); dirty = false; }
                 cg[0] = g[0]; cg[1] = g[1]; cg[2] = g[2];
             }
             if (d.x != 0.0f || d.y != 0.0f) {
+                float wt[8];
+                corner_weights(w, wt);
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    uint32_t p[3]; const float wt = corner_weight(c, w, g, p);
-                    acc[c].x += wt * d.x; acc[c].y += wt * d.y;
-                }
+                for (int c = 0; c < 8; c++) { acc[c].x += wt[c] * d.x; acc[c].y += wt[c] * d.y; }
                 dirty = true;
             }
         }
-        if (dirty) {
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const uint32_t p[3] = {cg[0] + (c & 1), cg[1] + ((c >> 1) & 1), cg[2] + ((c >> 2) & 1)};
-                atomicAdd(table_grad + off + grid_index(size, res, p), acc[c]);
-            }
-        }
+        if (dirty) flush();
     }
 }
 
@@ -553,12 +550,24 @@ int make_levels(const arn_levels_t& lv, LevelTable& t) {
     for (int l = 0; l < ARN_N_LEVELS; l++) {
         t.scale[l] = lv.scale_host[l]; t.res[l] = lv.res_host[l]; t.size[l] = lv.size_host[l]; t.offset[l] = lv.offset_host[l];
         if (t.size[l] == 0) { set_error("levels: empty level"); return ARN_E_INVALID; }
+        // run grid_index's stride loop once (uint32 arithmetic, as on the device) to classify the level
+        uint32_t stride = 1; int dims = 0;
+        for (int d = 0; d < 3; d++) if (stride <= t.size[l]) { stride *= t.res[l]; dims++; }
+        const bool hashed = t.size[l] < stride;
+        const bool pow2 = (t.size[l] & (t.size[l] - 1u)) == 0;
+        const bool fits = (uint64_t)t.res[l] * t.res[l] * t.res[l] <= (uint64_t)t.size[l];
+        t.mode[l] = hashed ? (pow2 ? kIdxHashPow2 : kIdxGeneric) : ((dims == 3 && fits) ? kIdxDense : kIdxGeneric);
     }
     return ARN_OK;
 }
 int make_box(const float* mn, const float* mx, Aabb& b) {
     if (!mn || !mx) { set_error("aabb: null host pointer"); return ARN_E_INVALID; }
-    for (int k = 0; k < 3; k++) { b.mn[k] = mn[k]; b.mx[k] = mx[k]; }
+    for (int k = 0; k < 3; k++) {
+        b.mn[k] = mn[k]; b.mx[k] = mx[k];
+        const float ext = mx[k] - mn[k];
+        int e = 0;
+        b.inv[k] = (ext > 0.0f && frexpf(ext, &e) == 0.5f && e > -100 && e < 100) ? 1.0f / ext : 0.0f;
+    }
     return ARN_OK;
 }
 }  // namespace arn

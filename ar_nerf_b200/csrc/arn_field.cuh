@@ -5,13 +5,21 @@
 
 namespace arn {
 
-struct LevelTable {  // 256 B, passed by value (__grid_constant__)
+// Index rule of a level, decided once on the host (make_levels) by running tiny-cuda-nn's grid_index stride loop:
+//   kIdxDense   all three strides fit: index = x + y*res + z*res^2, reduced mod size only in the (boundary) case index >= size
+//   kIdxHashPow2  hashed and size is a power of two: index = hash & (size - 1)
+//   kIdxGeneric anything else: the literal rule (grid_index below)
+enum : uint32_t { kIdxDense = 0, kIdxHashPow2 = 1, kIdxGeneric = 2 };
+struct LevelTable {  // 320 B, passed by value (__grid_constant__)
     float scale[ARN_N_LEVELS];
     uint32_t res[ARN_N_LEVELS];
     uint32_t size[ARN_N_LEVELS];
     uint32_t offset[ARN_N_LEVELS];
+    uint32_t mode[ARN_N_LEVELS];
 };
-struct Aabb { float mn[3], mx[3]; };
+// inv[d] = 1/(mx-mn) when that extent is a power of two (every NGP box: 2*scale), else 0: dividing by a power of two and
+// multiplying by its reciprocal round the same real number, so the product is bit-identical with the IEEE division.
+struct Aabb { float mn[3], mx[3], inv[3]; };
 
 int make_levels(const arn_levels_t& lv, LevelTable& t);
 int make_box(const float* mn, const float* mx, Aabb& b);
@@ -36,7 +44,8 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t hashmap_size, uint32_t r
 __device__ __forceinline__ void level_position(const float* __restrict__ xyz, const Aabb& box, float scale, float w[3], uint32_t g[3]) {
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-        const float x01 = __fdiv_rn(__fsub_rn(xyz[d], box.mn[d]), __fsub_rn(box.mx[d], box.mn[d]));
+        const float num = __fsub_rn(xyz[d], box.mn[d]);
+        const float x01 = box.inv[d] != 0.0f ? __fmul_rn(num, box.inv[d]) : __fdiv_rn(num, __fsub_rn(box.mx[d], box.mn[d]));
         const float pos = __fmaf_rn(scale, x01, 0.5f);
         const float fl = floorf(pos);
         w[d] = __fsub_rn(pos, fl); g[d] = (uint32_t)(int32_t)fl;
@@ -52,6 +61,40 @@ __device__ __forceinline__ float corner_weight(int c, const float w[3], const ui
         else { wt = __fmul_rn(wt, __fsub_rn(1.0f, w[d])); p[d] = g[d]; }
     }
     return wt;
+}
+
+// The 8 corner indices (c = cx + 2*cy + 4*cz, cell corner g + (cx,cy,cz)) and weights of one (sample, level): same
+// values as grid_index / corner_weight corner by corner, with the shared sub-terms computed once.
+__device__ __forceinline__ void corner_indices(uint32_t mode, uint32_t size, uint32_t res, const uint32_t g[3], uint32_t idx[8]) {
+    if (mode == kIdxHashPow2) {
+        const uint32_t m = size - 1u;
+        const uint32_t hx[2] = {g[0], g[0] + 1u};
+        const uint32_t hy0 = g[1] * 2654435761u, hz0 = g[2] * 805459861u;
+        const uint32_t hy[2] = {hy0, hy0 + 2654435761u}, hz[2] = {hz0, hz0 + 805459861u};
+#pragma unroll
+        for (int c = 0; c < 8; c++) idx[c] = (hx[c & 1] ^ hy[(c >> 1) & 1] ^ hz[(c >> 2) & 1]) & m;
+    } else if (mode == kIdxDense) {
+        const uint32_t sy = res, sz = res * res;
+        const uint32_t b = g[0] + g[1] * sy + g[2] * sz;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint32_t i = b + (uint32_t)(c & 1) + ((c & 2) ? sy : 0u) + ((c & 4) ? sz : 0u);
+            if (i >= size) i %= size;  // only for x01 == 1 or positions outside the box
+            idx[c] = i;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint32_t p[3] = {g[0] + (uint32_t)(c & 1), g[1] + (uint32_t)((c >> 1) & 1), g[2] + (uint32_t)((c >> 2) & 1)};
+            idx[c] = grid_index(size, res, p);
+        }
+    }
+}
+// corner_weight's product ((1*ax)*ay)*az with 1*ax == ax: four xy products shared by the two z values
+__device__ __forceinline__ void corner_weights(const float w[3], float wt[8]) {
+    const float ax[2] = {__fsub_rn(1.0f, w[0]), w[0]}, ay[2] = {__fsub_rn(1.0f, w[1]), w[1]}, az[2] = {__fsub_rn(1.0f, w[2]), w[2]};
+#pragma unroll
+    for (int c = 0; c < 8; c++) wt[c] = __fmul_rn(__fmul_rn(ax[c & 1], ay[(c >> 1) & 1]), az[(c >> 2) & 1]);
 }
 
 // SH degree 4 of d/|d| routed through u = (d^+1)/2 and x = 2u-1 exactly as networks.py:144-145 + tcnn do (Appendix A.4)

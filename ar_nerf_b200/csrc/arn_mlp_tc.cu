@@ -526,21 +526,25 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-// grad += sum over the CTAs' slabs, in slab order (deterministic).  One thread per weight; 10240 weights.
+// grad += sum over the CTAs' slabs in a fixed order (deterministic).  A block owns 32 consecutive weights: warp w adds
+// the slabs k = w, w+8, ... (128-byte coalesced rows), the eight partial sums are combined in warp order.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ wpart, int n_slabs, int with_rgb,
                                                            float* __restrict__ dWd, float* __restrict__ dWc) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= kWgradFloats) return;
-    if (e < 7168 && !with_rgb) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int k = 0;
-    for (; k + 3 < n_slabs; k += 4) {
-        s0 += wpart[(size_t)k * kWgradFloats + e]; s1 += wpart[(size_t)(k + 1) * kWgradFloats + e];
-        s2 += wpart[(size_t)(k + 2) * kWgradFloats + e]; s3 += wpart[(size_t)(k + 3) * kWgradFloats + e];
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
+    float s0 = 0.f, s1 = 0.f;
+    int k = w;
+    for (; k + 8 < n_slabs; k += 16) { s0 += wpart[(size_t)k * kWgradFloats + e]; s1 += wpart[(size_t)(k + 8) * kWgradFloats + e]; }
+    if (k < n_slabs) s0 += wpart[(size_t)k * kWgradFloats + e];
+    part[w][lane] = s0 + s1;
+    __syncthreads();
+    if (w == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) sum += part[j][lane];
+        if (e < 7168) { if (with_rgb) dWc[e] += sum; } else dWd[e - 7168] += sum;
     }
-    for (; k < n_slabs; k++) s0 += wpart[(size_t)k * kWgradFloats + e];
-    const float sum = (s0 + s1) + (s2 + s3);
-    if (e < 7168) dWc[e] += sum; else dWd[e - 7168] += sum;
 }
 
 }  // namespace arn
@@ -592,7 +596,7 @@ int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, co
         (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, grad_params_xyz,
         grad_params_rgb, dfeat_scratch, wpart));
     if (int e = check_launch("field_mlp_bw_tc")) return e;
-    ARN_LAUNCH("wgrad_reduce_kernel", st, arn::wgrad_reduce_kernel<<<arn::kWgradFloats / 256, 256, 0, st>>>(wpart, grid, with_rgb ? 1 : 0, grad_params_xyz, grad_params_rgb));
+    ARN_LAUNCH("wgrad_reduce_kernel", st, arn::wgrad_reduce_kernel<<<arn::kWgradFloats / 32, 256, 0, st>>>(wpart, grid, with_rgb ? 1 : 0, grad_params_xyz, grad_params_rgb));
     if (int e = check_launch("wgrad_reduce")) return e;
     return arn_hash_encode_bw_dyn(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
                                   grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, stream);

@@ -449,9 +449,15 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
     float T = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
     int64_t samples = N; bool done = false;
     int base = 0;
+    // the next 32 samples are requested before the current 32 go through the scans: a long ray no longer pays one
+    // exposed load latency per chunk
+    float n_sg = 0.f, n_dl = 0.f, n_cr = 0.f, n_cg = 0.f, n_cb = 0.f, n_ct = 0.f;
+    if (lane < N) { const int64_t s = start + lane; n_sg = sigmas[s]; n_dl = deltas[s]; n_cr = rgbs[3 * s]; n_cg = rgbs[3 * s + 1]; n_cb = rgbs[3 * s + 2]; n_ct = ts[s]; }
     for (; base < N && !done; base += 32) {
         const int i = base + lane; const bool in = i < N; const int64_t s = start + i;
-        const float a = in ? alpha_of(sigmas[s], deltas[s]) : 0.0f;
+        const float c_sg = n_sg, c_dl = n_dl, c_cr = n_cr, c_cg = n_cg, c_cb = n_cb, c_ct = n_ct;
+        if (i + 32 < N) { const int64_t q = s + 32; n_sg = sigmas[q]; n_dl = deltas[q]; n_cr = rgbs[3 * q]; n_cg = rgbs[3 * q + 1]; n_cb = rgbs[3 * q + 2]; n_ct = ts[q]; }
+        const float a = in ? alpha_of(c_sg, c_dl) : 0.0f;
         const float incl = warp_incl_prod(__fsub_rn(1.0f, a), lane);
         float excl = __shfl_up_sync(kFull, incl, 1); if (lane == 0) excl = 1.0f;
         const float T_before = T * excl, T_after = T * incl;
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
         const float w = use ? a * T_before : 0.0f;
         if (in) ws[s] = w;
         float cr = 0.f, cg = 0.f, cb = 0.f, ct = 0.f;
-        if (use) { cr = rgbs[3 * s]; cg = rgbs[3 * s + 1]; cb = rgbs[3 * s + 2]; ct = ts[s]; }
+        if (use) { cr = c_cr; cg = c_cg; cb = c_cb; ct = c_ct; }
         acc_r += warp_sum(w * cr); acc_g += warp_sum(w * cg); acc_b += warp_sum(w * cb);
         acc_d += warp_sum(w * ct); acc_o += warp_sum(w);
         if (term) { done = true; samples = base + last; }  // break happens before samples++ (:40-41)
@@ -502,12 +508,20 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(const float* __
     }
     float T = 1.0f, r = 0.f, g = 0.f, b = 0.f, d = 0.f, ww = 0.f;
     bool done = false; int base = 0;
+    float n_sg = 0.f, n_dl = 0.f, n_cr = 0.f, n_cg = 0.f, n_cb = 0.f, n_ct = 0.f, n_gw = 0.f, n_ws = 0.f;  // prefetched chunk (see the forward)
+    if (lane < N) {
+        const int64_t s = start + lane;
+        n_sg = sigmas[s]; n_dl = deltas[s]; n_cr = rgbs[3 * s]; n_cg = rgbs[3 * s + 1]; n_cb = rgbs[3 * s + 2]; n_ct = ts[s];
+        if (dL_dws) { n_gw = dL_dws[s]; n_ws = ws[s]; }
+    }
     for (; base < N && !done; base += 32) {
         const int i = base + lane; const bool in = i < N; const int64_t s = start + i;
         float sg = 0.f, dl = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, ct = 0.f, gw = 0.f, wsv = 0.f;
-        if (in) {
-            sg = sigmas[s]; dl = deltas[s]; cr = rgbs[3 * s]; cg = rgbs[3 * s + 1]; cb = rgbs[3 * s + 2]; ct = ts[s];
-            if (dL_dws) { gw = dL_dws[s]; wsv = ws[s]; }
+        if (in) { sg = n_sg; dl = n_dl; cr = n_cr; cg = n_cg; cb = n_cb; ct = n_ct; gw = n_gw; wsv = n_ws; }
+        if (i + 32 < N) {
+            const int64_t q = s + 32;
+            n_sg = sigmas[q]; n_dl = deltas[q]; n_cr = rgbs[3 * q]; n_cg = rgbs[3 * q + 1]; n_cb = rgbs[3 * q + 2]; n_ct = ts[q];
+            if (dL_dws) { n_gw = dL_dws[q]; n_ws = ws[q]; }
         }
         const float a = in ? alpha_of(sg, dl) : 0.0f;
         const float incl = warp_incl_prod(__fsub_rn(1.0f, a), lane);
