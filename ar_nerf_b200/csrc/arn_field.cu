@@ -26,10 +26,15 @@ __global__ void __launch_bounds__(256) cast_f32_f16_kernel(const float* __restri
 // Forward, one thread per (sample, level) -- SURVEY Appendix A.3.
 __global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                              const __grid_constant__ LevelTable tbl,
-                                                             const __half2* __restrict__ table, __half2* __restrict__ feat) {
+                                                             const __half2* __restrict__ table, __half2* __restrict__ feat, int img) {
     if (n_dev) n = min(n, (int64_t)*n_dev);
     const int l = blockIdx.y;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // tile image: the rows that pad the last 128-row tile are written as zeros (the MLP kernels move whole tiles, and the
+    // backward multiplies them by zero gradients: they must be finite)
+    const int64_t n_rows = img ? ((n + 127) & ~(int64_t)127) : n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t col = img ? ((img_chunk64(i, (uint32_t)l >> 2) << 2) | ((uint32_t)l & 3u)) : (uint32_t)l;
+    if (i >= n) { feat[i * ARN_N_LEVELS + col] = __floats2half2_rn(0.0f, 0.0f); continue; }
     float w[3]; uint32_t g[3];
     level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
     uint32_t idx[8]; float wt[8];
@@ -45,18 +50,23 @@ __global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __rest
         const float2 v = __half22float2(tv[c]);
         acc0 = __fmaf_rn(wt[c], v.x, acc0); acc1 = __fmaf_rn(wt[c], v.y, acc1);
     }
-    feat[i * ARN_N_LEVELS + l] = __floats2half2_rn(acc0, acc1);
+    // a 64-byte feature row = 4 chunks of 4 levels; tile image: chunk permuted (arn_field.cuh)
+    feat[i * ARN_N_LEVELS + col] = __floats2half2_rn(acc0, acc1);
     }
 }
 
 // Backward into the table, one thread per (sample, level): vector red.global.add.v2.f32 per corner.
+// dfeat row = 128 bytes = 8 chunks of 2 levels (float2 each); tile image: chunk permuted (arn_field.cuh)
+__device__ __forceinline__ uint32_t dfeat_col(int img, int64_t i, int l) {
+    return img ? ((img_chunk128(i, (uint32_t)l >> 1) << 1) | ((uint32_t)l & 1u)) : (uint32_t)l;
+}
 __global__ void __launch_bounds__(256) hash_encode_bw_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                              const __grid_constant__ LevelTable tbl,
-                                                             const float2* __restrict__ dfeat, float2* __restrict__ table_grad) {
+                                                             const float2* __restrict__ dfeat, float2* __restrict__ table_grad, int img) {
     if (n_dev) n = min(n, (int64_t)*n_dev);
     const int l = blockIdx.y;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float2 d = dfeat[i * ARN_N_LEVELS + l];
+    const float2 d = dfeat[i * ARN_N_LEVELS + dfeat_col(img, i, l)];
     if (d.x == 0.0f && d.y == 0.0f) continue;
     float w[3]; uint32_t g[3];
     level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
@@ -73,7 +83,7 @@ __global__ void __launch_bounds__(256) hash_encode_bw_kernel(const float* __rest
 __global__ void __launch_bounds__(256) hash_encode_dx_kernel(const float* __restrict__ xyzs, int64_t n, Aabb box,
                                                              const __grid_constant__ LevelTable tbl,
                                                              const __half2* __restrict__ table, const float2* __restrict__ dfeat,
-                                                             float* __restrict__ dL_dxyzs) {
+                                                             float* __restrict__ dL_dxyzs, int img) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float gx[3] = {0.f, 0.f, 0.f};
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(256) hash_encode_dx_kernel(const float* __rest
         float w[3]; uint32_t g[3];
         level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
         const uint32_t size = tbl.size[l], res = tbl.res[l], off = tbl.offset[l];
-        const float2 d = dfeat[i * ARN_N_LEVELS + l];
+        const float2 d = dfeat[i * ARN_N_LEVELS + dfeat_col(img, i, l)];
         for (int c = 0; c < 8; c++) {
             uint32_t p[3]; corner_weight(c, w, g, p);
             const float2 t = __half22float2(table[off + grid_index(size, res, p)]);
@@ -109,7 +119,7 @@ __global__ void __launch_bounds__(256) hash_encode_dx_kernel(const float* __rest
 template <int SEG>
 __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                                   const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
-                                                                  float2* __restrict__ table_grad, int level0, int nlevels) {
+                                                                  float2* __restrict__ table_grad, int level0, int nlevels, int img) {
     if (n_dev) n = min(n, (int64_t)*n_dev);
     const int l = (threadIdx.x & 15);
     const int64_t n_seg = (n + SEG - 1) / SEG;
@@ -132,7 +142,7 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
             for (int c = 0; c < 8; c++) { atomicAdd(lvl + idx[c], acc[c]); acc[c] = make_float2(0.f, 0.f); }
         };
         for (int64_t i = i0; i < i1; i++) {
-            const float2 d = dfeat[i * ARN_N_LEVELS + l];
+            const float2 d = dfeat[i * ARN_N_LEVELS + dfeat_col(img, i, l)];
             float w[3]; uint32_t g[3];
             level_position(xyzs + 3 * i, box, scale, w, g);
             if (g[0] != cg[0] || g[1] != cg[1] || g[2] != cg[2]) {
@@ -153,19 +163,19 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
 
 template <int SEG>
 static int launch_hash_bw_runs(const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
-                               float* table_grad, int level0, int nlevels, cudaStream_t st) {
+                               float* table_grad, int level0, int nlevels, int img, cudaStream_t st) {
     const int64_t threads = ((n + SEG - 1) / SEG) * 16;
     const int grid = (int)min((int64_t)148 * 8, (threads + 255) / 256);
-    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, hash_encode_bw_runs_kernel<SEG><<<grid, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels));
+    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, hash_encode_bw_runs_kernel<SEG><<<grid, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img));
     return check_launch("hash_encode_bw_runs");
 }
 static int hash_bw_runs(int seg, const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
-                        float* table_grad, int level0, int nlevels, cudaStream_t st) {
+                        float* table_grad, int level0, int nlevels, int img, cudaStream_t st) {
     switch (seg) {
-        case 8: return launch_hash_bw_runs<8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, st);
-        case 16: return launch_hash_bw_runs<16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, st);
-        case 64: return launch_hash_bw_runs<64>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, st);
-        default: return launch_hash_bw_runs<32>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, st);
+        case 8: return launch_hash_bw_runs<8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st);
+        case 16: return launch_hash_bw_runs<16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st);
+        case 64: return launch_hash_bw_runs<64>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st);
+        default: return launch_hash_bw_runs<32>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st);
     }
 }
 
@@ -232,13 +242,23 @@ __device__ __forceinline__ void matvec_t(const __half* sW, const __half* g, floa
     }
 }
 
+// Rows of the saved activations are stored as tile images (arn_field.cuh img_chunk64/128): chunk q of row i sits at the
+// permuted position.  NV = 32 halves -> 64-byte rows, NV = 64 -> 128-byte rows.  `buf` is the start of the buffer.
 template <int NV>
-__device__ __forceinline__ void load_row(const __half* __restrict__ src, __half* dst) {  // NV halves, 16-byte chunks
+__device__ __forceinline__ uint32_t img_chunk(int64_t row, uint32_t q) { return NV == 32 ? img_chunk64(row, q) : img_chunk128(row, q); }
+template <int NV>
+__device__ __forceinline__ void load_row(const __half* __restrict__ buf, int64_t row, __half* dst) {
 #pragma unroll
-    for (int q = 0; q < NV / 8; q++) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(src)[q];
+    for (int q = 0; q < NV / 8; q++) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(buf + NV * row)[img_chunk<NV>(row, q)];
 }
 template <int NV>
-__device__ __forceinline__ void store_row(__half* __restrict__ dst, const __half* src) {
+__device__ __forceinline__ void store_row(__half* __restrict__ buf, int64_t row, const __half* src) {
+#pragma unroll
+    for (int q = 0; q < NV / 8; q++) reinterpret_cast<uint4*>(buf + NV * row)[img_chunk<NV>(row, q)] = reinterpret_cast<const uint4*>(src)[q];
+}
+// shared-memory staging rows of the simt backward (plain layout)
+template <int NV>
+__device__ __forceinline__ void copy_row(__half* dst, const __half* src) {
 #pragma unroll
     for (int q = 0; q < NV / 8; q++) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(src)[q];
 }
@@ -252,13 +272,13 @@ __global__ void __launch_bounds__(128) density_mlp_fw_simt_kernel(const __half* 
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    __align__(16) __half x[32]; load_row<32>(feat + 32 * i, x);
+    __align__(16) __half x[32]; load_row<32>(feat, i, x);
     float acc[64];
     matvec<64, 32>(sW1, x, acc);
     __align__(16) __half hv[64];
 #pragma unroll
     for (int j = 0; j < 64; j++) hv[j] = __float2half_rn(fmaxf(acc[j], 0.0f));
-    store_row<64>(hid + 64 * i, hv);
+    store_row<64>(hid, i, hv);
     float o[16];
     matvec<16, 64>(sW2, hv, o);
 #pragma unroll
@@ -283,17 +303,17 @@ __global__ void __launch_bounds__(128) rgb_mlp_fw_simt_kernel(const float* __res
 #pragma unroll
         for (int k = 0; k < 16; k++) { x[k] = __float2half_rn(sh[k]); x[16 + k] = __float2half_rn(h[16 * i + k]); }
     }
-    store_row<32>(in32 + 32 * i, x);
+    store_row<32>(in32, i, x);
     float acc[64];
     __align__(16) __half a1[64], a2[64];
     matvec<64, 32>(sW1, x, acc);
 #pragma unroll
     for (int j = 0; j < 64; j++) a1[j] = __float2half_rn(fmaxf(acc[j], 0.0f));
-    store_row<64>(hid1 + 64 * i, a1);
+    store_row<64>(hid1, i, a1);
     matvec<64, 64>(sW2, a1, acc);
 #pragma unroll
     for (int j = 0; j < 64; j++) a2[j] = __float2half_rn(fmaxf(acc[j], 0.0f));
-    store_row<64>(hid2 + 64 * i, a2);
+    store_row<64>(hid2, i, a2);
     float o[16];
     matvec<16, 64>(sW3, a2, o);
 #pragma unroll
@@ -370,7 +390,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_simt_kernel(int64_t n, const
                 }
                 g64[j] = __float2half_rn(g * loss_scale);
             }
-            if (valid) { store_row<16>(myG, g64); load_row<64>(hid2 + 64 * i, myX); }
+            if (valid) { copy_row<16>(myG, g64); load_row<64>(hid2, i, myX); }
             __syncthreads();
             wgrad_tile<16, 64>(sG, sX, rows, aC3);
             __syncthreads();
@@ -380,7 +400,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_simt_kernel(int64_t n, const
                 for (int k = 0; k < 64; k++) g64[k] = __float2half_rn(__half2float(myX[k]) > 0.0f ? t[k] : 0.0f);
             }
             __syncthreads();
-            if (valid) { store_row<64>(myG, g64); load_row<64>(hid1 + 64 * i, myX); }
+            if (valid) { copy_row<64>(myG, g64); load_row<64>(hid1, i, myX); }
             __syncthreads();
             wgrad_tile<64, 64>(sG, sX, rows, aC2);
             __syncthreads();
@@ -390,7 +410,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_simt_kernel(int64_t n, const
                 for (int k = 0; k < 64; k++) g64[k] = __float2half_rn(__half2float(myX[k]) > 0.0f ? t[k] : 0.0f);
             }
             __syncthreads();
-            if (valid) { store_row<64>(myG, g64); load_row<32>(in32 + 32 * i, myX); }
+            if (valid) { copy_row<64>(myG, g64); load_row<32>(in32, i, myX); }
             __syncthreads();
             wgrad_tile<64, 32>(sG, sX, rows, aC1);
             __syncthreads();
@@ -407,7 +427,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_simt_kernel(int64_t n, const
                 if (j == 0 && dL_dsigmas) g += (dL_dsigmas[i] * expf(fminf(fmaxf(h[16 * i], -15.0f), 15.0f))) * loss_scale;
                 g64[j] = __float2half_rn(g);
             }
-            store_row<16>(myG, g64); load_row<64>(hid + 64 * i, myX);
+            copy_row<16>(myG, g64); load_row<64>(hid, i, myX);
         }
         __syncthreads();
         wgrad_tile<16, 64>(sG, sX, rows, aD2);
@@ -418,7 +438,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_simt_kernel(int64_t n, const
             for (int k = 0; k < 64; k++) g64[k] = __float2half_rn(__half2float(myX[k]) > 0.0f ? t[k] : 0.0f);
         }
         __syncthreads();
-        if (valid) { store_row<64>(myG, g64); load_row<32>(feat + 32 * i, myX); }
+        if (valid) { copy_row<64>(myG, g64); load_row<32>(feat, i, myX); }
         __syncthreads();
         wgrad_tile<64, 32>(sG, sX, rows, aD1);
         __syncthreads();
@@ -426,7 +446,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_simt_kernel(int64_t n, const
             matvec_t<64, 32>(sWd1, g64, t);
 #pragma unroll
             for (int q = 0; q < 8; q++)
-                reinterpret_cast<float4*>(dfeat + 32 * i)[q] =
+                reinterpret_cast<float4*>(dfeat + 32 * i)[img_chunk128(i, q)] =
                     make_float4(t[4 * q] * inv_scale, t[4 * q + 1] * inv_scale, t[4 * q + 2] * inv_scale, t[4 * q + 3] * inv_scale);
         }
     }
@@ -572,14 +592,12 @@ int make_box(const float* mn, const float* mx, Aabb& b) {
 }
 }  // namespace arn
 
-extern "C" int arn_hash_encode_bw_dyn(const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const float*, float*,
-                                      float*, arn_stream_t);
 namespace arn {
 // n is the count (n_dev == nullptr) or the capacity with the real count read on the device from *n_dev (fused step).
 inline int sample_grid(int64_t n, const int32_t* n_dev) { return n_dev ? (int)min((int64_t)148 * 8, (n + 255) / 256) : ceil_div(n, 256); }
 }
-extern "C" ARN_API int arn_hash_encode_fw_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
-                                      arn_levels_t levels, const void* table_f16, void* feat_f16, arn_stream_t stream) {
+int arn::hash_encode_fw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                             arn_levels_t levels, const void* table_f16, void* feat_f16, int tile_image, arn_stream_t stream) {
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(xyzs && table_f16 && feat_f16, "null pointer");
@@ -587,22 +605,31 @@ extern "C" ARN_API int arn_hash_encode_fw_dyn(const float* xyzs, int64_t n, cons
     if (int e = make_levels(levels, t)) return e;
     if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
     dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS);
-    ARN_LAUNCH("hash_encode_fw_kernel", (cudaStream_t)stream, hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, n_dev, b, t, (const __half2*)table_f16, (__half2*)feat_f16));
+    ARN_LAUNCH("hash_encode_fw_kernel", (cudaStream_t)stream, hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, n_dev, b, t, (const __half2*)table_f16, (__half2*)feat_f16, tile_image));
     return check_launch("hash_encode_fw");
+}
+extern "C" ARN_API int arn_hash_encode_fw_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                                      arn_levels_t levels, const void* table_f16, void* feat_f16, arn_stream_t stream) {
+    return hash_encode_fw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, table_f16, feat_f16, 0, stream);
 }
 extern "C" ARN_API int arn_hash_encode_fw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
                                   arn_levels_t levels, const void* table_f16, void* feat_f16, arn_stream_t stream) {
-    return arn_hash_encode_fw_dyn(xyzs, n, nullptr, xyz_min_host, xyz_max_host, levels, table_f16, feat_f16, stream);
+    return hash_encode_fw_impl(xyzs, n, nullptr, xyz_min_host, xyz_max_host, levels, table_f16, feat_f16, 0, stream);
 }
 
 extern "C" ARN_API int arn_hash_encode_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host,
                                   arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad,
                                   float* dL_dxyzs, arn_stream_t stream) {
-    return arn_hash_encode_bw_dyn(xyzs, n, nullptr, xyz_min_host, xyz_max_host, levels, table_f16, dfeat, table_grad, dL_dxyzs, stream);
+    return hash_encode_bw_impl(xyzs, n, nullptr, xyz_min_host, xyz_max_host, levels, table_f16, dfeat, table_grad, dL_dxyzs, 0, stream);
 }
 extern "C" ARN_API int arn_hash_encode_bw_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
                                       arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad,
                                       float* dL_dxyzs, arn_stream_t stream) {
+    return hash_encode_bw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, table_f16, dfeat, table_grad, dL_dxyzs, 0, stream);
+}
+int arn::hash_encode_bw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                             arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad,
+                             float* dL_dxyzs, int tile_image, arn_stream_t stream) {
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(xyzs && dfeat, "null pointer");
@@ -613,16 +640,16 @@ extern "C" ARN_API int arn_hash_encode_bw_dyn(const float* xyzs, int64_t n, cons
     if (table_grad) {
         const int mode = tunable(kTunHashBwMode);  // 0: one reduction per (sample, level, corner); else: run-aggregating, segment length
         if (mode) {
-            if (int e = hash_bw_runs(mode, xyzs, n, n_dev, b, t, dfeat, table_grad, 0, ARN_N_LEVELS, st)) return e;
+            if (int e = hash_bw_runs(mode, xyzs, n, n_dev, b, t, dfeat, table_grad, 0, ARN_N_LEVELS, tile_image, st)) return e;
         } else {
             dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS);
-            ARN_LAUNCH("hash_encode_bw_kernel", st, hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad));
+            ARN_LAUNCH("hash_encode_bw_kernel", st, hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, tile_image));
             if (int e = check_launch("hash_encode_bw")) return e;
         }
     }
     if (dL_dxyzs) {
         ARN_REQUIRE(table_f16 && !n_dev, "dL_dxyzs needs the table and a host-side count");
-        ARN_LAUNCH("hash_encode_dx_kernel", st, hash_encode_dx_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xyzs, n, b, t, (const __half2*)table_f16, (const float2*)dfeat, dL_dxyzs));
+        ARN_LAUNCH("hash_encode_dx_kernel", st, hash_encode_dx_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xyzs, n, b, t, (const __half2*)table_f16, (const float2*)dfeat, dL_dxyzs, tile_image));
         if (int e = check_launch("hash_encode_dx")) return e;
     }
     return ARN_OK;
@@ -646,7 +673,7 @@ extern "C" ARN_API int arn_field_fw_simt(const float* xyzs, const float* dirs, i
     if (with_rgb) ARN_REQUIRE(params_rgb_f16 && ws.in32 && ws.hid1 && ws.hid2 && rgbs, "null pointer (colour branch)");
     cudaStream_t st = (cudaStream_t)stream;
     const __half* pxyz = (const __half*)params_xyz_f16;
-    if (int e = arn_hash_encode_fw(xyzs, n, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, stream)) return e;
+    if (int e = hash_encode_fw_impl(xyzs, n, nullptr, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, 1, stream)) return e;
     ARN_LAUNCH("density_mlp_fw_simt_kernel", st, density_mlp_fw_simt_kernel<<<ceil_div(n, 128), 128, 0, st>>>((const __half*)ws.feat, n, pxyz, (__half*)ws.hid, ws.h, sigmas));
     if (int e = check_launch("density_mlp_fw_simt")) return e;
     if (with_rgb) {
@@ -681,8 +708,8 @@ extern "C" ARN_API int arn_field_bw_simt(const float* xyzs, int64_t n, const flo
                                                      (const __half*)ws.hid2, pxyz, with_rgb ? (const __half*)params_rgb_f16 : nullptr,
                                                      rgb_act, loss_scale, grad_params_xyz, grad_params_rgb, dfeat_scratch));
     if (int e = check_launch("field_mlp_bw_simt")) return e;
-    return arn_hash_encode_bw(xyzs, n, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
-                              grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, stream);
+    return hash_encode_bw_impl(xyzs, n, nullptr, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
+                               grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, 1, stream);
 }
 
 extern "C" ARN_API int arn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* dst_f16, int64_t n, float lr,
@@ -760,5 +787,5 @@ extern "C" ARN_API int arn_dbg_hash_bw(const float* xyzs, int64_t n, const float
         ARN_LAUNCH("hash_encode_bw_range_kernel", st, hash_encode_bw_range_kernel<<<grid, 256, 0, st>>>(xyzs, n, nullptr, b, t, (const float2*)dfeat, (float2*)table_grad, level0));
         return check_launch("dbg_hash_bw");
     }
-    return hash_bw_runs(mode, xyzs, n, nullptr, b, t, dfeat, table_grad, level0, nlevels, st);
+    return hash_bw_runs(mode, xyzs, n, nullptr, b, t, dfeat, table_grad, level0, nlevels, 0, st);
 }

@@ -23,11 +23,24 @@ struct Aabb { float mn[3], mx[3], inv[3]; };
 
 int make_levels(const arn_levels_t& lv, LevelTable& t);
 int make_box(const float* mn, const float* mx, Aabb& b);
+// Hash-grid encode / backward with the layout of feat / dfeat selectable: tile_image = 0 is the plain row-major layout of
+// the public entry points, 1 the chunk-permuted activation image the MLP kernels bulk-copy (img_chunk64/128 below).
+int hash_encode_fw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                        arn_levels_t levels, const void* table_f16, void* feat_f16, int tile_image, arn_stream_t stream);
+int hash_encode_bw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
+                        arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad, float* dL_dxyzs,
+                        int tile_image, arn_stream_t stream);
 // arn_field_bw_tc_dyn with the option of reusing the weight image already in ws.wimg (arn_mlp_tc.cu)
 int field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
                      arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
                      const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
                      float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, bool pack_weights, arn_stream_t stream);
+
+// Activation images (arn_mlp_tc.cu): position of logical 16-byte chunk c of row `row` inside the row.  Equal to the
+// shared-memory swizzle of a 1024-byte aligned tile with 64- / 128-byte rows (tc::swz<64>, tc::swz<128>); depends on
+// row % 8 only, so it is the same for the global row index and the row inside its 128-row tile.
+__device__ __forceinline__ uint32_t img_chunk64(int64_t row, uint32_t c) { return c ^ ((uint32_t)(row >> 1) & 3u); }
+__device__ __forceinline__ uint32_t img_chunk128(int64_t row, uint32_t c) { return c ^ ((uint32_t)row & 7u); }
 
 // tiny-cuda-nn grid.h grid_index
 __device__ __forceinline__ uint32_t grid_index(uint32_t hashmap_size, uint32_t res, const uint32_t p[3]) {

@@ -1,11 +1,19 @@
-// libarnerf.so -- tensor-core MLPs of the field (density 32-64-16, colour 32-64-64-16) on tcgen05 / TMEM.
+// libarnerf.so -- tensor-core MLPs of the field (density 32-64-16, colour 32-64-64-16) on tcgen05 / TMEM, fed by TMA.
 //
-// Forward, one CTA of 128 threads per 128-sample tile (persistent over tiles, up to 4 CTAs per SM):
-//   * the five weight matrices arrive once per CTA as ONE bulk (TMA) copy of a pre-swizzled 20 KB operand image;
-//   * thread t owns sample row t: it stages the row as a swizzled K-major A tile in shared memory, one elected thread
-//     issues the layer's tcgen05.mma chain (M=128, N=64|16, K=16 per instruction, fp32 accumulators in TMEM) and commits
-//     to an mbarrier, every thread then pulls ITS row of the accumulator with tcgen05.ld (32x32b: lane == row),
-//     applies the activation, rounds to fp16 and writes the next layer's A tile (+ the saved activation for backward).
+// Activation images.  Every saved activation (feat, hid, in32, hid1, hid2: fp16; dfeat: fp32) lives in global memory as
+// a sequence of 128-row TILES whose bytes are exactly the shared-memory operand image tcgen05 wants (rows of 64 or 128
+// bytes, 16-byte chunks permuted by the hardware swizzle of that width: arn_field.cuh img_chunk64/128).  A tile is
+// therefore ONE contiguous 8 or 16 KB block: the forward stores it and the backward loads it with a single bulk
+// (TMA) copy issued by one thread -- no per-thread row loads/stores (which cost 32 L1 transactions per warp
+// instruction and made both kernels LSU-bound), no tensor maps.  Buffers hold a whole number of tiles.
+//
+// Forward, one CTA of 128 threads per 128-sample tile (persistent over tiles, 2 CTAs per SM):
+//   * the five weight matrices arrive once per CTA as ONE bulk copy of a pre-swizzled 20 KB operand image;
+//   * the feature tile of the NEXT tile is requested (bulk copy + mbarrier) while the current one is processed;
+//   * thread t owns sample row t: one elected thread issues the layer's tcgen05.mma chain (M=128, N=64|16, K=16 per
+//     instruction, fp32 accumulators in TMEM) and commits to an mbarrier, every thread then pulls ITS row of the
+//     accumulator with tcgen05.ld (32x32b: lane == row), applies the activation, rounds to fp16 and writes the next
+//     layer's A tile; the same shared-memory tile is handed to the TMA engine as the saved activation.
 //   Numeric contract: fp16 operands, fp32 accumulate -- identical rounding points to the simt
 //   kernels and the oracle; only the accumulation order inside the MMA differs.
 #include "arn_common.cuh"
@@ -55,7 +63,10 @@ __device__ __forceinline__ void epilogue_row_f16(uint32_t taddr, uint32_t* out) 
 
 constexpr int kFwSmemTile32 = 128 * 64;    // 128 rows x 32 halves
 constexpr int kFwSmemTile64 = 128 * 128;   // 128 rows x 64 halves
-constexpr int kFwSmemBytes = kWimgBytes + kFwSmemTile32 + kFwSmemTile64 + 1024;  // + alignment slack
+// shared-memory map of the forward (offsets from the 1024-aligned base)
+constexpr int kFwF0 = kWimgBytes, kFwF1 = kFwF0 + kFwSmemTile32, kFwI = kFwF1 + kFwSmemTile32, kFwH0 = kFwI + kFwSmemTile32,
+              kFwH1 = kFwH0 + kFwSmemTile64, kFwH2 = kFwH1 + kFwSmemTile64, kFwHS = kFwH2 + kFwSmemTile64;
+constexpr int kFwSmemBytes = kFwHS + 128 * 64 + 1024;  // + h staging (128 x 16 f32) + alignment slack
 
 __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __restrict__ feat, const float* __restrict__ dirs, int64_t n,
                                                               const int32_t* __restrict__ n_dev, const uint8_t* __restrict__ wimg, int rgb_act, int with_rgb,
@@ -63,32 +74,38 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
                                                               __half* __restrict__ in32, __half* __restrict__ hid1, __half* __restrict__ hid2,
                                                               float* __restrict__ rgbs) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[4];
     __shared__ uint32_t tmem_slot;
     if (n_dev) n = min(n, (int64_t)*n_dev);  // fused step: the sample count lives on the device
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzled tiles need 1024-byte alignment
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sW = base, sT32 = base + kWimgBytes, sT64 = sT32 + kFwSmemTile32;
-    uint8_t* pT32 = sm + kWimgBytes; uint8_t* pT64 = pT32 + kFwSmemTile32;
-    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+    const uint32_t sW = base;
+    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]), bar_f0 = smem_u32(&bars[2]), bar_f1 = smem_u32(&bars[3]);
     const int tid = threadIdx.x, warp = tid >> 5;
 
-    if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_mma, 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_mma, 1); mbar_init(bar_f0, 1); mbar_init(bar_f1, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_slot, 128);
     fence_before_sync(); __syncthreads(); fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const uint32_t wbytes = with_rgb ? kWimgBytes : kWimgC1;
-    if (tid == 0) { mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w); }
+    const int64_t n_tiles = (n + 127) / 128;
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w);
+        if (blockIdx.x < n_tiles) { mbar_expect_tx(bar_f0, kFwSmemTile32); bulk_g2s(base + kFwF0, feat + (int64_t)blockIdx.x * 128 * 32, kFwSmemTile32, bar_f0); }
+    }
     mbar_wait(bar_w, 0);
 
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes; lane == sample row
-    const uint64_t aT32 = smem_desc<64>(sT32), aT64 = smem_desc<128>(sT64);
+    const uint64_t aF0 = smem_desc<64>(base + kFwF0), aF1 = smem_desc<64>(base + kFwF1);
+    const uint64_t aI = smem_desc<64>(base + kFwI);
+    const uint64_t aH0 = smem_desc<128>(base + kFwH0), aH1 = smem_desc<128>(base + kFwH1), aH2 = smem_desc<128>(base + kFwH2);
     const uint64_t bD1 = smem_desc<64>(sW + kWimgD1), bD2 = smem_desc<128>(sW + kWimgD2);
     const uint64_t bC1 = smem_desc<64>(sW + kWimgC1), bC2 = smem_desc<128>(sW + kWimgC2), bC3 = smem_desc<128>(sW + kWimgC3);
     constexpr uint32_t kI64 = instr_desc(128, 64, 0, 0), kI16 = instr_desc(128, 16, 0, 0);
     uint32_t phase = 0;
 
-    // issue one layer: D[tmem cols] = A (128 x K) * W^T, K = 16 * ksteps; then commit
+    // issue one layer: D[tmem cols] = A (128 x K) * W^T, K = 16 * ksteps; then commit.  The barrier in front publishes the
+    // A tile the threads have just written (generic proxy -> async proxy) to the tensor core AND to the TMA engine.
     auto issue_only = [&](uint32_t dcol, uint64_t a, uint64_t b, uint32_t idesc, int ksteps) {
         fence_before_sync(); fence_async_smem(); __syncthreads();
         if (tid == 0) {
@@ -101,52 +118,61 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
         mbar_wait(bar_mma, phase); phase ^= 1;
         fence_after_sync();
     };
-    auto issue = [&](uint32_t dcol, uint64_t a, uint64_t b, uint32_t idesc, int ksteps) { issue_only(dcol, a, b, idesc, ksteps); wait_mma(); };
-
-    // The tile's only global inputs (feature row, ray direction) are requested one tile ahead, between the issue of the
-    // previous tile's last MMA and its completion (ptxas cannot hoist them above that bar.sync; see the backward kernel).
-    const int64_t n_tiles = (n + 127) / 128;
-    uint4 fr[4]; float dr[3] = {1.0f, 0.0f, 0.0f};
-    auto fetch_inputs = [&](int64_t t) {
-        const int64_t i = t * 128 + tid;
-        const bool ok = t < n_tiles && i < n;
+    // epilogue of a 64-wide hidden layer: ReLU, fp16, this thread's row of the next A tile
+    auto hidden_row = [&](uint32_t taddr, uint8_t* tile) {
+        uint32_t o[32];
+        epilogue_row_f16<4, true>(taddr, o);
 #pragma unroll
-        for (int c = 0; c < 4; c++) fr[c] = ok ? __ldg(reinterpret_cast<const uint4*>(feat + 32 * i) + c) : make_uint4(0, 0, 0, 0);
-        if (with_rgb) {
-            dr[0] = ok ? dirs[3 * i] : 1.0f; dr[1] = ok ? dirs[3 * i + 1] : 0.0f; dr[2] = ok ? dirs[3 * i + 2] : 0.0f;
-        }
+        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(tile + swz<128>(tid, c)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
     };
-    fetch_inputs(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+
+    // ray direction of this thread's sample, requested one tile ahead (between an MMA issue and its completion)
+    float dr[3] = {1.0f, 0.0f, 0.0f};
+    auto fetch_dir = [&](int64_t t) {
+        const int64_t i = t * 128 + tid;
+        const bool ok = with_rgb && t < n_tiles && i < n;
+        dr[0] = ok ? dirs[3 * i] : 1.0f; dr[1] = ok ? dirs[3 * i + 1] : 0.0f; dr[2] = ok ? dirs[3 * i + 2] : 0.0f;
+    };
+    fetch_dir(blockIdx.x);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
-        // ---- density layer 1: A = feat row (32 halves)
-#pragma unroll
-        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(pT32 + swz<64>(tid, c)) = fr[c];
-        const float dcur[3] = {dr[0], dr[1], dr[2]};
-        issue_only(0, aT32, bD1, kI64, 2);
-        if (!with_rgb) fetch_inputs(tile + gridDim.x);
-        wait_mma();
-        {
-            uint32_t o[32];
-            epilogue_row_f16<4, true>(trow + 0, o);
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const uint4 v = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-                *reinterpret_cast<uint4*>(pT64 + swz<128>(tid, c)) = v;
-                if (valid) reinterpret_cast<uint4*>(hid + 64 * i)[c] = v;
+        const int buf = it & 1;
+        uint8_t* pF = sm + (buf ? kFwF1 : kFwF0);
+        if (tid == 0) {
+            // the previous tile's bulk stores have left shared memory (they are a whole tile old): H0..H2, I, HS are free;
+            // F[buf^1] was released by the previous tile's first MMA
+            bulk_wait_read<0>();
+            const int64_t next = tile + gridDim.x;
+            if (next < n_tiles) {
+                const uint32_t bf = buf ? bar_f0 : bar_f1;
+                mbar_expect_tx(bf, kFwSmemTile32);
+                bulk_g2s(base + (buf ? kFwF0 : kFwF1), feat + next * 128 * 32, kFwSmemTile32, bf);
             }
         }
+        mbar_wait(buf ? bar_f1 : bar_f0, (uint32_t)(it >> 1) & 1u);
+        if (!valid) {  // rows past the sample count: zero features keep every saved activation of the pad rows finite
+#pragma unroll
+            for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(pF + swz<64>(tid, c)) = make_uint4(0, 0, 0, 0);
+        }
+        const float dcur[3] = {dr[0], dr[1], dr[2]};
+        // ---- density layer 1: A = feature tile
+        issue_only(0, buf ? aF1 : aF0, bD1, kI64, 2);
+        wait_mma();
+        hidden_row(trow + 0, sm + kFwH0);
         // ---- density layer 2 -> h (16, fp32), sigma
-        issue(64, aT64, bD2, kI16, 4);
+        issue_only(64, aH0, bD2, kI16, 4);
+        if (tid == 0) { bulk_s2g(hid + tile * 128 * 64, base + kFwH0, kFwSmemTile64); bulk_commit(); }
+        wait_mma();
         {
             float hv[16];
             tmem_ld16(trow + 64, hv); tmem_ld_wait();
-            if (valid) {
+            if (valid) sigmas[i] = expf(hv[0]);
+            // h tile staging: plain row-major 128 x 16 f32, the public layout of h
 #pragma unroll
-                for (int q = 0; q < 4; q++) reinterpret_cast<float4*>(h + 16 * i)[q] = make_float4(hv[4 * q], hv[4 * q + 1], hv[4 * q + 2], hv[4 * q + 3]);
-                sigmas[i] = expf(hv[0]);
-            }
+            for (int c = 0; c < 4; c++)
+                *reinterpret_cast<float4*>(sm + kFwHS + tid * 64 + c * 16) = make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
             if (with_rgb) {  // colour-net input row [sh16 | fp16(h16)]
                 float sh[16];
                 sh4_eval(dcur, sh);
@@ -154,41 +180,32 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
 #pragma unroll
                 for (int j = 0; j < 8; j++) { o[j] = pack2(sh[2 * j], sh[2 * j + 1]); o[8 + j] = pack2(hv[2 * j], hv[2 * j + 1]); }
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const uint4 v = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-                    *reinterpret_cast<uint4*>(pT32 + swz<64>(tid, c)) = v;
-                    if (valid) reinterpret_cast<uint4*>(in32 + 32 * i)[c] = v;
-                }
+                for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(sm + kFwI + swz<64>(tid, c)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
             }
         }
-        if (!with_rgb) continue;
+        if (!with_rgb) {
+            fence_async_smem(); __syncthreads();
+            if (tid == 0) { bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64); bulk_commit(); }
+            continue;
+        }
         // ---- colour layer 1
-        issue(0, aT32, bC1, kI64, 2);
-        {
-            uint32_t o[32];
-            epilogue_row_f16<4, true>(trow + 0, o);
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const uint4 v = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-                *reinterpret_cast<uint4*>(pT64 + swz<128>(tid, c)) = v;
-                if (valid) reinterpret_cast<uint4*>(hid1 + 64 * i)[c] = v;
-            }
+        issue_only(0, aI, bC1, kI64, 2);
+        if (tid == 0) {
+            bulk_s2g(in32 + tile * 128 * 32, base + kFwI, kFwSmemTile32);
+            bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64);
+            bulk_commit();
         }
-        // ---- colour layer 2 (its A tile is overwritten by its own output once the MMA has completed)
-        issue(64, aT64, bC2, kI64, 4);
-        {
-            uint32_t o[32];
-            epilogue_row_f16<4, true>(trow + 64, o);
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const uint4 v = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-                *reinterpret_cast<uint4*>(pT64 + swz<128>(tid, c)) = v;
-                if (valid) reinterpret_cast<uint4*>(hid2 + 64 * i)[c] = v;
-            }
-        }
+        wait_mma();
+        hidden_row(trow + 0, sm + kFwH1);
+        // ---- colour layer 2
+        issue_only(64, aH1, bC2, kI64, 4);
+        if (tid == 0) { bulk_s2g(hid1 + tile * 128 * 64, base + kFwH1, kFwSmemTile64); bulk_commit(); }
+        wait_mma();
+        hidden_row(trow + 64, sm + kFwH2);
         // ---- colour layer 3 -> rgb
-        issue_only(0, aT64, bC3, kI16, 4);
-        fetch_inputs(tile + gridDim.x);
+        issue_only(0, aH2, bC3, kI16, 4);
+        if (tid == 0) { bulk_s2g(hid2 + tile * 128 * 64, base + kFwH2, kFwSmemTile64); bulk_commit(); }
+        fetch_dir(tile + gridDim.x);
         wait_mma();
         {
             float ov[16];
@@ -199,6 +216,7 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
             }
         }
     }
+    if (tid == 0) bulk_wait_read<0>();
     fence_before_sync(); __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
@@ -231,7 +249,7 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
     if (with_rgb) ARN_REQUIRE(params_rgb_f16 && ws.in32 && ws.hid1 && ws.hid2 && rgbs, "null pointer (colour branch)");
     cudaStream_t st = (cudaStream_t)stream;
     const __half* pxyz = (const __half*)params_xyz_f16;
-    if (int e = arn_hash_encode_fw_dyn(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, stream)) return e;
+    if (int e = hash_encode_fw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, /*tile_image=*/1, stream)) return e;
     ARN_LAUNCH("pack_mlp_weights_kernel", st, pack_mlp_weights_kernel<<<5, 256, 0, st>>>(pxyz, (const __half*)params_rgb_f16, (uint8_t*)ws.wimg));
     if (int e = check_launch("pack_mlp_weights")) return e;
     static int n_sm = 0;
@@ -240,7 +258,7 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
         ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
     }
     const int64_t n_tiles = (n + 127) / 128;
-    const int grid = (int)(n_tiles < (int64_t)n_sm * 4 ? n_tiles : (int64_t)n_sm * 4);
+    const int grid = (int)(n_tiles < (int64_t)n_sm * 2 ? n_tiles : (int64_t)n_sm * 2);
     ARN_LAUNCH("field_mlp_fw_tc_kernel", st, field_mlp_fw_tc_kernel<<<grid, 128, kFwSmemBytes, st>>>(
         (const __half*)ws.feat, dirs, n, n_dev, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, (__half*)ws.hid, ws.h, sigmas,
         (__half*)ws.in32, (__half*)ws.hid1, (__half*)ws.hid2, rgbs));
@@ -255,24 +273,18 @@ using namespace tc;
 //   dgrad   R[128 x in]  = G (K-major A: rows = samples, K = out)  x  W (MN-major B straight from the forward's weight image)
 //   wgrad   dW[out x in] += G^T X : A = G as MN-major (M = out), B = X as MN-major (N = in), K = the 128 samples of the tile
 // The five weight-gradient accumulators stay in TENSOR MEMORY for the whole kernel (160 columns) and are flushed once
-// per CTA with atomicAdd; layers with 16 outputs accumulate the transposed product (M = in = 64, N = 16).
+// per CTA; layers with 16 outputs accumulate the transposed product (M = in = 64, N = 16).
 // Thread t then pulls row t of R with tcgen05.ld, applies the ReLU mask of its own activation row, scales/rounds to
 // fp16 and writes the next G tile.  Rounding points are those of the simt kernel / oracle (fp16 G, fp32 accumulate).
+// The saved activation tiles X (hid2, hid1, in32, hid, feat -- in this order, 5 per sample tile) stream through a ring of
+// three 16 KB slots: one thread issues each tile as a single bulk (TMA) copy two layers before its MMA, as soon as the
+// slot's previous tile has been consumed; the layer's threads only wait on the slot's mbarrier.  dfeat leaves the same way.
 // TMEM map: [0,64) R | [64,80) dWc3^T | [80,144) dWc2 | [144,176) dWc1 | [176,192) dWd2^T | [192,224) dWd1   (256 allocated)
-constexpr int kBwSmemBytes = kWimgBytes + 3 * kFwSmemTile64 + 1024;
+constexpr int kBwGa = kWimgBytes, kBwGb = kBwGa + kFwSmemTile64, kBwX0 = kBwGb + kFwSmemTile64;
+constexpr int kBwSmemBytes = kBwX0 + 3 * kFwSmemTile64 + 1024;
 constexpr int kWgradFloats = 7168 + 3072;  // one slab of per-CTA weight gradients
 constexpr int kMaxBwCtas = ARN_FIELD_SCRATCH_SLABS;
 constexpr uint32_t kColR = 0, kColC3 = 64, kColC2 = 80, kColC1 = 144, kColD2 = 176, kColD1 = 192;
-
-template <int RB>
-__device__ __forceinline__ void stage_row(uint8_t* tile, int row, const __half* __restrict__ src, bool valid) {
-#pragma unroll
-    for (int c = 0; c < RB / 16; c++) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (valid) v = reinterpret_cast<const uint4*>(src)[c];
-        *reinterpret_cast<uint4*>(tile + swz<RB>(row, c)) = v;
-    }
-}
 
 // t[NQ*16] = this thread's row of R; g = fp16(relu'(x) * t) written as a RB=128 row of `gtile`; mask from row of `xtile`.
 __device__ __forceinline__ void epilogue_mask64(uint32_t taddr, const uint8_t* xtile, uint8_t* gtile, int row) {
@@ -295,44 +307,80 @@ __device__ __forceinline__ void epilogue_mask64(uint32_t taddr, const uint8_t* x
 }
 
 __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const int32_t* __restrict__ n_dev, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
-                                                              const float* __restrict__ rgbs, const float* __restrict__ h,
+                                                              const float* __restrict__ rgbs, const float* __restrict__ sigmas,
                                                               const __half* __restrict__ feat, const __half* __restrict__ hid,
                                                               const __half* __restrict__ in32, const __half* __restrict__ hid1,
                                                               const __half* __restrict__ hid2, const uint8_t* __restrict__ wimg, int rgb_act,
-                                                              int with_rgb, float loss_scale, float* __restrict__ dWd, float* __restrict__ dWc,
-                                                              float* __restrict__ dfeat, float* __restrict__ wpart) {
+                                                              int with_rgb, float loss_scale, float exp_hi, float* __restrict__ dfeat, float* __restrict__ wpart) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[5];
     __shared__ uint32_t tmem_slot;
     if (n_dev) n = min(n, (int64_t)*n_dev);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sW = base, sGa = base + kWimgBytes, sGb = sGa + kFwSmemTile64, sX = sGb + kFwSmemTile64;
-    uint8_t* pGa = sm + kWimgBytes; uint8_t* pGb = pGa + kFwSmemTile64; uint8_t* pX = pGb + kFwSmemTile64;
+    const uint32_t sW = base, sGa = base + kBwGa, sGb = base + kBwGb;
+    uint8_t* pGa = sm + kBwGa; uint8_t* pGb = sm + kBwGb;
     const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_mma, 1); mbar_fence_init(); }
+    if (tid == 0) {
+        mbar_init(bar_w, 1); mbar_init(bar_mma, 1);
+        for (int k = 0; k < 3; k++) mbar_init(smem_u32(&bars[2 + k]), 1);
+        mbar_fence_init();
+    }
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
     fence_before_sync(); __syncthreads(); fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const uint32_t wbytes = with_rgb ? kWimgBytes : kWimgC1;
-    if (tid == 0) { mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w); }
+    const int64_t n_tiles = (n + 127) / 128;
+
+    // ---- activation-tile stream: load j of this CTA = tile (j / L) of its tile sequence, kind (j % L); slot j % 3
+    const int L = with_rgb ? 5 : 2;
+    auto issue_load = [&](int64_t j) {  // thread 0 only
+        const int64_t t = (int64_t)blockIdx.x + (j / L) * gridDim.x;
+        if (t >= n_tiles) return;
+        const int kind = with_rgb ? (int)(j % 5) : 3 + (int)(j % 2);
+        const __half* src; uint32_t bytes;
+        switch (kind) {
+            case 0: src = hid2 + t * 128 * 64; bytes = kFwSmemTile64; break;
+            case 1: src = hid1 + t * 128 * 64; bytes = kFwSmemTile64; break;
+            case 2: src = in32 + t * 128 * 32; bytes = kFwSmemTile32; break;
+            case 3: src = hid + t * 128 * 64; bytes = kFwSmemTile64; break;
+            default: src = feat + t * 128 * 32; bytes = kFwSmemTile32; break;
+        }
+        const int slot = (int)(j % 3);
+        const uint32_t bx = smem_u32(&bars[2 + slot]);
+        mbar_expect_tx(bx, bytes);
+        bulk_g2s(base + kBwX0 + slot * kFwSmemTile64, src, bytes, bx);
+    };
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w);
+        issue_load(0); issue_load(1);
+    }
     mbar_wait(bar_w, 0);
 
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
     const float inv_scale = 1.0f / loss_scale;
+    const float exp_lo = 1.0f / exp_hi;
     uint32_t acc = 0;  // 0 on the CTA's first tile: the wgrad accumulators are initialised by the MMA itself
+    int64_t j = 0;     // index of the next activation tile to be consumed
 
-    // One layer step: wgrad (K = 128 samples, 8 MMAs) + dgrad (K = out, ksteps MMAs), one commit.
-    //   g   : G tile (rows = samples, RBG bytes per row)        x : X tile (RBX bytes per row)
+    // One layer step: wait for the layer's X tile, publish the G tile, then wgrad (K = 128 samples, 8 MMAs) + dgrad
+    // (K = out, ksteps MMAs) under one commit.  After the barrier the slot of the PREVIOUS layer's X tile is free (its MMA
+    // has completed and every thread is past its epilogue), so thread 0 refills it with the tile two layers ahead.
+    //   g   : G tile (rows = samples, RBG bytes per row)        x : X tile in slot j % 3 (RBX bytes per row)
     //   w   : weight tile of this layer in the image (MN-major B for dgrad), RBW bytes per row (= 2*in)
     //   wgrad M=64: A = (t_out16 ? x : g) MN-major, B = (t_out16 ? g : x) MN-major
-    auto layer = [&](uint64_t g_desc, int rbg, uint64_t x_desc, int rbx, uint64_t w_desc, int rbw, int n_in, int n_out, uint32_t wcol) {
+    auto layer = [&](uint64_t g_desc, int rbg, int rbx, uint64_t w_desc, int rbw, int n_in, int n_out, uint32_t wcol) -> const uint8_t* {
+        const int slot = (int)(j % 3);
+        const uint32_t sX = base + kBwX0 + slot * kFwSmemTile64;
+        mbar_wait(smem_u32(&bars[2 + slot]), (uint32_t)(j / 3) & 1u);
         fence_before_sync(); fence_async_smem(); __syncthreads();
         if (tid == 0) {
             fence_after_sync();
+            issue_load(j + 2);
+            const uint64_t x_desc = rbx == 128 ? smem_desc<128>(sX) : smem_desc<64>(sX);
             const bool t16 = n_out == 16;
             const uint64_t wa = t16 ? x_desc : g_desc, wb = t16 ? g_desc : x_desc;
             const int rba = t16 ? rbx : rbg, rbb = t16 ? rbg : rbx;
@@ -344,6 +392,8 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                 mma_f16(tmem + kColR, desc_advance(g_desc, 32 * k), desc_advance(w_desc, 16 * rbw * k), di, k > 0);
             mma_commit(bar_mma);
         }
+        j++;
+        return sm + kBwX0 + slot * kFwSmemTile64;
     };
     auto layer_wait = [&]() {
         mbar_wait(bar_mma, phase); phase ^= 1;
@@ -351,139 +401,94 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     };
 
     const uint64_t dGa128 = smem_desc<128>(sGa), dGa32 = smem_desc<32>(sGa), dGb128 = smem_desc<128>(sGb), dGb32 = smem_desc<32>(sGb);
-    const uint64_t dX128 = smem_desc<128>(sX), dX64 = smem_desc<64>(sX);
     const uint64_t wD1 = smem_desc<64>(sW + kWimgD1), wD2 = smem_desc<128>(sW + kWimgD2);
     const uint64_t wC1 = smem_desc<64>(sW + kWimgC1), wC2 = smem_desc<128>(sW + kWimgC2), wC3 = smem_desc<128>(sW + kWimgC3);
 
-    // Global -> register prefetch: the activation row a layer needs is requested one layer ahead (and the first layer's
-    // inputs of the NEXT tile during the last layer), so its DRAM/L2 latency overlaps the MMA round trip and the epilogue
-    // instead of being exposed five times per tile.
-    // The consumer of a prefetched row must come BEFORE the next prefetch is issued: loads retire through in-order
-    // scoreboards, so a use placed after younger loads waits for those as well (seen in ncu as long-scoreboard stalls on
-    // the first use).  ptxas hoists loads to the top of a basic block, so every fetch sits between layer() -- whose
-    // bar.sync it cannot cross -- and layer_wait(), after the previous row has gone to shared memory.
-    auto fetch_row128 = [&](uint4* r, const __half* src, bool ok) {
+    // per-sample scalars, requested one tile ahead between an MMA issue and its completion (ptxas hoists loads to the top
+    // of a basic block but not across the bar.sync; a use placed after younger loads would wait for those as well)
+    float pre_y[3] = {0.f, 0.f, 0.f}, pre_g[3] = {0.f, 0.f, 0.f}, pre_ds = 0.f, pre_sig = 1.f;
+    auto fetch_scalars = [&](int64_t t) {
+        const int64_t i = t * 128 + tid;
+        const bool ok = t < n_tiles && i < n;
 #pragma unroll
-        for (int c = 0; c < 8; c++) r[c] = ok ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
-    };
-    auto fetch_row64 = [&](uint4* r, const __half* src, bool ok) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) r[c] = ok ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
-    };
-    auto put_row128 = [&](const uint4* r) {
-#pragma unroll
-        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(pX + swz<128>(tid, c)) = r[c];
-    };
-    auto put_row64 = [&](const uint4* r) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(pX + swz<64>(tid, c)) = r[c];
-    };
-
-    const int64_t n_tiles = (n + 127) / 128;
-    uint4 xr[8], xs[4];           // prefetched activation rows (128-byte / 64-byte)
-    float pre_y[3], pre_g[3];     // prefetched rgbs / dL_drgbs of this thread's sample
-    {
-        const int64_t i = (int64_t)blockIdx.x * 128 + tid;
-        const bool valid = blockIdx.x < n_tiles && i < n;
-        if (with_rgb) {
-            fetch_row128(xr, hid2 + 64 * i, valid);
-#pragma unroll
-            for (int j = 0; j < 3; j++) { pre_y[j] = valid ? rgbs[3 * i + j] : 0.0f; pre_g[j] = (valid && dL_drgbs) ? dL_drgbs[3 * i + j] : 0.0f; }
-        } else {
-            fetch_row128(xr, hid + 64 * i, valid);
+        for (int k = 0; k < 3; k++) {
+            pre_y[k] = (ok && with_rgb) ? rgbs[3 * i + k] : 0.0f;
+            pre_g[k] = (ok && with_rgb && dL_drgbs) ? dL_drgbs[3 * i + k] : 0.0f;
         }
-    }
+        pre_ds = (ok && dL_dsigmas) ? dL_dsigmas[i] : 0.0f;
+        pre_sig = ok ? sigmas[i] : 1.0f;
+    };
+    fetch_scalars(blockIdx.x);
+
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
         float tcol[16];  // scaled dL/dh from the colour branch
 #pragma unroll
-        for (int j = 0; j < 16; j++) tcol[j] = 0.0f;
-        float pre_ds = 0.0f, pre_h0 = 0.0f;
+        for (int k = 0; k < 16; k++) tcol[k] = 0.0f;
+        // d sigma / d h0 = exp(clamp(h0, -15, 15)) (custom_functions.py:170-173) = clamp(sigma, e^-15, e^15): exp is monotone
+        const float g_sigma = valid ? pre_ds * fminf(fmaxf(pre_sig, exp_lo), exp_hi) * loss_scale : 0.0f;
+        if (tid == 0) bulk_wait_read<0>();  // the previous tile's dfeat has left Gb (ordered before its reuse by the barrier of the first layer)
+        if (!with_rgb) __syncthreads();     // density-only: Gb is written before the first layer's barrier
         if (with_rgb) {
             // ---- colour output layer: g3 (16) -> Ga (RB32), X = hid2
             {
                 uint32_t o[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) o[j] = 0;
-                if (valid && dL_drgbs) {
-                    float g[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int k = 0; k < 8; k++) o[k] = 0;
+                if (valid) {
+                    float g[3];
 #pragma unroll
-                    for (int j = 0; j < 3; j++) g[j] = pre_g[j] * (rgb_act ? pre_y[j] * (1.0f - pre_y[j]) : 1.0f) * loss_scale;
+                    for (int k = 0; k < 3; k++) g[k] = pre_g[k] * (rgb_act ? pre_y[k] * (1.0f - pre_y[k]) : 1.0f) * loss_scale;
                     o[0] = pack2(g[0], g[1]); o[1] = pack2(g[2], 0.0f);
                 }
                 *reinterpret_cast<uint4*>(pGa + swz<32>(tid, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<uint4*>(pGa + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
-                put_row128(xr);
             }
-            layer(dGa32, 32, dX128, 128, wC3, 128, 64, 16, kColC3);
-            fetch_row128(xr, hid1 + 64 * i, valid);
-            if (valid && dL_dsigmas) { pre_ds = dL_dsigmas[i]; pre_h0 = h[16 * i]; }
+            const uint8_t* x;
+            x = layer(dGa32, 32, 128, wC3, 128, 64, 16, kColC3);
             layer_wait();
-            epilogue_mask64(trow + kColR, pX, pGb, tid);              // g2 -> Gb
-            fence_before_sync(); __syncthreads();                     // everyone has read its X row before it is replaced
-            put_row128(xr);
-            layer(dGb128, 128, dX128, 128, wC2, 128, 64, 64, kColC2);
-            fetch_row64(xs, in32 + 32 * i, valid);
+            epilogue_mask64(trow + kColR, x, pGb, tid);               // g2 -> Gb
+            x = layer(dGb128, 128, 128, wC2, 128, 64, 64, kColC2);
             layer_wait();
-            epilogue_mask64(trow + kColR, pX, pGa, tid);              // g1 -> Ga
-            fence_before_sync(); __syncthreads();
-            put_row64(xs);
-            layer(dGa128, 128, dX64, 64, wC1, 64, 32, 64, kColC1);
-            fetch_row128(xr, hid + 64 * i, valid);
+            epilogue_mask64(trow + kColR, x, pGa, tid);               // g1 -> Ga
+            layer(dGa128, 128, 64, wC1, 64, 32, 64, kColC1);
             layer_wait();
-            {   // R[:, 16:32] = scaled dL/dh from the colour branch
-                tmem_ld16(trow + kColR + 16, tcol); tmem_ld_wait();
-            }
-        } else if (valid && dL_dsigmas) { pre_ds = dL_dsigmas[i]; pre_h0 = h[16 * i]; }
+            tmem_ld16(trow + kColR + 16, tcol); tmem_ld_wait();        // R[:, 16:32] = scaled dL/dh from the colour branch
+        }
         // ---- density output layer: gh (16) -> Gb (RB32), X = hid
         {
-            float g0 = tcol[0];
-            if (valid && dL_dsigmas) g0 += (pre_ds * expf(fminf(fmaxf(pre_h0, -15.0f), 15.0f))) * loss_scale;
             uint32_t o[8];
-            o[0] = pack2(g0, tcol[1]);
+            o[0] = pack2(tcol[0] + g_sigma, tcol[1]);
 #pragma unroll
-            for (int j = 1; j < 8; j++) o[j] = pack2(tcol[2 * j], tcol[2 * j + 1]);
+            for (int k = 1; k < 8; k++) o[k] = pack2(tcol[2 * k], tcol[2 * k + 1]);
             if (!valid) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) o[j] = 0;
+                for (int k = 0; k < 8; k++) o[k] = 0;
             }
-            fence_before_sync(); __syncthreads();                     // previous layer's tiles are free
+            // Gb was last read by the C2 MMA, which has completed
             *reinterpret_cast<uint4*>(pGb + swz<32>(tid, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<uint4*>(pGb + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
-            put_row128(xr);
         }
-        layer(dGb32, 32, dX128, 128, wD2, 128, 64, 16, kColD2);
-        fetch_row64(xs, feat + 32 * i, valid);
-        {   // first-layer inputs of this CTA's next tile (xr is free: its row went to shared memory before this layer)
-            const int64_t in = (tile + gridDim.x) * 128 + tid;
-            const bool vn = tile + gridDim.x < n_tiles && in < n;
-            if (with_rgb) {
-                fetch_row128(xr, hid2 + 64 * in, vn);
-#pragma unroll
-                for (int j = 0; j < 3; j++) { pre_y[j] = vn ? rgbs[3 * in + j] : 0.0f; pre_g[j] = (vn && dL_drgbs) ? dL_drgbs[3 * in + j] : 0.0f; }
-            } else {
-                fetch_row128(xr, hid + 64 * in, vn);
-            }
-        }
+        const uint8_t* xh = layer(dGb32, 32, 128, wD2, 128, 64, 16, kColD2);
         layer_wait();
-        epilogue_mask64(trow + kColR, pX, pGa, tid);                  // gd -> Ga
-        fence_before_sync(); __syncthreads();
-        put_row64(xs);
-        layer(dGa128, 128, dX64, 64, wD1, 64, 32, 64, kColD1);
+        epilogue_mask64(trow + kColR, xh, pGa, tid);                  // gd -> Ga
+        layer(dGa128, 128, 64, wD1, 64, 32, 64, kColD1);
+        fetch_scalars(tile + gridDim.x);
         layer_wait();
-        {
+        {   // dfeat tile: fp32 rows of 128 B, chunk-permuted like a RB128 image; staged in Gb (free since the D2 MMA) and stored by TMA
             float v[32];
             tmem_ld16(trow + kColR, v); tmem_ld16(trow + kColR + 16, v + 16); tmem_ld_wait();
-            if (valid) {
 #pragma unroll
-                for (int q = 0; q < 8; q++)
-                    reinterpret_cast<float4*>(dfeat + 32 * i)[q] =
-                        make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale, v[4 * q + 3] * inv_scale);
-            }
+            for (int q = 0; q < 8; q++)
+                *reinterpret_cast<float4*>(pGb + swz<128>(tid, q)) =
+                    make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale, v[4 * q + 3] * inv_scale);
+            fence_async_smem(); __syncthreads();
+            if (tid == 0) { bulk_s2g(dfeat + tile * 128 * 32, sGb, kFwSmemTile64); bulk_commit(); }
         }
         acc = 1;
     }
+    if (tid == 0) bulk_wait_read<0>();
 
     // ---- flush the weight gradients: M=64 accumulators live in lanes 0-15 of each warp's quadrant (row = 16*warp + lane).
     // Every CTA writes its five accumulators as one 10240-float slab of `wpart` (parameter order: colour 7168 | density
@@ -568,10 +573,9 @@ int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, co
                           arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,
                           const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
                           float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, bool pack_weights, arn_stream_t stream) {
-    (void)sigmas;
     ARN_REQUIRE(n >= 0 && loss_scale > 0, "bad size / loss_scale");
     if (n == 0) return ARN_OK;
-    ARN_REQUIRE(xyzs && params_xyz_f16 && ws.feat && ws.hid && ws.h && ws.wimg && dfeat_scratch && grad_params_xyz, "null pointer");
+    ARN_REQUIRE(xyzs && params_xyz_f16 && ws.feat && ws.hid && ws.wimg && sigmas && dfeat_scratch && grad_params_xyz, "null pointer");
     const bool with_rgb = params_rgb_f16 != nullptr && dL_drgbs != nullptr;
     if (with_rgb) ARN_REQUIRE(ws.in32 && ws.hid1 && ws.hid2 && rgbs && grad_params_rgb, "null pointer (colour branch)");
     cudaStream_t st = (cudaStream_t)stream;
@@ -592,12 +596,12 @@ int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, co
     if (grid > arn::kMaxBwCtas) grid = arn::kMaxBwCtas;
     float* wpart = reinterpret_cast<float*>((uint8_t*)ws.wimg + arn::kWimgBytes);  // slabs follow the weight image in the scratch
     ARN_LAUNCH("field_mlp_bw_tc_kernel", st, arn::field_mlp_bw_tc_kernel<<<grid, 128, arn::kBwSmemBytes, st>>>(
-        n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, ws.h, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32,
-        (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, grad_params_xyz,
-        grad_params_rgb, dfeat_scratch, wpart));
+        n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, sigmas, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32,
+        (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, expf(15.0f),
+        dfeat_scratch, wpart));
     if (int e = check_launch("field_mlp_bw_tc")) return e;
     ARN_LAUNCH("wgrad_reduce_kernel", st, arn::wgrad_reduce_kernel<<<arn::kWgradFloats / 32, 256, 0, st>>>(wpart, grid, with_rgb ? 1 : 0, grad_params_xyz, grad_params_rgb));
     if (int e = check_launch("wgrad_reduce")) return e;
-    return arn_hash_encode_bw_dyn(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
-                                  grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, stream);
+    return hash_encode_bw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
+                               grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, /*tile_image=*/1, stream);
 }

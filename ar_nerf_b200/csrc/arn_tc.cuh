@@ -102,6 +102,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
+// Bulk shared -> global copy (TMA engine); grouped, the issuing thread waits for the group's shared-memory reads.
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+
 }  // namespace tc
 
 // Weight image: the five MLP matrices as swizzled operand tiles, built by pack_mlp_weights_kernel from the fp16 params.

@@ -121,11 +121,17 @@ class FieldState:
         self.mn = (C.c_float * 3)(*[float(v) for v in xyz_min]); self.mx = (C.c_float * 3)(*[float(v) for v in xyz_max])
 
 
+def tile_rows(n):
+    """Saved activations are stored as whole 128-row tiles (include/arnerf.h, arn_field_ws_t)."""
+    return (n + 127) // 128 * 128
+
+
 def _workspace(n, device, with_rgb):
     e = lambda *s, dt=torch.float16: torch.empty(*s, dtype=dt, device=device)
-    ws = dict(feat=e(n, 32), hid=e(n, 64), h=e(n, 16, dt=torch.float32), wimg=torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device))
+    m = tile_rows(n)
+    ws = dict(feat=e(m, 32), hid=e(m, 64), h=e(m, 16, dt=torch.float32), wimg=torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device))
     if with_rgb:
-        ws.update(in32=e(n, 32), hid1=e(n, 64), hid2=e(n, 64))
+        ws.update(in32=e(m, 32), hid1=e(m, 64), hid2=e(m, 64))
     return ws
 
 
@@ -159,7 +165,7 @@ class FieldFunction(torch.autograd.Function):
         ctx.p16 = (p16x, p16c)
         ctx.save_for_backward(xyzs, sigmas, rgbs, params_xyz, params_rgb)
         ctx.set_materialize_grads(False)
-        h = ws["h"]
+        h = ws["h"][:n]
         ctx.mark_non_differentiable(h)
         if with_rgb:
             return sigmas, rgbs, h
@@ -185,7 +191,7 @@ class FieldFunction(torch.autograd.Function):
         else:
             gx = torch.zeros_like(params_xyz, dtype=torch.float32)
             gc = torch.zeros(RGB_MLP_PARAMS, dtype=torch.float32, device=dev) if ctx.with_rgb else None
-        dfeat = torch.empty(n, 32, dtype=torch.float32, device=dev)
+        dfeat = torch.empty(tile_rows(n), 32, dtype=torch.float32, device=dev)
         dx = torch.empty(n, 3, dtype=torch.float32, device=dev) if need_dx else None
         g = state.geometry
         call("arn_field_bw" + ctx.impl, ptr(xyzs), n, state.mn, state.mx, g.c_levels, ptr(p16x), ptr(p16c), state.rgb_act,

@@ -99,7 +99,7 @@ class NGPTrainer:
         m, st = self.model, self.model.field_state
         R, dev = rays_o.shape[0], rays_o.device
         if self._ws is None or self._ws.n_rays != R:
-            self._ws = _FusedWorkspace(R, self.sample_capacity or R * MAX_SAMPLES, dev)
+            self._ws = _FusedWorkspace(R, (int(self.sample_capacity or R * MAX_SAMPLES) + 127) // 128 * 128, dev)
         w = self._ws
         center, half = m.host_box()
         if noise is None:

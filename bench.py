@@ -236,11 +236,17 @@ def run_ours(args):
     hbm, tf_burst, tf_sus, peak_src = read_peaks()
     # algorithmic bytes / flops per launch (DESIGN.md "Kernels"): N = marched samples of the step
     N = n_samples
-    model_bytes = {"hash_encode_fw_kernel": 588.0 * N, "hash_encode_bw_kernel": 588.0 * N,
+    n_params = sum(p.numel() for p in model.parameters())
+    model_bytes = {"hash_encode_fw_kernel": 588.0 * N, "hash_encode_bw_kernel": 588.0 * N, "hash_encode_bw_runs_kernel": 588.0 * N,
                    "composite_train_fw_kernel": 28.0 * N + 20 * BATCH, "composite_train_bw_kernel": 60.0 * N,
-                   "march_train_emit_kernel": 36.0 * N, "adam_kernel": 34.0 * (11448112 + 7168) / 2}
+                   "march_train_emit_kernel": 36.0 * N, "march_train_count_warp_kernel": 36.0 * BATCH + 4.0 * N,
+                   "adam_kernel": 34.0 * n_params / 2, "adam_vec4_kernel": 34.0 * n_params / 2}  # 2 launches per step (xyz, rgb)
     model_flops = {"field_mlp_bw_simt_kernel": 40960.0 * N, "density_mlp_fw_simt_kernel": 2 * 3072.0 * N, "rgb_mlp_fw_simt_kernel": 2 * 7168.0 * N,
-                   "field_mlp_bw_tc_kernel": 40960.0 * N, "field_fw_tc_kernel": 20480.0 * N}
+                   "field_mlp_bw_tc_kernel": 40960.0 * N, "field_mlp_fw_tc_kernel": 20480.0 * N}
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch read from the committed ncu --set full capture
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch", {})
     per_step = {k: ms / args.steps for k, (c, ms) in prof.items()}
     top = max(per_step, key=per_step.get) if per_step else None
     roof = None
@@ -249,11 +255,11 @@ def run_ours(args):
         per_launch_s = ms / calls * 1e-3
         if top in model_flops:
             ach = model_flops[top] / per_launch_s / 1e12
-            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": traffic.get(top),
                     "peak_source": peak_src + " (sustained bf16)", "ms_per_launch": per_launch_s * 1e3}
         else:
             ach = model_bytes.get(top, 0.0) / per_launch_s / 1e9
-            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic.get(top),
                     "peak_source": peak_src, "ms_per_launch": per_launch_s * 1e3}
     hash_gbs = None
     if "hash_encode_fw_kernel" in prof:

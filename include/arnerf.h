@@ -175,11 +175,15 @@ typedef struct {
     const uint32_t* offset_host;
 } arn_levels_t;
 
-/* Workspace layout of one field evaluation over n samples (all device buffers owned by the caller).
- *   feat  (n,32) f16   encoded features                      hid   (n,64) f16   density hidden layer
- *   h     (n,16) f32   density-net output (h[:,0] = log sigma)
- *   in32  (n,32) f16   colour-net input [sh16 | h16]         hid1, hid2 (n,64) f16  colour hidden layers
- * For a density-only evaluation (NGP.density) dirs, in32, hid1, hid2, rgbs and params_rgb_f16 are NULL. */
+/* Workspace layout of one field evaluation over n samples (all device buffers owned by the caller).  Every buffer holds
+ * m = 128 * ceil(n / 128) rows: the kernels move whole 128-row tiles with bulk (TMA) copies.
+ *   feat  (m,32) f16   encoded features                      hid   (m,64) f16   density hidden layer
+ *   h     (m,16) f32   density-net output (h[:,0] = log sigma), plain row-major
+ *   in32  (m,32) f16   colour-net input [sh16 | h16]         hid1, hid2 (m,64) f16  colour hidden layers
+ * feat/hid/in32/hid1/hid2 (and dfeat_scratch (m,32) f32 of the backward) are opaque "tile images": within a row the
+ * 16-byte chunks are stored in the order of the shared-memory swizzle of that row width, so that a tile is one contiguous
+ * block the tensor-core kernels copy straight into an operand buffer.  They are produced and consumed by this library
+ * only.  For a density-only evaluation (NGP.density) dirs, in32, hid1, hid2, rgbs and params_rgb_f16 are NULL. */
 #define ARN_FIELD_SCRATCH_SLABS 512
 #define ARN_FIELD_SCRATCH_BYTES (20480 + ARN_FIELD_SCRATCH_SLABS * 10240 * 4)
 typedef struct {
