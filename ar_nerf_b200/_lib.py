@@ -48,6 +48,8 @@ SIGNATURES = {
     "arn_last_error": [],
     "arn_launch_count": [],
     "arn_set_tunable": [C.c_char_p, I],
+    "arn_grid_cell_positions": [P, P, L, I, F, P, P],
+    "arn_density_grid_update": [P, P, P, F, F, L, P, P, P],
     "arn_profile_enable": [I],
     "arn_profile_report": [C.c_char_p, I],
     "arn_ray_aabb_intersect": [P, P, L, P, P, I, I, P, P, P, P],

@@ -163,16 +163,18 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
         hidden_row(trow + 0, sm + kFwH0);
         // ---- density layer 2 -> h (16, fp32), sigma
         issue_only(64, aH0, bD2, kI16, 4);
-        if (tid == 0) { bulk_s2g(hid + tile * 128 * 64, base + kFwH0, kFwSmemTile64); bulk_commit(); }
+        if (tid == 0 && hid) { bulk_s2g(hid + tile * 128 * 64, base + kFwH0, kFwSmemTile64); bulk_commit(); }
         wait_mma();
         {
             float hv[16];
             tmem_ld16(trow + 64, hv); tmem_ld_wait();
             if (valid) sigmas[i] = expf(hv[0]);
             // h tile staging: plain row-major 128 x 16 f32, the public layout of h
+            if (h) {
 #pragma unroll
-            for (int c = 0; c < 4; c++)
-                *reinterpret_cast<float4*>(sm + kFwHS + tid * 64 + c * 16) = make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+                for (int c = 0; c < 4; c++)
+                    *reinterpret_cast<float4*>(sm + kFwHS + tid * 64 + c * 16) = make_float4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+            }
             if (with_rgb) {  // colour-net input row [sh16 | fp16(h16)]
                 float sh[16];
                 sh4_eval(dcur, sh);
@@ -184,27 +186,29 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
             }
         }
         if (!with_rgb) {
-            fence_async_smem(); __syncthreads();
-            if (tid == 0) { bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64); bulk_commit(); }
+            if (h) {
+                fence_async_smem(); __syncthreads();
+                if (tid == 0) { bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64); bulk_commit(); }
+            }
             continue;
         }
         // ---- colour layer 1
         issue_only(0, aI, bC1, kI64, 2);
         if (tid == 0) {
-            bulk_s2g(in32 + tile * 128 * 32, base + kFwI, kFwSmemTile32);
-            bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64);
+            if (hid) bulk_s2g(in32 + tile * 128 * 32, base + kFwI, kFwSmemTile32);
+            if (h) bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64);
             bulk_commit();
         }
         wait_mma();
         hidden_row(trow + 0, sm + kFwH1);
         // ---- colour layer 2
         issue_only(64, aH1, bC2, kI64, 4);
-        if (tid == 0) { bulk_s2g(hid1 + tile * 128 * 64, base + kFwH1, kFwSmemTile64); bulk_commit(); }
+        if (tid == 0 && hid) { bulk_s2g(hid1 + tile * 128 * 64, base + kFwH1, kFwSmemTile64); bulk_commit(); }
         wait_mma();
         hidden_row(trow + 64, sm + kFwH2);
         // ---- colour layer 3 -> rgb
         issue_only(0, aH2, bC3, kI16, 4);
-        if (tid == 0) { bulk_s2g(hid2 + tile * 128 * 64, base + kFwH2, kFwSmemTile64); bulk_commit(); }
+        if (tid == 0 && hid) { bulk_s2g(hid2 + tile * 128 * 64, base + kFwH2, kFwSmemTile64); bulk_commit(); }
         fetch_dir(tile + gridDim.x);
         wait_mma();
         {
@@ -244,9 +248,10 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
                                            int rgb_act, arn_field_ws_t ws, float* sigmas, float* rgbs, arn_stream_t stream) {
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
-    ARN_REQUIRE(xyzs && params_xyz_f16 && ws.feat && ws.hid && ws.h && ws.wimg && sigmas, "null pointer");
+    ARN_REQUIRE(xyzs && params_xyz_f16 && ws.feat && ws.wimg && sigmas, "null pointer");
     const bool with_rgb = dirs != nullptr;
-    if (with_rgb) ARN_REQUIRE(params_rgb_f16 && ws.in32 && ws.hid1 && ws.hid2 && rgbs, "null pointer (colour branch)");
+    // ws.hid == NULL: inference -- no activation is saved for a backward (ws.h is optional in either mode)
+    if (with_rgb) ARN_REQUIRE(params_rgb_f16 && rgbs && (!ws.hid || (ws.in32 && ws.hid1 && ws.hid2)), "null pointer (colour branch)");
     cudaStream_t st = (cudaStream_t)stream;
     const __half* pxyz = (const __half*)params_xyz_f16;
     if (int e = hash_encode_fw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, /*tile_image=*/1, stream)) return e;

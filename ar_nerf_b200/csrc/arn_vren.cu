@@ -136,6 +136,73 @@ __global__ void __launch_bounds__(256) packbits_f64_kernel(const double* __restr
     bits[n] = (uint8_t)byte;
 }
 
+// ---------------------------------------------------------------------------------------------- occupancy refresh
+// networks.py:263-267: cell centre in world units plus a uniform jitter of half a cell, in torch's operation order
+// (int -> float, division by the scalar G-1 -- which torch's CUDA kernel performs as a multiplication by the float
+// reciprocal --, *2, -1, *(s - half); rand*2-1, *half; +): positions are bit-identical with
+//   xyzs_w = (coords / (G-1) * 2 - 1) * (s - half);  xyzs_w += (rand * 2 - 1) * half
+__global__ void __launch_bounds__(256) cell_positions_kernel(const int32_t* __restrict__ coords, const float* __restrict__ rnd, int64_t n3,
+                                                             float inv_gm1, float s_minus_half, float half, float* __restrict__ xyzs) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one coordinate per thread
+    if (e >= n3) return;
+    const float c = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)coords[e], inv_gm1), 2.0f), 1.0f), s_minus_half);
+    const float j = __fmul_rn(__fsub_rn(__fmul_rn(rnd[e], 2.0f), 1.0f), half);
+    xyzs[e] = __fadd_rn(c, j);
+}
+
+// networks.py:273-279: grid = where(grid < 0, grid, max(grid * decay, tmp)) in place, plus the sum / count of the positive
+// cells of the result (for the mean that caps the occupancy threshold).  Per-block partials in double, fixed order.
+__global__ void __launch_bounds__(256) grid_update_kernel(float* __restrict__ grid, const float* __restrict__ tmp, const float* __restrict__ decay_cells,
+                                                          float decay, int64_t n, double* __restrict__ part_sum, int64_t* __restrict__ part_cnt) {
+    __shared__ double s_sum[8]; __shared__ int64_t s_cnt[8];
+    double sum = 0.0; int64_t cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = grid[i];
+        float ng = g;
+        if (!(g < 0.0f)) { ng = fmaxf(__fmul_rn(g, decay_cells ? decay_cells[i] : decay), tmp[i]); grid[i] = ng; }
+        if (ng > 0.0f) { sum += (double)ng; cnt++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(kFull, sum, o); cnt += __shfl_xor_sync(kFull, cnt, o); }
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0; int64_t b = 0;
+        for (int k = 0; k < 8; k++) { a += s_sum[k]; b += s_cnt[k]; }
+        part_sum[blockIdx.x] = a; part_cnt[blockIdx.x] = b;
+    }
+}
+// threshold = min(mean of the positive cells, density_threshold) (networks.py:280-281), written to thr_out[0]
+__global__ void __launch_bounds__(256) grid_threshold_kernel(const double* __restrict__ part_sum, const int64_t* __restrict__ part_cnt, int n_parts,
+                                                             float density_threshold, float* __restrict__ thr_out) {
+    __shared__ double s_sum[256]; __shared__ int64_t s_cnt[256];
+    double a = 0.0; int64_t b = 0;
+    for (int k = threadIdx.x; k < n_parts; k += 256) { a += part_sum[k]; b += part_cnt[k]; }
+    s_sum[threadIdx.x] = a; s_cnt[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = 0.0; b = 0;
+        for (int k = 0; k < 256; k++) { a += s_sum[k]; b += s_cnt[k]; }
+        // no positive cell: torch's mean of an empty selection is NaN and min(NaN, thr) in Python keeps NaN -> nothing is occupied
+        const float mean = b > 0 ? (float)(a / (double)b) : NAN;
+        thr_out[0] = mean < density_threshold ? mean : (b > 0 ? density_threshold : NAN);
+    }
+}
+// packbits with the threshold read from device memory (no host round trip between the refresh and the packing)
+__global__ void __launch_bounds__(256) packbits_devthr_kernel(const float* __restrict__ grid, const float* __restrict__ thr_dev, uint8_t* __restrict__ bits, int64_t n_bytes) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b0 = w * 4;
+    if (b0 >= n_bytes) return;
+    const float thr = thr_dev[0];
+    const int nb = (int)min((int64_t)4, n_bytes - b0);
+    for (int b = 0; b < nb; b++) {
+        uint32_t byte = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) byte |= (grid[(b0 + b) * 8 + i] > thr) ? (1u << i) : 0u;
+        bits[b0 + b] = (uint8_t)byte;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- march (train)
 // Pass 1 (raymarching.cu:184-234).  Counts go to rays_a[r][2]; if t_scratch != nullptr the parameter t of sample i
 // of ray r is recorded at t_scratch[r*max_samples + i] so that pass 2 needs no second march.
@@ -717,6 +784,38 @@ extern "C" ARN_API int arn_packbits(const void* density_grid, int grid_dtype, fl
     else if (grid_dtype == 2) ARN_LAUNCH("packbits_f64_kernel", st, packbits_f64_kernel<<<ceil_div(n_bytes, 256), 256, 0, st>>>((const double*)density_grid, threshold, density_bitfield, n_bytes));
     else { set_error("arn_packbits: grid_dtype must be 0 (f32), 1 (f16) or 2 (f64)"); return ARN_E_INVALID; }
     return check_launch("packbits");
+}
+
+extern "C" ARN_API int arn_grid_cell_positions(const int32_t* coords, const float* rnd, int64_t n_cells, int grid_size, float s, float* xyzs,
+                                               arn_stream_t stream) {
+    ARN_REQUIRE(n_cells >= 0 && grid_size >= 2, "bad size");
+    if (n_cells == 0) return ARN_OK;
+    ARN_REQUIRE(coords && rnd && xyzs, "null pointer");
+    const float half = s / (float)grid_size;  // Python: half_grid_size = s / G (double), s - half (double), both then cast by torch to float32
+    const float s_minus_half = (float)((double)s - (double)s / (double)grid_size);
+    const float half_f = (float)((double)s / (double)grid_size);
+    (void)half;
+    ARN_LAUNCH("cell_positions_kernel", (cudaStream_t)stream, cell_positions_kernel<<<ceil_div(3 * n_cells, 256), 256, 0, (cudaStream_t)stream>>>(
+        coords, rnd, 3 * n_cells, 1.0f / (float)(grid_size - 1), s_minus_half, half_f, xyzs));
+    return check_launch("grid_cell_positions");
+}
+
+extern "C" ARN_API int arn_density_grid_update(float* density_grid, const float* density_tmp, const float* decay_cells, float decay,
+                                               float density_threshold, int64_t n_cells, uint8_t* density_bitfield, void* scratch,
+                                               arn_stream_t stream) {
+    ARN_REQUIRE(n_cells > 0 && n_cells % 8 == 0, "n_cells must be a positive multiple of 8");
+    ARN_REQUIRE(density_grid && density_tmp && density_bitfield && scratch, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_parts = (int)min((int64_t)ARN_GRID_UPDATE_PARTS, (n_cells + 255) / 256);
+    double* part_sum = (double*)scratch; int64_t* part_cnt = (int64_t*)(part_sum + ARN_GRID_UPDATE_PARTS);
+    float* thr = (float*)(part_cnt + ARN_GRID_UPDATE_PARTS);
+    ARN_LAUNCH("grid_update_kernel", st, grid_update_kernel<<<n_parts, 256, 0, st>>>(density_grid, density_tmp, decay_cells, decay, n_cells, part_sum, part_cnt));
+    if (int e = check_launch("grid_update")) return e;
+    ARN_LAUNCH("grid_threshold_kernel", st, grid_threshold_kernel<<<1, 256, 0, st>>>(part_sum, part_cnt, n_parts, density_threshold, thr));
+    if (int e = check_launch("grid_threshold")) return e;
+    const int64_t n_bytes = n_cells / 8;
+    ARN_LAUNCH("packbits_devthr_kernel", st, packbits_devthr_kernel<<<ceil_div((n_bytes + 3) / 4, 256), 256, 0, st>>>(density_grid, thr, density_bitfield, n_bytes));
+    return check_launch("packbits_devthr");
 }
 
 static int check_march_cfg(int cascades, int grid_size, int max_samples) {

@@ -126,18 +126,56 @@ def tile_rows(n):
     return (n + 127) // 128 * 128
 
 
-def _workspace(n, device, with_rgb):
+_WIMG = {}
+
+
+def _scratch(device):
+    """Inference calls share one scratch per device (nothing outlives the call); a training forward owns its own."""
+    key = (device.type, device.index)
+    if key not in _WIMG:
+        _WIMG[key] = torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device)
+    return _WIMG[key]
+
+
+def _workspace(n, device, with_rgb, save=True, want_h=True):
+    """save=False (no backward will follow: torch.no_grad / test-time rendering / occupancy refresh): only the feature
+    tile image and, if asked for, h are allocated and the forward stores no activation."""
     e = lambda *s, dt=torch.float16: torch.empty(*s, dtype=dt, device=device)
     m = tile_rows(n)
-    ws = dict(feat=e(m, 32), hid=e(m, 64), h=e(m, 16, dt=torch.float32), wimg=torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device))
+    ws = dict(feat=e(m, 32))
+    if want_h or save:
+        ws["h"] = e(m, 16, dt=torch.float32)
+    if not save:
+        ws["wimg"] = _scratch(device)
+        return ws
+    ws.update(hid=e(m, 64), wimg=torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device))
     if with_rgb:
         ws.update(in32=e(m, 32), hid1=e(m, 64), hid2=e(m, 64))
     return ws
 
 
 def _c_ws(ws):
-    return FieldWs(ptr(ws["feat"]), ptr(ws["hid"]), ptr(ws["h"]), ptr(ws.get("in32")), ptr(ws.get("hid1")), ptr(ws.get("hid2")),
+    return FieldWs(ptr(ws["feat"]), ptr(ws.get("hid")), ptr(ws.get("h")), ptr(ws.get("in32")), ptr(ws.get("hid1")), ptr(ws.get("hid2")),
                    ptr(ws["wimg"]))
+
+
+@torch.no_grad()
+def field_inference(xyzs, dirs, params_xyz, params_rgb, state, impl="", want_h=False):
+    """Forward only (no autograd graph, no saved activations): (sigmas, rgbs | None, h | None)."""
+    xyzs = xyzs.contiguous().float()
+    n, dev = xyzs.shape[0], xyzs.device
+    with_rgb = dirs is not None
+    p16x = state.cache_xyz.get(params_xyz)
+    p16c = state.cache_rgb.get(params_rgb) if with_rgb else None
+    save = impl != ""  # the CUDA-core cross-check kernels always write their activations
+    ws = _workspace(n, dev, with_rgb, save=save, want_h=want_h)
+    sigmas = torch.empty(n, dtype=torch.float32, device=dev)
+    rgbs = torch.empty(n, 3, dtype=torch.float32, device=dev) if with_rgb else None
+    if with_rgb:
+        dirs = dirs.contiguous().float()
+    call("arn_field_fw" + impl, ptr(xyzs), ptr(dirs), n, state.mn, state.mx, state.geometry.c_levels, ptr(p16x), ptr(p16c),
+         state.rgb_act, _c_ws(ws), ptr(sigmas), ptr(rgbs), stream())
+    return sigmas, rgbs, (ws["h"][:n] if "h" in ws else None)
 
 
 class FieldFunction(torch.autograd.Function):

@@ -8,7 +8,7 @@ from torch import nn
 
 from . import vren
 from .custom_functions import TruncExp
-from .field import Encoding, FieldFunction, FieldState, HashGeometry, Network, NetworkWithInputEncoding
+from .field import Encoding, FieldFunction, FieldState, HashGeometry, Network, NetworkWithInputEncoding, field_inference
 
 NEAR_DISTANCE = 0.01  # models/rendering.py:10 (imported from there by the reference; defined here to avoid the cycle)
 
@@ -82,10 +82,16 @@ class NGP(nn.Module):
     def density(self, x, return_feat=False):
         """networks.py:95-108.  x (N,3) in [-scale, scale] -> sigmas (N) [, h (N,16)]."""
         self.host_box()
-        sigmas, _, h = FieldFunction.apply(x, None, self.xyz_encoder.params, None, self.field_state, self.field_impl)
+        if self._needs_graph(x):
+            sigmas, _, h = FieldFunction.apply(x, None, self.xyz_encoder.params, None, self.field_state, self.field_impl)
+        else:  # no backward can follow: nothing is saved, no activation leaves the SM
+            sigmas, _, h = field_inference(x, None, self.xyz_encoder.params, None, self.field_state, self.field_impl, want_h=return_feat)
         if return_feat:
             return sigmas, h
         return sigmas
+
+    def _needs_graph(self, x):
+        return torch.is_grad_enabled() and (x.requires_grad or self.xyz_encoder.params.requires_grad or self.rgb_net.params.requires_grad)
 
     def log_radiance_to_rgb(self, log_radiances, **kwargs):
         """networks.py:110-131."""
@@ -99,8 +105,11 @@ class NGP(nn.Module):
     def forward(self, x, d, **kwargs):
         """networks.py:133-165.  x (N,3), d (N,3) -> sigmas (N), rgbs (N,3)."""
         self.host_box()
-        sigmas, rgbs, _ = FieldFunction.apply(x, d, self.xyz_encoder.params, self.rgb_net.params, self.field_state,
-                                              self.field_impl)
+        if self._needs_graph(x):
+            sigmas, rgbs, _ = FieldFunction.apply(x, d, self.xyz_encoder.params, self.rgb_net.params, self.field_state,
+                                                  self.field_impl)
+        else:
+            sigmas, rgbs, _ = field_inference(x, d, self.xyz_encoder.params, self.rgb_net.params, self.field_state, self.field_impl)
         if self.use_raw_HDR:
             rgbs = F.leaky_relu(rgbs) if not kwargs.get('output_radiance', False) else torch.relu(rgbs)
         elif self.rgb_act == 'None':
@@ -124,9 +133,12 @@ class NGP(nn.Module):
 
     @torch.no_grad()
     def get_all_cells(self):
-        """networks.py:167-179."""
-        indices = vren.morton3D(self.grid_coords).long()
-        return [(indices, self.grid_coords)] * self.cascades
+        """networks.py:167-179.  grid_coords never changes, so its morton codes are computed once."""
+        key = (self.grid_coords.data_ptr(), self.grid_coords._version)
+        if getattr(self, '_all_cells_key', None) != key:
+            self._all_cells_idx = vren.morton3D(self.grid_coords).long()
+            self._all_cells_key = key
+        return [(self._all_cells_idx, self.grid_coords)] * self.cascades
 
     @torch.no_grad()
     def sample_uniform_and_occupied_cells(self, M, density_threshold):
@@ -180,13 +192,12 @@ class NGP(nn.Module):
         for c in range(self.cascades):
             indices, coords = cells[c]
             s = min(2 ** (c - 1), self.scale)
-            half_grid_size = s / self.grid_size
-            xyzs_w = (coords / (self.grid_size - 1) * 2 - 1) * (s - half_grid_size)
-            xyzs_w += (torch.rand_like(xyzs_w) * 2 - 1) * half_grid_size
+            # xyzs_w = (coords/(G-1)*2-1)*(s - s/G) + (rand*2-1)*(s/G): one kernel, same torch.rand_like draw, same bits
+            rnd = torch.rand(coords.shape, dtype=torch.float32, device=coords.device)
+            xyzs_w = vren.grid_cell_positions(coords, rnd, self.grid_size, s)
             density_grid_tmp[c, indices] = self.density(xyzs_w)
+        decay_cells = None
         if erode:
-            decay = torch.clamp(decay ** (1 / self.count_grid), 0.1, 0.95)
-        self.density_grid = torch.where(self.density_grid < 0, self.density_grid,
-                                        torch.maximum(self.density_grid * decay, density_grid_tmp))
-        mean_density = self.density_grid[self.density_grid > 0].mean().item()
-        vren.packbits(self.density_grid, min(mean_density, density_threshold), self.density_bitfield)
+            decay_cells = torch.clamp(decay ** (1 / self.count_grid), 0.1, 0.95).float().contiguous()
+        # where(grid < 0, grid, max(grid*decay, tmp)) in place, mean of the positive cells, threshold, packbits: no host sync
+        vren.density_grid_update(self.density_grid, density_grid_tmp, decay_cells, decay, density_threshold, self.density_bitfield)

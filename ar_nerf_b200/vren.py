@@ -94,6 +94,40 @@ def packbits(density_grid, density_threshold, density_bitfield):
          ptr(density_bitfield), n_bytes, stream())
 
 
+def grid_cell_positions(coords, rnd, grid_size, s):
+    """networks.py:263-267 in one kernel: (coords/(G-1)*2-1)*(s - s/G) + (rnd*2-1)*(s/G); coords (M,3) i32, rnd (M,3) f32."""
+    check_tensor(coords, "coords", torch.int32, 2, 3); check_tensor(rnd, "rnd", torch.float32, 2, 3)
+    if rnd.shape != coords.shape:
+        raise RuntimeError("rnd must have the shape of coords")
+    out = torch.empty(coords.shape, dtype=torch.float32, device=coords.device)
+    call("arn_grid_cell_positions", ptr(coords), ptr(rnd), coords.shape[0], int(grid_size), float(s), ptr(out), stream())
+    return out
+
+
+_GRID_SCRATCH = {}
+
+
+def density_grid_update(density_grid, density_tmp, decay_cells, decay, density_threshold, density_bitfield):
+    """networks.py:273-281 without the host round trip: EMA/max refresh in place, threshold = min(mean(grid[grid>0]),
+    density_threshold) on the device, packbits.  Returns the 1-element device tensor holding the threshold used."""
+    check_tensor(density_grid, "density_grid", torch.float32); check_tensor(density_tmp, "density_tmp", torch.float32)
+    check_tensor(density_bitfield, "density_bitfield", torch.uint8)
+    n = density_grid.numel()
+    if density_tmp.numel() != n or density_bitfield.numel() * 8 != n:
+        raise RuntimeError("density_tmp / density_bitfield do not match density_grid")
+    if decay_cells is not None:
+        check_tensor(decay_cells, "decay_cells", torch.float32)
+        if decay_cells.numel() != n:
+            raise RuntimeError("decay_cells does not match density_grid")
+    key = (density_grid.device.type, density_grid.device.index)
+    if key not in _GRID_SCRATCH:
+        _GRID_SCRATCH[key] = torch.empty(2048 * 16 + 16, dtype=torch.uint8, device=density_grid.device)
+    scratch = _GRID_SCRATCH[key]
+    call("arn_density_grid_update", ptr(density_grid), ptr(density_tmp), ptr(decay_cells), float(decay) if decay_cells is None else 0.0,
+         float(density_threshold), n, ptr(density_bitfield), ptr(scratch), stream())
+    return scratch[2048 * 16:2048 * 16 + 4].view(torch.float32)
+
+
 def raymarching_train(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size,
                       max_samples):
     """binding.cpp:60-81 -> raymarching.cu:283-332.  Returns [rays_a, xyzs, dirs, deltas, ts, counter]."""

@@ -76,6 +76,22 @@ int arn_morton3d_invert(const int32_t* indices, int64_t n, int32_t* coords, arn_
 int arn_packbits(const void* density_grid, int grid_dtype, float threshold, uint8_t* density_bitfield,
                  int64_t n_bytes, arn_stream_t stream);
 
+/* Occupancy refresh, the arithmetic of NGP.update_density_grid (networks.py:253-281) around the density evaluation:
+ *   arn_grid_cell_positions : xyzs_w = (coords/(G-1)*2-1)*(s - s/G) + (rnd*2-1)*(s/G) for n_cells cells (networks.py:263-267;
+ *                             rnd is the caller's torch.rand_like draw, positions are bit-identical with the torch expression);
+ *   arn_density_grid_update : density_grid = where(grid < 0, grid, max(grid*decay, tmp)) IN PLACE (decay_cells != NULL: a
+ *                             per-cell decay, the `erode` path), threshold = min(mean(grid[grid > 0]), density_threshold)
+ *                             accumulated in double on the device, then packbits with that threshold -- no host round trip
+ *                             (the reference does .item() here).  scratch: ARN_GRID_UPDATE_SCRATCH_BYTES; the threshold used
+ *                             is left in the last 4 bytes of the scratch (float). */
+#define ARN_GRID_UPDATE_PARTS 2048
+#define ARN_GRID_UPDATE_SCRATCH_BYTES (ARN_GRID_UPDATE_PARTS * 16 + 16)
+int arn_grid_cell_positions(const int32_t* coords, const float* rnd, int64_t n_cells, int grid_size, float s, float* xyzs,
+                            arn_stream_t stream);
+int arn_density_grid_update(float* density_grid, const float* density_tmp, const float* decay_cells, float decay,
+                            float density_threshold, int64_t n_cells, uint8_t* density_bitfield, void* scratch,
+                            arn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Training ray march.  Replaces vren.raymarching_train (binding.cpp:60-81 -> raymarching.cu:283-332, kernel :166-280).
  * The reference's one kernel (count, two atomics, re-march into worst-case R*max_samples buffers) is split:
@@ -183,7 +199,9 @@ typedef struct {
  * feat/hid/in32/hid1/hid2 (and dfeat_scratch (m,32) f32 of the backward) are opaque "tile images": within a row the
  * 16-byte chunks are stored in the order of the shared-memory swizzle of that row width, so that a tile is one contiguous
  * block the tensor-core kernels copy straight into an operand buffer.  They are produced and consumed by this library
- * only.  For a density-only evaluation (NGP.density) dirs, in32, hid1, hid2, rgbs and params_rgb_f16 are NULL. */
+ * only.  For a density-only evaluation (NGP.density) dirs, in32, hid1, hid2, rgbs and params_rgb_f16 are NULL.
+ * Inference (no backward will follow): hid = in32 = hid1 = hid2 = NULL skips every activation store of the forward
+ * (tensor-core path); h = NULL skips the h output as well. */
 #define ARN_FIELD_SCRATCH_SLABS 512
 #define ARN_FIELD_SCRATCH_BYTES (20480 + ARN_FIELD_SCRATCH_SLABS * 10240 * 4)
 typedef struct {

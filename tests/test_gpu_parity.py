@@ -624,6 +624,34 @@ def test_render_test_end_to_end(w1):
     assert_rel(N(res["rgb"]), rgb, rtol=1e-4, what="rgb", atol=ALPHA_ATOL * 10)
 
 
+def test_grid_refresh_kernels_vs_torch(vren):
+    """arn_grid_cell_positions / arn_density_grid_update against the torch expressions of networks.py:263-281."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    G, M = 128, 100_000
+    coords = torch.randint(G, (M, 3), dtype=torch.int32, device=dev(), generator=g)
+    rnd = torch.rand(M, 3, device=dev(), generator=g)
+    for s in (0.5, 1.0, 8.0):
+        half = s / G
+        want = (coords / (G - 1) * 2 - 1) * (s - half)
+        want += (rnd * 2 - 1) * half
+        assert torch.equal(vren.grid_cell_positions(coords, rnd, G, s), want)
+    n = 2 * 64 ** 3
+    for thr_cap, erode in ((5.912, False), (0.3, False), (5.912, True)):
+        grid = torch.randn(n, device=dev(), generator=g) * 3
+        grid[torch.rand(n, device=dev(), generator=g) < 0.2] = -1.0
+        tmp = torch.rand(n, device=dev(), generator=g) * 10 * (torch.rand(n, device=dev(), generator=g) < 0.3)
+        decay_cells = torch.clamp(0.95 ** (1 / torch.rand(n, device=dev(), generator=g)), 0.1, 0.95) if erode else None
+        want_grid = torch.where(grid < 0, grid, torch.maximum(grid * (decay_cells if erode else 0.95), tmp))
+        thr = min(float(np.float32(N(want_grid[want_grid > 0]).astype(np.float64).mean())), thr_cap)
+        want_bits = np.zeros(n // 8, np.uint8)
+        oracle.packbits(N(want_grid), thr, want_bits)
+        bitfield = torch.zeros(n // 8, dtype=torch.uint8, device=dev())
+        thr_dev = vren.density_grid_update(grid, tmp, decay_cells, 0.95, thr_cap, bitfield)
+        assert torch.equal(grid, want_grid)
+        assert float(thr_dev.item()) == float(np.float32(thr))  # the reference casts the threshold to float at the binding
+        assert np.array_equal(N(bitfield), want_bits)
+
+
 def test_density_grid_update_bits(w1):
     """update_density_grid (networks.py:253-281): given the same density values the packed bits are bit-exact."""
     from ar_nerf_b200.networks import NGP
@@ -632,7 +660,7 @@ def test_density_grid_update_bits(w1):
     w1.install(model)
     model.update_density_grid(5.912, warmup=True)
     dg = N(model.density_grid)
-    thr = min(float(dg[dg > 0].mean()), 5.912)
+    thr = min(float(np.float32(dg[dg > 0].astype(np.float64).mean())), 5.912)  # the mean is accumulated in double on the device
     want = np.zeros(model.density_bitfield.numel(), np.uint8)
     oracle.packbits(dg, thr, want)
     assert np.array_equal(N(model.density_bitfield), want)
