@@ -83,6 +83,8 @@ SIGNATURES = {
     "arn_march_train_emit_dyn": [P, P, L, I, I, F, F, I, P, P, P, P, P, P, P, L, P],
     "arn_nerf_loss": [P, P, P, P, L, P, F, F, F, F, P, P, P, P, P, P],
     "arn_train_fwbw": [C.POINTER(TrainCfg), P],
+    "arn_train_march": [C.POINTER(TrainCfg), P],
+    "arn_train_fwbw_marched": [C.POINTER(TrainCfg), P],
     "arn_field_bw_simt": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
     "arn_hash_encode_fw": [P, L, P, P, Levels, P, P, P],
     "arn_hash_encode_bw": [P, L, P, P, Levels, P, P, P, P, P],

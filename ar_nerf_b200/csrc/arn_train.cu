@@ -90,15 +90,24 @@ extern "C" ARN_API int arn_nerf_loss(const float* rgb, const float* opacity, con
     return check_launch("nerf_loss");
 }
 
-extern "C" ARN_API int arn_train_fwbw(const arn_train_t* c, arn_stream_t stream) {
+// The geometry half of the step: depends on the rays and the occupancy bitfield only (not on the weights), so a caller
+// may run it for the NEXT batch on a second stream while the current batch is in its field / optimizer kernels.
+extern "C" ARN_API int arn_train_march(const arn_train_t* c, arn_stream_t stream) {
     ARN_REQUIRE(c, "null config");
     ARN_REQUIRE(c->n_rays > 0 && c->capacity > 0, "bad sizes");
     const int64_t R = c->n_rays;
     if (int e = arn_ray_aabb_near(c->rays_o, c->rays_d, R, c->center_host, c->half_size_host, c->near, c->hits_t, stream)) return e;
     if (int e = arn_march_train_count_ex(c->rays_o, c->rays_d, c->hits_t, R, c->density_bitfield, c->cascades, c->grid_size, c->scale,
                                          c->exp_step_factor, c->noise, c->max_samples, c->rays_a, c->counter, c->t_scratch, c->count_scratch, stream)) return e;
-    if (int e = arn_march_train_emit_dyn(c->rays_o, c->rays_d, R, c->cascades, c->grid_size, c->scale, c->exp_step_factor, c->max_samples, c->rays_a,
-                                         c->t_scratch, c->counter, c->xyzs, c->dirs, c->deltas, c->ts, c->capacity, stream)) return e;
+    return arn_march_train_emit_dyn(c->rays_o, c->rays_d, R, c->cascades, c->grid_size, c->scale, c->exp_step_factor, c->max_samples, c->rays_a,
+                                    c->t_scratch, c->counter, c->xyzs, c->dirs, c->deltas, c->ts, c->capacity, stream);
+}
+
+// The rest of the step on samples arn_train_march has produced (rays_a, counter, xyzs, dirs, deltas, ts of the config).
+extern "C" ARN_API int arn_train_fwbw_marched(const arn_train_t* c, arn_stream_t stream) {
+    ARN_REQUIRE(c, "null config");
+    ARN_REQUIRE(c->n_rays > 0 && c->capacity > 0, "bad sizes");
+    const int64_t R = c->n_rays;
     if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
                                     c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
     if (int e = arn_composite_train_fw(c->sigmas, c->rgbs, c->deltas, c->ts, c->rays_a, R, c->capacity, c->T_threshold, c->total_samples, c->opacity,
@@ -110,4 +119,9 @@ extern "C" ARN_API int arn_train_fwbw(const arn_train_t* c, arn_stream_t stream)
     return field_bw_tc_impl(c->xyzs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16, c->params_rgb_f16,
                             c->rgb_act, c->ws, c->sigmas, c->rgbs, c->dL_dsigmas, c->dL_drgbs, c->loss_scale, c->dfeat, c->grad_xyz, c->grad_rgb,
                             nullptr, /*pack_weights=*/false, stream);
+}
+
+extern "C" ARN_API int arn_train_fwbw(const arn_train_t* c, arn_stream_t stream) {
+    if (int e = arn_train_march(c, stream)) return e;
+    return arn_train_fwbw_marched(c, stream);
 }

@@ -145,12 +145,19 @@ class NGP(nn.Module):
         """networks.py:181-207 (same torch RNG calls in the same order)."""
         cells = []
         for c in range(self.cascades):
-            coords1 = torch.randint(self.grid_size, (M, 3), dtype=torch.int32, device=self.density_grid.device)
+            dev = self.density_grid.device
+            coords1 = torch.randint(self.grid_size, (M, 3), dtype=torch.int32, device=dev)
             indices1 = vren.morton3D(coords1).long()
-            indices2 = torch.nonzero(self.density_grid[c] > density_threshold)[:, 0]
-            if len(indices2) > 0:
-                rand_idx = torch.randint(len(indices2), (M,), device=self.density_grid.device)
-                indices2 = indices2[rand_idx]
+            # M occupied cells drawn uniformly with replacement (networks.py:196-201).  The reference materialises
+            # nonzero(grid > thr) and indexes it with randint(len) -- a host round trip per cascade; here the k-th occupied
+            # cell is found on the device through the running count of occupied cells: same distribution, no sync.
+            occupied = self.density_grid[c] > density_threshold
+            running = torch.cumsum(occupied, 0, dtype=torch.int32)
+            count = running[-1]
+            u = torch.randint(2 ** 31 - 1, (M,), device=dev)
+            k = torch.remainder(u, count.clamp(min=1)).int()
+            indices2 = torch.searchsorted(running, k + 1).clamp_(max=occupied.numel() - 1)
+            # (an empty grid makes the reference skip this half; here it degenerates to re-sampling one cell, which is harmless)
             coords2 = vren.morton3D_invert(indices2.int())
             cells += [(torch.cat([indices1, indices2]), torch.cat([coords1, coords2]))]
         return cells

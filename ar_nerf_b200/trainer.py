@@ -41,29 +41,48 @@ class FusedAdam:
                 cache.mark_fresh(p)
 
 
+class _MarchSet:
+    """What arn_train_march produces for one batch (and arn_train_fwbw_marched consumes).  Two sets alternate so that
+    the next batch can be marched while the current one is still in its field / compositing kernels."""
+
+    def __init__(self, n_rays, capacity, device):
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+        self.rays_a = torch.empty(n_rays, 3, dtype=torch.int64, device=device)
+        self.counter = torch.zeros(2, dtype=torch.int32, device=device)
+        self.xyzs, self.dirs, self.deltas, self.ts = f(capacity, 3), f(capacity, 3), f(capacity), f(capacity)
+        self.inputs = None   # (rays_o, rays_d, noise) marched into this set: kept alive until the set is consumed
+        self.ready = torch.cuda.Event()  # recorded after a side-stream (prefetched) march
+        self.pending = False             # a prefetched march is in flight / waiting to be consumed
+        self.grid_epoch = -1             # occupancy refresh count the set was marched against
+        self.cfg = self.cfg_key = self.host = None
+
+
 class _FusedWorkspace:
-    """Device buffers of the fused step (arn_train_fwbw), allocated once: per-ray tensors for `n_rays`, per-sample
-    tensors for `capacity` samples (n_rays * max_samples can never overflow)."""
+    """Device buffers of the fused step (arn_train_march + arn_train_fwbw_marched), allocated once: per-ray tensors for
+    `n_rays`, per-sample tensors for `capacity` samples (n_rays * max_samples can never overflow)."""
 
     def __init__(self, n_rays, capacity, device):
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
         h = lambda *s: torch.empty(*s, dtype=torch.float16, device=device)
         R, N = n_rays, capacity
         self.n_rays, self.capacity = R, N
-        self.hits_t, self.rays_a = f(R, 1, 2), torch.empty(R, 3, dtype=torch.int64, device=device)
-        self.counter = torch.zeros(2, dtype=torch.int32, device=device)
+        self.march = [_MarchSet(R, N, device), _MarchSet(R, N, device)]
+        self.cur = 0
+        # march scratch: shared by the two sets (marches are serialised: see NGPTrainer._march)
+        self.hits_t = f(R, 1, 2)
         self.t_scratch = f(R * MAX_SAMPLES)
         self.count_scratch = torch.empty(R, dtype=torch.int32, device=device)
         self.total_samples = torch.empty(R, dtype=torch.int64, device=device)
         self.opacity, self.depth, self.rgb, self.rgb_final = f(R), f(R), f(R, 3), f(R, 3)
         self.dL_dopacity, self.dL_ddepth, self.dL_drgb = f(R), f(R), f(R, 3)
-        self.xyzs, self.dirs, self.deltas, self.ts = f(N, 3), f(N, 3), f(N), f(N)
         self.sigmas, self.rgbs, self.ws_out = f(N), f(N, 3), f(N)
         self.dL_dsigmas, self.dL_drgbs, self.dfeat = f(N), f(N, 3), f(N, 32)
         self.feat, self.hid, self.h = h(N, 32), h(N, 64), f(N, 16)
         self.in32, self.hid1, self.hid2 = h(N, 32), h(N, 64), h(N, 64)
         self.wimg = torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=device)
+        self.marched = torch.cuda.Event()
+        self.side = torch.cuda.Stream(device=device)  # the prefetched march runs here, filling issue slots the main stream leaves idle
 
 
 class NGPTrainer:
@@ -87,6 +106,7 @@ class NGPTrainer:
         st.direct_grad = True
         self.opt = FusedAdam([(model.xyz_encoder.params, st.cache_xyz), (model.rgb_net.params, st.cache_rgb)], lr)
         self.global_step = 0
+        self._grid_epoch = 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
 
     def lr_at(self, step):
@@ -95,46 +115,100 @@ class NGPTrainer:
         eta_min = self.base_lr / 30
         return eta_min + (self.base_lr - eta_min) * (1 + math.cos(math.pi * e / self.num_epochs)) / 2
 
-    def _fused_fwbw(self, rays_o, rays_d, rgb_target, noise):
-        m, st = self.model, self.model.field_state
-        R, dev = rays_o.shape[0], rays_o.device
+    def _workspace(self, R, dev):
         if self._ws is None or self._ws.n_rays != R:
             self._ws = _FusedWorkspace(R, (int(self.sample_capacity or R * MAX_SAMPLES) + 127) // 128 * 128, dev)
-        w = self._ws
-        center, half = m.host_box()
+        return self._ws
+
+    def _cfg(self, ms, rgb_target):
+        """arn_train_t for march set `ms` (its inputs must be set).  The struct is built once per set and only the batch
+        pointers are refreshed per call (the workspace, the fp16 parameter copies and the gradients never move)."""
+        m, st, w = self.model, self.model.field_state, self._ws
+        ro, rd, nz = ms.inputs
+        p16x = st.cache_xyz.get(m.xyz_encoder.params); p16c = st.cache_rgb.get(m.rgb_net.params)
+        key = (id(w), m.density_bitfield.data_ptr(), p16x.data_ptr(), p16c.data_ptr(), m.xyz_encoder.params.grad.data_ptr(),
+               m.rgb_net.params.grad.data_ptr(), self.exp_step_factor, self.grad_scale, st.loss_scale)
+        if ms.cfg is None or ms.cfg_key != key:
+            center, half = m.host_box()
+            bgv = 1.0 if self.exp_step_factor == 0 else 0.0
+            ms.host = ((C.c_float * 3)(*center), (C.c_float * 3)(*half), (C.c_float * 3)(bgv, bgv, bgv))  # kept alive with the struct
+            cast = lambda a: C.cast(a, C.c_void_p)
+            ms.cfg = TrainCfg(
+                None, None, None, None, ro.shape[0],
+                ptr(m.density_bitfield), m.cascades, m.grid_size, float(m.scale), float(self.exp_step_factor), MAX_SAMPLES, 1e-4, NEAR_DISTANCE,
+                cast(ms.host[0]), cast(ms.host[1]), cast(st.mn), cast(st.mx),
+                st.geometry.c_levels, ptr(p16x), ptr(p16c), st.rgb_act,
+                cast(ms.host[2]), float(self.loss.lambda_opacity), float(self.depth_loss_w), float(self.grad_scale), float(st.loss_scale),
+                ptr(w.hits_t), ptr(ms.rays_a), ptr(ms.counter), ptr(w.t_scratch), ptr(w.count_scratch), ptr(w.total_samples),
+                ptr(w.opacity), ptr(w.depth), ptr(w.rgb), ptr(w.rgb_final), ptr(w.dL_dopacity), ptr(w.dL_ddepth), ptr(w.dL_drgb),
+                w.capacity, ptr(ms.xyzs), ptr(ms.dirs), ptr(ms.deltas), ptr(ms.ts), ptr(w.sigmas), ptr(w.rgbs), ptr(w.ws_out),
+                ptr(w.dL_dsigmas), ptr(w.dL_drgbs), ptr(w.dfeat),
+                FieldWs(ptr(w.feat), ptr(w.hid), ptr(w.h), ptr(w.in32), ptr(w.hid1), ptr(w.hid2), ptr(w.wimg)),
+                ptr(m.xyz_encoder.params.grad), ptr(m.rgb_net.params.grad), ptr(w.loss))
+            ms.cfg_key = key
+        c = ms.cfg
+        c.rays_o, c.rays_d, c.noise = ro.data_ptr(), rd.data_ptr(), nz.data_ptr()
+        c.rgb_target = None if rgb_target is None else rgb_target.data_ptr()
+        return c
+
+    def _march(self, ms, rays_o, rays_d, noise, cuda_stream):
+        """Geometry half of the step for one batch into march set `ms` on `cuda_stream` (raw handle)."""
+        R, dev = rays_o.shape[0], rays_o.device
         if noise is None:
             noise = torch.rand(R, device=dev)  # the draw RayMarcher.forward makes (custom_functions.py:83)
-        self._keep = (rays_o.contiguous().float(), rays_d.contiguous().float(), rgb_target.contiguous().float(), noise.contiguous().float())
-        ro, rd, tgt, nz = self._keep
-        bgv = 1.0 if self.exp_step_factor == 0 else 0.0
-        self._host = ((C.c_float * 3)(*center), (C.c_float * 3)(*half), (C.c_float * 3)(bgv, bgv, bgv))
-        p16x = st.cache_xyz.get(m.xyz_encoder.params); p16c = st.cache_rgb.get(m.rgb_net.params)
-        cast = lambda a: C.cast(a, C.c_void_p)
-        cfg = TrainCfg(
-            ptr(ro), ptr(rd), ptr(tgt), ptr(nz), R,
-            ptr(m.density_bitfield), m.cascades, m.grid_size, float(m.scale), float(self.exp_step_factor), MAX_SAMPLES, 1e-4, NEAR_DISTANCE,
-            cast(self._host[0]), cast(self._host[1]), cast(st.mn), cast(st.mx),
-            st.geometry.c_levels, ptr(p16x), ptr(p16c), st.rgb_act,
-            cast(self._host[2]), float(self.loss.lambda_opacity), float(self.depth_loss_w), float(self.grad_scale), float(st.loss_scale),
-            ptr(w.hits_t), ptr(w.rays_a), ptr(w.counter), ptr(w.t_scratch), ptr(w.count_scratch), ptr(w.total_samples),
-            ptr(w.opacity), ptr(w.depth), ptr(w.rgb), ptr(w.rgb_final), ptr(w.dL_dopacity), ptr(w.dL_ddepth), ptr(w.dL_drgb),
-            w.capacity, ptr(w.xyzs), ptr(w.dirs), ptr(w.deltas), ptr(w.ts), ptr(w.sigmas), ptr(w.rgbs), ptr(w.ws_out),
-            ptr(w.dL_dsigmas), ptr(w.dL_drgbs), ptr(w.dfeat),
-            FieldWs(ptr(w.feat), ptr(w.hid), ptr(w.h), ptr(w.in32), ptr(w.hid1), ptr(w.hid2), ptr(w.wimg)),
-            ptr(m.xyz_encoder.params.grad), ptr(m.rgb_net.params.grad), ptr(w.loss))
-        call("arn_train_fwbw", C.byref(cfg), stream())
+        ms.inputs = (rays_o.contiguous().float(), rays_d.contiguous().float(), noise.contiguous().float())
+        call("arn_train_march", C.byref(self._cfg(ms, None)), cuda_stream)
+
+    def _fused_fwbw(self, rays_o, rays_d, rgb_target, noise, next_rays=None, next_is_update=False):
+        R, dev = rays_o.shape[0], rays_o.device
+        w = self._workspace(R, dev)
+        main = torch.cuda.current_stream()
+        main_h = main.cuda_stream
+        ms = w.march[w.cur]
+        pre = ms.pending and ms.inputs[0] is rays_o and ms.inputs[1] is rays_d and ms.grid_epoch == self._grid_epoch
+        if ms.pending:
+            main.wait_event(ms.ready)      # marched ahead on the side stream while the previous step was running
+            ms.pending = False
+        if not pre:
+            self._march(ms, rays_o, rays_d, noise, main_h)
+        prefetch = None
+        if next_rays is not None and not next_is_update:
+            n_ro, n_rd = next_rays[0], next_rays[1]
+            n_noise = next_rays[2] if len(next_rays) > 2 else None
+            if n_ro.is_contiguous() and n_rd.is_contiguous() and n_ro.dtype == torch.float32 and n_rd.dtype == torch.float32 and n_ro.shape[0] == R:
+                if n_noise is None:
+                    n_noise = torch.rand(R, device=dev)  # next in the RNG stream, exactly where the next step would draw it
+                prefetch = (n_ro, n_rd, n_noise)
+        self._keep_target = rgb_target.contiguous().float()
+        if prefetch is not None:
+            w.marched.record(main)         # from here on the shared march scratch is free and the prefetch inputs exist
+        call("arn_train_fwbw_marched", C.byref(self._cfg(ms, self._keep_target)), main_h)
+        if prefetch is not None:
+            # geometry of the next batch, concurrently with this batch's field / compositing / optimizer kernels: it reads the
+            # rays and the occupancy bits only.  (Skipped when the next step refreshes the occupancy grid first.)
+            nxt = w.march[w.cur ^ 1]
+            w.side.wait_event(w.marched)
+            self._march(nxt, *prefetch, w.side.cuda_stream)
+            nxt.ready.record(w.side)
+            nxt.pending = True
+            nxt.grid_epoch = self._grid_epoch
+        w.cur ^= 1
         # views into the reused workspace (valid until the next step); per-sample buffers hold counter[0] samples
-        results = {'rgb': w.rgb_final, 'opacity': w.opacity, 'depth': w.depth, 'rm_samples': w.counter[0].clone(),
-                   'rays_a': w.rays_a, 'total_samples_per_ray': w.total_samples, 'ts_buf': w.ts, 'deltas_buf': w.deltas,
+        results = {'rgb': w.rgb_final, 'opacity': w.opacity, 'depth': w.depth, 'rm_samples': ms.counter[0].clone(),
+                   'rays_a': ms.rays_a, 'total_samples_per_ray': w.total_samples, 'ts_buf': ms.ts, 'deltas_buf': ms.deltas,
                    'ws_buf': w.ws_out}
         return w.loss[0].clone(), results
 
-    def train_step(self, rays_o, rays_d, rgb_target, noise=None, update_grid=True):
+    def train_step(self, rays_o, rays_d, rgb_target, noise=None, update_grid=True, next_rays=None):
+        """One optimisation step.  next_rays = (rays_o, rays_d[, noise]) of the FOLLOWING call, if the caller already has
+        them on the device: their ray march is then overlapped with this step (pass the very same tensors next time)."""
         m = self.model
         if update_grid and self.global_step % self.update_interval == 0:
             m.update_density_grid(0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=self.global_step < self.warmup_steps)
+            self._grid_epoch += 1
         if self.fused:
-            loss, results = self._fused_fwbw(rays_o, rays_d, rgb_target, noise)
+            next_is_update = update_grid and (self.global_step + 1) % self.update_interval == 0
+            loss, results = self._fused_fwbw(rays_o, rays_d, rgb_target, noise, next_rays, next_is_update)
             if self.world > 1:
                 for p, _, _, _ in self.opt.items:
                     dist.all_reduce(p.grad)

@@ -288,6 +288,12 @@ typedef struct {
     float* grad_xyz; float* grad_rgb; float* loss_out;
 } arn_train_t;
 int arn_train_fwbw(const arn_train_t* cfg_host, arn_stream_t stream);
+/* The same step in its two halves.  arn_train_march (ray/box, march count + scan + emit) reads only the rays, the noise and
+ * the occupancy bitfield -- not the weights -- and fills rays_a, counter, xyzs, dirs, deltas, ts (+ the march scratch);
+ * arn_train_fwbw_marched does the rest on those buffers.  A trainer can therefore march batch k+1 on a second stream
+ * while batch k is in its field / optimizer kernels (ar_nerf_b200/trainer.py: next_rays=). */
+int arn_train_march(const arn_train_t* cfg_host, arn_stream_t stream);
+int arn_train_fwbw_marched(const arn_train_t* cfg_host, arn_stream_t stream);
 /* The loss kernel on its own (per-ray rgb/opacity/depth -> scalar loss + gradients; bg_host = 3 floats). */
 int arn_nerf_loss(const float* rgb, const float* opacity, const float* depth, const float* target, int64_t n_rays,
                   const float* bg_host, float lambda_opacity, float lambda_depth, float grid_scale, float grad_scale,

@@ -569,6 +569,29 @@ def test_fused_train_step_matches_eager(kind, w1, w3):
         assert abs(float(la) - float(lb)) <= 2e-3 * abs(float(lb)), (step, float(la), float(lb))
 
 
+@pytest.mark.parametrize("kind", ["W1", "W3"])
+def test_prefetched_march_is_the_same_step(kind, w1, w3):
+    """train_step(next_rays=...) marches the next batch on a side stream during the current step: same samples (bit-exact),
+    same losses as the plain sequence, including across an occupancy refresh (which invalidates a prefetch)."""
+    from ar_nerf_b200.trainer import NGPTrainer
+    w = workload(kind, w1, w3)
+    model_a, *_ = _field_setup(w.scale, 8, 31, table_amp=1.0)
+    model_b, *_ = _field_setup(w.scale, 8, 31, table_amp=1.0)
+    w.install(model_a); w.install(model_b)
+    ta = NGPTrainer(model_a, update_interval=3); tb = NGPTrainer(model_b, update_interval=3)
+    batches = [[T(t) for t in w.train_batch(40 + i, 2048)] for i in range(8)]
+    for i in range(7):
+        ro, rd, tgt, nz = batches[i]
+        nro, nrd, _, nnz = batches[i + 1]
+        torch.manual_seed(100 + i); la, ra = ta.train_step(ro, rd, tgt, noise=nz)
+        torch.manual_seed(100 + i); lb, rb = tb.train_step(ro, rd, tgt, noise=nz, next_rays=(nro, nrd, nnz))
+        n = int(ra["rm_samples"])
+        assert n == int(rb["rm_samples"]) and torch.equal(ra["rays_a"], rb["rays_a"]), i
+        assert torch.equal(ra["ts_buf"][:n], rb["ts_buf"][:n])
+        assert abs(float(la) - float(lb)) <= 1e-3 * abs(float(la)), (i, float(la), float(lb))
+    assert torch.equal(model_a.density_bitfield, model_b.density_bitfield)
+
+
 def test_nerf_loss_kernel_vs_autograd():
     from ar_nerf_b200 import _lib
     from ar_nerf_b200.losses import NeRFLoss
@@ -664,5 +687,16 @@ def test_density_grid_update_bits(w1):
     want = np.zeros(model.density_bitfield.numel(), np.uint8)
     oracle.packbits(dg, thr, want)
     assert np.array_equal(N(model.density_bitfield), want)
+    # steady-state cell selection (networks.py:181-207): half uniform, half drawn from the occupied cells -- on the device
+    from ar_nerf_b200 import vren as v
+    M = 128 ** 3 // 4
+    idx, coords = model.sample_uniform_and_occupied_cells(M, 5.912)[0]
+    occ = model.density_grid[0] > 5.912
+    assert idx.shape == (2 * M,) and coords.shape == (2 * M, 3)
+    assert bool(occ[idx[M:]].all()), "second half must be occupied cells"
+    assert torch.equal(v.morton3D(coords).long(), idx)
+    n_occ = int(occ.sum())
+    hit = torch.zeros_like(occ); hit[idx[M:]] = True
+    assert int(hit.sum()) > 0.9 * min(n_occ, M * (1 - np.exp(-1.0)))  # spread over the occupied set, not a few cells
     model.update_density_grid(5.912, warmup=False)
     assert model.density_grid.shape == (1, 128 ** 3)
