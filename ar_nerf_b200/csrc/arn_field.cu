@@ -23,39 +23,65 @@ __global__ void __launch_bounds__(256) cast_f32_f16_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ hash grid
-// Forward, one thread per (sample, level) -- SURVEY Appendix A.3.
+// Forward -- SURVEY Appendix A.3.  One thread per (sample, group of 8 levels): the normalised position is computed once,
+// each level keeps its eight gathers in flight, and the thread owns 32 contiguous bytes of the feature row (two 16-byte
+// chunks, one full sector) instead of scattering one 4-byte half2 per thread into a sector of its own.  Consecutive
+// lanes are consecutive samples of a ray, so at the coarse levels a warp's gathers fall into a few cache lines.
 __global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                              const __grid_constant__ LevelTable tbl,
                                                              const __half2* __restrict__ table, __half2* __restrict__ feat, int img) {
     if (n_dev) n = min(n, (int64_t)*n_dev);
-    const int l = blockIdx.y;
+    const int grp = blockIdx.y;  // levels [8*grp, 8*grp + 8)
     // tile image: the rows that pad the last 128-row tile are written as zeros (the MLP kernels move whole tiles, and the
     // backward multiplies them by zero gradients: they must be finite)
     const int64_t n_rows = img ? ((n + 127) & ~(int64_t)127) : n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t col = img ? ((img_chunk64(i, (uint32_t)l >> 2) << 2) | ((uint32_t)l & 3u)) : (uint32_t)l;
-    if (i >= n) { feat[i * ARN_N_LEVELS + col] = __floats2half2_rn(0.0f, 0.0f); continue; }
-    float w[3]; uint32_t g[3];
-    level_position(xyzs + 3 * i, box, tbl.scale[l], w, g);
-    uint32_t idx[8]; float wt[8];
-    corner_indices(tbl.mode[l], tbl.size[l], tbl.res[l], g, idx);
-    corner_weights(w, wt);
-    const __half2* lvl = table + tbl.offset[l];
-    __half2 tv[8];
+        uint32_t out[8];
+        if (i < n) {
+            float x01[3];
 #pragma unroll
-    for (int c = 0; c < 8; c++) tv[c] = lvl[idx[c]];  // eight independent gathers in flight
-    float acc0 = 0.0f, acc1 = 0.0f;
+            for (int d = 0; d < 3; d++) {
+                const float num = __fsub_rn(xyzs[3 * i + d], box.mn[d]);
+                x01[d] = box.inv[d] != 0.0f ? __fmul_rn(num, box.inv[d]) : __fdiv_rn(num, __fsub_rn(box.mx[d], box.mn[d]));
+            }
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const float2 v = __half22float2(tv[c]);
-        acc0 = __fmaf_rn(wt[c], v.x, acc0); acc1 = __fmaf_rn(wt[c], v.y, acc1);
-    }
-    // a 64-byte feature row = 4 chunks of 4 levels; tile image: chunk permuted (arn_field.cuh)
-    feat[i * ARN_N_LEVELS + col] = __floats2half2_rn(acc0, acc1);
+            for (int k = 0; k < 8; k++) {
+                const int l = 8 * grp + k;
+                float w[3]; uint32_t g[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const float pos = __fmaf_rn(tbl.scale[l], x01[d], 0.5f);
+                    const float fl = floorf(pos);
+                    w[d] = __fsub_rn(pos, fl); g[d] = (uint32_t)(int32_t)fl;
+                }
+                uint32_t idx[8]; float wt[8];
+                corner_indices(tbl.mode[l], tbl.size[l], tbl.res[l], g, idx);
+                corner_weights(w, wt);
+                const __half2* lvl = table + tbl.offset[l];
+                __half2 tv[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) tv[c] = lvl[idx[c]];  // eight independent gathers in flight
+                float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float2 v = __half22float2(tv[c]);
+                    acc0 = __fmaf_rn(wt[c], v.x, acc0); acc1 = __fmaf_rn(wt[c], v.y, acc1);
+                }
+                const __half2 r = __floats2half2_rn(acc0, acc1);
+                out[k] = *reinterpret_cast<const uint32_t*>(&r);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) out[k] = 0u;
+        }
+        // a 64-byte feature row = 4 chunks of 4 levels; this thread owns chunks 2*grp and 2*grp+1 (tile image: permuted)
+        uint4* row = reinterpret_cast<uint4*>(feat + i * ARN_N_LEVELS);
+        const uint32_t c0 = 2 * grp, c1 = 2 * grp + 1;
+        row[img ? img_chunk64(i, c0) : c0] = make_uint4(out[0], out[1], out[2], out[3]);
+        row[img ? img_chunk64(i, c1) : c1] = make_uint4(out[4], out[5], out[6], out[7]);
     }
 }
 
-// Backward into the table, one thread per (sample, level): vector red.global.add.v2.f32 per corner.
 // dfeat row = 128 bytes = 8 chunks of 2 levels (float2 each); tile image: chunk permuted (arn_field.cuh)
 __device__ __forceinline__ uint32_t dfeat_col(int img, int64_t i, int l) {
     return img ? ((img_chunk128(i, (uint32_t)l >> 1) << 1) | ((uint32_t)l & 1u)) : (uint32_t)l;
@@ -125,6 +151,7 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
     const int64_t n_seg = (n + SEG - 1) / SEG;
     const uint32_t size = tbl.size[l], res = tbl.res[l], mode = tbl.mode[l];
     float2* lvl = table_grad + tbl.offset[l];
+    const bool pair_ok = (reinterpret_cast<uintptr_t>(lvl) & 15) == 0;  // 16-byte reductions need the level base aligned
     const float scale = tbl.scale[l];
     const bool active = l >= level0 && l < level0 + nlevels;
     for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; seg < n_seg; seg += ((int64_t)gridDim.x * blockDim.x) >> 4) {
@@ -135,11 +162,24 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
 #pragma unroll
         for (int c = 0; c < 8; c++) acc[c] = make_float2(0.f, 0.f);
         bool dirty = false;
+        // The two x-corners of a cell are neighbouring table entries whenever they form an aligned pair (hashed level: x even,
+        // since the hash is x ^ f(y,z); dense level: even linear index): one 16-byte reduction then replaces two 8-byte
+        // ones -- the kernel is bound by the number of reduction sectors the L2 can retire.
         auto flush = [&]() {
             uint32_t idx[8];
             corner_indices(mode, size, res, cg, idx);
 #pragma unroll
-            for (int c = 0; c < 8; c++) { atomicAdd(lvl + idx[c], acc[c]); acc[c] = make_float2(0.f, 0.f); }
+            for (int q = 0; q < 4; q++) {
+                const uint32_t i0 = idx[2 * q], i1 = idx[2 * q + 1];
+                if (pair_ok && (i0 ^ i1) == 1u) {
+                    const bool lo0 = (i0 & 1u) == 0u;
+                    const float2 a = lo0 ? acc[2 * q] : acc[2 * q + 1], b = lo0 ? acc[2 * q + 1] : acc[2 * q];
+                    atomicAdd(reinterpret_cast<float4*>(lvl + (i0 & ~1u)), make_float4(a.x, a.y, b.x, b.y));
+                } else {
+                    atomicAdd(lvl + i0, acc[2 * q]); atomicAdd(lvl + i1, acc[2 * q + 1]);
+                }
+                acc[2 * q] = make_float2(0.f, 0.f); acc[2 * q + 1] = make_float2(0.f, 0.f);
+            }
         };
         for (int64_t i = i0; i < i1; i++) {
             const float2 d = dfeat[i * ARN_N_LEVELS + dfeat_col(img, i, l)];
@@ -604,7 +644,8 @@ int arn::hash_encode_fw_impl(const float* xyzs, int64_t n, const int32_t* n_dev,
     LevelTable t; Aabb b;
     if (int e = make_levels(levels, t)) return e;
     if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
-    dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS);
+    ARN_REQUIRE(((uintptr_t)feat_f16 & 15) == 0, "feat must be 16-byte aligned");
+    dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS / 8);
     ARN_LAUNCH("hash_encode_fw_kernel", (cudaStream_t)stream, hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, n_dev, b, t, (const __half2*)table_f16, (__half2*)feat_f16, tile_image));
     return check_launch("hash_encode_fw");
 }
