@@ -82,6 +82,7 @@ SIGNATURES = {
     "arn_hash_encode_bw_dyn": [P, L, P, P, P, Levels, P, P, P, P, P],
     "arn_march_train_emit_dyn": [P, P, L, I, I, F, F, I, P, P, P, P, P, P, P, L, P],
     "arn_nerf_loss": [P, P, P, P, L, P, F, F, F, F, P, P, P, P, P, P],
+    "arn_composite_train_fw_loss": [P, P, P, P, P, L, L, F, P, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, P],
     "arn_train_fwbw": [C.POINTER(TrainCfg), P],
     "arn_train_march": [C.POINTER(TrainCfg), P],
     "arn_train_fwbw_marched": [C.POINTER(TrainCfg), P],

@@ -25,11 +25,15 @@ int make_levels(const arn_levels_t& lv, LevelTable& t);
 int make_box(const float* mn, const float* mx, Aabb& b);
 // Hash-grid encode / backward with the layout of feat / dfeat selectable: tile_image = 0 is the plain row-major layout of
 // the public entry points, 1 the chunk-permuted activation image the MLP kernels bulk-copy (img_chunk64/128 below).
+// Optional riders: pack_* != NULL makes the first blocks of the forward build the MLP weight image (arn_tc.cuh);
+// red.wpart != NULL makes extra blocks of the run-aggregating backward sum the MLP weight-gradient slabs.
+struct WgradReduce { const float* wpart; int n_slabs; int with_rgb; float* dWd; float* dWc; };
 int hash_encode_fw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
-                        arn_levels_t levels, const void* table_f16, void* feat_f16, int tile_image, arn_stream_t stream);
+                        arn_levels_t levels, const void* table_f16, void* feat_f16, int tile_image, arn_stream_t stream,
+                        const __half* pack_wd = nullptr, const __half* pack_wc = nullptr, uint8_t* pack_img = nullptr);
 int hash_encode_bw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
                         arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad, float* dL_dxyzs,
-                        int tile_image, arn_stream_t stream);
+                        int tile_image, arn_stream_t stream, WgradReduce red = WgradReduce{nullptr, 0, 0, nullptr, nullptr});
 // arn_field_bw_tc_dyn with the option of reusing the weight image already in ws.wimg (arn_mlp_tc.cu)
 int field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
                      arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,

@@ -24,21 +24,10 @@ namespace arn {
 
 using namespace tc;
 
-// fp16 params (row-major [out][in] per layer, tcnn order) -> swizzled operand image (arn_tc.cuh)
+// fp16 params -> swizzled operand image (arn_tc.cuh), stand-alone launch (the fused paths pack inside the hash-grid forward)
 __global__ void __launch_bounds__(256) pack_mlp_weights_kernel(const __half* __restrict__ Wd, const __half* __restrict__ Wc,
                                                                uint8_t* __restrict__ img) {
-    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 halves) per thread
-    // chunk ranges per layer: D1 256, D2 128, C1 256, C2 512, C3 128  -> 1280 chunks
-    const __half* src; uint32_t dst;
-    if (chunk < 256) { const int r = chunk >> 2, c = chunk & 3; src = Wd + r * 32 + c * 8; dst = kWimgD1 + swz<64>(r, c); }
-    else if (chunk < 384) { const int q = chunk - 256, r = q >> 3, c = q & 7; src = Wd + 2048 + r * 64 + c * 8; dst = kWimgD2 + swz<128>(r, c); }
-    else if (chunk < 640) { const int q = chunk - 384, r = q >> 2, c = q & 3; src = Wc ? Wc + r * 32 + c * 8 : nullptr; dst = kWimgC1 + swz<64>(r, c); }
-    else if (chunk < 1152) { const int q = chunk - 640, r = q >> 3, c = q & 7; src = Wc ? Wc + 2048 + r * 64 + c * 8 : nullptr; dst = kWimgC2 + swz<128>(r, c); }
-    else if (chunk < 1280) { const int q = chunk - 1152, r = q >> 3, c = q & 7; src = Wc ? Wc + 6144 + r * 64 + c * 8 : nullptr; dst = kWimgC3 + swz<128>(r, c); }
-    else return;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (src) v = *reinterpret_cast<const uint4*>(src);
-    *reinterpret_cast<uint4*>(img + dst) = v;
+    pack_weight_chunk(blockIdx.x * blockDim.x + threadIdx.x, Wd, Wc, img);
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -254,9 +243,9 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
     if (with_rgb) ARN_REQUIRE(params_rgb_f16 && rgbs && (!ws.hid || (ws.in32 && ws.hid1 && ws.hid2)), "null pointer (colour branch)");
     cudaStream_t st = (cudaStream_t)stream;
     const __half* pxyz = (const __half*)params_xyz_f16;
-    if (int e = hash_encode_fw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, /*tile_image=*/1, stream)) return e;
-    ARN_LAUNCH("pack_mlp_weights_kernel", st, pack_mlp_weights_kernel<<<5, 256, 0, st>>>(pxyz, (const __half*)params_rgb_f16, (uint8_t*)ws.wimg));
-    if (int e = check_launch("pack_mlp_weights")) return e;
+    // the weight image is packed by the first blocks of the hash-grid forward (no launch of its own)
+    if (int e = hash_encode_fw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, /*tile_image=*/1, stream,
+                                    pxyz, (const __half*)params_rgb_f16, (uint8_t*)ws.wimg)) return e;
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0; ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -287,7 +276,6 @@ using namespace tc;
 // TMEM map: [0,64) R | [64,80) dWc3^T | [80,144) dWc2 | [144,176) dWc1 | [176,192) dWd2^T | [192,224) dWd1   (256 allocated)
 constexpr int kBwGa = kWimgBytes, kBwGb = kBwGa + kFwSmemTile64, kBwX0 = kBwGb + kFwSmemTile64;
 constexpr int kBwSmemBytes = kBwX0 + 3 * kFwSmemTile64 + 1024;
-constexpr int kWgradFloats = 7168 + 3072;  // one slab of per-CTA weight gradients
 constexpr int kMaxBwCtas = ARN_FIELD_SCRATCH_SLABS;
 constexpr uint32_t kColR = 0, kColC3 = 64, kColC2 = 80, kColC1 = 144, kColD2 = 176, kColD1 = 192;
 
@@ -536,25 +524,11 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-// grad += sum over the CTAs' slabs in a fixed order (deterministic).  A block owns 32 consecutive weights: warp w adds
-// the slabs k = w, w+8, ... (128-byte coalesced rows), the eight partial sums are combined in warp order.
+// grad += sum over the CTAs' slabs (arn_tc.cuh wgrad_reduce_block), stand-alone launch
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ wpart, int n_slabs, int with_rgb,
                                                            float* __restrict__ dWd, float* __restrict__ dWc) {
     __shared__ float part[8][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int e = blockIdx.x * 32 + lane;
-    float s0 = 0.f, s1 = 0.f;
-    int k = w;
-    for (; k + 8 < n_slabs; k += 16) { s0 += wpart[(size_t)k * kWgradFloats + e]; s1 += wpart[(size_t)(k + 8) * kWgradFloats + e]; }
-    if (k < n_slabs) s0 += wpart[(size_t)k * kWgradFloats + e];
-    part[w][lane] = s0 + s1;
-    __syncthreads();
-    if (w == 0) {
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; j++) sum += part[j][lane];
-        if (e < 7168) { if (with_rgb) dWc[e] += sum; } else dWd[e - 7168] += sum;
-    }
+    wgrad_reduce_block(blockIdx.x, wpart, n_slabs, with_rgb, dWd, dWc, part);
 }
 
 }  // namespace arn
@@ -605,8 +579,13 @@ int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, co
         (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, expf(15.0f),
         dfeat_scratch, wpart));
     if (int e = check_launch("field_mlp_bw_tc")) return e;
-    ARN_LAUNCH("wgrad_reduce_kernel", st, arn::wgrad_reduce_kernel<<<arn::kWgradFloats / 32, 256, 0, st>>>(wpart, grid, with_rgb ? 1 : 0, grad_params_xyz, grad_params_rgb));
-    if (int e = check_launch("wgrad_reduce")) return e;
+    // the slab sum rides in extra blocks of the hash-grid backward (run-aggregating form); otherwise it is launched here
+    WgradReduce red{wpart, grid, with_rgb ? 1 : 0, grad_params_xyz, grad_params_rgb};
+    if (!tunable(kTunHashBwMode)) {
+        ARN_LAUNCH("wgrad_reduce_kernel", st, arn::wgrad_reduce_kernel<<<arn::kWgradFloats / 32, 256, 0, st>>>(red.wpart, red.n_slabs, red.with_rgb, red.dWd, red.dWc));
+        if (int e = check_launch("wgrad_reduce")) return e;
+        red.wpart = nullptr;
+    }
     return hash_encode_bw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
-                               grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, /*tile_image=*/1, stream);
+                               grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, /*tile_image=*/1, stream, red);
 }

@@ -117,5 +117,44 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 //   [6144)   colour  W1 [64][32]  RB 64     4096 B        [10240)  colour  W2 [64][64]  RB 128   8192 B
 //   [18432)  colour  W3 [16][64]  RB 128    2048 B        total 20480 B
 constexpr int kWimgD1 = 0, kWimgD2 = 4096, kWimgC1 = 6144, kWimgC2 = 10240, kWimgC3 = 18432, kWimgBytes = 20480;
+constexpr int kWimgChunks = 1280;  // 16-byte chunks of the image
+
+// fp16 params (row-major [out][in] per layer, tcnn order) -> swizzled operand image: one 16-byte chunk (8 halves)
+__device__ __forceinline__ void pack_weight_chunk(int chunk, const __half* __restrict__ Wd, const __half* __restrict__ Wc, uint8_t* __restrict__ img) {
+    using tc::swz;
+    // chunk ranges per layer: D1 256, D2 128, C1 256, C2 512, C3 128  -> 1280 chunks
+    const __half* src; uint32_t dst;
+    if (chunk < 256) { const int r = chunk >> 2, c = chunk & 3; src = Wd + r * 32 + c * 8; dst = kWimgD1 + swz<64>(r, c); }
+    else if (chunk < 384) { const int q = chunk - 256, r = q >> 3, c = q & 7; src = Wd + 2048 + r * 64 + c * 8; dst = kWimgD2 + swz<128>(r, c); }
+    else if (chunk < 640) { const int q = chunk - 384, r = q >> 2, c = q & 3; src = Wc ? Wc + r * 32 + c * 8 : nullptr; dst = kWimgC1 + swz<64>(r, c); }
+    else if (chunk < 1152) { const int q = chunk - 640, r = q >> 3, c = q & 7; src = Wc ? Wc + 2048 + r * 64 + c * 8 : nullptr; dst = kWimgC2 + swz<128>(r, c); }
+    else if (chunk < 1280) { const int q = chunk - 1152, r = q >> 3, c = q & 7; src = Wc ? Wc + 6144 + r * 64 + c * 8 : nullptr; dst = kWimgC3 + swz<128>(r, c); }
+    else return;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (src) v = *reinterpret_cast<const uint4*>(src);
+    *reinterpret_cast<uint4*>(img + dst) = v;
+}
+
+// Sum of the backward CTAs' weight-gradient slabs into the gradient buffers, fixed order (deterministic).  A block of 256
+// threads owns 32 consecutive weights: warp w adds the slabs k = w, w+8, ... (128-byte coalesced rows), the eight partial
+// sums are combined in warp order.  `part` is an 8 x 32 shared-memory scratch.
+constexpr int kWgradFloats = 7168 + 3072;  // one slab: colour 7168 | density 3072
+__device__ __forceinline__ void wgrad_reduce_block(int block, const float* __restrict__ wpart, int n_slabs, int with_rgb,
+                                                   float* __restrict__ dWd, float* __restrict__ dWc, float (*part)[32]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int e = block * 32 + lane;
+    float s0 = 0.f, s1 = 0.f;
+    int k = w;
+    for (; k + 8 < n_slabs; k += 16) { s0 += wpart[(size_t)k * kWgradFloats + e]; s1 += wpart[(size_t)(k + 8) * kWgradFloats + e]; }
+    if (k < n_slabs) s0 += wpart[(size_t)k * kWgradFloats + e];
+    part[w][lane] = s0 + s1;
+    __syncthreads();
+    if (w == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) sum += part[j][lane];
+        if (e < 7168) { if (with_rgb) dWc[e] += sum; } else dWd[e - 7168] += sum;
+    }
+}
 
 }  // namespace arn

@@ -503,16 +503,58 @@ __device__ __forceinline__ float warp_incl_prod(float v, int lane) {
     return v;
 }
 
+// NeRFLoss ('raw', losses.py:63-82) + background blend (rendering.py:287-296) as the per-ray epilogue of the compositing
+// kernel: the values are in lane 0's registers when the ray is done, so the separate loss kernel and its re-read of the
+// per-ray outputs disappear from the fused training step.  Same arithmetic as nerf_loss_kernel (arn_train.cu).
+struct LossEpilogue {
+    const float* target; float bg[3]; float lambda_opacity, lambda_depth, grid_scale, grad_scale;
+    float* rgb_out; float* dL_drgb; float* dL_dopacity; float* dL_ddepth; float* loss_out;
+};
+__device__ __forceinline__ float ray_loss(const LossEpilogue& L, int64_t r, int64_t n_rays, const float c[3], float o, float dep) {
+    const float inv_r = 1.0f / (float)n_rays, inv_3r = inv_r / 3.0f;
+    float loss = 0.0f, g_op = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float est = c[k] + L.bg[k] * (1.0f - o);
+        if (L.rgb_out) L.rgb_out[3 * r + k] = est;
+        const float den = est + 1e-3f;
+        const float e = (est - L.target[3 * r + k]) / den;
+        loss += e * e * inv_3r;
+        const float g = 2.0f * e / den * inv_3r * L.grad_scale;
+        L.dL_drgb[3 * r + k] = g;
+        g_op -= L.bg[k] * g;
+    }
+    const float oe = o + 1e-10f;
+    loss += L.lambda_opacity * (-oe * logf(oe)) * inv_r;
+    g_op += L.lambda_opacity * (-logf(oe) - 1.0f) * inv_r * L.grad_scale;
+    L.dL_dopacity[r] = g_op;
+    float g_d = 0.0f;
+    if (L.lambda_depth != 0.0f) {
+        const float v = dep / L.grid_scale + 1e-10f;
+        loss += -L.lambda_depth * logf(fminf(v, 1.0f)) * inv_r;
+        if (v < 1.0f) g_d = -L.lambda_depth / v / L.grid_scale * inv_r * L.grad_scale;
+    }
+    L.dL_ddepth[r] = g_d;
+    return loss;
+}
+
 // volumerendering.cu:5-44, one warp per rays_a row.
+template <bool LOSS>
 __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                                  const float* __restrict__ deltas, const float* __restrict__ ts,
                                                                  const int64_t* __restrict__ rays_a, int64_t n_rays, float T_thr,
                                                                  int64_t* __restrict__ total_samples, float* __restrict__ opacity,
-                                                                 float* __restrict__ depth, float* __restrict__ rgb, float* __restrict__ ws) {
+                                                                 float* __restrict__ depth, float* __restrict__ rgb, float* __restrict__ ws,
+                                                                 const LossEpilogue L) {
+    __shared__ float s_loss[8];
+    if (LOSS && threadIdx.x < 8) s_loss[threadIdx.x] = 0.0f;
+    if (LOSS) __syncthreads();
     const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (n >= n_rays) return;
-    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1]; const int N = (int)rays_a[3 * n + 2];
+    const bool live = n < n_rays;
+    if (!LOSS && !live) return;
+    int64_t ray_idx = 0, start = 0; int N = 0;
+    if (live) { ray_idx = rays_a[3 * n]; start = rays_a[3 * n + 1]; N = (int)rays_a[3 * n + 2]; }
     float T = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
     int64_t samples = N; bool done = false;
     int base = 0;
@@ -541,10 +583,23 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
         T = __shfl_sync(kFull, T_after, 31);
     }
     for (int i = base + lane; i < N; i += 32) ws[start + i] = 0.0f;  // after termination (reference: zero-init, :59)
-    if (lane == 0) {
+    if (lane == 0 && live) {
         opacity[ray_idx] = acc_o; depth[ray_idx] = acc_d;
         rgb[3 * ray_idx] = acc_r; rgb[3 * ray_idx + 1] = acc_g; rgb[3 * ray_idx + 2] = acc_b;
         total_samples[ray_idx] = samples;
+        if (LOSS) {
+            const float c[3] = {acc_r, acc_g, acc_b};
+            s_loss[threadIdx.x >> 5] = ray_loss(L, ray_idx, n_rays, c, acc_o, acc_d);
+        }
+    }
+    if (LOSS) {  // one atomic per CTA (8 rays)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float v = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v += s_loss[k];
+            atomicAdd(L.loss_out, v);
+        }
     }
 }
 
@@ -928,9 +983,28 @@ extern "C" ARN_API int arn_composite_train_fw(const float* sigmas, const float* 
     if (n_rays == 0) return ARN_OK;
     ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "null pointer");
     ARN_REQUIRE(n_samples == 0 || (sigmas && rgbs && deltas && ts && ws), "null pointer");
-    ARN_LAUNCH("composite_train_fw_kernel", (cudaStream_t)stream, composite_train_fw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
-                                                                                          total_samples, opacity, depth, rgb, ws));
+    ARN_LAUNCH("composite_train_fw_kernel", (cudaStream_t)stream, composite_train_fw_kernel<false><<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
+                                                                                          total_samples, opacity, depth, rgb, ws, LossEpilogue{}));
     return check_launch("composite_train_fw");
+}
+
+// Compositing + NeRFLoss in one launch (the fused training step); rays_a must be in canonical ray order (ray_idx == row).
+extern "C" ARN_API int arn_composite_train_fw_loss(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                                                   const int64_t* rays_a, int64_t n_rays, int64_t n_samples, float T_threshold,
+                                                   int64_t* total_samples, float* opacity, float* depth, float* rgb, float* ws,
+                                                   const float* target, const float* bg_host, float lambda_opacity, float lambda_depth,
+                                                   float grid_scale, float grad_scale, float* rgb_out, float* dL_drgb, float* dL_dopacity,
+                                                   float* dL_ddepth, float* loss_out, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays > 0 && n_samples >= 0, "bad size");
+    ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb && sigmas && rgbs && deltas && ts && ws, "null pointer");
+    ARN_REQUIRE(target && bg_host && dL_drgb && dL_dopacity && dL_ddepth && loss_out, "null pointer (loss)");
+    cudaStream_t st = (cudaStream_t)stream;
+    ARN_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    LossEpilogue L{target, {bg_host[0], bg_host[1], bg_host[2]}, lambda_opacity, lambda_depth, grid_scale, grad_scale, rgb_out, dL_drgb, dL_dopacity,
+                   dL_ddepth, loss_out};
+    ARN_LAUNCH("composite_train_fw_loss_kernel", st, composite_train_fw_kernel<true><<<ceil_div(n_rays * 32, 256), 256, 0, st>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
+                                                                                          total_samples, opacity, depth, rgb, ws, L));
+    return check_launch("composite_train_fw_loss");
 }
 
 extern "C" ARN_API int arn_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drgb, const float* dL_dws,

@@ -294,6 +294,14 @@ int arn_train_fwbw(const arn_train_t* cfg_host, arn_stream_t stream);
  * while batch k is in its field / optimizer kernels (ar_nerf_b200/trainer.py: next_rays=). */
 int arn_train_march(const arn_train_t* cfg_host, arn_stream_t stream);
 int arn_train_fwbw_marched(const arn_train_t* cfg_host, arn_stream_t stream);
+/* Compositing forward with the NeRFLoss epilogue of the fused step (one launch instead of two; rays_a in canonical ray
+ * order).  Same outputs as arn_composite_train_fw followed by arn_nerf_loss. */
+int arn_composite_train_fw_loss(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                                const int64_t* rays_a, int64_t n_rays, int64_t n_samples, float T_threshold,
+                                int64_t* total_samples, float* opacity, float* depth, float* rgb, float* ws,
+                                const float* target, const float* bg_host, float lambda_opacity, float lambda_depth,
+                                float grid_scale, float grad_scale, float* rgb_out, float* dL_drgb, float* dL_dopacity,
+                                float* dL_ddepth, float* loss_out, arn_stream_t stream);
 /* The loss kernel on its own (per-ray rgb/opacity/depth -> scalar loss + gradients; bg_host = 3 floats). */
 int arn_nerf_loss(const float* rgb, const float* opacity, const float* depth, const float* target, int64_t n_rays,
                   const float* bg_host, float lambda_opacity, float lambda_depth, float grid_scale, float grad_scale,
