@@ -88,14 +88,20 @@ class _F16Cache:
     every forward; the fused Adam of trainer.py refreshes the copy itself and calls mark_fresh())."""
 
     def __init__(self):
-        self.buf = None
+        self.buf = None      # capacity >= numel (the sharded optimizer pads it to a whole number of shards)
+        self.key = None
+        self.capacity = 0
+
+    def reserve(self, p, capacity):
+        """(Re)allocate with room for `capacity` elements; the copy is re-cast on the next get()."""
+        self.capacity = max(int(capacity), p.numel())
+        self.buf = torch.empty(self.capacity, dtype=torch.float16, device=p.device)
         self.key = None
 
     def get(self, p):
         key = (p.data_ptr(), p._version, p.device)
-        if self.buf is None or self.buf.numel() != p.numel() or self.buf.device != p.device:
-            self.buf = torch.empty(p.numel(), dtype=torch.float16, device=p.device)
-            self.key = None
+        if self.buf is None or self.buf.numel() < p.numel() or self.buf.device != p.device:
+            self.reserve(p, max(self.capacity, p.numel()))
         if key != self.key:
             src = p.detach()
             call("arn_cast_f32_to_f16", ptr(src), ptr(self.buf), src.numel(), stream())

@@ -37,3 +37,46 @@ def gather_frame(local, n_total, rank, world, dst=0):
     if rank != dst:
         return None
     return torch.cat([b[:hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sharded optimizer state (ZeRO-1 style) for the one large parameter, the hash table: instead of all-reducing the 45.8 MB
+# fp32 gradient and running the same 11.4 M-element Adam on every rank, the gradient is reduce-scattered, every rank
+# updates ITS contiguous slice (fp32 master, moments, fp16 working copy) and the fp16 slices are all-gathered.
+# Traffic per rank: (N-1)/N * (4 + 2) bytes per parameter instead of (N-1)/N * 8; Adam's HBM traffic drops by N.
+def shard_size(n, world, align=8):
+    """Elements per rank: ceil(n / world) rounded up to `align` (16-byte vector access of the fp16 copy / fp32 state)."""
+    per = (n + world - 1) // world
+    return (per + align - 1) // align * align
+
+
+def padded_numel(n, world, align=8):
+    return shard_size(n, world, align) * world
+
+
+def reduce_scatter_sum(full, out, rank, world):
+    """out (S) <- sum over ranks of full[rank*S:(rank+1)*S]; full has world*S elements."""
+    if world == 1:
+        out.copy_(full[:out.numel()])
+        return
+    if dist.get_backend() == "nccl":
+        dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM)
+    else:  # gloo has no reduce-scatter: same result through an all-reduce (CPU tests)
+        tmp = full.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
+        out.copy_(tmp[rank * out.numel():(rank + 1) * out.numel()])
+
+
+def all_gather_shards(full, rank, world):
+    """In place: every rank contributes full[rank*S:(rank+1)*S]; afterwards `full` is identical on all ranks."""
+    if world == 1:
+        return
+    S = full.numel() // world
+    mine = full[rank * S:(rank + 1) * S]
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(full, mine)
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.clone())
+        for r, part in enumerate(parts):
+            full[r * S:(r + 1) * S].copy_(part)

@@ -5,7 +5,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ar_nerf_b200.sharding import allreduce_grads, gather_frame, shard_bounds, shard_rays
+from ar_nerf_b200.sharding import (all_gather_shards, allreduce_grads, gather_frame, padded_numel, reduce_scatter_sum, shard_bounds,
+                                   shard_rays, shard_size)
 
 
 def test_shard_bounds_cover_exactly():
@@ -29,6 +30,18 @@ def _worker(rank, world, port):
     grad = [o.sum(0).clone(), d.sum(0).clone()]
     allreduce_grads(grad, world)
     assert torch.allclose(grad[0], rays_o.sum(0), atol=1e-4) and torch.allclose(grad[1], rays_d.sum(0), atol=1e-4)
+    # sharded optimizer plumbing: reduce-scatter of a padded gradient, a slice-local update, all-gather of the slices
+    n = 1003
+    S, P = shard_size(n, world), padded_numel(n, world)
+    assert S % 8 == 0 and P == S * world and P >= n
+    gfull = torch.zeros(P); gfull[:n] = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    gs = torch.empty(S)
+    reduce_scatter_sum(gfull, gs, rank, world)
+    want = torch.zeros(P); want[:n] = torch.arange(n, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    assert torch.equal(gs, want[rank * S:(rank + 1) * S])
+    params = torch.zeros(P); params[rank * S:(rank + 1) * S] = -0.5 * gs   # each rank updates its slice only
+    all_gather_shards(params, rank, world)
+    assert torch.equal(params, -0.5 * want)
     frame = gather_frame(o * 2, 1001, rank, world)
     if rank == 0:
         assert torch.equal(frame, rays_o * 2)
