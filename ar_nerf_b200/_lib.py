@@ -42,6 +42,17 @@ class TrainCfg(C.Structure):
                 ("grad_xyz", P), ("grad_rgb", P), ("loss_out", P)]
 
 
+class TestIterCfg(C.Structure):
+    """Mirror of arn_test_iter_t (include/arnerf.h)."""
+    _fields_ = [("rays_o", P), ("rays_d", P), ("hits_t", P), ("alive", P), ("n_alive", L),
+                ("density_bitfield", P), ("cascades", I), ("grid_size", I), ("scale", F), ("exp_step_factor", F), ("n_samples", I), ("max_samples", I),
+                ("T_threshold", F),
+                ("xyz_min_host", P), ("xyz_max_host", P), ("levels", Levels), ("params_xyz_f16", P), ("params_rgb_f16", P), ("rgb_act", I),
+                ("capacity", L), ("deltas", P), ("ts", P), ("n_eff", P), ("rays_a", P), ("counts", P), ("counts_alive", P),
+                ("xyzs", P), ("dirs", P), ("sigmas", P), ("rgbs", P), ("ws", FieldWs),
+                ("opacity", P), ("depth", P), ("rgb", P), ("alive_out", P), ("total_samples", P)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/arnerf.h one to one
 SIGNATURES = {
     "arn_version": [],
@@ -84,6 +95,7 @@ SIGNATURES = {
     "arn_nerf_loss": [P, P, P, P, L, P, F, F, F, F, P, P, P, P, P, P],
     "arn_composite_train_fw_loss": [P, P, P, P, P, L, L, F, P, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, P],
     "arn_train_fwbw": [C.POINTER(TrainCfg), P],
+    "arn_render_test_iter": [C.POINTER(TestIterCfg), P],
     "arn_train_march": [C.POINTER(TrainCfg), P],
     "arn_train_fwbw_marched": [C.POINTER(TrainCfg), P],
     "arn_field_bw_simt": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],

@@ -482,6 +482,48 @@ __global__ void __launch_bounds__(128) march_test_kernel(const float* __restrict
     }
 }
 
+// Test-time render iteration, compact form (arn_render_test_iter): the march records only t / dt per (alive ray, slot)
+// and the per-ray count; a scan lays the valid samples out contiguously, and this kernel materialises their positions.
+__global__ void __launch_bounds__(128) march_test_lite_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                              float* __restrict__ hits_t, const int64_t* __restrict__ alive,
+                                                              int64_t n_alive, const uint8_t* __restrict__ bitfield, ArnMarchConsts c,
+                                                              int S, float* __restrict__ deltas, float* __restrict__ ts, int32_t* __restrict__ n_eff) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int64_t r = alive[n];
+    const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
+    float t = hits_t[2 * r]; const float t2 = hits_t[2 * r + 1];
+    int s = 0;
+    float t_resume = t; bool moved = false;
+    while (t < t2 && s < S) {
+        float x, y, z, dt;
+        if (arn_march_eval(c, ray, bitfield, t, x, y, z, dt)) {
+            const int64_t o = n * S + s;
+            ts[o] = t; deltas[o] = dt;
+            t = __fadd_rn(t, dt);
+            t_resume = t; moved = true;  // raymarching.cu:386: only an occupied step moves the resume point
+            s++;
+        }
+    }
+    if (moved) hits_t[2 * r] = t_resume;
+    n_eff[n] = s;
+}
+// one thread per (alive ray, slot): valid slots write their sample into the compact list at start[ray] + slot
+__global__ void __launch_bounds__(256) emit_test_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                        const int64_t* __restrict__ alive, int64_t n_alive, int S,
+                                                        const int64_t* __restrict__ rays_a, const float* __restrict__ ts,
+                                                        float* __restrict__ xyzs, float* __restrict__ dirs) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_alive * S) return;
+    const int64_t n = e / S; const int sl = (int)(e % S);
+    if (sl >= (int)rays_a[3 * n + 2]) return;
+    const int64_t r = alive[n], o = rays_a[3 * n + 1] + sl;
+    const float t = ts[e];
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    xyzs[3 * o] = __fmaf_rn(dx, t, rays_o[3 * r]); xyzs[3 * o + 1] = __fmaf_rn(dy, t, rays_o[3 * r + 1]); xyzs[3 * o + 2] = __fmaf_rn(dz, t, rays_o[3 * r + 2]);
+    dirs[3 * o] = dx; dirs[3 * o + 1] = dy; dirs[3 * o + 2] = dz;
+}
+
 // ---------------------------------------------------------------------------------------------- compositing
 // alpha = 1 - __expf(-sigma*delta): SASS of the reference is FMUL s*d ; FMUL -1.44269502 ; MUFU.EX2 (volumerendering.cu:27)
 __device__ __forceinline__ float alpha_of(float sigma, float delta) {
@@ -703,6 +745,53 @@ __global__ void __launch_bounds__(256) composite_test_fw_kernel(const float* __r
         if (T <= T_thr) { alive[n] = -1; break; }
     }
     opacity[r] = O; depth[r] = D; rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+}
+
+// composite_test_fw_kernel on the compact sample list: sigmas / rgbs at rays_a[n].start + s, deltas / ts in their padded
+// slots.  Also writes keep[n] = 1 if the ray stays alive (the input of the alive-list compaction) and adds the
+// effective samples of the iteration to *total (rendering.py:203).
+__global__ void __launch_bounds__(256) composite_test_compact_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                     const float* __restrict__ deltas, const float* __restrict__ ts,
+                                                                     const int64_t* __restrict__ alive, int64_t n_alive, int S, float T_thr,
+                                                                     const int64_t* __restrict__ rays_a, float* __restrict__ opacity,
+                                                                     float* __restrict__ depth, float* __restrict__ rgb, int32_t* __restrict__ keep,
+                                                                     unsigned long long* __restrict__ total) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int ne = 0; bool live = false;
+    if (n < n_alive) {
+        ne = (int)rays_a[3 * n + 2];
+        if (ne > 0) {
+            live = true;
+            const int64_t r = alive[n], c0 = rays_a[3 * n + 1];
+            float O = opacity[r];
+            float T = __fsub_rn(1.0f, O);
+            float cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2], D = depth[r];
+            for (int s = 0; s < ne; s++) {
+                const int64_t o = n * S + s, q = c0 + s;
+                const float a = alpha_of(sigmas[q], deltas[o]);
+                const float w = __fmul_rn(a, T);
+                cr = __fmaf_rn(w, rgbs[3 * q], cr); cg = __fmaf_rn(w, rgbs[3 * q + 1], cg); cb = __fmaf_rn(w, rgbs[3 * q + 2], cb);
+                D = __fmaf_rn(w, ts[o], D);
+                O = __fadd_rn(O, w);
+                T = __fmul_rn(T, __fsub_rn(1.0f, a));
+                if (T <= T_thr) { live = false; break; }
+            }
+            opacity[r] = O; depth[r] = D; rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+        }
+        keep[n] = live ? 1 : 0;
+    }
+    // effective samples of this iteration: warp sum, one atomic per warp
+    unsigned v = (unsigned)ne;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, (unsigned long long)v);
+}
+// alive_out[start[n]] = alive[n] for the rays that stay alive (order preserved: alive_indices[alive_indices >= 0])
+__global__ void __launch_bounds__(256) alive_scatter_kernel(const int64_t* __restrict__ alive, int64_t n_alive, const int64_t* __restrict__ rays_a,
+                                                            int64_t* __restrict__ alive_out) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    if (rays_a[3 * n + 2] > 0) alive_out[rays_a[3 * n + 1]] = alive[n];
 }
 
 // ---------------------------------------------------------------------------------------------- distortion loss
@@ -1059,4 +1148,41 @@ extern "C" ARN_API int arn_march_train_bw(const float* dL_dxyzs, const float* dL
     ARN_REQUIRE(dL_dxyzs && ts && rays_a && dL_drays_o && dL_drays_d, "null pointer");
     ARN_LAUNCH("march_train_bw_kernel", (cudaStream_t)stream, march_train_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dxyzs, dL_ddirs, ts, rays_a, n_rays, dL_drays_o, dL_drays_d));
     return check_launch("march_train_bw");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One iteration of the test-time render loop (rendering.py:189-236) in one host call, no host round trip inside:
+//   march the alive rays by <= S samples (t, dt, count) -> scan -> compact sample list -> field (inference, count on the
+//   device) -> front-to-back compositing with ray kill -> order-preserving compaction of the alive list.
+// The caller reads counts_out = (valid samples of this iteration, rays still alive) once per iteration to drive the
+// reference's schedule (N_samples = max(min(N_rays // N_alive, 64), min_samples)).
+extern "C" int arn_field_fw_tc_dyn(const float*, const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const void*,
+                                   int, arn_field_ws_t, float*, float*, arn_stream_t);
+extern "C" ARN_API int arn_render_test_iter(const arn_test_iter_t* c, arn_stream_t stream) {
+    ARN_REQUIRE(c, "null config");
+    ARN_REQUIRE(c->n_alive > 0 && c->n_samples >= 1 && c->capacity >= c->n_alive * c->n_samples, "bad sizes");
+    if (int e = check_march_cfg(c->cascades, c->grid_size, c->max_samples)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = c->n_alive; const int S = c->n_samples;
+    // raymarching.cu:370,399: the test kernel passes `cascades` where calc_dt expects `scale`
+    const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
+    ARN_LAUNCH("march_test_lite_kernel", st, march_test_lite_kernel<<<ceil_div(n, 128), 128, 0, st>>>(c->rays_o, c->rays_d, c->hits_t, c->alive, n, c->density_bitfield, mc, S,
+                                                                                                  c->deltas, c->ts, c->n_eff));
+    if (int e = check_launch("march_test_lite")) return e;
+    ARN_LAUNCH("rays_scan_compact_kernel", st, rays_scan_compact_kernel<<<ceil_div(n, 1024), 1024, 0, st>>>(c->n_eff, n, c->rays_a, c->counts));
+    if (int e = check_launch("rays_scan")) return e;
+    ARN_LAUNCH("emit_test_kernel", st, emit_test_kernel<<<ceil_div(n * S, 256), 256, 0, st>>>(c->rays_o, c->rays_d, c->alive, n, S, c->rays_a, c->ts, c->xyzs, c->dirs));
+    if (int e = check_launch("emit_test")) return e;
+    if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, c->capacity, c->counts, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
+                                    c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
+    ARN_LAUNCH("composite_test_compact_kernel", st, composite_test_compact_kernel<<<ceil_div(n, 256), 256, 0, st>>>(c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, n, S, c->T_threshold,
+                                                                                                               c->rays_a, c->opacity, c->depth, c->rgb, c->n_eff,
+                                                                                                               (unsigned long long*)c->total_samples));
+    if (int e = check_launch("composite_test_compact")) return e;
+    // n_eff now holds the keep flags; the scan reuses rays_a and leaves (rays kept, n) in counts_alive
+    ARN_LAUNCH("rays_scan_compact_kernel", st, rays_scan_compact_kernel<<<ceil_div(n, 1024), 1024, 0, st>>>(c->n_eff, n, c->rays_a, c->counts_alive));
+    if (int e = check_launch("rays_scan")) return e;
+    ARN_LAUNCH("alive_scatter_kernel", st, alive_scatter_kernel<<<ceil_div(n, 256), 256, 0, st>>>(c->alive, n, c->rays_a, c->alive_out));
+    return check_launch("alive_scatter");
 }

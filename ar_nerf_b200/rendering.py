@@ -82,6 +82,82 @@ def render(model, rays_o, rays_d, **kwargs):
     return results
 
 
+_TEST_WS = {}
+
+
+def _test_workspace(R, min_samples, device):
+    """Buffers of the fused test loop, kept per (rays, min_samples, device): every iteration marches at most
+    n_alive * N_samples <= R * min_samples samples (N_samples = max(min(R // n_alive, 64), min_samples))."""
+    key = (R, min_samples, device.type, device.index)
+    ws = _TEST_WS.get(key)
+    if ws is None:
+        from .field import tile_rows, _scratch
+        cap = R * min_samples
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+        ws = dict(cap=cap, deltas=f(cap), ts=f(cap), n_eff=torch.empty(R, dtype=torch.int32, device=device),
+                  rays_a=torch.empty(R, 3, dtype=torch.int64, device=device), counts=torch.zeros(4, dtype=torch.int32, device=device),
+                  xyzs=f(cap, 3), dirs=f(cap, 3), sigmas=f(cap), rgbs=f(cap, 3),
+                  feat=torch.empty(tile_rows(cap), 32, dtype=torch.float16, device=device), wimg=_scratch(device),
+                  alive=[torch.empty(R, dtype=torch.int64, device=device), torch.empty(R, dtype=torch.int64, device=device)],
+                  total=torch.zeros(1, dtype=torch.int64, device=device))
+        _TEST_WS.clear()  # one frame size at a time
+        _TEST_WS[key] = ws
+    return ws
+
+
+@torch.no_grad()
+def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
+    """The loop of rendering.py:162-236 with each iteration as ONE native call (arn_render_test_iter: march, compact sample
+    list, field, compositing + ray kill, alive-list compaction) and one host read per iteration -- the two counts that
+    drive the reference's schedule.  Same schedule, same per-ray arithmetic, same results."""
+    import ctypes as C
+    from . import _lib
+    from ._lib import FieldWs, TestIterCfg, call, ptr, stream
+    exp_step_factor = kwargs.get('exp_step_factor', 0.)
+    T_threshold = kwargs.get('T_threshold', 1e-4)
+    max_samples = kwargs.get('max_samples', MAX_SAMPLES)
+    N_rays, device = len(rays_o), rays_o.device
+    opacity = torch.zeros(N_rays, device=device)
+    depth = torch.zeros(N_rays, device=device)
+    rgb = torch.zeros(N_rays, 3, device=device)
+    min_samples = 1 if exp_step_factor == 0 else 4
+    w = _test_workspace(N_rays, min_samples, device)
+    st = model.field_state
+    model.host_box()
+    p16x = st.cache_xyz.get(model.xyz_encoder.params); p16c = st.cache_rgb.get(model.rgb_net.params)
+    hits_t2 = hits_t[:, 0]
+    if not hits_t2.is_contiguous():
+        raise RuntimeError("hits_t must be contiguous")
+    rays_o = rays_o.contiguous().float(); rays_d = rays_d.contiguous().float()
+    cur = 0
+    torch.arange(N_rays, out=w['alive'][0])
+    w['total'].zero_()
+    cast = lambda a: C.cast(a, C.c_void_p)
+    cfg = TestIterCfg(
+        ptr(rays_o), ptr(rays_d), ptr(hits_t2), None, 0,
+        ptr(model.density_bitfield), model.cascades, model.grid_size, float(model.scale), float(exp_step_factor), 1, MAX_SAMPLES,
+        float(T_threshold),
+        cast(st.mn), cast(st.mx), st.geometry.c_levels, ptr(p16x), ptr(p16c), st.rgb_act,
+        w['cap'], ptr(w['deltas']), ptr(w['ts']), ptr(w['n_eff']), ptr(w['rays_a']), w['counts'].data_ptr(), w['counts'].data_ptr() + 8,
+        ptr(w['xyzs']), ptr(w['dirs']), ptr(w['sigmas']), ptr(w['rgbs']),
+        FieldWs(ptr(w['feat']), None, None, None, None, None, ptr(w['wimg'])),
+        ptr(opacity), ptr(depth), ptr(rgb), None, ptr(w['total']))
+    samples, N_alive = 0, N_rays
+    s_ = stream()
+    while samples < max_samples and N_alive > 0:
+        N_samples = max(min(N_rays // N_alive, 64), min_samples)
+        samples += N_samples
+        cfg.alive, cfg.alive_out = w['alive'][cur].data_ptr(), w['alive'][cur ^ 1].data_ptr()
+        cfg.n_alive, cfg.n_samples = N_alive, N_samples
+        call("arn_render_test_iter", C.byref(cfg), s_)
+        n_valid, _, n_keep, _ = w['counts'].tolist()  # the one host read of the iteration
+        if n_valid == 0:
+            break  # rendering.py:206 (nothing was composited, nothing changed)
+        cur ^= 1
+        N_alive = n_keep
+    return opacity, depth, rgb, w['total'][0].clone()
+
+
 @torch.no_grad()
 def __render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     """rendering.py:162-253: iterative march / evaluate / composite with alive-ray compaction (schedule kept, Q10)."""
@@ -90,6 +166,11 @@ def __render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
 
     N_rays = len(rays_o)
     device = rays_o.device
+    fused = (getattr(model, 'field_impl', '') == '' and model.rgb_act == 'Sigmoid' and not model.use_raw_HDR
+             and 'val_batch_size' not in kwargs and not kwargs.get('eager_test_loop', False) and N_rays > 0)
+    if fused:
+        opacity, depth, rgb, total_samples = _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs)
+        return _finish_test(results, opacity, depth, rgb, total_samples, rays_d, **kwargs)
     opacity = torch.zeros(N_rays, device=device)
     depth = torch.zeros(N_rays, device=device)
     rgb = torch.zeros(N_rays, 3, device=device)
@@ -136,6 +217,12 @@ def __render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
                                N_eff_samples, opacity, depth, rgb)
         alive_indices = alive_indices[alive_indices >= 0]  # remove converged rays
 
+    return _finish_test(results, opacity, depth, rgb, total_samples, rays_d, **kwargs)
+
+
+def _finish_test(results, opacity, depth, rgb, total_samples, rays_d, **kwargs):
+    """rendering.py:238-253: result dict and background blend."""
+    device = rgb.device
     results['opacity'] = opacity
     results['depth'] = depth
     results['rgb'] = rgb

@@ -330,6 +330,27 @@ int arn_field_bw_tc_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, cons
                         arn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * One iteration of the test-time render loop (rendering.py:189-236: raymarching_test -> model -> composite_test_fw ->
+ * alive_indices[alive_indices >= 0]) in ONE host call with no host round trip inside.  Same schedule, same per-ray
+ * arithmetic as the reference's loop: the march is the bit-exact test march, samples are evaluated as a compact list
+ * (the reference's valid_mask indexing), compositing is composite_test_fw's loop, the alive list keeps its order.
+ * After the call the caller reads counts[0] (valid samples of this iteration; 0 -> the reference breaks) and
+ * counts_alive[0] (rays still alive) to drive N_samples of the next iteration.  hits_t (R,2), opacity/depth/rgb in place.
+ * capacity >= n_alive * n_samples bounds every per-sample buffer; ws.hid etc. may be NULL (inference). */
+typedef struct {
+    const float* rays_o; const float* rays_d; float* hits_t; const int64_t* alive; int64_t n_alive;
+    const uint8_t* density_bitfield; int cascades; int grid_size; float scale; float exp_step_factor; int n_samples; int max_samples;
+    float T_threshold;
+    const float* xyz_min_host; const float* xyz_max_host; arn_levels_t levels; const void* params_xyz_f16; const void* params_rgb_f16; int rgb_act;
+    /* workspace */
+    int64_t capacity; float* deltas; float* ts; int32_t* n_eff; int64_t* rays_a; int32_t* counts; int32_t* counts_alive;
+    float* xyzs; float* dirs; float* sigmas; float* rgbs; arn_field_ws_t ws;
+    /* in/out */
+    float* opacity; float* depth; float* rgb; int64_t* alive_out; int64_t* total_samples;
+} arn_test_iter_t;
+int arn_render_test_iter(const arn_test_iter_t* cfg_host, arn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Optimizer step.  Replaces apex FusedAdam(lr, betas=(0.9,0.999), eps=1e-15, weight_decay=0) (train.py:146).
  * One fused pass: Adam update of the fp32 master, optional un-scaling of the gradient by inv_grad_scale, refresh of
  * the fp16 working copy (dst_f16 may be NULL), and zeroing of the gradient for the next step (zero_grad != 0).

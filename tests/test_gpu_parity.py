@@ -647,6 +647,23 @@ def test_render_test_end_to_end(w1):
     assert_rel(N(res["rgb"]), rgb, rtol=1e-4, what="rgb", atol=ALPHA_ATOL * 10)
 
 
+@pytest.mark.parametrize("kind,thr,max_samples", [("W1", 1e-4, 1024), ("W1", 1e-2, 100), ("W3", 1e-2, 100)])
+def test_fused_test_loop_equals_eager_loop(kind, thr, max_samples, w1, w3):
+    """arn_render_test_iter (one native call per iteration, compact sample list, device-side alive compaction) against the
+    eager loop that mirrors rendering.py:189-236 op by op: same schedule, same samples, identical pixels."""
+    from ar_nerf_b200.rendering import render
+    w = workload(kind, w1, w3)
+    model, *_ = _field_setup(w.scale, 8, 23, table_amp=4.0)
+    w.install(model)
+    ro, rd = w.test_frame(160, 120)
+    kw = dict(test_time=True, T_threshold=thr, max_samples=max_samples, exp_step_factor=w.exp_step_factor)
+    a = render(model, T(ro), T(rd), **kw)
+    b = render(model, T(ro), T(rd), eager_test_loop=True, **kw)
+    assert int(a["total_samples"]) == int(b["total_samples"]) > 0
+    for k in ("opacity", "depth", "rgb"):
+        assert torch.equal(a[k], b[k]), k
+
+
 def test_grid_refresh_kernels_vs_torch(vren):
     """arn_grid_cell_positions / arn_density_grid_update against the torch expressions of networks.py:263-281."""
     g = torch.Generator(device="cuda").manual_seed(7)
