@@ -28,7 +28,7 @@ traffic = {}
 for name, lst in res.items():
     d = max(lst, key=lambda x: x.get('gpu__time_duration.sum', 0))
     tr = to_bytes(d.get('dram__bytes_read.sum', 0), d.get('dram__bytes_read.sum#unit')) + to_bytes(d.get('dram__bytes_write.sum', 0), d.get('dram__bytes_write.sum#unit'))
-    traffic[name] = tr
+    traffic[__import__('re').sub(r'<.*>', '', name)] = tr
     print(f"== {name}  ({len(lst)} launches captured)")
     for w in want:
         if w in d: print(f"   {w:72s} {d[w]} {d[w + '#unit']}")
