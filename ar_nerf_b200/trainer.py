@@ -52,17 +52,28 @@ class FusedAdam:
                 m, v = torch.zeros_like(p), torch.zeros_like(p)
             self.items.append((p, cache, m, v, st))
         self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        # the small all-reduces ride on their own communicator so that they overlap the table's reduce-scatter instead of
+        # queueing behind it (a 28 KB all-reduce is pure latency: ~28 us at 8 GPUs)
+        self.small_group = dist.new_group() if world > 1 and any(st is not None for *_, st in self.items) else None
 
     def step(self, inv_grad_scale=1.0):
         from .sharding import all_gather_shards, reduce_scatter_sum
         self.t += 1
         s_ = stream()
         hyper = (float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), self.t, float(inv_grad_scale))
-        for p, cache, m, v, st in self.items:
+        pending = {}
+        if self.world > 1:
+            for i, (p, cache, m, v, st) in enumerate(self.items):
+                if st is None:
+                    pending[i] = dist.all_reduce(p.grad, group=self.small_group, async_op=True)
+        # sharded parameters first: their collectives are the long ones
+        order = sorted(range(len(self.items)), key=lambda i: self.items[i][4] is None)
+        for i in order:
+            p, cache, m, v, st = self.items[i]
             p16 = cache.get(p) if cache is not None else None
             if st is None:
-                if self.world > 1:
-                    dist.all_reduce(p.grad)
+                if i in pending:
+                    pending[i].wait()
                 call("arn_adam_step", ptr(p.data), ptr(p.grad), ptr(m), ptr(v), ptr(p16), p.numel(), *hyper, 1, s_)
             else:
                 reduce_scatter_sum(st["gpad"], st["gshard"], self.rank, self.world)
