@@ -59,6 +59,14 @@ SIGNATURES = {
     "arn_last_error": [],
     "arn_launch_count": [],
     "arn_set_tunable": [C.c_char_p, I],
+    "arn_p2p_alloc": [C.POINTER(C.c_void_p), L],
+    "arn_p2p_free": [P],
+    "arn_p2p_export": [P, C.c_char_p],
+    "arn_p2p_open": [C.c_char_p, C.POINTER(C.c_void_p)],
+    "arn_p2p_close": [P],
+    "arn_p2p_signal": [C.POINTER(C.c_void_p), I, I, I, C.c_uint64, P],
+    "arn_p2p_wait": [P, I, I, C.c_uint64, P],
+    "arn_p2p_adam_exchange": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), I, L, L, P, P, P, F, F, F, F, I, F, P],
     "arn_grid_cell_positions": [P, P, L, I, F, P, P],
     "arn_density_grid_update": [P, P, P, F, F, L, P, P, P],
     "arn_profile_enable": [I],

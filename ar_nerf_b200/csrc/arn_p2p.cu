@@ -1,0 +1,164 @@
+// libarnerf.so -- multi-GPU gradient exchange fused with the optimizer, over NVLink peer memory.
+//
+// Data-parallel training replicates the hash table; per step every rank must (1) sum the table gradients of all
+// ranks, (2) run Adam, (3) see the updated fp16 table.  With NCCL that is reduce-scatter (fp32) -> Adam on the rank's
+// slice -> all-gather (fp16): three serial phases, ~170 us at 8 GPUs for the 45.8 MB table.  Here ONE kernel does all
+// three for the rank's slice: it LOADS the slice of every rank's gradient buffer straight from peer memory (fixed rank
+// order: deterministic sum), applies Adam to the fp32 master / moments it owns, and STORES the fp16 result into every
+// rank's working copy through the same peer mappings -- inbound gradient loads and outbound fp16 stores use the two
+// directions of the links at once and overlap the arithmetic element by element.
+//
+// Ranks are separate processes (one per GPU): buffers come from arn_p2p_alloc (cudaMalloc, so that the CUDA IPC handle
+// of the base pointer can be exported) and are opened by the peers with arn_p2p_open.  Synchronisation is a pair of
+// monotonic flag slots per rank in peer-visible memory: arn_p2p_signal publishes "my step s is done" into every rank's
+// flag array (after a system-scope fence), arn_p2p_wait spins until all ranks have published >= s.  Each rank always
+// signals before it waits on the same stream, so no rank can wait for a kernel that is not already queued on its peer;
+// the spin is bounded (trap after ~4 s) so that a dead peer fails the launch instead of hanging the GPU.
+#include "arn_common.cuh"
+#include <string.h>
+
+namespace arn {
+
+constexpr int kMaxRanks = ARN_P2P_MAX_RANKS;
+struct PeerF32 { const float* p[kMaxRanks]; };
+struct PeerF16 { __half* p[kMaxRanks]; };
+struct PeerFlags { unsigned long long* p[kMaxRanks]; };
+
+__global__ void p2p_signal_kernel(PeerFlags peers, int n_ranks, int rank, int slot, unsigned long long value) {
+    __threadfence_system();  // everything this stream has written (also into peer memory) is visible before the flag
+    const int r = threadIdx.x;
+    if (r < n_ranks) {
+        volatile unsigned long long* f = peers.p[r] + slot * kMaxRanks + rank;
+        *f = value;
+    }
+    __threadfence_system();
+}
+
+__global__ void p2p_wait_kernel(const unsigned long long* __restrict__ flags, int n_ranks, int slot, unsigned long long value) {
+    const int r = threadIdx.x;
+    if (r < n_ranks) {
+        const volatile unsigned long long* f = flags + slot * kMaxRanks + r;
+        const long long t0 = clock64();
+        while (*f < value) {
+            __nanosleep(200);
+            if (clock64() - t0 > (long long)8e9) __trap();  // ~4 s at 2 GHz: a peer died
+        }
+    }
+    __threadfence_system();
+}
+
+__device__ __forceinline__ uint2 pack_half4_(const float4& a) {
+    const __half2 lo = __floats2half2_rn(a.x, a.y), hi = __floats2half2_rn(a.z, a.w);
+    uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    return o;
+}
+
+// Elements [lo, lo + 4*n4) of the flat parameter: sum of the ranks' gradients (rank order), Adam (arn_adam_step's
+// arithmetic with inv_gs = 1 / (grad_scale * world)), fp16 result to every rank.  p / m / v point at this rank's slice.
+__global__ void __launch_bounds__(256) p2p_adam_exchange_kernel(PeerF32 grads, PeerF16 p16, int n_ranks, int64_t lo, int64_t n4,
+                                                                float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
+                                                                float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_gs) {
+    const float lr_bc1 = lr / bc1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = lo + 4 * i;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 gr[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; r++)
+            if (r < n_ranks) gr[r] = __ldcs(reinterpret_cast<const float4*>(grads.p[r] + e));  // all peer loads in flight
+        const float4 m4 = __ldcs(m + i), v4 = __ldcs(v + i), p4 = __ldcs(p + i);
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; r++)
+            if (r < n_ranks) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
+        float pn[4] = {p4.x, p4.y, p4.z, p4.w}, mn[4] = {m4.x, m4.y, m4.z, m4.w}, vn[4] = {v4.x, v4.y, v4.z, v4.w};
+        const float gs[4] = {g.x * inv_gs, g.y * inv_gs, g.z * inv_gs, g.w * inv_gs};
+        bool touched = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (gs[k] == 0.0f && mn[k] == 0.0f && vn[k] == 0.0f) continue;  // untouched hash entry: the update is exactly zero
+            touched = true;
+            mn[k] = b1 * mn[k] + (1.0f - b1) * gs[k];
+            vn[k] = b2 * vn[k] + (1.0f - b2) * gs[k] * gs[k];
+            const float denom = sqrtf(vn[k]) / bc2_sqrt + eps;
+            pn[k] = pn[k] - lr_bc1 * (mn[k] / denom);
+        }
+        if (!touched) continue;  // parameter unchanged: every rank's fp16 copy already holds it
+        __stcs(m + i, make_float4(mn[0], mn[1], mn[2], mn[3])); __stcs(v + i, make_float4(vn[0], vn[1], vn[2], vn[3]));
+        const float4 pnew = make_float4(pn[0], pn[1], pn[2], pn[3]);
+        __stcs(p + i, pnew);
+        const uint2 h = pack_half4_(pnew);
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; r++)
+            if (r < n_ranks) *reinterpret_cast<uint2*>(p16.p[r] + e) = h;
+    }
+}
+
+}  // namespace arn
+
+using namespace arn;
+
+extern "C" ARN_API int arn_p2p_alloc(void** ptr_host, int64_t bytes) {
+    ARN_REQUIRE(ptr_host && bytes > 0, "bad arguments");
+    ARN_CUDA(cudaMalloc(ptr_host, (size_t)bytes));
+    ARN_CUDA(cudaMemset(*ptr_host, 0, (size_t)bytes));
+    return ARN_OK;
+}
+extern "C" ARN_API int arn_p2p_free(void* ptr) {
+    if (ptr) ARN_CUDA(cudaFree(ptr));
+    return ARN_OK;
+}
+extern "C" ARN_API int arn_p2p_export(void* ptr, unsigned char* handle64_host) {
+    ARN_REQUIRE(ptr && handle64_host, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    ARN_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle64_host, &h, 64);
+    return ARN_OK;
+}
+extern "C" ARN_API int arn_p2p_open(const unsigned char* handle64_host, void** ptr_host) {
+    ARN_REQUIRE(handle64_host && ptr_host, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, 64);
+    ARN_CUDA(cudaIpcOpenMemHandle(ptr_host, h, cudaIpcMemLazyEnablePeerAccess));
+    return ARN_OK;
+}
+extern "C" ARN_API int arn_p2p_close(void* ptr) {
+    if (ptr) ARN_CUDA(cudaIpcCloseMemHandle(ptr));
+    return ARN_OK;
+}
+
+extern "C" ARN_API int arn_p2p_signal(void* const* peer_flags_host, int n_ranks, int rank, int slot, uint64_t value, arn_stream_t stream) {
+    ARN_REQUIRE(peer_flags_host && n_ranks >= 1 && n_ranks <= kMaxRanks && rank >= 0 && rank < n_ranks && slot >= 0 && slot < ARN_P2P_FLAG_SLOTS, "bad arguments");
+    PeerFlags pf{};
+    for (int r = 0; r < n_ranks; r++) { ARN_REQUIRE(peer_flags_host[r], "null peer flag array"); pf.p[r] = (unsigned long long*)peer_flags_host[r]; }
+    ARN_LAUNCH("p2p_signal_kernel", (cudaStream_t)stream, p2p_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, n_ranks, rank, slot, (unsigned long long)value));
+    return check_launch("p2p_signal");
+}
+extern "C" ARN_API int arn_p2p_wait(const void* my_flags, int n_ranks, int slot, uint64_t value, arn_stream_t stream) {
+    ARN_REQUIRE(my_flags && n_ranks >= 1 && n_ranks <= kMaxRanks && slot >= 0 && slot < ARN_P2P_FLAG_SLOTS, "bad arguments");
+    ARN_LAUNCH("p2p_wait_kernel", (cudaStream_t)stream, p2p_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)my_flags, n_ranks, slot, (unsigned long long)value));
+    return check_launch("p2p_wait");
+}
+
+extern "C" ARN_API int arn_p2p_adam_exchange(void* const* peer_grads_host, void* const* peer_p16_host, int n_ranks, int64_t lo, int64_t count,
+                                             float* params_slice, float* exp_avg_slice, float* exp_avg_sq_slice, float lr, float beta1, float beta2,
+                                             float eps, int step, float inv_grad_scale, arn_stream_t stream) {
+    ARN_REQUIRE(peer_grads_host && peer_p16_host && n_ranks >= 1 && n_ranks <= kMaxRanks && step >= 1, "bad arguments");
+    ARN_REQUIRE(lo >= 0 && count >= 0 && lo % 4 == 0 && count % 4 == 0, "slice must be 4-element aligned");
+    if (count == 0) return ARN_OK;
+    ARN_REQUIRE(params_slice && exp_avg_slice && exp_avg_sq_slice, "null pointer");
+    PeerF32 g{}; PeerF16 h{};
+    for (int r = 0; r < n_ranks; r++) {
+        ARN_REQUIRE(peer_grads_host[r] && peer_p16_host[r], "null peer buffer");
+        ARN_REQUIRE(((uintptr_t)peer_grads_host[r] & 15) == 0 && ((uintptr_t)peer_p16_host[r] & 7) == 0, "peer buffers must be 16-byte aligned");
+        g.p[r] = (const float*)peer_grads_host[r]; h.p[r] = (__half*)peer_p16_host[r];
+    }
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    const int64_t n4 = count / 4;
+    const int grid = (int)min((int64_t)148 * 8, (n4 + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    ARN_LAUNCH("p2p_adam_exchange_kernel", st, p2p_adam_exchange_kernel<<<grid, 256, 0, st>>>(g, h, n_ranks, lo, n4, (float4*)params_slice, (float4*)exp_avg_slice,
+                                                                                             (float4*)exp_avg_sq_slice, lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale));
+    return check_launch("p2p_adam_exchange");
+}

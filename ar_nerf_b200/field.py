@@ -98,6 +98,11 @@ class _F16Cache:
         self.buf = torch.empty(self.capacity, dtype=torch.float16, device=p.device)
         self.key = None
 
+    def adopt(self, p, buf):
+        """Use an externally owned fp16 buffer (peer-mapped memory of the multi-GPU exchange) as the working copy."""
+        assert buf.dtype == torch.float16 and buf.numel() >= p.numel()
+        self.buf, self.capacity, self.key = buf, buf.numel(), None
+
     def get(self, p):
         key = (p.data_ptr(), p._version, p.device)
         if self.buf is None or self.buf.numel() < p.numel() or self.buf.device != p.device:

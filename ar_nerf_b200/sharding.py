@@ -80,3 +80,69 @@ def all_gather_shards(full, rank, world):
         dist.all_gather(parts, mine.clone())
         for r, part in enumerate(parts):
             full[r * S:(r + 1) * S].copy_(part)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Peer-memory exchange (csrc/arn_p2p.cu): the gradient buffer and the fp16 working copy of the sharded parameter live in
+# cudaMalloc'ed memory whose CUDA IPC handles are exchanged once; afterwards ONE kernel per step reads the ranks'
+# gradient slices over NVLink, runs Adam and writes the fp16 slice into every rank's copy.
+class _RawCuda:
+    """Zero-copy torch view of raw device memory (torch.as_tensor understands __cuda_array_interface__)."""
+
+    def __init__(self, ptr, numel, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """Buffers + peer mappings + flag slots of one sharded parameter.  Collective constructor (every rank calls it)."""
+
+    def __init__(self, n, world, rank, device):
+        import ctypes as C
+        from . import _lib
+        self.n, self.world, self.rank = n, world, rank
+        self.S, self.P = shard_size(n, world), padded_numel(n, world)
+        self.lo = rank * self.S
+        self.cnt = max(0, min(self.lo + self.S, n) - self.lo)
+
+        def alloc(nbytes):
+            out = C.c_void_p()
+            _lib.call("arn_p2p_alloc", C.byref(out), int(nbytes))
+            return out.value
+
+        def export(ptr):
+            buf = C.create_string_buffer(64)
+            _lib.call("arn_p2p_export", ptr, buf)
+            return buf.raw
+
+        with torch.cuda.device(device):
+            self.g_ptr, self.h_ptr, self.f_ptr = alloc(self.P * 4), alloc(self.P * 2), alloc(4096)
+            mine = (export(self.g_ptr), export(self.h_ptr), export(self.f_ptr))
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+            arrs = []
+            for k, own in enumerate((self.g_ptr, self.h_ptr, self.f_ptr)):
+                ptrs = []
+                for r in range(world):
+                    if r == rank:
+                        ptrs.append(own)
+                    else:
+                        out = C.c_void_p()
+                        _lib.call("arn_p2p_open", everyone[r][k], C.byref(out))
+                        ptrs.append(out.value)
+                arrs.append((C.c_void_p * world)(*ptrs))
+            self.G, self.H, self.F = arrs
+        self.grad = torch.as_tensor(_RawCuda(self.g_ptr, self.P, "<f4"), device=device)
+        self.p16 = torch.as_tensor(_RawCuda(self.h_ptr, self.P, "<f2"), device=device)
+        dist.barrier()  # every mapping exists before anyone signals
+
+    def step(self, p_flat, m, v, hyper, step_id, cuda_stream):
+        """hyper = (lr, beta1, beta2, eps, step, inv_grad_scale).  Gradients of every rank must be complete on this stream."""
+        from ._lib import call, ptr
+        call("arn_p2p_signal", self.F, self.world, self.rank, 0, step_id, cuda_stream)   # my gradients are final
+        call("arn_p2p_wait", self.f_ptr, self.world, 0, step_id, cuda_stream)                                  # ... and everyone's
+        if self.cnt > 0:
+            call("arn_p2p_adam_exchange", self.G, self.H, self.world, self.lo, self.cnt, ptr(p_flat[self.lo:self.lo + self.cnt]), ptr(m), ptr(v),
+                 *hyper, cuda_stream)
+        call("arn_p2p_signal", self.F, self.world, self.rank, 1, step_id, cuda_stream)   # my fp16 slice is in every copy, I am done reading
+        call("arn_p2p_wait", self.f_ptr, self.world, 1, step_id, cuda_stream)             # my copy is complete, nobody reads my gradients any more
+        self.grad.zero_()

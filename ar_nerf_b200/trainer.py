@@ -27,8 +27,8 @@ class FusedAdam:
     on the wire and 1/world of Adam's HBM traffic.  The fp32 master of a sharded parameter is current only inside the
     owner's slice until gather_master() (call it before saving a checkpoint)."""
 
-    def __init__(self, params_and_caches, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, world=1, rank=0, shard_min_numel=1 << 20):
-        from .sharding import padded_numel, shard_size
+    def __init__(self, params_and_caches, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, world=1, rank=0, shard_min_numel=1 << 20, exchange="p2p"):
+        from .sharding import PeerExchange, padded_numel, shard_size
         self.items = []
         self.world, self.rank = world, rank
         for p, cache in params_and_caches:
@@ -38,12 +38,29 @@ class FusedAdam:
             sharded = world > 1 and n >= shard_min_numel and cache is not None
             if sharded:
                 S, P = shard_size(n, world), padded_numel(n, world)
-                gpad = torch.zeros(P, dtype=p.dtype, device=p.device)
-                p.grad = gpad[:n].view_as(p)       # the kernels accumulate here; the tail pads the last shard
-                cache.reserve(p, P)
                 lo = rank * S
                 cnt = max(0, min(lo + S, n) - lo)
-                st = dict(S=S, P=P, lo=lo, cnt=cnt, gpad=gpad, gshard=torch.empty(S, dtype=p.dtype, device=p.device))
+                px = None
+                if exchange == "p2p" and dist.get_backend() == "nccl":
+                    # peer-memory exchange fused with Adam (csrc/arn_p2p.cu); every rank must succeed, else all fall back to NCCL
+                    try:
+                        px = PeerExchange(n, world, rank, p.device)
+                        ok = torch.ones(1, device=p.device)
+                    except RuntimeError as e:
+                        print(f"[ar_nerf_b200] peer-memory exchange unavailable on rank {rank}: {e}")
+                        ok = torch.zeros(1, device=p.device)
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                    if float(ok.item()) == 0:
+                        px = None
+                if px is not None:
+                    gpad = px.grad
+                    cache.adopt(p, px.p16)
+                else:
+                    gpad = torch.zeros(P, dtype=p.dtype, device=p.device)
+                    cache.reserve(p, P)
+                p.grad = gpad[:n].view_as(p)       # the kernels accumulate here; the tail pads the last shard
+                st = dict(S=S, P=P, lo=lo, cnt=cnt, gpad=gpad, px=px,
+                          gshard=None if px is not None else torch.empty(S, dtype=p.dtype, device=p.device))
                 m, v = torch.zeros(S, dtype=p.dtype, device=p.device), torch.zeros(S, dtype=p.dtype, device=p.device)
             else:
                 if p.grad is None:
@@ -75,6 +92,8 @@ class FusedAdam:
                 if i in pending:
                     pending[i].wait()
                 call("arn_adam_step", ptr(p.data), ptr(p.grad), ptr(m), ptr(v), ptr(p16), p.numel(), *hyper, 1, s_)
+            elif st["px"] is not None:
+                st["px"].step(p.data.view(-1), m, v, hyper, self.t, s_)
             else:
                 reduce_scatter_sum(st["gpad"], st["gshard"], self.rank, self.world)
                 st["gpad"].zero_()
@@ -149,7 +168,7 @@ class _FusedWorkspace:
 class NGPTrainer:
     def __init__(self, model, lr=1e-2, num_epochs=30, steps_per_epoch=1000, loss_func='raw', depth_loss_w=0.0,
                  distortion_loss_w=0.0, exp_step_factor=None, random_bg=False, grad_scale=1.0,
-                 update_interval=16, warmup_steps=256, fused=True, sample_capacity=None, shard_optimizer=True):
+                 update_interval=16, warmup_steps=256, fused=True, sample_capacity=None, shard_optimizer=True, exchange="p2p"):
         self.model = model
         # the fused native step covers the default training configuration (train.py defaults: 'raw' loss, no distortion
         # loss, fixed background); anything else runs the eager render() + autograd path
@@ -168,7 +187,8 @@ class NGPTrainer:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.opt = FusedAdam([(model.xyz_encoder.params, st.cache_xyz), (model.rgb_net.params, st.cache_rgb)], lr,
-                             world=self.world, rank=self.rank, shard_min_numel=(1 << 20) if shard_optimizer else (1 << 62))
+                             world=self.world, rank=self.rank, shard_min_numel=(1 << 20) if shard_optimizer else (1 << 62),
+                             exchange=exchange)
         self.global_step = 0
         self._grid_epoch = 0
 

@@ -360,6 +360,30 @@ int arn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
                   float lr, float beta1, float beta2, float eps, int step, float inv_grad_scale, int zero_grad,
                   arn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: gradient exchange fused with the optimizer over NVLink peer memory (one process per GPU; replaces the
+ * DDP all-reduce of train.py's Lightning trainer + apex FusedAdam for the hash table).
+ *   arn_p2p_alloc / free    device buffer whose base pointer can be exported (cudaMalloc, zero-filled)
+ *   arn_p2p_export / open / close   CUDA IPC handle (64 bytes) of such a buffer / mapping of a peer's buffer
+ *   arn_p2p_signal          publish `value` in slot `slot` of every rank's flag array (after a system-scope fence)
+ *   arn_p2p_wait            wait until every rank has published >= value in `slot` of MY flag array (bounded spin)
+ *   arn_p2p_adam_exchange   for the slice [lo, lo+count) of the flat parameter: sum the ranks' gradients read from peer
+ *                           memory (rank order), Adam (arn_adam_step's arithmetic), write the fp16 result into every rank's
+ *                           fp16 working copy.  params/exp_avg/exp_avg_sq point at this rank's slice (local memory).
+ * Flag arrays hold ARN_P2P_FLAG_SLOTS * ARN_P2P_MAX_RANKS uint64 and must come from arn_p2p_alloc (zeroed). */
+#define ARN_P2P_MAX_RANKS 8
+#define ARN_P2P_FLAG_SLOTS 4
+int arn_p2p_alloc(void** ptr_host, int64_t bytes);
+int arn_p2p_free(void* ptr);
+int arn_p2p_export(void* ptr, unsigned char* handle64_host);
+int arn_p2p_open(const unsigned char* handle64_host, void** ptr_host);
+int arn_p2p_close(void* ptr);
+int arn_p2p_signal(void* const* peer_flags_host, int n_ranks, int rank, int slot, uint64_t value, arn_stream_t stream);
+int arn_p2p_wait(const void* my_flags, int n_ranks, int slot, uint64_t value, arn_stream_t stream);
+int arn_p2p_adam_exchange(void* const* peer_grads_host, void* const* peer_p16_host, int n_ranks, int64_t lo, int64_t count,
+                          float* params_slice, float* exp_avg_slice, float* exp_avg_sq_slice, float lr, float beta1,
+                          float beta2, float eps, int step, float inv_grad_scale, arn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,8 +16,10 @@ for _ in range(2):
     torch.manual_seed(0)
     m = NGP(w.scale).to(dev); w.install(m); models.append(m)
 assert torch.equal(models[0].xyz_encoder.params, models[1].xyz_encoder.params)
-ta = NGPTrainer(models[0], shard_optimizer=True); tb = NGPTrainer(models[1], shard_optimizer=False)
+mode = os.environ.get("EXCHANGE", "p2p")
+ta = NGPTrainer(models[0], shard_optimizer=True, exchange=mode); tb = NGPTrainer(models[1], shard_optimizer=False)
 assert ta.opt.items[0][4] is not None and tb.opt.items[0][4] is None
+print(f"rank {rank}: exchange = {'p2p' if ta.opt.items[0][4]['px'] is not None else 'nccl'}", flush=True)
 B = [[t.to(dev) for t in w.train_batch(i, 4096, seed=rank)] for i in range(6)]
 for i, b in enumerate(B):
     la, _ = ta.train_step(b[0], b[1], b[2], noise=b[3], update_grid=False)
