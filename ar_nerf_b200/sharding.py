@@ -17,6 +17,32 @@ def shard_rays(rays_o, rays_d, rank, world, *extra):
     return tuple(t[lo:hi] for t in (rays_o, rays_d) + extra)
 
 
+def shard_rays_interleaved(rays_o, rays_d, rank, world, *extra):
+    """Rank r takes rays r, r + world, r + 2*world, ...: every rank sees the same mix of empty and occupied pixels, so the
+    test-time render loop is balanced (contiguous bands give the middle ranks all the work of a centred object)."""
+    return tuple(t[rank::world].contiguous() for t in (rays_o, rays_d) + extra)
+
+
+def gather_frame_interleaved(local, n_total, rank, world, dst=0):
+    """Inverse of shard_rays_interleaved for per-ray results (n_local, C): the (n_total, C) frame on `dst`, None elsewhere."""
+    if world == 1:
+        return local
+    pad = (n_total + world - 1) // world
+    send = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    send[:local.shape[0]] = local
+    if dist.get_backend() == "nccl":
+        out = torch.empty((world, pad) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out.view((world * pad,) + tuple(local.shape[1:])), send)
+    else:
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send)
+        out = torch.stack(parts, 0)
+    if rank != dst:
+        return None
+    # ray i*world + r is row i of rank r; the padding rows all land behind n_total
+    return out.transpose(0, 1).reshape((world * pad,) + tuple(local.shape[1:]))[:n_total]
+
+
 def allreduce_grads(grads, world):
     """Sum-reduce gradient buffers in place (the optimizer divides by world); one collective per buffer."""
     if world > 1:
@@ -32,6 +58,15 @@ def gather_frame(local, n_total, rank, world, dst=0):
     pad = max(hi - lo for lo, hi in sizes)  # collectives want equal shapes: pad every band to the largest one
     send = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     send[:local.shape[0]] = local
+    if dist.get_backend() == "nccl":
+        # one all-gather (a single NCCL kernel over NVSwitch) instead of gather's world-1 send/recv pairs; 12.8 MB per frame
+        out = torch.empty((world * pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, send)
+        if rank != dst:
+            return None
+        if all(hi - lo == pad for lo, hi in sizes):
+            return out[:n_total]
+        return torch.cat([out[r * pad:r * pad + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], 0)
     bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
     dist.gather(send, bufs, dst=dst)
     if rank != dst:

@@ -277,15 +277,15 @@ def run_ours(args):
         c, ms = prof["hash_encode_fw_kernel"]
         hash_gbs = 588.0 * N / (ms / c * 1e-3) / 1e9
 
-    # 800x800 test frame (configs[2]); row bands sharded across ranks, gathered on rank 0
-    from ar_nerf_b200.sharding import gather_frame, shard_rays
+    # 800x800 test frame (configs[2]); pixels interleaved across ranks (balanced), gathered on rank 0
+    from ar_nerf_b200.sharding import gather_frame_interleaved, shard_rays_interleaved
     fro, frd = w.test_frame(800, 800)
-    fro, frd = shard_rays(fro, frd, rank, world)
+    fro, frd = shard_rays_interleaved(fro, frd, rank, world)
     fro, frd = fro.to(dev), frd.to(dev)
 
     def frame(i):
         r = render(model, fro, frd, test_time=True, T_threshold=1e-4)
-        gather_frame(torch.cat([r["rgb"], r["depth"][:, None], r["opacity"][:, None]], 1), 640000, rank, world)
+        gather_frame_interleaved(torch.cat([r["rgb"], r["depth"][:, None], r["opacity"][:, None]], 1), 640000, rank, world)
 
     frame(0)
     n_frames = 3

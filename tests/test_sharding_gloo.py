@@ -5,8 +5,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ar_nerf_b200.sharding import (all_gather_shards, allreduce_grads, gather_frame, padded_numel, reduce_scatter_sum, shard_bounds,
-                                   shard_rays, shard_size)
+from ar_nerf_b200.sharding import (all_gather_shards, allreduce_grads, gather_frame, gather_frame_interleaved, padded_numel,
+                                   reduce_scatter_sum, shard_bounds, shard_rays, shard_rays_interleaved, shard_size)
 
 
 def test_shard_bounds_cover_exactly():
@@ -42,6 +42,10 @@ def _worker(rank, world, port):
     params = torch.zeros(P); params[rank * S:(rank + 1) * S] = -0.5 * gs   # each rank updates its slice only
     all_gather_shards(params, rank, world)
     assert torch.equal(params, -0.5 * want)
+    oi, di = shard_rays_interleaved(rays_o, rays_d, rank, world)
+    assert torch.equal(oi, rays_o[rank::world]) and torch.equal(di, rays_d[rank::world])
+    fi = gather_frame_interleaved(oi * 3, 1001, rank, world)
+    assert (fi is None) if rank else torch.equal(fi, rays_o * 3)
     frame = gather_frame(o * 2, 1001, rank, world)
     if rank == 0:
         assert torch.equal(frame, rays_o * 2)
