@@ -276,11 +276,13 @@ class NGPTrainer:
             nxt.pending = True
             nxt.grid_epoch = self._grid_epoch
         w.cur ^= 1
-        # views into the reused workspace (valid until the next step); per-sample buffers hold counter[0] samples
-        results = {'rgb': w.rgb_final, 'opacity': w.opacity, 'depth': w.depth, 'rm_samples': ms.counter[0].clone(),
+        # everything returned is a VIEW into the reused workspace: the per-ray outputs and the loss are valid until the next
+        # step, the march products (rm_samples, rays_a, ts/deltas) until the step after it; per-sample buffers hold
+        # rm_samples samples.  Clone what has to live longer.
+        results = {'rgb': w.rgb_final, 'opacity': w.opacity, 'depth': w.depth, 'rm_samples': ms.counter[0],
                    'rays_a': ms.rays_a, 'total_samples_per_ray': w.total_samples, 'ts_buf': ms.ts, 'deltas_buf': ms.deltas,
                    'ws_buf': w.ws_out}
-        return w.loss[0].clone(), results
+        return w.loss[0], results
 
     def train_step(self, rays_o, rays_d, rgb_target, noise=None, update_grid=True, next_rays=None):
         """One optimisation step.  next_rays = (rays_o, rays_d[, noise]) of the FOLLOWING call, if the caller already has

@@ -200,7 +200,7 @@ def run_ours(args):
         ro, rd, tgt = resident[i % N_BATCHES]
         nro, nrd, _ = resident[(i + 1) % N_BATCHES]  # the trainer marches the next batch while this one trains
         _, res = trainer.train_step(ro, rd, tgt, next_rays=None if NO_PREFETCH else (nro, nrd))
-        samples_seen.append(res["rm_samples"])
+        samples_seen.append(res["rm_samples"].clone())  # the trainer returns views into its workspace
 
     staged = {}
 
@@ -291,6 +291,29 @@ def run_ours(args):
     n_frames = 3
     fps = n_frames / (timed(frame, n_frames) * 1e-3)
 
+    # informational: the unbounded configuration (configs[3]: scale 16, 6 cascades, exp_step_factor 1/256), same step
+    other = None
+    if world == 1 and not args.skip_w3:
+        w3 = Workload("W3")
+        m3 = NGP(w3.scale).to(dev)
+        w3.install(m3)
+        t3 = NGPTrainer(m3)
+        b3 = [[t.to(dev) for t in w3.train_batch(i, BATCH)[:3]] for i in range(8)]
+        seen3 = []
+
+        def step_w3(i):
+            ro, rd, tgt = b3[i % 8]
+            _, res = t3.train_step(ro, rd, tgt, next_rays=tuple(b3[(i + 1) % 8][:2]))
+            seen3.append(res["rm_samples"].clone())
+
+        for i in range(2 * t3.update_interval):
+            step_w3(i)
+        seen3.clear()
+        ms3 = timed(step_w3, 32)
+        other = {"W3_unbounded_scale16_train_Mrays_per_s": BATCH * 32 / (ms3 * 1e-3) / 1e6, "ms_per_step": ms3 / 32,
+                 "samples_per_step": float(torch.stack([x.float() for x in seen3]).mean().item())}
+        del t3, m3, b3
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         mrays, cores, sec = cpu_reference(2048, 3, 1)
@@ -307,7 +330,7 @@ def run_ours(args):
                            "grid_update": "every 16 steps inside the timed region (warm-up form: all 128^3 cells)"},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": BATCH * 36, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-                "frames_per_s_800x800": fps, "hash_encode_GBps": hash_gbs,
+                "frames_per_s_800x800": fps, "hash_encode_GBps": hash_gbs, "other_configs": other,
                 "kernel_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
         print(json.dumps(line))
     if world > 1:
@@ -321,6 +344,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-w3", action="store_true", help="skip the informational unbounded-scene (W3) leg")
     ap.add_argument("--train-only", action="store_true", help="profiling runs: skip the e2e, test-frame and CPU legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
