@@ -20,7 +20,7 @@ class Levels(C.Structure):
     _fields_ = [("scale_host", P), ("res_host", P), ("size_host", P), ("offset_host", P)]
 
 
-FIELD_SCRATCH_BYTES = 20480 + 512 * 10240 * 4  # ARN_FIELD_SCRATCH_BYTES (include/arnerf.h)
+FIELD_SCRATCH_BYTES = 20480 + 1280 * 10240 * 4  # ARN_FIELD_SCRATCH_BYTES (include/arnerf.h)
 
 
 class FieldWs(C.Structure):

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "arn_common.cuh"
+#include "arn_field.cuh"
 
 namespace arn {
 static thread_local char g_err[512] = "";
@@ -21,9 +22,30 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- kernel-variant switches
-static std::atomic<int> g_tun[kTunCount] = {{1}, {32}, {1}};
-static const char* const g_tun_names[kTunCount] = {"march_warp", "hash_bw_mode", "adam_vec"};
+static std::atomic<int> g_tun[kTunCount] = {{1}, {32}, {1}, {1}};
+static const char* const g_tun_names[kTunCount] = {"march_warp", "hash_bw_mode", "adam_vec", "pipeline_parts"};
 int tunable(Tunable t) { return g_tun[t].load(std::memory_order_relaxed); }
+
+// ---- side stream + events for the pipelined field evaluation, one set per device
+int pipe_streams(PipeStreams** out) {
+    static PipeStreams pool[16];
+    static bool made[16] = {};
+    static std::mutex mu;
+    int dev = 0;
+    ARN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { set_error("pipe_streams: device index out of range"); return ARN_E_INVALID; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (!made[dev]) {
+        PipeStreams& p = pool[dev];
+        ARN_CUDA(cudaStreamCreateWithFlags(&p.side, cudaStreamNonBlocking));
+        ARN_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+        ARN_CUDA(cudaEventCreateWithFlags(&p.join, cudaEventDisableTiming));
+        for (int k = 0; k < 8; k++) ARN_CUDA(cudaEventCreateWithFlags(&p.ev[k], cudaEventDisableTiming));
+        made[dev] = true;
+    }
+    *out = &pool[dev];
+    return ARN_OK;
+}
 
 // ---- per-kernel timing
 struct TimedLaunch { const char* name; cudaEvent_t e0, e1; };

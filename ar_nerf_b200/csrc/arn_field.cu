@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __rest
                                                              const __grid_constant__ LevelTable tbl,
                                                              const __half2* __restrict__ table, __half2* __restrict__ feat, int img,
                                                              const __half* __restrict__ pack_wd, const __half* __restrict__ pack_wc,
-                                                             uint8_t* __restrict__ pack_img) {
+                                                             uint8_t* __restrict__ pack_img, int part, int parts) {
     if (n_dev) n = min(n, (int64_t)*n_dev);
     const int grp = blockIdx.y;  // levels [8*grp, 8*grp + 8)
     if (pack_img && grp == 0) {  // rider: the MLP kernels that follow read the weights as a swizzled operand image
@@ -41,8 +41,12 @@ __global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __rest
     }
     // tile image: the rows that pad the last 128-row tile are written as zeros (the MLP kernels move whole tiles, and the
     // backward multiplies them by zero gradients: they must be finite)
-    const int64_t n_rows = img ? ((n + 127) & ~(int64_t)127) : n;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n_rows = img ? ((n + 127) & ~(int64_t)127) : n;
+    // one of `parts` consecutive ranges of 128-row tiles (the host pipelines range p+1 under the MLP of range p)
+    const int64_t tiles_all = (n + 127) / 128;
+    const int64_t row0 = (tiles_all * part / parts) * 128;
+    n_rows = min(n_rows, (tiles_all * (part + 1) / parts) * 128);
+    for (int64_t i = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t out[8];
         if (i < n) {
             float x01[3];
@@ -153,7 +157,7 @@ template <int SEG>
 __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                                   const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
                                                                   float2* __restrict__ table_grad, int level0, int nlevels, int img,
-                                                                  int n_main_blocks, WgradReduce red) {
+                                                                  int n_main_blocks, WgradReduce red, int part, int parts) {
     __shared__ float red_part[8][32];
     if ((int)blockIdx.x >= n_main_blocks) {  // rider blocks: sum of the MLP weight-gradient slabs (independent of the table work)
         wgrad_reduce_block((int)blockIdx.x - n_main_blocks, red.wpart, red.n_slabs, red.with_rgb, red.dWd, red.dWc, red_part);
@@ -161,13 +165,16 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
     }
     if (n_dev) n = min(n, (int64_t)*n_dev);
     const int l = (threadIdx.x & 15);
-    const int64_t n_seg = (n + SEG - 1) / SEG;
+    // segments of one of `parts` consecutive ranges of 128-sample tiles (a tile is 128 / SEG segments)
+    const int64_t tiles_all = (n + 127) / 128;
+    const int64_t seg0 = (tiles_all * part / parts) * (128 / SEG);
+    const int64_t n_seg = min((n + SEG - 1) / SEG, (tiles_all * (part + 1) / parts) * (128 / SEG));
     const uint32_t size = tbl.size[l], res = tbl.res[l], mode = tbl.mode[l];
     float2* lvl = table_grad + tbl.offset[l];
     const bool pair_ok = (reinterpret_cast<uintptr_t>(lvl) & 15) == 0;  // 16-byte reductions need the level base aligned
     const float scale = tbl.scale[l];
     const bool active = l >= level0 && l < level0 + nlevels;
-    for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; seg < n_seg; seg += ((int64_t)n_main_blocks * blockDim.x) >> 4) {
+    for (int64_t seg = seg0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4); seg < n_seg; seg += ((int64_t)n_main_blocks * blockDim.x) >> 4) {
         if (!active) continue;
         const int64_t i0 = seg * SEG, i1 = min(n, i0 + SEG);
         uint32_t cg[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
@@ -216,20 +223,21 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
 
 template <int SEG>
 static int launch_hash_bw_runs(const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
-                               float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red) {
-    const int64_t threads = ((n + SEG - 1) / SEG) * 16;
-    const int grid = (int)min((int64_t)148 * 8, (threads + 255) / 256);
+                               float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red, int part, int parts) {
+    const int64_t threads = ((n + SEG - 1) / SEG) * 16 / parts;
+    const int grid = (int)max((int64_t)1, min((int64_t)148 * 8, (threads + 255) / 256));
     const int riders = red.wpart ? kWgradFloats / 32 : 0;
-    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, hash_encode_bw_runs_kernel<SEG><<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img, grid, red));
+    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, hash_encode_bw_runs_kernel<SEG><<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img, grid, red, part, parts));
     return check_launch("hash_encode_bw_runs");
 }
 static int hash_bw_runs(int seg, const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
-                        float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red = WgradReduce{nullptr, 0, 0, nullptr, nullptr}) {
+                        float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red = WgradReduce{nullptr, 0, 0, nullptr, nullptr},
+                        int part = 0, int parts = 1) {
     switch (seg) {
-        case 8: return launch_hash_bw_runs<8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red);
-        case 16: return launch_hash_bw_runs<16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red);
-        case 64: return launch_hash_bw_runs<64>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red);
-        default: return launch_hash_bw_runs<32>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red);
+        case 8: return launch_hash_bw_runs<8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+        case 16: return launch_hash_bw_runs<16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+        case 64: return launch_hash_bw_runs<64>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+        default: return launch_hash_bw_runs<32>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
     }
 }
 
@@ -652,7 +660,7 @@ inline int sample_grid(int64_t n, const int32_t* n_dev) { return n_dev ? (int)mi
 }
 int arn::hash_encode_fw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
                              arn_levels_t levels, const void* table_f16, void* feat_f16, int tile_image, arn_stream_t stream,
-                             const __half* pack_wd, const __half* pack_wc, uint8_t* pack_img) {
+                             const __half* pack_wd, const __half* pack_wc, uint8_t* pack_img, int part, int parts) {
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(xyzs && table_f16 && feat_f16, "null pointer");
@@ -660,9 +668,10 @@ int arn::hash_encode_fw_impl(const float* xyzs, int64_t n, const int32_t* n_dev,
     if (int e = make_levels(levels, t)) return e;
     if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
     ARN_REQUIRE(((uintptr_t)feat_f16 & 15) == 0, "feat must be 16-byte aligned");
-    dim3 grid(max(sample_grid(n, n_dev), pack_img ? ceil_div(kWimgChunks, 256) : 1), ARN_N_LEVELS / 8);
+    ARN_REQUIRE(parts >= 1 && part >= 0 && part < parts, "bad part");
+    dim3 grid(max(max(sample_grid(n, n_dev) / parts, 1), pack_img ? ceil_div(kWimgChunks, 256) : 1), ARN_N_LEVELS / 8);
     ARN_LAUNCH("hash_encode_fw_kernel", (cudaStream_t)stream, hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, n_dev, b, t, (const __half2*)table_f16, (__half2*)feat_f16, tile_image,
-                                                                                                                           pack_wd, pack_wc, pack_img));
+                                                                                                                           pack_wd, pack_wc, pack_img, part, parts));
     return check_launch("hash_encode_fw");
 }
 extern "C" ARN_API int arn_hash_encode_fw_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
@@ -686,7 +695,7 @@ extern "C" ARN_API int arn_hash_encode_bw_dyn(const float* xyzs, int64_t n, cons
 }
 int arn::hash_encode_bw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
                              arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad,
-                             float* dL_dxyzs, int tile_image, arn_stream_t stream, WgradReduce red) {
+                             float* dL_dxyzs, int tile_image, arn_stream_t stream, WgradReduce red, int part, int parts) {
     ARN_REQUIRE(n >= 0, "bad size");
     if (n == 0) return ARN_OK;
     ARN_REQUIRE(xyzs && dfeat, "null pointer");
@@ -697,8 +706,9 @@ int arn::hash_encode_bw_impl(const float* xyzs, int64_t n, const int32_t* n_dev,
     if (table_grad) {
         const int mode = tunable(kTunHashBwMode);  // 0: one reduction per (sample, level, corner); else: run-aggregating, segment length
         if (mode) {
-            if (int e = hash_bw_runs(mode, xyzs, n, n_dev, b, t, dfeat, table_grad, 0, ARN_N_LEVELS, tile_image, st, red)) return e;
+            if (int e = hash_bw_runs(mode, xyzs, n, n_dev, b, t, dfeat, table_grad, 0, ARN_N_LEVELS, tile_image, st, red, part, parts)) return e;
         } else {
+            ARN_REQUIRE(parts == 1, "the per-sample backward kernel is not pipelined");
             dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS);
             ARN_LAUNCH("hash_encode_bw_kernel", st, hash_encode_bw_kernel<<<grid, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, tile_image));
             if (int e = check_launch("hash_encode_bw")) return e;

@@ -30,10 +30,16 @@ int make_box(const float* mn, const float* mx, Aabb& b);
 struct WgradReduce { const float* wpart; int n_slabs; int with_rgb; float* dWd; float* dWc; };
 int hash_encode_fw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
                         arn_levels_t levels, const void* table_f16, void* feat_f16, int tile_image, arn_stream_t stream,
-                        const __half* pack_wd = nullptr, const __half* pack_wc = nullptr, uint8_t* pack_img = nullptr);
+                        const __half* pack_wd = nullptr, const __half* pack_wc = nullptr, uint8_t* pack_img = nullptr,
+                        int part = 0, int parts = 1);
 int hash_encode_bw_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
                         arn_levels_t levels, const void* table_f16, const float* dfeat, float* table_grad, float* dL_dxyzs,
-                        int tile_image, arn_stream_t stream, WgradReduce red = WgradReduce{nullptr, 0, 0, nullptr, nullptr});
+                        int tile_image, arn_stream_t stream, WgradReduce red = WgradReduce{nullptr, 0, 0, nullptr, nullptr},
+                        int part = 0, int parts = 1);
+// `part`/`parts`: the call covers one of `parts` consecutive ranges of 128-sample tiles (pipelined field evaluation).
+// Side stream + event pool of the calling device for that pipelining (arn_core.cu); events are reused call after call.
+struct PipeStreams { cudaStream_t side; cudaEvent_t fork, join, ev[8]; };
+int pipe_streams(PipeStreams** out);
 // arn_field_bw_tc_dyn with the option of reusing the weight image already in ws.wimg (arn_mlp_tc.cu)
 int field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
                      arn_levels_t levels, const void* params_xyz_f16, const void* params_rgb_f16, int rgb_act, arn_field_ws_t ws,

@@ -50,6 +50,15 @@ __device__ __forceinline__ void epilogue_row_f16(uint32_t taddr, uint32_t* out) 
     }
 }
 
+// number of pipelined tile ranges of a field evaluation over (up to) n samples: "pipeline_parts" (arn_set_tunable; default 1:
+// on B200 the overlap of the L2-bound hash kernels with the MLP kernels loses to the fixed cost every extra persistent
+// launch pays -- TMEM allocation, weight image, the 40 KB weight-gradient slab per CTA); 1 for small calls in any case
+inline int pipeline_parts(int64_t n) {
+    const int want = tunable(kTunPipelineParts);
+    if (want <= 1 || n < 64 * 1024) return 1;
+    return want > 8 ? 8 : want;
+}
+
 constexpr int kFwSmemTile32 = 128 * 64;    // 128 rows x 32 halves
 constexpr int kFwSmemTile64 = 128 * 128;   // 128 rows x 64 halves
 // shared-memory map of the forward (offsets from the 1024-aligned base)
@@ -61,7 +70,7 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
                                                               const int32_t* __restrict__ n_dev, const uint8_t* __restrict__ wimg, int rgb_act, int with_rgb,
                                                               __half* __restrict__ hid, float* __restrict__ h, float* __restrict__ sigmas,
                                                               __half* __restrict__ in32, __half* __restrict__ hid1, __half* __restrict__ hid2,
-                                                              float* __restrict__ rgbs) {
+                                                              float* __restrict__ rgbs, int part, int parts) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[4];
     __shared__ uint32_t tmem_slot;
@@ -77,10 +86,14 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
     fence_before_sync(); __syncthreads(); fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const uint32_t wbytes = with_rgb ? kWimgBytes : kWimgC1;
-    const int64_t n_tiles = (n + 127) / 128;
+    // this launch owns the tiles [t_begin, n_tiles) of the sample list (one of `parts` consecutive ranges: the host pipelines
+    // the hash-grid forward of range p+1 on a second stream under the MLP of range p)
+    const int64_t n_tiles_all = (n + 127) / 128;
+    const int64_t t_begin = n_tiles_all * part / parts, n_tiles = n_tiles_all * (part + 1) / parts;
+    const int64_t tile0 = t_begin + blockIdx.x;
     if (tid == 0) {
         mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w);
-        if (blockIdx.x < n_tiles) { mbar_expect_tx(bar_f0, kFwSmemTile32); bulk_g2s(base + kFwF0, feat + (int64_t)blockIdx.x * 128 * 32, kFwSmemTile32, bar_f0); }
+        if (tile0 < n_tiles) { mbar_expect_tx(bar_f0, kFwSmemTile32); bulk_g2s(base + kFwF0, feat + tile0 * 128 * 32, kFwSmemTile32, bar_f0); }
     }
     mbar_wait(bar_w, 0);
 
@@ -122,9 +135,9 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
         const bool ok = with_rgb && t < n_tiles && i < n;
         dr[0] = ok ? dirs[3 * i] : 1.0f; dr[1] = ok ? dirs[3 * i + 1] : 0.0f; dr[2] = ok ? dirs[3 * i + 2] : 0.0f;
     };
-    fetch_dir(blockIdx.x);
+    fetch_dir(tile0);
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+    for (int64_t tile = tile0; tile < n_tiles; tile += gridDim.x, it++) {
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
         const int buf = it & 1;
@@ -243,20 +256,38 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
     if (with_rgb) ARN_REQUIRE(params_rgb_f16 && rgbs && (!ws.hid || (ws.in32 && ws.hid1 && ws.hid2)), "null pointer (colour branch)");
     cudaStream_t st = (cudaStream_t)stream;
     const __half* pxyz = (const __half*)params_xyz_f16;
-    // the weight image is packed by the first blocks of the hash-grid forward (no launch of its own)
-    if (int e = hash_encode_fw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, /*tile_image=*/1, stream,
-                                    pxyz, (const __half*)params_rgb_f16, (uint8_t*)ws.wimg)) return e;
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0; ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
     }
+    // Pipelined over `parts` consecutive ranges of tiles: the hash-grid forward (gathers out of L2) of range p+1 runs on
+    // a second stream under the MLP (tensor core + HBM stores) of range p -- the two kernels stress different units.
     const int64_t n_tiles = (n + 127) / 128;
-    const int grid = (int)(n_tiles < (int64_t)n_sm * 2 ? n_tiles : (int64_t)n_sm * 2);
-    ARN_LAUNCH("field_mlp_fw_tc_kernel", st, field_mlp_fw_tc_kernel<<<grid, 128, kFwSmemBytes, st>>>(
-        (const __half*)ws.feat, dirs, n, n_dev, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, (__half*)ws.hid, ws.h, sigmas,
-        (__half*)ws.in32, (__half*)ws.hid1, (__half*)ws.hid2, rgbs));
-    return check_launch("field_mlp_fw_tc");
+    const int parts = pipeline_parts(n);
+    const int grid = (int)max((int64_t)1, min((int64_t)n_sm * 2, (n_tiles + parts - 1) / parts));
+    PipeStreams* ps = nullptr;
+    if (parts > 1) {
+        if (int e = pipe_streams(&ps)) return e;
+        ARN_CUDA(cudaEventRecord(ps->fork, st));
+        ARN_CUDA(cudaStreamWaitEvent(ps->side, ps->fork, 0));
+    }
+    for (int p = 0; p < parts; p++) {
+        cudaStream_t hs = parts > 1 ? ps->side : st;
+        // the weight image is packed by the first blocks of the first hash-grid launch (no launch of its own)
+        if (int e = hash_encode_fw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, ws.feat, /*tile_image=*/1, hs,
+                                        p == 0 ? pxyz : nullptr, p == 0 ? (const __half*)params_rgb_f16 : nullptr, p == 0 ? (uint8_t*)ws.wimg : nullptr,
+                                        p, parts)) return e;
+        if (parts > 1) ARN_CUDA(cudaEventRecord(ps->ev[p], hs));
+    }
+    for (int p = 0; p < parts; p++) {
+        if (parts > 1) ARN_CUDA(cudaStreamWaitEvent(st, ps->ev[p], 0));
+        ARN_LAUNCH("field_mlp_fw_tc_kernel", st, field_mlp_fw_tc_kernel<<<grid, 128, kFwSmemBytes, st>>>(
+            (const __half*)ws.feat, dirs, n, n_dev, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, (__half*)ws.hid, ws.h, sigmas,
+            (__half*)ws.in32, (__half*)ws.hid1, (__half*)ws.hid2, rgbs, p, parts));
+        if (int e = check_launch("field_mlp_fw_tc")) return e;
+    }
+    return ARN_OK;
 }
 
 namespace arn {
@@ -304,7 +335,8 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                                                               const __half* __restrict__ feat, const __half* __restrict__ hid,
                                                               const __half* __restrict__ in32, const __half* __restrict__ hid1,
                                                               const __half* __restrict__ hid2, const uint8_t* __restrict__ wimg, int rgb_act,
-                                                              int with_rgb, float loss_scale, float exp_hi, float* __restrict__ dfeat, float* __restrict__ wpart) {
+                                                              int with_rgb, float loss_scale, float exp_hi, float* __restrict__ dfeat, float* __restrict__ wpart,
+                                                              int part, int parts, int slab0) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[5];
     __shared__ uint32_t tmem_slot;
@@ -325,12 +357,15 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     fence_before_sync(); __syncthreads(); fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const uint32_t wbytes = with_rgb ? kWimgBytes : kWimgC1;
-    const int64_t n_tiles = (n + 127) / 128;
+    // tiles [t_begin, n_tiles) of the sample list (see the forward kernel)
+    const int64_t n_tiles_all = (n + 127) / 128;
+    const int64_t t_begin = n_tiles_all * part / parts, n_tiles = n_tiles_all * (part + 1) / parts;
+    const int64_t tile0 = t_begin + blockIdx.x;
 
     // ---- activation-tile stream: load j of this CTA = tile (j / L) of its tile sequence, kind (j % L); slot j % 3
     const int L = with_rgb ? 5 : 2;
     auto issue_load = [&](int64_t j) {  // thread 0 only
-        const int64_t t = (int64_t)blockIdx.x + (j / L) * gridDim.x;
+        const int64_t t = tile0 + (j / L) * gridDim.x;
         if (t >= n_tiles) return;
         const int kind = with_rgb ? (int)(j % 5) : 3 + (int)(j % 2);
         const __half* src; uint32_t bytes;
@@ -411,9 +446,9 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
         pre_ds = (ok && dL_dsigmas) ? dL_dsigmas[i] : 0.0f;
         pre_sig = ok ? sigmas[i] : 1.0f;
     };
-    fetch_scalars(blockIdx.x);
+    fetch_scalars(tile0);
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = tile0; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
         float tcol[16];  // scaled dL/dh from the colour branch
@@ -489,7 +524,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     // 10240 addresses with atomics serialised in L2 and cost 28 % of this kernel; the slab sum is also deterministic.)
     fence_before_sync(); __syncthreads(); fence_after_sync();
     {
-        float* slab = wpart + (size_t)blockIdx.x * kWgradFloats;
+        float* slab = wpart + (size_t)(slab0 + blockIdx.x) * kWgradFloats;
         const int m = 16 * warp + lane;
         const bool own = lane < 16;
         auto flush = [&](uint32_t col, int ncols, float* dst, int ld_row, int ld_col, bool live) {
@@ -570,22 +605,42 @@ int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, co
         int dev = 0; ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         ARN_CUDA(cudaFuncSetAttribute(arn::field_mlp_bw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, arn::kBwSmemBytes));
     }
+    // Pipelined like the forward: the hash-grid backward (L2 reductions) of range p runs on a second stream under the MLP
+    // backward (tensor core + HBM loads) of range p+1.  Every MLP launch writes its own block of weight-gradient slabs;
+    // the slab sum rides in the LAST hash-grid launch (run-aggregating form), otherwise it is launched on its own.
     const int64_t n_tiles = (n + 127) / 128;
-    int grid = (int)(n_tiles < (int64_t)n_sm * 2 ? n_tiles : (int64_t)n_sm * 2);
-    if (grid > arn::kMaxBwCtas) grid = arn::kMaxBwCtas;
+    const bool runs = tunable(kTunHashBwMode) != 0;
+    const int parts = (dL_dxyzs || !runs) ? 1 : pipeline_parts(n);
+    int grid = (int)max((int64_t)1, min((int64_t)n_sm * 2, (n_tiles + parts - 1) / parts));
+    if (grid * parts > arn::kMaxBwCtas) grid = arn::kMaxBwCtas / parts;
     float* wpart = reinterpret_cast<float*>((uint8_t*)ws.wimg + arn::kWimgBytes);  // slabs follow the weight image in the scratch
-    ARN_LAUNCH("field_mlp_bw_tc_kernel", st, arn::field_mlp_bw_tc_kernel<<<grid, 128, arn::kBwSmemBytes, st>>>(
-        n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, sigmas, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32,
-        (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, expf(15.0f),
-        dfeat_scratch, wpart));
-    if (int e = check_launch("field_mlp_bw_tc")) return e;
-    // the slab sum rides in extra blocks of the hash-grid backward (run-aggregating form); otherwise it is launched here
-    WgradReduce red{wpart, grid, with_rgb ? 1 : 0, grad_params_xyz, grad_params_rgb};
-    if (!tunable(kTunHashBwMode)) {
+    PipeStreams* ps = nullptr;
+    if (parts > 1) { if (int e = pipe_streams(&ps)) return e; }
+    for (int p = 0; p < parts; p++) {
+        ARN_LAUNCH("field_mlp_bw_tc_kernel", st, arn::field_mlp_bw_tc_kernel<<<grid, 128, arn::kBwSmemBytes, st>>>(
+            n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, sigmas, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32,
+            (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, expf(15.0f),
+            dfeat_scratch, wpart, p, parts, p * grid));
+        if (int e = check_launch("field_mlp_bw_tc")) return e;
+        if (parts > 1) ARN_CUDA(cudaEventRecord(ps->ev[p], st));
+    }
+    WgradReduce red{wpart, grid * parts, with_rgb ? 1 : 0, grad_params_xyz, grad_params_rgb};
+    if (!runs) {
         ARN_LAUNCH("wgrad_reduce_kernel", st, arn::wgrad_reduce_kernel<<<arn::kWgradFloats / 32, 256, 0, st>>>(red.wpart, red.n_slabs, red.with_rgb, red.dWd, red.dWc));
         if (int e = check_launch("wgrad_reduce")) return e;
         red.wpart = nullptr;
     }
-    return hash_encode_bw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
-                               grad_params_xyz + ARN_DENSITY_MLP_PARAMS, dL_dxyzs, /*tile_image=*/1, stream, red);
+    const WgradReduce none{nullptr, 0, 0, nullptr, nullptr};
+    for (int p = 0; p < parts; p++) {
+        cudaStream_t hs = parts > 1 ? ps->side : st;
+        if (parts > 1) ARN_CUDA(cudaStreamWaitEvent(hs, ps->ev[p], 0));
+        if (int e = hash_encode_bw_impl(xyzs, n, n_dev, xyz_min_host, xyz_max_host, levels, pxyz + ARN_DENSITY_MLP_PARAMS, dfeat_scratch,
+                                        grad_params_xyz + ARN_DENSITY_MLP_PARAMS, p == parts - 1 ? dL_dxyzs : nullptr, /*tile_image=*/1, hs,
+                                        p == parts - 1 ? red : none, p, parts)) return e;
+    }
+    if (parts > 1) {
+        ARN_CUDA(cudaEventRecord(ps->join, ps->side));
+        ARN_CUDA(cudaStreamWaitEvent(st, ps->join, 0));
+    }
+    return ARN_OK;
 }

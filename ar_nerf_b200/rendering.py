@@ -149,6 +149,7 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
         samples += N_samples
         cfg.alive, cfg.alive_out = w['alive'][cur].data_ptr(), w['alive'][cur ^ 1].data_ptr()
         cfg.n_alive, cfg.n_samples = N_alive, N_samples
+        cfg.capacity = N_alive * N_samples  # this iteration's bound (<= the workspace's): small iterations skip the pipelining
         call("arn_render_test_iter", C.byref(cfg), s_)
         n_valid, _, n_keep, _ = w['counts'].tolist()  # the one host read of the iteration
         if n_valid == 0:

@@ -42,7 +42,9 @@ int64_t arn_launch_count(void);
 /* Kernel-variant switch for A/B measurements and for the tests that hold the variants to each other; every variant of
  * a kernel computes the same results.  Names: "march_warp" (1 = warp-per-ray window march, 0 = thread-per-ray loop),
  * "hash_bw_mode" (8/16/32/64 = run-aggregating hash-grid backward with that segment length, 0 = one reduction per
- * sample and corner), "adam_vec" (1 = 128-bit Adam kernel). */
+ * sample and corner), "adam_vec" (1 = 128-bit Adam kernel), "pipeline_parts" (field evaluations of >= 64 K samples are split
+ * into this many consecutive tile ranges, hash-grid and MLP kernels of neighbouring ranges overlapped on two streams; default
+ * 1 = off: measured on B200 the overlap loses to the per-launch fixed costs, 0.384 / 0.409 / 0.469 ms per step at 1 / 2 / 3). */
 int arn_set_tunable(const char* name, int value);
 int arn_profile_enable(int on);
 int arn_profile_report(char* buf_host, int capacity);
@@ -202,7 +204,7 @@ typedef struct {
  * only.  For a density-only evaluation (NGP.density) dirs, in32, hid1, hid2, rgbs and params_rgb_f16 are NULL.
  * Inference (no backward will follow): hid = in32 = hid1 = hid2 = NULL skips every activation store of the forward
  * (tensor-core path); h = NULL skips the h output as well. */
-#define ARN_FIELD_SCRATCH_SLABS 512
+#define ARN_FIELD_SCRATCH_SLABS 1280
 #define ARN_FIELD_SCRATCH_BYTES (20480 + ARN_FIELD_SCRATCH_SLABS * 10240 * 4)
 typedef struct {
     void* feat; void* hid; float* h; void* in32; void* hid1; void* hid2;

@@ -592,6 +592,30 @@ def test_prefetched_march_is_the_same_step(kind, w1, w3):
     assert torch.equal(model_a.density_bitfield, model_b.density_bitfield)
 
 
+def test_pipelined_field_evaluation_is_the_same_step(w1):
+    """pipeline_parts > 1 (hash-grid and MLP kernels of consecutive tile ranges overlapped on two streams) computes the same
+    forward and the same gradients as the plain sequence."""
+    from ar_nerf_b200 import _lib
+    from ar_nerf_b200.trainer import NGPTrainer
+    w = w1
+    losses, grads = [], []
+    for parts in (1, 3):
+        model, *_ = _field_setup(w.scale, 8, 31, table_amp=1.0)
+        w.install(model)
+        tr = NGPTrainer(model)
+        ro, rd, target, noise = [T(t) for t in w.train_batch(9, 8192)]
+        try:
+            _lib.set_tunable("pipeline_parts", parts)
+            loss, res = tr._fused_fwbw(ro, rd, target, noise)
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_tunable("pipeline_parts", 1)
+        assert int(res["rm_samples"]) > 64 * 1024  # large enough for the split to be taken
+        losses.append(float(loss)); grads.append((N(model.xyz_encoder.params.grad), N(model.rgb_net.params.grad)))
+    assert abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[0])
+    assert_rel(grads[1][0], grads[0][0], rtol=5e-5, floor=1.0, what="xyz grad"); assert_rel(grads[1][1], grads[0][1], rtol=5e-5, floor=1.0, what="rgb grad")
+
+
 def test_nerf_loss_kernel_vs_autograd():
     from ar_nerf_b200 import _lib
     from ar_nerf_b200.losses import NeRFLoss
