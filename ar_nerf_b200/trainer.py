@@ -257,21 +257,24 @@ class NGPTrainer:
         prefetch = None
         if next_rays is not None and not next_is_update:
             n_ro, n_rd = next_rays[0], next_rays[1]
-            n_noise = next_rays[2] if len(next_rays) > 2 else None
             if n_ro.is_contiguous() and n_rd.is_contiguous() and n_ro.dtype == torch.float32 and n_rd.dtype == torch.float32 and n_ro.shape[0] == R:
-                if n_noise is None:
-                    n_noise = torch.rand(R, device=dev)  # next in the RNG stream, exactly where the next step would draw it
-                prefetch = (n_ro, n_rd, n_noise)
+                prefetch = (n_ro, n_rd, next_rays[2] if len(next_rays) > 2 else None)
         self._keep_target = rgb_target.contiguous().float()
         if prefetch is not None:
-            w.marched.record(main)         # from here on the shared march scratch is free and the prefetch inputs exist
+            w.marched.record(main)         # from here on the shared march scratch is free and the next batch's rays exist
         call("arn_train_fwbw_marched", C.byref(self._cfg(ms, self._keep_target)), main_h)
         if prefetch is not None:
             # geometry of the next batch, concurrently with this batch's field / compositing / optimizer kernels: it reads the
             # rays and the occupancy bits only.  (Skipped when the next step refreshes the occupancy grid first.)
             nxt = w.march[w.cur ^ 1]
             w.side.wait_event(w.marched)
-            self._march(nxt, *prefetch, w.side.cuda_stream)
+            n_ro, n_rd, n_noise = prefetch
+            if n_noise is None:
+                # next in the RNG stream, exactly where the next step would draw it; generated on the side stream (the Philox
+                # offset advances on the host, the values do not depend on the stream) so that nothing queues behind this step
+                with torch.cuda.stream(w.side):
+                    n_noise = torch.rand(R, device=dev)
+            self._march(nxt, n_ro, n_rd, n_noise, w.side.cuda_stream)
             nxt.ready.record(w.side)
             nxt.pending = True
             nxt.grid_epoch = self._grid_epoch

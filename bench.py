@@ -204,14 +204,19 @@ def run_ours(args):
 
     staged = {}
 
-    def step_e2e(i):
-        # every step copies ONE batch host -> device (the next one, so that its march can overlap this step) and reads the loss back
+    def stage(i):
         if i not in staged:
             staged[i] = [t.to(dev, non_blocking=True) for t in pinned[i % N_BATCHES]]
-        staged[i + 1] = [t.to(dev, non_blocking=True) for t in pinned[(i + 1) % N_BATCHES]]
+
+    def step_e2e(i):
+        # Every step copies ONE batch host -> device and reads the loss back.  The input pipeline runs two batches ahead (the
+        # batch copied during step i is trained at step i+2 and marched during step i+1), and the copy is enqueued AFTER the
+        # step's kernels so that the GPU is not left idle while the host queues it.
+        stage(i); stage(i + 1)                       # no-ops in steady state
         ro, rd, tgt = staged.pop(i)
-        loss, _ = trainer.train_step(ro, rd, tgt, next_rays=tuple(staged[i + 1][:2]))
-        return float(loss.item())  # device -> host read of the step's result
+        loss, _ = trainer.train_step(ro, rd, tgt, next_rays=None if NO_PREFETCH else tuple(staged[i + 1][:2]))
+        staged.pop(i + 2, None); stage(i + 2)        # this step's host -> device copy
+        return float(loss.item())                    # device -> host read of the step's result
 
     # untimed: the first steps carry one-time costs (CUDA module loading, allocator growth, the first occupancy refresh);
     # at least two refresh intervals are run before the timed region whatever --warmup says, and reported as `warmup`
