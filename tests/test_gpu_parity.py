@@ -447,7 +447,7 @@ def test_hash_backward_variants_agree(kind, w1, w3, vren):
             _lib.call("arn_hash_encode_bw", xyzs.data_ptr(), n, mn, mx, geo.c_levels, None, dfeat.data_ptr(), tg.data_ptr(), None, _lib.stream())
             res[mode] = N(tg)
     finally:
-        _lib.set_tunable("hash_bw_mode", 32)
+        _lib.set_tunable("hash_bw_mode", 16)
     x01 = (N(xyzs) - np.float32(-w.scale)) / (np.float32(w.scale) - np.float32(-w.scale))
     o_geo = oracle.HashGeometry(per_level_scale=geo.per_level_scale)
     o_tg, _ = oracle.hash_encode_bw(x01.astype(np.float32), o_geo, np.zeros(geo.total * 2, np.float16), N(dfeat))

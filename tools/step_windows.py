@@ -11,6 +11,8 @@ tr = NGPTrainer(model)
 B = [[t.to(dev) for t in w.train_batch(i)] for i in range(16)]
 pf = os.environ.get("PF", "1") == "1"
 from ar_nerf_b200 import _lib
+if os.environ.get("HBW"):
+    _lib.set_tunable("hash_bw_mode", int(os.environ["HBW"]))
 if os.environ.get("PARTS"):
     _lib.set_tunable("pipeline_parts", int(os.environ["PARTS"]))
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
