@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
                                                                  const int64_t* __restrict__ rays_a, int64_t n_rays, float T_thr,
                                                                  int64_t* __restrict__ total_samples, float* __restrict__ opacity,
                                                                  float* __restrict__ depth, float* __restrict__ rgb, float* __restrict__ ws,
-                                                                 const LossEpilogue L) {
+                                                                 const LossEpilogue L, int64_t n_samples) {
     __shared__ float s_loss[8];
     if (LOSS && threadIdx.x < 8) s_loss[threadIdx.x] = 0.0f;
     if (LOSS) __syncthreads();
@@ -596,7 +596,11 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
     const bool live = n < n_rays;
     if (!LOSS && !live) return;
     int64_t ray_idx = 0, start = 0; int N = 0;
-    if (live) { ray_idx = rays_a[3 * n]; start = rays_a[3 * n + 1]; N = (int)rays_a[3 * n + 2]; }
+    if (live) {
+        ray_idx = rays_a[3 * n]; start = rays_a[3 * n + 1]; N = (int)rays_a[3 * n + 2];
+        // never read past the sample buffers (a caller-chosen sample capacity smaller than the march: the tail is dropped)
+        N = (int)max((int64_t)0, min((int64_t)N, n_samples - start));
+    }
     float T = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
     int64_t samples = N; bool done = false;
     int base = 0;
@@ -654,11 +658,12 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(const float* __
                                                                  const float* __restrict__ ts, const int64_t* __restrict__ rays_a,
                                                                  const float* __restrict__ opacity, const float* __restrict__ depth,
                                                                  const float* __restrict__ rgb, int64_t n_rays, float T_thr,
-                                                                 float* __restrict__ dL_dsigmas, float* __restrict__ dL_drgbs) {
+                                                                 float* __restrict__ dL_dsigmas, float* __restrict__ dL_drgbs, int64_t n_samples) {
     const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= n_rays) return;
-    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1]; const int N = (int)rays_a[3 * n + 2];
+    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1];
+    const int N = (int)max((int64_t)0, min(rays_a[3 * n + 2], n_samples - start));  // same clamp as the forward
     if (N <= 0) return;
     const float R = rgb[3 * ray_idx], G = rgb[3 * ray_idx + 1], B = rgb[3 * ray_idx + 2];
     const float O = opacity[ray_idx], D = depth[ray_idx];
@@ -1073,7 +1078,7 @@ extern "C" ARN_API int arn_composite_train_fw(const float* sigmas, const float* 
     ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "null pointer");
     ARN_REQUIRE(n_samples == 0 || (sigmas && rgbs && deltas && ts && ws), "null pointer");
     ARN_LAUNCH("composite_train_fw_kernel", (cudaStream_t)stream, composite_train_fw_kernel<false><<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
-                                                                                          total_samples, opacity, depth, rgb, ws, LossEpilogue{}));
+                                                                                          total_samples, opacity, depth, rgb, ws, LossEpilogue{}, n_samples));
     return check_launch("composite_train_fw");
 }
 
@@ -1092,7 +1097,7 @@ extern "C" ARN_API int arn_composite_train_fw_loss(const float* sigmas, const fl
     LossEpilogue L{target, {bg_host[0], bg_host[1], bg_host[2]}, lambda_opacity, lambda_depth, grid_scale, grad_scale, rgb_out, dL_drgb, dL_dopacity,
                    dL_ddepth, loss_out};
     ARN_LAUNCH("composite_train_fw_loss_kernel", st, composite_train_fw_kernel<true><<<ceil_div(n_rays * 32, 256), 256, 0, st>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
-                                                                                          total_samples, opacity, depth, rgb, ws, L));
+                                                                                          total_samples, opacity, depth, rgb, ws, L, n_samples));
     return check_launch("composite_train_fw_loss");
 }
 
@@ -1107,7 +1112,7 @@ extern "C" ARN_API int arn_composite_train_bw(const float* dL_dopacity, const fl
                 "null pointer");
     ARN_LAUNCH("composite_train_bw_kernel", (cudaStream_t)stream, composite_train_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws,
                                                                                           deltas, ts, rays_a, opacity, depth, rgb, n_rays,
-                                                                                          T_threshold, dL_dsigmas, dL_drgbs));
+                                                                                          T_threshold, dL_dsigmas, dL_drgbs, n_samples));
     return check_launch("composite_train_bw");
 }
 

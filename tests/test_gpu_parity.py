@@ -616,6 +616,30 @@ def test_pipelined_field_evaluation_is_the_same_step(w1):
     assert_rel(grads[1][0], grads[0][0], rtol=5e-5, floor=1.0, what="xyz grad"); assert_rel(grads[1][1], grads[0][1], rtol=5e-5, floor=1.0, what="rgb grad")
 
 
+def test_fused_step_edge_cases(w1):
+    """Batches that march nothing (every ray misses the box), one-ray batches and a sample capacity smaller than the march
+    (the tail of the sample list is dropped, nothing is read or written out of bounds) go through the fused step."""
+    from ar_nerf_b200.trainer import NGPTrainer
+    w = w1
+    model, *_ = _field_setup(w.scale, 8, 31, table_amp=1.0)
+    w.install(model)
+    tr = NGPTrainer(model)
+    ro, rd, target, noise = [T(t) for t in w.train_batch(3, 512)]
+    away = ro + 10.0 * torch.sign(ro)  # origins far outside, looking further away: no ray hits the scene box
+    loss, res = tr.train_step(away.contiguous(), (ro / ro.norm(dim=1, keepdim=True)).contiguous(), target, noise=noise, update_grid=False)
+    assert int(res["rm_samples"]) == 0 and torch.isfinite(loss) and float(res["opacity"].abs().max()) == 0.0
+    assert torch.equal(res["rgb"], torch.ones_like(res["rgb"]))  # white background (exp_step_factor == 0)
+    assert torch.isfinite(model.xyz_encoder.params).all()
+    loss1, res1 = tr.train_step(ro[:1].contiguous(), rd[:1].contiguous(), target[:1].contiguous(), noise=noise[:1].contiguous(), update_grid=False)
+    assert torch.isfinite(loss1)
+    # capacity overflow: 4096 rays march ~120 k samples, the workspace holds 20 k
+    small = NGPTrainer(model, sample_capacity=20_000)
+    ro, rd, target, noise = [T(t) for t in w.train_batch(5, 4096)]
+    loss2, res2 = small.train_step(ro, rd, target, noise=noise, update_grid=False)
+    assert int(res2["rm_samples"]) > small._ws.capacity
+    assert torch.isfinite(loss2) and torch.isfinite(model.xyz_encoder.params).all() and torch.isfinite(res2["rgb"]).all()
+
+
 def test_nerf_loss_kernel_vs_autograd():
     from ar_nerf_b200 import _lib
     from ar_nerf_b200.losses import NeRFLoss
