@@ -47,6 +47,23 @@ __global__ void p2p_wait_kernel(const unsigned long long* __restrict__ flags, in
     __threadfence_system();
 }
 
+// signal + wait in one launch (the pair always comes together on the training path)
+__global__ void p2p_barrier_kernel(PeerFlags peers, const unsigned long long* __restrict__ flags, int n_ranks, int rank, int slot, unsigned long long value) {
+    __threadfence_system();
+    const int r = threadIdx.x;
+    if (r < n_ranks) {
+        volatile unsigned long long* f = peers.p[r] + slot * kMaxRanks + rank;
+        *f = value;
+        const volatile unsigned long long* mine = flags + slot * kMaxRanks + r;
+        const long long t0 = clock64();
+        while (*mine < value) {
+            __nanosleep(100);
+            if (clock64() - t0 > (long long)8e9) __trap();
+        }
+    }
+    __threadfence_system();
+}
+
 __device__ __forceinline__ uint2 pack_half4_(const float4& a) {
     const __half2 lo = __floats2half2_rn(a.x, a.y), hi = __floats2half2_rn(a.z, a.w);
     uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
@@ -138,6 +155,14 @@ extern "C" ARN_API int arn_p2p_wait(const void* my_flags, int n_ranks, int slot,
     ARN_REQUIRE(my_flags && n_ranks >= 1 && n_ranks <= kMaxRanks && slot >= 0 && slot < ARN_P2P_FLAG_SLOTS, "bad arguments");
     ARN_LAUNCH("p2p_wait_kernel", (cudaStream_t)stream, p2p_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)my_flags, n_ranks, slot, (unsigned long long)value));
     return check_launch("p2p_wait");
+}
+
+extern "C" ARN_API int arn_p2p_barrier(void* const* peer_flags_host, const void* my_flags, int n_ranks, int rank, int slot, uint64_t value, arn_stream_t stream) {
+    ARN_REQUIRE(peer_flags_host && my_flags && n_ranks >= 1 && n_ranks <= kMaxRanks && rank >= 0 && rank < n_ranks && slot >= 0 && slot < ARN_P2P_FLAG_SLOTS, "bad arguments");
+    PeerFlags pf{};
+    for (int r = 0; r < n_ranks; r++) { ARN_REQUIRE(peer_flags_host[r], "null peer flag array"); pf.p[r] = (unsigned long long*)peer_flags_host[r]; }
+    ARN_LAUNCH("p2p_barrier_kernel", (cudaStream_t)stream, p2p_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, (const unsigned long long*)my_flags, n_ranks, rank, slot, (unsigned long long)value));
+    return check_launch("p2p_barrier");
 }
 
 extern "C" ARN_API int arn_p2p_adam_exchange(void* const* peer_grads_host, void* const* peer_p16_host, int n_ranks, int64_t lo, int64_t count,

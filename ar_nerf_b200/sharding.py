@@ -173,11 +173,10 @@ class PeerExchange:
     def step(self, p_flat, m, v, hyper, step_id, cuda_stream):
         """hyper = (lr, beta1, beta2, eps, step, inv_grad_scale).  Gradients of every rank must be complete on this stream."""
         from ._lib import call, ptr
-        call("arn_p2p_signal", self.F, self.world, self.rank, 0, step_id, cuda_stream)   # my gradients are final
-        call("arn_p2p_wait", self.f_ptr, self.world, 0, step_id, cuda_stream)                                  # ... and everyone's
+        call("arn_p2p_barrier", self.F, self.f_ptr, self.world, self.rank, 0, step_id, cuda_stream)   # my gradients are final ... and everyone's
         if self.cnt > 0:
             call("arn_p2p_adam_exchange", self.G, self.H, self.world, self.lo, self.cnt, ptr(p_flat[self.lo:self.lo + self.cnt]), ptr(m), ptr(v),
                  *hyper, cuda_stream)
-        call("arn_p2p_signal", self.F, self.world, self.rank, 1, step_id, cuda_stream)   # my fp16 slice is in every copy, I am done reading
-        call("arn_p2p_wait", self.f_ptr, self.world, 1, step_id, cuda_stream)             # my copy is complete, nobody reads my gradients any more
+        # my fp16 slice is in every copy and I am done reading ... my copy is complete, nobody reads my gradients any more
+        call("arn_p2p_barrier", self.F, self.f_ptr, self.world, self.rank, 1, step_id, cuda_stream)
         self.grad.zero_()

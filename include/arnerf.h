@@ -382,6 +382,9 @@ int arn_p2p_open(const unsigned char* handle64_host, void** ptr_host);
 int arn_p2p_close(void* ptr);
 int arn_p2p_signal(void* const* peer_flags_host, int n_ranks, int rank, int slot, uint64_t value, arn_stream_t stream);
 int arn_p2p_wait(const void* my_flags, int n_ranks, int slot, uint64_t value, arn_stream_t stream);
+/* arn_p2p_signal followed by arn_p2p_wait on the same slot and value, as one launch. */
+int arn_p2p_barrier(void* const* peer_flags_host, const void* my_flags, int n_ranks, int rank, int slot, uint64_t value,
+                    arn_stream_t stream);
 int arn_p2p_adam_exchange(void* const* peer_grads_host, void* const* peer_p16_host, int n_ranks, int64_t lo, int64_t count,
                           float* params_slice, float* exp_avg_slice, float* exp_avg_sq_slice, float lr, float beta1,
                           float beta2, float eps, int step, float inv_grad_scale, arn_stream_t stream);
