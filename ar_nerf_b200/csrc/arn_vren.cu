@@ -93,6 +93,31 @@ __global__ void __launch_bounds__(256) aabb_near_kernel(const float* __restrict_
     hits_t[r] = out;
 }
 
+// ---------------------------------------------------------------------------------------------- ray generation
+// train.py:121-126 + datasets/ray_utils.py:46-70 for one sampled batch: directions[pix_idxs] rotated by poses[img_idxs]
+// (rays_d = R d, k ascending, fp32 like the reference's batched matmul under autocast(float32)), rays_o = the camera
+// centre.  K != NULL recomputes the direction from the pixel index (ray_utils.py:33-35) instead of reading a table.
+__global__ void __launch_bounds__(256) gather_rays_kernel(const float* __restrict__ directions, const float* __restrict__ poses,
+                                                          const int64_t* __restrict__ img_idxs, int64_t img_single,
+                                                          const int64_t* __restrict__ pix_idxs, int64_t n, int width, float fx, float fy, float cx,
+                                                          float cy, float* __restrict__ rays_o, float* __restrict__ rays_d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t pix = pix_idxs[i];
+    float d[3];
+    if (directions) { d[0] = directions[3 * pix]; d[1] = directions[3 * pix + 1]; d[2] = directions[3 * pix + 2]; }
+    else {
+        const float u = (float)(pix % width), v = (float)(pix / width);
+        d[0] = __fdiv_rn(__fadd_rn(__fsub_rn(u, cx), 0.5f), fx); d[1] = __fdiv_rn(__fadd_rn(__fsub_rn(v, cy), 0.5f), fy); d[2] = 1.0f;
+    }
+    const float* P = poses + 12 * (img_idxs ? img_idxs[i] : img_single);
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        rays_d[3 * i + r] = __fmaf_rn(d[2], P[4 * r + 2], __fmaf_rn(d[1], P[4 * r + 1], __fmul_rn(d[0], P[4 * r])));
+        rays_o[3 * i + r] = P[4 * r + 3];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- grid utilities
 __global__ void __launch_bounds__(256) morton3d_kernel(const int32_t* __restrict__ coords, int64_t n, int32_t* __restrict__ indices) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -933,6 +958,19 @@ extern "C" ARN_API int arn_packbits(const void* density_grid, int grid_dtype, fl
     else if (grid_dtype == 2) ARN_LAUNCH("packbits_f64_kernel", st, packbits_f64_kernel<<<ceil_div(n_bytes, 256), 256, 0, st>>>((const double*)density_grid, threshold, density_bitfield, n_bytes));
     else { set_error("arn_packbits: grid_dtype must be 0 (f32), 1 (f16) or 2 (f64)"); return ARN_E_INVALID; }
     return check_launch("packbits");
+}
+
+extern "C" ARN_API int arn_gather_rays(const float* directions, const float* K_host, int width, const float* poses, const int64_t* img_idxs,
+                                       int64_t img_single, const int64_t* pix_idxs, int64_t n, float* rays_o, float* rays_d, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(poses && pix_idxs && rays_o && rays_d, "null pointer");
+    ARN_REQUIRE(directions || (K_host && width > 0), "either the direction table or the intrinsics + image width are needed");
+    float fx = 1.f, fy = 1.f, cx = 0.f, cy = 0.f;
+    if (!directions) { fx = K_host[0]; fy = K_host[4]; cx = K_host[2]; cy = K_host[5]; }
+    ARN_LAUNCH("gather_rays_kernel", (cudaStream_t)stream, gather_rays_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        directions, poses, img_idxs, img_single, pix_idxs, n, width, fx, fy, cx, cy, rays_o, rays_d));
+    return check_launch("gather_rays");
 }
 
 extern "C" ARN_API int arn_grid_cell_positions(const int32_t* coords, const float* rnd, int64_t n_cells, int grid_size, float s, float* xyzs,

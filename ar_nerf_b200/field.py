@@ -34,8 +34,34 @@ class HashGeometry:
         self.size = np.zeros(n_levels, np.uint32); self.offset = np.zeros(n_levels + 1, np.uint32)
         call("arn_hashgrid_geometry", n_levels, base_resolution, C.c_float(per_level_scale), log2_hashmap_size,
              self.scale.ctypes.data, self.res.ctypes.data, self.size.ctypes.data, self.offset.ctypes.data)
+        self._finish()
+
+    def _finish(self):
         self.total = int(self.offset[-1])
         self.c_levels = Levels(self.scale.ctypes.data, self.res.ctypes.data, self.size.ctypes.data, self.offset.ctypes.data)
+
+    @classmethod
+    def in_double(cls, n_levels=16, base_resolution=16, per_level_scale=1.3195079, log2_hashmap_size=19):
+        """The same rule evaluated in float64: a tiny-cuda-nn build that computes the level scales in
+        double lands just BELOW the integer where float32 lands just above it (scale 0.5, level 5: res 64 instead of 65), which
+        shifts every later offset.  Used to read checkpoints written by such a build."""
+        g = cls.__new__(cls)
+        g.n_levels, g.base_resolution = n_levels, base_resolution
+        g.per_level_scale, g.log2_hashmap_size = float(per_level_scale), log2_hashmap_size
+        g.scale = np.zeros(n_levels, np.float32); g.res = np.zeros(n_levels, np.uint32)
+        g.size = np.zeros(n_levels, np.uint32); g.offset = np.zeros(n_levels + 1, np.uint32)
+        off = 0
+        for l in range(n_levels):
+            sc = 2.0 ** (l * math.log2(per_level_scale)) * base_resolution - 1.0
+            res = int(math.ceil(sc)) + 1
+            params = min(res ** 3, 0xffffffff // 2)
+            params = (params + 7) // 8 * 8
+            params = min(params, 1 << log2_hashmap_size)
+            g.scale[l], g.res[l], g.size[l], g.offset[l] = np.float32(sc), res, params, off
+            off += params
+        g.offset[n_levels] = off
+        g._finish()
+        return g
 
 
 def _xavier_uniform_(t, fan_out, fan_in, gen):

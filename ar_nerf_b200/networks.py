@@ -53,6 +53,7 @@ class NGP(nn.Module):
         b = np.exp(np.log(2048 * scale / N_min) / (L - 1))
         print(f'GridEncoding: Nmin={N_min} b={b:.5f} F={Fdim} T=2^{log2_T} L={L}')
 
+        self._per_level_scale_f64 = float(b)
         self.geometry = HashGeometry(L, N_min, float(np.float32(b)), log2_T)
         self.xyz_encoder = NetworkWithInputEncoding(self.geometry)
         self.dir_encoder = Encoding()
@@ -74,8 +75,20 @@ class NGP(nn.Module):
             self.field_state.set_box(self.xyz_min[0].tolist(), self.xyz_max[0].tolist())
         return self._host_box
 
-    def _load_from_state_dict(self, *args, **kwargs):
-        super()._load_from_state_dict(*args, **kwargs)
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # A checkpoint written by a tiny-cuda-nn build that sized the levels in double has a different table length
+        # (5 710 032 instead of 5 722 520 entries at scale 0.5): adopt that geometry before loading.
+        key = prefix + 'xyz_encoder.params'
+        if key in state_dict and state_dict[key].numel() != self.xyz_encoder.params.numel():
+            g = self.geometry
+            alt = HashGeometry.in_double(g.n_levels, g.base_resolution, self._per_level_scale_f64, g.log2_hashmap_size)
+            if state_dict[key].numel() == 3072 + 2 * alt.total:
+                self.geometry = alt
+                self.xyz_encoder.geometry = alt
+                self.xyz_encoder.params = nn.Parameter(torch.empty(3072 + 2 * alt.total, dtype=self.xyz_encoder.params.dtype,
+                                                                   device=self.xyz_encoder.params.device))
+                self.field_state.geometry = alt
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
         self._host_box_key = None
 
     # -------------------------------------------------------------------------------------------- field

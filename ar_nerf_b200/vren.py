@@ -94,6 +94,33 @@ def packbits(density_grid, density_threshold, density_bitfield):
          ptr(density_bitfield), n_bytes, stream())
 
 
+def gather_rays(poses, img_idxs, pix_idxs, directions=None, K=None, width=None):
+    """rays_o, rays_d (n,3) of a sampled batch, on the device (train.py:121-126 + ray_utils.get_rays in one kernel).
+    poses (n_images,3,4) f32; img_idxs (n) i64 tensor or a python int ('same_image'); pix_idxs (n) i64; directions (H*W,3) f32
+    or K (3,3) + width to compute pixel-centre directions on the fly."""
+    import ctypes as C
+    check_tensor(poses, "poses", torch.float32, 3, 4); check_tensor(pix_idxs, "pix_idxs", torch.int64, 1)
+    n, dev = pix_idxs.shape[0], poses.device
+    single = 0
+    if isinstance(img_idxs, torch.Tensor):
+        check_tensor(img_idxs, "img_idxs", torch.int64, 1)
+        if img_idxs.shape[0] != n:
+            raise RuntimeError("img_idxs and pix_idxs must have the same length")
+    else:
+        single, img_idxs = int(img_idxs), None
+    k_host = None
+    if directions is not None:
+        check_tensor(directions, "directions", torch.float32, 2, 3)
+    else:
+        if K is None or width is None:
+            raise RuntimeError("gather_rays needs either directions or K and width")
+        k_host = (C.c_float * 9)(*[float(v) for v in torch.as_tensor(K).reshape(-1).tolist()])
+    rays_o = torch.empty(n, 3, dtype=torch.float32, device=dev); rays_d = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    call("arn_gather_rays", ptr(directions), k_host, int(width or 0), ptr(poses), ptr(img_idxs), single, ptr(pix_idxs), n,
+         ptr(rays_o), ptr(rays_d), stream())
+    return rays_o, rays_d
+
+
 def grid_cell_positions(coords, rnd, grid_size, s):
     """networks.py:263-267 in one kernel: (coords/(G-1)*2-1)*(s - s/G) + (rnd*2-1)*(s/G); coords (M,3) i32, rnd (M,3) f32."""
     check_tensor(coords, "coords", torch.int32, 2, 3); check_tensor(rnd, "rnd", torch.float32, 2, 3)

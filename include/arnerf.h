@@ -78,6 +78,14 @@ int arn_morton3d_invert(const int32_t* indices, int64_t n, int32_t* coords, arn_
 int arn_packbits(const void* density_grid, int grid_dtype, float threshold, uint8_t* density_bitfield,
                  int64_t n_bytes, arn_stream_t stream);
 
+/* Rays of one sampled training batch on the device: replaces `poses[img_idxs]`, `directions[pix_idxs]` and
+ * get_rays (train.py:121-126, datasets/ray_utils.py:46-70).  directions (H*W,3) f32 as get_ray_directions builds them,
+ * or NULL with K_host (3x3 row-major intrinsics, host) + width to compute ((u-cx+.5)/fx, (v-cy+.5)/fy, 1) from the pixel
+ * index (ray_utils.py:33-35).  poses (n_images,3,4) f32 camera-to-world; img_idxs (n) i64 or NULL with img_single (the
+ * 'same_image' sampling strategy, datasets/base.py:27-28); pix_idxs (n) i64.  rays_o, rays_d (n,3) f32, rays_d un-normalised. */
+int arn_gather_rays(const float* directions, const float* K_host, int width, const float* poses, const int64_t* img_idxs,
+                    int64_t img_single, const int64_t* pix_idxs, int64_t n, float* rays_o, float* rays_d, arn_stream_t stream);
+
 /* Occupancy refresh, the arithmetic of NGP.update_density_grid (networks.py:253-281) around the density evaluation:
  *   arn_grid_cell_positions : xyzs_w = (coords/(G-1)*2-1)*(s - s/G) + (rnd*2-1)*(s/G) for n_cells cells (networks.py:263-267;
  *                             rnd is the caller's torch.rand_like draw, positions are bit-identical with the torch expression);

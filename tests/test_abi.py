@@ -77,3 +77,22 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libarnerf.so")
     with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
         _lib.lib()
+
+
+def test_checkpoint_with_double_precision_geometry_loads():
+    """at scale 0.5 the float64 evaluation of the level rule gives res 64 (not 65) at level 5 and a table
+    of 5 710 032 entries; a state dict of that size is adopted together with its geometry (no GPU needed)."""
+    import torch
+    from ar_nerf_b200.field import HashGeometry
+    from ar_nerf_b200.networks import NGP
+    b64 = float(np.exp(np.log(2048 * 0.5 / 16) / 15))
+    f32, f64 = HashGeometry(per_level_scale=float(np.float32(b64))), HashGeometry.in_double(per_level_scale=b64)
+    assert f32.total == 5722520 and int(f32.res[5]) == 65
+    assert f64.total == 5710032 and int(f64.res[5]) == 64
+    assert np.array_equal(f32.res[:5], f64.res[:5]) and np.array_equal(f32.size[6:], f64.size[6:])
+    m = NGP(0.5)
+    sd = m.state_dict()
+    sd['xyz_encoder.params'] = torch.arange(3072 + 2 * f64.total, dtype=torch.float32)
+    m.load_state_dict(sd)
+    assert m.xyz_encoder.params.numel() == 3072 + 2 * f64.total and m.geometry.total == f64.total
+    assert m.field_state.geometry is m.geometry and float(m.xyz_encoder.params[-1]) == 3072 + 2 * f64.total - 1

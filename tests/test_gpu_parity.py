@@ -712,6 +712,24 @@ def test_fused_test_loop_equals_eager_loop(kind, thr, max_samples, w1, w3):
         assert torch.equal(a[k], b[k]), k
 
 
+def test_gather_rays_vs_reference_expression(vren):
+    """arn_gather_rays against poses[img_idxs] / directions[pix_idxs] / get_rays (train.py:121-126, ray_utils.py:46-70)."""
+    from ar_nerf_b200.workload import get_rays, intrinsics, look_at_poses, ray_directions
+    K = intrinsics(200, 160)
+    dirs = ray_directions(160, 200, K).to(dev()); poses = look_at_poses(12, 1.5, 3).to(dev())
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n = 5000
+    img = torch.randint(12, (n,), device=dev(), generator=g); pix = torch.randint(200 * 160, (n,), device=dev(), generator=g)
+    want_o, want_d = get_rays(dirs[pix], poses[img])
+    for kw in (dict(directions=dirs), dict(K=K, width=200)):
+        o, d = vren.gather_rays(poses, img, pix, **kw)
+        assert torch.equal(o, want_o)
+        assert_rel(N(d), N(want_d), rtol=2e-6, what="rays_d")
+    o, d = vren.gather_rays(poses, 7, pix, directions=dirs)   # 'same_image' strategy
+    want_o, want_d = get_rays(dirs[pix], poses[7])
+    assert torch.equal(o, want_o); assert_rel(N(d), N(want_d), rtol=2e-6, what="rays_d (single image)")
+
+
 def test_grid_refresh_kernels_vs_torch(vren):
     """arn_grid_cell_positions / arn_density_grid_update against the torch expressions of networks.py:263-281."""
     g = torch.Generator(device="cuda").manual_seed(7)
