@@ -107,6 +107,7 @@ SIGNATURES = {
     "arn_train_fwbw": [C.POINTER(TrainCfg), P],
     "arn_render_test_iter": [C.POINTER(TestIterCfg), P],
     "arn_train_march": [C.POINTER(TrainCfg), P],
+    "arn_train_set_fork": [I, P],
     "arn_train_fwbw_marched": [C.POINTER(TrainCfg), P],
     "arn_field_bw_simt": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
     "arn_hash_encode_fw": [P, L, P, P, Levels, P, P, P],

@@ -46,6 +46,9 @@ int field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const f
                      const float* sigmas, const float* rgbs, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale,
                      float* dfeat_scratch, float* grad_params_xyz, float* grad_params_rgb, float* dL_dxyzs, bool pack_weights, arn_stream_t stream);
 
+// arn_train_set_fork (arn_train.cu): records the caller's event on `st` if `stage` is the selected fork point
+int train_fork(int stage, cudaStream_t st);
+
 // Activation images (arn_mlp_tc.cu): position of logical 16-byte chunk c of row `row` inside the row.  Equal to the
 // shared-memory swizzle of a 1024-byte aligned tile with 64- / 128-byte rows (tc::swz<64>, tc::swz<128>); depends on
 // row % 8 only, so it is the same for the global row index and the row inside its 128-row tile.

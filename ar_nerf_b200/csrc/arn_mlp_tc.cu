@@ -624,6 +624,7 @@ int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, co
         if (int e = check_launch("field_mlp_bw_tc")) return e;
         if (parts > 1) ARN_CUDA(cudaEventRecord(ps->ev[p], st));
     }
+    if (int e = train_fork(3, st)) return e;  // arn_train_set_fork: in front of the hash-grid backward
     WgradReduce red{wpart, grid * parts, with_rgb ? 1 : 0, grad_params_xyz, grad_params_rgb};
     if (!runs) {
         ARN_LAUNCH("wgrad_reduce_kernel", st, arn::wgrad_reduce_kernel<<<arn::kWgradFloats / 32, 256, 0, st>>>(red.wpart, red.n_slabs, red.with_rgb, red.dWd, red.dWc));

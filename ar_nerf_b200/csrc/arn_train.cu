@@ -105,21 +105,41 @@ extern "C" ARN_API int arn_train_march(const arn_train_t* c, arn_stream_t stream
                                     c->t_scratch, c->counter, c->xyzs, c->dirs, c->deltas, c->ts, c->capacity, stream);
 }
 
+namespace arn {
+thread_local int g_fork_stage = -1;
+thread_local cudaEvent_t g_fork_event = nullptr;
+int train_fork(int stage, cudaStream_t st) {
+    if (g_fork_event && g_fork_stage == stage) ARN_CUDA(cudaEventRecord(g_fork_event, st));
+    return ARN_OK;
+}
+}  // namespace arn
+extern "C" ARN_API int arn_train_set_fork(int stage, void* cuda_event) {
+    ARN_REQUIRE(!cuda_event || (stage >= 0 && stage <= 4), "stage must be 0..4");
+    arn::g_fork_stage = cuda_event ? stage : -1;
+    arn::g_fork_event = (cudaEvent_t)cuda_event;
+    return ARN_OK;
+}
+
 // The rest of the step on samples arn_train_march has produced (rays_a, counter, xyzs, dirs, deltas, ts of the config).
 extern "C" ARN_API int arn_train_fwbw_marched(const arn_train_t* c, arn_stream_t stream) {
     ARN_REQUIRE(c, "null config");
     ARN_REQUIRE(c->n_rays > 0 && c->capacity > 0, "bad sizes");
     const int64_t R = c->n_rays;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int e = train_fork(0, st)) return e;
     if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
                                     c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
+    if (int e = train_fork(1, st)) return e;
     if (int e = arn_composite_train_fw_loss(c->sigmas, c->rgbs, c->deltas, c->ts, c->rays_a, R, c->capacity, c->T_threshold, c->total_samples, c->opacity,
                                             c->depth, c->rgb, c->ws_out, c->rgb_target, c->bg_host, c->lambda_opacity, c->lambda_depth, c->scale,
                                             c->grad_scale, c->rgb_final, c->dL_drgb, c->dL_dopacity, c->dL_ddepth, c->loss_out, stream)) return e;
     if (int e = arn_composite_train_bw(c->dL_dopacity, c->dL_ddepth, c->dL_drgb, nullptr, c->sigmas, c->rgbs, c->ws_out, c->deltas, c->ts, c->rays_a,
                                        c->opacity, c->depth, c->rgb, R, c->capacity, c->T_threshold, c->dL_dsigmas, c->dL_drgbs, stream)) return e;
-    return field_bw_tc_impl(c->xyzs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16, c->params_rgb_f16,
-                            c->rgb_act, c->ws, c->sigmas, c->rgbs, c->dL_dsigmas, c->dL_drgbs, c->loss_scale, c->dfeat, c->grad_xyz, c->grad_rgb,
-                            nullptr, /*pack_weights=*/false, stream);
+    if (int e = train_fork(2, st)) return e;
+    if (int e = field_bw_tc_impl(c->xyzs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16, c->params_rgb_f16,
+                                 c->rgb_act, c->ws, c->sigmas, c->rgbs, c->dL_dsigmas, c->dL_drgbs, c->loss_scale, c->dfeat, c->grad_xyz, c->grad_rgb,
+                                 nullptr, /*pack_weights=*/false, stream)) return e;
+    return train_fork(4, st);
 }
 
 extern "C" ARN_API int arn_train_fwbw(const arn_train_t* c, arn_stream_t stream) {

@@ -7,6 +7,7 @@ gradient all-reduce -> fused Adam (lr 1e-2, eps 1e-15, train.py:146) with fp16 w
 """
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -162,7 +163,9 @@ class _FusedWorkspace:
         self.wimg = torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device)
         self.loss = torch.zeros(1, dtype=torch.float32, device=device)
         self.marched = torch.cuda.Event()
-        self.side = torch.cuda.Stream(device=device)  # the prefetched march runs here, filling issue slots the main stream leaves idle
+        # the prefetched march runs here, filling issue slots the main stream leaves idle
+        self.side = torch.cuda.Stream(device=device, priority=int(os.environ.get("ARN_SIDE_PRIO", "0")))
+        self.fork_armed = False
 
 
 class NGPTrainer:
@@ -191,6 +194,9 @@ class NGPTrainer:
                              exchange=exchange)
         self.global_step = 0
         self._grid_epoch = 0
+        self.fork_stage = int(os.environ.get("ARN_FORK_STAGE", "2"))  # where the prefetched march joins the step (arn_train_set_fork):
+        # measured on B200, ms per step with the fork at stage 0..4: 0.375 / 0.358 / 0.345 / 0.356 / 0.390 -- behind compositing the
+        # march shares the SMs with the MLP backward (8 warps per SM, latency-bound) and the memory-bound hash-grid backward + Adam
 
     def lr_at(self, step):
         """CosineAnnealingLR(T_max=num_epochs, eta_min=lr/30) stepped once per epoch (train.py:150-152)."""
@@ -261,8 +267,15 @@ class NGPTrainer:
                 prefetch = (n_ro, n_rd, next_rays[2] if len(next_rays) > 2 else None)
         self._keep_target = rgb_target.contiguous().float()
         if prefetch is not None:
-            w.marched.record(main)         # from here on the shared march scratch is free and the next batch's rays exist
+            # the side stream forks where the library records `marched`: from there on the shared march scratch is free and
+            # the next batch's rays exist (any stage of this call qualifies); see arn_train_set_fork for the choice of stage
+            if not w.fork_armed:
+                w.marched.record(main)     # creates the CUDA event handle
+                w.fork_armed = True
+            call("arn_train_set_fork", self.fork_stage, C.c_void_p(w.marched.cuda_event))
         call("arn_train_fwbw_marched", C.byref(self._cfg(ms, self._keep_target)), main_h)
+        if prefetch is not None:
+            call("arn_train_set_fork", 0, None)
         if prefetch is not None:
             # geometry of the next batch, concurrently with this batch's field / compositing / optimizer kernels: it reads the
             # rays and the occupancy bits only.  (Skipped when the next step refreshes the occupancy grid first.)

@@ -35,19 +35,58 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region: an NVML polling thread (2 ms period, so that
+    a region of a few tens of milliseconds still gets samples); `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.proc = None
+        import threading
+        self.proc = self.thread = None
+        self.sm, self.mx, self.reasons, self.stop_flag = [], [], set(), False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._sample()  # fail here, not in the thread
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
 
+    def _sample(self):
+        nv, h = self.nv, self.h
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(h))
+        for bit, name in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.002)
+
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join()
+            sm, mx = self.sm[1:] or self.sm, self.mx  # the first sample predates the timed region
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -65,7 +104,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------- CPU reference
@@ -133,10 +172,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_rays = 2048
-    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 2))
+    sample_rays = BATCH
+    steps, warmup = max(1, min(args.steps, 16)), max(1, min(args.warmup, 2))
     mrays, cores, sec = cpu_reference(sample_rays, steps, warmup)
-    sample = f"{steps} timed steps of {sample_rays} rays (1/4 of the 8192-ray batch) each, oracle/ C port with OpenMP on {cores} threads"
+    sample = f"{steps} timed steps of the full {sample_rays}-ray batch each, oracle/ C port with OpenMP on {cores} threads"
     line = {"impl": "reference", "metric": "train_Mrays_per_s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
@@ -208,19 +247,38 @@ def run_ours(args):
         if i not in staged:
             staged[i] = [t.to(dev, non_blocking=True) for t in pinned[i % N_BATCHES]]
 
+    loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    losses = []
+
     def step_e2e(i):
-        # Every step copies ONE batch host -> device and reads the loss back.  The input pipeline runs two batches ahead (the
-        # batch copied during step i is trained at step i+2 and marched during step i+1), and the copy is enqueued AFTER the
-        # step's kernels so that the GPU is not left idle while the host queues it.
+        # Every step copies ONE batch host -> device and reads the step's loss back to the host.  The input pipeline runs
+        # two batches ahead (the batch copied during step i is trained at step i+2 and marched during step i+1), and the copy
+        # is enqueued AFTER the step's kernels so that the GPU is not left idle while the host queues it.  The loss goes to
+        # pinned host memory with an asynchronous copy behind the step's kernels and is READ by the host one step later (while
+        # step i+1 is already queued): every step's loss reaches the host inside the timed region, none is waited for with an
+        # empty GPU queue -- what a training loop that logs its loss does.
         stage(i); stage(i + 1)                       # no-ops in steady state
         ro, rd, tgt = staged.pop(i)
         loss, _ = trainer.train_step(ro, rd, tgt, next_rays=None if NO_PREFETCH else tuple(staged[i + 1][:2]))
         staged.pop(i + 2, None); stage(i + 2)        # this step's host -> device copy
-        return float(loss.item())                    # device -> host read of the step's result
+        k = i & 1
+        loss_pin[k:k + 1].copy_(loss.reshape(1), non_blocking=True)  # device -> host copy of the step's result
+        loss_ev[k].record()
+        if losses is not None and i > 0:
+            loss_ev[k ^ 1].synchronize()
+            losses.append(float(loss_pin[k ^ 1]))    # host read of the previous step's loss
+
+    def finish_e2e(n):
+        loss_ev[(n - 1) & 1].synchronize()
+        losses.append(float(loss_pin[(n - 1) & 1]))
 
     # untimed: the first steps carry one-time costs (CUDA module loading, allocator growth, the first occupancy refresh);
     # at least two refresh intervals are run before the timed region whatever --warmup says, and reported as `warmup`
-    args.warmup = max(args.warmup, 2 * trainer.update_interval)
+    # ... and the first `warmup_steps` (256) optimisation steps refresh ALL 128^3 cells instead of the steady-state sample
+    # (networks.py:253-281, train.py:175-178): the timed region starts behind them, where 29 744 of the 30 000 steps of
+    # BASELINE.json's configs[1] run
+    args.warmup = max(args.warmup, trainer.warmup_steps + 2 * trainer.update_interval)
     for i in range(args.warmup):
         step_resident(i)
     samples_seen.clear()
@@ -240,12 +298,25 @@ def run_ours(args):
         return
     for i in range(min(args.warmup, 3)):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    losses.clear()
+
+    def e2e_region(i):
+        step_e2e(i)
+        if i == args.steps - 1:
+            finish_e2e(args.steps)                   # the last loss is read before the region's closing event
+    ms_e2e = timed(e2e_region, args.steps)
+    assert len(losses) >= args.steps and all(l == l for l in losses), "e2e: a step's loss did not reach the host"
     e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3) / 1e6
 
     # instrumented pass (not part of `value`): device time of every libarnerf.so kernel over the same steps
+    # (every kernel alone on one stream: with the next batch's march running beside them on the side stream, the events would
+    # time the co-running pair, not the kernel)
+    def step_serial(i):
+        ro, rd, tgt = resident[i % N_BATCHES]
+        trainer.train_step(ro, rd, tgt, next_rays=None)
+
     _lib.profile_enable(True)
-    timed(step_resident, args.steps)
+    timed(step_serial, min(args.steps, 96))
     prof = _lib.profile_report()
     _lib.profile_enable(False)
 
@@ -263,7 +334,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch read from the committed ncu --set full capture
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch", {})
-    per_step = {k: ms / args.steps for k, (c, ms) in prof.items()}
+    per_step = {k: ms / min(args.steps, 96) for k, (c, ms) in prof.items()}
     top = max(per_step, key=per_step.get) if per_step else None
     roof = None
     if top is not None:
@@ -321,19 +392,21 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        mrays, cores, sec = cpu_reference(2048, 3, 1)
+        mrays, cores, sec = cpu_reference(BATCH, 8, 1)
         cpu = {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port",
-               "sample": f"3 timed oracle steps of 2048 rays (1/4 batch), {sec:.2f} s each, OpenMP on {cores} threads"}
+               "sample": f"8 timed oracle steps of the full {BATCH}-ray batch (1 untimed), {sec:.2f} s each, C + OpenMP on {cores} threads"}
 
     if rank == 0:
         line = {"metric": "train_Mrays_per_s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": BATCH, "samples_per_step_per_gpu": N,
-                           "parallelism": f"dp{world} (rays sharded, NCCL all-reduce of hash-table + MLP gradients)",
+                           "parallelism": f"dp{world} (rays sharded; hash-table gradient reduce-scatter + sharded Adam + all-gather as one kernel over NVLink peer "
+                                          "memory, NCCL all-reduce of the MLP gradients)" if world > 1 else "dp1",
                            "l2_policy": "no explicit flush: one step streams ~350 MB (fp32 master + Adam moments + gradients 206 MB, activations ~140 MB) > 126 MB L2",
-                           "grid_update": "every 16 steps inside the timed region (warm-up form: all 128^3 cells)"},
-                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": BATCH * 36, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                           "grid_update": "every 16 steps inside the timed region (steady-state form of steps >= 256: G^3/4 uniform + G^3/4 occupied cells)"},
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": BATCH * 36, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                        "note": "NGPTrainer.train_step on pinned host batches; loss copied to pinned host memory every step, read by the host one step late"},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                 "frames_per_s_800x800": fps, "hash_encode_GBps": hash_gbs, "other_configs": other,
                 "kernel_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
@@ -345,8 +418,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=48)
-    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=480)
+    ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-w3", action="store_true", help="skip the informational unbounded-scene (W3) leg")

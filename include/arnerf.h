@@ -304,6 +304,12 @@ int arn_train_fwbw(const arn_train_t* cfg_host, arn_stream_t stream);
  * while batch k is in its field / optimizer kernels (ar_nerf_b200/trainer.py: next_rays=). */
 int arn_train_march(const arn_train_t* cfg_host, arn_stream_t stream);
 int arn_train_fwbw_marched(const arn_train_t* cfg_host, arn_stream_t stream);
+/* Fork point for that second stream: the next arn_train_fwbw_marched calls of this thread record `cuda_event` (a cudaEvent_t)
+ * on their stream right after launching stage `stage` (0 = before the field forward, 1 = after the field forward, 2 =
+ * after compositing fw + bw, 3 = after the MLP backward i.e. in front of the hash-grid backward, 4 = after the whole call),
+ * so that the caller can make the side stream wait there: the ray march is issue-bound and shares an SM best with the
+ * memory-bound tail of the step (hash-grid reductions, Adam).  cuda_event == NULL switches the recording off. */
+int arn_train_set_fork(int stage, void* cuda_event);
 /* Compositing forward with the NeRFLoss epilogue of the fused step (one launch instead of two; rays_a in canonical ray
  * order).  Same outputs as arn_composite_train_fw followed by arn_nerf_loss. */
 int arn_composite_train_fw_loss(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
