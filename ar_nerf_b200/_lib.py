@@ -106,6 +106,8 @@ SIGNATURES = {
     "arn_composite_train_fw_loss": [P, P, P, P, P, L, L, F, P, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, P],
     "arn_train_fwbw": [C.POINTER(TrainCfg), P],
     "arn_render_test_iter": [C.POINTER(TestIterCfg), P],
+    "arn_march_test_far_clamp": [P, P, P, L, P, I, I, F, F, I, P],
+    "arn_render_test_step": [C.POINTER(TestIterCfg), P, P, P, I, I, L, P],
     "arn_train_march": [C.POINTER(TrainCfg), P],
     "arn_train_set_fork": [I, P],
     "arn_train_fwbw_marched": [C.POINTER(TrainCfg), P],

@@ -178,6 +178,18 @@ ARN_HD bool arn_march_eval(const ArnMarchConsts& c, const ArnRay& r, const uint8
     return false;
 }
 
+#if defined(__cplusplus)
+// The same evaluation with the compile-time shortcuts of arn_march_probe (identical results).
+template <bool FAST>
+ARN_HD bool arn_march_eval_t(const ArnMarchConsts& c, const ArnRay& r, const uint8_t* __restrict__ bitfield, float& t,
+                             float& x, float& y, float& z, float& dt) {
+    float t_target;
+    if (arn_march_probe<FAST, FAST>(c, r, bitfield, t, x, y, z, dt, t_target)) return true;
+    do { t = ARN_ADD(t, arn_calc_dt(c, t)); } while (t < t_target);
+    return false;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Window form of the train march (warp-cooperative kernel, arn_vren.cu).
 //

@@ -824,6 +824,322 @@ __global__ void __launch_bounds__(256) alive_scatter_kernel(const int64_t* __res
     if (rays_a[3 * n + 2] > 0) alive_out[rays_a[3 * n + 1]] = alive[n];
 }
 
+// ---------------------------------------------------------------------------------------------- test loop, device-driven
+// arn_render_test_step: the same iteration with the loop's control state ON THE DEVICE, so the host can queue iterations
+// without reading anything back.  state = {n_alive, N_samples, samples requested so far, active, iterations done}; an
+// iteration reads state_in and its last kernel writes state_out (double-buffered by the caller: a CTA of that kernel may
+// still be reading state_in).  Every kernel is a grid-stride loop over the device-side count (the host sizes the grids
+// from an upper bound of n_alive).  Producers of per-ray counts also write the sum of every chunk of 128 rays (`partial`),
+// from which the scan kernels get their offset without re-reading all earlier counts.
+constexpr int kStN = 0, kStS = 1, kStDone = 2, kStActive = 3, kStIters = 4;
+
+__device__ __forceinline__ int block_sum_128(int v, int* sm4) {  // sum over a 128-thread group (4 warps), result in every thread
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    const int w = (threadIdx.x >> 5) & 3;
+    if ((threadIdx.x & 31) == 0) sm4[w] = v;
+    __syncthreads();
+    const int t = sm4[0] + sm4[1] + sm4[2] + sm4[3];
+    __syncthreads();
+    return t;
+}
+
+// Far clamp of a frame's rays, once, in front of the loop: every ray is marched to its end (same chain, same visits as the
+// loop's march) and hits_t[r][1] is pulled back to the chain point behind its LAST occupied sample (to hits_t[r][0] for
+// a ray that meets no occupied cell).  Nothing the loop computes changes -- the samples, their order, every N_eff and
+// the kill pattern are those of the unclamped march, whose `t < t2` test now ends where it would have found nothing
+// more -- but no iteration has to walk a ray's empty exit stretch (twice: once behind its last samples, once to find
+// zero samples), which left each iteration waiting for a handful of threads doing ~150 dependent probes.
+template <bool FAST>
+__global__ void __launch_bounds__(128) march_test_far_clamp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                                   float* __restrict__ hits_t, int64_t n_rays,
+                                                                   const uint8_t* __restrict__ bitfield, ArnMarchConsts c) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
+    float t = hits_t[2 * r]; const float t2 = hits_t[2 * r + 1];
+    if (!(t < t2)) return;
+    float t_end = t;
+    while (t < t2) {
+        float x, y, z, dt;
+        if (arn_march_eval_t<FAST>(c, ray, bitfield, t, x, y, z, dt)) { t = __fadd_rn(t, dt); t_end = t; }
+    }
+    if (t_end < t2) hits_t[2 * r + 1] = t_end;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(128) march_test_dyn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                             float* __restrict__ hits_t, const int64_t* __restrict__ alive,
+                                                             const int32_t* __restrict__ state, const uint8_t* __restrict__ bitfield,
+                                                             ArnMarchConsts c, float* __restrict__ deltas, float* __restrict__ ts,
+                                                             int32_t* __restrict__ n_eff, int32_t* __restrict__ partial) {
+    __shared__ int sm4[4];
+    const int64_t n_alive = state[kStN]; const int S = state[kStS];
+    for (int64_t base = (int64_t)blockIdx.x * 128; base < n_alive; base += (int64_t)gridDim.x * 128) {
+        const int64_t n = base + threadIdx.x;
+        int s = 0;
+        if (n < n_alive) {
+            const int64_t r = alive[n];
+            const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
+            float t = hits_t[2 * r]; const float t2 = hits_t[2 * r + 1];
+            float t_resume = t; bool moved = false;
+            while (t < t2 && s < S) {
+                float x, y, z, dt;
+                if (arn_march_eval_t<FAST>(c, ray, bitfield, t, x, y, z, dt)) {
+                    const int64_t o = n * S + s;
+                    ts[o] = t; deltas[o] = dt;
+                    t = __fadd_rn(t, dt);
+                    t_resume = t; moved = true;  // raymarching.cu:386: only an occupied step moves the resume point
+                    s++;
+                }
+            }
+            if (moved) hits_t[2 * r] = t_resume;
+            n_eff[n] = s;
+        }
+        const int tot = block_sum_128(s, sm4);
+        if (threadIdx.x == 0) partial[base >> 7] = tot;
+    }
+}
+
+// The same march with one WARP per alive ray (arn_march_core.h, "Window form": 32 chain points probed per turn, visited
+// occupied points compacted with ballot/popc) for the iterations in which few rays take many samples each -- one thread
+// walking 64 samples is a serial chain of probes (~1 us per sample), a warp takes them a window at a time.  Same samples,
+// same resume point; writes no chunk sums (the scan re-reads the few counts instead).
+template <bool CONST_DT, bool FAST>
+__global__ void __launch_bounds__(256) march_test_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                              float* __restrict__ hits_t, const int64_t* __restrict__ alive,
+                                                              const int32_t* __restrict__ state, const uint8_t* __restrict__ bitfield,
+                                                              ArnMarchConsts c, float* __restrict__ deltas, float* __restrict__ ts,
+                                                              int32_t* __restrict__ n_eff) {
+    const int64_t n_alive = state[kStN]; const int S = state[kStS];
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_alive; n += n_warps) {
+        const int64_t r = alive[n];
+        const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
+        const float t1 = hits_t[2 * r], t2 = hits_t[2 * r + 1];
+        int N = 0;
+        float t_resume = t1; bool moved = false;
+        if (t1 < t2) {
+            float t = t1;
+#pragma unroll
+            for (int j = 0; j < 31; j++) {
+                const float tn = __fadd_rn(t, CONST_DT ? c.dt_lo : arn_calc_dt(c, t));
+                if (lane > j) t = tn;
+            }
+            float pending = -INFINITY;
+            for (;;) {
+                float x, y, z, dt, tgt;
+                const bool occ = arn_march_probe<FAST, FAST>(c, ray, bitfield, t, x, y, z, dt, tgt);
+                const unsigned valid = __ballot_sync(kFull, t < t2);
+                const unsigned occm = __ballot_sync(kFull, occ);
+                const int s0 = __popc(__ballot_sync(kFull, t < pending));
+                int lo = lane + 1, hi = 32;
+#pragma unroll
+                for (int it = 0; it < 5; it++) {
+                    const int mid = (lo + hi) >> 1;
+                    const float tv = __shfl_sync(kFull, t, mid & 31);
+                    if (lo < hi) { if (tv < tgt) lo = mid + 1; else hi = mid; }
+                }
+                int R = occ ? lane + 1 : lo;
+                unsigned M = 1u << lane;
+#pragma unroll
+                for (int it = 0; it < 5; it++) {
+                    const unsigned Mo = __shfl_sync(kFull, M, R & 31);
+                    const int Ro = __shfl_sync(kFull, R, R & 31);
+                    if (R < 32) { M |= Mo; R = Ro; }
+                }
+                const unsigned vis = s0 < 32 ? __shfl_sync(kFull, M, s0 & 31) : 0u;
+                unsigned emit = vis & occm & valid;
+                const int rem = S - N;
+                bool done = valid != kFull;
+                if (__popc(emit) >= rem) {  // the iteration's sample budget ends the march inside this window
+                    done = true;
+                    const int rank_all = __popc(emit & ((1u << lane) - 1u));
+                    emit = __ballot_sync(kFull, ((emit >> lane) & 1u) && rank_all < rem);
+                }
+                if ((emit >> lane) & 1u) {
+                    const int64_t o = n * S + N + __popc(emit & ((1u << lane) - 1u));
+                    ts[o] = t; deltas[o] = dt;
+                }
+                if (emit) {  // raymarching.cu:386: the resume point follows the last sample taken
+                    const int last = 31 - __clz(emit);
+                    t_resume = __shfl_sync(kFull, __fadd_rn(t, dt), last);
+                    moved = true;
+                }
+                N += __popc(emit);
+                if (done) break;
+                if (vis) {
+                    const int last = 31 - __clz(vis);
+                    pending = __shfl_sync(kFull, occ ? -INFINITY : tgt, last);
+                }
+#pragma unroll
+                for (int k = 0; k < 32; k++) t = __fadd_rn(t, CONST_DT ? c.dt_lo : arn_calc_dt(c, t));
+            }
+        }
+        if (lane == 0) {
+            if (moved) hits_t[2 * r] = t_resume;
+            n_eff[n] = N;
+        }
+    }
+}
+
+// Offsets of the compact sample list: rays_a[n] = (n, start, N) for the n_alive rays, counts = (valid samples, n_alive).
+__global__ void __launch_bounds__(1024) scan_test_dyn_kernel(const int32_t* __restrict__ counts_in, const int32_t* __restrict__ partial,
+                                                             const int32_t* __restrict__ state, int64_t* __restrict__ rays_a,
+                                                             int32_t* __restrict__ counter) {
+    __shared__ int64_t warp_inc[32];
+    __shared__ int64_t s_pre;
+    const int64_t n_rays = state[kStN];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int64_t r_base = (int64_t)blockIdx.x * 1024; r_base < n_rays || (r_base == 0 && n_rays == 0); r_base += (int64_t)gridDim.x * 1024) {
+        const int64_t r = r_base + threadIdx.x;
+        int64_t pre = 0;
+        if (partial) { for (int64_t j = threadIdx.x; j < (r_base >> 7); j += 1024) pre += partial[j]; }
+        else { for (int64_t j = threadIdx.x; j < r_base; j += 1024) pre += counts_in[j]; }
+        const int32_t mine = r < n_rays ? counts_in[r] : 0;
+        int64_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += u; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(kFull, pre, o);
+        __syncthreads();  // the previous turn's readers of warp_inc / s_pre are done
+        if (lane == 31) warp_inc[wid] = inc;
+        if (threadIdx.x == 0) s_pre = 0;
+        __syncthreads();
+        if (lane == 0 && pre) atomicAdd((unsigned long long*)&s_pre, (unsigned long long)pre);
+        if (wid == 0) {
+            int64_t v = warp_inc[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, v, o); if (lane >= o) v += u; }
+            warp_inc[lane] = v;  // inclusive over warps
+        }
+        __syncthreads();
+        const int64_t before = s_pre;
+        const int64_t start = before + (wid ? warp_inc[wid - 1] : 0) + inc - mine;
+        if (r < n_rays) { rays_a[3 * r] = r; rays_a[3 * r + 1] = start; rays_a[3 * r + 2] = mine; }
+        if (threadIdx.x == 0 && n_rays <= r_base + 1024) {  // the CTA that holds the last ray (or the only CTA of an empty list)
+            const int64_t tot = before + warp_inc[31];
+            counter[0] = (int32_t)(tot > 0x7fffffff ? 0x7fffffff : tot);
+            counter[1] = (int32_t)n_rays;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) emit_test_dyn_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                            const int64_t* __restrict__ alive, const int32_t* __restrict__ state,
+                                                            const int64_t* __restrict__ rays_a, const float* __restrict__ ts,
+                                                            float* __restrict__ xyzs, float* __restrict__ dirs) {
+    const int64_t n_alive = state[kStN]; const int S = state[kStS];
+    const int64_t total = n_alive * S;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = e / S; const int sl = (int)(e - n * S);
+        if (sl >= (int)rays_a[3 * n + 2]) continue;
+        const int64_t r = alive[n], o = rays_a[3 * n + 1] + sl;
+        const float t = ts[e];
+        const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+        xyzs[3 * o] = __fmaf_rn(dx, t, rays_o[3 * r]); xyzs[3 * o + 1] = __fmaf_rn(dy, t, rays_o[3 * r + 1]); xyzs[3 * o + 2] = __fmaf_rn(dz, t, rays_o[3 * r + 2]);
+        dirs[3 * o] = dx; dirs[3 * o + 1] = dy; dirs[3 * o + 2] = dz;
+    }
+}
+
+// composite_test_compact_kernel over the device-side count; keep flags + their sums per 128 rays
+__global__ void __launch_bounds__(128) composite_test_dyn_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                 const float* __restrict__ deltas, const float* __restrict__ ts,
+                                                                 const int64_t* __restrict__ alive, const int32_t* __restrict__ state, float T_thr,
+                                                                 const int64_t* __restrict__ rays_a, float* __restrict__ opacity,
+                                                                 float* __restrict__ depth, float* __restrict__ rgb, int32_t* __restrict__ keep,
+                                                                 int32_t* __restrict__ partial, unsigned long long* __restrict__ total) {
+    __shared__ int sm4[4];
+    const int64_t n_alive = state[kStN]; const int S = state[kStS];
+    for (int64_t base = (int64_t)blockIdx.x * 128; base < n_alive; base += (int64_t)gridDim.x * 128) {
+        const int64_t n = base + threadIdx.x;
+        int ne = 0; bool live = false;
+        if (n < n_alive) {
+            ne = (int)rays_a[3 * n + 2];
+            if (ne > 0) {
+                live = true;
+                const int64_t r = alive[n], c0 = rays_a[3 * n + 1];
+                float O = opacity[r];
+                float T = __fsub_rn(1.0f, O);
+                float cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2], D = depth[r];
+                for (int s = 0; s < ne; s++) {
+                    const int64_t o = n * S + s, q = c0 + s;
+                    const float a = alpha_of(sigmas[q], deltas[o]);
+                    const float w = __fmul_rn(a, T);
+                    cr = __fmaf_rn(w, rgbs[3 * q], cr); cg = __fmaf_rn(w, rgbs[3 * q + 1], cg); cb = __fmaf_rn(w, rgbs[3 * q + 2], cb);
+                    D = __fmaf_rn(w, ts[o], D);
+                    O = __fadd_rn(O, w);
+                    T = __fmul_rn(T, __fsub_rn(1.0f, a));
+                    if (T <= T_thr) { live = false; break; }
+                }
+                opacity[r] = O; depth[r] = D; rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+            }
+            keep[n] = live ? 1 : 0;
+        }
+        unsigned v = (unsigned)ne;  // effective samples of this iteration: warp sum, one atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, (unsigned long long)v);
+        const int kept = block_sum_128(live ? 1 : 0, sm4);
+        if (threadIdx.x == 0) partial[base >> 7] = kept;
+    }
+}
+
+// alive_out = alive[keep != 0] (order preserved: alive_indices[alive_indices >= 0]) and the control state of the NEXT
+// iteration, the schedule of rendering.py:184-206: stop when nothing was marched, nobody is alive or the sample budget is
+// spent; otherwise N_samples = max(min(N_rays // N_alive, 64), min_samples).
+__global__ void __launch_bounds__(1024) alive_compact_dyn_kernel(const int64_t* __restrict__ alive, const int32_t* __restrict__ keep,
+                                                                 const int32_t* __restrict__ partial, const int32_t* __restrict__ state_in,
+                                                                 const int32_t* __restrict__ counts, int64_t* __restrict__ alive_out,
+                                                                 int32_t* __restrict__ counts_alive, int32_t* __restrict__ state_out,
+                                                                 int64_t n_rays_total, int min_samples, int budget) {
+    __shared__ int64_t warp_inc[32];
+    __shared__ int64_t s_pre;
+    const int64_t n = state_in[kStN];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int64_t r_base = (int64_t)blockIdx.x * 1024; r_base < n || (r_base == 0 && n == 0); r_base += (int64_t)gridDim.x * 1024) {
+        const int64_t r = r_base + threadIdx.x;
+        int64_t pre = 0;
+        for (int64_t j = threadIdx.x; j < (r_base >> 7); j += 1024) pre += partial[j];
+        const int32_t mine = r < n ? keep[r] : 0;
+        int64_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += u; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(kFull, pre, o);
+        __syncthreads();
+        if (lane == 31) warp_inc[wid] = inc;
+        if (threadIdx.x == 0) s_pre = 0;
+        __syncthreads();
+        if (lane == 0 && pre) atomicAdd((unsigned long long*)&s_pre, (unsigned long long)pre);
+        if (wid == 0) {
+            int64_t v = warp_inc[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int64_t u = __shfl_up_sync(kFull, v, o); if (lane >= o) v += u; }
+            warp_inc[lane] = v;
+        }
+        __syncthreads();
+        const int64_t before = s_pre;
+        if (mine) alive_out[before + (wid ? warp_inc[wid - 1] : 0) + inc - mine] = alive[r];
+        if (threadIdx.x == 0 && n <= r_base + 1024) {
+            const int64_t n_keep = before + warp_inc[31];
+            counts_alive[0] = (int32_t)n_keep; counts_alive[1] = (int32_t)n;
+            int active = state_in[kStActive], done = state_in[kStDone], S = 1;
+            int64_t n_next = 0;
+            if (active && counts[0] == 0) active = 0;                       // rendering.py:206: nothing was marched
+            if (active) { n_next = n_keep; if (n_next == 0 || done >= budget) active = 0; }
+            if (active) {
+                const int64_t q = n_rays_total / n_next;
+                S = (int)(q < 64 ? q : 64); if (S < min_samples) S = min_samples;
+                done += S;
+            } else n_next = 0;
+            state_out[kStN] = (int32_t)n_next; state_out[kStS] = S; state_out[kStDone] = done; state_out[kStActive] = active;
+            state_out[kStIters] = state_in[kStIters] + 1;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- distortion loss
 // losses.cu:7-59,62-107: one warp per row; inclusive scans kept for the backward, loss reduced in the same pass.
 __global__ void __launch_bounds__(256) distortion_fw_kernel(const float* __restrict__ ws, const float* __restrict__ deltas,
@@ -1228,4 +1544,68 @@ extern "C" ARN_API int arn_render_test_iter(const arn_test_iter_t* c, arn_stream
     if (int e = check_launch("rays_scan")) return e;
     ARN_LAUNCH("alive_scatter_kernel", st, alive_scatter_kernel<<<ceil_div(n, 256), 256, 0, st>>>(c->alive, n, c->rays_a, c->alive_out));
     return check_launch("alive_scatter");
+}
+
+// Far clamp of the rays of a frame, once, in front of the test loop (march_test_far_clamp_kernel): hits_t (R,2) in place.
+extern "C" ARN_API int arn_march_test_far_clamp(const float* rays_o, const float* rays_d, float* hits_t, int64_t n_rays,
+                                                const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                                                float exp_step_factor, int max_samples, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0, "bad size");
+    if (n_rays == 0) return ARN_OK;
+    ARN_REQUIRE(rays_o && rays_d && hits_t && density_bitfield, "null pointer");
+    if (int e = check_march_cfg(cascades, grid_size, max_samples)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ArnMarchConsts mc = arn_march_consts(cascades, grid_size, scale, (float)cascades, exp_step_factor, max_samples);  // the test march's dt (Q2)
+    if (cascades == 1 && grid_size <= 256)
+        ARN_LAUNCH("march_test_far_clamp_kernel", st, march_test_far_clamp_kernel<true><<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, mc));
+    else
+        ARN_LAUNCH("march_test_far_clamp_kernel", st, march_test_far_clamp_kernel<false><<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, mc));
+    return check_launch("march_test_far_clamp");
+}
+
+// The iteration above with the loop control on the device (kernels: "test loop, device-driven").  c->n_alive = N_rays of the
+// frame (the numerator of the schedule), c->n_samples is ignored; n_upper bounds the device-side n_alive (grid sizing only).
+extern "C" ARN_API int arn_render_test_step(const arn_test_iter_t* c, const int32_t* state_in, int32_t* state_out, int32_t* partial,
+                                            int min_samples, int budget_samples, int64_t n_upper, arn_stream_t stream) {
+    ARN_REQUIRE(c && state_in && state_out && partial, "null pointer");
+    ARN_REQUIRE(c->n_alive > 0 && min_samples >= 1 && n_upper >= 0 && n_upper <= c->n_alive, "bad sizes");
+    ARN_REQUIRE(c->capacity >= c->n_alive * (int64_t)min_samples, "capacity must hold N_rays * min_samples samples");
+    if (int e = check_march_cfg(c->cascades, c->grid_size, c->max_samples)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nu = n_upper > 0 ? n_upper : 1;
+    const int64_t samples_upper = nu * min_samples > c->n_alive ? nu * min_samples : c->n_alive;  // n * S <= max(N_rays, n * min_samples)
+    const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
+    const int g128 = (int)min((int64_t)148 * 64, (nu + 127) / 128), g1024 = (int)min((int64_t)148 * 8, (nu + 1023) / 1024);
+    // few rays, many samples each (N_samples >= 9 once n_alive <= N_rays / 9): one warp per ray
+    const bool warp_march = tunable(kTunMarchWarp) != 0 && nu <= 65536 && nu * 9 <= c->n_alive;
+    if (warp_march) {
+        const int gw = (int)min((int64_t)148 * 16, (nu + 7) / 8);
+        const bool cd = c->exp_step_factor == 0.0f, fa = c->cascades == 1 && c->grid_size <= 256;
+#define ARN_TEST_WARP(CD, FA) ARN_LAUNCH("march_test_warp_kernel", st, (march_test_warp_kernel<CD, FA><<<gw, 256, 0, st>>>(c->rays_o, c->rays_d, c->hits_t, c->alive, state_in, c->density_bitfield, mc, c->deltas, c->ts, c->n_eff)))
+        if (cd && fa) ARN_TEST_WARP(true, true); else if (cd) ARN_TEST_WARP(true, false); else if (fa) ARN_TEST_WARP(false, true); else ARN_TEST_WARP(false, false);
+#undef ARN_TEST_WARP
+        if (int e = check_launch("march_test_warp")) return e;
+    } else {
+        if (c->cascades == 1 && c->grid_size <= 256)
+            ARN_LAUNCH("march_test_dyn_kernel", st, march_test_dyn_kernel<true><<<g128, 128, 0, st>>>(c->rays_o, c->rays_d, c->hits_t, c->alive, state_in, c->density_bitfield, mc,
+                                                                                                  c->deltas, c->ts, c->n_eff, partial));
+        else
+            ARN_LAUNCH("march_test_dyn_kernel", st, march_test_dyn_kernel<false><<<g128, 128, 0, st>>>(c->rays_o, c->rays_d, c->hits_t, c->alive, state_in, c->density_bitfield, mc,
+                                                                                                   c->deltas, c->ts, c->n_eff, partial));
+        if (int e = check_launch("march_test_dyn")) return e;
+    }
+    ARN_LAUNCH("scan_test_dyn_kernel", st, scan_test_dyn_kernel<<<g1024, 1024, 0, st>>>(c->n_eff, warp_march ? nullptr : partial, state_in, c->rays_a, c->counts));
+    if (int e = check_launch("scan_test_dyn")) return e;
+    const int g_emit = (int)min((int64_t)148 * 32, (samples_upper + 255) / 256);
+    ARN_LAUNCH("emit_test_dyn_kernel", st, emit_test_dyn_kernel<<<g_emit, 256, 0, st>>>(c->rays_o, c->rays_d, c->alive, state_in, c->rays_a, c->ts, c->xyzs, c->dirs));
+    if (int e = check_launch("emit_test_dyn")) return e;
+    if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, samples_upper, c->counts, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
+                                    c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
+    ARN_LAUNCH("composite_test_dyn_kernel", st, composite_test_dyn_kernel<<<g128, 128, 0, st>>>(c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, state_in, c->T_threshold,
+                                                                                            c->rays_a, c->opacity, c->depth, c->rgb, c->n_eff, partial,
+                                                                                            (unsigned long long*)c->total_samples));
+    if (int e = check_launch("composite_test_dyn")) return e;
+    ARN_LAUNCH("alive_compact_dyn_kernel", st, alive_compact_dyn_kernel<<<g1024, 1024, 0, st>>>(c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
+                                                                                           c->counts_alive, state_out, c->n_alive, min_samples, budget_samples));
+    return check_launch("alive_compact_dyn");
 }

@@ -83,6 +83,8 @@ def render(model, rays_o, rays_d, **kwargs):
 
 
 _TEST_WS = {}
+_STATE_RING = 4   # read-back slots of the device-driven test loop
+_STATE_LAG = 2    # the host looks at the control state of the iteration queued this many calls earlier
 
 
 def _test_workspace(R, min_samples, device):
@@ -99,7 +101,12 @@ def _test_workspace(R, min_samples, device):
                   xyzs=f(cap, 3), dirs=f(cap, 3), sigmas=f(cap), rgbs=f(cap, 3),
                   feat=torch.empty(tile_rows(cap), 32, dtype=torch.float16, device=device), wimg=_scratch(device),
                   alive=[torch.empty(R, dtype=torch.int64, device=device), torch.empty(R, dtype=torch.int64, device=device)],
-                  total=torch.zeros(1, dtype=torch.int64, device=device))
+                  total=torch.zeros(1, dtype=torch.int64, device=device),
+                  # device-driven loop (arn_render_test_step): two control-state buffers, chunk sums, pinned read-back ring
+                  state=torch.zeros(2, 8, dtype=torch.int32, device=device), partial=torch.empty((R + 127) // 128, dtype=torch.int32, device=device),
+                  state_host=torch.zeros(_STATE_RING, 8, dtype=torch.int32).pin_memory(),
+                  state_init=torch.zeros(8, dtype=torch.int32).pin_memory(),
+                  state_ev=[torch.cuda.Event() for _ in range(_STATE_RING)])
         _TEST_WS.clear()  # one frame size at a time
         _TEST_WS[key] = ws
     return ws
@@ -142,8 +149,39 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
         ptr(w['xyzs']), ptr(w['dirs']), ptr(w['sigmas']), ptr(w['rgbs']),
         FieldWs(ptr(w['feat']), None, None, None, None, None, ptr(w['wimg'])),
         ptr(opacity), ptr(depth), ptr(rgb), None, ptr(w['total']))
-    samples, N_alive = 0, N_rays
     s_ = stream()
+    if not kwargs.get('host_driven_test_loop', False):
+        # Loop control on the device: iterations are queued without waiting for their counts; the control state comes back
+        # through pinned memory and is looked at _STATE_LAG iterations late (an iteration queued after the loop has ended
+        # is a handful of empty launches).  n_alive never grows, so a stale value still bounds the grids.
+        if kwargs.get('far_clamp', True):
+            call("arn_march_test_far_clamp", ptr(rays_o), ptr(rays_d), ptr(hits_t2), N_rays, ptr(model.density_bitfield), model.cascades,
+                 model.grid_size, float(model.scale), float(exp_step_factor), MAX_SAMPLES, s_)
+        S0 = max(1, min_samples)
+        w['state_init'][:5] = torch.tensor([N_rays, S0, S0, 1 if max_samples > 0 else 0, 0], dtype=torch.int32)
+        w['state'][0].copy_(w['state_init'], non_blocking=True)
+        cfg.n_alive = N_rays
+        cfg.capacity = w['cap']
+        n_upper, it = N_rays, 0
+        state_ptr = (w['state'][0].data_ptr(), w['state'][1].data_ptr())
+        cur_stream = torch.cuda.current_stream()
+        while True:
+            cfg.alive, cfg.alive_out = w['alive'][it & 1].data_ptr(), w['alive'][(it & 1) ^ 1].data_ptr()
+            call("arn_render_test_step", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(w['partial']), min_samples,
+                 int(max_samples), n_upper, s_)
+            k = it % _STATE_RING
+            w['state_host'][k].copy_(w['state'][(it & 1) ^ 1], non_blocking=True)
+            w['state_ev'][k].record(cur_stream)
+            it += 1
+            if it >= _STATE_LAG:
+                j = (it - _STATE_LAG) % _STATE_RING
+                w['state_ev'][j].synchronize()
+                n_next, _, _, active, _ = w['state_host'][j][:5].tolist()
+                if not active:
+                    break
+                n_upper = n_next
+        return opacity, depth, rgb, w['total'][0].clone()
+    samples, N_alive = 0, N_rays
     while samples < max_samples and N_alive > 0:
         N_samples = max(min(N_rays // N_alive, 64), min_samples)
         samples += N_samples

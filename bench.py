@@ -211,7 +211,6 @@ def run_ours(args):
     trainer = NGPTrainer(model)
     # per-rank batches (weak scaling: every GPU marches its own 8192 rays); pinned host copies feed the e2e leg
     host = [w.train_batch(i, BATCH, seed=rank) for i in range(N_BATCHES)]
-    pinned = [[t.pin_memory() for t in b[:3]] for b in host]
     resident = [[t.to(dev) for t in b[:3]] for b in host]
 
     def sync_all():
@@ -241,31 +240,49 @@ def run_ours(args):
         _, res = trainer.train_step(ro, rd, tgt, next_rays=None if NO_PREFETCH else (nro, nrd))
         samples_seen.append(res["rm_samples"].clone())  # the trainer returns views into its workspace
 
-    staged = {}
+    # ---- e2e leg: host batches -> device through a copy stream, three device slots
+    # Every step copies ONE batch (rays_o | rays_d | target packed as one (3, R, 3) pinned block, one cudaMemcpyAsync) host ->
+    # device and brings the step's loss back to the host.  The input pipeline runs two batches ahead (the batch copied during
+    # step i is trained at step i+2 and marched during step i+1) on its own stream, so the copy overlaps the step's kernels
+    # instead of queueing between them; events order slot reuse (the slot of batch i+2 was last read by step i-1).
+    packed = [torch.stack([t.float() for t in b[:3]]).contiguous().pin_memory() for b in host]
+    slots = [torch.empty(3, BATCH, 3, device=dev) for _ in range(3)]
+    slot_views = [tuple(sl.unbind(0)) for sl in slots]  # the trainer recognises a prefetched batch by tensor identity
+    copy_stream = torch.cuda.Stream(device=dev)
+    landed = {}                                      # batch index -> event recorded on the copy stream
+    step_done = {}                                   # step index -> event recorded on the main stream
 
     def stage(i):
-        if i not in staged:
-            staged[i] = [t.to(dev, non_blocking=True) for t in pinned[i % N_BATCHES]]
+        if i in landed:
+            return
+        with torch.cuda.stream(copy_stream):
+            if i - 3 in step_done:
+                copy_stream.wait_event(step_done[i - 3])
+            slots[i % 3].copy_(packed[i % N_BATCHES], non_blocking=True)
+            landed[i] = torch.cuda.Event()
+            landed[i].record(copy_stream)
 
     loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     losses = []
 
     def step_e2e(i):
-        # Every step copies ONE batch host -> device and reads the step's loss back to the host.  The input pipeline runs
-        # two batches ahead (the batch copied during step i is trained at step i+2 and marched during step i+1), and the copy
-        # is enqueued AFTER the step's kernels so that the GPU is not left idle while the host queues it.  The loss goes to
-        # pinned host memory with an asynchronous copy behind the step's kernels and is READ by the host one step later (while
-        # step i+1 is already queued): every step's loss reaches the host inside the timed region, none is waited for with an
-        # empty GPU queue -- what a training loop that logs its loss does.
+        # The loss goes to pinned host memory with an asynchronous copy behind the step's kernels and is READ by the host one
+        # step later (while step i+1 is already queued): every step's loss reaches the host inside the timed region, none is
+        # waited for with an empty GPU queue -- what a training loop that logs its loss does.
         stage(i); stage(i + 1)                       # no-ops in steady state
-        ro, rd, tgt = staged.pop(i)
-        loss, _ = trainer.train_step(ro, rd, tgt, next_rays=None if NO_PREFETCH else tuple(staged[i + 1][:2]))
-        staged.pop(i + 2, None); stage(i + 2)        # this step's host -> device copy
+        main = torch.cuda.current_stream()
+        main.wait_event(landed[i]); main.wait_event(landed[i + 1])
+        ro, rd, tgt = slot_views[i % 3]
+        nro, nrd, _ = slot_views[(i + 1) % 3]
+        loss, _ = trainer.train_step(ro, rd, tgt, next_rays=None if NO_PREFETCH else (nro, nrd))
+        step_done[i] = torch.cuda.Event(); step_done[i].record(main)
+        step_done.pop(i - 4, None); landed.pop(i - 1, None)
+        stage(i + 2)                                 # this step's host -> device copy
         k = i & 1
         loss_pin[k:k + 1].copy_(loss.reshape(1), non_blocking=True)  # device -> host copy of the step's result
         loss_ev[k].record()
-        if losses is not None and i > 0:
+        if i > 0:
             loss_ev[k ^ 1].synchronize()
             losses.append(float(loss_pin[k ^ 1]))    # host read of the previous step's loss
 
@@ -296,14 +313,15 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    for i in range(min(args.warmup, 3)):
+    n_pre = 3
+    for i in range(n_pre):
         step_e2e(i)
     losses.clear()
 
-    def e2e_region(i):
-        step_e2e(i)
-        if i == args.steps - 1:
-            finish_e2e(args.steps)                   # the last loss is read before the region's closing event
+    def e2e_region(k):                               # continues the batch sequence of the three untimed steps
+        step_e2e(n_pre + k)
+        if k == args.steps - 1:
+            finish_e2e(n_pre + args.steps)           # the last loss is read before the region's closing event
     ms_e2e = timed(e2e_region, args.steps)
     assert len(losses) >= args.steps and all(l == l for l in losses), "e2e: a step's loss did not reach the host"
     e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3) / 1e6

@@ -365,6 +365,25 @@ typedef struct {
     float* opacity; float* depth; float* rgb; int64_t* alive_out; int64_t* total_samples;
 } arn_test_iter_t;
 int arn_render_test_iter(const arn_test_iter_t* cfg_host, arn_stream_t stream);
+/* Far clamp of a frame's rays, once, in front of the test loop: every ray is marched to its end with the test march's
+ * own arithmetic and hits_t[r][1] is pulled back to the chain point behind the ray's last occupied sample (to
+ * hits_t[r][0] if it meets no occupied cell).  The loop then produces exactly the samples, N_eff values and kill pattern
+ * of the unclamped march, without any iteration walking a ray's empty exit stretch.  hits_t (R,2) in place. */
+int arn_march_test_far_clamp(const float* rays_o, const float* rays_d, float* hits_t, int64_t n_rays,
+                             const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                             float exp_step_factor, int max_samples, arn_stream_t stream);
+/* The same iteration with the loop's control state on the device, so that a caller can queue iterations without reading
+ * anything back (the reference's loop costs three host synchronisations per iteration, rendering.py:186,198,219).
+ * state (5 x int32, device) = {n_alive, N_samples, samples requested so far, active, iterations done}: the iteration reads
+ * state_in and writes state_out -- the schedule of rendering.py:184-206 (stop when nothing was marched, nobody is alive or
+ * budget_samples (= kwargs max_samples) is spent; N_samples = max(min(N_rays // N_alive, 64), min_samples)); pass two
+ * alternating buffers.  Initial state for a frame of N_rays: {N_rays, S0, S0, 1, 0} with S0 = max(1, min_samples) (or
+ * active = 0 when budget_samples <= 0).  An inactive state turns the call into no-ops, so iterations may be queued
+ * speculatively and the state read back late.  cfg->n_alive = N_rays (whole frame), cfg->alive/alive_out alternate as
+ * before, cfg->n_samples is ignored; n_upper >= the device-side n_alive (grid sizing only; N_rays is always valid);
+ * partial: (N_rays + 127) / 128 int32 of scratch; capacity >= N_rays * min_samples. */
+int arn_render_test_step(const arn_test_iter_t* cfg_host, const int32_t* state_in, int32_t* state_out, int32_t* partial,
+                         int min_samples, int budget_samples, int64_t n_upper, arn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Optimizer step.  Replaces apex FusedAdam(lr, betas=(0.9,0.999), eps=1e-15, weight_decay=0) (train.py:146).

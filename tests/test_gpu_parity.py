@@ -705,11 +705,22 @@ def test_fused_test_loop_equals_eager_loop(kind, thr, max_samples, w1, w3):
     w.install(model)
     ro, rd = w.test_frame(160, 120)
     kw = dict(test_time=True, T_threshold=thr, max_samples=max_samples, exp_step_factor=w.exp_step_factor)
-    a = render(model, T(ro), T(rd), **kw)
+    a = render(model, T(ro), T(rd), **kw)                              # arn_render_test_step: loop control on the device
+    h = render(model, T(ro), T(rd), host_driven_test_loop=True, **kw)  # arn_render_test_iter: counts read per iteration
     b = render(model, T(ro), T(rd), eager_test_loop=True, **kw)
-    assert int(a["total_samples"]) == int(b["total_samples"]) > 0
+    assert int(a["total_samples"]) == int(h["total_samples"]) == int(b["total_samples"]) > 0
     for k in ("opacity", "depth", "rgb"):
-        assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a[k], b[k]) and torch.equal(h[k], b[k]), k
+    # a frame whose rays all miss, a one-ray frame and an exhausted sample budget end the device-driven loop as well
+    far = T(ro) + 100.0
+    z = render(model, far, T(rd), **kw)
+    assert int(z["total_samples"]) == 0 and float(z["opacity"].abs().max()) == 0.0
+    one = render(model, T(ro)[:1].contiguous(), T(rd)[:1].contiguous(), **kw)
+    one_e = render(model, T(ro)[:1].contiguous(), T(rd)[:1].contiguous(), eager_test_loop=True, **kw)
+    assert torch.equal(one["rgb"], one_e["rgb"]) and int(one["total_samples"]) == int(one_e["total_samples"])
+    kw3 = dict(kw, max_samples=3)
+    c3 = render(model, T(ro), T(rd), **kw3); e3 = render(model, T(ro), T(rd), eager_test_loop=True, **kw3)
+    assert int(c3["total_samples"]) == int(e3["total_samples"]) and torch.equal(c3["rgb"], e3["rgb"])
 
 
 def test_gather_rays_vs_reference_expression(vren):
