@@ -61,10 +61,16 @@ inline int pipeline_parts(int64_t n) {
 
 constexpr int kFwSmemTile32 = 128 * 64;    // 128 rows x 32 halves
 constexpr int kFwSmemTile64 = 128 * 128;   // 128 rows x 64 halves
-// shared-memory map of the forward (offsets from the 1024-aligned base)
-constexpr int kFwF0 = kWimgBytes, kFwF1 = kFwF0 + kFwSmemTile32, kFwI = kFwF1 + kFwSmemTile32, kFwH0 = kFwI + kFwSmemTile32,
-              kFwH1 = kFwH0 + kFwSmemTile64, kFwH2 = kFwH1 + kFwSmemTile64, kFwHS = kFwH2 + kFwSmemTile64;
-constexpr int kFwSmemBytes = kFwHS + 128 * 64 + 1024;  // + h staging (128 x 16 f32) + alignment slack
+// Shared-memory map of the forward (offsets from the 1024-aligned base): weight image | F0 F1 (feature tiles, double
+// buffered) | A B (two 16 KB activation buffers used in turn: hid -> A, in32 -> B, hid1 -> A, hid2 -> B).  The h staging
+// tile (128 x 16 f32) reuses the current feature buffer, free once the first MMA has read it.  68 KB + slack: THREE CTAs
+// per SM (the kernel is a chain of short latencies per tile -- MMA completion, TMEM load, shared-memory fence -- and the
+// tensor pipe idles ~90 % of the time with two tiles in flight per SM).  A buffer is overwritten two layers after it was
+// written; its bulk store (issued one layer after the write) has then had a whole layer to read it, and the thread that
+// issues the MMAs waits for that read before it issues the layer whose epilogue overwrites the buffer.
+constexpr int kFwF0 = kWimgBytes, kFwF1 = kFwF0 + kFwSmemTile32, kFwA = kFwF1 + kFwSmemTile32, kFwB = kFwA + kFwSmemTile64;
+constexpr int kFwSmemBytes = kFwB + kFwSmemTile64 + 1024;  // + alignment slack
+constexpr int kFwCtasPerSm = 3;
 
 __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __restrict__ feat, const float* __restrict__ dirs, int64_t n,
                                                               const int32_t* __restrict__ n_dev, const uint8_t* __restrict__ wimg, int rgb_act, int with_rgb,
@@ -99,8 +105,9 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
 
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes; lane == sample row
     const uint64_t aF0 = smem_desc<64>(base + kFwF0), aF1 = smem_desc<64>(base + kFwF1);
-    const uint64_t aI = smem_desc<64>(base + kFwI);
-    const uint64_t aH0 = smem_desc<128>(base + kFwH0), aH1 = smem_desc<128>(base + kFwH1), aH2 = smem_desc<128>(base + kFwH2);
+    const uint64_t aI = smem_desc<64>(base + kFwB);
+    const uint64_t aH0 = smem_desc<128>(base + kFwA), aH1 = smem_desc<128>(base + kFwA), aH2 = smem_desc<128>(base + kFwB);
+    constexpr int kFwH0 = kFwA, kFwI = kFwB, kFwH1 = kFwA, kFwH2 = kFwB;
     const uint64_t bD1 = smem_desc<64>(sW + kWimgD1), bD2 = smem_desc<128>(sW + kWimgD2);
     const uint64_t bC1 = smem_desc<64>(sW + kWimgC1), bC2 = smem_desc<128>(sW + kWimgC2), bC3 = smem_desc<128>(sW + kWimgC3);
     constexpr uint32_t kI64 = instr_desc(128, 64, 0, 0), kI16 = instr_desc(128, 16, 0, 0);
@@ -108,10 +115,13 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
 
     // issue one layer: D[tmem cols] = A (128 x K) * W^T, K = 16 * ksteps; then commit.  The barrier in front publishes the
     // A tile the threads have just written (generic proxy -> async proxy) to the tensor core AND to the TMA engine.
-    auto issue_only = [&](uint32_t dcol, uint64_t a, uint64_t b, uint32_t idesc, int ksteps) {
+    // free_buf: the epilogue of this layer overwrites a buffer that an earlier bulk store may still be reading; the issuing
+    // thread waits for those reads BEFORE it issues the MMAs, and the other threads cannot write before the MMAs commit.
+    auto issue_only = [&](uint32_t dcol, uint64_t a, uint64_t b, uint32_t idesc, int ksteps, bool free_buf) {
         fence_before_sync(); fence_async_smem(); __syncthreads();
         if (tid == 0) {
             fence_after_sync();
+            if (free_buf) bulk_wait_read<0>();
             for (int k = 0; k < ksteps; k++) mma_f16(tmem + dcol, desc_advance(a, 32 * k), desc_advance(b, 32 * k), idesc, k > 0);
             mma_commit(bar_mma);
         }
@@ -141,10 +151,10 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
         const int buf = it & 1;
+        const int kFwHS = buf ? kFwF1 : kFwF0;  // h staging: the feature buffer of this tile, once the first MMA has read it
         uint8_t* pF = sm + (buf ? kFwF1 : kFwF0);
         if (tid == 0) {
-            // the previous tile's bulk stores have left shared memory (they are a whole tile old): H0..H2, I, HS are free;
-            // F[buf^1] was released by the previous tile's first MMA
+            // F[buf^1] held the previous tile's features and then its h staging tile, whose bulk store must have read it
             bulk_wait_read<0>();
             const int64_t next = tile + gridDim.x;
             if (next < n_tiles) {
@@ -160,11 +170,11 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
         }
         const float dcur[3] = {dr[0], dr[1], dr[2]};
         // ---- density layer 1: A = feature tile
-        issue_only(0, buf ? aF1 : aF0, bD1, kI64, 2);
+        issue_only(0, buf ? aF1 : aF0, bD1, kI64, 2, true);    // epilogue -> A (previous tile's hid1)
         wait_mma();
         hidden_row(trow + 0, sm + kFwH0);
         // ---- density layer 2 -> h (16, fp32), sigma
-        issue_only(64, aH0, bD2, kI16, 4);
+        issue_only(64, aH0, bD2, kI16, 4, true);                 // epilogue -> B (previous tile's hid2), h staging
         if (tid == 0 && hid) { bulk_s2g(hid + tile * 128 * 64, base + kFwH0, kFwSmemTile64); bulk_commit(); }
         wait_mma();
         {
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
             continue;
         }
         // ---- colour layer 1
-        issue_only(0, aI, bC1, kI64, 2);
+        issue_only(0, aI, bC1, kI64, 2, true);                   // epilogue -> A (hid)
         if (tid == 0) {
             if (hid) bulk_s2g(in32 + tile * 128 * 32, base + kFwI, kFwSmemTile32);
             if (h) bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64);
@@ -204,12 +214,12 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
         wait_mma();
         hidden_row(trow + 0, sm + kFwH1);
         // ---- colour layer 2
-        issue_only(64, aH1, bC2, kI64, 4);
+        issue_only(64, aH1, bC2, kI64, 4, true);                 // epilogue -> B (in32)
         if (tid == 0 && hid) { bulk_s2g(hid1 + tile * 128 * 64, base + kFwH1, kFwSmemTile64); bulk_commit(); }
         wait_mma();
         hidden_row(trow + 64, sm + kFwH2);
         // ---- colour layer 3 -> rgb
-        issue_only(0, aH2, bC3, kI16, 4);
+        issue_only(0, aH2, bC3, kI16, 4, false);
         if (tid == 0 && hid) { bulk_s2g(hid2 + tile * 128 * 64, base + kFwH2, kFwSmemTile64); bulk_commit(); }
         fetch_dir(tile + gridDim.x);
         wait_mma();
@@ -260,12 +270,13 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
     if (!n_sm) {
         int dev = 0; ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
+        ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     // Pipelined over `parts` consecutive ranges of tiles: the hash-grid forward (gathers out of L2) of range p+1 runs on
     // a second stream under the MLP (tensor core + HBM stores) of range p -- the two kernels stress different units.
     const int64_t n_tiles = (n + 127) / 128;
     const int parts = pipeline_parts(n);
-    const int grid = (int)max((int64_t)1, min((int64_t)n_sm * 2, (n_tiles + parts - 1) / parts));
+    const int grid = (int)max((int64_t)1, min((int64_t)n_sm * kFwCtasPerSm, (n_tiles + parts - 1) / parts));
     PipeStreams* ps = nullptr;
     if (parts > 1) {
         if (int e = pipe_streams(&ps)) return e;

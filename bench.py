@@ -410,9 +410,9 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        mrays, cores, sec = cpu_reference(BATCH, 8, 1)
+        mrays, cores, sec = cpu_reference(BATCH, 16, 1)
         cpu = {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port",
-               "sample": f"8 timed oracle steps of the full {BATCH}-ray batch (1 untimed), {sec:.2f} s each, C + OpenMP on {cores} threads"}
+               "sample": f"16 timed oracle steps of the full {BATCH}-ray batch (1 untimed), {sec:.2f} s each, C + OpenMP on {cores} threads"}
 
     if rank == 0:
         line = {"metric": "train_Mrays_per_s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
