@@ -53,6 +53,13 @@ class TestIterCfg(C.Structure):
                 ("opacity", P), ("depth", P), ("rgb", P), ("alive_out", P), ("total_samples", P)]
 
 
+class SgTables(C.Structure):
+    """Mirror of arn_sg_tables_t (include/arnerf.h)."""
+    _fields_ = [("coeff_cl", P), ("D", I), ("H", I), ("W", I), ("C", I), ("components", P), ("mean", P), ("envH", I), ("envW", I),
+                ("fh_tab", P), ("fh_h", I), ("fh_w", I), ("vol_range", F), ("angle_decay_fac", F), ("shadow_pow_fac", F),
+                ("self_shadow_pow_fac", F)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/arnerf.h one to one
 SIGNATURES = {
     "arn_version": [],
@@ -115,6 +122,9 @@ SIGNATURES = {
     "arn_hash_encode_fw": [P, L, P, P, Levels, P, P, P],
     "arn_hash_encode_bw": [P, L, P, P, Levels, P, P, P, P, P],
     "arn_sh4": [P, L, P, P],
+    "arn_sg_shadow_factor": [C.POINTER(SgTables), P, I, P, L, P, P, F, P, P, P],
+    "arn_sg_shade": [C.POINTER(SgTables), P, P, I, P, L, P, P, F, P, P, P, P, P, I, I, P, P, P, P],
+    "arn_sg_shade_px": [P, I, I, L, P, P, P, P, P, I, P, P],
     "arn_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, I, P],
 }
 _RESTYPES = {"arn_last_error": C.c_char_p, "arn_launch_count": C.c_int64}

@@ -422,6 +422,48 @@ int arn_p2p_adam_exchange(void* const* peer_grads_host, void* const* peer_p16_ho
                           float* params_slice, float* exp_avg_slice, float* exp_avg_sq_slice, float lr, float beta1,
                           float beta2, float eps, int step, float inv_grad_scale, arn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Spherical-Gaussian shadow and shading of an inserted object (AR insertion frame, BASELINE.json configs[4]).
+ * Replaces insert/sg_shadow.py:103-116 SGShadow.calc_shadow_factor, :118-153 SGShadow.calc_self_shadow_light_dacay and
+ * insert/render_utils.py:321-375 SG_render_core (with :266-318 SGProduct / SGHemisphereIntegral / SGIrradiance).
+ * Tables (device, fp32): coeff_cl = the PCA coefficient volume CHANNEL-LAST (D,H,W,C) -- the reference's
+ * coeff_volume (1,C,D,H,W) permuted once by the caller; components (C,envH,envW), mean (envH,envW) = the PCA basis over the
+ * light direction; fh_tab (fh_h = sharpness rows, fh_w = angle columns) = insert/data/fh_pretab.npy.
+ * lSGs (L,7) = axis(3) | sharpness | rgb; pts (n,3) world positions; model_pos_host (3), rot_inv_host (9, row-major, may
+ * be NULL), scale = model radius.  light_scratch: ARN_SG_SCRATCH_FLOATS(L, C) floats of device scratch (per-light tables
+ * built by a one-block prologue kernel).  All arithmetic fp32 in the reference's operation order; grid_sample's
+ * bilinear / padding_mode='border' rules (align_corners as the reference calls it: True for the volume only).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define ARN_SG_MAX_LIGHTS 64
+#define ARN_SG_MAX_COMPONENTS 32
+#define ARN_SG_SCRATCH_FLOATS(n_lights, n_components) ((n_lights) * ((n_components) + 12) + 3)
+typedef struct {
+    const float* coeff_cl; int D; int H; int W; int C;
+    const float* components; const float* mean; int envH; int envW;
+    const float* fh_tab; int fh_h; int fh_w;
+    float vol_range; float angle_decay_fac; float shadow_pow_fac; float self_shadow_pow_fac;
+} arn_sg_tables_t;
+/* factor (n): the shadow the object casts on scene points (lSGs already rotated into the model frame by the caller when
+ * rot_inv_host is given, as main.py:496-499 does). */
+int arn_sg_shadow_factor(const arn_sg_tables_t* tables_host, const float* lSGs, int n_lights, const float* pts, int64_t n,
+                         const float* model_pos_host, const float* rot_inv_host, float scale, float* light_scratch,
+                         float* factor, arn_stream_t stream);
+/* Self-shadow attenuation of the lights per pixel fused with SG_render_core: radiance (n,3).  lSGs_axis (L,7; may be NULL =
+ * lSGs) supplies the axes used for the environment lookup (the lights rotated into the model frame), lSGs the axes /
+ * sharpness / colours that are shaded.  self_shadow = 0: SG_render_core(..., self_shadow=False) on lSGs as they are.
+ * lSGs_out (n,L,7), optional: the attenuated lights (what calc_self_shadow_light_dacay returns); radiance == NULL computes
+ * only those.  albedo (n,3), metal (n), rough (n), normal (n,3) (any length), vdirs (n,3) unit view directions. */
+int arn_sg_shade(const arn_sg_tables_t* tables_host, const float* lSGs, const float* lSGs_axis, int n_lights, const float* pts,
+                 int64_t n, const float* model_pos_host, const float* rot_inv_host, float scale, const float* albedo,
+                 const float* metal, const float* rough, const float* normal, const float* vdirs, int clamp01, int self_shadow,
+                 float* light_scratch, float* lSGs_out, float* radiance, arn_stream_t stream);
+
+/* SG_render_core on lights given by the caller: per_pixel = 1: lSGs (n,L,7), one set per pixel (self_shadow=True: what
+ * calc_self_shadow_light_dacay returned); per_pixel = 0: lSGs (L,7) shared by all pixels (self_shadow=False). */
+int arn_sg_shade_px(const float* lSGs, int n_lights, int per_pixel, int64_t n, const float* albedo, const float* metal,
+                    const float* rough, const float* normal, const float* vdirs, int clamp01, float* radiance,
+                    arn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
