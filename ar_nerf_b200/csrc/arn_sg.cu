@@ -73,8 +73,13 @@ __global__ void sg_light_tables_kernel(arn_sg_tables_t tb, const float* __restri
 
 struct SgFrame { float pos[3]; float rot[9]; int has_rot; float scale; };
 
-// sg_shadow.py:80-101 up to the PCA coefficients: pca[C] and the angle term of the point
-__device__ __forceinline__ void pca_of_point(const arn_sg_tables_t& tb, const SgFrame& fr, const float* __restrict__ pt, float* pca, float& delta) {
+// sg_shadow.py:80-101: ssdf of one point against every light, clipped to [-pi/2, pi/2] (:111), left in shared memory at
+// ssdf[l * blockDim.x + threadIdx.x].  The PCA coefficients are fetched 32 at a time (registers: static indices) and each
+// chunk is folded into the per-light sums straight away, so any number of components up to ARN_SG_MAX_COMPONENTS works
+// without spilling (the insertion tool runs 128: insert/main.py:107).
+__device__ __forceinline__ void ssdf_of_point(const arn_sg_tables_t& tb, const SgFrame& fr, const float* __restrict__ pt,
+                                              const float* __restrict__ lights, int n_lights, float* __restrict__ ssdf) {
+    const int rec = tb.C + kLRec;
     float m[3] = {pt[0] - fr.pos[0], pt[1] - fr.pos[1], pt[2] - fr.pos[2]};
     if (fr.has_rot) {
         const float a = fr.rot[0] * m[0] + fr.rot[1] * m[1] + fr.rot[2] * m[2];
@@ -88,7 +93,7 @@ __device__ __forceinline__ void pca_of_point(const arn_sg_tables_t& tb, const Sg
     const float dis = fmaxf(sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]), 1.0f);
 #pragma unroll
     for (int k = 0; k < 3; k++) p[k] = p[k] / dis;
-    delta = (asinf(1.0f / tb.vol_range) - asinf(1.0f / (dis * tb.vol_range))) * tb.angle_decay_fac;
+    const float delta = (asinf(1.0f / tb.vol_range) - asinf(1.0f / (dis * tb.vol_range))) * tb.angle_decay_fac;
     // grid_sample 3-D: x -> W, y -> H, z -> D; bilinear, border, align_corners = True
     const int S[3] = {tb.W, tb.H, tb.D};
     int i0[3]; float w1[3]; bool ok1[3];
@@ -98,30 +103,54 @@ __device__ __forceinline__ void pca_of_point(const arn_sg_tables_t& tb, const Sg
         const float f = floorf(i);
         i0[k] = (int)f; w1[k] = i - f; ok1[k] = i0[k] + 1 < S[k];
     }
-#pragma unroll
-    for (int c = 0; c < kSgMaxComp; c++) pca[c] = 0.0f;   // (static indices: the coefficients stay in registers)
+    float cw[8]; size_t coff[8];
 #pragma unroll
     for (int corner = 0; corner < 8; corner++) {
         const int dx = corner & 1, dy = (corner >> 1) & 1, dz = corner >> 2;
-        if ((dx && !ok1[0]) || (dy && !ok1[1]) || (dz && !ok1[2])) continue;
-        const float w = (dx ? w1[0] : 1.0f - w1[0]) * (dy ? w1[1] : 1.0f - w1[1]) * (dz ? w1[2] : 1.0f - w1[2]);
-        const float4* src = reinterpret_cast<const float4*>(tb.coeff_cl + ((size_t)((i0[2] + dz) * tb.H + (i0[1] + dy)) * tb.W + (i0[0] + dx)) * tb.C);
+        const bool ok = !((dx && !ok1[0]) || (dy && !ok1[1]) || (dz && !ok1[2]));
+        cw[corner] = ok ? (dx ? w1[0] : 1.0f - w1[0]) * (dy ? w1[1] : 1.0f - w1[1]) * (dz ? w1[2] : 1.0f - w1[2]) : 0.0f;
+        coff[corner] = ok ? ((size_t)((i0[2] + dz) * tb.H + (i0[1] + dy)) * tb.W + (i0[0] + dx)) * tb.C : 0;
+    }
+    for (int l = 0; l < n_lights; l++) ssdf[l * blockDim.x + threadIdx.x] = 0.0f;
+    for (int c0 = 0; c0 < tb.C; c0 += 32) {
+        float pca[32];
 #pragma unroll
-        for (int c4 = 0; c4 < kSgMaxComp / 4; c4++) {
-            if (4 * c4 < tb.C) {
-                const float4 v = __ldg(src + c4);
-                pca[4 * c4] += v.x * w; pca[4 * c4 + 1] += v.y * w; pca[4 * c4 + 2] += v.z * w; pca[4 * c4 + 3] += v.w * w;
+        for (int c = 0; c < 32; c++) pca[c] = 0.0f;
+#pragma unroll
+        for (int corner = 0; corner < 8; corner++) {
+            if (cw[corner] == 0.0f) continue;  // (outside the volume's last cell, or a zero weight: contributes nothing)
+            const float4* src = reinterpret_cast<const float4*>(tb.coeff_cl + coff[corner] + c0);
+            const float w = cw[corner];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++) {
+                if (c0 + 4 * c4 < tb.C) {
+                    const float4 v = __ldg(src + c4);
+                    pca[4 * c4] += v.x * w; pca[4 * c4 + 1] += v.y * w; pca[4 * c4 + 2] += v.z * w; pca[4 * c4 + 3] += v.w * w;
+                }
             }
         }
+        for (int l = 0; l < n_lights; l++) {
+            // (records are 16-byte aligned: C and the header are multiples of 4 floats; one 128-bit broadcast load per 4 components)
+            const float4* comp = reinterpret_cast<const float4*>(lights + l * rec + kLRec + c0);
+            float acc = 0.0f;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++) {
+                if (c0 + 4 * c4 < tb.C) {
+                    const float4 q = comp[c4];
+                    acc += pca[4 * c4] * q.x; acc += pca[4 * c4 + 1] * q.y; acc += pca[4 * c4 + 2] * q.z; acc += pca[4 * c4 + 3] * q.w;
+                }
+            }
+            ssdf[l * blockDim.x + threadIdx.x] += acc;
+        }
+    }
+    for (int l = 0; l < n_lights; l++) {
+        const float v = ssdf[l * blockDim.x + threadIdx.x] + lights[l * rec + kLMean] + delta;
+        ssdf[l * blockDim.x + threadIdx.x] = clampf(v, -kPi / 2.0f, kPi / 2.0f);
     }
 }
 
-// f_h of (pixel, light): ssdf = clip(pca . comp_s + mean_s + delta) -> table fetch (sg_shadow.py:55-64)
-__device__ __forceinline__ float fh_of(const arn_sg_tables_t& tb, const float* __restrict__ rec, const float* pca, float delta) {
-    float ssdf = 0.0f;
-#pragma unroll
-    for (int c = 0; c < kSgMaxComp; c++) if (c < tb.C) ssdf += pca[c] * rec[kLRec + c];
-    ssdf = clampf(ssdf + rec[kLMean] + delta, -kPi / 2.0f, kPi / 2.0f);
+// f_h of (pixel, light) from the clipped ssdf: table fetch (sg_shadow.py:55-64)
+__device__ __forceinline__ float fh_of(const arn_sg_tables_t& tb, const float* __restrict__ rec, float ssdf) {
     const float ix = clampf(unnorm(ssdf / (kPi / 2.0f), tb.fh_w, false), 0.0f, (float)(tb.fh_w - 1));
     const float fx = floorf(ix);
     const int x0 = (int)fx, y0 = (int)rec[kLRow0];
@@ -143,12 +172,12 @@ __global__ void __launch_bounds__(128) sg_shadow_factor_kernel(arn_sg_tables_t t
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float pca[kSgMaxComp], delta;
-    pca_of_point(tb, fr, pts + 3 * i, pca, delta);
+    float* ssdf = sm + n_lights * rec + 4;
+    ssdf_of_point(tb, fr, pts + 3 * i, sm, n_lights, ssdf);
     float col[3] = {0.f, 0.f, 0.f};
     for (int l = 0; l < n_lights; l++) {                       // fhs @ lcols (sg_shadow.py:65-67)
         const float* r = sm + l * rec;
-        const float fh = fh_of(tb, r, pca, delta);
+        const float fh = fh_of(tb, r, ssdf[l * blockDim.x + threadIdx.x]);
         col[0] += fh * r[kLCol]; col[1] += fh * r[kLCol + 1]; col[2] += fh * r[kLCol + 2];
     }
     const float* inte_L = sm + n_lights * rec;
@@ -255,8 +284,8 @@ __global__ void __launch_bounds__(128) sg_shade_kernel(arn_sg_tables_t tb, SgFra
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float pca[kSgMaxComp], delta = 0.0f;
-    if (self_shadow) pca_of_point(tb, fr, pts + 3 * i, pca, delta);
+    float* ssdf = sm + n_lights * rec + 4;
+    if (self_shadow) ssdf_of_point(tb, fr, pts + 3 * i, sm, n_lights, ssdf);
     ShadePix sp;
     if (shade) shade_begin(normal, vdirs, rough, i, sp);
     float spec_irr[3] = {0.f, 0.f, 0.f}, diff_irr[3] = {0.f, 0.f, 0.f};
@@ -266,7 +295,7 @@ __global__ void __launch_bounds__(128) sg_shade_kernel(arn_sg_tables_t tb, SgFra
 #pragma unroll
         for (int k = 0; k < 3; k++) { L.ax[k] = r[kLAxis + k]; L.col[k] = r[kLCol + k]; }
         if (self_shadow) {   // sg_shadow.py:131-152
-            const float fh = fh_of(tb, r, pca, delta);
+            const float fh = fh_of(tb, r, ssdf[l * blockDim.x + threadIdx.x]);
             const float decay = powf(clampf(fabsf(fh / r[kLFhN]), 0.0f, 1.0f), tb.self_shadow_pow_fac);
 #pragma unroll
             for (int k = 0; k < 3; k++) L.col[k] *= decay;
@@ -303,6 +332,8 @@ __global__ void __launch_bounds__(128) sg_shade_px_kernel(const float* __restric
     shade_end(sp, spec_irr, diff_irr, albedo, metal, rough, i, clamp01, radiance);
 }
 
+// per-light tables + inte_L (padded to 4 floats) + one ssdf per (light, thread of the 128-thread block)
+static size_t sg_smem_bytes(int n_lights, int C) { return ((size_t)n_lights * (C + kLRec) + 4 + (size_t)n_lights * 128) * sizeof(float); }
 static int check_tables(const arn_sg_tables_t* tb, int n_lights) {
     if (!tb || !tb->coeff_cl || !tb->components || !tb->mean || !tb->fh_tab) { set_error("arn_sg: null table pointer"); return ARN_E_INVALID; }
     if (tb->C < 4 || tb->C > kSgMaxComp || tb->C % 4 || n_lights < 1 || n_lights > kSgMaxLights || tb->D < 1 || tb->H < 1 || tb->W < 1 ||
@@ -337,7 +368,8 @@ extern "C" ARN_API int arn_sg_shadow_factor(const arn_sg_tables_t* tables_host, 
     const arn_sg_tables_t tb = *tables_host;
     ARN_LAUNCH("sg_light_tables_kernel", st, sg_light_tables_kernel<<<1, 256, 0, st>>>(tb, lSGs, lSGs, n_lights, light_scratch));
     if (int e = check_launch("sg_light_tables")) return e;
-    const size_t smem = ((size_t)n_lights * (tb.C + kLRec) + 3) * sizeof(float);
+    const size_t smem = sg_smem_bytes(n_lights, tb.C);
+    ARN_CUDA(cudaFuncSetAttribute(sg_shadow_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem_bytes(kSgMaxLights, kSgMaxComp)));
     ARN_LAUNCH("sg_shadow_factor_kernel", st, sg_shadow_factor_kernel<<<ceil_div(n, 128), 128, smem, st>>>(tb, make_frame(model_pos_host, rot_inv_host, scale), light_scratch,
                                                                                                           n_lights, pts, n, factor));
     return check_launch("sg_shadow_factor");
@@ -359,7 +391,8 @@ extern "C" ARN_API int arn_sg_shade(const arn_sg_tables_t* tables_host, const fl
     const arn_sg_tables_t tb = *tables_host;
     ARN_LAUNCH("sg_light_tables_kernel", st, sg_light_tables_kernel<<<1, 256, 0, st>>>(tb, lSGs_axis ? lSGs_axis : lSGs, lSGs, n_lights, light_scratch));
     if (int e = check_launch("sg_light_tables")) return e;
-    const size_t smem = ((size_t)n_lights * (tb.C + kLRec) + 3) * sizeof(float);
+    const size_t smem = sg_smem_bytes(n_lights, tb.C);
+    ARN_CUDA(cudaFuncSetAttribute(sg_shade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem_bytes(kSgMaxLights, kSgMaxComp)));
     ARN_LAUNCH("sg_shade_kernel", st, sg_shade_kernel<<<ceil_div(n, 128), 128, smem, st>>>(tb, make_frame(model_pos_host, rot_inv_host, scale > 0.0f ? scale : 1.0f),
                                                                                          light_scratch, n_lights, pts, n, albedo, metal, rough, normal, vdirs,
                                                                                          clamp01, self_shadow, shade ? 1 : 0, lSGs_out, radiance));

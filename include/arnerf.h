@@ -435,7 +435,7 @@ int arn_p2p_adam_exchange(void* const* peer_grads_host, void* const* peer_p16_ho
  * bilinear / padding_mode='border' rules (align_corners as the reference calls it: True for the volume only).
  * ---------------------------------------------------------------------------------------------------------- */
 #define ARN_SG_MAX_LIGHTS 64
-#define ARN_SG_MAX_COMPONENTS 32
+#define ARN_SG_MAX_COMPONENTS 128
 #define ARN_SG_SCRATCH_FLOATS(n_lights, n_components) ((n_lights) * ((n_components) + 12) + 3)
 typedef struct {
     const float* coeff_cl; int D; int H; int W; int C;

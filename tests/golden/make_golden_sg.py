@@ -78,7 +78,10 @@ def main():
         # reference's output is rounding noise (its float64 evaluation lies up to 0.2 away, i.e. ~2 noise units).  The tests
         # hold a result to |x - reference| <= 1e-4 relative + 4 noise units.
         rs = np.random.RandomState(1)
-        jit = lambda x: torch.from_numpy((x.numpy().view(np.int32) + rs.choice([-1, 0, 1], size=tuple(x.shape)).astype(np.int32)).view(np.float32))
+        def jit(x):
+            x = x.numpy(); step = rs.choice([-1, 0, 1], size=x.shape)
+            far = np.where(step > 0, np.float32(np.inf), np.float32(-np.inf)).astype(np.float32)
+            return torch.from_numpy(np.where(step == 0, x, np.nextafter(x, far)).astype(np.float32))
         for name, lights, shadow in (("radiance_clamp", dec, True), ("radiance_hdr", dec_rot, True), ("radiance_noshadow", lSGs, False)):
             base = render_utils.SG_render_core(*args, lights, False, shadow).numpy()
             noise = np.zeros_like(base)

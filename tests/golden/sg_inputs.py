@@ -16,13 +16,14 @@ def _unit(v):
     return v / np.linalg.norm(v, axis=-1, keepdims=True)
 
 
-def make_inputs(seed=0):
+def make_inputs(seed=0, ncomp=NCOMP, grid=(GRID, GRID, GRID), env=(ENV, ENV)):
+    """grid = (D, H, W) of the coefficient volume, env = (envH, envW); the golden file uses the defaults."""
     r = np.random.RandomState(seed)
     f = np.float32
     d = {}
-    d["coeff_volume"] = (r.randn(1, NCOMP, GRID, GRID, GRID) * 0.3).astype(f)     # 1,C,D,H,W as SGShadow.__init__ lays it out
-    d["components"] = (r.randn(NCOMP, ENV, ENV) * 0.2).astype(f)
-    d["mean"] = (r.randn(1, ENV, ENV) * 0.3).astype(f)
+    d["coeff_volume"] = (r.randn(1, ncomp, *grid) * 0.3 * np.sqrt(NCOMP / ncomp)).astype(f)   # 1,C,D,H,W as SGShadow.__init__ lays it out
+    d["components"] = (r.randn(ncomp, *env) * 0.2).astype(f)
+    d["mean"] = (r.randn(1, *env) * 0.3).astype(f)
     axis = _unit(r.randn(N_LIGHTS, 3))
     lam = 10.0 ** r.uniform(-0.5, 3.0, (N_LIGHTS, 1))
     col = r.uniform(0.05, 2.0, (N_LIGHTS, 3))
