@@ -117,6 +117,7 @@ SIGNATURES = {
     "arn_render_test_step": [C.POINTER(TestIterCfg), P, P, P, I, I, L, P],
     "arn_train_march": [C.POINTER(TrainCfg), P],
     "arn_train_set_fork": [I, P],
+    "arn_train_set_join": [I, P],
     "arn_train_fwbw_marched": [C.POINTER(TrainCfg), P],
     "arn_field_bw_simt": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
     "arn_hash_encode_fw": [P, L, P, P, Levels, P, P, P],

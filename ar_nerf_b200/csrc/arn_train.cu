@@ -108,11 +108,20 @@ extern "C" ARN_API int arn_train_march(const arn_train_t* c, arn_stream_t stream
 namespace arn {
 thread_local int g_fork_stage = -1;
 thread_local cudaEvent_t g_fork_event = nullptr;
+thread_local int g_join_stage = -1;
+thread_local cudaEvent_t g_join_event = nullptr;
 int train_fork(int stage, cudaStream_t st) {
+    if (g_join_event && g_join_stage == stage) ARN_CUDA(cudaStreamWaitEvent(st, g_join_event, 0));
     if (g_fork_event && g_fork_stage == stage) ARN_CUDA(cudaEventRecord(g_fork_event, st));
     return ARN_OK;
 }
 }  // namespace arn
+extern "C" ARN_API int arn_train_set_join(int stage, void* cuda_event) {
+    ARN_REQUIRE(!cuda_event || (stage >= 0 && stage <= 4), "stage must be 0..4");
+    arn::g_join_stage = cuda_event ? stage : -1;
+    arn::g_join_event = (cudaEvent_t)cuda_event;
+    return ARN_OK;
+}
 extern "C" ARN_API int arn_train_set_fork(int stage, void* cuda_event) {
     ARN_REQUIRE(!cuda_event || (stage >= 0 && stage <= 4), "stage must be 0..4");
     arn::g_fork_stage = cuda_event ? stage : -1;

@@ -106,6 +106,18 @@ class FusedAdam:
             if cache is not None:
                 cache.mark_fresh(p)
 
+    def pending_zero(self):
+        """The peer exchange whose gradient buffer is still being zeroed on its side stream, or None."""
+        for *_, st in self.items:
+            if st is not None and st["px"] is not None and st["px"].zero_pending:
+                return st["px"]
+        return None
+
+    def wait_zeroed(self):
+        for *_, st in self.items:
+            if st is not None and st["px"] is not None:
+                st["px"].wait_zeroed()
+
     @torch.no_grad()
     def gather_master(self):
         """Make the fp32 master of every sharded parameter current on all ranks (checkpoints, evaluation in fp32)."""
@@ -273,7 +285,13 @@ class NGPTrainer:
                 w.marched.record(main)     # creates the CUDA event handle
                 w.fork_armed = True
             call("arn_train_set_fork", self.fork_stage, C.c_void_p(w.marched.cuda_event))
+        px = self.opt.pending_zero()
+        if px is not None:  # the gradient buffer is being zeroed on a side stream: the MLP backward (first writer) waits for it
+            call("arn_train_set_join", 2, C.c_void_p(px.zeroed.cuda_event))
         call("arn_train_fwbw_marched", C.byref(self._cfg(ms, self._keep_target)), main_h)
+        if px is not None:
+            call("arn_train_set_join", 0, None)
+            px.zero_pending = False
         if prefetch is not None:
             call("arn_train_set_fork", 0, None)
         if prefetch is not None:
@@ -314,6 +332,7 @@ class NGPTrainer:
             self.opt.step(inv_grad_scale=1.0 / (self.grad_scale * self.world))
             self.global_step += 1
             return loss, results
+        self.opt.wait_zeroed()
         kwargs = {'test_time': False, 'random_bg': self.random_bg, 'exp_step_factor': self.exp_step_factor}
         if noise is not None:
             kwargs['noise'] = noise

@@ -310,6 +310,10 @@ int arn_train_fwbw_marched(const arn_train_t* cfg_host, arn_stream_t stream);
  * so that the caller can make the side stream wait there: the ray march is issue-bound and shares an SM best with the
  * memory-bound tail of the step (hash-grid reductions, Adam).  cuda_event == NULL switches the recording off. */
 int arn_train_set_fork(int stage, void* cuda_event);
+/* The opposite direction: the next arn_train_fwbw_marched calls of this thread make their stream WAIT for `cuda_event`
+ * in front of stage `stage` (same numbering; 2 = in front of the MLP backward, the first kernel that writes parameter
+ * gradients) -- e.g. for a gradient buffer that a side stream zeroes while the forward runs.  NULL switches it off. */
+int arn_train_set_join(int stage, void* cuda_event);
 /* Compositing forward with the NeRFLoss epilogue of the fused step (one launch instead of two; rays_a in canonical ray
  * order).  Same outputs as arn_composite_train_fw followed by arn_nerf_loss. */
 int arn_composite_train_fw_loss(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
@@ -421,6 +425,7 @@ int arn_p2p_barrier(void* const* peer_flags_host, const void* my_flags, int n_ra
 int arn_p2p_adam_exchange(void* const* peer_grads_host, void* const* peer_p16_host, int n_ranks, int64_t lo, int64_t count,
                           float* params_slice, float* exp_avg_slice, float* exp_avg_sq_slice, float lr, float beta1,
                           float beta2, float eps, int step, float inv_grad_scale, arn_stream_t stream);
+
 
 /* ------------------------------------------------------------------------------------------------------------
  * Spherical-Gaussian shadow and shading of an inserted object (AR insertion frame, BASELINE.json configs[4]).
