@@ -114,6 +114,8 @@ SIGNATURES = {
     "arn_train_fwbw": [C.POINTER(TrainCfg), P],
     "arn_render_test_iter": [C.POINTER(TestIterCfg), P],
     "arn_march_test_far_clamp": [P, P, P, L, P, I, I, F, F, I, P],
+    "arn_march_test_all": [P, P, P, L, P, I, I, F, F, I, I, P, P, P, P],
+    "arn_render_test_step_pre": [C.POINTER(TestIterCfg), P, P, P, P, P, P, I, I, L, P],
     "arn_render_test_step": [C.POINTER(TestIterCfg), P, P, P, I, I, L, P],
     "arn_train_march": [C.POINTER(TrainCfg), P],
     "arn_train_set_fork": [I, P],

@@ -984,6 +984,74 @@ __global__ void __launch_bounds__(256) march_test_warp_kernel(const float* __res
     }
 }
 
+// ---- The frame's samples marched ONCE (arn_march_test_all): the test march is resumable and deterministic -- an iteration
+// starts at the chain point behind the previous iteration's last sample -- so the sequence of samples of a ray does not
+// depend on how the loop slices it.  One thread per ray marches the whole ray and records the parameter t of every
+// occupied sample, sample-major (ts_all[s * n_rays + r]: neighbouring rays write neighbouring words), up to `stride`
+// samples (the loop never asks a ray for more than max_samples + 63); an iteration of the loop then only slices the
+// next N_samples of each alive ray (neff / emit kernels below) instead of marching -- no iteration waits for a thread
+// that crosses an empty stretch, and no empty cell is probed twice.  dt of a sample is calc_dt(t), as the march computes it.
+template <bool FAST>
+__global__ void __launch_bounds__(128) march_test_all_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                             const float* __restrict__ hits_t, int64_t n_rays,
+                                                             const uint8_t* __restrict__ bitfield, ArnMarchConsts c, int stride,
+                                                             float* __restrict__ ts_all, int32_t* __restrict__ totals, int32_t* __restrict__ cursor) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const ArnRay ray = arn_load_ray(rays_o + 3 * r, rays_d + 3 * r);
+    float t = hits_t[2 * r]; const float t2 = hits_t[2 * r + 1];
+    int s = 0;
+    while (t < t2 && s < stride) {
+        float x, y, z, dt;
+        if (arn_march_eval_t<FAST>(c, ray, bitfield, t, x, y, z, dt)) {
+            ts_all[(int64_t)s * n_rays + r] = t;
+            t = __fadd_rn(t, dt);
+            s++;
+        }
+    }
+    totals[r] = s; cursor[r] = 0;
+}
+
+// N_eff of the iteration for every alive ray (what the march would have returned) + chunk sums for the scan
+__global__ void __launch_bounds__(128) neff_test_pre_kernel(const int64_t* __restrict__ alive, const int32_t* __restrict__ state,
+                                                            const int32_t* __restrict__ totals, const int32_t* __restrict__ cursor,
+                                                            int32_t* __restrict__ n_eff, int32_t* __restrict__ partial) {
+    __shared__ int sm4[4];
+    const int64_t n_alive = state[kStN]; const int S = state[kStS];
+    for (int64_t base = (int64_t)blockIdx.x * 128; base < n_alive; base += (int64_t)gridDim.x * 128) {
+        const int64_t n = base + threadIdx.x;
+        int s = 0;
+        if (n < n_alive) {
+            const int64_t r = alive[n];
+            s = min(S, totals[r] - cursor[r]);
+            n_eff[n] = s;
+        }
+        const int tot = block_sum_128(s, sm4);
+        if (threadIdx.x == 0) partial[base >> 7] = tot;
+    }
+}
+
+// the iteration's samples sliced out of ts_all: padded (deltas, ts) for the compositing kernel, compact (xyzs, dirs) for the field
+__global__ void __launch_bounds__(256) emit_test_pre_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                            const int64_t* __restrict__ alive, const int32_t* __restrict__ state,
+                                                            const int64_t* __restrict__ rays_a, const float* __restrict__ ts_all,
+                                                            const int32_t* __restrict__ cursor, int64_t n_rays, ArnMarchConsts c,
+                                                            float* __restrict__ deltas, float* __restrict__ ts,
+                                                            float* __restrict__ xyzs, float* __restrict__ dirs) {
+    const int64_t n_alive = state[kStN]; const int S = state[kStS];
+    const int64_t total = n_alive * S;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = e / S; const int sl = (int)(e - n * S);
+        if (sl >= (int)rays_a[3 * n + 2]) continue;
+        const int64_t r = alive[n], o = rays_a[3 * n + 1] + sl;
+        const float t = ts_all[(int64_t)(cursor[r] + sl) * n_rays + r];
+        ts[e] = t; deltas[e] = arn_calc_dt(c, t);
+        const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+        xyzs[3 * o] = __fmaf_rn(dx, t, rays_o[3 * r]); xyzs[3 * o + 1] = __fmaf_rn(dy, t, rays_o[3 * r + 1]); xyzs[3 * o + 2] = __fmaf_rn(dz, t, rays_o[3 * r + 2]);
+        dirs[3 * o] = dx; dirs[3 * o + 1] = dy; dirs[3 * o + 2] = dz;
+    }
+}
+
 // Offsets of the compact sample list: rays_a[n] = (n, start, N) for the n_alive rays, counts = (valid samples, n_alive).
 __global__ void __launch_bounds__(1024) scan_test_dyn_kernel(const int32_t* __restrict__ counts_in, const int32_t* __restrict__ partial,
                                                              const int32_t* __restrict__ state, int64_t* __restrict__ rays_a,
@@ -1049,7 +1117,8 @@ __global__ void __launch_bounds__(128) composite_test_dyn_kernel(const float* __
                                                                  const int64_t* __restrict__ alive, const int32_t* __restrict__ state, float T_thr,
                                                                  const int64_t* __restrict__ rays_a, float* __restrict__ opacity,
                                                                  float* __restrict__ depth, float* __restrict__ rgb, int32_t* __restrict__ keep,
-                                                                 int32_t* __restrict__ partial, unsigned long long* __restrict__ total) {
+                                                                 int32_t* __restrict__ partial, unsigned long long* __restrict__ total,
+                                                                 int32_t* __restrict__ cursor) {
     __shared__ int sm4[4];
     const int64_t n_alive = state[kStN]; const int S = state[kStS];
     for (int64_t base = (int64_t)blockIdx.x * 128; base < n_alive; base += (int64_t)gridDim.x * 128) {
@@ -1060,6 +1129,7 @@ __global__ void __launch_bounds__(128) composite_test_dyn_kernel(const float* __
             if (ne > 0) {
                 live = true;
                 const int64_t r = alive[n], c0 = rays_a[3 * n + 1];
+                if (cursor) cursor[r] += ne;  // pre-marched frame: the ray's next slice starts behind these samples
                 float O = opacity[r];
                 float T = __fsub_rn(1.0f, O);
                 float cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2], D = depth[r];
@@ -1603,7 +1673,57 @@ extern "C" ARN_API int arn_render_test_step(const arn_test_iter_t* c, const int3
                                     c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
     ARN_LAUNCH("composite_test_dyn_kernel", st, composite_test_dyn_kernel<<<g128, 128, 0, st>>>(c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, state_in, c->T_threshold,
                                                                                             c->rays_a, c->opacity, c->depth, c->rgb, c->n_eff, partial,
-                                                                                            (unsigned long long*)c->total_samples));
+                                                                                            (unsigned long long*)c->total_samples, nullptr));
+    if (int e = check_launch("composite_test_dyn")) return e;
+    ARN_LAUNCH("alive_compact_dyn_kernel", st, alive_compact_dyn_kernel<<<g1024, 1024, 0, st>>>(c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
+                                                                                           c->counts_alive, state_out, c->n_alive, min_samples, budget_samples));
+    return check_launch("alive_compact_dyn");
+}
+
+// The frame's samples marched once (march_test_all_kernel): ts_all (stride x n_rays floats, sample-major), totals / cursor (n_rays).
+extern "C" ARN_API int arn_march_test_all(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                                          const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                                          float exp_step_factor, int max_samples, int stride, float* ts_all, int32_t* totals,
+                                          int32_t* cursor, arn_stream_t stream) {
+    ARN_REQUIRE(n_rays >= 0 && stride >= 1, "bad size");
+    if (n_rays == 0) return ARN_OK;
+    ARN_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && ts_all && totals && cursor, "null pointer");
+    if (int e = check_march_cfg(cascades, grid_size, max_samples)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ArnMarchConsts mc = arn_march_consts(cascades, grid_size, scale, (float)cascades, exp_step_factor, max_samples);  // the test march's dt (Q2)
+    if (cascades == 1 && grid_size <= 256)
+        ARN_LAUNCH("march_test_all_kernel", st, march_test_all_kernel<true><<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, mc, stride, ts_all, totals, cursor));
+    else
+        ARN_LAUNCH("march_test_all_kernel", st, march_test_all_kernel<false><<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, mc, stride, ts_all, totals, cursor));
+    return check_launch("march_test_all");
+}
+
+// arn_render_test_step on a frame marched by arn_march_test_all: the iteration slices its samples instead of marching.
+extern "C" ARN_API int arn_render_test_step_pre(const arn_test_iter_t* c, const int32_t* state_in, int32_t* state_out, int32_t* partial,
+                                                const float* ts_all, const int32_t* totals, int32_t* cursor, int min_samples,
+                                                int budget_samples, int64_t n_upper, arn_stream_t stream) {
+    ARN_REQUIRE(c && state_in && state_out && partial && ts_all && totals && cursor, "null pointer");
+    ARN_REQUIRE(c->n_alive > 0 && min_samples >= 1 && n_upper >= 0 && n_upper <= c->n_alive, "bad sizes");
+    ARN_REQUIRE(c->capacity >= c->n_alive * (int64_t)min_samples, "capacity must hold N_rays * min_samples samples");
+    if (int e = check_march_cfg(c->cascades, c->grid_size, c->max_samples)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nu = n_upper > 0 ? n_upper : 1;
+    const int64_t samples_upper = nu * min_samples > c->n_alive ? nu * min_samples : c->n_alive;
+    const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
+    const int g128 = (int)min((int64_t)148 * 64, (nu + 127) / 128), g1024 = (int)min((int64_t)148 * 8, (nu + 1023) / 1024);
+    ARN_LAUNCH("neff_test_pre_kernel", st, neff_test_pre_kernel<<<g128, 128, 0, st>>>(c->alive, state_in, totals, cursor, c->n_eff, partial));
+    if (int e = check_launch("neff_test_pre")) return e;
+    ARN_LAUNCH("scan_test_dyn_kernel", st, scan_test_dyn_kernel<<<g1024, 1024, 0, st>>>(c->n_eff, partial, state_in, c->rays_a, c->counts));
+    if (int e = check_launch("scan_test_dyn")) return e;
+    const int g_emit = (int)min((int64_t)148 * 32, (samples_upper + 255) / 256);
+    ARN_LAUNCH("emit_test_pre_kernel", st, emit_test_pre_kernel<<<g_emit, 256, 0, st>>>(c->rays_o, c->rays_d, c->alive, state_in, c->rays_a, ts_all, cursor, c->n_alive, mc,
+                                                                                     c->deltas, c->ts, c->xyzs, c->dirs));
+    if (int e = check_launch("emit_test_pre")) return e;
+    if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, samples_upper, c->counts, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
+                                    c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
+    ARN_LAUNCH("composite_test_dyn_kernel", st, composite_test_dyn_kernel<<<g128, 128, 0, st>>>(c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, state_in, c->T_threshold,
+                                                                                            c->rays_a, c->opacity, c->depth, c->rgb, c->n_eff, partial,
+                                                                                            (unsigned long long*)c->total_samples, cursor));
     if (int e = check_launch("composite_test_dyn")) return e;
     ARN_LAUNCH("alive_compact_dyn_kernel", st, alive_compact_dyn_kernel<<<g1024, 1024, 0, st>>>(c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
                                                                                            c->counts_alive, state_out, c->n_alive, min_samples, budget_samples));

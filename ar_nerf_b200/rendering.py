@@ -85,6 +85,7 @@ def render(model, rays_o, rays_d, **kwargs):
 _TEST_WS = {}
 _STATE_RING = 4   # read-back slots of the device-driven test loop
 _STATE_LAG = 2    # the host looks at the control state of the iteration queued this many calls earlier
+_PREMARCH_MAX_BYTES = 12 << 30  # largest per-frame sample table (stride x N_rays floats) the fused test loop allocates
 
 
 def _test_workspace(R, min_samples, device):
@@ -154,7 +155,20 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
         # Loop control on the device: iterations are queued without waiting for their counts; the control state comes back
         # through pinned memory and is looked at _STATE_LAG iterations late (an iteration queued after the loop has ended
         # is a handful of empty launches).  n_alive never grows, so a stale value still bounds the grids.
-        if kwargs.get('far_clamp', True):
+        # The frame's samples are marched once, in front of the loop (arn_march_test_all), when their table fits: the loop
+        # never asks a ray for more than max_samples + 63 samples.  Otherwise the iterations march (far-clamped rays).
+        stride = int(max(1, min(max_samples, MAX_SAMPLES))) + 64
+        premarch = kwargs.get('premarch_test_loop', True) and max_samples > 0 and stride * N_rays * 4 <= _PREMARCH_MAX_BYTES
+        if premarch:
+            pm = w.get('premarch')
+            if pm is None or pm[0].numel() < stride * N_rays:
+                pm = (torch.empty(stride * N_rays, dtype=torch.float32, device=device), torch.empty(N_rays, dtype=torch.int32, device=device),
+                      torch.empty(N_rays, dtype=torch.int32, device=device))
+                w['premarch'] = pm
+            ts_all, totals, cursor = pm
+            call("arn_march_test_all", ptr(rays_o), ptr(rays_d), ptr(hits_t2), N_rays, ptr(model.density_bitfield), model.cascades,
+                 model.grid_size, float(model.scale), float(exp_step_factor), MAX_SAMPLES, stride, ptr(ts_all), ptr(totals), ptr(cursor), s_)
+        elif kwargs.get('far_clamp', True):
             call("arn_march_test_far_clamp", ptr(rays_o), ptr(rays_d), ptr(hits_t2), N_rays, ptr(model.density_bitfield), model.cascades,
                  model.grid_size, float(model.scale), float(exp_step_factor), MAX_SAMPLES, s_)
         S0 = max(1, min_samples)
@@ -167,8 +181,12 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
         cur_stream = torch.cuda.current_stream()
         while True:
             cfg.alive, cfg.alive_out = w['alive'][it & 1].data_ptr(), w['alive'][(it & 1) ^ 1].data_ptr()
-            call("arn_render_test_step", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(w['partial']), min_samples,
-                 int(max_samples), n_upper, s_)
+            if premarch:
+                call("arn_render_test_step_pre", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(w['partial']), ptr(ts_all), ptr(totals),
+                     ptr(cursor), min_samples, int(max_samples), n_upper, s_)
+            else:
+                call("arn_render_test_step", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(w['partial']), min_samples,
+                     int(max_samples), n_upper, s_)
             k = it % _STATE_RING
             w['state_host'][k].copy_(w['state'][(it & 1) ^ 1], non_blocking=True)
             w['state_ev'][k].record(cur_stream)

@@ -388,6 +388,20 @@ int arn_march_test_far_clamp(const float* rays_o, const float* rays_d, float* hi
  * partial: (N_rays + 127) / 128 int32 of scratch; capacity >= N_rays * min_samples. */
 int arn_render_test_step(const arn_test_iter_t* cfg_host, const int32_t* state_in, int32_t* state_out, int32_t* partial,
                          int min_samples, int budget_samples, int64_t n_upper, arn_stream_t stream);
+/* The frame's samples marched ONCE.  The test march is resumable and deterministic (an iteration starts at the chain point
+ * behind the previous iteration's last sample), so a ray's sample sequence does not depend on how the loop slices it:
+ * arn_march_test_all marches every ray of the frame to its end with the test march's own arithmetic and records the
+ * parameter t of every occupied sample, sample-major (ts_all[s * n_rays + r]), at most `stride` per ray (the loop never
+ * asks a ray for more than max_samples + 63: stride = budget + 64 is always enough), the count in totals[r], and zeroes
+ * cursor[r].  arn_render_test_step_pre is arn_render_test_step with the march replaced by a slice of ts_all at the ray's
+ * cursor (dt = calc_dt(t) as the march computes it): same samples, same N_eff, same kill pattern, no marching inside the
+ * loop.  hits_t is not advanced in this form. */
+int arn_march_test_all(const float* rays_o, const float* rays_d, const float* hits_t, int64_t n_rays,
+                       const uint8_t* density_bitfield, int cascades, int grid_size, float scale, float exp_step_factor,
+                       int max_samples, int stride, float* ts_all, int32_t* totals, int32_t* cursor, arn_stream_t stream);
+int arn_render_test_step_pre(const arn_test_iter_t* cfg_host, const int32_t* state_in, int32_t* state_out, int32_t* partial,
+                             const float* ts_all, const int32_t* totals, int32_t* cursor, int min_samples,
+                             int budget_samples, int64_t n_upper, arn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Optimizer step.  Replaces apex FusedAdam(lr, betas=(0.9,0.999), eps=1e-15, weight_decay=0) (train.py:146).

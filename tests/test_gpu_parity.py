@@ -705,7 +705,9 @@ def test_fused_test_loop_equals_eager_loop(kind, thr, max_samples, w1, w3):
     w.install(model)
     ro, rd = w.test_frame(160, 120)
     kw = dict(test_time=True, T_threshold=thr, max_samples=max_samples, exp_step_factor=w.exp_step_factor)
-    a = render(model, T(ro), T(rd), **kw)                              # arn_render_test_step: loop control on the device
+    a = render(model, T(ro), T(rd), **kw)                              # frame marched once + arn_render_test_step_pre (loop control on the device)
+    m = render(model, T(ro), T(rd), premarch_test_loop=False, **kw)    # arn_render_test_step: every iteration marches
+    assert int(m["total_samples"]) == int(a["total_samples"]) and all(torch.equal(m[k], a[k]) for k in ("opacity", "depth", "rgb"))
     h = render(model, T(ro), T(rd), host_driven_test_loop=True, **kw)  # arn_render_test_iter: counts read per iteration
     b = render(model, T(ro), T(rd), eager_test_loop=True, **kw)
     assert int(a["total_samples"]) == int(h["total_samples"]) == int(b["total_samples"]) > 0
