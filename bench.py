@@ -366,6 +366,11 @@ def run_ours(args):
             ach = model_bytes.get(top, 0.0) / per_launch_s / 1e9
             roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic.get(top),
                     "peak_source": peak_src, "ms_per_launch": per_launch_s * 1e3}
+    if roof is not None and roof["kernel"].startswith("hash_encode_bw"):
+        # what actually bounds this kernel: the rate at which the L2 retires reduction sectors
+        roof["note"] = ("bound by L2 reduction throughput, not by HBM: 44.6 red.global sector operations per sample (levels 11-15: 6 per level, "
+                        "the minimum for 8 corners = 4 aligned 16-byte pairs at even x, 8 singles at odd x) = 10.9 M per launch "
+                        "(ncu lts__t_sectors_srcunit_tex_op_red, profiles/r01b_ncu_full_step.txt), ~73 per clock; more resident warps make it slower")
     hash_gbs = None
     if "hash_encode_fw_kernel" in prof:
         c, ms = prof["hash_encode_fw_kernel"]

@@ -69,6 +69,13 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src and "oracle/_ref" not in src and "dlopen" not in src, f
+    # ... and nothing else at the repository root or under tools/ / models/ does either: only tests/, bench.py's CPU legs and
+    # __graft_entry__.smoke() may use the checker
+    others = [os.path.join(ROOT, f) for f in os.listdir(ROOT) if f.endswith(".py") and f not in ("bench.py", "__graft_entry__.py")]
+    for d in ("tools", "models"):
+        others += [os.path.join(ROOT, d, f) for f in os.listdir(os.path.join(ROOT, d)) if f.endswith(".py")]
+    for f in others:
+        assert not re.search(r"^\s*(import|from)\s+oracle\b", open(f).read(), flags=re.M), f
 
 
 def test_missing_library_fails_loudly(monkeypatch):

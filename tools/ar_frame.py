@@ -3,11 +3,10 @@
   (2) NeRF background render with the object's colours as IM_bkg and its depth as mesh_depth_map        [render(test_time=True, T=1e-2, 100 samples)]
   (3) the shadow the object casts on the scene, one factor per pixel of the frame                        [arn_sg_shadow_factor]
 with synthetic stand-ins of the reference's git-ignored tables at the sizes insert/main.py:107 uses (f_h 2048x1024, PCA
-volume 20^3 x 128 components, components 128 x 74 x 148).  Prints one JSON line; `--cpu` adds the numpy oracle timed on a 20 000-pixel sample."""
+volume 20^3 x 128 components, components 128 x 74 x 148).  Prints one JSON line."""
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -70,14 +69,6 @@ def main():
     line = {"workload": "W4 AR insertion frame 1920x1080: SG shading of a 400x400 object under 32 SG lights + NeRF background (T=1e-2, 100 samples) + SG shadow factor per pixel",
             "ms_per_frame": ms_frame, "frames_per_s": 1e3 / ms_frame, "sg_shade_ms": ms_shade, "sg_shade_pixels": n_obj,
             "sg_shadow_factor_ms": ms_factor, "sg_shadow_factor_pixels": H * W, "finite": bool(torch.isfinite(img).all())}
-    if "--cpu" in sys.argv:
-        from oracle import sg_shadow as osg
-        n = 20000
-        tabs = (sg.coeff_volume[0].cpu().numpy(), sg.components.cpu().numpy(), sg.mean.cpu().numpy(), sg.fh_tab[0, 0].cpu().numpy())
-        t0 = time.perf_counter()
-        osg.calc_shadow_factor(model_r, pts_all[:n].cpu().numpy(), model_pos.numpy(), lSGs.cpu().numpy(), *tabs)
-        line["oracle_shadow_factor_ms_per_Mpx"] = (time.perf_counter() - t0) * 1e3 / n * 1e6
-        line["sg_shadow_factor_ms_per_Mpx"] = ms_factor / (H * W) * 1e6
     print(json.dumps(line))
 
 
