@@ -175,6 +175,101 @@ __global__ void __launch_bounds__(256) cell_positions_kernel(const int32_t* __re
     xyzs[e] = __fadd_rn(c, j);
 }
 
+// ---- Steady-state cell selection of the occupancy refresh (networks.py:181-207 + :263-267) in three small launches.
+// M uniform cells come from the caller's randint draw; M occupied cells are "the k-th occupied cell, k = u mod count" of the
+// caller's second draw (the reference indexes nonzero(grid > thr) with randint(count): the same distribution).  The k-th
+// occupied cell is found through occupancy bit masks (one word per 32 cells) and a prefix over 1024-cell chunks -- a binary
+// search in shared memory and one 128-byte read of the chunk's masks -- instead of cumsum + searchsorted over the whole
+// grid; the jittered position of the cell (networks.py:263-267) is written by the same thread.
+// (Measured and dropped: ordering the selected cells along the morton curve with a counting sort over the chunks.  The
+// density evaluation that follows does get cheaper -- 293 -> 200 us of hash-grid gathers for the 1 M cells -- but the
+// histogram and the scatter cost more than that.)
+constexpr int kCellChunk = 1024;  // cells per chunk = 32 mask words
+constexpr int kMaxChunks = 4096;
+__global__ void __launch_bounds__(256) occ_mask_kernel(const float* __restrict__ grid, float thr, int64_t n_cells, uint32_t* __restrict__ masks,
+                                                       int32_t* __restrict__ chunk_count) {
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per chunk
+    const int lane = threadIdx.x & 31;
+    if (chunk * kCellChunk >= n_cells) return;
+    uint32_t mine = 0u; int cnt = 0;
+    for (int w = 0; w < 32; w++) {
+        const int64_t i = chunk * kCellChunk + w * 32 + lane;
+        const unsigned m = __ballot_sync(kFull, i < n_cells && grid[i] > thr);
+        if (lane == w) mine = m;
+        cnt += __popc(m);
+    }
+    masks[chunk * 32 + lane] = mine;
+    if (lane == 0) chunk_count[chunk] = cnt;
+}
+// exclusive prefix of up to 4096 ints in one CTA: out[i] = sum(in[0..i)), out[n] = total
+__global__ void __launch_bounds__(1024) small_scan_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict__ out) {
+    __shared__ int warp_tot[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int v[4]; int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int i = threadIdx.x * 4 + k; v[k] = i < n ? in[i] : 0; sum += v[k]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(kFull, w, o); if (lane >= o) w += u; }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    int run = inc - sum + (wid ? warp_tot[wid - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int i = threadIdx.x * 4 + k; if (i < n) out[i] = run; run += v[k]; }
+    if (threadIdx.x == 0) out[n] = warp_tot[31];
+}
+// cell index + jittered position of every draw (j < M: uniform; j >= M: k-th occupied)
+__global__ void __launch_bounds__(256) pick_cells_kernel(const int32_t* __restrict__ coords1, const int64_t* __restrict__ u, int64_t M,
+                                                         const uint32_t* __restrict__ masks, const int32_t* __restrict__ chunk_prefix, int n_chunks,
+                                                         const float* __restrict__ rnd, float inv_gm1, float s_minus_half, float half,
+                                                         int64_t* __restrict__ indices, float* __restrict__ xyzs) {
+    __shared__ int s_prefix[kMaxChunks + 1];
+    const bool occupied_half = (int64_t)blockIdx.x * blockDim.x >= M;  // M is a multiple of the block size (checked by the host)
+    if (occupied_half) {
+        for (int b = threadIdx.x; b <= n_chunks; b += blockDim.x) s_prefix[b] = chunk_prefix[b];
+        __syncthreads();
+    }
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 2 * M) return;
+    uint32_t idx;
+    if (!occupied_half) {
+        idx = arn_morton3d((uint32_t)coords1[3 * j], (uint32_t)coords1[3 * j + 1], (uint32_t)coords1[3 * j + 2]);
+    } else {
+        const int total = s_prefix[n_chunks];
+        const int k = (int)(u[j - M] % (int64_t)max(total, 1));
+        int lo = 0, hi = n_chunks - 1;  // last chunk with prefix <= k
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_prefix[mid] <= k) lo = mid; else hi = mid - 1; }
+        int rem = k - s_prefix[lo];
+        const uint4* mw = reinterpret_cast<const uint4*>(masks + (int64_t)lo * 32);
+        uint32_t m[32];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { const uint4 v = __ldg(mw + q); m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w; }
+        int w = 31; uint32_t word = m[31]; bool found = false;
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+            const int c = __popc(m[q]);
+            if (!found) { if (rem < c) { found = true; w = q; word = m[q]; } else rem -= c; }
+        }
+        const int bit = (total > 0 && found) ? (int)__fns(word, 0, rem + 1) : 0;  // (an empty grid degenerates to one cell, harmless: see networks.py)
+        idx = (uint32_t)lo * kCellChunk + (uint32_t)w * 32u + (uint32_t)(bit & 31);
+    }
+    indices[j] = (int64_t)idx;
+    const uint32_t c[3] = {arn_morton3d_invert(idx), arn_morton3d_invert(idx >> 1), arn_morton3d_invert(idx >> 2)};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float cc = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)(int32_t)c[d], inv_gm1), 2.0f), 1.0f), s_minus_half);
+        const float jj = __fmul_rn(__fsub_rn(__fmul_rn(rnd[3 * j + d], 2.0f), 1.0f), half);
+        xyzs[3 * j + d] = __fadd_rn(cc, jj);
+    }
+}
+
 // networks.py:273-279: grid = where(grid < 0, grid, max(grid * decay, tmp)) in place, plus the sum / count of the positive
 // cells of the result (for the mean that caps the occupancy threshold).  Per-block partials in double, fixed order.
 __global__ void __launch_bounds__(256) grid_update_kernel(float* __restrict__ grid, const float* __restrict__ tmp, const float* __restrict__ decay_cells,
@@ -1371,6 +1466,31 @@ extern "C" ARN_API int arn_grid_cell_positions(const int32_t* coords, const floa
     ARN_LAUNCH("cell_positions_kernel", (cudaStream_t)stream, cell_positions_kernel<<<ceil_div(3 * n_cells, 256), 256, 0, (cudaStream_t)stream>>>(
         coords, rnd, 3 * n_cells, 1.0f / (float)(grid_size - 1), s_minus_half, half_f, xyzs));
     return check_launch("grid_cell_positions");
+}
+
+extern "C" ARN_API int arn_grid_sample_cells(const float* density_grid, float density_threshold, int grid_size, float s, const int32_t* coords1,
+                                             const int64_t* u, int64_t M, const float* rnd, void* scratch, int64_t* indices, float* xyzs,
+                                             arn_stream_t stream) {
+    ARN_REQUIRE(grid_size >= 2 && grid_size <= 1024 && M > 0 && M % 256 == 0, "bad sizes (M must be a positive multiple of 256)");
+    ARN_REQUIRE(density_grid && coords1 && u && rnd && scratch && indices && xyzs, "null pointer");
+    const int64_t n_cells = (int64_t)grid_size * grid_size * grid_size;
+    const int n_chunks = (int)((n_cells + kCellChunk - 1) / kCellChunk);
+    ARN_REQUIRE(n_chunks <= kMaxChunks - 1, "grid too large for the single-CTA chunk scan (grid_size <= 160)");
+    ARN_REQUIRE(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch: masks (32 per chunk) | chunk_count (n_chunks) | chunk_prefix (n_chunks + 1)
+    uint32_t* masks = (uint32_t*)scratch;
+    int32_t* chunk_count = (int32_t*)(masks + (size_t)n_chunks * 32);
+    int32_t* chunk_prefix = chunk_count + n_chunks;
+    ARN_LAUNCH("occ_mask_kernel", st, occ_mask_kernel<<<ceil_div((int64_t)n_chunks * 32, 256), 256, 0, st>>>(density_grid, density_threshold, n_cells, masks, chunk_count));
+    if (int e = check_launch("occ_mask")) return e;
+    ARN_LAUNCH("small_scan_kernel", st, small_scan_kernel<<<1, 1024, 0, st>>>(chunk_count, n_chunks, chunk_prefix));
+    if (int e = check_launch("small_scan")) return e;
+    const float s_minus_half = (float)((double)s - (double)s / (double)grid_size);
+    const float half_f = (float)((double)s / (double)grid_size);
+    ARN_LAUNCH("pick_cells_kernel", st, pick_cells_kernel<<<ceil_div(2 * M, 256), 256, 0, st>>>(coords1, u, M, masks, chunk_prefix, n_chunks, rnd,
+                                                                                              1.0f / (float)(grid_size - 1), s_minus_half, half_f, indices, xyzs));
+    return check_launch("pick_cells");
 }
 
 extern "C" ARN_API int arn_density_grid_update(float* density_grid, const float* density_tmp, const float* decay_cells, float decay,

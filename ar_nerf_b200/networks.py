@@ -205,16 +205,28 @@ class NGP(nn.Module):
     def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):
         """networks.py:252-281."""
         density_grid_tmp = torch.zeros_like(self.density_grid)
+        G, dev = self.grid_size, self.density_grid.device
+        native_sampling = not warmup and G <= 160 and (G ** 3 // 4) % 256 == 0 and self.density_grid.is_cuda
         if warmup:
             cells = self.get_all_cells()
+        elif native_sampling:
+            # the two randint draws of sample_uniform_and_occupied_cells, cascade by cascade, in the reference's order
+            M = G ** 3 // 4
+            draws = [(torch.randint(G, (M, 3), dtype=torch.int32, device=dev), torch.randint(2 ** 31 - 1, (M,), device=dev))
+                     for _ in range(self.cascades)]
         else:
-            cells = self.sample_uniform_and_occupied_cells(self.grid_size ** 3 // 4, density_threshold)
+            cells = self.sample_uniform_and_occupied_cells(G ** 3 // 4, density_threshold)
         for c in range(self.cascades):
-            indices, coords = cells[c]
             s = min(2 ** (c - 1), self.scale)
-            # xyzs_w = (coords/(G-1)*2-1)*(s - s/G) + (rand*2-1)*(s/G): one kernel, same torch.rand_like draw, same bits
-            rnd = torch.rand(coords.shape, dtype=torch.float32, device=coords.device)
-            xyzs_w = vren.grid_cell_positions(coords, rnd, self.grid_size, s)
+            if native_sampling:
+                # selection (k-th occupied cell through bit masks) and positions in one native call
+                rnd = torch.rand((2 * M, 3), dtype=torch.float32, device=dev)
+                indices, xyzs_w = vren.grid_sample_cells(self.density_grid[c], density_threshold, G, s, *draws[c], rnd)
+            else:
+                indices, coords = cells[c]
+                # xyzs_w = (coords/(G-1)*2-1)*(s - s/G) + (rand*2-1)*(s/G): one kernel, same torch.rand_like draw, same bits
+                rnd = torch.rand(coords.shape, dtype=torch.float32, device=coords.device)
+                xyzs_w = vren.grid_cell_positions(coords, rnd, self.grid_size, s)
             density_grid_tmp[c, indices] = self.density(xyzs_w)
         decay_cells = None
         if erode:

@@ -131,6 +131,32 @@ def grid_cell_positions(coords, rnd, grid_size, s):
     return out
 
 
+_SAMPLE_SCRATCH = {}
+
+
+def grid_sample_cells(density_grid_c, density_threshold, grid_size, s, coords1, u, rnd):
+    """Steady-state cell selection of ONE cascade (networks.py:181-207 + :263-267) without torch glue: coords1 (M,3) i32 and
+    u (M,) i64 are the caller's two randint draws, rnd (2M,3) its rand draw.  Returns (indices (2M,) i64, xyzs_w (2M,3)) in
+    draw order (uniform half first)."""
+    check_tensor(density_grid_c, "density_grid", torch.float32, 1)
+    check_tensor(coords1, "coords1", torch.int32, 2, 3); check_tensor(u, "u", torch.int64, 1); check_tensor(rnd, "rnd", torch.float32, 2, 3)
+    M = coords1.shape[0]
+    if u.shape[0] != M or rnd.shape[0] != 2 * M or density_grid_c.numel() != grid_size ** 3:
+        raise RuntimeError("grid_sample_cells: inconsistent sizes")
+    dev = density_grid_c.device
+    need = ((grid_size ** 3 + 1023) // 1024) * 34 + 4  # ARN_GRID_SAMPLE_SCRATCH_INTS
+    key = (dev.index, need)
+    scratch = _SAMPLE_SCRATCH.get(key)
+    if scratch is None:
+        _SAMPLE_SCRATCH.clear()
+        scratch = _SAMPLE_SCRATCH[key] = torch.empty(need, dtype=torch.int32, device=dev)
+    indices = torch.empty(2 * M, dtype=torch.int64, device=dev)
+    xyzs = torch.empty(2 * M, 3, dtype=torch.float32, device=dev)
+    call("arn_grid_sample_cells", ptr(density_grid_c), float(density_threshold), int(grid_size), float(s), ptr(coords1), ptr(u), M, ptr(rnd),
+         ptr(scratch), ptr(indices), ptr(xyzs), stream())
+    return indices, xyzs
+
+
 _GRID_SCRATCH = {}
 
 

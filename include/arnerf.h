@@ -98,6 +98,17 @@ int arn_gather_rays(const float* directions, const float* K_host, int width, con
 #define ARN_GRID_UPDATE_SCRATCH_BYTES (ARN_GRID_UPDATE_PARTS * 16 + 16)
 int arn_grid_cell_positions(const int32_t* coords, const float* rnd, int64_t n_cells, int grid_size, float s, float* xyzs,
                             arn_stream_t stream);
+/* Steady-state cell selection of the refresh (networks.py:181-207 sample_uniform_and_occupied_cells + :263-267 positions) for
+ * ONE cascade: coords1 (M,3) i32 = the caller's torch.randint(G) draw (M uniform cells), u (M) i64 = the caller's second
+ * randint draw (the k-th occupied cell with k = u mod count, count = #(density_grid > density_threshold): the distribution of
+ * the reference's nonzero()[randint(count)]), rnd (2M,3) = the caller's torch.rand draw.  Out, in draw order (uniform half
+ * first, as the reference concatenates them): indices (2M) i64 morton codes and xyzs (2M,3) jittered positions.  No host
+ * round trip, three small launches (occupancy bit masks + chunk prefix instead of cumsum / searchsorted over the grid).
+ * scratch: ARN_GRID_SAMPLE_SCRATCH_INTS(G^3) int32, 16-byte aligned.  M: multiple of 256.  grid_size <= 160. */
+#define ARN_GRID_SAMPLE_SCRATCH_INTS(n_cells) ((((n_cells) + 1023) / 1024) * 34 + 4)
+int arn_grid_sample_cells(const float* density_grid, float density_threshold, int grid_size, float s, const int32_t* coords1,
+                          const int64_t* u, int64_t M, const float* rnd, void* scratch, int64_t* indices, float* xyzs,
+                          arn_stream_t stream);
 int arn_density_grid_update(float* density_grid, const float* density_tmp, const float* decay_cells, float decay,
                             float density_threshold, int64_t n_cells, uint8_t* density_bitfield, void* scratch,
                             arn_stream_t stream);

@@ -794,5 +794,16 @@ def test_density_grid_update_bits(w1):
     n_occ = int(occ.sum())
     hit = torch.zeros_like(occ); hit[idx[M:]] = True
     assert int(hit.sum()) > 0.9 * min(n_occ, M * (1 - np.exp(-1.0)))  # spread over the occupied set, not a few cells
+    # the refresh's own native selection (arn_grid_sample_cells): given the same draws, the same cells as the torch
+    # formulation, in the same order, with the same positions
+    G = 128
+    coords1 = torch.randint(G, (M, 3), dtype=torch.int32, device=dev()); u = torch.randint(2 ** 31 - 1, (M,), device=dev())
+    rnd = torch.rand(2 * M, 3, device=dev())
+    n_idx, n_xyz = v.grid_sample_cells(model.density_grid[0], 5.912, G, 0.5, coords1, u, rnd)
+    running = torch.cumsum(occ, 0, dtype=torch.int32)
+    want2 = torch.searchsorted(running, torch.remainder(u, running[-1].clamp(min=1)).int() + 1).clamp_(max=occ.numel() - 1)
+    want = torch.cat([v.morton3D(coords1).long(), want2])
+    assert torch.equal(n_idx, want)
+    assert torch.equal(n_xyz, v.grid_cell_positions(v.morton3D_invert(n_idx.int()), rnd, G, 0.5))  # same bits as the torch expression
     model.update_density_grid(5.912, warmup=False)
     assert model.density_grid.shape == (1, 128 ** 3)
