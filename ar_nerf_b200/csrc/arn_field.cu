@@ -521,11 +521,9 @@ __global__ void __launch_bounds__(128) field_mlp_bw_simt_kernel(int64_t n, const
 
 // ------------------------------------------------------------------------------------------------ Adam
 // torch.optim.Adam / apex FusedAdam (adam_w_mode=False, wd=0) update, fused with grad un-scale, fp16 refresh, zeroing.
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                                   __half* __restrict__ p16, int64_t n, float lr, float b1, float b2, float eps,
-                                                   float bc1, float bc2_sqrt, float inv_gs, int zero_grad) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void adam_one(int64_t i, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                         __half* __restrict__ p16, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_gs,
+                                         int zero_grad) {
     const float gr = g[i] * inv_gs;
     if (zero_grad) g[i] = 0.0f;
     if (gr == 0.0f && m[i] == 0.0f && v[i] == 0.0f) return;  // untouched hash entry: the update is exactly zero
@@ -536,6 +534,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
     const float np = p[i] - (lr / bc1) * (mi / denom);
     p[i] = np;
     if (p16) p16[i] = __float2half_rn(np);
+}
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                   __half* __restrict__ p16, int64_t n, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2_sqrt, float inv_gs, int zero_grad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    adam_one(i, p, g, m, v, p16, lr, b1, b2, eps, bc1, bc2_sqrt, inv_gs, zero_grad);
 }
 
 // 128-bit form: one thread updates 2 x 4 consecutive parameters per turn; all eight 128-bit loads (p, g, m, v of both
@@ -563,11 +568,19 @@ __device__ __forceinline__ uint2 pack_half4(const float4& a) {
     uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
     return o;
 }
+// A second, small tensor (the colour net's 7168 parameters) rides in the same launch: the blocks behind `n_main_blocks` update
+// it element by element with adam_kernel's arithmetic -- one launch less on the step's serial chain.
+struct AdamRider { float* p; float* g; float* m; float* v; __half* p16; int64_t n; };
 __global__ void __launch_bounds__(256) adam_vec4_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
                                                         uint2* __restrict__ p16, int64_t n4, float lr, float b1, float b2, float eps,
-                                                        float bc1, float bc2_sqrt, float inv_gs, int zero_grad) {
+                                                        float bc1, float bc2_sqrt, float inv_gs, int zero_grad, int n_main_blocks, AdamRider rd) {
     const float lr_bc1 = lr / bc1;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if ((int)blockIdx.x >= n_main_blocks) {
+        const int64_t i = (int64_t)(blockIdx.x - n_main_blocks) * blockDim.x + threadIdx.x;
+        if (i < rd.n) adam_one(i, rd.p, rd.g, rd.m, rd.v, rd.p16, lr, b1, b2, eps, bc1, bc2_sqrt, inv_gs, zero_grad);
+        return;
+    }
+    const int64_t stride = (int64_t)n_main_blocks * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
         const int64_t j = i + stride;
         const bool two = j < n4;
@@ -792,12 +805,32 @@ extern "C" ARN_API int arn_adam_step(float* params, float* grads, float* exp_avg
         const int64_t n4 = n / 4;
         const int grid = (int)min((int64_t)148 * 16, (n4 + 255) / 256);
         ARN_LAUNCH("adam_vec4_kernel", st, adam_vec4_kernel<<<grid, 256, 0, st>>>((float4*)params, (float4*)grads, (float4*)exp_avg, (float4*)exp_avg_sq, (uint2*)dst_f16, n4,
-                                                                                  lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad));
+                                                                                  lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad, grid, AdamRider{}));
     } else {
         ARN_LAUNCH("adam_kernel", st, adam_kernel<<<ceil_div(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)dst_f16, n, lr, beta1, beta2,
                                                                                      eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad));
     }
     return check_launch("adam_step");
+}
+
+// arn_adam_step for a large tensor and a small one (same hyper-parameters, same step) in ONE launch.
+extern "C" ARN_API int arn_adam_step2(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* dst_f16, int64_t n,
+                                      float* params2, float* grads2, float* exp_avg2, float* exp_avg_sq2, void* dst2_f16, int64_t n2,
+                                      float lr, float beta1, float beta2, float eps, int step, float inv_grad_scale, int zero_grad, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 4096 && n % 4 == 0 && n2 > 0 && n2 <= (1 << 20) && step >= 1, "bad sizes (first tensor: >= 4096 elements, multiple of 4; second: at most 2^20)");
+    ARN_REQUIRE(params && grads && exp_avg && exp_avg_sq && params2 && grads2 && exp_avg2 && exp_avg_sq2, "null pointer");
+    ARN_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0 && ((uintptr_t)dst_f16 & 7) == 0,
+                "the first tensor must be 16-byte aligned (8 for the fp16 copy)");
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n4 = n / 4;
+    const int grid = (int)min((int64_t)148 * 16, (n4 + 255) / 256);
+    const AdamRider rd{params2, grads2, exp_avg2, exp_avg_sq2, (__half*)dst2_f16, n2};
+    ARN_LAUNCH("adam_vec4_kernel", st, adam_vec4_kernel<<<grid + ceil_div(n2, 256), 256, 0, st>>>((float4*)params, (float4*)grads, (float4*)exp_avg, (float4*)exp_avg_sq,
+                                                                                               (uint2*)dst_f16, n4, lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale,
+                                                                                               zero_grad, grid, rd));
+    return check_launch("adam_step2");
 }
 
 // Public entry points: the tensor-core kernels (arn_mlp_tc.cu).

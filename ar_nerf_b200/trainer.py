@@ -79,6 +79,14 @@ class FusedAdam:
         self.t += 1
         s_ = stream()
         hyper = (float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), self.t, float(inv_grad_scale))
+        if self.world == 1 and len(self.items) == 2:
+            # single GPU: the hash table and the colour net in one launch (arn_adam_step2)
+            (pa, ca, ma, va, _), (pb, cb, mb, vb, _) = sorted(self.items, key=lambda it: -it[0].numel())
+            if pa.numel() >= 4096 and pa.numel() % 4 == 0 and pb.numel() <= (1 << 20) and ca is not None and cb is not None:
+                call("arn_adam_step2", ptr(pa.data), ptr(pa.grad), ptr(ma), ptr(va), ptr(ca.get(pa)), pa.numel(),
+                     ptr(pb.data), ptr(pb.grad), ptr(mb), ptr(vb), ptr(cb.get(pb)), pb.numel(), *hyper, 1, s_)
+                ca.mark_fresh(pa); cb.mark_fresh(pb)
+                return
         pending = {}
         if self.world > 1:
             for i, (p, cache, m, v, st) in enumerate(self.items):

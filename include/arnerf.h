@@ -423,6 +423,12 @@ int arn_render_test_step_pre(const arn_test_iter_t* cfg_host, const int32_t* sta
 int arn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* dst_f16, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, float inv_grad_scale, int zero_grad,
                   arn_stream_t stream);
+/* The same update for a large tensor (>= 4096 elements, multiple of 4, 16-byte aligned) and a small one (<= 2^20 elements,
+ * updated element by element by extra blocks) in ONE launch: same hyper-parameters, step and zero_grad for both. */
+int arn_adam_step2(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* dst_f16, int64_t n,
+                   float* params2, float* grads2, float* exp_avg2, float* exp_avg_sq2, void* dst2_f16, int64_t n2,
+                   float lr, float beta1, float beta2, float eps, int step, float inv_grad_scale, int zero_grad,
+                   arn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Multi-GPU: gradient exchange fused with the optimizer over NVLink peer memory (one process per GPU; replaces the

@@ -468,6 +468,34 @@ def test_adam_step_vs_torch(vren):
         _lib.set_tunable("adam_vec", 1)
 
 
+def test_adam_two_tensors_one_launch():
+    """arn_adam_step2 (hash table + colour net in one launch) against two arn_adam_step calls: identical bits."""
+    from ar_nerf_b200 import _lib
+    g = torch.Generator(device=dev()).manual_seed(9)
+    na, nb = 400_000, 7168
+    mk = lambda n: [torch.randn(n, device=dev(), generator=g), torch.zeros(n, device=dev()), torch.zeros(n, device=dev())]
+    (pa, ma, va), (pb, mb, vb) = mk(na), mk(nb)
+    ref = [t.clone() for t in (pa, ma, va, pb, mb, vb)]
+    ha, hb = pa.half(), pb.half(); ra, rb = ha.clone(), hb.clone()
+    for step in range(1, 4):
+        ga = torch.randn(na, device=dev(), generator=g) * (torch.rand(na, device=dev(), generator=g) > 0.5) * 128
+        gb = torch.randn(nb, device=dev(), generator=g) * 128
+        ga2, gb2 = ga.clone(), gb.clone()
+        _lib.call("arn_adam_step2", pa.data_ptr(), ga.data_ptr(), ma.data_ptr(), va.data_ptr(), ha.data_ptr(), na,
+                  pb.data_ptr(), gb.data_ptr(), mb.data_ptr(), vb.data_ptr(), hb.data_ptr(), nb, 1e-2, 0.9, 0.999, 1e-15, step, 1.0 / 128, 1, _lib.stream())
+        _lib.call("arn_adam_step", ref[0].data_ptr(), ga2.data_ptr(), ref[1].data_ptr(), ref[2].data_ptr(), ra.data_ptr(), na, 1e-2, 0.9, 0.999, 1e-15, step,
+                  1.0 / 128, 1, _lib.stream())
+        try:  # the small tensor rides with the element-wise kernel's arithmetic
+            _lib.set_tunable("adam_vec", 0)
+            _lib.call("arn_adam_step", ref[3].data_ptr(), gb2.data_ptr(), ref[4].data_ptr(), ref[5].data_ptr(), rb.data_ptr(), nb, 1e-2, 0.9, 0.999, 1e-15, step,
+                      1.0 / 128, 1, _lib.stream())
+        finally:
+            _lib.set_tunable("adam_vec", 1)
+        assert (ga == 0).all() and (gb == 0).all()
+        for x, y in zip((pa, ma, va, pb, mb, vb, ha, hb), (*ref, ra, rb)):
+            assert torch.equal(x, y)
+
+
 def _adam_case(g, n):
     from ar_nerf_b200 import _lib
     p = torch.randn(n, device=dev(), generator=g); p_ref = p.clone().requires_grad_(True)
