@@ -70,8 +70,8 @@ int arn_march_train_count_ex(const float*, const float*, const float*, int64_t, 
                              int32_t*, float*, int32_t*, arn_stream_t);
 int arn_march_train_emit_dyn(const float*, const float*, int64_t, int, int, float, float, int, const int64_t*, const float*, const int32_t*, float*,
                              float*, float*, float*, int64_t, arn_stream_t);
-int arn_composite_train_fw_loss(const float*, const float*, const float*, const float*, const int64_t*, int64_t, int64_t, float, int64_t*, float*, float*,
-                                float*, float*, const float*, const float*, float, float, float, float, float*, float*, float*, float*, float*, arn_stream_t);
+int arn_composite_train_fw_loss_ex(const float*, const float*, const float*, const float*, const int64_t*, int64_t, int64_t, float, int64_t*, float*, float*,
+                                   float*, float*, const float*, const float*, float, float, float, float, float*, float*, float*, float*, float*, int, arn_stream_t);
 int arn_field_fw_tc_dyn(const float*, const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const void*, int,
                         arn_field_ws_t, float*, float*, arn_stream_t);
 int arn_field_bw_tc_dyn(const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const void*, int, arn_field_ws_t,
@@ -98,6 +98,9 @@ extern "C" ARN_API int arn_train_march(const arn_train_t* c, arn_stream_t stream
     ARN_REQUIRE(c, "null config");
     ARN_REQUIRE(c->n_rays > 0 && c->capacity > 0, "bad sizes");
     const int64_t R = c->n_rays;
+    // the step's loss accumulator is zeroed here, with the geometry (on the side stream when the march is prefetched): one
+    // node less on the serial chain of arn_train_fwbw_marched.  Every march set has its own accumulator (arn_train_t).
+    if (c->loss_out) ARN_CUDA(cudaMemsetAsync(c->loss_out, 0, sizeof(float), (cudaStream_t)stream));
     if (int e = arn_ray_aabb_near(c->rays_o, c->rays_d, R, c->center_host, c->half_size_host, c->near, c->hits_t, stream)) return e;
     if (int e = arn_march_train_count_ex(c->rays_o, c->rays_d, c->hits_t, R, c->density_bitfield, c->cascades, c->grid_size, c->scale,
                                          c->exp_step_factor, c->noise, c->max_samples, c->rays_a, c->counter, c->t_scratch, c->count_scratch, stream)) return e;
@@ -139,9 +142,9 @@ extern "C" ARN_API int arn_train_fwbw_marched(const arn_train_t* c, arn_stream_t
     if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
                                     c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
     if (int e = train_fork(1, st)) return e;
-    if (int e = arn_composite_train_fw_loss(c->sigmas, c->rgbs, c->deltas, c->ts, c->rays_a, R, c->capacity, c->T_threshold, c->total_samples, c->opacity,
-                                            c->depth, c->rgb, c->ws_out, c->rgb_target, c->bg_host, c->lambda_opacity, c->lambda_depth, c->scale,
-                                            c->grad_scale, c->rgb_final, c->dL_drgb, c->dL_dopacity, c->dL_ddepth, c->loss_out, stream)) return e;
+    if (int e = arn_composite_train_fw_loss_ex(c->sigmas, c->rgbs, c->deltas, c->ts, c->rays_a, R, c->capacity, c->T_threshold, c->total_samples, c->opacity,
+                                               c->depth, c->rgb, c->ws_out, c->rgb_target, c->bg_host, c->lambda_opacity, c->lambda_depth, c->scale,
+                                               c->grad_scale, c->rgb_final, c->dL_drgb, c->dL_dopacity, c->dL_ddepth, c->loss_out, /*zero_loss=*/0, stream)) return e;
     if (int e = arn_composite_train_bw(c->dL_dopacity, c->dL_ddepth, c->dL_drgb, nullptr, c->sigmas, c->rgbs, c->ws_out, c->deltas, c->ts, c->rays_a,
                                        c->opacity, c->depth, c->rgb, R, c->capacity, c->T_threshold, c->dL_dsigmas, c->dL_drgbs, stream)) return e;
     if (int e = train_fork(2, st)) return e;

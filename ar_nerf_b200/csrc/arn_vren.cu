@@ -1626,6 +1626,9 @@ extern "C" ARN_API int arn_composite_train_fw(const float* sigmas, const float* 
     return check_launch("composite_train_fw");
 }
 
+extern "C" int arn_composite_train_fw_loss_ex(const float*, const float*, const float*, const float*, const int64_t*, int64_t, int64_t, float, int64_t*, float*,
+                                              float*, float*, float*, const float*, const float*, float, float, float, float, float*, float*, float*, float*,
+                                              float*, int, arn_stream_t);
 // Compositing + NeRFLoss in one launch (the fused training step); rays_a must be in canonical ray order (ray_idx == row).
 extern "C" ARN_API int arn_composite_train_fw_loss(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
                                                    const int64_t* rays_a, int64_t n_rays, int64_t n_samples, float T_threshold,
@@ -1633,11 +1636,21 @@ extern "C" ARN_API int arn_composite_train_fw_loss(const float* sigmas, const fl
                                                    const float* target, const float* bg_host, float lambda_opacity, float lambda_depth,
                                                    float grid_scale, float grad_scale, float* rgb_out, float* dL_drgb, float* dL_dopacity,
                                                    float* dL_ddepth, float* loss_out, arn_stream_t stream) {
+    return arn_composite_train_fw_loss_ex(sigmas, rgbs, deltas, ts, rays_a, n_rays, n_samples, T_threshold, total_samples, opacity, depth, rgb, ws, target, bg_host,
+                                          lambda_opacity, lambda_depth, grid_scale, grad_scale, rgb_out, dL_drgb, dL_dopacity, dL_ddepth, loss_out, 1, stream);
+}
+// zero_loss = 0: *loss_out has been zeroed by the caller (the fused step does it in arn_train_march, off the serial chain)
+extern "C" int arn_composite_train_fw_loss_ex(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                                              const int64_t* rays_a, int64_t n_rays, int64_t n_samples, float T_threshold,
+                                              int64_t* total_samples, float* opacity, float* depth, float* rgb, float* ws,
+                                              const float* target, const float* bg_host, float lambda_opacity, float lambda_depth,
+                                              float grid_scale, float grad_scale, float* rgb_out, float* dL_drgb, float* dL_dopacity,
+                                              float* dL_ddepth, float* loss_out, int zero_loss, arn_stream_t stream) {
     ARN_REQUIRE(n_rays > 0 && n_samples >= 0, "bad size");
     ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb && sigmas && rgbs && deltas && ts && ws, "null pointer");
     ARN_REQUIRE(target && bg_host && dL_drgb && dL_dopacity && dL_ddepth && loss_out, "null pointer (loss)");
     cudaStream_t st = (cudaStream_t)stream;
-    ARN_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    if (zero_loss) ARN_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
     LossEpilogue L{target, {bg_host[0], bg_host[1], bg_host[2]}, lambda_opacity, lambda_depth, grid_scale, grad_scale, rgb_out, dL_drgb, dL_dopacity,
                    dL_ddepth, loss_out};
     ARN_LAUNCH("composite_train_fw_loss_kernel", st, composite_train_fw_kernel<true><<<ceil_div(n_rays * 32, 256), 256, 0, st>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,

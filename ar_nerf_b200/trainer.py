@@ -151,6 +151,7 @@ class _MarchSet:
         self.rays_a = torch.empty(n_rays, 3, dtype=torch.int64, device=device)
         self.counter = torch.zeros(2, dtype=torch.int32, device=device)
         self.xyzs, self.dirs, self.deltas, self.ts = f(capacity, 3), f(capacity, 3), f(capacity), f(capacity)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=device)  # zeroed by the set's march, accumulated by its step
         self.inputs = None   # (rays_o, rays_d, noise) marched into this set: kept alive until the set is consumed
         self.ready = torch.cuda.Event()  # recorded after a side-stream (prefetched) march
         self.pending = False             # a prefetched march is in flight / waiting to be consumed
@@ -181,7 +182,6 @@ class _FusedWorkspace:
         self.feat, self.hid, self.h = h(N, 32), h(N, 64), f(N, 16)
         self.in32, self.hid1, self.hid2 = h(N, 32), h(N, 64), h(N, 64)
         self.wimg = torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device)
-        self.loss = torch.zeros(1, dtype=torch.float32, device=device)
         self.marched = torch.cuda.Event()
         # the prefetched march runs here, filling issue slots the main stream leaves idle
         self.side = torch.cuda.Stream(device=device, priority=int(os.environ.get("ARN_SIDE_PRIO", "0")))
@@ -253,7 +253,7 @@ class NGPTrainer:
                 w.capacity, ptr(ms.xyzs), ptr(ms.dirs), ptr(ms.deltas), ptr(ms.ts), ptr(w.sigmas), ptr(w.rgbs), ptr(w.ws_out),
                 ptr(w.dL_dsigmas), ptr(w.dL_drgbs), ptr(w.dfeat),
                 FieldWs(ptr(w.feat), ptr(w.hid), ptr(w.h), ptr(w.in32), ptr(w.hid1), ptr(w.hid2), ptr(w.wimg)),
-                ptr(m.xyz_encoder.params.grad), ptr(m.rgb_net.params.grad), ptr(w.loss))
+                ptr(m.xyz_encoder.params.grad), ptr(m.rgb_net.params.grad), ptr(ms.loss))
             ms.cfg_key = key
         c = ms.cfg
         c.rays_o, c.rays_d, c.noise = ro.data_ptr(), rd.data_ptr(), nz.data_ptr()
@@ -318,13 +318,13 @@ class NGPTrainer:
             nxt.pending = True
             nxt.grid_epoch = self._grid_epoch
         w.cur ^= 1
-        # everything returned is a VIEW into the reused workspace: the per-ray outputs and the loss are valid until the next
-        # step, the march products (rm_samples, rays_a, ts/deltas) until the step after it; per-sample buffers hold
+        # everything returned is a VIEW into the reused workspace: the per-ray outputs are valid until the next step, the loss
+        # and the march products (rm_samples, rays_a, ts/deltas) until the step after it; per-sample buffers hold
         # rm_samples samples.  Clone what has to live longer.
         results = {'rgb': w.rgb_final, 'opacity': w.opacity, 'depth': w.depth, 'rm_samples': ms.counter[0],
                    'rays_a': ms.rays_a, 'total_samples_per_ray': w.total_samples, 'ts_buf': ms.ts, 'deltas_buf': ms.deltas,
                    'ws_buf': w.ws_out}
-        return w.loss[0], results
+        return ms.loss[0], results
 
     def train_step(self, rays_o, rays_d, rgb_target, noise=None, update_grid=True, next_rays=None):
         """One optimisation step.  next_rays = (rays_o, rays_d[, noise]) of the FOLLOWING call, if the caller already has

@@ -309,6 +309,8 @@ typedef struct {
     float* grad_xyz; float* grad_rgb; float* loss_out;
 } arn_train_t;
 int arn_train_fwbw(const arn_train_t* cfg_host, arn_stream_t stream);
+/* (loss_out is zeroed by arn_train_march and accumulated by arn_train_fwbw_marched: give every march set that may be in
+ * flight its own accumulator.) */
 /* The same step in its two halves.  arn_train_march (ray/box, march count + scan + emit) reads only the rays, the noise and
  * the occupancy bitfield -- not the weights -- and fills rays_a, counter, xyzs, dirs, deltas, ts (+ the march scratch);
  * arn_train_fwbw_marched does the rest on those buffers.  A trainer can therefore march batch k+1 on a second stream
