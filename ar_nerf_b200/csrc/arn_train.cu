@@ -71,7 +71,8 @@ int arn_march_train_count_ex(const float*, const float*, const float*, int64_t, 
 int arn_march_train_emit_dyn(const float*, const float*, int64_t, int, int, float, float, int, const int64_t*, const float*, const int32_t*, float*,
                              float*, float*, float*, int64_t, arn_stream_t);
 int arn_composite_train_fw_loss_ex(const float*, const float*, const float*, const float*, const int64_t*, int64_t, int64_t, float, int64_t*, float*, float*,
-                                   float*, float*, const float*, const float*, float, float, float, float, float*, float*, float*, float*, float*, int, arn_stream_t);
+                                   float*, float*, const float*, const float*, float, float, float, float, float*, float*, float*, float*, float*, int, float*, float*,
+                                   arn_stream_t);
 int arn_field_fw_tc_dyn(const float*, const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const void*, int,
                         arn_field_ws_t, float*, float*, arn_stream_t);
 int arn_field_bw_tc_dyn(const float*, int64_t, const int32_t*, const float*, const float*, arn_levels_t, const void*, const void*, int, arn_field_ws_t,
@@ -144,9 +145,8 @@ extern "C" ARN_API int arn_train_fwbw_marched(const arn_train_t* c, arn_stream_t
     if (int e = train_fork(1, st)) return e;
     if (int e = arn_composite_train_fw_loss_ex(c->sigmas, c->rgbs, c->deltas, c->ts, c->rays_a, R, c->capacity, c->T_threshold, c->total_samples, c->opacity,
                                                c->depth, c->rgb, c->ws_out, c->rgb_target, c->bg_host, c->lambda_opacity, c->lambda_depth, c->scale,
-                                               c->grad_scale, c->rgb_final, c->dL_drgb, c->dL_dopacity, c->dL_ddepth, c->loss_out, /*zero_loss=*/0, stream)) return e;
-    if (int e = arn_composite_train_bw(c->dL_dopacity, c->dL_ddepth, c->dL_drgb, nullptr, c->sigmas, c->rgbs, c->ws_out, c->deltas, c->ts, c->rays_a,
-                                       c->opacity, c->depth, c->rgb, R, c->capacity, c->T_threshold, c->dL_dsigmas, c->dL_drgbs, stream)) return e;
+                                               c->grad_scale, c->rgb_final, c->dL_drgb, c->dL_dopacity, c->dL_ddepth, c->loss_out, /*zero_loss=*/0,
+                                               c->dL_dsigmas, c->dL_drgbs, stream)) return e;  // forward + NeRFLoss + backward of every ray in one launch
     if (int e = train_fork(2, st)) return e;
     if (int e = field_bw_tc_impl(c->xyzs, c->capacity, c->counter, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16, c->params_rgb_f16,
                                  c->rgb_act, c->ws, c->sigmas, c->rgbs, c->dL_dsigmas, c->dL_drgbs, c->loss_scale, c->dfeat, c->grad_xyz, c->grad_rgb,

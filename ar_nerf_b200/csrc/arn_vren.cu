@@ -672,123 +672,46 @@ struct LossEpilogue {
     const float* target; float bg[3]; float lambda_opacity, lambda_depth, grid_scale, grad_scale;
     float* rgb_out; float* dL_drgb; float* dL_dopacity; float* dL_ddepth; float* loss_out;
 };
-__device__ __forceinline__ float ray_loss(const LossEpilogue& L, int64_t r, int64_t n_rays, const float c[3], float o, float dep) {
+// store: this lane writes the per-ray results; every calling lane gets the gradients (g_rgb, g_op, g_d) back
+__device__ __forceinline__ float ray_loss(const LossEpilogue& L, int64_t r, int64_t n_rays, const float c[3], float o, float dep, bool store,
+                                          float g_rgb[3], float& g_op, float& g_d) {
     const float inv_r = 1.0f / (float)n_rays, inv_3r = inv_r / 3.0f;
-    float loss = 0.0f, g_op = 0.0f;
+    float loss = 0.0f;
+    g_op = 0.0f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const float est = c[k] + L.bg[k] * (1.0f - o);
-        if (L.rgb_out) L.rgb_out[3 * r + k] = est;
+        if (store && L.rgb_out) L.rgb_out[3 * r + k] = est;
         const float den = est + 1e-3f;
         const float e = (est - L.target[3 * r + k]) / den;
         loss += e * e * inv_3r;
         const float g = 2.0f * e / den * inv_3r * L.grad_scale;
-        L.dL_drgb[3 * r + k] = g;
+        g_rgb[k] = g;
+        if (store) L.dL_drgb[3 * r + k] = g;
         g_op -= L.bg[k] * g;
     }
     const float oe = o + 1e-10f;
     loss += L.lambda_opacity * (-oe * logf(oe)) * inv_r;
     g_op += L.lambda_opacity * (-logf(oe) - 1.0f) * inv_r * L.grad_scale;
-    L.dL_dopacity[r] = g_op;
-    float g_d = 0.0f;
+    if (store) L.dL_dopacity[r] = g_op;
+    g_d = 0.0f;
     if (L.lambda_depth != 0.0f) {
         const float v = dep / L.grid_scale + 1e-10f;
         loss += -L.lambda_depth * logf(fminf(v, 1.0f)) * inv_r;
         if (v < 1.0f) g_d = -L.lambda_depth / v / L.grid_scale * inv_r * L.grad_scale;
     }
-    L.dL_ddepth[r] = g_d;
+    if (store) L.dL_ddepth[r] = g_d;
     return loss;
 }
 
-// volumerendering.cu:5-44, one warp per rays_a row.
-template <bool LOSS>
-__global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
-                                                                 const float* __restrict__ deltas, const float* __restrict__ ts,
-                                                                 const int64_t* __restrict__ rays_a, int64_t n_rays, float T_thr,
-                                                                 int64_t* __restrict__ total_samples, float* __restrict__ opacity,
-                                                                 float* __restrict__ depth, float* __restrict__ rgb, float* __restrict__ ws,
-                                                                 const LossEpilogue L, int64_t n_samples) {
-    __shared__ float s_loss[8];
-    if (LOSS && threadIdx.x < 8) s_loss[threadIdx.x] = 0.0f;
-    if (LOSS) __syncthreads();
-    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const bool live = n < n_rays;
-    if (!LOSS && !live) return;
-    int64_t ray_idx = 0, start = 0; int N = 0;
-    if (live) {
-        ray_idx = rays_a[3 * n]; start = rays_a[3 * n + 1]; N = (int)rays_a[3 * n + 2];
-        // never read past the sample buffers (a caller-chosen sample capacity smaller than the march: the tail is dropped)
-        N = (int)max((int64_t)0, min((int64_t)N, n_samples - start));
-    }
-    float T = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
-    int64_t samples = N; bool done = false;
-    int base = 0;
-    // the next 32 samples are requested before the current 32 go through the scans: a long ray no longer pays one
-    // exposed load latency per chunk
-    float n_sg = 0.f, n_dl = 0.f, n_cr = 0.f, n_cg = 0.f, n_cb = 0.f, n_ct = 0.f;
-    if (lane < N) { const int64_t s = start + lane; n_sg = sigmas[s]; n_dl = deltas[s]; n_cr = rgbs[3 * s]; n_cg = rgbs[3 * s + 1]; n_cb = rgbs[3 * s + 2]; n_ct = ts[s]; }
-    for (; base < N && !done; base += 32) {
-        const int i = base + lane; const bool in = i < N; const int64_t s = start + i;
-        const float c_sg = n_sg, c_dl = n_dl, c_cr = n_cr, c_cg = n_cg, c_cb = n_cb, c_ct = n_ct;
-        if (i + 32 < N) { const int64_t q = s + 32; n_sg = sigmas[q]; n_dl = deltas[q]; n_cr = rgbs[3 * q]; n_cg = rgbs[3 * q + 1]; n_cb = rgbs[3 * q + 2]; n_ct = ts[q]; }
-        const float a = in ? alpha_of(c_sg, c_dl) : 0.0f;
-        const float incl = warp_incl_prod(__fsub_rn(1.0f, a), lane);
-        float excl = __shfl_up_sync(kFull, incl, 1); if (lane == 0) excl = 1.0f;
-        const float T_before = T * excl, T_after = T * incl;
-        const unsigned term = __ballot_sync(kFull, in && (T_after <= T_thr));
-        const int last = term ? __ffs(term) - 1 : 31;  // the terminating sample still contributes (:37-40)
-        const bool use = in && lane <= last;
-        const float w = use ? a * T_before : 0.0f;
-        if (in) ws[s] = w;
-        float cr = 0.f, cg = 0.f, cb = 0.f, ct = 0.f;
-        if (use) { cr = c_cr; cg = c_cg; cb = c_cb; ct = c_ct; }
-        acc_r += warp_sum(w * cr); acc_g += warp_sum(w * cg); acc_b += warp_sum(w * cb);
-        acc_d += warp_sum(w * ct); acc_o += warp_sum(w);
-        if (term) { done = true; samples = base + last; }  // break happens before samples++ (:40-41)
-        T = __shfl_sync(kFull, T_after, 31);
-    }
-    for (int i = base + lane; i < N; i += 32) ws[start + i] = 0.0f;  // after termination (reference: zero-init, :59)
-    if (lane == 0 && live) {
-        opacity[ray_idx] = acc_o; depth[ray_idx] = acc_d;
-        rgb[3 * ray_idx] = acc_r; rgb[3 * ray_idx + 1] = acc_g; rgb[3 * ray_idx + 2] = acc_b;
-        total_samples[ray_idx] = samples;
-        if (LOSS) {
-            const float c[3] = {acc_r, acc_g, acc_b};
-            s_loss[threadIdx.x >> 5] = ray_loss(L, ray_idx, n_rays, c, acc_o, acc_d);
-        }
-    }
-    if (LOSS) {  // one atomic per CTA (8 rays)
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float v = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 8; k++) v += s_loss[k];
-            atomicAdd(L.loss_out, v);
-        }
-    }
-}
-
-// volumerendering.cu:86-150, one warp per row.  The reference's in-kernel serial thrust scan of dL_dws*ws (:118-121)
-// becomes a warp reduction (total) plus a running warp scan.
-__global__ void __launch_bounds__(256) composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __restrict__ dL_ddepth,
-                                                                 const float* __restrict__ dL_drgb, const float* __restrict__ dL_dws,
-                                                                 const float* __restrict__ sigmas, const float* __restrict__ rgbs,
-                                                                 const float* __restrict__ ws, const float* __restrict__ deltas,
-                                                                 const float* __restrict__ ts, const int64_t* __restrict__ rays_a,
-                                                                 const float* __restrict__ opacity, const float* __restrict__ depth,
-                                                                 const float* __restrict__ rgb, int64_t n_rays, float T_thr,
-                                                                 float* __restrict__ dL_dsigmas, float* __restrict__ dL_drgbs, int64_t n_samples) {
-    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (n >= n_rays) return;
-    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1];
-    const int N = (int)max((int64_t)0, min(rays_a[3 * n + 2], n_samples - start));  // same clamp as the forward
-    if (N <= 0) return;
-    const float R = rgb[3 * ray_idx], G = rgb[3 * ray_idx + 1], B = rgb[3 * ray_idx + 2];
-    const float O = opacity[ray_idx], D = depth[ray_idx];
-    const float gR = dL_drgb[3 * ray_idx], gG = dL_drgb[3 * ray_idx + 1], gB = dL_drgb[3 * ray_idx + 2];
-    const float gO = dL_dopacity[ray_idx], gD = dL_ddepth[ray_idx];
+// volumerendering.cu:86-150 for one ray, by one warp.  The reference's in-kernel serial thrust scan of dL_dws*ws (:118-121)
+// becomes a warp reduction (total) plus a running warp scan.  Shared by composite_train_bw_kernel and by the fused
+// forward + loss + backward of the training step.
+__device__ __forceinline__ void composite_bw_ray(int lane, int64_t start, int N, float R, float G, float B, float O, float D,
+                                                 float gR, float gG, float gB, float gO, float gD, const float* __restrict__ dL_dws,
+                                                 const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ ws,
+                                                 const float* __restrict__ deltas, const float* __restrict__ ts, float T_thr,
+                                                 float* __restrict__ dL_dsigmas, float* __restrict__ dL_drgbs) {
     float ww_total = 0.0f;
     if (dL_dws) {
         float p = 0.0f;
@@ -842,6 +765,105 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(const float* __
         const int64_t s = start + i;
         dL_drgbs[3 * s] = 0.f; dL_drgbs[3 * s + 1] = 0.f; dL_drgbs[3 * s + 2] = 0.f; dL_dsigmas[s] = 0.f;
     }
+}
+
+// volumerendering.cu:5-44, one warp per rays_a row.
+template <bool LOSS>
+__global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                 const float* __restrict__ deltas, const float* __restrict__ ts,
+                                                                 const int64_t* __restrict__ rays_a, int64_t n_rays, float T_thr,
+                                                                 int64_t* __restrict__ total_samples, float* __restrict__ opacity,
+                                                                 float* __restrict__ depth, float* __restrict__ rgb, float* __restrict__ ws,
+                                                                 const LossEpilogue L, int64_t n_samples,
+                                                                 float* __restrict__ bw_dsigmas, float* __restrict__ bw_drgbs) {
+    __shared__ float s_loss[8];
+    if (LOSS && threadIdx.x < 8) s_loss[threadIdx.x] = 0.0f;
+    if (LOSS) __syncthreads();
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool live = n < n_rays;
+    if (!LOSS && !live) return;
+    int64_t ray_idx = 0, start = 0; int N = 0;
+    if (live) {
+        ray_idx = rays_a[3 * n]; start = rays_a[3 * n + 1]; N = (int)rays_a[3 * n + 2];
+        // never read past the sample buffers (a caller-chosen sample capacity smaller than the march: the tail is dropped)
+        N = (int)max((int64_t)0, min((int64_t)N, n_samples - start));
+    }
+    float T = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
+    int64_t samples = N; bool done = false;
+    int base = 0;
+    // the next 32 samples are requested before the current 32 go through the scans: a long ray no longer pays one
+    // exposed load latency per chunk
+    float n_sg = 0.f, n_dl = 0.f, n_cr = 0.f, n_cg = 0.f, n_cb = 0.f, n_ct = 0.f;
+    if (lane < N) { const int64_t s = start + lane; n_sg = sigmas[s]; n_dl = deltas[s]; n_cr = rgbs[3 * s]; n_cg = rgbs[3 * s + 1]; n_cb = rgbs[3 * s + 2]; n_ct = ts[s]; }
+    for (; base < N && !done; base += 32) {
+        const int i = base + lane; const bool in = i < N; const int64_t s = start + i;
+        const float c_sg = n_sg, c_dl = n_dl, c_cr = n_cr, c_cg = n_cg, c_cb = n_cb, c_ct = n_ct;
+        if (i + 32 < N) { const int64_t q = s + 32; n_sg = sigmas[q]; n_dl = deltas[q]; n_cr = rgbs[3 * q]; n_cg = rgbs[3 * q + 1]; n_cb = rgbs[3 * q + 2]; n_ct = ts[q]; }
+        const float a = in ? alpha_of(c_sg, c_dl) : 0.0f;
+        const float incl = warp_incl_prod(__fsub_rn(1.0f, a), lane);
+        float excl = __shfl_up_sync(kFull, incl, 1); if (lane == 0) excl = 1.0f;
+        const float T_before = T * excl, T_after = T * incl;
+        const unsigned term = __ballot_sync(kFull, in && (T_after <= T_thr));
+        const int last = term ? __ffs(term) - 1 : 31;  // the terminating sample still contributes (:37-40)
+        const bool use = in && lane <= last;
+        const float w = use ? a * T_before : 0.0f;
+        if (in) ws[s] = w;
+        float cr = 0.f, cg = 0.f, cb = 0.f, ct = 0.f;
+        if (use) { cr = c_cr; cg = c_cg; cb = c_cb; ct = c_ct; }
+        acc_r += warp_sum(w * cr); acc_g += warp_sum(w * cg); acc_b += warp_sum(w * cb);
+        acc_d += warp_sum(w * ct); acc_o += warp_sum(w);
+        if (term) { done = true; samples = base + last; }  // break happens before samples++ (:40-41)
+        T = __shfl_sync(kFull, T_after, 31);
+    }
+    for (int i = base + lane; i < N; i += 32) ws[start + i] = 0.0f;  // after termination (reference: zero-init, :59)
+    if (lane == 0 && live) {
+        opacity[ray_idx] = acc_o; depth[ray_idx] = acc_d;
+        rgb[3 * ray_idx] = acc_r; rgb[3 * ray_idx + 1] = acc_g; rgb[3 * ray_idx + 2] = acc_b;
+        total_samples[ray_idx] = samples;
+    }
+    if (LOSS && live) {
+        // every lane evaluates the ray's loss terms (the sums are warp-uniform), lane 0 stores them; with bw_dsigmas the warp
+        // then runs the ray's backward at once (composite_train_bw's arithmetic on the samples it has just read): the fused
+        // training step needs no second compositing launch and no re-read of rays_a / the per-ray outputs
+        const float c[3] = {acc_r, acc_g, acc_b};
+        float g_rgb[3], g_op, g_d;
+        const float l = ray_loss(L, ray_idx, n_rays, c, acc_o, acc_d, lane == 0, g_rgb, g_op, g_d);
+        if (lane == 0) s_loss[threadIdx.x >> 5] = l;
+        if (bw_dsigmas && N > 0)
+            composite_bw_ray(lane, start, N, acc_r, acc_g, acc_b, acc_o, acc_d, g_rgb[0], g_rgb[1], g_rgb[2], g_op, g_d, nullptr, sigmas, rgbs, ws, deltas, ts,
+                             T_thr, bw_dsigmas, bw_drgbs);
+    }
+    if (LOSS) {  // one atomic per CTA (8 rays)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float v = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v += s_loss[k];
+            atomicAdd(L.loss_out, v);
+        }
+    }
+}
+
+// volumerendering.cu:86-150, one warp per row.  The reference's in-kernel serial thrust scan of dL_dws*ws (:118-121)
+// becomes a warp reduction (total) plus a running warp scan.
+__global__ void __launch_bounds__(256) composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __restrict__ dL_ddepth,
+                                                                 const float* __restrict__ dL_drgb, const float* __restrict__ dL_dws,
+                                                                 const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                 const float* __restrict__ ws, const float* __restrict__ deltas,
+                                                                 const float* __restrict__ ts, const int64_t* __restrict__ rays_a,
+                                                                 const float* __restrict__ opacity, const float* __restrict__ depth,
+                                                                 const float* __restrict__ rgb, int64_t n_rays, float T_thr,
+                                                                 float* __restrict__ dL_dsigmas, float* __restrict__ dL_drgbs, int64_t n_samples) {
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= n_rays) return;
+    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1];
+    const int N = (int)max((int64_t)0, min(rays_a[3 * n + 2], n_samples - start));  // same clamp as the forward
+    if (N <= 0) return;
+    composite_bw_ray(lane, start, N, rgb[3 * ray_idx], rgb[3 * ray_idx + 1], rgb[3 * ray_idx + 2], opacity[ray_idx], depth[ray_idx],
+                     dL_drgb[3 * ray_idx], dL_drgb[3 * ray_idx + 1], dL_drgb[3 * ray_idx + 2], dL_dopacity[ray_idx], dL_ddepth[ray_idx], dL_dws,
+                     sigmas, rgbs, ws, deltas, ts, T_thr, dL_dsigmas, dL_drgbs);
 }
 
 // volumerendering.cu:204-248.  Chunks are short (S <= 64, usually 1..8): one thread per alive ray, registers for the
@@ -1622,13 +1644,13 @@ extern "C" ARN_API int arn_composite_train_fw(const float* sigmas, const float* 
     ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "null pointer");
     ARN_REQUIRE(n_samples == 0 || (sigmas && rgbs && deltas && ts && ws), "null pointer");
     ARN_LAUNCH("composite_train_fw_kernel", (cudaStream_t)stream, composite_train_fw_kernel<false><<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
-                                                                                          total_samples, opacity, depth, rgb, ws, LossEpilogue{}, n_samples));
+                                                                                          total_samples, opacity, depth, rgb, ws, LossEpilogue{}, n_samples, nullptr, nullptr));
     return check_launch("composite_train_fw");
 }
 
 extern "C" int arn_composite_train_fw_loss_ex(const float*, const float*, const float*, const float*, const int64_t*, int64_t, int64_t, float, int64_t*, float*,
                                               float*, float*, float*, const float*, const float*, float, float, float, float, float*, float*, float*, float*,
-                                              float*, int, arn_stream_t);
+                                              float*, int, float*, float*, arn_stream_t);
 // Compositing + NeRFLoss in one launch (the fused training step); rays_a must be in canonical ray order (ray_idx == row).
 extern "C" ARN_API int arn_composite_train_fw_loss(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
                                                    const int64_t* rays_a, int64_t n_rays, int64_t n_samples, float T_threshold,
@@ -1637,16 +1659,19 @@ extern "C" ARN_API int arn_composite_train_fw_loss(const float* sigmas, const fl
                                                    float grid_scale, float grad_scale, float* rgb_out, float* dL_drgb, float* dL_dopacity,
                                                    float* dL_ddepth, float* loss_out, arn_stream_t stream) {
     return arn_composite_train_fw_loss_ex(sigmas, rgbs, deltas, ts, rays_a, n_rays, n_samples, T_threshold, total_samples, opacity, depth, rgb, ws, target, bg_host,
-                                          lambda_opacity, lambda_depth, grid_scale, grad_scale, rgb_out, dL_drgb, dL_dopacity, dL_ddepth, loss_out, 1, stream);
+                                          lambda_opacity, lambda_depth, grid_scale, grad_scale, rgb_out, dL_drgb, dL_dopacity, dL_ddepth, loss_out, 1, nullptr, nullptr,
+                                          stream);
 }
-// zero_loss = 0: *loss_out has been zeroed by the caller (the fused step does it in arn_train_march, off the serial chain)
+// zero_loss = 0: *loss_out has been zeroed by the caller (the fused step does it in arn_train_march, off the serial chain);
+// bw_dsigmas / bw_drgbs != NULL: the compositing backward of every ray runs in the same launch, behind the ray's loss terms
 extern "C" int arn_composite_train_fw_loss_ex(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
                                               const int64_t* rays_a, int64_t n_rays, int64_t n_samples, float T_threshold,
                                               int64_t* total_samples, float* opacity, float* depth, float* rgb, float* ws,
                                               const float* target, const float* bg_host, float lambda_opacity, float lambda_depth,
                                               float grid_scale, float grad_scale, float* rgb_out, float* dL_drgb, float* dL_dopacity,
-                                              float* dL_ddepth, float* loss_out, int zero_loss, arn_stream_t stream) {
+                                              float* dL_ddepth, float* loss_out, int zero_loss, float* bw_dsigmas, float* bw_drgbs, arn_stream_t stream) {
     ARN_REQUIRE(n_rays > 0 && n_samples >= 0, "bad size");
+    ARN_REQUIRE(!bw_dsigmas == !bw_drgbs, "the fused backward needs both sample-gradient buffers");
     ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb && sigmas && rgbs && deltas && ts && ws, "null pointer");
     ARN_REQUIRE(target && bg_host && dL_drgb && dL_dopacity && dL_ddepth && loss_out, "null pointer (loss)");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1654,7 +1679,7 @@ extern "C" int arn_composite_train_fw_loss_ex(const float* sigmas, const float* 
     LossEpilogue L{target, {bg_host[0], bg_host[1], bg_host[2]}, lambda_opacity, lambda_depth, grid_scale, grad_scale, rgb_out, dL_drgb, dL_dopacity,
                    dL_ddepth, loss_out};
     ARN_LAUNCH("composite_train_fw_loss_kernel", st, composite_train_fw_kernel<true><<<ceil_div(n_rays * 32, 256), 256, 0, st>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
-                                                                                          total_samples, opacity, depth, rgb, ws, L, n_samples));
+                                                                                          total_samples, opacity, depth, rgb, ws, L, n_samples, bw_dsigmas, bw_drgbs));
     return check_launch("composite_train_fw_loss");
 }
 
