@@ -70,6 +70,8 @@ class FusedAdam:
                 m, v = torch.zeros_like(p), torch.zeros_like(p)
             self.items.append((p, cache, m, v, st))
         self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        self.small_stream = self.small_done = None
+        self.small_pending = False
         # the small all-reduces ride on their own communicator so that they overlap the table's reduce-scatter instead of
         # queueing behind it (a 28 KB all-reduce is pure latency: ~28 us at 8 GPUs)
         self.small_group = dist.new_group() if world > 1 and any(st is not None for *_, st in self.items) else None
@@ -99,8 +101,17 @@ class FusedAdam:
             p16 = cache.get(p) if cache is not None else None
             if st is None:
                 if i in pending:
-                    pending[i].wait()
-                call("arn_adam_step", ptr(p.data), ptr(p.grad), ptr(m), ptr(v), ptr(p16), p.numel(), *hyper, 1, s_)
+                    # small parameters (the colour net): their all-reduce and their Adam run on a side stream, beside the table's
+                    # exchange instead of behind it; step() ends with the calling stream waiting for `small_done`
+                    if self.small_stream is None:
+                        self.small_stream, self.small_done = torch.cuda.Stream(device=p.device), torch.cuda.Event()
+                    with torch.cuda.stream(self.small_stream):
+                        pending[i].wait()
+                        call("arn_adam_step", ptr(p.data), ptr(p.grad), ptr(m), ptr(v), ptr(p16), p.numel(), *hyper, 1, self.small_stream.cuda_stream)
+                    self.small_done.record(self.small_stream)
+                    self.small_pending = True
+                else:
+                    call("arn_adam_step", ptr(p.data), ptr(p.grad), ptr(m), ptr(v), ptr(p16), p.numel(), *hyper, 1, s_)
             elif st["px"] is not None:
                 st["px"].step(p.data.view(-1), m, v, hyper, self.t, s_)
             else:
@@ -113,6 +124,13 @@ class FusedAdam:
                 all_gather_shards(p16[:st["P"]], self.rank, self.world)
             if cache is not None:
                 cache.mark_fresh(p)
+        self.wait_small()  # the stream that called step() sees the side-stream update: it ran beside the exchange, not behind it
+
+    def wait_small(self):
+        """Make the current stream wait for the small parameters' side-stream update (no-op if none is pending)."""
+        if self.small_pending:
+            torch.cuda.current_stream().wait_event(self.small_done)
+            self.small_pending = False
 
     def pending_zero(self):
         """The peer exchange whose gradient buffer is still being zeroed on its side stream, or None."""
