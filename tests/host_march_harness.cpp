@@ -41,6 +41,28 @@ extern "C" void h_march_test(int n_alive, const float* o, const float* d, float*
     }
 }
 
+// march_test_all_kernel (arn_vren.cu): every ray marched once to its end, t of every occupied sample recorded sample-major
+// (ts_all[s * n_rays + r]), at most `stride` per ray; dt of a sample is calc_dt(t).  fast = the compile-time shortcuts.
+extern "C" void h_march_test_all(int n_rays, const float* o, const float* d, const float* hits_t, const uint8_t* bits, int cascades,
+                                 int grid, float scale, float esf, int max_samples, int stride, int fast, float* ts_all, float* dt_all,
+                                 int32_t* totals) {
+    const ArnMarchConsts c = arn_march_consts(cascades, grid, scale, (float)cascades, esf, max_samples);
+    for (int r = 0; r < n_rays; r++) {
+        const ArnRay ray = arn_load_ray(o + 3 * r, d + 3 * r);
+        float t = hits_t[2 * r]; const float t2 = hits_t[2 * r + 1];
+        int s = 0;
+        while (t < t2 && s < stride) {
+            float x, y, z, dt;
+            const bool occ = fast ? arn_march_eval_t<true>(c, ray, bits, t, x, y, z, dt) : arn_march_eval_t<false>(c, ray, bits, t, x, y, z, dt);
+            if (occ) {
+                ts_all[(size_t)s * n_rays + r] = t; dt_all[(size_t)s * n_rays + r] = arn_calc_dt(c, t);
+                t = ARN_ADD(t, dt); s++;
+            }
+        }
+        totals[r] = s;
+    }
+}
+
 extern "C" int h_frexp_exponent(float x) { return arn_frexp_exponent(x); }
 
 // Lane-by-lane emulation of march_train_count_warp_kernel (arn_vren.cu): same window procedure, the warp primitives

@@ -73,3 +73,36 @@ def test_test_march_bit_exact(harness, kind, w1, w3):
                              C.c_float(w.exp_step_factor), S, 1024, _p(ts), _p(dls), _p(xs), _p(ne))
         assert np.array_equal(ne, neff) and np.array_equal(ts, t) and np.array_equal(dls, dl) and np.array_equal(xs, x)
         assert np.array_equal(h1, h2)
+
+
+@pytest.mark.parametrize("kind", ["W1", "W3"])
+def test_frame_marched_once_equals_sliced_test_march(harness, kind, w1, w3):
+    """The claim behind arn_march_test_all / arn_render_test_step_pre: the test march is resumable and deterministic, so
+    ONE march of a ray to its end yields exactly the samples the loop's iterations take slice by slice (oracle:
+    raymarching_test called with the schedule's varying N_samples, rendering.py:189-203), with dt = calc_dt(t)."""
+    w = w1 if kind == "W1" else w3
+    ro, rd, _, _ = w.train_batch(3, 1024)
+    ro, rd = ro.numpy(), rd.numpy()
+    ht = scene_hits(w, ro, rd); bits = w.bitfield.numpy()
+    R, stride = len(ro), 1088
+    fast_ok = w.cascades == 1
+    outs = []
+    for fast in ([0, 1] if fast_ok else [0]):
+        ts_all = np.zeros((stride, R), np.float32); dt_all = np.zeros((stride, R), np.float32); totals = np.zeros(R, np.int32)
+        harness.h_march_test_all(R, _p(ro), _p(rd), _p(ht), _p(bits), w.cascades, 128, C.c_float(w.scale), C.c_float(w.exp_step_factor), 1024, stride,
+                                 fast, _p(ts_all), _p(dt_all), _p(totals))
+        outs.append((ts_all, dt_all, totals))
+    if fast_ok:  # the compile-time shortcuts (one cascade, grid <= 256) change nothing
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+    ts_all, dt_all, totals = outs[0]
+    # the loop's slices from the oracle: every ray stays alive (no compositing here), N_samples varies like the schedule's
+    h = ht.copy(); alive = np.arange(R, dtype=np.int64); cursor = np.zeros(R, np.int64)
+    for S in (1, 2, 3, 7, 16, 64, 64, 5, 64, 64, 64, 64, 64, 64, 64, 64, 64, 64, 64, 64):
+        _, _, dl, t, neff = oracle.raymarching_test(ro, rd, h, alive, bits, w.cascades, w.scale, w.exp_step_factor, 128, 1024, S)
+        assert np.array_equal(neff, np.minimum(S, totals - cursor))       # N_eff = min(S, total - cursor)
+        for sl in range(S):
+            m = sl < neff
+            assert np.array_equal(t[m, sl], ts_all[(cursor + sl)[m], np.nonzero(m)[0]])
+            assert np.array_equal(dl[m, sl], dt_all[(cursor + sl)[m], np.nonzero(m)[0]])
+        cursor += neff
+    assert (cursor <= totals).all() and cursor.sum() > 0
