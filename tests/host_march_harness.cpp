@@ -130,3 +130,73 @@ extern "C" void h_march_train_window(int n_rays, const float* o, const float* d,
         counts[r] = N;
     }
 }
+
+
+// Lane-by-lane emulation of march_test_warp_kernel (arn_vren.cu): the window procedure above with the test march's start
+// (hits_t[r][0], no jitter), the iteration's sample budget S and the resume point behind the last sample taken.
+extern "C" void h_march_test_window(int n_alive, const float* o, const float* d, float* hits_t, const int64_t* alive, const uint8_t* bits,
+                                    int cascades, int grid, float scale, float esf, int S, int max_samples, float* ts, float* deltas,
+                                    int32_t* n_eff) {
+    const ArnMarchConsts c = arn_march_consts(cascades, grid, scale, (float)cascades, esf, max_samples);
+    const bool fast = cascades == 1 && grid <= 256;
+    for (int n = 0; n < n_alive; n++) {
+        const int64_t r = alive[n];
+        const ArnRay ray = arn_load_ray(o + 3 * r, d + 3 * r);
+        const float t1 = hits_t[2 * r], t2 = hits_t[2 * r + 1];
+        int N = 0; float t_resume = t1; bool moved = false;
+        if (t1 < t2) {
+            float pending = -INFINITY;
+            float t[32];
+            t[0] = t1;
+            for (int j = 1; j < 32; j++) t[j] = ARN_ADD(t[j - 1], arn_calc_dt(c, t[j - 1]));
+            for (;;) {
+                float tgt[32], dts[32]; bool occ[32]; int R[32]; uint32_t M[32];
+                uint32_t valid = 0, occm = 0; int s0 = 0;
+                for (int l = 0; l < 32; l++) {
+                    float x, y, z;
+                    occ[l] = fast ? arn_march_probe<true, true>(c, ray, bits, t[l], x, y, z, dts[l], tgt[l])
+                                  : arn_march_probe<false, false>(c, ray, bits, t[l], x, y, z, dts[l], tgt[l]);
+                    if (t[l] < t2) valid |= 1u << l;
+                    if (occ[l]) occm |= 1u << l;
+                    if (t[l] < pending) s0++;
+                }
+                for (int l = 0; l < 32; l++) {
+                    int lo = l + 1, hi = 32;
+                    for (int it = 0; it < 5; it++) {
+                        const int mid = (lo + hi) >> 1;
+                        const float tv = t[mid & 31];
+                        if (lo < hi) { if (tv < tgt[l]) lo = mid + 1; else hi = mid; }
+                    }
+                    R[l] = occ[l] ? l + 1 : lo; M[l] = 1u << l;
+                }
+                for (int it = 0; it < 5; it++) {
+                    uint32_t Mo[32]; int Ro[32];
+                    for (int l = 0; l < 32; l++) { Mo[l] = M[R[l] & 31]; Ro[l] = R[R[l] & 31]; }
+                    for (int l = 0; l < 32; l++) if (R[l] < 32) { M[l] |= Mo[l]; R[l] = Ro[l]; }
+                }
+                const uint32_t vis = s0 < 32 ? M[s0 & 31] : 0u;
+                uint32_t emit = vis & occm & valid;
+                const int rem = S - N;
+                bool done = valid != 0xffffffffu;
+                if (popc32(emit) >= rem) {
+                    done = true;
+                    uint32_t e2 = 0;
+                    for (int l = 0; l < 32; l++) if (((emit >> l) & 1u) && popc32(emit & ((1u << l) - 1u)) < rem) e2 |= 1u << l;
+                    emit = e2;
+                }
+                for (int l = 0; l < 32; l++) if ((emit >> l) & 1u) {
+                    const size_t q = (size_t)n * S + N + popc32(emit & ((1u << l) - 1u));
+                    ts[q] = t[l]; deltas[q] = dts[l];
+                }
+                if (emit) { const int last = 31 - __builtin_clz(emit); t_resume = ARN_ADD(t[last], dts[last]); moved = true; }
+                N += popc32(emit);
+                if (done) break;
+                if (vis) { const int last = 31 - __builtin_clz(vis); pending = occ[last] ? -INFINITY : tgt[last]; }
+                for (int l = 0; l < 32; l++)
+                    for (int k = 0; k < 32; k++) t[l] = ARN_ADD(t[l], arn_calc_dt(c, t[l]));
+            }
+        }
+        if (moved) hits_t[2 * r] = t_resume;
+        n_eff[n] = N;
+    }
+}

@@ -73,6 +73,15 @@ def test_test_march_bit_exact(harness, kind, w1, w3):
                              C.c_float(w.exp_step_factor), S, 1024, _p(ts), _p(dls), _p(xs), _p(ne))
         assert np.array_equal(ne, neff) and np.array_equal(ts, t) and np.array_equal(dls, dl) and np.array_equal(xs, x)
         assert np.array_equal(h1, h2)
+    # the warp-window form of the test march (march_test_warp_kernel), emulated lane by lane: same samples, same resume points
+    h1, h3 = ht.copy(), ht.copy()
+    for S in (9, 16, 64, 64, 33):
+        _, _, dl, t, neff = oracle.raymarching_test(ro, rd, h1, alive, bits, w.cascades, w.scale, w.exp_step_factor, 128, 1024, S)
+        ts = np.zeros((len(alive), S), np.float32); dls = np.zeros((len(alive), S), np.float32); ne = np.zeros(len(alive), np.int32)
+        harness.h_march_test_window(len(alive), _p(ro), _p(rd), _p(h3), _p(alive), _p(bits), w.cascades, 128, C.c_float(w.scale),
+                                    C.c_float(w.exp_step_factor), S, 1024, _p(ts), _p(dls), _p(ne))
+        assert np.array_equal(ne, neff) and np.array_equal(ts, t) and np.array_equal(dls, dl)
+        assert np.array_equal(h1, h3)
 
 
 @pytest.mark.parametrize("kind", ["W1", "W3"])
