@@ -47,20 +47,25 @@ def main():
     import render_utils
     import sg_shadow
 
-    d = make_inputs(0)
     prev = os.path.join(HERE, "sg_shadow_ref.npz")
     fh = np.load(prev)["fh_tab"] if os.path.exists(prev) and "--recompute-fh" not in sys.argv else fh_table()  # 90 s of scipy dblquad
+    # two geometries: the small default one, and the insertion tool's own (insert/main.py:107: SGShadow(pca, 20, 128, 2, envH=74, envW=148))
+    for tag, d, vol_range in (("", make_inputs(0), 4), ("_tool", make_inputs(3, ncomp=128, grid=(20, 20, 20), env=(74, 148)), 2)):
+        run_case(sg_shadow, render_utils, d, fh, vol_range, os.path.join(HERE, f"sg_shadow_ref{tag}.npz"), keep_fh=(tag == ""))
+
+
+def run_case(sg_shadow, render_utils, d, fh, vol_range, path, keep_fh):
     T = torch.from_numpy
     sg = object.__new__(sg_shadow.SGShadow)  # __init__ (sg_shadow.py:11-32) with stand-in data, on the CPU
     sg.delta_angle_decay_fac, sg.delta_shadow_fac, sg.delta_self_shadow_fac = 0.4, 2, 0.1
-    sg.vol_range = 4
-    sg.raw_h_angle = torch.asin(torch.Tensor([1.0 / 4]))
+    sg.vol_range = vol_range
+    sg.raw_h_angle = torch.asin(torch.Tensor([1.0 / vol_range]))
     sg.ncomponents, sg.envH, sg.envW = d["components"].shape[0], d["components"].shape[1], d["components"].shape[2]
     sg.fh_tab = T(fh)[None, None, ...]
     sg.coeff_volume, sg.components, sg.mean = T(d["coeff_volume"]), T(d["components"]), T(d["mean"])
 
     lSGs, pts, pos, rot = T(d["lSGs"]), T(d["pts"]), T(d["model_pos"]), T(d["rot_inv"])
-    out = {"fh_tab": fh}
+    out = {"fh_tab": fh} if keep_fh else {"vol_range": np.int32(vol_range)}
     with torch.no_grad():
         out["factor"] = sg.calc_shadow_factor(d["model_radius"], pts, pos, lSGs).numpy()
         lrot = lSGs.clone(); lrot[:, :3] = (rot @ lrot[:, :3].T).T          # main.py:496-499
@@ -88,7 +93,8 @@ def main():
             for _ in range(16):
                 noise = np.maximum(noise, np.abs(render_utils.SG_render_core(*[jit(a) for a in args], jit(lights.contiguous()), False, shadow).numpy() - base))
             out[name + "_noise"] = noise
-    np.savez_compressed(os.path.join(HERE, "sg_shadow_ref.npz"), **out)
+    np.savez_compressed(path, **out)
+    print(path)
     for k, v in out.items():
         print(k, v.shape, float(np.abs(v).mean()))
 

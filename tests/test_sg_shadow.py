@@ -26,8 +26,16 @@ from oracle import sg_shadow as osg  # noqa: E402
 RTOL, FLOOR = 1e-4, 1e-3
 
 
-def golden():
-    return np.load(os.path.join(ROOT, "tests", "golden", "sg_shadow_ref.npz"))
+def golden(tag=""):
+    return np.load(os.path.join(ROOT, "tests", "golden", f"sg_shadow_ref{tag}.npz"))
+
+
+# the two golden sets: (file tag, inputs, vol_range) -- the small default geometry and the insertion tool's own
+# (insert/main.py:107: SGShadow(pca_path, 20, 128, 2, envH=74, envW=148))
+def golden_case(tag):
+    if tag == "":
+        return make_inputs(0), 4
+    return make_inputs(3, ncomp=128, grid=(20, 20, 20), env=(74, 148)), 2
 
 
 def close(got, ref, what, band=None, rtol=RTOL):
@@ -42,15 +50,16 @@ def close(got, ref, what, band=None, rtol=RTOL):
 
 
 # ------------------------------------------------------------------------------------------------------------ oracle (CPU)
-def _oracle_all(d, fh):
+def _oracle_all(d, fh, vol_range=4):
     cv = d["coeff_volume"][0]
     tabs = (cv, d["components"], d["mean"], fh)
+    vr = dict(vol_range=vol_range)
     lrot = d["lSGs"].copy(); lrot[:, :3] = (d["rot_inv"] @ lrot[:, :3].T).T
     out = {}
-    out["factor"] = osg.calc_shadow_factor(d["model_radius"], d["pts"], d["model_pos"], d["lSGs"], *tabs)
-    out["factor_rot"] = osg.calc_shadow_factor(d["model_radius"], d["pts"], d["model_pos"], lrot, *tabs, rot_inv=d["rot_inv"])
-    dec = osg.calc_self_shadow_light_decay(d["model_radius"], d["pts"], d["model_pos"], d["lSGs"], *tabs)
-    dec_rot = osg.calc_self_shadow_light_decay(d["model_radius"], d["pts"], d["model_pos"], d["lSGs"], *tabs, rot_inv=d["rot_inv"])
+    out["factor"] = osg.calc_shadow_factor(d["model_radius"], d["pts"], d["model_pos"], d["lSGs"], *tabs, **vr)
+    out["factor_rot"] = osg.calc_shadow_factor(d["model_radius"], d["pts"], d["model_pos"], lrot, *tabs, rot_inv=d["rot_inv"], **vr)
+    dec = osg.calc_self_shadow_light_decay(d["model_radius"], d["pts"], d["model_pos"], d["lSGs"], *tabs, **vr)
+    dec_rot = osg.calc_self_shadow_light_decay(d["model_radius"], d["pts"], d["model_pos"], d["lSGs"], *tabs, rot_inv=d["rot_inv"], **vr)
     out["decay_full"], out["decay_rot_full"] = dec, dec_rot
     out["decay"], out["decay_rot"] = dec[:64], dec_rot[:64]
     g = [d[k] for k in ("albedo", "metal", "rough", "normal", "vdirs")]
@@ -60,11 +69,13 @@ def _oracle_all(d, fh):
     return out
 
 
-def test_oracle_matches_unmodified_reference():
-    g = golden()
-    o = _oracle_all(make_inputs(0), g["fh_tab"])
+@pytest.mark.parametrize("tag", ["", "_tool"])
+def test_oracle_matches_unmodified_reference(tag):
+    g = golden(tag)
+    d, vol_range = golden_case(tag)
+    o = _oracle_all(d, golden()["fh_tab"], vol_range)
     for k in ("factor", "factor_rot", "decay", "decay_rot"):
-        close(o[k], g[k], k)
+        close(o[k], g[k], k, rtol=RTOL if tag == "" else 3e-4)   # 128-term ssdf sums next to steep f_h columns: see the second-seed test
     for k in ("radiance_clamp", "radiance_hdr", "radiance_noshadow"):
         close(o[k], g[k], k, band=g[k + "_noise"])
 
@@ -106,12 +117,12 @@ def _jitter(x, rs):
 
 
 # ------------------------------------------------------------------------------------------------------------ CUDA (GPU)
-def _cuda_all(d, fh):
+def _cuda_all(d, fh, vol_range=4):
     import torch
     from ar_nerf_b200.sg_shadow import SG_render_core, SGShadow
     dev = torch.device("cuda:0")
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    sg = SGShadow.from_tensors(T(d["coeff_volume"]), T(d["components"]), T(d["mean"]), T(fh), device=dev)
+    sg = SGShadow.from_tensors(T(d["coeff_volume"]), T(d["components"]), T(d["mean"]), T(fh), vol_range=vol_range, device=dev)
     lSGs, pts, pos, rot = T(d["lSGs"]), T(d["pts"]), T(d["model_pos"]), T(d["rot_inv"])
     lrot = lSGs.clone(); lrot[:, :3] = (rot @ lrot[:, :3].T).T
     out = {}
@@ -132,11 +143,13 @@ def _cuda_all(d, fh):
 
 
 @pytest.mark.gpu
-def test_cuda_matches_unmodified_reference():
-    g = golden()
-    c = _cuda_all(make_inputs(0), g["fh_tab"])
+@pytest.mark.parametrize("tag", ["", "_tool"])
+def test_cuda_matches_unmodified_reference(tag):
+    g = golden(tag)
+    d, vol_range = golden_case(tag)
+    c = _cuda_all(d, golden()["fh_tab"], vol_range)
     for k in ("factor", "factor_rot", "decay", "decay_rot"):
-        close(c[k], g[k], k)
+        close(c[k], g[k], k, rtol=RTOL if tag == "" else 3e-4)
     for k in ("radiance_clamp", "radiance_hdr", "radiance_noshadow"):
         close(c[k], g[k], k, band=g[k + "_noise"])
     close(c["fused_clamp"], g["radiance_clamp"], "fused_clamp", band=g["radiance_clamp_noise"])
