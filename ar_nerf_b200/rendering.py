@@ -162,9 +162,13 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
         if premarch:
             pm = w.get('premarch')
             if pm is None or pm[0].numel() < stride * N_rays:
-                pm = (torch.empty(stride * N_rays, dtype=torch.float32, device=device), torch.empty(N_rays, dtype=torch.int32, device=device),
-                      torch.empty(N_rays, dtype=torch.int32, device=device))
+                try:
+                    pm = (torch.empty(stride * N_rays, dtype=torch.float32, device=device), torch.empty(N_rays, dtype=torch.int32, device=device),
+                          torch.empty(N_rays, dtype=torch.int32, device=device))
+                except torch.cuda.OutOfMemoryError:  # no room for the sample table next to whatever else lives on the GPU: march per iteration
+                    pm, premarch = None, False
                 w['premarch'] = pm
+        if premarch:
             ts_all, totals, cursor = pm
             call("arn_march_test_all", ptr(rays_o), ptr(rays_d), ptr(hits_t2), N_rays, ptr(model.density_bitfield), model.cascades,
                  model.grid_size, float(model.scale), float(exp_step_factor), MAX_SAMPLES, stride, ptr(ts_all), ptr(totals), ptr(cursor), s_)
