@@ -116,6 +116,32 @@ def _jitter(x, rs):
     return np.where(step == 0, x, np.nextafter(x, np.where(step > 0, np.float32(np.inf), np.float32(-np.inf)).astype(np.float32))).astype(np.float32)
 
 
+def test_host_mirror_reads_the_reference_files_and_has_no_cpu_path(tmp_path):
+    """ar_nerf_b200.sg_shadow.SGShadow.__init__ mirrors insert/sg_shadow.py:11-32: same files, same table layout, same
+    attribute names; the per-pixel methods refuse host tensors (there is no CPU / PyTorch fallback)."""
+    import torch
+    from ar_nerf_b200.sg_shadow import SGShadow
+    g, C_, eh, ew = 5, 8, 6, 7
+    r = np.random.RandomState(0)
+    data = {"coeff": torch.from_numpy(r.randn(g * g * g, C_).astype(np.float32)), "component": torch.from_numpy(r.randn(C_, eh, ew).astype(np.float32)),
+            "mean": torch.from_numpy(r.randn(1, eh, ew).astype(np.float32))}
+    pca, fh = str(tmp_path / "pca.pt"), str(tmp_path / "fh_pretab.npy")
+    torch.save(data, pca); np.save(fh, r.rand(12, 9).astype(np.float32))
+    sg = SGShadow(pca, g, C_, 2, envH=eh, envW=ew, fh_tab_path=fh, device="cpu")
+    want = data["coeff"].reshape(g, g, g, C_).permute(3, 2, 1, 0).unsqueeze(0)       # sg_shadow.py:27-29
+    assert torch.equal(sg.coeff_volume, want) and sg.coeff_volume.shape == (1, C_, g, g, g)
+    assert torch.equal(sg._coeff_cl, want[0].permute(1, 2, 3, 0)) and sg._coeff_cl.is_contiguous()   # channel-last copy the kernels read
+    assert torch.equal(sg.components, data["component"]) and torch.equal(sg.mean, data["mean"])
+    assert sg.fh_tab.shape == (1, 1, 12, 9) and sg.vol_range == 2 and sg.ncomponents == C_ and (sg.envH, sg.envW) == (eh, ew)
+    assert (sg.delta_angle_decay_fac, sg.delta_shadow_fac, sg.delta_self_shadow_fac) == (0.4, 2, 0.1)
+    assert abs(float(sg.raw_h_angle) - float(np.arcsin(0.5))) < 1e-7
+    lSGs = torch.from_numpy(make_inputs(0)["lSGs"])
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        sg.calc_shadow_factor(0.3, torch.zeros(4, 3), torch.zeros(3), lSGs)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        sg.calc_self_shadow_light_dacay(0.3, torch.zeros(4, 3), torch.zeros(3), lSGs)
+
+
 # ------------------------------------------------------------------------------------------------------------ CUDA (GPU)
 def _cuda_all(d, fh, vol_range=4):
     import torch
