@@ -129,6 +129,7 @@ SIGNATURES = {
     "arn_sg_shadow_factor": [C.POINTER(SgTables), P, I, P, L, P, P, F, P, P, P],
     "arn_sg_shade": [C.POINTER(SgTables), P, P, I, P, L, P, P, F, P, P, P, P, P, I, I, P, P, P, P],
     "arn_sg_shade_px": [P, I, I, L, P, P, P, P, P, I, P, P],
+    "arn_sf_soft_shadow": [P, I, I, I, I, F, P, P, L, P, P, F, P, P, P],
     "arn_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, I, P],
     "arn_adam_step2": [P, P, P, P, P, L, P, P, P, P, P, L, F, F, F, F, I, F, I, P],
 }

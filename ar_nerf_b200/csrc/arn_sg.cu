@@ -334,6 +334,59 @@ __global__ void __launch_bounds__(128) sg_shade_px_kernel(const float* __restric
 
 // per-light tables + inte_L (padded to 4 floats) + one ssdf per (light, thread of the 128-thread block)
 static size_t sg_smem_bytes(int n_lights, int C) { return ((size_t)n_lights * (C + kLRec) + 4 + (size_t)n_lights * 128) * sizeof(float); }
+// ---- Shadow field, the SH alternative to the SG shadow (insert/shadow_fields.py:59-78 soft_shadow_map): K SH coefficients of the
+// object's visibility fetched trilinearly at the point (grid_sample, border, align_corners = True; channel-last volume: a
+// corner is K contiguous floats), SH_product0 against the lighting's SH per colour, ratio to the unshadowed DC term, pow 10.
+struct SfLight { float sh[ARN_SF_MAX_COEFFS * 3]; };  // model_sh9[k][c]
+__global__ void __launch_bounds__(256) sf_soft_shadow_kernel(const float* __restrict__ sf_cl, int D, int H, int W, int K, float vol_range, SgFrame fr,
+                                                             SfLight ml, const float* __restrict__ pts, int64_t n, float* __restrict__ sh_out,
+                                                             float* __restrict__ shadow) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m[3] = {pts[3 * i] - fr.pos[0], pts[3 * i + 1] - fr.pos[1], pts[3 * i + 2] - fr.pos[2]};
+    if (fr.has_rot) {
+        const float a = fr.rot[0] * m[0] + fr.rot[1] * m[1] + fr.rot[2] * m[2];
+        const float b = fr.rot[3] * m[0] + fr.rot[4] * m[1] + fr.rot[5] * m[2];
+        const float c = fr.rot[6] * m[0] + fr.rot[7] * m[1] + fr.rot[8] * m[2];
+        m[0] = a; m[1] = b; m[2] = c;
+    }
+    const int S[3] = {W, H, D};
+    int i0[3]; float w1[3]; bool ok1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float p = m[k] / fr.scale / vol_range;                      // shadow_fields.py:93 (no normalisation beyond the volume)
+        const float x = clampf(unnorm(p, S[k], true), 0.0f, (float)(S[k] - 1));
+        const float f = floorf(x);
+        i0[k] = (int)f; w1[k] = x - f; ok1[k] = i0[k] + 1 < S[k];
+    }
+    float sh[ARN_SF_MAX_COEFFS];
+#pragma unroll
+    for (int k = 0; k < ARN_SF_MAX_COEFFS; k++) sh[k] = 0.0f;
+#pragma unroll
+    for (int corner = 0; corner < 8; corner++) {
+        const int dx = corner & 1, dy = (corner >> 1) & 1, dz = corner >> 2;
+        if ((dx && !ok1[0]) || (dy && !ok1[1]) || (dz && !ok1[2])) continue;
+        const float w = (dx ? w1[0] : 1.0f - w1[0]) * (dy ? w1[1] : 1.0f - w1[1]) * (dz ? w1[2] : 1.0f - w1[2]);
+        const float* src = sf_cl + ((size_t)((i0[2] + dz) * H + (i0[1] + dy)) * W + (i0[0] + dx)) * K;
+#pragma unroll
+        for (int k = 0; k < ARN_SF_MAX_COEFFS; k++) if (k < K) sh[k] += __ldg(src + k) * w;
+    }
+    if (sh_out) {
+#pragma unroll
+        for (int k = 0; k < ARN_SF_MAX_COEFFS; k++) if (k < K) sh_out[i * K + k] = sh[k];
+    }
+    if (!shadow) return;
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float dot = 0.0f;
+#pragma unroll
+        for (int k = 0; k < ARN_SF_MAX_COEFFS; k++) if (k < K) dot += sh[k] * ml.sh[3 * k + c];
+        acc += clampf(0.2821f * dot / ml.sh[c], 0.0f, 1.0f);               // SH_product0 (insert_utils.py:153-154) over the unshadowed DC term
+    }
+    shadow[i] = powf(acc / 3.0f, 10.0f);                                   // mean over the colours, "to augment shadow effect" (:76)
+}
+
 static int check_tables(const arn_sg_tables_t* tb, int n_lights) {
     if (!tb || !tb->coeff_cl || !tb->components || !tb->mean || !tb->fh_tab) { set_error("arn_sg: null table pointer"); return ARN_E_INVALID; }
     if (tb->C < 4 || tb->C > kSgMaxComp || tb->C % 4 || n_lights < 1 || n_lights > kSgMaxLights || tb->D < 1 || tb->H < 1 || tb->W < 1 ||
@@ -409,4 +462,18 @@ extern "C" ARN_API int arn_sg_shade_px(const float* lSGs, int n_lights, int per_
     ARN_LAUNCH("sg_shade_px_kernel", st, sg_shade_px_kernel<<<ceil_div(n, 128), 128, 0, st>>>(lSGs, n_lights, per_pixel, n, albedo, metal, rough, normal, vdirs,
                                                                                              clamp01, radiance));
     return check_launch("sg_shade_px");
+}
+
+extern "C" ARN_API int arn_sf_soft_shadow(const float* sf_cl, int D, int H, int W, int K, float vol_range, const float* model_sh_host, const float* pts,
+                                          int64_t n, const float* model_pos_host, const float* rot_inv_host, float scale, float* sh_out, float* shadow,
+                                          arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0 && D >= 1 && H >= 1 && W >= 1 && K >= 1 && K <= ARN_SF_MAX_COEFFS && vol_range > 0.0f && scale > 0.0f, "bad sizes");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(sf_cl && pts && model_pos_host && (sh_out || shadow) && (!shadow || model_sh_host), "null pointer");
+    SfLight ml{};
+    if (model_sh_host) for (int k = 0; k < 3 * K; k++) ml.sh[k] = model_sh_host[k];
+    cudaStream_t st = (cudaStream_t)stream;
+    ARN_LAUNCH("sf_soft_shadow_kernel", st, sf_soft_shadow_kernel<<<ceil_div(n, 256), 256, 0, st>>>(sf_cl, D, H, W, K, vol_range, make_frame(model_pos_host, rot_inv_host, scale),
+                                                                                                   ml, pts, n, sh_out, shadow));
+    return check_launch("sf_soft_shadow");
 }

@@ -502,6 +502,16 @@ int arn_sg_shade_px(const float* lSGs, int n_lights, int per_pixel, int64_t n, c
                     const float* rough, const float* normal, const float* vdirs, int clamp01, float* radiance,
                     arn_stream_t stream);
 
+/* Shadow field, the SH alternative to the SG shadow: insert/shadow_fields.py:59-78 soft_shadow_map with :92-101 / :112-121
+ * fetch_sh (SimplifySF / ComplexSF) and insert/insert_utils.py:153-154 SH_product0.  sf_cl = the field's volume CHANNEL-LAST
+ * (D,H,W,K) -- the reference's sf_vol (1,K,D,H,W) permuted once by the caller --, K <= ARN_SF_MAX_COEFFS SH coefficients;
+ * model_sh_host = the lighting's SH (K,3) row-major on the host.  Out (either may be NULL): sh_out (n,K) = fetch_sh of the
+ * points relative to the model, shadow (n) = the soft shadow factor. */
+#define ARN_SF_MAX_COEFFS 16
+int arn_sf_soft_shadow(const float* sf_cl, int D, int H, int W, int K, float vol_range, const float* model_sh_host, const float* pts,
+                       int64_t n, const float* model_pos_host, const float* rot_inv_host, float scale, float* sh_out, float* shadow,
+                       arn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

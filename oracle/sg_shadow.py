@@ -198,3 +198,22 @@ def sg_render_core(albedo, metal, rough, normal, vdirs, lSGs, clamp01, self_shad
         kD = (F(1) - kS) * (F(1) - metal)
         rad = kD * diff + spec
     return (np.clip(rad, 0, 1) if clamp01 else np.maximum(rad, F(0))).astype(F)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Shadow field (the SH alternative to the SG shadow): insert/shadow_fields.py:59-78 soft_shadow_map, :92-101 / :112-121
+# fetch_sh, insert/insert_utils.py:153-154 SH_product0.  Pinned by tests/golden/shadow_field_ref.npz
+# (tests/golden/make_golden_sf.py: outputs of the unmodified reference functions).
+def sf_fetch_sh(scale, m2pts, sf_vol, vol_range):
+    """shadow_fields.py:92-101: sf_vol (K,D,H,W); points relative to the model, NOT normalised beyond the volume (border)."""
+    p = m2pts.astype(F) / F(scale) / F(vol_range)
+    return grid_sample_3d(sf_vol, p, align_corners=True)
+
+
+def soft_shadow_map(sf_vol, vol_range, model_pos, model_r, model_sh9, pts, rot_inv=None):
+    """shadow_fields.py:59-78.  model_sh9 (1,K,3) -> (px,)."""
+    sh = sf_fetch_sh(model_r, _m2pts(pts, model_pos, rot_inv), sf_vol, vol_range)               # px,K
+    new_ir = F(0.2821) * (sh @ model_sh9[0].astype(F))                                           # SH_product0 per colour: px,3
+    old_ir = model_sh9[:, 0, :].astype(F)                                                        # 1,3
+    res = np.mean(np.clip(new_ir / old_ir, 0.0, 1.0), axis=-1, dtype=F)
+    return np.power(res, F(10)).astype(F)

@@ -47,3 +47,26 @@ def make_inputs(seed=0, ncomp=NCOMP, grid=(GRID, GRID, GRID), env=(ENV, ENV)):
     d["metal"] = r.uniform(0.0, 1.0, (N_PTS, 1)).astype(f)
     d["rough"] = r.uniform(0.2, 1.0, (N_PTS, 1)).astype(f)
     return d
+
+
+def make_sf_inputs(seed=0, k=9, grid=(12, 10, 11)):
+    """Shadow-field inputs (insert/shadow_fields.py): sf_vol (1,K,D,H,W) SH coefficients of the object's visibility, the
+    lighting's SH model_sh9 (1,K,3), scene points around the model, a rotation."""
+    r = np.random.RandomState(100 + seed)
+    f = np.float32
+    d = {}
+    vol = r.randn(1, k, *grid) * 0.2
+    vol[:, 0] = np.abs(vol[:, 0]) * 2 + 3.0                   # visibility: a dominant positive DC term (shadow ratios around 0.85 .. 1.1)
+    d["sf_vol"] = vol.astype(f)
+    sh = r.randn(1, k, 3) * 0.3
+    sh[:, 0, :] = np.abs(sh[:, 0, :]) + 1.0
+    d["model_sh9"] = sh.astype(f)
+    d["model_pos"] = np.array([-0.2, 0.1, 0.05], f)
+    d["model_radius"] = 0.25
+    rad = np.concatenate([r.uniform(0.1, 1.0, N_PTS // 2), r.uniform(1.0, 4.0, N_PTS - N_PTS // 2)])[:, None]
+    d["pts"] = (d["model_pos"] + _unit(r.randn(N_PTS, 3)) * rad).astype(f)
+    q, _ = np.linalg.qr(r.randn(3, 3))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    d["rot_inv"] = q.astype(f)
+    return d
