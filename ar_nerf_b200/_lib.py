@@ -79,6 +79,7 @@ SIGNATURES = {
     "arn_grid_cell_positions": [P, P, L, I, F, P, P],
     "arn_grid_sample_cells": [P, F, I, F, P, P, L, P, P, P, P, P],
     "arn_density_grid_update": [P, P, P, F, F, L, P, P, P],
+    "arn_mark_invisible_cells": [P, P, L, I, F, P, I, P, F, F, F, P, P, P],
     "arn_profile_enable": [I],
     "arn_profile_report": [C.c_char_p, I],
     "arn_ray_aabb_intersect": [P, P, L, P, P, I, I, P, P, P, P],

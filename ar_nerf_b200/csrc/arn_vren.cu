@@ -175,6 +175,55 @@ __global__ void __launch_bounds__(256) cell_positions_kernel(const int32_t* __re
     xyzs[e] = __fadd_rn(c, j);
 }
 
+// NGP.mark_invisible_cells (networks.py:209-250): a cell of cascade c is kept (density 0) when at least one camera sees its
+// centre inside the image at depth >= near and no camera has it inside the image closer than near; otherwise -1.  One
+// thread per cell walks all cameras (world-to-camera rows staged through shared memory); count_grid gets the covered
+// fraction.  Operation order (plain IEEE mul/add, this file is compiled with -fmad=false):
+//   x_w = ((coord * 1/(G-1)) * 2 - 1) * (s - s/G);  x_c[i] = ((R[i][0] x + R[i][1] y) + R[i][2] z) + T[i];
+//   uvd[i] = (K[i][0] x_c + K[i][1] y_c) + K[i][2] z_c;  uv = uvd[:2] / uvd[2]
+constexpr int kCamTile = 128;
+__global__ void __launch_bounds__(256) mark_invisible_kernel(const int32_t* __restrict__ coords, const int64_t* __restrict__ indices, int64_t n_cells,
+                                                             float inv_gm1, float s_minus_half, const float* __restrict__ w2c, int n_cams,
+                                                             float k00, float k01, float k02, float k10, float k11, float k12, float k20, float k21,
+                                                             float k22, float img_w, float img_h, float near, float* __restrict__ density_grid,
+                                                             float* __restrict__ count_grid) {
+    __shared__ float cam[kCamTile * 12];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n_cells;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (live) {
+        x = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)coords[3 * i], inv_gm1), 2.0f), 1.0f), s_minus_half);
+        y = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)coords[3 * i + 1], inv_gm1), 2.0f), 1.0f), s_minus_half);
+        z = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)coords[3 * i + 2], inv_gm1), 2.0f), 1.0f), s_minus_half);
+    }
+    int covered = 0; bool too_near = false;
+    for (int c0 = 0; c0 < n_cams; c0 += kCamTile) {
+        const int nc = min(kCamTile, n_cams - c0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nc * 12; e += blockDim.x) cam[e] = w2c[(int64_t)c0 * 12 + e];
+        __syncthreads();
+        if (!live) continue;
+        for (int c = 0; c < nc; c++) {
+            const float* M = cam + 12 * c;  // R row-major (9) | T (3)
+            const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x), __fmul_rn(M[1], y)), __fmul_rn(M[2], z)), M[9]);
+            const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[3], x), __fmul_rn(M[4], y)), __fmul_rn(M[5], z)), M[10]);
+            const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[6], x), __fmul_rn(M[7], y)), __fmul_rn(M[8], z)), M[11]);
+            const float u0 = __fadd_rn(__fadd_rn(__fmul_rn(k00, xc), __fmul_rn(k01, yc)), __fmul_rn(k02, zc));
+            const float v0 = __fadd_rn(__fadd_rn(__fmul_rn(k10, xc), __fmul_rn(k11, yc)), __fmul_rn(k12, zc));
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(k20, xc), __fmul_rn(k21, yc)), __fmul_rn(k22, zc));
+            const float u = __fdiv_rn(u0, d), v = __fdiv_rn(v0, d);
+            const bool in_image = d >= 0.0f && u >= 0.0f && u < img_w && v >= 0.0f && v < img_h;
+            covered += (in_image && d >= near) ? 1 : 0;
+            too_near |= in_image && d < near;
+        }
+    }
+    if (!live) return;
+    const float count = __fdiv_rn((float)covered, (float)n_cams);
+    const int64_t o = indices[i];
+    count_grid[o] = count;
+    density_grid[o] = (count > 0.0f && !too_near) ? 0.0f : -1.0f;
+}
+
 // ---- Steady-state cell selection of the occupancy refresh (networks.py:181-207 + :263-267) in three small launches.
 // M uniform cells come from the caller's randint draw; M occupied cells are "the k-th occupied cell, k = u mod count" of the
 // caller's second draw (the reference indexes nonzero(grid > thr) with randint(count): the same distribution).  The k-th
@@ -1488,6 +1537,19 @@ extern "C" ARN_API int arn_grid_cell_positions(const int32_t* coords, const floa
     ARN_LAUNCH("cell_positions_kernel", (cudaStream_t)stream, cell_positions_kernel<<<ceil_div(3 * n_cells, 256), 256, 0, (cudaStream_t)stream>>>(
         coords, rnd, 3 * n_cells, 1.0f / (float)(grid_size - 1), s_minus_half, half_f, xyzs));
     return check_launch("grid_cell_positions");
+}
+
+extern "C" ARN_API int arn_mark_invisible_cells(const int32_t* coords, const int64_t* indices, int64_t n_cells, int grid_size, float s,
+                                                const float* w2c, int n_cams, const float* K_host, float img_w, float img_h, float near,
+                                                float* density_grid, float* count_grid, arn_stream_t stream) {
+    ARN_REQUIRE(n_cells >= 0 && grid_size >= 2 && n_cams >= 1, "bad size");
+    if (n_cells == 0) return ARN_OK;
+    ARN_REQUIRE(coords && indices && w2c && K_host && density_grid && count_grid, "null pointer");
+    const float s_minus_half = (float)((double)s - (double)s / (double)grid_size);  // Python double arithmetic, cast by torch to float32
+    ARN_LAUNCH("mark_invisible_kernel", (cudaStream_t)stream, mark_invisible_kernel<<<ceil_div(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(
+        coords, indices, n_cells, 1.0f / (float)(grid_size - 1), s_minus_half, w2c, n_cams, K_host[0], K_host[1], K_host[2], K_host[3], K_host[4],
+        K_host[5], K_host[6], K_host[7], K_host[8], img_w, img_h, near, density_grid, count_grid));
+    return check_launch("mark_invisible_cells");
 }
 
 extern "C" ARN_API int arn_grid_sample_cells(const float* density_grid, float density_threshold, int grid_size, float s, const int32_t* coords1,

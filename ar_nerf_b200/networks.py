@@ -177,29 +177,17 @@ class NGP(nn.Module):
 
     @torch.no_grad()
     def mark_invisible_cells(self, K, poses, img_wh, chunk=64 ** 3):
-        """networks.py:209-250."""
-        N_cams = poses.shape[0]
+        """networks.py:209-250: cells no camera covers, or that lie closer than NEAR_DISTANCE in front of a camera, get density
+        -1 (never revived by update_density_grid); `count_grid` holds the covered fraction.  One native launch per cascade over
+        all cells and cameras (arn_mark_invisible_cells); `chunk` is accepted for signature compatibility and unused."""
         self.count_grid = torch.zeros_like(self.density_grid)
-        w2c_R = rearrange(poses[:, :3, :3], 'n a b -> n b a')
-        w2c_T = -w2c_R @ poses[:, :3, 3:]
-        cells = self.get_all_cells()
-        for c in range(self.cascades):
-            indices, coords = cells[c]
-            for i in range(0, len(indices), chunk):
-                xyzs = coords[i:i + chunk] / (self.grid_size - 1) * 2 - 1
-                s = min(2 ** (c - 1), self.scale)
-                half_grid_size = s / self.grid_size
-                xyzs_w = (xyzs * (s - half_grid_size)).T
-                xyzs_c = w2c_R @ xyzs_w + w2c_T
-                uvd = K @ xyzs_c
-                uv = uvd[:, :2] / uvd[:, 2:]
-                in_image = (uvd[:, 2] >= 0) & (uv[:, 0] >= 0) & (uv[:, 0] < img_wh[0]) & (uv[:, 1] >= 0) & (uv[:, 1] < img_wh[1])
-                covered_by_cam = (uvd[:, 2] >= NEAR_DISTANCE) & in_image
-                self.count_grid[c, indices[i:i + chunk]] = count = covered_by_cam.sum(0) / N_cams
-                too_near_to_cam = (uvd[:, 2] < NEAR_DISTANCE) & in_image
-                too_near_to_any_cam = too_near_to_cam.any(0)
-                valid_mask = (count > 0) & (~too_near_to_any_cam)
-                self.density_grid[c, indices[i:i + chunk]] = torch.where(valid_mask, 0., -1.)
+        dev = self.density_grid.device
+        c2w = poses.to(dev).float()
+        rot = c2w[:, :3, :3].transpose(1, 2)                                   # world -> camera rotation
+        w2c = torch.cat([rot.reshape(-1, 9), (-rot @ c2w[:, :3, 3:]).reshape(-1, 3)], 1).contiguous()
+        for c, (indices, coords) in enumerate(self.get_all_cells()):
+            vren.mark_invisible_cells(coords, indices, self.grid_size, min(2 ** (c - 1), self.scale), w2c, K, img_wh, NEAR_DISTANCE,
+                                      self.density_grid[c], self.count_grid[c])
 
     @torch.no_grad()
     def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):

@@ -181,6 +181,20 @@ def density_grid_update(density_grid, density_tmp, decay_cells, decay, density_t
     return scratch[2048 * 16:2048 * 16 + 4].view(torch.float32)
 
 
+def mark_invisible_cells(coords, indices, grid_size, s, w2c, K, img_wh, near, density_grid_c, count_grid_c):
+    """networks.py:209-250 for one cascade, every camera in one launch.  coords (n,3) i32, indices (n) i64, w2c (n_cams,12) f32
+    (rotation row-major | translation), K (3,3); density_grid_c / count_grid_c (G^3) f32 are written at `indices`."""
+    import ctypes as C
+    check_tensor(coords, "coords", torch.int32, 2, 3); check_tensor(indices, "indices", torch.int64, 1)
+    check_tensor(w2c, "w2c", torch.float32, 2, 12)
+    check_tensor(density_grid_c, "density_grid", torch.float32, 1); check_tensor(count_grid_c, "count_grid", torch.float32, 1)
+    if indices.shape[0] != coords.shape[0]:
+        raise RuntimeError("indices and coords must have the same length")
+    k_host = (C.c_float * 9)(*[float(v) for v in torch.as_tensor(K, dtype=torch.float32).reshape(-1).tolist()])
+    call("arn_mark_invisible_cells", ptr(coords), ptr(indices), coords.shape[0], int(grid_size), float(s), ptr(w2c), w2c.shape[0], k_host,
+         float(img_wh[0]), float(img_wh[1]), float(near), ptr(density_grid_c), ptr(count_grid_c), stream())
+
+
 def raymarching_train(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size,
                       max_samples):
     """binding.cpp:60-81 -> raymarching.cu:283-332.  Returns [rays_a, xyzs, dirs, deltas, ts, counter]."""

@@ -112,6 +112,15 @@ int arn_grid_sample_cells(const float* density_grid, float density_threshold, in
 int arn_density_grid_update(float* density_grid, const float* density_tmp, const float* decay_cells, float decay,
                             float density_threshold, int64_t n_cells, uint8_t* density_bitfield, void* scratch,
                             arn_stream_t stream);
+/* NGP.mark_invisible_cells (networks.py:209-250) for ONE cascade, all cameras in one launch (the reference chunks the cells
+ * and materialises (N_cams,3,chunk) tensors): cell i (coords (n_cells,3) i32, indices (n_cells) i64 = morton codes) projects
+ * its centre x_w = (coords/(G-1)*2-1)*(s - s/G) through every camera -- w2c (n_cams,12) f32 on the device, per camera the
+ * world-to-camera rotation row-major (9) then the translation (3), i.e. poses[:, :3, :3]^T and -R^T t -- and K_host (3x3
+ * row-major, host).  count_grid[idx] = (#cameras with the cell inside the image at depth >= near) / n_cams;
+ * density_grid[idx] = 0 if count > 0 and no camera has the cell inside the image closer than near, else -1. */
+int arn_mark_invisible_cells(const int32_t* coords, const int64_t* indices, int64_t n_cells, int grid_size, float s,
+                             const float* w2c, int n_cams, const float* K_host, float img_w, float img_h, float near,
+                             float* density_grid, float* count_grid, arn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Training ray march.  Replaces vren.raymarching_train (binding.cpp:60-81 -> raymarching.cu:283-332, kernel :166-280).

@@ -94,6 +94,60 @@ def packbits(density_grid, threshold, density_bitfield):
     lib().orc_packbits(i32(density_bitfield.size), _p(g), f(threshold), _p(density_bitfield))
 
 
+def mark_invisible_cells(coords, indices, grid_size, s, poses, K, img_wh, near=0.01, return_margin=False):
+    """models/networks.py:209-250 for one cascade (half extent s): (density (G^3) f32 in {0,-1}, count (G^3) f32) written at
+    `indices`.  float32 throughout, plain IEEE mul/add in a FIXED order (the reference's batched matmuls leave the order to
+    cuBLAS / MKL): x_w = ((c * 1/(G-1)) * 2 - 1) * f32(s - s/G); x_c = ((R0 x + R1 y) + R2 z) + T; uvd = (K0 x_c + K1 y_c) + K2 z_c.
+    return_margin: also the smallest relative distance of any decision (d>=0, d>=near, 0<=u<W, 0<=v<H) to its threshold per
+    cell, evaluated in float64 -- cells with a tiny margin may legitimately differ under another summation order."""
+    f32 = np.float32
+    coords = np.ascontiguousarray(coords, np.int32); indices = _i64(indices)
+    poses = _f32(poses); K = _f32(K)
+    G = int(grid_size)
+    smh = f32(float(s) - float(s) / G)
+    xyz = ((coords.astype(f32) * f32(f32(1.0) / f32(G - 1))) * f32(2.0) - f32(1.0)) * smh          # (n,3)
+    rot = np.transpose(poses[:, :3, :3], (0, 2, 1)).astype(f32)                                  # (N,3,3) world -> camera
+    trans = np.zeros((len(poses), 3), f32)
+    for i in range(3):  # -R^T t, torch bmm on tiny operands: computed in float64 and rounded once (the kernel receives this tensor)
+        trans[:, i] = -(rot[:, i, :].astype(np.float64) * poses[:, :3, 3].astype(np.float64)).sum(1)
+    n, N = len(coords), len(poses)
+    covered = np.zeros(n, np.int32); too_near = np.zeros(n, bool)
+    margin = np.full(n, np.inf)
+    x, y, z = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    W, H = f32(img_wh[0]), f32(img_wh[1])
+    for c in range(N):
+        R, T = rot[c], trans[c]
+        pc = [((R[i, 0] * x + R[i, 1] * y) + R[i, 2] * z) + T[i] for i in range(3)]
+        uvd = [(K[i, 0] * pc[0] + K[i, 1] * pc[1]) + K[i, 2] * pc[2] for i in range(3)]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u, v = uvd[0] / uvd[2], uvd[1] / uvd[2]
+            d = uvd[2]
+            in_image = (d >= 0) & (u >= 0) & (u < W) & (v >= 0) & (v < H)
+            covered += (in_image & (d >= f32(near))).astype(np.int32)
+            too_near |= in_image & (d < f32(near))
+            if return_margin:
+                d64, u64, v64 = d.astype(np.float64), u.astype(np.float64), v.astype(np.float64)
+                m = np.minimum.reduce([np.abs(d64), np.abs(d64 - near), np.abs(u64) / float(W), np.abs(u64 - float(W)) / float(W),
+                                       np.abs(v64) / float(H), np.abs(v64 - float(H)) / float(H)])
+                margin = np.minimum(margin, np.nan_to_num(m, nan=0.0))
+    count = covered.astype(f32) / f32(N)
+    density = np.full(G ** 3, np.nan, f32); cnt = np.full(G ** 3, np.nan, f32)
+    density[indices] = np.where((count > 0) & ~too_near, f32(0.0), f32(-1.0)); cnt[indices] = count
+    if return_margin:
+        mg = np.full(G ** 3, np.inf); mg[indices] = margin
+        return density, cnt, mg
+    return density, cnt
+
+
+def world_to_camera(poses):
+    """(N,12) f32: per camera the world-to-camera rotation row-major then the translation (what arn_mark_invisible_cells takes),
+    with the translation computed as in mark_invisible_cells above."""
+    poses = _f32(poses)
+    rot = np.transpose(poses[:, :3, :3], (0, 2, 1)).astype(np.float32)
+    trans = -(rot.astype(np.float64) * poses[:, None, :3, 3].astype(np.float64)).sum(2)
+    return np.concatenate([rot.reshape(-1, 9), trans.astype(np.float32)], 1)
+
+
 def raymarching_train(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size,
                       max_samples):
     """Returns (rays_a, xyzs, dirs, deltas, ts, counter) already sliced to counter[0] samples, canonical ray order."""

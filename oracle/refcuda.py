@@ -1,0 +1,159 @@
+"""TEST / MEASUREMENT INFRASTRUCTURE -- never imported by the product (ar_nerf_b200/).
+
+Times the UNMODIFIED reference CUDA extension (oracle/_ref/vren*.so, built by oracle/build_ref.sh from
+/root/reference/models/csrc for sm_100a) on a B200, stage by stage, beside libarnerf.so on the SAME inputs:
+
+  train geometry   : ray_aabb_intersect + near clamp + raymarching_train + slice by counter[0]
+                     (models/rendering.py:29-31, models/custom_functions.py:79-96 -> intersection.cu:59-100, raymarching.cu:283-332)
+  train compositing: composite_train_fw + composite_train_bw (custom_functions.py:139-159 -> volumerendering.cu:47-201)
+  test frame       : every raymarching_test + composite_test_fw call of the loop of models/rendering.py:189-236
+                     (raymarching.cu:407-454, volumerendering.cu:251-284)
+
+Both sides are driven through the same Python call sequence the reference uses (the `vren` module functions), each
+stage bracketed by CUDA events on the current stream; the sigmas / rgbs fed to the compositing stages come from
+libarnerf's field in both cases.  The FIELD half of the reference (tiny-cuda-nn hash grid + fully fused MLP) is an
+un-vendored dependency that is absent here, so it has no reference timing: the table says so.
+"""
+import glob
+import importlib.util
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NEAR_DISTANCE = 0.01
+MAX_SAMPLES = 1024
+_mod = None
+
+
+def load():
+    """The reference's pybind module `vren`, or None when oracle/_ref holds no build."""
+    global _mod
+    if _mod is None:
+        cands = glob.glob(os.path.join(ROOT, "oracle", "_ref", "vren*.so"))
+        if not cands:
+            return None
+        import torch  # noqa: F401  (libtorch must be loaded first)
+        spec = importlib.util.spec_from_file_location("vren", cands[0])
+        _mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_mod)
+    return _mod
+
+
+def _timed(fn, iters, warm=3):
+    """Mean device ms of fn() over `iters` calls (CUDA events on the current stream, synchronised on both sides)."""
+    import torch
+    out = None
+    for _ in range(warm):
+        out = fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, out
+
+
+def train_stages(model, batches, iters=20):
+    """Per-stage device ms of one 8192-ray training batch: reference extension vs libarnerf.so, same call sequence.
+    `batches`: list of (rays_o, rays_d, rgb) on the device."""
+    import torch
+
+    from ar_nerf_b200 import vren as ours
+    ref = load()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/vren*.so not built"}
+    dev = batches[0][0].device
+    center, half = model.center, model.half_size
+    esf = 0.0 if model.scale <= 0.5 else 1.0 / 256
+    k = [0]
+
+    def geometry(v):
+        def run():
+            ro, rd, _ = batches[k[0] % len(batches)]
+            k[0] += 1
+            _, hits_t, _ = v.ray_aabb_intersect(ro, rd, center, half, 1)
+            hits_t[(hits_t[:, 0, 0] >= 0) & (hits_t[:, 0, 0] < NEAR_DISTANCE), 0, 0] = NEAR_DISTANCE
+            noise = torch.rand_like(ro[:, 0])
+            rays_a, xyzs, dirs, deltas, ts, counter = v.raymarching_train(ro, rd, hits_t[:, 0].contiguous(), model.density_bitfield, model.cascades,
+                                                                       model.scale, esf, noise, model.grid_size, MAX_SAMPLES)
+            total = counter[0]
+            return rays_a, xyzs[:total], dirs[:total], deltas[:total], ts[:total]  # the slice is the reference's host sync
+        return run
+
+    out = {}
+    k[0] = 0
+    t_ref_geo, marched = _timed(geometry(ref), iters)
+    k[0] = 0
+    t_our_geo, _ = _timed(geometry(ours), iters)
+    rays_a, xyzs, dirs, deltas, ts = marched
+    with torch.no_grad():
+        sigmas, rgbs = model(xyzs.contiguous(), dirs.contiguous())
+    sigmas, rgbs, deltas, ts = sigmas.float().contiguous(), rgbs.float().contiguous(), deltas.contiguous(), ts.contiguous()
+    R = rays_a.shape[0]
+    g_o, g_d, g_c = torch.randn(R, device=dev), torch.zeros(R, device=dev), torch.randn(R, 3, device=dev)
+    g_ws = torch.zeros(sigmas.shape[0], device=dev)
+
+    def composite(v):
+        def run():
+            total, opacity, depth, rgb, ws = v.composite_train_fw(sigmas, rgbs, deltas, ts, rays_a, 1e-4)
+            return v.composite_train_bw(g_o, g_d, g_c, g_ws, sigmas, rgbs, ws, deltas, ts, rays_a, opacity, depth, rgb, 1e-4)
+        return run
+
+    t_ref_c, _ = _timed(composite(ref), iters)
+    t_our_c, _ = _timed(composite(ours), iters)
+    out["train_geometry_ms"] = {"reference": t_ref_geo, "ours": t_our_geo, "speedup": t_ref_geo / t_our_geo}
+    out["train_compositing_ms"] = {"reference": t_ref_c, "ours": t_our_c, "speedup": t_ref_c / t_our_c}
+    out["samples"] = int(sigmas.shape[0])
+    out["field"] = "no reference timing: tiny-cuda-nn (hash grid + fully fused MLP) is an un-vendored dependency absent from this image"
+    return out
+
+
+def test_frame_stages(model, rays_o, rays_d, T_threshold=1e-4):
+    """Device ms spent inside raymarching_test + composite_test_fw over one test frame's loop (models/rendering.py:189-236,
+    the eager loop of ar_nerf_b200.rendering with the `vren` module swapped), reference extension vs libarnerf.so."""
+    import torch
+
+    from ar_nerf_b200 import rendering
+    from ar_nerf_b200 import vren as ours
+    ref = load()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/vren*.so not built"}
+
+    class Swap:
+        """`vren` stand-in for rendering.py: the two test-loop functions come from `v` and are timed, the rest is libarnerf's."""
+
+        def __init__(self, v):
+            self.v, self.ev = v, []
+
+        def __getattr__(self, name):
+            return getattr(ours, name)
+
+        def _t(self, fn, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = fn(*a); e1.record()
+            self.ev.append((e0, e1))
+            return r
+
+        def raymarching_test(self, *a):
+            return self._t(self.v.raymarching_test, *a)
+
+        def composite_test_fw(self, *a):
+            return self._t(self.v.composite_test_fw, *a)
+
+    res = {}
+    saved = rendering.vren
+    try:
+        for name, v in (("reference", ref), ("ours", ours)):
+            for rep in range(2):  # the second pass is the timed one
+                sw = Swap(v)
+                rendering.vren = sw
+                out = rendering.render(model, rays_o, rays_d, test_time=True, T_threshold=T_threshold, eager_test_loop=True)
+                torch.cuda.synchronize()
+            res[name] = {"ms": sum(a.elapsed_time(b) for a, b in sw.ev), "calls": len(sw.ev), "rgb": out["rgb"]}
+    finally:
+        rendering.vren = saved
+    same = bool(torch.equal(res["reference"]["rgb"], res["ours"]["rgb"]))
+    return {"test_march_composite_ms": {"reference": res["reference"]["ms"], "ours": res["ours"]["ms"],
+                                        "speedup": res["reference"]["ms"] / max(res["ours"]["ms"], 1e-9)},
+            "calls": res["ours"]["calls"], "pixels_identical": same}

@@ -835,3 +835,51 @@ def test_density_grid_update_bits(w1):
     assert torch.equal(n_xyz, v.grid_cell_positions(v.morton3D_invert(n_idx.int()), rnd, G, 0.5))  # same bits as the torch expression
     model.update_density_grid(5.912, warmup=False)
     assert model.density_grid.shape == (1, 128 ** 3)
+
+
+# ------------------------------------------------------------------------------------------------ mark_invisible_cells
+@pytest.mark.parametrize("case", [0, 1])
+def test_mark_invisible_cells(case, vren):
+    """arn_mark_invisible_cells (models/networks.py:209-250): bit-identical with the oracle (same operation
+    order), identical with the unmodified reference's output (tests/golden/mark_invisible_ref.npz) on every cell whose
+    decisions are not borderline, and NGP.mark_invisible_cells -- which derives the world-to-camera matrices with torch
+    -- against the same golden vectors."""
+    from test_oracle_golden import BORDERLINE, invisible_case
+    from ar_nerf_b200.networks import NGP
+    G, scale, C, K, poses, wh, idx, coords, gd, gc = invisible_case(case)
+    w2c = T(oracle.world_to_camera(poses))
+    margins = []
+    for c in range(C):
+        s = min(2.0 ** (c - 1), scale)
+        dens = torch.full((G ** 3,), 7.0, device=dev()); cnt = torch.full((G ** 3,), 7.0, device=dev())
+        vren.mark_invisible_cells(T(coords), T(idx), G, s, w2c, K, wh, 0.01, dens, cnt)
+        od, oc, margin = oracle.mark_invisible_cells(coords, idx, G, s, poses, K, wh, return_margin=True)
+        assert np.array_equal(bits(N(dens)), bits(od)) and np.array_equal(bits(N(cnt)), bits(oc)), c
+        clear = margin > BORDERLINE
+        assert np.array_equal(N(dens)[clear].astype(np.int8), gd[c][clear])
+        assert np.array_equal(np.round(N(cnt)[clear] * len(poses)).astype(np.uint8), gc[c][clear])
+        margins.append(margin)
+    # the module method (same constructor / attributes as the reference's NGP), grid_size overridden to the golden case's
+    m = NGP(scale).to(dev())
+    m.grid_size = G
+    m.register_buffer('density_grid', torch.zeros(C, G ** 3, device=dev()))
+    m.register_buffer('grid_coords', T(coords))
+    assert m.cascades == C
+    m.mark_invisible_cells(T(K), T(poses), wh)
+    clear = np.stack(margins) > BORDERLINE
+    assert np.array_equal(N(m.density_grid)[clear].astype(np.int8), gd[clear])
+    assert np.array_equal(np.round(N(m.count_grid)[clear] * len(poses)).astype(np.uint8), gc[clear])
+    assert (~clear).sum() <= 1e-3 * clear.size
+
+
+def test_mark_invisible_cells_full_size(w1, vren):
+    """128^3 cells (the size train.py:79-82 runs it at) x 48 cameras against the oracle, bit for bit."""
+    from ar_nerf_b200.networks import NGP
+    m = NGP(0.5).to(dev())
+    m.init_density_grid()
+    K, poses = w1.K, w1.poses[:48]
+    (idx, coords), = m.get_all_cells()
+    dens = torch.empty(128 ** 3, device=dev()); cnt = torch.empty(128 ** 3, device=dev())
+    vren.mark_invisible_cells(coords, idx, 128, 0.25, T(oracle.world_to_camera(poses.numpy())), K, (800, 800), 0.01, dens, cnt)
+    od, oc = oracle.mark_invisible_cells(N(coords), N(idx), 128, 0.25, poses.numpy(), K.numpy(), (800, 800))
+    assert np.array_equal(bits(N(dens)), bits(od)) and np.array_equal(bits(N(cnt)), bits(oc))

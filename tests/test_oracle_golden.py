@@ -105,3 +105,38 @@ def test_distortion(kind):
     np.testing.assert_allclose(loss, g["dist_loss"], rtol=1e-3, atol=1e-6)
     dws = oracle.distortion_loss_bw(g["dist_gl"], g["dist_wsi"], g["dist_wtsi"], g["dist_ws"], g["train_deltas"], g["train_ts"], rays_a)
     assert np.abs(dws - g["dist_dws"]).max() <= 1e-4 * np.abs(g["dist_dws"]).max()
+
+
+# ------------------------------------------------------------------------------------------------ mark_invisible_cells
+def invisible_case(case):
+    """Inputs of golden case `case` (tests/golden/make_golden_invisible.py) + the golden outputs of the unmodified reference."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_invisible import invisible_inputs, morton_cells
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mark_invisible_ref.npz"))
+    G, scale, C, K, poses, wh = invisible_inputs(case)
+    idx, coords = morton_cells(G)
+    return G, scale, C, K.numpy(), poses.numpy(), wh, idx.numpy(), coords.numpy(), g[f"density{case}"], g[f"count{case}"]
+
+
+BORDERLINE = 1e-5  # a decision closer than this (relative) to its threshold may flip under another float32 summation order
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_mark_invisible_cells_oracle_vs_reference(case):
+    """oracle.mark_invisible_cells (fixed summation order) against models/networks.py:209-250 run unmodified (MKL matmuls):
+    identical on every cell whose decisions are not borderline, and borderline cells are rare."""
+    G, scale, C, K, poses, wh, idx, coords, gd, gc = invisible_case(case)
+    n_border = 0
+    for c in range(C):
+        s = min(2.0 ** (c - 1), scale)
+        d, cnt, margin = oracle.mark_invisible_cells(coords, idx, G, s, poses, K, wh, return_margin=True)
+        clear = margin > BORDERLINE
+        n_border += int((~clear).sum())
+        assert np.array_equal(d[clear].astype(np.int8), gd[c][clear])
+        assert np.array_equal(np.round(cnt[clear] * len(poses)).astype(np.uint8), gc[c][clear])
+        assert np.array_equal(cnt, (np.round(cnt * len(poses)) / np.float32(len(poses))).astype(np.float32))
+        # borderline cells: the covered count may move by the number of cameras that are borderline for that cell
+        assert np.abs(np.round(cnt * len(poses)).astype(int) - gc[c].astype(int)).max() <= 2
+    assert n_border <= 1e-3 * C * G ** 3
+    assert (gd == 0).any() and (gd == -1).any()
