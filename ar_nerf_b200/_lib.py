@@ -76,6 +76,7 @@ SIGNATURES = {
     "arn_p2p_barrier": [C.POINTER(C.c_void_p), P, I, I, I, C.c_uint64, P],
     "arn_p2p_adam_exchange": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), I, L, L, P, P, P, F, F, F, F, I, F, P],
     "arn_gather_rays": [P, P, I, P, P, L, P, L, P, P, P],
+    "arn_gather_batch": [P, P, I, P, P, L, P, L, P, L, I, P, P, P, P],
     "arn_grid_cell_positions": [P, P, L, I, F, P, P],
     "arn_grid_sample_cells": [P, F, I, F, P, P, L, P, P, P, P, P],
     "arn_density_grid_update": [P, P, P, F, F, L, P, P, P],

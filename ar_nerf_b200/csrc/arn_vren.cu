@@ -100,10 +100,16 @@ __global__ void __launch_bounds__(256) aabb_near_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) gather_rays_kernel(const float* __restrict__ directions, const float* __restrict__ poses,
                                                           const int64_t* __restrict__ img_idxs, int64_t img_single,
                                                           const int64_t* __restrict__ pix_idxs, int64_t n, int width, float fx, float fy, float cx,
-                                                          float cy, float* __restrict__ rays_o, float* __restrict__ rays_d) {
+                                                          float cy, float* __restrict__ rays_o, float* __restrict__ rays_d,
+                                                          const float* __restrict__ images, int64_t pixels_per_image, int channels,
+                                                          float* __restrict__ pixels_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t pix = pix_idxs[i];
+    if (images) {  // rays[img_idxs, pix_idxs] of datasets/base.py:32: the pixel's colour (+ exposure) row
+        const float* src = images + ((img_idxs ? img_idxs[i] : img_single) * pixels_per_image + pix) * channels;
+        for (int c = 0; c < channels; c++) pixels_out[i * channels + c] = src[c];
+    }
     float d[3];
     if (directions) { d[0] = directions[3 * pix]; d[1] = directions[3 * pix + 1]; d[2] = directions[3 * pix + 2]; }
     else {
@@ -997,7 +1003,7 @@ __global__ void __launch_bounds__(256) alive_scatter_kernel(const int64_t* __res
 // still be reading state_in).  Every kernel is a grid-stride loop over the device-side count (the host sizes the grids
 // from an upper bound of n_alive).  Producers of per-ray counts also write the sum of every chunk of 128 rays (`partial`),
 // from which the scan kernels get their offset without re-reading all earlier counts.
-constexpr int kStN = 0, kStS = 1, kStDone = 2, kStActive = 3, kStIters = 4;
+constexpr int kStN = 0, kStS = 1, kStDone = 2, kStActive = 3, kStIters = 4, kStLive = 5;  // kStLive: iterations that started active
 
 __device__ __forceinline__ int block_sum_128(int v, int* sm4) {  // sum over a 128-thread group (4 warps), result in every thread
 #pragma unroll
@@ -1372,6 +1378,7 @@ __global__ void __launch_bounds__(1024) alive_compact_dyn_kernel(const int64_t* 
             } else n_next = 0;
             state_out[kStN] = (int32_t)n_next; state_out[kStS] = S; state_out[kStDone] = done; state_out[kStActive] = active;
             state_out[kStIters] = state_in[kStIters] + 1;
+            state_out[kStLive] = state_in[kStLive] + (state_in[kStActive] ? 1 : 0);
         }
     }
 }
@@ -1521,8 +1528,23 @@ extern "C" ARN_API int arn_gather_rays(const float* directions, const float* K_h
     float fx = 1.f, fy = 1.f, cx = 0.f, cy = 0.f;
     if (!directions) { fx = K_host[0]; fy = K_host[4]; cx = K_host[2]; cy = K_host[5]; }
     ARN_LAUNCH("gather_rays_kernel", (cudaStream_t)stream, gather_rays_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        directions, poses, img_idxs, img_single, pix_idxs, n, width, fx, fy, cx, cy, rays_o, rays_d));
+        directions, poses, img_idxs, img_single, pix_idxs, n, width, fx, fy, cx, cy, rays_o, rays_d, nullptr, 0, 0, nullptr));
     return check_launch("gather_rays");
+}
+
+extern "C" ARN_API int arn_gather_batch(const float* directions, const float* K_host, int width, const float* poses, const int64_t* img_idxs,
+                                        int64_t img_single, const int64_t* pix_idxs, int64_t n, const float* images, int64_t pixels_per_image,
+                                        int channels, float* rays_o, float* rays_d, float* pixels_out, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(poses && pix_idxs && rays_o && rays_d && images && pixels_out, "null pointer");
+    ARN_REQUIRE(directions || (K_host && width > 0), "either directions or K_host + width");
+    ARN_REQUIRE(pixels_per_image > 0 && channels >= 1 && channels <= 8, "bad image layout");
+    float fx = 1.f, fy = 1.f, cx = 0.f, cy = 0.f;
+    if (!directions) { fx = K_host[0]; fy = K_host[4]; cx = K_host[2]; cy = K_host[5]; }
+    ARN_LAUNCH("gather_rays_kernel", (cudaStream_t)stream, gather_rays_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        directions, poses, img_idxs, img_single, pix_idxs, n, width, fx, fy, cx, cy, rays_o, rays_d, images, pixels_per_image, channels, pixels_out));
+    return check_launch("gather_batch");
 }
 
 extern "C" ARN_API int arn_grid_cell_positions(const int32_t* coords, const float* rnd, int64_t n_cells, int grid_size, float s, float* xyzs,
@@ -1865,7 +1887,7 @@ extern "C" ARN_API int arn_render_test_step(const arn_test_iter_t* c, const int3
     const int64_t nu = n_upper > 0 ? n_upper : 1;
     const int64_t samples_upper = nu * min_samples > c->n_alive ? nu * min_samples : c->n_alive;  // n * S <= max(N_rays, n * min_samples)
     const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
-    const int g128 = (int)min((int64_t)148 * 64, (nu + 127) / 128), g1024 = (int)min((int64_t)148 * 8, (nu + 1023) / 1024);
+    const int g128 = (int)min((int64_t)148 * 16, (nu + 127) / 128), g1024 = (int)min((int64_t)148 * 4, (nu + 1023) / 1024);  // grid-stride: full residency is enough
     // few rays, many samples each (N_samples >= 9 once n_alive <= N_rays / 9): one warp per ray
     const bool warp_march = tunable(kTunMarchWarp) != 0 && nu <= 65536 && nu * 9 <= c->n_alive;
     if (warp_march) {
@@ -1930,7 +1952,7 @@ extern "C" ARN_API int arn_render_test_step_pre(const arn_test_iter_t* c, const 
     const int64_t nu = n_upper > 0 ? n_upper : 1;
     const int64_t samples_upper = nu * min_samples > c->n_alive ? nu * min_samples : c->n_alive;
     const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
-    const int g128 = (int)min((int64_t)148 * 64, (nu + 127) / 128), g1024 = (int)min((int64_t)148 * 8, (nu + 1023) / 1024);
+    const int g128 = (int)min((int64_t)148 * 16, (nu + 127) / 128), g1024 = (int)min((int64_t)148 * 4, (nu + 1023) / 1024);  // grid-stride: full residency is enough
     ARN_LAUNCH("neff_test_pre_kernel", st, neff_test_pre_kernel<<<g128, 128, 0, st>>>(c->alive, state_in, totals, cursor, c->n_eff, partial));
     if (int e = check_launch("neff_test_pre")) return e;
     ARN_LAUNCH("scan_test_dyn_kernel", st, scan_test_dyn_kernel<<<g1024, 1024, 0, st>>>(c->n_eff, partial, state_in, c->rays_a, c->counts));

@@ -86,6 +86,12 @@ _TEST_WS = {}
 _STATE_RING = 4   # read-back slots of the device-driven test loop
 _STATE_LAG = 2    # the host looks at the control state of the iteration queued this many calls earlier
 _PREMARCH_MAX_BYTES = 12 << 30  # largest per-frame sample table (stride x N_rays floats) the fused test loop allocates
+_GRAPH_ITERS = 8  # loop iterations per CUDA-graph replay (even: the ping-pong buffers are back in place after a replay)
+
+
+def release_test_workspace():
+    """Frees the buffers the fused test loop keeps between frames (sample table, per-ray state, captured graphs)."""
+    _TEST_WS.clear()
 
 
 def _test_workspace(R, min_samples, device):
@@ -107,10 +113,107 @@ def _test_workspace(R, min_samples, device):
                   state=torch.zeros(2, 8, dtype=torch.int32, device=device), partial=torch.empty((R + 127) // 128, dtype=torch.int32, device=device),
                   state_host=torch.zeros(_STATE_RING, 8, dtype=torch.int32).pin_memory(),
                   state_init=torch.zeros(8, dtype=torch.int32).pin_memory(),
-                  state_ev=[torch.cuda.Event() for _ in range(_STATE_RING)])
+                  state_ev=[torch.cuda.Event() for _ in range(_STATE_RING)],
+                  # graph-driven loop: the frame's inputs / outputs live at fixed addresses
+                  g_rays_o=f(R, 3), g_rays_d=f(R, 3), g_hits=f(R, 2), g_opacity=f(R), g_depth=f(R), g_rgb=f(R, 3),
+                  g_arange=torch.arange(R, dtype=torch.int64, device=device), g_state0=torch.zeros(8, dtype=torch.int32, device=device),
+                  graphs={}, replays_hint=1)
         _TEST_WS.clear()  # one frame size at a time
         _TEST_WS[key] = ws
     return ws
+
+
+def _premarch_table(w, stride, N_rays, device):
+    pm = w.get('premarch')
+    if pm is None or pm[0].numel() < stride * N_rays:
+        try:
+            pm = (torch.empty(stride * N_rays, dtype=torch.float32, device=device), torch.empty(N_rays, dtype=torch.int32, device=device),
+                  torch.empty(N_rays, dtype=torch.int32, device=device))
+        except torch.cuda.OutOfMemoryError:  # no room for the sample table next to whatever else lives on the GPU: march per iteration
+            pm = None
+        w['premarch'] = pm
+        w['graphs'].clear()  # captured graphs hold the old table's address
+    return pm
+
+
+def _test_cfg(model, w, rays_o, rays_d, hits_t2, opacity, depth, rgb, exp_step_factor, T_threshold):
+    """arn_test_iter_t over the given frame buffers (alive lists / n_alive are filled in per call)."""
+    import ctypes as C
+    from ._lib import FieldWs, TestIterCfg, ptr
+    st = model.field_state
+    p16x = st.cache_xyz.get(model.xyz_encoder.params); p16c = st.cache_rgb.get(model.rgb_net.params)
+    cast = lambda a: C.cast(a, C.c_void_p)
+    return TestIterCfg(
+        ptr(rays_o), ptr(rays_d), ptr(hits_t2), None, 0,
+        ptr(model.density_bitfield), model.cascades, model.grid_size, float(model.scale), float(exp_step_factor), 1, MAX_SAMPLES,
+        float(T_threshold),
+        cast(st.mn), cast(st.mx), st.geometry.c_levels, ptr(p16x), ptr(p16c), st.rgb_act,
+        w['cap'], ptr(w['deltas']), ptr(w['ts']), ptr(w['n_eff']), ptr(w['rays_a']), w['counts'].data_ptr(), w['counts'].data_ptr() + 8,
+        ptr(w['xyzs']), ptr(w['dirs']), ptr(w['sigmas']), ptr(w['rgbs']),
+        FieldWs(ptr(w['feat']), None, None, None, None, None, ptr(w['wimg'])),
+        ptr(opacity), ptr(depth), ptr(rgb), None, ptr(w['total'])), (p16x, p16c)
+
+
+def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride):
+    """The device-driven loop replayed from CUDA graphs: ONE graph launch covers the frame's prologue (march of every ray,
+    state / alive-list / output initialisation) plus the first _GRAPH_ITERS iterations, every further launch _GRAPH_ITERS more
+    (an iteration behind the loop's end is a handful of empty kernels).  The frame's inputs are copied to fixed addresses;
+    the host reads the control state once per batch of replays -- as many as the previous frame of this size needed."""
+    import ctypes as C
+    from ._lib import call, ptr, stream
+    N_rays, device = rays_o.shape[0], rays_o.device
+    ts_all, totals, cursor = w['premarch']
+    st = model.field_state
+    key = (ptr(model.density_bitfield), model.cascades, model.grid_size, float(model.scale), float(exp_step_factor), float(T_threshold), int(max_samples),
+           int(min_samples), int(stride), st.cache_xyz.get(model.xyz_encoder.params).data_ptr(), st.cache_rgb.get(model.rgb_net.params).data_ptr(),
+           tuple(st.mn), tuple(st.mx), id(st.geometry), st.rgb_act, ts_all.data_ptr())
+    graphs = w['graphs'].get(key)
+    w['g_rays_o'].copy_(rays_o); w['g_rays_d'].copy_(rays_d); w['g_hits'].copy_(hits_t2)
+    if graphs is None:
+        cfg, keep = _test_cfg(model, w, w['g_rays_o'], w['g_rays_d'], w['g_hits'], w['g_opacity'], w['g_depth'], w['g_rgb'], exp_step_factor, T_threshold)
+        cfg.n_alive = N_rays
+        state_ptr = (w['state'][0].data_ptr(), w['state'][1].data_ptr())
+        S0 = max(1, min_samples)
+        w['g_state0'].copy_(torch.tensor([N_rays, S0, S0, 1 if max_samples > 0 else 0, 0, 0, 0, 0], dtype=torch.int32))
+
+        def prologue():
+            call("arn_march_test_all", ptr(w['g_rays_o']), ptr(w['g_rays_d']), ptr(w['g_hits']), N_rays, ptr(model.density_bitfield), model.cascades,
+                 model.grid_size, float(model.scale), float(exp_step_factor), MAX_SAMPLES, stride, ptr(ts_all), ptr(totals), ptr(cursor), stream())
+            w['alive'][0].copy_(w['g_arange']); w['state'][0].copy_(w['g_state0'])
+            w['total'].zero_(); w['g_opacity'].zero_(); w['g_depth'].zero_(); w['g_rgb'].zero_()
+
+        def iterations():
+            for it in range(_GRAPH_ITERS):
+                cfg.alive, cfg.alive_out = w['alive'][it & 1].data_ptr(), w['alive'][(it & 1) ^ 1].data_ptr()
+                call("arn_render_test_step_pre", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(w['partial']), ptr(ts_all), ptr(totals),
+                     ptr(cursor), min_samples, int(max_samples), N_rays, stream())
+
+        # one eager pass first: module loading and the kernels' one-time attribute calls are not capturable
+        prologue(); iterations()
+        torch.cuda.current_stream().synchronize()
+        first, more = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(first, capture_error_mode="thread_local"):
+            prologue(); iterations()
+        with torch.cuda.graph(more, capture_error_mode="thread_local"):
+            iterations()
+        graphs = (first, more, keep)
+        w['graphs'].clear()  # one configuration at a time
+        w['graphs'][key] = graphs
+    first, more, _ = graphs
+    first.replay()
+    queued, want = 1, max(1, w['replays_hint'])
+    while True:
+        while queued < want:
+            more.replay(); queued += 1
+        w['state_host'][0].copy_(w['state'][0], non_blocking=True)   # _GRAPH_ITERS is even: the last state written is state[0]
+        w['state_ev'][0].record(torch.cuda.current_stream())
+        w['state_ev'][0].synchronize()
+        active, live_iters = int(w['state_host'][0][3]), int(w['state_host'][0][5])
+        if not active or queued * _GRAPH_ITERS > int(max_samples):  # every live iteration requests at least one sample
+            break
+        want = queued + 1
+    w['replays_hint'] = max(1, -(-live_iters // _GRAPH_ITERS))
+    return w['g_opacity'].clone(), w['g_depth'].clone(), w['g_rgb'].clone(), w['total'][0].clone()
 
 
 @torch.no_grad()
@@ -120,56 +223,40 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
     drive the reference's schedule.  Same schedule, same per-ray arithmetic, same results."""
     import ctypes as C
     from . import _lib
-    from ._lib import FieldWs, TestIterCfg, call, ptr, stream
+    from ._lib import call, ptr, stream
     exp_step_factor = kwargs.get('exp_step_factor', 0.)
     T_threshold = kwargs.get('T_threshold', 1e-4)
     max_samples = kwargs.get('max_samples', MAX_SAMPLES)
     N_rays, device = len(rays_o), rays_o.device
-    opacity = torch.zeros(N_rays, device=device)
-    depth = torch.zeros(N_rays, device=device)
-    rgb = torch.zeros(N_rays, 3, device=device)
     min_samples = 1 if exp_step_factor == 0 else 4
     w = _test_workspace(N_rays, min_samples, device)
-    st = model.field_state
     model.host_box()
-    p16x = st.cache_xyz.get(model.xyz_encoder.params); p16c = st.cache_rgb.get(model.rgb_net.params)
     hits_t2 = hits_t[:, 0]
     if not hits_t2.is_contiguous():
         raise RuntimeError("hits_t must be contiguous")
     rays_o = rays_o.contiguous().float(); rays_d = rays_d.contiguous().float()
+    s_ = stream()
+    host_driven = kwargs.get('host_driven_test_loop', False)
+    # The frame's samples are marched once, in front of the loop (arn_march_test_all), when their table fits: the loop never
+    # asks a ray for more than max_samples + 63 samples.  Otherwise the iterations march (far-clamped rays).
+    stride = int(max(1, max_samples)) + 64
+    premarch = (not host_driven and kwargs.get('premarch_test_loop', True) and max_samples > 0 and stride * N_rays * 4 <= _PREMARCH_MAX_BYTES
+                and _premarch_table(w, stride, N_rays, device) is not None)
+    if premarch and kwargs.get('graph_test_loop', True) and not torch.cuda.is_current_stream_capturing():
+        return _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride)
+    opacity = torch.zeros(N_rays, device=device)
+    depth = torch.zeros(N_rays, device=device)
+    rgb = torch.zeros(N_rays, 3, device=device)
     cur = 0
     torch.arange(N_rays, out=w['alive'][0])
     w['total'].zero_()
-    cast = lambda a: C.cast(a, C.c_void_p)
-    cfg = TestIterCfg(
-        ptr(rays_o), ptr(rays_d), ptr(hits_t2), None, 0,
-        ptr(model.density_bitfield), model.cascades, model.grid_size, float(model.scale), float(exp_step_factor), 1, MAX_SAMPLES,
-        float(T_threshold),
-        cast(st.mn), cast(st.mx), st.geometry.c_levels, ptr(p16x), ptr(p16c), st.rgb_act,
-        w['cap'], ptr(w['deltas']), ptr(w['ts']), ptr(w['n_eff']), ptr(w['rays_a']), w['counts'].data_ptr(), w['counts'].data_ptr() + 8,
-        ptr(w['xyzs']), ptr(w['dirs']), ptr(w['sigmas']), ptr(w['rgbs']),
-        FieldWs(ptr(w['feat']), None, None, None, None, None, ptr(w['wimg'])),
-        ptr(opacity), ptr(depth), ptr(rgb), None, ptr(w['total']))
-    s_ = stream()
-    if not kwargs.get('host_driven_test_loop', False):
+    cfg, _keep = _test_cfg(model, w, rays_o, rays_d, hits_t2, opacity, depth, rgb, exp_step_factor, T_threshold)
+    if not host_driven:
         # Loop control on the device: iterations are queued without waiting for their counts; the control state comes back
         # through pinned memory and is looked at _STATE_LAG iterations late (an iteration queued after the loop has ended
         # is a handful of empty launches).  n_alive never grows, so a stale value still bounds the grids.
-        # The frame's samples are marched once, in front of the loop (arn_march_test_all), when their table fits: the loop
-        # never asks a ray for more than max_samples + 63 samples.  Otherwise the iterations march (far-clamped rays).
-        stride = int(max(1, min(max_samples, MAX_SAMPLES))) + 64
-        premarch = kwargs.get('premarch_test_loop', True) and max_samples > 0 and stride * N_rays * 4 <= _PREMARCH_MAX_BYTES
         if premarch:
-            pm = w.get('premarch')
-            if pm is None or pm[0].numel() < stride * N_rays:
-                try:
-                    pm = (torch.empty(stride * N_rays, dtype=torch.float32, device=device), torch.empty(N_rays, dtype=torch.int32, device=device),
-                          torch.empty(N_rays, dtype=torch.int32, device=device))
-                except torch.cuda.OutOfMemoryError:  # no room for the sample table next to whatever else lives on the GPU: march per iteration
-                    pm, premarch = None, False
-                w['premarch'] = pm
-        if premarch:
-            ts_all, totals, cursor = pm
+            ts_all, totals, cursor = w['premarch']
             call("arn_march_test_all", ptr(rays_o), ptr(rays_d), ptr(hits_t2), N_rays, ptr(model.density_bitfield), model.cascades,
                  model.grid_size, float(model.scale), float(exp_step_factor), MAX_SAMPLES, stride, ptr(ts_all), ptr(totals), ptr(cursor), s_)
         elif kwargs.get('far_clamp', True):
@@ -228,7 +315,9 @@ def __render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     N_rays = len(rays_o)
     device = rays_o.device
     fused = (getattr(model, 'field_impl', '') == '' and model.rgb_act == 'Sigmoid' and not model.use_raw_HDR
-             and 'val_batch_size' not in kwargs and not kwargs.get('eager_test_loop', False) and N_rays > 0)
+             and not kwargs.get('eager_test_loop', False) and N_rays > 0)
+    # val_batch_size (rendering.py:209-215) only bounds the reference's per-call field batch: the field is a per-sample
+    # function, so chunking cannot change a result; the fused loop's workspace holds a whole iteration and ignores it
     if fused:
         opacity, depth, rgb, total_samples = _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs)
         return _finish_test(results, opacity, depth, rgb, total_samples, rays_d, **kwargs)

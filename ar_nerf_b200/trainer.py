@@ -370,3 +370,61 @@ class NGPTrainer:
         self.opt.step(inv_grad_scale=1.0 / (self.grad_scale * self.world))
         self.global_step += 1
         return loss.detach(), results
+
+
+class DeviceDataset:
+    """The training set resident in HBM: poses (n_images,3,4), images (n_images, H*W, C) f32 -- the reference's `dataset.rays`,
+    which datasets/base.py:32 indexes on the HOST -- and the pixel directions (H*W,3) (`self.directions`, train.py:78)."""
+
+    def __init__(self, poses, images, directions, device):
+        self.poses = poses.to(device).float().contiguous()
+        self.images = images.to(device).float().contiguous()
+        self.directions = directions.to(device).float().contiguous()
+        self.device = device
+
+
+class BatchFeeder:
+    """Host-drawn index batches -> device batches, two steps ahead of the training step.
+
+    The reference's dataset draws `img_idxs` / `pix_idxs` on the host (datasets/base.py:24-30), gathers the pixels on the host
+    and ships them; poses / directions are gathered on the device (train.py:121-126).  Here one step's host -> device traffic
+    is the two index vectors (16 bytes per ray, ONE pinned block, ONE cudaMemcpyAsync on a copy stream) and arn_gather_batch
+    produces (rays_o, rays_d, rgb) on that same stream into one of `depth` slots; events order slot reuse against the step
+    that consumed the slot.  The trainer recognises a batch marched ahead by tensor identity, so get() returns the slot's
+    own tensors."""
+
+    def __init__(self, dataset, batch_size, depth=3):
+        dev = dataset.device
+        self.ds, self.B, self.depth = dataset, batch_size, depth
+        ch = dataset.images.shape[2]
+        self.idx = [torch.empty(2, batch_size, dtype=torch.int64, device=dev) for _ in range(depth)]
+        self.slots = [(torch.empty(batch_size, 3, device=dev), torch.empty(batch_size, 3, device=dev), torch.empty(batch_size, ch, device=dev))
+                      for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.landed, self.consumed = {}, {}
+        self.h2d_bytes_per_batch = 2 * batch_size * 8
+
+    def stage(self, i, idx_pinned):
+        """Queue batch i: idx_pinned (2, B) int64 pinned = (img_idxs, pix_idxs).  No-op if already staged."""
+        from . import vren
+        if i in self.landed:
+            return
+        k = i % self.depth
+        with torch.cuda.stream(self.copy_stream):
+            if i - self.depth in self.consumed:
+                self.copy_stream.wait_event(self.consumed[i - self.depth])  # the step that read this slot last has been queued and ordered
+            self.idx[k].copy_(idx_pinned, non_blocking=True)
+            vren.gather_batch(self.ds.poses, self.idx[k][0], self.idx[k][1], self.ds.images, directions=self.ds.directions, out=self.slots[k])
+            ev = torch.cuda.Event(); ev.record(self.copy_stream)
+            self.landed[i] = ev
+
+    def get(self, i):
+        """(rays_o, rays_d, rgb) of batch i; the current stream waits for its copy + gather."""
+        torch.cuda.current_stream().wait_event(self.landed[i])
+        return self.slots[i % self.depth]
+
+    def done(self, i):
+        """Call after the step that consumes batch i has been queued on the current stream."""
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
+        self.consumed[i] = ev
+        self.consumed.pop(i - 2 * self.depth, None); self.landed.pop(i - self.depth, None)

@@ -121,6 +121,41 @@ def gather_rays(poses, img_idxs, pix_idxs, directions=None, K=None, width=None):
     return rays_o, rays_d
 
 
+def gather_batch(poses, img_idxs, pix_idxs, images, directions=None, K=None, width=None, out=None):
+    """gather_rays + the batch's pixels images[img_idxs, pix_idxs] (datasets/base.py:32) in one kernel.  images (n_images, H*W, C)
+    f32 on the device.  out = (rays_o, rays_d, pixels) preallocated tensors to fill (the training loop's batch slots)."""
+    import ctypes as C
+    check_tensor(poses, "poses", torch.float32, 3, 4); check_tensor(pix_idxs, "pix_idxs", torch.int64, 1)
+    check_tensor(images, "images", torch.float32, 3)
+    n, dev = pix_idxs.shape[0], poses.device
+    single = 0
+    if isinstance(img_idxs, torch.Tensor):
+        check_tensor(img_idxs, "img_idxs", torch.int64, 1)
+        if img_idxs.shape[0] != n:
+            raise RuntimeError("img_idxs and pix_idxs must have the same length")
+    else:
+        single, img_idxs = int(img_idxs), None
+    k_host = None
+    if directions is not None:
+        check_tensor(directions, "directions", torch.float32, 2, 3)
+    else:
+        if K is None or width is None:
+            raise RuntimeError("gather_batch needs either directions or K and width")
+        k_host = (C.c_float * 9)(*[float(v) for v in torch.as_tensor(K).reshape(-1).tolist()])
+    ch = images.shape[2]
+    if out is None:
+        out = (torch.empty(n, 3, dtype=torch.float32, device=dev), torch.empty(n, 3, dtype=torch.float32, device=dev),
+               torch.empty(n, ch, dtype=torch.float32, device=dev))
+    rays_o, rays_d, pixels = out
+    for t, nm, last in ((rays_o, "rays_o", 3), (rays_d, "rays_d", 3), (pixels, "pixels", ch)):
+        check_tensor(t, nm, torch.float32, 2, last)
+        if t.shape[0] != n:
+            raise RuntimeError(f"{nm} must have {n} rows")
+    call("arn_gather_batch", ptr(directions), k_host, int(width or 0), ptr(poses), ptr(img_idxs), single, ptr(pix_idxs), n,
+         ptr(images), images.shape[1], ch, ptr(rays_o), ptr(rays_d), ptr(pixels), stream())
+    return rays_o, rays_d, pixels
+
+
 def grid_cell_positions(coords, rnd, grid_size, s):
     """networks.py:263-267 in one kernel: (coords/(G-1)*2-1)*(s - s/G) + (rnd*2-1)*(s/G); coords (M,3) i32, rnd (M,3) f32."""
     check_tensor(coords, "coords", torch.int32, 2, 3); check_tensor(rnd, "rnd", torch.float32, 2, 3)

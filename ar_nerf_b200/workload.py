@@ -146,3 +146,67 @@ class Workload:
         model.init_density_grid()
         model.density_grid.copy_(self.density_grid.to(model.density_grid.device))
         model.density_bitfield.copy_(self.bitfield.to(model.density_bitfield.device))
+
+
+class ARFrame:
+    """W4 (BASELINE.json configs[4]): one AR insertion frame at 1920x1080 --
+      (1) SG shading of the inserted object's G-buffer (a 400x400 disc) under 32 SG lights with self shadow  [arn_sg_shade]
+      (2) NeRF background render with the object's colours as IM_bkg and its depth as mesh_depth_map      [render(test_time=True, T=1e-2, 100 samples)]
+      (3) the shadow the object casts on the scene, one factor per pixel of the frame                      [arn_sg_shadow_factor]
+    (insert/main.py:476-519 ssdf_shadow, :559-576, :620-684 render_insert_object) with synthetic stand-ins of the reference's
+    git-ignored tables at the sizes insert/main.py:107 uses (f_h 2048x1024, PCA volume 20^3 x 128 components, components
+    128 x 74 x 148).  The frame is sharded like the test render: rank r owns pixels r, r + world, ... (every rank gets the same
+    share of object, occupied and empty pixels); `render()` returns the rank's pixels, `gather()` the whole frame on rank 0."""
+    H, W, BB = 1080, 1920, 400
+
+    def __init__(self, model, workload, device, rank=0, world=1):
+        from .sg_shadow import SGShadow
+        H, W, BB = self.H, self.W, self.BB
+        self.model, self.rank, self.world, self.dev = model, rank, world, device
+        ro, rd = workload.test_frame(H, W)
+        g = torch.Generator(device="cpu").manual_seed(0)
+        self.sg = SGShadow.from_tensors(torch.randn(1, 128, 20, 20, 20, generator=g) * 0.15, torch.randn(128, 74, 148, generator=g) * 0.2,
+                                        torch.randn(1, 74, 148, generator=g) * 0.3, torch.rand(2048, 1024, generator=g), vol_range=2, device=device)
+        axis = torch.nn.functional.normalize(torch.randn(32, 3, generator=g), dim=-1)
+        self.lSGs = torch.cat([axis, 10 ** (torch.rand(32, 1, generator=g) * 3.5 - 0.5), torch.rand(32, 3, generator=g) * 2 + 0.05], 1).to(device)
+        # G-buffer of a sphere-ish object in a BB x BB box at the centre of the frame
+        ys, xs = torch.meshgrid(torch.arange(BB), torch.arange(BB), indexing="ij")
+        rr = ((xs - BB / 2) ** 2 + (ys - BB / 2) ** 2).float().sqrt() / (BB / 2)
+        inside = rr < 1
+        nz = (1 - rr.clamp(max=1) ** 2).sqrt()
+        normal_bb = torch.stack([(xs - BB / 2) / (BB / 2), -(ys - BB / 2) / (BB / 2), nz], -1).float()
+        albedo_bb = torch.rand(BB, BB, 3, generator=g)
+        y0, x0 = H // 2 - BB // 2, W // 2 - BB // 2
+        frame_mask = torch.zeros(H, W, dtype=torch.bool); frame_mask[y0:y0 + BB, x0:x0 + BB] = inside
+        frame_normal = torch.zeros(H, W, 3); frame_normal[y0:y0 + BB, x0:x0 + BB] = normal_bb
+        frame_albedo = torch.zeros(H, W, 3); frame_albedo[y0:y0 + BB, x0:x0 + BB] = albedo_bb
+        mine = slice(rank, H * W, world)
+        self.n_total = H * W
+        self.ro, self.rd = ro[mine].contiguous().to(device), rd[mine].contiguous().to(device)
+        self.sel = frame_mask.flatten()[mine].to(device)
+        self.n_obj = int(self.sel.sum())
+        self.normal = frame_normal.reshape(-1, 3)[mine][self.sel.cpu()].contiguous().to(device)
+        self.albedo = frame_albedo.reshape(-1, 3)[mine][self.sel.cpu()].contiguous().to(device)
+        self.metal = torch.full((self.n_obj, 1), 0.9, device=device); self.rough = torch.full((self.n_obj, 1), 0.2, device=device)
+        self.vdirs = torch.nn.functional.normalize(self.rd[self.sel], dim=-1)
+        self.depth_obj = torch.full((self.n_obj,), 1.2, device=device)
+        self.pts_obj = self.ro[self.sel] + self.vdirs * self.depth_obj[:, None]
+        self.model_pos, self.model_r = torch.tensor([0.0, 0.0, 0.0]), 0.3
+
+    def shade(self):
+        return self.sg.shade(self.model_r, self.pts_obj, self.model_pos, self.lSGs, None, self.albedo, self.metal, self.rough, self.normal, self.vdirs, True)
+
+    def render(self):
+        from .rendering import render
+        n = self.ro.shape[0]
+        cols = self.shade()                                                                                        # main.py:559-576
+        im_bkg = torch.zeros(n, 3, device=self.dev); im_bkg[self.sel] = cols
+        mesh_depth = torch.zeros(n, device=self.dev); mesh_depth[self.sel] = self.depth_obj
+        res = render(self.model, self.ro, self.rd, test_time=True, T_threshold=1e-2, max_samples=100, IM_bkg=im_bkg, mesh_depth_map=mesh_depth)  # main.py:646-650
+        pts = self.ro + self.rd * res["depth"][:, None]                                                            # main.py:493
+        smap = self.sg.calc_shadow_factor(self.model_r, pts, self.model_pos, self.lSGs)                             # main.py:501
+        return res["rgb"] * smap[:, None]
+
+    def gather(self, local):
+        from .sharding import gather_frame_interleaved
+        return gather_frame_interleaved(local, self.n_total, self.rank, self.world)

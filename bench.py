@@ -185,15 +185,20 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
+N_POSES = 100
+PEER_COPY_GBS = 770.0  # measured peer copy per direction on this pool (B200_PROFILING.md); the roof of the exchange kernel
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
     from ar_nerf_b200 import _lib
     from ar_nerf_b200.networks import NGP
     from ar_nerf_b200.rendering import render
-    from ar_nerf_b200.trainer import NGPTrainer
-    from ar_nerf_b200.workload import Workload
+    from ar_nerf_b200.trainer import BatchFeeder, DeviceDataset, NGPTrainer
+    from ar_nerf_b200.workload import ARFrame, Workload
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -205,11 +210,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    w = Workload("W1")
+    w = Workload("W1", n_poses=N_POSES)
     model = NGP(w.scale).to(dev)
     w.install(model)
     trainer = NGPTrainer(model)
-    # per-rank batches (weak scaling: every GPU marches its own 8192 rays); pinned host copies feed the e2e leg
+    # per-rank batches (weak scaling: every GPU marches its own 8192 rays)
     host = [w.train_batch(i, BATCH, seed=rank) for i in range(N_BATCHES)]
     resident = [[t.to(dev) for t in b[:3]] for b in host]
 
@@ -219,7 +224,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        """W warm-up steps are done by the caller; times `steps` calls of fn(i) with CUDA events, max over ranks."""
+        """Times `steps` calls of fn(i) with CUDA events on the launch stream (barrier + synchronize on both sides), max over ranks."""
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -233,52 +238,81 @@ def run_ours(args):
         return float(ms.item())
 
     samples_seen = []
+    counter = [0]  # batches consumed so far: every leg continues the same sequence
 
-    def step_resident(i):
+    def step_resident(_i=0, update_grid=True):
+        i = counter[0]; counter[0] += 1
         ro, rd, tgt = resident[i % N_BATCHES]
         nro, nrd, _ = resident[(i + 1) % N_BATCHES]  # the trainer marches the next batch while this one trains
-        _, res = trainer.train_step(ro, rd, tgt, next_rays=None if NO_PREFETCH else (nro, nrd))
+        _, res = trainer.train_step(ro, rd, tgt, update_grid=update_grid, next_rays=None if NO_PREFETCH else (nro, nrd))
         samples_seen.append(res["rm_samples"].clone())  # the trainer returns views into its workspace
 
-    # ---- e2e leg: host batches -> device through a copy stream, three device slots
-    # Every step copies ONE batch (rays_o | rays_d | target packed as one (3, R, 3) pinned block, one cudaMemcpyAsync) host ->
-    # device and brings the step's loss back to the host.  The input pipeline runs two batches ahead (the batch copied during
-    # step i is trained at step i+2 and marched during step i+1) on its own stream, so the copy overlaps the step's kernels
-    # instead of queueing between them; events order slot reuse (the slot of batch i+2 was last read by step i-1).
-    packed = [torch.stack([t.float() for t in b[:3]]).contiguous().pin_memory() for b in host]
-    slots = [torch.empty(3, BATCH, 3, device=dev) for _ in range(3)]
-    slot_views = [tuple(sl.unbind(0)) for sl in slots]  # the trainer recognises a prefetched batch by tensor identity
-    copy_stream = torch.cuda.Stream(device=dev)
-    landed = {}                                      # batch index -> event recorded on the copy stream
-    step_done = {}                                   # step index -> event recorded on the main stream
+    # untimed: the first steps carry one-time costs (CUDA module loading, allocator growth, the first occupancy refresh);
+    # at least two refresh intervals are run before the timed region whatever --warmup says, and reported as `warmup`
+    # ... and the first `warmup_steps` (256) optimisation steps refresh ALL 128^3 cells instead of the steady-state sample
+    # (networks.py:253-281, train.py:175-178): the timed region starts behind them, where 29 744 of the 30 000 steps of
+    # BASELINE.json's configs[1] run
+    U = trainer.update_interval
+    args.warmup = max(args.warmup, trainer.warmup_steps + 2 * U)
+    for _ in range(args.warmup):
+        step_resident()
 
-    def stage(i):
-        if i in landed:
-            return
-        with torch.cuda.stream(copy_stream):
-            if i - 3 in step_done:
-                copy_stream.wait_event(step_done[i - 3])
-            slots[i % 3].copy_(packed[i % N_BATCHES], non_blocking=True)
-            landed[i] = torch.cuda.Event()
-            landed[i].record(copy_stream)
+    # ---- the headline: K steps, timed in `windows` windows that start at rotating phases of the 16-step refresh cycle.  A
+    # K = 20 window holds one or two refreshes depending on where it starts (+-7 % on the number); 8 windows at phases
+    # 0, 2, .., 14 hold the long-run share.  K >= 128 averages by itself and is timed as one window.
+    windows = 8 if args.steps < 128 else 1
+    clocks = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count()
+    win_ms = []
+    for wi in range(windows):
+        while windows > 1 and trainer.global_step % U != (2 * wi) % U:
+            step_resident()                                  # untimed: walk to the window's phase
+        samples_seen.clear() if wi == 0 else None
+        n_w = _lib.launch_count()
+        win_ms.append(timed(step_resident, args.steps))
+        launches = _lib.launch_count() - n_w
+    clk = clocks.stop() if clocks else None
+    ms_total = sum(win_ms) / len(win_ms)
+    n_samples = float(torch.stack([s.float() for s in samples_seen]).mean().item())
+    value = world * BATCH * args.steps / (ms_total * 1e-3) / 1e6
+    # the same steps without the occupancy refresh, and the refresh alone
+    ms_norefresh = timed(lambda i: step_resident(update_grid=False), min(args.steps, 64)) / min(args.steps, 64)
 
+    def refresh_only(_i):
+        model.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=False)
+    refresh_only(0)
+    refresh_ms = timed(refresh_only, 8) / 8
+
+    if args.train_only:
+        if rank == 0:
+            print(json.dumps({"metric": "train_Mrays_per_s", "value": value, "ms_per_step": ms_total / args.steps, "train_only": True,
+                              "ms_per_step_no_refresh": ms_norefresh, "refresh_ms": refresh_ms, "window_ms_per_step": [m / args.steps for m in win_ms]}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- e2e leg: the dataset lives in HBM (poses, directions, the images' pixels); per step the host draws the batch's
+    # (img_idxs, pix_idxs) as the reference's dataset does (datasets/base.py:24-30), ONE pinned (2, R) int64 block goes host ->
+    # device on a copy stream two steps ahead, arn_gather_batch builds rays and colours there (trainer.BatchFeeder), and the
+    # step's loss comes back to pinned host memory every step (read by the host one step late, while the next step is already
+    # queued: every loss reaches the host inside the timed region, none is waited for with an empty GPU queue).
+    g_img = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ds = DeviceDataset(w.poses, torch.rand(N_POSES, w.directions.shape[0], 3, device=dev, generator=g_img), w.directions, dev)
+    feeder = BatchFeeder(ds, BATCH)
+    g_idx = torch.Generator().manual_seed(99 + rank)
+    idx_host = [torch.stack([torch.randint(N_POSES, (BATCH,), generator=g_idx), torch.randint(w.directions.shape[0], (BATCH,), generator=g_idx)]).pin_memory()
+                for _ in range(N_BATCHES)]
     loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     losses = []
 
     def step_e2e(i):
-        # The loss goes to pinned host memory with an asynchronous copy behind the step's kernels and is READ by the host one
-        # step later (while step i+1 is already queued): every step's loss reaches the host inside the timed region, none is
-        # waited for with an empty GPU queue -- what a training loop that logs its loss does.
-        stage(i); stage(i + 1)                       # no-ops in steady state
-        main = torch.cuda.current_stream()
-        main.wait_event(landed[i]); main.wait_event(landed[i + 1])
-        ro, rd, tgt = slot_views[i % 3]
-        nro, nrd, _ = slot_views[(i + 1) % 3]
+        feeder.stage(i, idx_host[i % N_BATCHES]); feeder.stage(i + 1, idx_host[(i + 1) % N_BATCHES])  # no-ops in steady state
+        ro, rd, tgt = feeder.get(i)
+        nro, nrd, _ = feeder.get(i + 1)
         loss, _ = trainer.train_step(ro, rd, tgt, next_rays=None if NO_PREFETCH else (nro, nrd))
-        step_done[i] = torch.cuda.Event(); step_done[i].record(main)
-        step_done.pop(i - 4, None); landed.pop(i - 1, None)
-        stage(i + 2)                                 # this step's host -> device copy
+        feeder.done(i)
+        feeder.stage(i + 2, idx_host[(i + 2) % N_BATCHES])  # this step's host -> device copy
         k = i & 1
         loss_pin[k:k + 1].copy_(loss.reshape(1), non_blocking=True)  # device -> host copy of the step's result
         loss_ev[k].record()
@@ -290,93 +324,110 @@ def run_ours(args):
         loss_ev[(n - 1) & 1].synchronize()
         losses.append(float(loss_pin[(n - 1) & 1]))
 
-    # untimed: the first steps carry one-time costs (CUDA module loading, allocator growth, the first occupancy refresh);
-    # at least two refresh intervals are run before the timed region whatever --warmup says, and reported as `warmup`
-    # ... and the first `warmup_steps` (256) optimisation steps refresh ALL 128^3 cells instead of the steady-state sample
-    # (networks.py:253-281, train.py:175-178): the timed region starts behind them, where 29 744 of the 30 000 steps of
-    # BASELINE.json's configs[1] run
-    args.warmup = max(args.warmup, trainer.warmup_steps + 2 * trainer.update_interval)
-    for i in range(args.warmup):
-        step_resident(i)
-    samples_seen.clear()
-    clocks = ClockSampler(local) if rank == 0 else None
-    n0 = _lib.launch_count()
-    ms_total = timed(step_resident, args.steps)
-    launches = _lib.launch_count() - n0
-    clk = clocks.stop() if clocks else None
-    n_samples = float(torch.stack([s.float() for s in samples_seen]).mean().item())
-    value = world * BATCH * args.steps / (ms_total * 1e-3) / 1e6
-
-    if args.train_only:
-        if rank == 0:
-            print(json.dumps({"metric": "train_Mrays_per_s", "value": value, "ms_per_step": ms_total / args.steps, "train_only": True}))
-        if world > 1:
-            dist.destroy_process_group()
-        return
     n_pre = 3
     for i in range(n_pre):
         step_e2e(i)
-    losses.clear()
+    e2e_ms, e2e_at = [], n_pre
+    for wi in range(windows):
+        while windows > 1 and trainer.global_step % U != (2 * wi) % U:
+            step_e2e(e2e_at); e2e_at += 1
+        losses.clear()
+        base = e2e_at
 
-    def e2e_region(k):                               # continues the batch sequence of the three untimed steps
-        step_e2e(n_pre + k)
-        if k == args.steps - 1:
-            finish_e2e(n_pre + args.steps)           # the last loss is read before the region's closing event
-    ms_e2e = timed(e2e_region, args.steps)
-    assert len(losses) >= args.steps and all(l == l for l in losses), "e2e: a step's loss did not reach the host"
+        def e2e_region(k, base=base):
+            step_e2e(base + k)
+            if k == args.steps - 1:
+                finish_e2e(base + args.steps)        # the last loss is read before the region's closing event
+        e2e_ms.append(timed(e2e_region, args.steps))
+        e2e_at += args.steps
+        assert len(losses) >= args.steps and all(l == l for l in losses), "e2e: a step's loss did not reach the host"
+    ms_e2e = sum(e2e_ms) / len(e2e_ms)
     e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3) / 1e6
 
-    # instrumented pass (not part of `value`): device time of every libarnerf.so kernel over the same steps
-    # (every kernel alone on one stream: with the next batch's march running beside them on the side stream, the events would
-    # time the co-running pair, not the kernel)
-    def step_serial(i):
+    # ---- instrumented passes (not part of `value`): device time of every libarnerf.so kernel, every kernel alone on one
+    # stream (with the next batch's march running beside them the events would time the co-running pair).  Training steps
+    # and the occupancy refresh are profiled SEPARATELY: both launch hash_encode_fw_kernel / the MLP forward.
+    n_prof = min(args.steps, 96)
+
+    def step_serial(_i):
+        i = counter[0]; counter[0] += 1
         ro, rd, tgt = resident[i % N_BATCHES]
-        trainer.train_step(ro, rd, tgt, next_rays=None)
+        trainer.train_step(ro, rd, tgt, update_grid=False, next_rays=None)
 
     _lib.profile_enable(True)
-    timed(step_serial, min(args.steps, 96))
+    timed(step_serial, n_prof)
     prof = _lib.profile_report()
+    timed(refresh_only, 4)
+    prof_refresh = _lib.profile_report()
     _lib.profile_enable(False)
 
     hbm, tf_burst, tf_sus, peak_src = read_peaks()
     # algorithmic bytes / flops per launch (DESIGN.md "Kernels"): N = marched samples of the step
     N = n_samples
     n_params = sum(p.numel() for p in model.parameters())
+    n_table = model.xyz_encoder.params.numel() - 3072
     model_bytes = {"hash_encode_fw_kernel": 588.0 * N, "hash_encode_bw_kernel": 588.0 * N, "hash_encode_bw_runs_kernel": 588.0 * N,
                    "composite_train_fw_kernel": 28.0 * N + 20 * BATCH, "composite_train_bw_kernel": 60.0 * N,
+                   "composite_train_fw_loss_kernel": 88.0 * N + 56 * BATCH,
                    "march_train_emit_kernel": 36.0 * N, "march_train_count_warp_kernel": 36.0 * BATCH + 4.0 * N,
-                   "adam_kernel": 34.0 * n_params / 2, "adam_vec4_kernel": 34.0 * n_params / 2}  # 2 launches per step (xyz, rgb)
+                   "adam_kernel": 34.0 * n_params, "adam_vec4_kernel": 34.0 * n_params}
     model_flops = {"field_mlp_bw_simt_kernel": 40960.0 * N, "density_mlp_fw_simt_kernel": 2 * 3072.0 * N, "rgb_mlp_fw_simt_kernel": 2 * 7168.0 * N,
                    "field_mlp_bw_tc_kernel": 40960.0 * N, "field_mlp_fw_tc_kernel": 20480.0 * N}
+    # the fused exchange moves, per rank and direction, (world-1)/world of the fp32 gradient in and of the fp16 table out
+    # (and the same amounts the other way): 6 bytes per parameter of the (world-1) foreign slices
+    nvlink_bytes = 6.0 * n_table * (world - 1) / world
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch read from the committed ncu --set full capture
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch", {})
-    per_step = {k: ms / min(args.steps, 96) for k, (c, ms) in prof.items()}
+    per_step = {k: ms / n_prof for k, (c, ms) in prof.items()}
     top = max(per_step, key=per_step.get) if per_step else None
     roof = None
     if top is not None:
         calls, ms = prof[top]
         per_launch_s = ms / calls * 1e-3
+        launches_per_step = calls / n_prof
         if top in model_flops:
-            ach = model_flops[top] / per_launch_s / 1e12
+            ach = model_flops[top] / launches_per_step / per_launch_s / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": traffic.get(top),
                     "peak_source": peak_src + " (sustained bf16)", "ms_per_launch": per_launch_s * 1e3}
+        elif top == "p2p_adam_exchange_kernel":
+            ach = nvlink_bytes / launches_per_step / per_launch_s / 1e9
+            roof = {"kernel": top, "bound": "nvlink", "achieved": ach, "peak": PEER_COPY_GBS, "unit": "GB/s", "frac": ach / PEER_COPY_GBS, "traffic": None,
+                    "peak_source": "measured peer copy per direction (B200_PROFILING.md)", "ms_per_launch": per_launch_s * 1e3,
+                    "note": "bytes per rank and direction over NVLink: fp32 gradient slices of the other ranks in, fp16 table slices of the other ranks in (and the same out)"}
         else:
-            ach = model_bytes.get(top, 0.0) / per_launch_s / 1e9
+            ach = model_bytes.get(top, 0.0) / launches_per_step / per_launch_s / 1e9
             roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic.get(top),
                     "peak_source": peak_src, "ms_per_launch": per_launch_s * 1e3}
     if roof is not None and roof["kernel"].startswith("hash_encode_bw"):
-        # what actually bounds this kernel: the rate at which the L2 retires reduction sectors
-        roof["note"] = ("bound by L2 reduction throughput, not by HBM: 44.6 red.global sector operations per sample (levels 11-15: 6 per level, "
-                        "the minimum for 8 corners = 4 aligned 16-byte pairs at even x, 8 singles at odd x) = 10.9 M per launch "
-                        "(ncu lts__t_sectors_srcunit_tex_op_red, profiles/r01b_ncu_full_step.txt), ~73 per clock; more resident warps make it slower")
+        l2 = traffic.get("l2_red_peak_sectors_per_us")
+        roof["note"] = ("algorithmic bytes against the HBM copy peak, as the contract asks; what bounds this kernel is the rate at which the L2 retires "
+                        "reduction sectors (ncu lts__t_sectors_srcunit_tex_op_red, profiles/): DRAM traffic is below the algorithmic bytes")
+        if l2:
+            roof["l2_reduction"] = {"sectors_per_launch": traffic.get("hash_bw_red_sectors"), "peak_sectors_per_us": l2}
     hash_gbs = None
-    if "hash_encode_fw_kernel" in prof:
+    if "hash_encode_fw_kernel" in prof:  # training launches only (the refresh's 1 M-cell launches are in prof_refresh)
         c, ms = prof["hash_encode_fw_kernel"]
         hash_gbs = 588.0 * N / (ms / c * 1e-3) / 1e9
 
-    # 800x800 test frame (configs[2]); pixels interleaved across ranks (balanced), gathered on rank 0
+    # ---- the reference's own CUDA kernels on the same batches (oracle/_ref: the unmodified models/csrc built for sm_100a)
+    refcuda = None
+    if rank == 0 and world == 1 and not args.no_refcuda:
+        try:
+            from oracle import refcuda as rc
+            refcuda = rc.train_stages(model, resident[:8])
+            fro1, frd1 = [t.to(dev) for t in w.test_frame(800, 800)]
+            refcuda.update(rc.test_frame_stages(model, fro1, frd1))
+            ours_geo = sum(per_step.get(k, 0.0) for k in ("aabb_near_kernel", "march_train_count_warp_kernel", "rays_scan_compact_kernel", "march_train_emit_kernel"))
+            ours_comp = sum(per_step.get(k, 0.0) for k in ("composite_train_fw_loss_kernel", "composite_train_fw_kernel", "composite_train_bw_kernel"))
+            refcuda["fused_step_kernels_ms"] = {"geometry": ours_geo, "compositing_fw_loss_bw": ours_comp}
+            refcuda["note"] = ("reference = unmodified models/csrc kernels (oracle/_ref) driven through the reference's own call sequence incl. its allocations and "
+                               "host sync; ours = the same calls on libarnerf.so's vren shim.  fused_step_kernels_ms: what the same stages cost inside the fused step")
+        except Exception as e:  # the checker is optional on the box
+            refcuda = {"unavailable": f"{type(e).__name__}: {e}"}
+
+    # ---- 800x800 test frame (configs[2]); pixels interleaved across ranks (balanced), gathered on rank 0
     from ar_nerf_b200.sharding import gather_frame_interleaved, shard_rays_interleaved
     fro, frd = w.test_frame(800, 800)
     fro, frd = shard_rays_interleaved(fro, frd, rank, world)
@@ -386,21 +437,23 @@ def run_ours(args):
         r = render(model, fro, frd, test_time=True, T_threshold=1e-4)
         gather_frame_interleaved(torch.cat([r["rgb"], r["depth"][:, None], r["opacity"][:, None]], 1), 640000, rank, world)
 
-    frame(0)
-    n_frames = 3
+    frame(0); frame(1)
+    n_frames = 24
     fps = n_frames / (timed(frame, n_frames) * 1e-3)
 
-    # informational: the unbounded configuration (configs[3]: scale 16, 6 cascades, exp_step_factor 1/256), same step
-    other = None
-    if world == 1 and not args.skip_w3:
+    # ---- the other configurations at this GPU count: W3 = configs[3] (unbounded scene, 6 cascades, exp_step_factor 1/256, same
+    # step and exchange), W4 = configs[4] (AR insertion frame at 1920x1080, sharded like the test frame)
+    other = {}
+    if not args.skip_w3:
         w3 = Workload("W3")
         m3 = NGP(w3.scale).to(dev)
         w3.install(m3)
         t3 = NGPTrainer(m3)
-        b3 = [[t.to(dev) for t in w3.train_batch(i, BATCH)[:3]] for i in range(8)]
-        seen3 = []
+        b3 = [[t.to(dev) for t in w3.train_batch(i, BATCH, seed=rank)[:3]] for i in range(8)]
+        seen3, c3 = [], [0]
 
-        def step_w3(i):
+        def step_w3(_i):
+            i = c3[0]; c3[0] += 1
             ro, rd, tgt = b3[i % 8]
             _, res = t3.train_step(ro, rd, tgt, next_rays=tuple(b3[(i + 1) % 8][:2]))
             seen3.append(res["rm_samples"].clone())
@@ -409,9 +462,29 @@ def run_ours(args):
             step_w3(i)
         seen3.clear()
         ms3 = timed(step_w3, 32)
-        other = {"W3_unbounded_scale16_train_Mrays_per_s": BATCH * 32 / (ms3 * 1e-3) / 1e6, "ms_per_step": ms3 / 32,
-                 "samples_per_step": float(torch.stack([x.float() for x in seen3]).mean().item())}
+        other["W3_unbounded_scale16"] = {"train_Mrays_per_s": world * BATCH * 32 / (ms3 * 1e-3) / 1e6, "ms_per_step": ms3 / 32,
+                                         "samples_per_step_per_gpu": float(torch.stack([x.float() for x in seen3]).mean().item()),
+                                         "steps": 32, "grid_update": "2 refreshes of 6 cascades inside the 32 timed steps"}
         del t3, m3, b3
+    if not args.skip_w4:
+        from ar_nerf_b200.rendering import release_test_workspace
+        release_test_workspace()
+        ar = ARFrame(model, w, dev, rank, world)
+
+        def ar_frame(_i):
+            ar.gather(ar.render())
+        ar_frame(0); ar_frame(1)
+        ms4 = timed(ar_frame, 10) / 10
+        other["W4_ar_frame_1920x1080"] = {"frames_per_s": 1e3 / ms4, "ms_per_frame": ms4,
+                                          "what": "SG shading of the inserted object + NeRF background (T=1e-2, 100 samples) + SG shadow factor per pixel, pixels interleaved over the ranks, gathered on rank 0"}
+        release_test_workspace()
+
+    # ---- multi-GPU correctness, where the driver can see it (SCALE line): after all those steps the fp16 tables are
+    # bit-identical on every rank, and a fresh pair of trainers -- fused peer exchange vs NCCL all-reduce + replicated Adam --
+    # stays together on the same batches
+    mg = None
+    if world > 1:
+        mg = multi_gpu_check(model, w, dev, rank, world)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -424,18 +497,63 @@ def run_ours(args):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": BATCH, "samples_per_step_per_gpu": N,
-                           "parallelism": f"dp{world} (rays sharded; hash-table gradient reduce-scatter + sharded Adam + all-gather as one kernel over NVLink peer "
-                                          "memory, NCCL all-reduce of the MLP gradients)" if world > 1 else "dp1",
+                           "parallelism": f"dp{world} (rays sharded; hash-table gradient reduce-scatter + sharded Adam + all-gather as peer-memory kernels over NVLink, "
+                                          f"pipelined per level group behind the hash-grid backward; NCCL all-reduce of the MLP gradients)" if world > 1 else "dp1",
                            "l2_policy": "no explicit flush: one step streams ~350 MB (fp32 master + Adam moments + gradients 206 MB, activations ~140 MB) > 126 MB L2",
-                           "grid_update": "every 16 steps inside the timed region (steady-state form of steps >= 256: G^3/4 uniform + G^3/4 occupied cells)"},
-                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": BATCH * 36, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                        "note": "NGPTrainer.train_step on pinned host batches; loss copied to pinned host memory every step, read by the host one step late"},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-                "frames_per_s_800x800": fps, "hash_encode_GBps": hash_gbs, "other_configs": other,
-                "kernel_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
+                           "grid_update": "every 16 steps inside the timed region (steady-state form of steps >= 256: G^3/4 uniform + G^3/4 occupied cells)",
+                           "timing": f"{windows} window(s) of {args.steps} steps each, starting at phases 0,2,..,14 of the 16-step refresh cycle; value = mean window"},
+                "window_ms_per_step": [round(m / args.steps, 5) for m in win_ms],
+                "ms_per_step_no_refresh": ms_norefresh, "refresh_ms": refresh_ms,
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": feeder.h2d_bytes_per_batch, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                        "note": "NGPTrainer.train_step fed by trainer.BatchFeeder: the host draws (img_idxs, pix_idxs) per step (datasets/base.py:24-30), one pinned "
+                                "block goes host -> device, arn_gather_batch builds rays + colours from the HBM-resident dataset; the loss is copied to pinned host "
+                                "memory every step and read by the host one step late"},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "refcuda": refcuda,
+                "frames_per_s_800x800": fps, "frames_timed": n_frames, "hash_encode_GBps": hash_gbs, "other_configs": other, "multi_gpu_check": mg,
+                "kernel_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+                "refresh_kernel_ms": {k: round(ms / 4, 5) for k, (c, ms) in sorted(prof_refresh.items(), key=lambda kv: -kv[1][1])}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_check(model, w, dev, rank, world):
+    """(a) the fp16 working copy of the hash table of the benchmarked model is bit-identical on every rank; (b) a fresh model
+    trained 6 steps with the fused peer exchange equals the same model trained with NCCL all-reduce + replicated Adam:
+    losses within 1e-3, parameters equal except where Adam (eps = 1e-15) turns gradient rounding noise into a full-size
+    step -- fewer than 1e-3 of the entries may differ by more than 1e-4 (tools/check_sharded.py's bound)."""
+    import torch
+    import torch.distributed as dist
+
+    from ar_nerf_b200.networks import NGP
+    from ar_nerf_b200.trainer import NGPTrainer
+    out = {}
+    p = model.xyz_encoder.params
+    p16 = model.field_state.cache_xyz.get(p)[:p.numel()]
+    words = p16.view(torch.int16).to(torch.int64)
+    sig = torch.stack([words.sum(), (words * (torch.arange(words.numel(), device=dev) % 8191 + 1)).sum()])
+    sigs = [torch.empty_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig)
+    out["fp16_tables_identical"] = bool(all(torch.equal(sigs[0], s) for s in sigs))
+    models = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        m = NGP(w.scale).to(dev); w.install(m); models.append(m)
+    ta = NGPTrainer(models[0], shard_optimizer=True); tb = NGPTrainer(models[1], shard_optimizer=False)
+    out["exchange"] = "p2p" if (ta.opt.items[0][4] is not None and ta.opt.items[0][4]["px"] is not None) else "nccl"
+    worst = 0.0
+    for i in range(6):
+        b = [t.to(dev) for t in w.train_batch(1000 + i, 4096, seed=rank)]
+        la, _ = ta.train_step(b[0], b[1], b[2], noise=b[3], update_grid=False)
+        lb, _ = tb.train_step(b[0], b[1], b[2], noise=b[3], update_grid=False)
+        worst = max(worst, abs(float(la) - float(lb)) / abs(float(lb)))
+    ta.opt.gather_master()
+    pa, pb = models[0].xyz_encoder.params.detach(), models[1].xyz_encoder.params.detach()
+    frac = torch.tensor([float(((pa - pb).abs() > 1e-4).float().mean()), worst], device=dev)
+    dist.all_reduce(frac, op=dist.ReduceOp.MAX)
+    out["loss_rel_diff_max"] = float(frac[1]); out["frac_entries_differing_1e-4"] = float(frac[0])
+    out["pass"] = bool(out["fp16_tables_identical"] and out["loss_rel_diff_max"] <= 1e-3 and out["frac_entries_differing_1e-4"] < 1e-3)
+    return out
 
 
 def main():
@@ -445,7 +563,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip-w3", action="store_true", help="skip the informational unbounded-scene (W3) leg")
+    ap.add_argument("--skip-w3", action="store_true", help="skip the unbounded-scene (W3, configs[3]) leg")
+    ap.add_argument("--skip-w4", action="store_true", help="skip the AR-frame (W4, configs[4]) leg")
+    ap.add_argument("--no-refcuda", action="store_true", help="skip the reference-CUDA-kernel timing leg (oracle/_ref)")
     ap.add_argument("--train-only", action="store_true", help="profiling runs: skip the e2e, test-frame and CPU legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -85,6 +85,13 @@ int arn_packbits(const void* density_grid, int grid_dtype, float threshold, uint
  * 'same_image' sampling strategy, datasets/base.py:27-28); pix_idxs (n) i64.  rays_o, rays_d (n,3) f32, rays_d un-normalised. */
 int arn_gather_rays(const float* directions, const float* K_host, int width, const float* poses, const int64_t* img_idxs,
                     int64_t img_single, const int64_t* pix_idxs, int64_t n, float* rays_o, float* rays_d, arn_stream_t stream);
+/* The whole sampled batch of datasets/base.py:22-36 + train.py:121-126 from the two index vectors: arn_gather_rays plus the
+ * pixels `rays[img_idxs, pix_idxs]` of the DEVICE-resident training images (n_images, pixels_per_image, channels) f32
+ * (channels = 3 rgb, 4 with HDR-NeRF's exposure) into pixels_out (n, channels) -- so that a training step's host -> device
+ * traffic is the 2 x 8 bytes of indices per ray the dataset draws, not rays and colours. */
+int arn_gather_batch(const float* directions, const float* K_host, int width, const float* poses, const int64_t* img_idxs,
+                     int64_t img_single, const int64_t* pix_idxs, int64_t n, const float* images, int64_t pixels_per_image,
+                     int channels, float* rays_o, float* rays_d, float* pixels_out, arn_stream_t stream);
 
 /* Occupancy refresh, the arithmetic of NGP.update_density_grid (networks.py:253-281) around the density evaluation:
  *   arn_grid_cell_positions : xyzs_w = (coords/(G-1)*2-1)*(s - s/G) + (rnd*2-1)*(s/G) for n_cells cells (networks.py:263-267;
@@ -400,14 +407,17 @@ int arn_march_test_far_clamp(const float* rays_o, const float* rays_d, float* hi
                              float exp_step_factor, int max_samples, arn_stream_t stream);
 /* The same iteration with the loop's control state on the device, so that a caller can queue iterations without reading
  * anything back (the reference's loop costs three host synchronisations per iteration, rendering.py:186,198,219).
- * state (5 x int32, device) = {n_alive, N_samples, samples requested so far, active, iterations done}: the iteration reads
+ * state (8 x int32, device) = {n_alive, N_samples, samples requested so far, active, iterations done, iterations that started
+ * active, 0, 0}: the iteration reads
  * state_in and writes state_out -- the schedule of rendering.py:184-206 (stop when nothing was marched, nobody is alive or
  * budget_samples (= kwargs max_samples) is spent; N_samples = max(min(N_rays // N_alive, 64), min_samples)); pass two
- * alternating buffers.  Initial state for a frame of N_rays: {N_rays, S0, S0, 1, 0} with S0 = max(1, min_samples) (or
+ * alternating buffers.  Initial state for a frame of N_rays: {N_rays, S0, S0, 1, 0, 0, 0, 0} with S0 = max(1, min_samples) (or
  * active = 0 when budget_samples <= 0).  An inactive state turns the call into no-ops, so iterations may be queued
  * speculatively and the state read back late.  cfg->n_alive = N_rays (whole frame), cfg->alive/alive_out alternate as
  * before, cfg->n_samples is ignored; n_upper >= the device-side n_alive (grid sizing only; N_rays is always valid);
- * partial: (N_rays + 127) / 128 int32 of scratch; capacity >= N_rays * min_samples. */
+ * partial: (N_rays + 127) / 128 int32 of scratch; capacity >= N_rays * min_samples.  Every launch is a grid-stride loop over
+ * device-side counts with no host synchronisation, so a run of calls can be captured into a CUDA graph with n_upper = N_rays
+ * (ar_nerf_b200/rendering.py replays 8 iterations per graph launch). */
 int arn_render_test_step(const arn_test_iter_t* cfg_host, const int32_t* state_in, int32_t* state_out, int32_t* partial,
                          int min_samples, int budget_samples, int64_t n_upper, arn_stream_t stream);
 /* The frame's samples marched ONCE.  The test march is resumable and deterministic (an iteration starts at the chain point

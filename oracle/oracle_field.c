@@ -214,10 +214,13 @@ void orc_rgb_mlp_fw(int64_t n, const f16* sh, const float* h, const f16* Wc, int
 /* Backward of both nets.  Inputs dL_dsigma (N), dL_drgb (N,3) fp32 (unscaled).
  * Outputs: dWc (7168) double +=, dWd (3072) double += (both already divided by loss_scale),
  *          dfeat (N,32) fp32 = dL/dfeat (unscaled) for the encoding backward. */
-void orc_field_mlp_bw(int64_t n, const float* dL_dsigma, const float* dL_drgb, const float* rgb, const float* h,
-                      const f16* feat, const f16* hid, const f16* in32, const f16* hid1, const f16* hid2,
-                      const f16* Wd, const f16* Wc, int rgb_act, float loss_scale,
-                      double* dWd, double* dWc, float* dfeat) {
+static void field_mlp_bw_impl(int64_t n, const float* dL_dsigma, const float* dL_drgb, const float* rgb, const float* h,
+                              const f16* feat, const f16* hid, const f16* in32, const f16* hid1, const f16* hid2,
+                              const f16* Wd, const f16* Wc, int rgb_act, float loss_scale,
+                              double* dWd, double* dWc, float* dfeat, int abs_terms) {
+/* abs_terms: the weight-gradient accumulators sum |g * x| instead of g * x -- the L1 mass of every entry's sum, against
+ * which the parity tests measure a summation-order / fp16-tie error (tests/test_gpu_parity.py assert_sum). */
+#define ORC_TERM(a, b) (abs_terms ? fabs((double)((a) * (b))) : (double)((a) * (b)))
     const f16* Wc1 = Wc; const f16* Wc2 = Wc + 2048; const f16* Wc3 = Wc + 2048 + 4096;
     const f16* Wd1 = Wd; const f16* Wd2 = Wd + 2048;
     const float inv_scale = 1.0f / loss_scale;
@@ -239,15 +242,15 @@ void orc_field_mlp_bw(int64_t n, const float* dL_dsigma, const float* dL_drgb, c
                 g3[j] = (f16)(g * loss_scale);
             }
             for (int j = 0; j < 16; j++) for (int k = 0; k < 64; k++)
-                lWc[2048 + 4096 + j * 64 + k] += (float)g3[j] * (float)hid2[64 * i + k];
+                lWc[2048 + 4096 + j * 64 + k] += ORC_TERM((float)g3[j], (float)hid2[64 * i + k]);
             matvec_t(Wc3, 16, 64, g3, t);
             for (int k = 0; k < 64; k++) g2[k] = (f16)((float)hid2[64 * i + k] > 0.0f ? t[k] : 0.0f);
             for (int j = 0; j < 64; j++) for (int k = 0; k < 64; k++)
-                lWc[2048 + j * 64 + k] += (float)g2[j] * (float)hid1[64 * i + k];
+                lWc[2048 + j * 64 + k] += ORC_TERM((float)g2[j], (float)hid1[64 * i + k]);
             matvec_t(Wc2, 64, 64, g2, t);
             for (int k = 0; k < 64; k++) g1[k] = (f16)((float)hid1[64 * i + k] > 0.0f ? t[k] : 0.0f);
             for (int j = 0; j < 64; j++) for (int k = 0; k < 32; k++)
-                lWc[j * 32 + k] += (float)g1[j] * (float)in32[32 * i + k];
+                lWc[j * 32 + k] += ORC_TERM((float)g1[j], (float)in32[32 * i + k]);
             matvec_t(Wc1, 64, 32, g1, t); /* t[16..31] = scaled dL/dh from the colour branch */
             /* density output layer: dL/dh0 += dL/dsigma * exp(clamp(h0,-15,15))  (custom_functions.py:170-173) */
             for (int j = 0; j < 16; j++) {
@@ -256,11 +259,11 @@ void orc_field_mlp_bw(int64_t n, const float* dL_dsigma, const float* dL_drgb, c
                 gh[j] = (f16)g;
             }
             for (int j = 0; j < 16; j++) for (int k = 0; k < 64; k++)
-                lWd[2048 + j * 64 + k] += (float)gh[j] * (float)hid[64 * i + k];
+                lWd[2048 + j * 64 + k] += ORC_TERM((float)gh[j], (float)hid[64 * i + k]);
             matvec_t(Wd2, 16, 64, gh, t);
             for (int k = 0; k < 64; k++) gd[k] = (f16)((float)hid[64 * i + k] > 0.0f ? t[k] : 0.0f);
             for (int j = 0; j < 64; j++) for (int k = 0; k < 32; k++)
-                lWd[j * 32 + k] += (float)gd[j] * (float)feat[32 * i + k];
+                lWd[j * 32 + k] += ORC_TERM((float)gd[j], (float)feat[32 * i + k]);
             matvec_t(Wd1, 64, 32, gd, t);
             for (int k = 0; k < 32; k++) dfeat[32 * i + k] = t[k] * inv_scale;
         }
@@ -271,6 +274,20 @@ void orc_field_mlp_bw(int64_t n, const float* dL_dsigma, const float* dL_drgb, c
         }
         free(lWc); free(lWd);
     }
+#undef ORC_TERM
+}
+void orc_field_mlp_bw(int64_t n, const float* dL_dsigma, const float* dL_drgb, const float* rgb, const float* h,
+                      const f16* feat, const f16* hid, const f16* in32, const f16* hid1, const f16* hid2,
+                      const f16* Wd, const f16* Wc, int rgb_act, float loss_scale,
+                      double* dWd, double* dWc, float* dfeat) {
+    field_mlp_bw_impl(n, dL_dsigma, dL_drgb, rgb, h, feat, hid, in32, hid1, hid2, Wd, Wc, rgb_act, loss_scale, dWd, dWc, dfeat, 0);
+}
+/* Same walk; dWd / dWc receive sum |g x| / loss_scale per weight (dfeat as above). */
+void orc_field_mlp_bw_l1(int64_t n, const float* dL_dsigma, const float* dL_drgb, const float* rgb, const float* h,
+                         const f16* feat, const f16* hid, const f16* in32, const f16* hid1, const f16* hid2,
+                         const f16* Wd, const f16* Wc, int rgb_act, float loss_scale,
+                         double* dWd, double* dWc, float* dfeat) {
+    field_mlp_bw_impl(n, dL_dsigma, dL_drgb, rgb, h, feat, hid, in32, hid1, hid2, Wd, Wc, rgb_act, loss_scale, dWd, dWc, dfeat, 1);
 }
 
 /* fp32 -> fp16 parameter cast done every forward (Appendix A.5). */

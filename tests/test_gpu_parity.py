@@ -3,14 +3,24 @@ against the CPU oracle on the same seeded inputs and -- when oracle/_ref/vren*.s
 UNMODIFIED reference kernels themselves.
 
 Bar (BASELINE.json north_star): bit-exact for occupancy bits, morton codes, sample counts, indices and sample values;
-1e-4 relative for rgb / opacity / depth / ws and gradients.  How "relative" is measured (assert_rel):
-  * per-ray / per-sample outputs: |got-ref| <= rtol * max(|ref|, 1e-2 * max|ref|) + atol.  Against the ORACLE the
+1e-4 relative for rgb / opacity / depth / ws and gradients.  How "relative" is measured:
+  * per-ray / per-sample outputs (assert_rel): |got-ref| <= rtol * max(|ref|, 1e-2 * max|ref|) + atol.  Against the ORACLE the
     weights carry atol = 2 ulp(1.0) = 2.4e-7 per sample: alpha = 1 - __expf(-sigma*delta) cancels against 1.0, so one
     ulp of difference between MUFU.EX2 (GPU) and exp2f (host) moves alpha by 2^-24 whatever its size.  Against the
     REAL reference kernels (same MUFU) no atol is needed.
-  * parameter gradients (sums over ~10^5 samples with heavy cancellation, accumulated by fp32 atomics in an
-    order-dependent way -- tiny-cuda-nn's own half2 atomics are not reproducible run to run either): error relative
-    to the tensor's largest magnitude, floor = 1.0.  The oracle accumulates those sums in double."""
+  * parameter gradients (assert_sum): every entry is a SUM of up to ~10^5 signed terms, accumulated in fp32 in a
+    scheduling-dependent order (tiny-cuda-nn's own half2 atomics are not reproducible run to run either) while the oracle
+    sums in double.  Per entry: |got-ref| <= rtol * |ref| + c * 2^-24 * L1, L1 = the sum of the ABSOLUTE values of the
+    entry's terms, taken from the oracle (oracle.field_bw_l1).  No tensor-wide floor: an entry is judged against its own
+    terms.  c (C_ORDER, C_TIES) is stated next to each use.
+  * the tensor-core field (the path bench.py times) against the fp16-operand / fp32-accumulate contract: layer by layer
+    every output is the exact product of the layer's own fp16 inputs to within the fp32 accumulation bound and, for fp16
+    activations, half an fp16 ulp (test_field_tc_layerwise); end to end, h differs from the oracle's by at most ONE fp16
+    rounding interval of each hidden activation whose exact pre-activation lies within the accumulation bound of a
+    rounding boundary, times |W2| (h_apriori_bound).  What is NOT bounded a priori is rgb, three roundings deeper: its
+    tolerance is the measured one and is stated as such."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -43,6 +53,18 @@ def bits(a):
 
 
 ALPHA_ATOL = 2.4e-7  # 2 ulp(1.0), see the module docstring
+EPS32 = 2.0 ** -24   # unit roundoff of fp32
+# assert_sum constants, in units of eps32 * L1 (measured by tests/report_field_error.py on a B200, then given ~4x headroom):
+C_ORDER = 16.0       # the same fp16 terms summed in another fp32 order (CUDA-core kernels, kernel variants against each other)
+C_TIES = 64.0        # tensor-core path: additionally, fp16 roundings of G that sit on a tie may fall the other way
+
+
+REPORT = bool(os.environ.get("ARN_PARITY_REPORT"))  # calibration runs: print "measured / allowed" for every bound (pytest -s)
+
+
+def _report(what, worst):
+    if REPORT:
+        print(f"[parity-report] {what}: {worst:.4f} of the allowed error")
 
 
 def assert_rel(got, ref, rtol=RTOL, what="", atol=0.0, floor=REL_FLOOR):
@@ -52,7 +74,60 @@ def assert_rel(got, ref, rtol=RTOL, what="", atol=0.0, floor=REL_FLOOR):
         return
     denom = np.maximum(np.abs(ref), floor * np.abs(ref).max())
     err = np.maximum(np.abs(got - ref) - atol, 0.0) / np.maximum(denom, 1e-30)
+    _report(what, err.max() / rtol)
     assert err.max() <= rtol, f"{what}: max rel err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)} (ref {ref.flat[err.argmax()]:.6e}, got {got.flat[err.argmax()]:.6e})"
+
+
+def assert_sum(got, ref, l1, c, rtol=RTOL, what="", upstream=0.0):
+    """Per-entry bound for entries that are sums: |got - ref| <= rtol * |ref| + (c * eps32 + upstream) * l1, l1 = sum of
+    |terms| of the entry.  `upstream`: relative tolerance of the terms themselves when they come out of an earlier stage
+    that is only held to a tolerance (the compositing backward's dL/dsigma in the end-to-end tests)."""
+    got, ref, l1 = np.asarray(got, np.float64), np.asarray(ref, np.float64), np.asarray(l1, np.float64)
+    assert got.shape == ref.shape == l1.shape, (what, got.shape, ref.shape, l1.shape)
+    allowed = rtol * np.abs(ref) + (c * EPS32 + upstream) * l1
+    excess = np.abs(got - ref) - allowed
+    _report(what, float(np.max(np.abs(got - ref)[allowed > 0] / allowed[allowed > 0])) if (allowed > 0).any() else 0.0)
+    i = int(excess.argmax())
+    assert excess.flat[i] <= 0, (f"{what}: entry {i}: got {got.flat[i]:.6e} ref {ref.flat[i]:.6e} l1 {l1.flat[i]:.3e}: "
+                                 f"err {abs(got.flat[i] - ref.flat[i]):.3e} = {abs(got.flat[i] - ref.flat[i]) / max(EPS32 * l1.flat[i], 1e-300):.1f} eps32*L1")
+
+
+def ulp16(a):
+    """Spacing of fp16 numbers at |a| (2^-24 in the subnormal range)."""
+    a = np.abs(np.asarray(a, np.float64))
+    return 2.0 ** (np.floor(np.log2(np.maximum(a, 2.0 ** -14))) - 10)
+
+
+def untile(buf, n, width):
+    """Logical (n, width) fp16 rows of an activation tile image (ar_nerf_b200/csrc/arn_field.cuh img_chunk64 / img_chunk128)."""
+    a = N(buf)
+    rows = a.shape[0]
+    a = a.reshape(rows, width // 8, 8)
+    r = np.arange(rows)[:, None]; c = np.arange(width // 8)[None, :]
+    pos = (c ^ ((r >> 1) & 3)) if width == 32 else (c ^ (r & 7))
+    return a[r, pos].reshape(rows, width)[:n]
+
+
+def acc_bound(x16, W16):
+    """(exact, delta): the exact product x W^T of fp16 operands (float64 holds every product and these short sums exactly
+    enough) and the bound on |fl(sum) - exact| for ANY fp32 accumulation of the K products, rounding or truncating:
+    K additions, each off by at most one fp32 ulp (2 eps32) of a partial sum that never exceeds L1 = sum |w x|."""
+    x = x16.astype(np.float64); W = W16.astype(np.float64)
+    return x @ W.T, 2.0 * W.shape[1] * EPS32 * (np.abs(x) @ np.abs(W).T)
+
+
+def h_apriori_bound(ctx):
+    """Per element, how far ANY implementation of the contract may put h from the oracle's h: a hidden activation can land
+    on another fp16 number only if its exact pre-activation lies within the accumulation bound delta1 of a rounding boundary,
+    and then inside [fp16(a - delta1), fp16(a + delta1)] (ONE rounding interval unless the activation is smaller than
+    delta1 itself); h is linear in hid, so |dh_i| <= sum_j |W2_ij| (hi_j - lo_j) + both sides' accumulation bound.
+    Returns (bound (N,16), ambiguous (N,64) bool)."""
+    Wd = ctx["Wd"]; W1 = Wd[:2048].reshape(64, 32); W2 = Wd[2048:].reshape(16, 64)
+    pre, d1 = acc_bound(ctx["feat"], W1)
+    lo = np.maximum(pre - d1, 0.0).astype(np.float16).astype(np.float64); hi = np.maximum(pre + d1, 0.0).astype(np.float16).astype(np.float64)
+    _, d2 = acc_bound(ctx["hid"], W2)
+    bound = (hi - lo) @ np.abs(W2.astype(np.float64)).T + 2.0 * d2 + 2.0 * EPS32 * np.abs(ctx["h"])
+    return bound, hi != lo
 
 
 @pytest.fixture(scope="module")
@@ -371,11 +446,70 @@ def test_field_forward(impl, scale, n, vren):
     assert torch.equal(sig, sig2)
     if impl == "_simt":  # same operation order as the oracle: features, hidden activations and h are bit-identical
         assert np.array_equal(N(h).view(np.uint32), ctx["h"].view(np.uint32))
-    # tensor-core path: accumulation order differs inside the MMA and a hidden activation may flip one fp16 ulp, which moves
-    # h by ~1e-4 absolute whatever its size -> measured against max|h| (floor=1.0)
-    assert_rel(N(h), ctx["h"], rtol=2e-3 if impl == "" else 1e-6, floor=1.0 if impl == "" else REL_FLOOR, what="h")
-    assert_rel(N(sig), ctx["sigma"], rtol=5e-3 if impl == "" else 1e-5, what="sigma")
-    np.testing.assert_allclose(N(rgb), ctx["rgb"], atol=2e-3 if impl == "" else 1e-6)
+        assert_rel(N(sig), ctx["sigma"], rtol=1e-5, what="sigma")
+        np.testing.assert_allclose(N(rgb), ctx["rgb"], atol=1e-6)
+        return
+    # tensor-core path: the accumulation order inside the MMA differs, so a hidden activation whose exact value sits on an
+    # fp16 rounding boundary may land on the neighbouring fp16 number.  h_apriori_bound is what the CONTRACT allows for h:
+    bound, ambiguous = h_apriori_bound(ctx)
+    dh = np.abs(N(h).astype(np.float64) - ctx["h"])
+    _report(f"h vs a-priori bound (ambiguous activations {ambiguous.mean():.2e}, max |dh| {dh.max():.2e}, max |drgb| {np.abs(N(rgb) - ctx['rgb']).max():.2e})", np.max(dh / bound))
+    assert (dh <= bound).all(), f"h: {int((dh > bound).sum())} elements outside the rounding-interval bound, worst {np.max(dh / bound):.2f}x"
+    assert ambiguous.mean() < 0.05  # the bound is not vacuous: few activations are near a boundary at all
+    unamb = ~ambiguous.any(1)       # samples without a single ambiguous activation: only fp32 accumulation noise is allowed
+    assert unamb.sum() > 0.05 * n or n < 100
+    # sigma = exp(h0): relative error = |dh0| (+ 4 ulp of expf)
+    assert (np.abs(N(sig) - ctx["sigma"]) <= ctx["sigma"] * (np.expm1(bound[:, 0]) + 8 * EPS32)).all()
+    # rgb lies three fp16 roundings deeper (fp16(h) -> hid1 -> hid2): no a-priori bound is derived for it; 1e-3 absolute on a
+    # [0,1] output is the MEASURED spread (tests/report_field_error.py), test_field_tc_layerwise holds every layer to its own inputs
+    np.testing.assert_allclose(N(rgb), ctx["rgb"], atol=1e-3)
+
+
+def test_field_tc_layerwise(vren):
+    """The tensor-core MLPs layer by layer, each against the EXACT product of the fp16 inputs the kernel itself saved: the
+    output must be that product to within the fp32 accumulation bound (acc_bound) and, where the contract rounds to fp16,
+    half an fp16 ulp.  This pins every MMA (operand layout, descriptors, accumulate flags, ReLU, rounding) to the contract
+    without reference to another implementation's tie-breaking."""
+    n = 20000
+    model, geo, x, x01, d, pxyz, prgb = _field_setup(0.5, n, 3)
+    xt = T(x).requires_grad_(True)
+    sig, rgb = model(xt, T(d))
+    ws = sig.grad_fn.ws
+    ctx = oracle.field_fw(x01, d, geo, pxyz, prgb)
+    feat, hid = untile(ws["feat"], n, 32), untile(ws["hid"], n, 64)
+    in32, hid1, hid2 = untile(ws["in32"], n, 32), untile(ws["hid1"], n, 64), untile(ws["hid2"], n, 64)
+    h = N(ws["h"][:n])
+    assert np.array_equal(feat.view(np.uint16), ctx["feat"].view(np.uint16))  # the hash-grid forward is bit-exact
+    Wd, Wc = ctx["Wd"], ctx["Wc"]
+
+    def f16_layer(x16, W16, got16, what):
+        exact, delta = acc_bound(x16, W16)
+        a = np.maximum(exact, 0.0)
+        err = np.abs(got16.astype(np.float64) - a)
+        bound = 0.5 * ulp16(a + delta) + delta
+        _report(what, np.max(err / bound))
+        assert (err <= bound).all(), f"{what}: {int((err > bound).sum())} activations off, worst {np.max(err / bound):.2f}x the bound"
+
+    def f32_layer(x16, W16, got32, what):
+        exact, delta = acc_bound(x16, W16)
+        err = np.abs(got32.astype(np.float64) - exact)
+        bound = delta + 2 * EPS32 * np.abs(exact)
+        _report(what, np.max(err / bound))
+        assert (err <= bound).all(), f"{what}: worst {np.max(err / bound):.2f}x the bound"
+        return exact
+
+    f16_layer(feat, Wd[:2048].reshape(64, 32), hid, "density hidden")
+    f32_layer(hid, Wd[2048:].reshape(16, 64), h, "h")
+    assert_rel(N(sig), np.exp(h[:, 0].astype(np.float64)), rtol=4 * EPS32, floor=0.0, what="sigma = exp(h0)")
+    # colour input row = [sh16 | fp16(h)] of the kernel's own h; SH bit-identical with the oracle's
+    assert np.array_equal(in32[:, :16].view(np.uint16), ctx["in32"][:, :16].view(np.uint16))
+    assert np.array_equal(in32[:, 16:].view(np.uint16), h.astype(np.float16).view(np.uint16))
+    f16_layer(in32, Wc[:2048].reshape(64, 32), hid1, "colour hidden 1")
+    f16_layer(hid1, Wc[2048:6144].reshape(64, 64), hid2, "colour hidden 2")
+    exact, delta = acc_bound(hid2, Wc[6144:].reshape(16, 64))
+    want = 1.0 / (1.0 + np.exp(-exact[:, :3]))
+    # sigmoid' <= 1/4: the pre-activation bound maps to at most delta / 4 (+ 4 ulp of expf and the division)
+    assert (np.abs(N(rgb).astype(np.float64) - want) <= delta[:, :3] / 4 + 8 * EPS32).all()
 
 
 @pytest.mark.parametrize("impl", ["_simt", ""])
@@ -389,11 +523,14 @@ def test_field_backward(impl, vren):
     ((sig * T(gs)).sum() + (rgb * T(gc)).sum()).backward()
     ctx = oracle.field_fw(x01, d, geo, pxyz, prgb)
     o_gx, o_gc, o_dx, o_dfeat = oracle.field_bw(ctx, geo, gs, gc, loss_scale=128.0, want_dx=True)
-    tol = 1e-4 if impl == "_simt" else 2e-3
-    assert_rel(N(model.rgb_net.params.grad), o_gc, rtol=tol, floor=1.0, what="colour MLP grad")
-    assert_rel(N(model.xyz_encoder.params.grad)[:3072], o_gx[:3072], rtol=tol, floor=1.0, what="density MLP grad")
-    assert_rel(N(model.xyz_encoder.params.grad)[3072:], o_gx[3072:], rtol=tol, floor=1.0, what="hash table grad")
-    assert_rel(N(xt.grad), o_dx / (2 * 0.5), rtol=max(tol, 1e-3), floor=1.0, what="dL/dxyz")
+    l1x, l1c = oracle.field_bw_l1(ctx, geo, gs, gc, loss_scale=128.0)
+    c = C_ORDER if impl == "_simt" else C_TIES
+    gx, gcol = N(model.xyz_encoder.params.grad), N(model.rgb_net.params.grad)
+    assert_sum(gcol, o_gc, l1c, c, what="colour MLP grad")
+    assert_sum(gx[:3072], o_gx[:3072], l1x[:3072], c, what="density MLP grad")
+    assert_sum(gx[3072:], o_gx[3072:], l1x[3072:], c, what="hash table grad")
+    assert not gx[3072:][l1x[3072:] == 0].any()  # entries no sample touches stay exactly zero
+    assert_rel(N(xt.grad), o_dx / (2 * 0.5), rtol=1e-3 if impl == "_simt" else 2e-3, floor=1.0, what="dL/dxyz")
 
 
 def test_hash_encode_linearity_full_size(vren):
@@ -451,9 +588,12 @@ def test_hash_backward_variants_agree(kind, w1, w3, vren):
     x01 = (N(xyzs) - np.float32(-w.scale)) / (np.float32(w.scale) - np.float32(-w.scale))
     o_geo = oracle.HashGeometry(per_level_scale=geo.per_level_scale)
     o_tg, _ = oracle.hash_encode_bw(x01.astype(np.float32), o_geo, np.zeros(geo.total * 2, np.float16), N(dfeat))
+    l1, _ = oracle.hash_encode_bw(x01.astype(np.float32), o_geo, np.zeros(geo.total * 2, np.float16), np.abs(N(dfeat)))
+    l1 = l1.reshape(-1)
     for mode in (8, 16, 32, 64):
-        assert_rel(res[mode], res[0], rtol=5e-5, floor=1.0, what=f"hash bw runs seg {mode} vs per-sample")
-        assert_rel(res[mode], o_tg.reshape(-1), rtol=RTOL, floor=1.0, what=f"hash bw runs seg {mode} vs oracle")
+        assert_sum(res[mode], res[0], l1, C_ORDER, rtol=0.0, what=f"hash bw runs seg {mode} vs per-sample")
+        assert_sum(res[mode], o_tg.reshape(-1), l1, C_ORDER, what=f"hash bw runs seg {mode} vs oracle")
+        assert not res[mode][l1 == 0].any()
 
 
 def test_adam_step_vs_torch(vren):
@@ -524,6 +664,23 @@ def _oracle_render_train(w, model_params, ro, rd, noise, thr=1e-4):
     return dict(rays_a=rays_a, xyzs=xyzs, deltas=deltas, ts=ts, ctx=ctx, total=total, opacity=opacity, depth=depth, rgb=rgb, ws=ws)
 
 
+def _oracle_backward(w, o, geo, target):
+    """NeRFLoss ('raw', losses.py:63-82) + backward of the oracle pipeline `o` (_oracle_render_train): dL/d(rgb, opacity) by
+    autograd on the tiny per-ray loss, then the oracle's compositing / field backward.  Returns the parameter gradients and
+    the L1 mass of every entry's terms: (grad_xyz, grad_rgb, l1_xyz, l1_rgb)."""
+    bg = 1.0 if w.exp_step_factor == 0 else 0.0
+    o_rgb = o["rgb"] + bg * (1 - o["opacity"])[:, None]
+    rgb_t = torch.tensor(o_rgb, requires_grad=True); op_t = torch.tensor(o["opacity"], requires_grad=True)
+    l = (((rgb_t - target) / (rgb_t.detach() + 1e-3)) ** 2).mean() + (1e-3 * (-(op_t + 1e-10) * torch.log(op_t + 1e-10))).mean()
+    l.backward()
+    g_rgb = rgb_t.grad.numpy(); g_op = op_t.grad.numpy() - bg * g_rgb.sum(1)
+    dsig, drgbs = oracle.composite_train_bw(g_op, np.zeros_like(g_op), g_rgb, np.zeros(len(o["ts"]), np.float32), o["ctx"]["sigma"], o["ctx"]["rgb"],
+                                            o["ws"], o["deltas"], o["ts"], o["rays_a"], o["opacity"], o["depth"], o["rgb"], 1e-4)
+    o_gx, o_gc, _, _ = oracle.field_bw(o["ctx"], geo, dsig, drgbs, loss_scale=128.0)
+    l1x, l1c = oracle.field_bw_l1(o["ctx"], geo, dsig, drgbs, loss_scale=128.0)
+    return o_gx, o_gc, l1x, l1c
+
+
 @pytest.mark.parametrize("kind,impl", [("W1", "_simt"), ("W1", ""), ("W3", "")])
 def test_render_train_end_to_end(kind, impl, w1, w3):
     """rendering.render(train) + NeRFLoss + backward against the oracle pipeline on identical rays / weights / noise."""
@@ -549,19 +706,15 @@ def test_render_train_end_to_end(kind, impl, w1, w3):
     # loss + backward
     loss_d = NeRFLoss(30, 'raw', w.scale, 0.0, lambda_distortion=0.0)(res, {"rgb": T(target)})
     sum(l.mean() for l in loss_d.values()).backward()
-    # oracle backward: dL/d(rgb,opacity) by autograd on the tiny per-ray loss, then the oracle's composite/field backward
-    rgb_t = torch.tensor(o_rgb, requires_grad=True); op_t = torch.tensor(o["opacity"], requires_grad=True)
-    l = (((rgb_t - target) / (rgb_t.detach() + 1e-3)) ** 2).mean() + (1e-3 * (-(op_t + 1e-10) * torch.log(op_t + 1e-10))).mean()
-    l.backward()
-    g_rgb = rgb_t.grad.numpy(); g_op = op_t.grad.numpy() - bg * g_rgb.sum(1)
-    dsig, drgbs = oracle.composite_train_bw(g_op, np.zeros_like(g_op), g_rgb, np.zeros(len(o["ts"]), np.float32), o["ctx"]["sigma"], o["ctx"]["rgb"],
-                                            o["ws"], o["deltas"], o["ts"], o["rays_a"], o["opacity"], o["depth"], o["rgb"], 1e-4)
-    o_gx, o_gc, _, _ = oracle.field_bw(o["ctx"], geo, dsig, drgbs, loss_scale=128.0)
-    # the gradients inherit the forward's alpha rounding floor through dL/dsigma, hence 1e-3 here (1e-4 in test_field_backward)
-    gtol = 1e-3 if impl == "_simt" else 5e-3
-    assert_rel(N(model.rgb_net.params.grad), o_gc, rtol=gtol, floor=1.0, what="colour MLP grad")
-    assert_rel(N(model.xyz_encoder.params.grad)[:3072], o_gx[:3072], rtol=gtol, floor=1.0, what="density MLP grad")
-    assert_rel(N(model.xyz_encoder.params.grad)[3072:], o_gx[3072:], rtol=gtol, floor=1.0, what="hash table grad")
+    o_gx, o_gc, l1x, l1c = _oracle_backward(w, o, geo, target)
+    # per entry against the L1 mass of its own terms.  The terms themselves (dL/dsigma, dL/drgb per sample) come out of the
+    # compositing backward, which is held to `tol` above (alpha rounding floor; the tensor-core forward's sigma / rgb): that
+    # relative tolerance of the terms is `upstream`
+    c = C_ORDER if impl == "_simt" else C_TIES
+    gx = N(model.xyz_encoder.params.grad)
+    assert_sum(N(model.rgb_net.params.grad), o_gc, l1c, c, upstream=tol, what="colour MLP grad")
+    assert_sum(gx[:3072], o_gx[:3072], l1x[:3072], c, upstream=tol, what="density MLP grad")
+    assert_sum(gx[3072:], o_gx[3072:], l1x[3072:], c, upstream=tol, what="hash table grad")
 
 
 @pytest.mark.parametrize("kind", ["W1", "W3"])
@@ -587,8 +740,13 @@ def test_fused_train_step_matches_eager(kind, w1, w3):
     assert torch.equal(res_a["ts_buf"][:n], res_b["ts"]) and torch.equal(res_a["deltas_buf"][:n], res_b["deltas"])
     assert_rel(N(res_a["rgb"]), N(res_b["rgb"]), rtol=1e-5, what="rgb"); assert_rel(N(res_a["opacity"]), N(res_b["opacity"]), rtol=1e-5, what="opacity")
     assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * abs(float(loss_b))
-    for pa, pb, name in ((model_a.xyz_encoder.params, model_b.xyz_encoder.params, "xyz"), (model_a.rgb_net.params, model_b.rgb_net.params, "rgb")):
-        assert_rel(N(pa.grad), N(pb.grad), rtol=2e-4, floor=1.0, what=f"grad {name}")
+    # same kernels, other launch shapes: per entry against the L1 mass of its terms (from the oracle pipeline on the same batch)
+    geo = oracle.HashGeometry(per_level_scale=model_a.geometry.per_level_scale)
+    params = (N(model_a.xyz_encoder.params), N(model_a.rgb_net.params), geo)
+    o = _oracle_render_train(w, params, N(ro), N(rd), N(noise))
+    _, _, l1x, l1c = _oracle_backward(w, o, geo, target.cpu())
+    assert_sum(N(model_a.xyz_encoder.params.grad), N(model_b.xyz_encoder.params.grad), l1x, C_TIES, rtol=0.0, upstream=1e-5, what="grad xyz fused vs eager")
+    assert_sum(N(model_a.rgb_net.params.grad), N(model_b.rgb_net.params.grad), l1c, C_TIES, rtol=0.0, upstream=1e-5, what="grad rgb fused vs eager")
     # full steps (with Adam) stay in lockstep
     for step in range(3):
         b = [T(t) for t in w.train_batch(20 + step, 4096)]
@@ -627,8 +785,14 @@ def test_pipelined_field_evaluation_is_the_same_step(w1):
     from ar_nerf_b200.trainer import NGPTrainer
     w = w1
     losses, grads = [], []
+    l1 = None
     for parts in (1, 3):
         model, *_ = _field_setup(w.scale, 8, 31, table_amp=1.0)
+        if l1 is None:
+            geo = oracle.HashGeometry(per_level_scale=model.geometry.per_level_scale)
+            b = w.train_batch(9, 8192)
+            o = _oracle_render_train(w, (N(model.xyz_encoder.params), N(model.rgb_net.params), geo), b[0].numpy(), b[1].numpy(), b[3].numpy())
+            l1 = _oracle_backward(w, o, geo, b[2])[2:]
         w.install(model)
         tr = NGPTrainer(model)
         ro, rd, target, noise = [T(t) for t in w.train_batch(9, 8192)]
@@ -641,7 +805,8 @@ def test_pipelined_field_evaluation_is_the_same_step(w1):
         assert int(res["rm_samples"]) > 64 * 1024  # large enough for the split to be taken
         losses.append(float(loss)); grads.append((N(model.xyz_encoder.params.grad), N(model.rgb_net.params.grad)))
     assert abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[0])
-    assert_rel(grads[1][0], grads[0][0], rtol=5e-5, floor=1.0, what="xyz grad"); assert_rel(grads[1][1], grads[0][1], rtol=5e-5, floor=1.0, what="rgb grad")
+    assert_sum(grads[1][0], grads[0][0], l1[0], C_TIES, rtol=0.0, what="xyz grad, pipelined vs plain")
+    assert_sum(grads[1][1], grads[0][1], l1[1], C_TIES, rtol=0.0, what="rgb grad, pipelined vs plain")
 
 
 def test_fused_step_edge_cases(w1):
@@ -690,15 +855,20 @@ def test_nerf_loss_kernel_vs_autograd():
         assert_rel(N(outs[3]), N(d_.grad), rtol=1e-4, what="dL_ddepth")
 
 
-def test_render_test_end_to_end(w1):
-    """rendering.render(test_time=True): the iterative march/composite loop against the same loop driven by the oracle."""
+@pytest.mark.parametrize("impl", ["_simt", ""])
+def test_render_test_end_to_end(impl, w1):
+    """rendering.render(test_time=True) against the same loop driven by the oracle: the CUDA-core field through the eager
+    loop (bit-comparable field, 1e-4), and the PRODUCTION path -- tensor-core field, fused device-driven loop replayed from
+    CUDA graphs -- whose field carries the tie-rounding spread of test_field_forward: a ray may then cross the termination
+    threshold one sample earlier or later than in the oracle, which moves its pixel by at most T_threshold."""
     from ar_nerf_b200.rendering import render
     w = w1
     model, geo, _, _, _, pxyz, prgb = _field_setup(w.scale, 8, 22, table_amp=4.0)
-    model.field_impl = "_simt"
+    model.field_impl = impl
     w.install(model)
     ro, rd = w.test_frame(100, 100)
-    res = render(model, T(ro), T(rd), test_time=True, T_threshold=1e-2, max_samples=100)
+    thr = 1e-2
+    res = render(model, T(ro), T(rd), test_time=True, T_threshold=thr, max_samples=100, val_batch_size=2 ** 20)  # show_gui.py:89's kwargs
     ro_n, rd_n = ro.numpy(), rd.numpy()
     hits = scene_hits(w, ro_n, rd_n)
     R = len(ro_n)
@@ -715,12 +885,26 @@ def test_render_test_end_to_end(w1):
         ctx = oracle.field_fw((x.reshape(-1, 3)[valid] - mn) / (mx - mn), d.reshape(-1, 3)[valid], geo, pxyz, prgb)
         sig = np.zeros(len(valid), np.float32); col = np.zeros((len(valid), 3), np.float32)
         sig[valid] = ctx["sigma"]; col[valid] = ctx["rgb"]
-        oracle.composite_test_fw(sig.reshape(-1, S), col.reshape(-1, S, 3), dl, t, None, alive, 1e-2, neff, opacity, depth, rgb)
+        oracle.composite_test_fw(sig.reshape(-1, S), col.reshape(-1, S, 3), dl, t, None, alive, thr, neff, opacity, depth, rgb)
         alive = alive[alive >= 0]
-    assert int(res["total_samples"]) == total
-    assert_rel(N(res["opacity"]), opacity, rtol=1e-4, what="opacity", atol=ALPHA_ATOL * 10)
-    assert_rel(N(res["depth"]), depth, rtol=1e-4, what="depth", atol=ALPHA_ATOL * 10 * 3)
-    assert_rel(N(res["rgb"]), rgb, rtol=1e-4, what="rgb", atol=ALPHA_ATOL * 10)
+    if impl == "_simt":
+        assert int(res["total_samples"]) == total
+        assert_rel(N(res["opacity"]), opacity, rtol=1e-4, what="opacity", atol=ALPHA_ATOL * 10)
+        assert_rel(N(res["depth"]), depth, rtol=1e-4, what="depth", atol=ALPHA_ATOL * 10 * 3)
+        assert_rel(N(res["rgb"]), rgb, rtol=1e-4, what="rgb", atol=ALPHA_ATOL * 10)
+        return
+    # production path.  Rays whose termination flipped relative to the oracle: at most a handful, each within T_threshold
+    # of the oracle's pixel (the samples behind the threshold weigh less than T_threshold in total); everybody else within
+    # the field's measured spread.  The sample count moves with the flipped rays only.
+    d_op = np.abs(N(res["opacity"]) - opacity); d_rgb = np.abs(N(res["rgb"]) - rgb).max(1)
+    flipped = (d_op > 2e-3) | (d_rgb > 2e-3)
+    _report(f"test frame, production path: {int(flipped.sum())} of {R} rays flipped termination, total_samples {int(res['total_samples'])} vs {total}; "
+            f"max |d opacity| {d_op[~flipped].max():.2e}, max |d rgb| {d_rgb[~flipped].max():.2e} on the others", float(flipped.mean()) / 2e-3)
+    assert flipped.mean() <= 2e-3
+    assert d_op[flipped].max(initial=0.0) <= 2 * thr and d_rgb[flipped].max(initial=0.0) <= 2 * thr
+    assert abs(int(res["total_samples"]) - total) <= 64 * max(1, int(flipped.sum())) + 2e-3 * total
+    far = float(np.abs(depth).max())
+    assert_rel(N(res["depth"])[~flipped], depth[~flipped], rtol=2e-3, what="depth", atol=2e-3 * far)
 
 
 @pytest.mark.parametrize("kind,thr,max_samples", [("W1", 1e-4, 1024), ("W1", 1e-2, 100), ("W3", 1e-2, 100)])
@@ -733,9 +917,17 @@ def test_fused_test_loop_equals_eager_loop(kind, thr, max_samples, w1, w3):
     w.install(model)
     ro, rd = w.test_frame(160, 120)
     kw = dict(test_time=True, T_threshold=thr, max_samples=max_samples, exp_step_factor=w.exp_step_factor)
-    a = render(model, T(ro), T(rd), **kw)                              # frame marched once + arn_render_test_step_pre (loop control on the device)
+    a = render(model, T(ro), T(rd), **kw)                              # frame marched once + arn_render_test_step_pre, replayed from CUDA graphs
+    a2 = render(model, T(ro), T(rd), **kw)                             # second frame: pure replay, the replay count taken from the first
+    q = render(model, T(ro), T(rd), graph_test_loop=False, **kw)       # the same iterations queued call by call, state read back late
     m = render(model, T(ro), T(rd), premarch_test_loop=False, **kw)    # arn_render_test_step: every iteration marches
-    assert int(m["total_samples"]) == int(a["total_samples"]) and all(torch.equal(m[k], a[k]) for k in ("opacity", "depth", "rgb"))
+    for other in (a2, q, m):
+        assert int(other["total_samples"]) == int(a["total_samples"]) and all(torch.equal(other[k], a[k]) for k in ("opacity", "depth", "rgb"))
+    # another camera through the SAME captured graphs (the frame's inputs live at fixed addresses), the reference callers' kwargs
+    ro2, rd2 = T(ro).flip(0).contiguous(), T(rd).flip(0).contiguous()
+    f1 = render(model, ro2, rd2, val_batch_size=2 ** 20, **kw); f2 = render(model, ro2, rd2, eager_test_loop=True, **kw)
+    assert int(f1["total_samples"]) == int(f2["total_samples"]) and all(torch.equal(f1[k], f2[k]) for k in ("opacity", "depth", "rgb"))
+    assert all(torch.equal(f1[k].flip(0), a[k]) for k in ("opacity", "depth", "rgb"))
     h = render(model, T(ro), T(rd), host_driven_test_loop=True, **kw)  # arn_render_test_iter: counts read per iteration
     b = render(model, T(ro), T(rd), eager_test_loop=True, **kw)
     assert int(a["total_samples"]) == int(h["total_samples"]) == int(b["total_samples"]) > 0
