@@ -419,6 +419,11 @@ def run_ours(args):
             refcuda = rc.train_stages(model, resident[:8])
             fro1, frd1 = [t.to(dev) for t in w.test_frame(800, 800)]
             refcuda.update(rc.test_frame_stages(model, fro1, frd1))
+            mh = NGP(w.scale).to(dev); w.install(mh)  # its own model: the hybrid step trains it
+            refcuda["hybrid_step"] = rc.hybrid_train_step(mh, resident[:8])
+            refcuda["hybrid_step"]["ours_ms_per_step_no_refresh"] = ms_norefresh
+            refcuda["hybrid_step"]["speedup"] = refcuda["hybrid_step"]["ms_per_step"] / ms_norefresh
+            del mh
             ours_geo = sum(per_step.get(k, 0.0) for k in ("aabb_near_kernel", "march_train_count_warp_kernel", "rays_scan_compact_kernel", "march_train_emit_kernel"))
             ours_comp = sum(per_step.get(k, 0.0) for k in ("composite_train_fw_loss_kernel", "composite_train_fw_kernel", "composite_train_bw_kernel"))
             refcuda["fused_step_kernels_ms"] = {"geometry": ours_geo, "compositing_fw_loss_bw": ours_comp}

@@ -315,13 +315,15 @@ def field_bw(ctx, geo, dL_dsigma, dL_drgb, loss_scale=128.0, want_dx=False):
 
 
 def field_bw_l1(ctx, geo, dL_dsigma, dL_drgb, loss_scale=128.0):
-    """(l1_params_xyz, l1_params_rgb): for every parameter, the sum of the ABSOLUTE values of the terms its gradient sums
-    (field_bw's walk with |g x| / |w dfeat| accumulated) -- the scale against which a re-ordered or fp16-tie-perturbed
-    sum is judged (tests/test_gpu_parity.py assert_sum)."""
+    """(l1_params_xyz, l1_params_rgb): for every parameter, the ALL-PATHS L1 of its gradient -- field_bw's walk with every
+    weight replaced by |W| and every upstream gradient by |g| (orc_field_mlp_bw_l1), the hash-grid backward fed with the
+    resulting L1 of dL/dfeat -- i.e. the sum of the absolute values of all products that reach the entry.  It is the scale
+    against which a re-ordered or fp16-tie-perturbed sum is judged (tests/test_gpu_parity.py assert_sum): an entry is a sum
+    of sums, and an inner sum that cancels carries its own uncertainty outward."""
     N = len(ctx["feat"])
     dWd = np.zeros(3072, np.float64); dWc = np.zeros(7168, np.float64); dfeat = np.zeros((N, 32), np.float32)
     lib().orc_field_mlp_bw_l1(i64(N), _p(_f32(dL_dsigma)), _p(_f32(dL_drgb)), _p(ctx["rgb"]), _p(ctx["h"]),
                               _p(ctx["feat"]), _p(ctx["hid"]), _p(ctx["in32"]), _p(ctx["hid1"]), _p(ctx["hid2"]),
                               _p(ctx["Wd"]), _p(ctx["Wc"]), i32(ctx["rgb_act"]), f(loss_scale), _p(dWd), _p(dWc), _p(dfeat))
-    tg, _ = hash_encode_bw(ctx["x01"], geo, ctx["table"], np.abs(dfeat), True, False)
+    tg, _ = hash_encode_bw(ctx["x01"], geo, ctx["table"], dfeat, True, False)
     return np.concatenate([dWd, tg.reshape(-1)]), dWc

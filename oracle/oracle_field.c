@@ -214,13 +214,17 @@ void orc_rgb_mlp_fw(int64_t n, const f16* sh, const float* h, const f16* Wc, int
 /* Backward of both nets.  Inputs dL_dsigma (N), dL_drgb (N,3) fp32 (unscaled).
  * Outputs: dWc (7168) double +=, dWd (3072) double += (both already divided by loss_scale),
  *          dfeat (N,32) fp32 = dL/dfeat (unscaled) for the encoding backward. */
+/* |W|^T g for non-negative g (the all-paths magnitude propagation of field_mlp_bw_l1 below) */
+static inline void matvec_t_abs(const f16* W, int n_out, int n_in, const float* g, float* dx) {
+    for (int k = 0; k < n_in; k++) dx[k] = 0.0f;
+    for (int j = 0; j < n_out; j++)
+        for (int k = 0; k < n_in; k++) dx[k] += fabsf((float)W[j * n_in + k]) * g[j];
+}
+
 static void field_mlp_bw_impl(int64_t n, const float* dL_dsigma, const float* dL_drgb, const float* rgb, const float* h,
                               const f16* feat, const f16* hid, const f16* in32, const f16* hid1, const f16* hid2,
                               const f16* Wd, const f16* Wc, int rgb_act, float loss_scale,
-                              double* dWd, double* dWc, float* dfeat, int abs_terms) {
-/* abs_terms: the weight-gradient accumulators sum |g * x| instead of g * x -- the L1 mass of every entry's sum, against
- * which the parity tests measure a summation-order / fp16-tie error (tests/test_gpu_parity.py assert_sum). */
-#define ORC_TERM(a, b) (abs_terms ? fabs((double)((a) * (b))) : (double)((a) * (b)))
+                              double* dWd, double* dWc, float* dfeat) {
     const f16* Wc1 = Wc; const f16* Wc2 = Wc + 2048; const f16* Wc3 = Wc + 2048 + 4096;
     const f16* Wd1 = Wd; const f16* Wd2 = Wd + 2048;
     const float inv_scale = 1.0f / loss_scale;
@@ -242,15 +246,15 @@ static void field_mlp_bw_impl(int64_t n, const float* dL_dsigma, const float* dL
                 g3[j] = (f16)(g * loss_scale);
             }
             for (int j = 0; j < 16; j++) for (int k = 0; k < 64; k++)
-                lWc[2048 + 4096 + j * 64 + k] += ORC_TERM((float)g3[j], (float)hid2[64 * i + k]);
+                lWc[2048 + 4096 + j * 64 + k] += (float)g3[j] * (float)hid2[64 * i + k];
             matvec_t(Wc3, 16, 64, g3, t);
             for (int k = 0; k < 64; k++) g2[k] = (f16)((float)hid2[64 * i + k] > 0.0f ? t[k] : 0.0f);
             for (int j = 0; j < 64; j++) for (int k = 0; k < 64; k++)
-                lWc[2048 + j * 64 + k] += ORC_TERM((float)g2[j], (float)hid1[64 * i + k]);
+                lWc[2048 + j * 64 + k] += (float)g2[j] * (float)hid1[64 * i + k];
             matvec_t(Wc2, 64, 64, g2, t);
             for (int k = 0; k < 64; k++) g1[k] = (f16)((float)hid1[64 * i + k] > 0.0f ? t[k] : 0.0f);
             for (int j = 0; j < 64; j++) for (int k = 0; k < 32; k++)
-                lWc[j * 32 + k] += ORC_TERM((float)g1[j], (float)in32[32 * i + k]);
+                lWc[j * 32 + k] += (float)g1[j] * (float)in32[32 * i + k];
             matvec_t(Wc1, 64, 32, g1, t); /* t[16..31] = scaled dL/dh from the colour branch */
             /* density output layer: dL/dh0 += dL/dsigma * exp(clamp(h0,-15,15))  (custom_functions.py:170-173) */
             for (int j = 0; j < 16; j++) {
@@ -259,11 +263,11 @@ static void field_mlp_bw_impl(int64_t n, const float* dL_dsigma, const float* dL
                 gh[j] = (f16)g;
             }
             for (int j = 0; j < 16; j++) for (int k = 0; k < 64; k++)
-                lWd[2048 + j * 64 + k] += ORC_TERM((float)gh[j], (float)hid[64 * i + k]);
+                lWd[2048 + j * 64 + k] += (float)gh[j] * (float)hid[64 * i + k];
             matvec_t(Wd2, 16, 64, gh, t);
             for (int k = 0; k < 64; k++) gd[k] = (f16)((float)hid[64 * i + k] > 0.0f ? t[k] : 0.0f);
             for (int j = 0; j < 64; j++) for (int k = 0; k < 32; k++)
-                lWd[j * 32 + k] += ORC_TERM((float)gd[j], (float)feat[32 * i + k]);
+                lWd[j * 32 + k] += (float)gd[j] * (float)feat[32 * i + k];
             matvec_t(Wd1, 64, 32, gd, t);
             for (int k = 0; k < 32; k++) dfeat[32 * i + k] = t[k] * inv_scale;
         }
@@ -274,22 +278,65 @@ static void field_mlp_bw_impl(int64_t n, const float* dL_dsigma, const float* dL
         }
         free(lWc); free(lWd);
     }
-#undef ORC_TERM
 }
 void orc_field_mlp_bw(int64_t n, const float* dL_dsigma, const float* dL_drgb, const float* rgb, const float* h,
                       const f16* feat, const f16* hid, const f16* in32, const f16* hid1, const f16* hid2,
                       const f16* Wd, const f16* Wc, int rgb_act, float loss_scale,
                       double* dWd, double* dWc, float* dfeat) {
-    field_mlp_bw_impl(n, dL_dsigma, dL_drgb, rgb, h, feat, hid, in32, hid1, hid2, Wd, Wc, rgb_act, loss_scale, dWd, dWc, dfeat, 0);
+    field_mlp_bw_impl(n, dL_dsigma, dL_drgb, rgb, h, feat, hid, in32, hid1, hid2, Wd, Wc, rgb_act, loss_scale, dWd, dWc, dfeat);
 }
-/* Same walk; dWd / dWc receive sum |g x| / loss_scale per weight (dfeat as above). */
+/* The yardstick of the parity tests (tests/test_gpu_parity.py assert_sum): the SAME walk with magnitudes -- every weight
+ * replaced by |W|, every upstream gradient by |g|, no fp16 rounding -- so that each output is the sum of the absolute values
+ * of ALL products that reach it along all paths of the backward graph ("all-paths L1").  It bounds every intermediate
+ * cancellation: a gradient vector that is itself a cancelling sum (dL/dfeat = W1^T g, |W1|^T|g| >> |W1^T g|) carries its own
+ * uncertainty into the sums it feeds.  dWd / dWc receive the L1 of every weight gradient, dfeat the L1 of dL/dfeat. */
 void orc_field_mlp_bw_l1(int64_t n, const float* dL_dsigma, const float* dL_drgb, const float* rgb, const float* h,
                          const f16* feat, const f16* hid, const f16* in32, const f16* hid1, const f16* hid2,
                          const f16* Wd, const f16* Wc, int rgb_act, float loss_scale,
                          double* dWd, double* dWc, float* dfeat) {
-    field_mlp_bw_impl(n, dL_dsigma, dL_drgb, rgb, h, feat, hid, in32, hid1, hid2, Wd, Wc, rgb_act, loss_scale, dWd, dWc, dfeat, 1);
+    const f16* Wc1 = Wc; const f16* Wc2 = Wc + 2048; const f16* Wc3 = Wc + 2048 + 4096;
+    const f16* Wd1 = Wd; const f16* Wd2 = Wd + 2048;
+    (void)loss_scale;
+#pragma omp parallel
+    {
+        double* lWc = (double*)calloc(7168, sizeof(double));
+        double* lWd = (double*)calloc(3072, sizeof(double));
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < n; i++) {
+            float g3[16], g2[64], g1[64], gh[16], gd[64], t[64];
+            for (int j = 0; j < 16; j++) {
+                float g = 0.0f;
+                if (j < 3) { const float y = rgb[3 * i + j]; g = fabsf(dL_drgb[3 * i + j] * (rgb_act ? y * (1.0f - y) : 1.0f)); }
+                g3[j] = g;
+            }
+            for (int j = 0; j < 16; j++) for (int k = 0; k < 64; k++) lWc[2048 + 4096 + j * 64 + k] += g3[j] * fabsf((float)hid2[64 * i + k]);
+            matvec_t_abs(Wc3, 16, 64, g3, t);
+            for (int k = 0; k < 64; k++) g2[k] = (float)hid2[64 * i + k] > 0.0f ? t[k] : 0.0f;
+            for (int j = 0; j < 64; j++) for (int k = 0; k < 64; k++) lWc[2048 + j * 64 + k] += g2[j] * fabsf((float)hid1[64 * i + k]);
+            matvec_t_abs(Wc2, 64, 64, g2, t);
+            for (int k = 0; k < 64; k++) g1[k] = (float)hid1[64 * i + k] > 0.0f ? t[k] : 0.0f;
+            for (int j = 0; j < 64; j++) for (int k = 0; k < 32; k++) lWc[j * 32 + k] += g1[j] * fabsf((float)in32[32 * i + k]);
+            matvec_t_abs(Wc1, 64, 32, g1, t);
+            for (int j = 0; j < 16; j++) {
+                float g = t[16 + j];
+                if (j == 0) g += fabsf(dL_dsigma[i] * expf(fminf(fmaxf(h[16 * i], -15.0f), 15.0f)));
+                gh[j] = g;
+            }
+            for (int j = 0; j < 16; j++) for (int k = 0; k < 64; k++) lWd[2048 + j * 64 + k] += gh[j] * fabsf((float)hid[64 * i + k]);
+            matvec_t_abs(Wd2, 16, 64, gh, t);
+            for (int k = 0; k < 64; k++) gd[k] = (float)hid[64 * i + k] > 0.0f ? t[k] : 0.0f;
+            for (int j = 0; j < 64; j++) for (int k = 0; k < 32; k++) lWd[j * 32 + k] += gd[j] * fabsf((float)feat[32 * i + k]);
+            matvec_t_abs(Wd1, 64, 32, gd, t);
+            for (int k = 0; k < 32; k++) dfeat[32 * i + k] = t[k];
+        }
+#pragma omp critical
+        {
+            for (int k = 0; k < 7168; k++) dWc[k] += lWc[k];
+            for (int k = 0; k < 3072; k++) dWd[k] += lWd[k];
+        }
+        free(lWc); free(lWd);
+    }
 }
-
 /* fp32 -> fp16 parameter cast done every forward (Appendix A.5). */
 void orc_cast_f16(int64_t n, const float* src, f16* dst) {
 #pragma omp parallel for schedule(static)

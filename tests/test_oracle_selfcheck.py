@@ -220,17 +220,18 @@ def test_field_backward_vs_autograd():
 
 
 def test_field_bw_l1_dominates_the_gradient():
-    """oracle.field_bw_l1 (sum of |terms| per parameter, the yardstick of assert_sum in the GPU parity tests): entry by entry
-    >= |gradient| (triangle inequality), zero exactly where no sample contributes, and equal to |gradient| for the one
-    weight block whose terms all share a sign when the upstream gradient does (the output layer, non-negative activations)."""
+    """oracle.field_bw_l1 (all-paths sum of |products| per parameter, the yardstick of assert_sum in the GPU parity tests):
+    entry by entry >= |gradient| (triangle inequality; the gradient's fp16-rounded factors may exceed the unrounded
+    magnitudes by 2^-11 per rounding), zero exactly where no sample contributes, and equal to |gradient| for the one weight
+    block whose products all share a sign when the upstream gradient does (the output layer, non-negative activations)."""
     geo, x01, dirs, pxyz, prgb = _field_inputs(n=1500, seed=8)
     rng = np.random.default_rng(10)
     ctx = oracle.field_fw(x01, dirs, geo, pxyz, prgb)
     gs = (rng.standard_normal(len(x01)) * 1e-2).astype(np.float32); gc = np.abs(rng.standard_normal((len(x01), 3)) * 1e-2).astype(np.float32)
     gx, gcw, _, _ = oracle.field_bw(ctx, geo, gs, gc, loss_scale=128.0)
     l1x, l1c = oracle.field_bw_l1(ctx, geo, gs, gc, loss_scale=128.0)
-    assert (l1x >= np.abs(gx) * (1 - 1e-12)).all() and (l1c >= np.abs(gcw) * (1 - 1e-12)).all()
+    assert (l1x >= np.abs(gx) * (1 - 2e-3)).all() and (l1c >= np.abs(gcw) * (1 - 2e-3)).all()
     assert np.array_equal(l1x[3072:] == 0, gx[3072:] == 0) or not (gx[3072:][l1x[3072:] == 0] != 0).any()
     out_rows = slice(6144, 6144 + 3 * 64)  # dW3 rows of the three colour outputs: g3 >= 0 (positive upstream, sigmoid' > 0), hid2 >= 0
-    np.testing.assert_allclose(l1c[out_rows], np.abs(gcw[out_rows]), rtol=1e-12)
+    np.testing.assert_allclose(l1c[out_rows], np.abs(gcw[out_rows]), rtol=1e-3)
     assert l1c.sum() > np.abs(gcw).sum() * 1.5  # cancellation is real elsewhere
