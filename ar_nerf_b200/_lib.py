@@ -75,6 +75,9 @@ SIGNATURES = {
     "arn_p2p_wait": [P, I, I, C.c_uint64, P],
     "arn_p2p_barrier": [C.POINTER(C.c_void_p), P, I, I, I, C.c_uint64, P],
     "arn_p2p_adam_exchange": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), I, L, L, P, P, P, F, F, F, F, I, F, P],
+    "arn_p2p_set_timeout": [C.c_double],
+    "arn_p2p_set_error_word": [P],
+    "arn_p2p_set_grid": [I],
     "arn_gather_rays": [P, P, I, P, P, L, P, L, P, P, P],
     "arn_gather_batch": [P, P, I, P, P, L, P, L, P, L, I, P, P, P, P],
     "arn_grid_cell_positions": [P, P, L, I, F, P, P],
@@ -123,6 +126,7 @@ SIGNATURES = {
     "arn_train_march": [C.POINTER(TrainCfg), P],
     "arn_train_set_fork": [I, P],
     "arn_train_set_join": [I, P],
+    "arn_train_set_level_groups": [I, C.POINTER(C.c_int), C.POINTER(C.c_void_p)],
     "arn_train_fwbw_marched": [C.POINTER(TrainCfg), P],
     "arn_field_bw_simt": [P, L, P, P, Levels, P, P, I, FieldWs, P, P, P, P, F, P, P, P, P, P],
     "arn_hash_encode_fw": [P, L, P, P, Levels, P, P, P],

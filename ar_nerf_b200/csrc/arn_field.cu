@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) hash_encode_dx_kernel(const float* __rest
 // SEG consecutive samples of ONE level, keeps the 8 corner gradients of the current cell in registers and issues the
 // red.global.add.v2.f32 only when the cell changes.  lane % 16 = level: a half-warp reads one full 128-byte dfeat row
 // per step and the xyz loads are broadcasts.  (Sums are re-associated relative to the per-sample kernel: same tolerance.)
-template <int SEG>
+template <int SEG, int LPG>
 __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                                   const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
                                                                   float2* __restrict__ table_grad, int level0, int nlevels, int img,
@@ -164,17 +164,20 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
         return;
     }
     if (n_dev) n = min(n, (int64_t)*n_dev);
-    const int l = (threadIdx.x & 15);
+    // LPG consecutive lanes share a sample and take the levels level0 .. level0 + LPG - 1 (LPG = 16: the whole row; smaller
+    // groups when the caller walks the levels group by group so that a finished group's gradient can leave early)
+    const int l = level0 + (threadIdx.x & (LPG - 1));
+    const bool active = l < level0 + nlevels && l < ARN_N_LEVELS;
+    const int lc = active ? l : level0;
     // segments of one of `parts` consecutive ranges of 128-sample tiles (a tile is 128 / SEG segments)
     const int64_t tiles_all = (n + 127) / 128;
     const int64_t seg0 = (tiles_all * part / parts) * (128 / SEG);
     const int64_t n_seg = min((n + SEG - 1) / SEG, (tiles_all * (part + 1) / parts) * (128 / SEG));
-    const uint32_t size = tbl.size[l], res = tbl.res[l], mode = tbl.mode[l];
-    float2* lvl = table_grad + tbl.offset[l];
+    const uint32_t size = tbl.size[lc], res = tbl.res[lc], mode = tbl.mode[lc];
+    float2* lvl = table_grad + tbl.offset[lc];
     const bool pair_ok = (reinterpret_cast<uintptr_t>(lvl) & 15) == 0;  // 16-byte reductions need the level base aligned
-    const float scale = tbl.scale[l];
-    const bool active = l >= level0 && l < level0 + nlevels;
-    for (int64_t seg = seg0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4); seg < n_seg; seg += ((int64_t)n_main_blocks * blockDim.x) >> 4) {
+    const float scale = tbl.scale[lc];
+    for (int64_t seg = seg0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPG); seg < n_seg; seg += ((int64_t)n_main_blocks * blockDim.x) / LPG) {
         if (!active) continue;
         const int64_t i0 = seg * SEG, i1 = min(n, i0 + SEG);
         uint32_t cg[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
@@ -221,23 +224,32 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
     }
 }
 
-template <int SEG>
+template <int SEG, int LPG>
 static int launch_hash_bw_runs(const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
                                float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red, int part, int parts) {
-    const int64_t threads = ((n + SEG - 1) / SEG) * 16 / parts;
+    const int64_t threads = ((n + SEG - 1) / SEG) * LPG / parts;
     const int grid = (int)max((int64_t)1, min((int64_t)148 * 8, (threads + 255) / 256));
     const int riders = red.wpart ? kWgradFloats / 32 : 0;
-    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, hash_encode_bw_runs_kernel<SEG><<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img, grid, red, part, parts));
+    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, (hash_encode_bw_runs_kernel<SEG, LPG><<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img, grid, red, part, parts)));
     return check_launch("hash_encode_bw_runs");
+}
+template <int SEG>
+static int hash_bw_runs_lpg(const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
+                            float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red, int part, int parts) {
+    // lanes per sample: the smallest power of two that holds the group's levels
+    if (nlevels > 8) return launch_hash_bw_runs<SEG, 16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+    if (nlevels > 4) return launch_hash_bw_runs<SEG, 8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+    if (nlevels > 2) return launch_hash_bw_runs<SEG, 4>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+    return launch_hash_bw_runs<SEG, 2>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
 }
 static int hash_bw_runs(int seg, const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
                         float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red = WgradReduce{nullptr, 0, 0, nullptr, nullptr},
                         int part = 0, int parts = 1) {
     switch (seg) {
-        case 8: return launch_hash_bw_runs<8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-        case 16: return launch_hash_bw_runs<16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-        case 64: return launch_hash_bw_runs<64>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-        default: return launch_hash_bw_runs<32>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+        case 8: return hash_bw_runs_lpg<8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+        case 16: return hash_bw_runs_lpg<16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+        case 64: return hash_bw_runs_lpg<64>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+        default: return hash_bw_runs_lpg<32>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
     }
 }
 
@@ -719,7 +731,19 @@ int arn::hash_encode_bw_impl(const float* xyzs, int64_t n, const int32_t* n_dev,
     if (table_grad) {
         const int mode = tunable(kTunHashBwMode);  // 0: one reduction per (sample, level, corner); else: run-aggregating, segment length
         if (mode) {
-            if (int e = hash_bw_runs(mode, xyzs, n, n_dev, b, t, dfeat, table_grad, 0, ARN_N_LEVELS, tile_image, st, red, part, parts)) return e;
+            // arn_train_set_level_groups: the levels are walked group by group, each group one launch, and the caller's event of
+            // a group is recorded behind its launch -- the gradient of those levels is final there and may leave (optimizer /
+            // multi-GPU exchange on another stream) while the next group is still reducing.  The MLP weight-gradient slab sum
+            // rides in the FIRST launch: the small gradients are final with the first event.
+            const LevelGroups& lg = level_groups();
+            const bool grouped = lg.n > 0 && parts == 1;
+            const int ng = grouped ? lg.n : 1;
+            const WgradReduce none{nullptr, 0, 0, nullptr, nullptr};
+            for (int g = 0; g < ng; g++) {
+                const int l0 = grouped ? lg.begin[g] : 0, l1 = grouped ? lg.begin[g + 1] : ARN_N_LEVELS;
+                if (int e = hash_bw_runs(mode, xyzs, n, n_dev, b, t, dfeat, table_grad, l0, l1 - l0, tile_image, st, g == 0 ? red : none, part, parts)) return e;
+                if (grouped && lg.events[g]) ARN_CUDA(cudaEventRecord((cudaEvent_t)lg.events[g], st));
+            }
         } else {
             ARN_REQUIRE(parts == 1, "the per-sample backward kernel is not pipelined");
             dim3 grid(sample_grid(n, n_dev), ARN_N_LEVELS);

@@ -48,6 +48,10 @@ int field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, const f
 
 // arn_train_set_fork (arn_train.cu): records the caller's event on `st` if `stage` is the selected fork point
 int train_fork(int stage, cudaStream_t st);
+// arn_train_set_level_groups (arn_train.cu): level ranges [begin[g], begin[g+1]) the hash-grid backward walks one launch at a
+// time, in this order, with an event recorded behind each (n == 0: one launch over all levels)
+struct LevelGroups { int n; int begin[ARN_N_LEVELS + 1]; void* events[ARN_N_LEVELS]; };
+const LevelGroups& level_groups();
 
 // Activation images (arn_mlp_tc.cu): position of logical 16-byte chunk c of row `row` inside the row.  Equal to the
 // shared-memory swizzle of a 1024-byte aligned tile with 64- / 128-byte rows (tc::swz<64>, tc::swz<128>); depends on

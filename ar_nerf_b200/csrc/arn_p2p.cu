@@ -13,7 +13,9 @@
 // monotonic flag slots per rank in peer-visible memory: arn_p2p_signal publishes "my step s is done" into every rank's
 // flag array (after a system-scope fence), arn_p2p_wait spins until all ranks have published >= s.  Each rank always
 // signals before it waits on the same stream, so no rank can wait for a kernel that is not already queued on its peer;
-// the spin is bounded (trap after ~4 s) so that a dead peer fails the launch instead of hanging the GPU.
+// the spin is bounded (arn_p2p_set_timeout, default 120 s -- ranks may legitimately drift apart by a checkpoint write or a
+// validation pass) so that a dead peer cannot hang the GPU for ever: a wait that times out raises a flag in a host-visible
+// word (arn_p2p_set_error_word) and RETURNS -- no trap, the context stays usable -- and the host raises at its next look.
 #include "arn_common.cuh"
 #include <string.h>
 
@@ -23,6 +25,22 @@ constexpr int kMaxRanks = ARN_P2P_MAX_RANKS;
 struct PeerF32 { const float* p[kMaxRanks]; };
 struct PeerF16 { __half* p[kMaxRanks]; };
 struct PeerFlags { unsigned long long* p[kMaxRanks]; };
+
+// spin budget in clock64 ticks and the host-visible error word (pinned, mapped) of this process's device
+static long long g_timeout_ticks = (long long)240e9;  // ~120 s at 2 GHz
+static int g_blocks_per_sm = 8;
+static unsigned int* g_err_word = nullptr;
+__device__ __forceinline__ bool spin_until(const volatile unsigned long long* f, unsigned long long value, long long budget, unsigned int* err, unsigned int code) {
+    const long long t0 = clock64();
+    while (*f < value) {
+        __nanosleep(100);
+        if (clock64() - t0 > budget) {
+            if (err) { atomicExch_system(err, code); __threadfence_system(); }
+            return false;
+        }
+    }
+    return true;
+}
 
 __global__ void p2p_signal_kernel(PeerFlags peers, int n_ranks, int rank, int slot, unsigned long long value) {
     __threadfence_system();  // everything this stream has written (also into peer memory) is visible before the flag
@@ -34,32 +52,22 @@ __global__ void p2p_signal_kernel(PeerFlags peers, int n_ranks, int rank, int sl
     __threadfence_system();
 }
 
-__global__ void p2p_wait_kernel(const unsigned long long* __restrict__ flags, int n_ranks, int slot, unsigned long long value) {
+__global__ void p2p_wait_kernel(const unsigned long long* __restrict__ flags, int n_ranks, int slot, unsigned long long value, long long budget,
+                                unsigned int* err) {
     const int r = threadIdx.x;
-    if (r < n_ranks) {
-        const volatile unsigned long long* f = flags + slot * kMaxRanks + r;
-        const long long t0 = clock64();
-        while (*f < value) {
-            __nanosleep(200);
-            if (clock64() - t0 > (long long)8e9) __trap();  // ~4 s at 2 GHz: a peer died
-        }
-    }
+    if (r < n_ranks) spin_until(flags + slot * kMaxRanks + r, value, budget, err, 0x100u | (unsigned)r);
     __threadfence_system();
 }
 
 // signal + wait in one launch (the pair always comes together on the training path)
-__global__ void p2p_barrier_kernel(PeerFlags peers, const unsigned long long* __restrict__ flags, int n_ranks, int rank, int slot, unsigned long long value) {
+__global__ void p2p_barrier_kernel(PeerFlags peers, const unsigned long long* __restrict__ flags, int n_ranks, int rank, int slot, unsigned long long value,
+                                   long long budget, unsigned int* err) {
     __threadfence_system();
     const int r = threadIdx.x;
     if (r < n_ranks) {
         volatile unsigned long long* f = peers.p[r] + slot * kMaxRanks + rank;
         *f = value;
-        const volatile unsigned long long* mine = flags + slot * kMaxRanks + r;
-        const long long t0 = clock64();
-        while (*mine < value) {
-            __nanosleep(100);
-            if (clock64() - t0 > (long long)8e9) __trap();
-        }
+        spin_until(flags + slot * kMaxRanks + r, value, budget, err, 0x200u | (unsigned)r);
     }
     __threadfence_system();
 }
@@ -74,7 +82,10 @@ __device__ __forceinline__ uint2 pack_half4_(const float4& a) {
 // arithmetic with inv_gs = 1 / (grad_scale * world)), fp16 result to every rank.  p / m / v point at this rank's slice.
 __global__ void __launch_bounds__(256) p2p_adam_exchange_kernel(PeerF32 grads, PeerF16 p16, int n_ranks, int64_t lo, int64_t n4,
                                                                 float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
-                                                                float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_gs) {
+                                                                float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_gs,
+                                                                const unsigned int* __restrict__ err) {
+    // a wait in front of this kernel timed out (a peer is gone or far behind): its gradients are not final, update nothing
+    if (err && *reinterpret_cast<const volatile unsigned int*>(err) != 0u) return;
     const float lr_bc1 = lr / bc1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = lo + 4 * i;
@@ -153,7 +164,8 @@ extern "C" ARN_API int arn_p2p_signal(void* const* peer_flags_host, int n_ranks,
 }
 extern "C" ARN_API int arn_p2p_wait(const void* my_flags, int n_ranks, int slot, uint64_t value, arn_stream_t stream) {
     ARN_REQUIRE(my_flags && n_ranks >= 1 && n_ranks <= kMaxRanks && slot >= 0 && slot < ARN_P2P_FLAG_SLOTS, "bad arguments");
-    ARN_LAUNCH("p2p_wait_kernel", (cudaStream_t)stream, p2p_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)my_flags, n_ranks, slot, (unsigned long long)value));
+    ARN_LAUNCH("p2p_wait_kernel", (cudaStream_t)stream, p2p_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)my_flags, n_ranks, slot, (unsigned long long)value,
+                                                                                                       g_timeout_ticks, g_err_word));
     return check_launch("p2p_wait");
 }
 
@@ -161,7 +173,8 @@ extern "C" ARN_API int arn_p2p_barrier(void* const* peer_flags_host, const void*
     ARN_REQUIRE(peer_flags_host && my_flags && n_ranks >= 1 && n_ranks <= kMaxRanks && rank >= 0 && rank < n_ranks && slot >= 0 && slot < ARN_P2P_FLAG_SLOTS, "bad arguments");
     PeerFlags pf{};
     for (int r = 0; r < n_ranks; r++) { ARN_REQUIRE(peer_flags_host[r], "null peer flag array"); pf.p[r] = (unsigned long long*)peer_flags_host[r]; }
-    ARN_LAUNCH("p2p_barrier_kernel", (cudaStream_t)stream, p2p_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, (const unsigned long long*)my_flags, n_ranks, rank, slot, (unsigned long long)value));
+    ARN_LAUNCH("p2p_barrier_kernel", (cudaStream_t)stream, p2p_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, (const unsigned long long*)my_flags, n_ranks, rank, slot, (unsigned long long)value,
+                                                                                                             g_timeout_ticks, g_err_word));
     return check_launch("p2p_barrier");
 }
 
@@ -181,9 +194,28 @@ extern "C" ARN_API int arn_p2p_adam_exchange(void* const* peer_grads_host, void*
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
     const int64_t n4 = count / 4;
-    const int grid = (int)min((int64_t)148 * 8, (n4 + 255) / 256);
+    // grid: arn_p2p_set_grid blocks per SM (default 8 = whatever fits); a caller that runs the exchange of one level group
+    // beside the hash-grid backward of the next asks for fewer so that both kernels hold SM slots at the same time
+    const int grid = (int)min((int64_t)148 * g_blocks_per_sm, (n4 + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
     ARN_LAUNCH("p2p_adam_exchange_kernel", st, p2p_adam_exchange_kernel<<<grid, 256, 0, st>>>(g, h, n_ranks, lo, n4, (float4*)params_slice, (float4*)exp_avg_slice,
-                                                                                             (float4*)exp_avg_sq_slice, lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale));
+                                                                                             (float4*)exp_avg_sq_slice, lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale,
+                                                                                             g_err_word));
     return check_launch("p2p_adam_exchange");
+}
+
+extern "C" ARN_API int arn_p2p_set_grid(int blocks_per_sm) {
+    ARN_REQUIRE(blocks_per_sm >= 1 && blocks_per_sm <= 16, "1..16 blocks per SM");
+    g_blocks_per_sm = blocks_per_sm;
+    return ARN_OK;
+}
+extern "C" ARN_API int arn_p2p_set_timeout(double seconds) {
+    ARN_REQUIRE(seconds > 0, "timeout must be positive");
+    g_timeout_ticks = (long long)(seconds * 2.0e9);
+    return ARN_OK;
+}
+// err_word: device-accessible address of a zeroed 32-bit word in pinned, mapped host memory (or NULL: timeouts go unreported)
+extern "C" ARN_API int arn_p2p_set_error_word(void* err_word) {
+    g_err_word = (unsigned int*)err_word;
+    return ARN_OK;
 }

@@ -120,6 +120,21 @@ int train_fork(int stage, cudaStream_t st) {
     return ARN_OK;
 }
 }  // namespace arn
+namespace arn {
+thread_local LevelGroups g_level_groups = {0, {0}, {nullptr}};
+const LevelGroups& level_groups() { return g_level_groups; }
+}  // namespace arn
+extern "C" ARN_API int arn_train_set_level_groups(int n_groups, const int* level_begin_host, void* const* cuda_events_host) {
+    ARN_REQUIRE(n_groups >= 0 && n_groups <= ARN_N_LEVELS, "0..16 groups");
+    if (n_groups == 0) { arn::g_level_groups.n = 0; return ARN_OK; }
+    ARN_REQUIRE(level_begin_host, "null pointer");
+    ARN_REQUIRE(level_begin_host[0] == 0 && level_begin_host[n_groups] == ARN_N_LEVELS, "the groups must cover levels 0..16");
+    for (int g = 0; g < n_groups; g++) ARN_REQUIRE(level_begin_host[g] < level_begin_host[g + 1], "level ranges must be increasing and non-empty");
+    arn::g_level_groups.n = n_groups;
+    for (int g = 0; g <= n_groups; g++) arn::g_level_groups.begin[g] = level_begin_host[g];
+    for (int g = 0; g < n_groups; g++) arn::g_level_groups.events[g] = cuda_events_host ? cuda_events_host[g] : nullptr;
+    return ARN_OK;
+}
 extern "C" ARN_API int arn_train_set_join(int stage, void* cuda_event) {
     ARN_REQUIRE(!cuda_event || (stage >= 0 && stage <= 4), "stage must be 0..4");
     arn::g_join_stage = cuda_event ? stage : -1;

@@ -130,16 +130,39 @@ class _RawCuda:
         self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-class PeerExchange:
-    """Buffers + peer mappings + flag slots of one sharded parameter.  Collective constructor (every rank calls it)."""
+def group_runs(bounds, world, rank):
+    """Ownership of a parameter sharded GROUP BY GROUP: bounds = [0, b1, .., n] (multiples of 8).  Rank r owns, of group g,
+    the run [b_g + r*S_g, b_g + (r+1)*S_g) clipped to the group (S_g = shard_size(len_g, world)).  Returns [(lo, cnt, off)]:
+    start and length of the rank's run of each group in the flat parameter and where it starts in the rank's packed state."""
+    runs, off = [], 0
+    for a, b in zip(bounds, bounds[1:]):
+        S = shard_size(b - a, world)
+        lo = min(a + rank * S, b)
+        cnt = max(0, min(lo + S, b) - lo)
+        runs.append((lo, cnt, off))
+        off += cnt
+    return runs
 
-    def __init__(self, n, world, rank, device):
+
+class PeerExchange:
+    """Buffers + peer mappings + flag slots of one sharded parameter.  Collective constructor (every rank calls it).
+
+    bounds = element boundaries [0, b1, .., n] of GROUPS of the flat parameter (multiples of 8): every group is sharded over
+    the ranks on its own -- rank r owns [b_g + r*S_g, b_g + (r+1)*S_g) of group g -- so that a group whose gradient is final
+    can be exchanged while the hash-grid backward is still reducing the next one (step(..., group_events=)).  m / v hold the
+    rank's owned elements group after group (`off` = where a group's run starts)."""
+
+    def __init__(self, n, world, rank, device, bounds=None):
         import ctypes as C
         from . import _lib
         self.n, self.world, self.rank = n, world, rank
-        self.S, self.P = shard_size(n, world), padded_numel(n, world)
-        self.lo = rank * self.S
-        self.cnt = max(0, min(self.lo + self.S, n) - self.lo)
+        bounds = [0, n] if bounds is None else [int(b) for b in bounds]
+        assert bounds[0] == 0 and bounds[-1] == n and all(a < b and a % 8 == 0 for a, b in zip(bounds, bounds[1:])), bounds
+        assert len(bounds) - 1 <= 16
+        self.bounds = bounds
+        self.groups = group_runs(bounds, world, rank)  # (lo, cnt, off): this rank's run of each group inside the flat parameter / inside m, v
+        self.owned = sum(c for _, c, _ in self.groups)
+        self.P = (n + 7) // 8 * 8
 
         def alloc(nbytes):
             out = C.c_void_p()
@@ -171,26 +194,68 @@ class PeerExchange:
         self.grad = torch.as_tensor(_RawCuda(self.g_ptr, self.P, "<f4"), device=device)
         self.p16 = torch.as_tensor(_RawCuda(self.h_ptr, self.P, "<f2"), device=device)
         self.zero_stream = torch.cuda.Stream(device=device)
+        # the exchange runs on its own high-priority stream: its blocks take the SM slots the hash-grid backward's blocks free
+        self.x_stream = torch.cuda.Stream(device=device, priority=-1)
         self.exchanged, self.zeroed = torch.cuda.Event(), torch.cuda.Event()
         self.zeroed.record(); self.exchanged.record()   # creates the CUDA event handles
         self.zero_pending = False
+        # a wait that times out raises this host-visible word instead of trapping (arn_p2p_set_error_word)
+        self.err = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _lib.call("arn_p2p_set_error_word", self.err.data_ptr())
+        _lib.call("arn_p2p_set_timeout", float(os.environ.get("ARN_P2P_TIMEOUT_S", "120")))
+        self.grid_overlap = int(os.environ.get("ARN_P2P_GRID_OVERLAP", "2"))   # blocks per SM while the backward of the next group runs
+        self.grid_tail = int(os.environ.get("ARN_P2P_GRID_TAIL", "8"))
         dist.barrier()  # every mapping exists before anyone signals
 
-    def step(self, p_flat, m, v, hyper, step_id, cuda_stream):
-        """hyper = (lr, beta1, beta2, eps, step, inv_grad_scale).  Gradients of every rank must be complete on this stream."""
+    def check(self):
+        """Raises if a peer wait timed out since the last look (host read of a pinned word: no synchronisation)."""
+        code = int(self.err[0])
+        if code:
+            raise RuntimeError(f"peer-memory exchange: rank {self.rank} waited longer than the timeout for rank {code & 0xff} "
+                               f"({'barrier' if code & 0x200 else 'wait'}); a rank died or fell far behind -- put a dist.barrier() in front of "
+                               "rank-asymmetric work, or raise ARN_P2P_TIMEOUT_S")
+
+    def _exchange_group(self, g, p_flat, m, v, hyper, cuda_stream):
         from ._lib import call, ptr
-        call("arn_p2p_barrier", self.F, self.f_ptr, self.world, self.rank, 0, step_id, cuda_stream)   # my gradients are final ... and everyone's
-        if self.cnt > 0:
-            call("arn_p2p_adam_exchange", self.G, self.H, self.world, self.lo, self.cnt, ptr(p_flat[self.lo:self.lo + self.cnt]), ptr(m), ptr(v),
+        lo, cnt, off = self.groups[g]
+        if cnt > 0:
+            call("arn_p2p_adam_exchange", self.G, self.H, self.world, lo, cnt, ptr(p_flat[lo:lo + cnt]), ptr(m[off:off + cnt]), ptr(v[off:off + cnt]),
                  *hyper, cuda_stream)
-        # my fp16 slice is in every copy and I am done reading ... my copy is complete, nobody reads my gradients any more
-        # (measured: folding the two synchronisations into the exchange kernel -- spinning blocks at its start, a system fence
-        # per thread at its end -- is slower than the two one-block barrier launches: 0.420 vs 0.389 ms per step at 2 GPUs)
-        call("arn_p2p_barrier", self.F, self.f_ptr, self.world, self.rank, 1, step_id, cuda_stream)
+
+    def step(self, p_flat, m, v, hyper, step_id, cuda_stream, group_events=None):
+        """hyper = (lr, beta1, beta2, eps, step, inv_grad_scale).  group_events = None: the gradients of every rank must be
+        complete on `cuda_stream`; everything is queued there.  group_events = [torch.cuda.Event per group]: event g is recorded
+        (arn_train_set_level_groups) where group g's gradient is final on this rank; the exchange of group g then runs on the
+        exchange stream behind a flag barrier of its own -- beside the backward of group g+1 -- and `cuda_stream` only waits for
+        the end of the last one."""
+        from ._lib import call
+        self.check()
+        G = len(self.groups)
+        main = torch.cuda.current_stream()
+        if group_events is None:
+            call("arn_p2p_barrier", self.F, self.f_ptr, self.world, self.rank, 0, step_id, cuda_stream)   # my gradients are final ... and everyone's
+            call("arn_p2p_set_grid", self.grid_tail)
+            for g in range(G):
+                self._exchange_group(g, p_flat, m, v, hyper, cuda_stream)
+            # my fp16 slices are in every copy and I am done reading ... my copy is complete, nobody reads my gradients any more
+            # (measured: folding the two synchronisations into the exchange kernel -- spinning blocks at its start, a system fence
+            # per thread at its end -- is slower than the two one-block barrier launches: 0.420 vs 0.389 ms per step at 2 GPUs)
+            call("arn_p2p_barrier", self.F, self.f_ptr, self.world, self.rank, G, step_id, cuda_stream)
+            self.exchanged.record(main)
+        else:
+            assert len(group_events) == G
+            xs = self.x_stream
+            xh = xs.cuda_stream
+            for g in range(G):
+                xs.wait_event(group_events[g])
+                call("arn_p2p_barrier", self.F, self.f_ptr, self.world, self.rank, g, step_id, xh)        # group g is final on every rank
+                call("arn_p2p_set_grid", self.grid_overlap if g < G - 1 else self.grid_tail)
+                self._exchange_group(g, p_flat, m, v, hyper, xh)
+            call("arn_p2p_barrier", self.F, self.f_ptr, self.world, self.rank, G, step_id, xh)
+            self.exchanged.record(xs)
+            main.wait_event(self.exchanged)  # whatever reads the table next
         # The 45.8 MB memset runs on its own stream, under the next step's forward; whoever writes gradients next waits for
         # `zeroed` (NGPTrainer arms arn_train_set_join in front of the MLP backward; wait_zeroed() for everybody else).
-        main = torch.cuda.current_stream()
-        self.exchanged.record(main)
         self.zero_stream.wait_event(self.exchanged)
         with torch.cuda.stream(self.zero_stream):
             self.grad.zero_()
@@ -202,3 +267,12 @@ class PeerExchange:
         if self.zero_pending:
             torch.cuda.current_stream().wait_event(self.zeroed)
             self.zero_pending = False
+
+    @torch.no_grad()
+    def gather_owned(self, flat):
+        """In place: every rank's owned runs of `flat` (n elements) become current everywhere (checkpoints)."""
+        tmp = torch.zeros_like(flat)
+        for lo, cnt, _ in self.groups:
+            tmp[lo:lo + cnt] = flat[lo:lo + cnt]
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM)  # every element has exactly one owner
+        flat.copy_(tmp)

@@ -28,10 +28,16 @@ class FusedAdam:
     on the wire and 1/world of Adam's HBM traffic.  The fp32 master of a sharded parameter is current only inside the
     owner's slice until gather_master() (call it before saving a checkpoint)."""
 
-    def __init__(self, params_and_caches, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, world=1, rank=0, shard_min_numel=1 << 20, exchange="p2p"):
+    def __init__(self, params_and_caches, lr=1e-2, betas=(0.9, 0.999), eps=1e-15, world=1, rank=0, shard_min_numel=1 << 20, exchange="p2p",
+                 group_bounds=None):
+        """group_bounds: element boundaries [0, b1, .., numel] of the LEVEL GROUPS of the large parameter (the hash table behind
+        its 3072 MLP weights), matching arn_train_set_level_groups: step(group_events=) then updates / exchanges a group as soon
+        as its gradient is final, beside the hash-grid backward of the next group."""
         from .sharding import PeerExchange, padded_numel, shard_size
         self.items = []
         self.world, self.rank = world, rank
+        self.group_bounds = group_bounds
+        self.opt_stream = self.opt_done = None
         for p, cache in params_and_caches:
             if p.numel() == 0:
                 continue
@@ -45,7 +51,7 @@ class FusedAdam:
                 if exchange == "p2p" and dist.get_backend() == "nccl":
                     # peer-memory exchange fused with Adam (csrc/arn_p2p.cu); every rank must succeed, else all fall back to NCCL
                     try:
-                        px = PeerExchange(n, world, rank, p.device)
+                        px = PeerExchange(n, world, rank, p.device, bounds=group_bounds if group_bounds and group_bounds[-1] == n else None)
                         ok = torch.ones(1, device=p.device)
                     except RuntimeError as e:
                         print(f"[ar_nerf_b200] peer-memory exchange unavailable on rank {rank}: {e}")
@@ -56,6 +62,7 @@ class FusedAdam:
                 if px is not None:
                     gpad = px.grad
                     cache.adopt(p, px.p16)
+                    S = px.owned  # m, v: the rank's owned runs, group after group
                 else:
                     gpad = torch.zeros(P, dtype=p.dtype, device=p.device)
                     cache.reserve(p, P)
@@ -76,15 +83,38 @@ class FusedAdam:
         # queueing behind it (a 28 KB all-reduce is pure latency: ~28 us at 8 GPUs)
         self.small_group = dist.new_group() if world > 1 and any(st is not None for *_, st in self.items) else None
 
-    def step(self, inv_grad_scale=1.0):
+    def step(self, inv_grad_scale=1.0, group_events=None):
+        """group_events: one torch.cuda.Event per level group, recorded by the backward where the group's gradient is final
+        (NGPTrainer arms them with arn_train_set_level_groups); None = everything behind the current stream's work."""
         from .sharding import all_gather_shards, reduce_scatter_sum
         self.t += 1
         s_ = stream()
         hyper = (float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), self.t, float(inv_grad_scale))
         if self.world == 1 and len(self.items) == 2:
-            # single GPU: the hash table and the colour net in one launch (arn_adam_step2)
             (pa, ca, ma, va, _), (pb, cb, mb, vb, _) = sorted(self.items, key=lambda it: -it[0].numel())
-            if pa.numel() >= 4096 and pa.numel() % 4 == 0 and pb.numel() <= (1 << 20) and ca is not None and cb is not None:
+            ok = pa.numel() >= 4096 and pa.numel() % 4 == 0 and pb.numel() <= (1 << 20) and ca is not None and cb is not None
+            if ok and group_events is not None and self.group_bounds and self.group_bounds[-1] == pa.numel():
+                # single GPU, pipelined: Adam of a level group runs on the optimizer stream as soon as the group's gradient is
+                # final, beside the hash-grid backward of the next group (HBM-bound against L2-reduction-bound); the colour
+                # net's gradient is final with the first event
+                if self.opt_stream is None:
+                    self.opt_stream, self.opt_done = torch.cuda.Stream(device=pa.device, priority=-1), torch.cuda.Event()
+                os_, oh = self.opt_stream, self.opt_stream.cuda_stream
+                fa, ga, p16a = pa.data.view(-1), pa.grad.view(-1), ca.get(pa)
+                for g, ev in enumerate(group_events):
+                    lo, hi = self.group_bounds[g], self.group_bounds[g + 1]
+                    os_.wait_event(ev)
+                    if g == 0:
+                        call("arn_adam_step2", ptr(fa[lo:hi]), ptr(ga[lo:hi]), ptr(ma[lo:hi]), ptr(va[lo:hi]), ptr(p16a[lo:hi]), hi - lo,
+                             ptr(pb.data), ptr(pb.grad), ptr(mb), ptr(vb), ptr(cb.get(pb)), pb.numel(), *hyper, 1, oh)
+                    else:
+                        call("arn_adam_step", ptr(fa[lo:hi]), ptr(ga[lo:hi]), ptr(ma[lo:hi]), ptr(va[lo:hi]), ptr(p16a[lo:hi]), hi - lo, *hyper, 1, oh)
+                self.opt_done.record(os_)
+                torch.cuda.current_stream().wait_event(self.opt_done)
+                ca.mark_fresh(pa); cb.mark_fresh(pb)
+                return
+            if ok:
+                # single GPU: the hash table and the colour net in one launch (arn_adam_step2)
                 call("arn_adam_step2", ptr(pa.data), ptr(pa.grad), ptr(ma), ptr(va), ptr(ca.get(pa)), pa.numel(),
                      ptr(pb.data), ptr(pb.grad), ptr(mb), ptr(vb), ptr(cb.get(pb)), pb.numel(), *hyper, 1, s_)
                 ca.mark_fresh(pa); cb.mark_fresh(pb)
@@ -93,7 +123,15 @@ class FusedAdam:
         if self.world > 1:
             for i, (p, cache, m, v, st) in enumerate(self.items):
                 if st is None:
-                    pending[i] = dist.all_reduce(p.grad, group=self.small_group, async_op=True)
+                    if group_events is not None:
+                        # the MLP gradients are final behind the first group's event: their all-reduce starts there
+                        if self.small_stream is None:
+                            self.small_stream, self.small_done = torch.cuda.Stream(device=p.device), torch.cuda.Event()
+                        self.small_stream.wait_event(group_events[0])
+                        with torch.cuda.stream(self.small_stream):
+                            pending[i] = dist.all_reduce(p.grad, group=self.small_group, async_op=True)
+                    else:
+                        pending[i] = dist.all_reduce(p.grad, group=self.small_group, async_op=True)
         # sharded parameters first: their collectives are the long ones
         order = sorted(range(len(self.items)), key=lambda i: self.items[i][4] is None)
         for i in order:
@@ -113,7 +151,8 @@ class FusedAdam:
                 else:
                     call("arn_adam_step", ptr(p.data), ptr(p.grad), ptr(m), ptr(v), ptr(p16), p.numel(), *hyper, 1, s_)
             elif st["px"] is not None:
-                st["px"].step(p.data.view(-1), m, v, hyper, self.t, s_)
+                ev = group_events if (group_events is not None and len(group_events) == len(st["px"].groups)) else None
+                st["px"].step(p.data.view(-1), m, v, hyper, self.t, s_, group_events=ev)
             else:
                 reduce_scatter_sum(st["gpad"], st["gshard"], self.rank, self.world)
                 st["gpad"].zero_()
@@ -150,6 +189,10 @@ class FusedAdam:
         from .sharding import all_gather_shards
         for p, cache, m, v, st in self.items:
             if st is None:
+                continue
+            if st["px"] is not None:
+                st["px"].gather_owned(p.data.view(-1))
+                cache.mark_fresh(p)
                 continue
             tmp = torch.zeros(st["P"], dtype=p.dtype, device=p.device)
             lo, cnt = st["lo"], st["cnt"]
@@ -227,9 +270,26 @@ class NGPTrainer:
         st.direct_grad = True
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
+        # Level-major hash-grid backward (arn_train_set_level_groups): the optimizer / the multi-GPU exchange of a level group
+        # starts where that group's gradient is final, beside the backward of the next group.  Coarse levels first: they cost the
+        # backward least per byte of gradient (consecutive samples of a ray share cells), so the exchange -- the longer of the two
+        # pipelines -- starts early.  ARN_LEVEL_GROUPS="0,16" switches the pipelining off.
+        default_groups = "0,8,11,13,16" if self.world > 1 else os.environ.get("ARN_LEVEL_GROUPS_1GPU", "0,16")
+        lv = [int(x) for x in os.environ.get("ARN_LEVEL_GROUPS", default_groups).split(",")]
+        self.level_groups = lv if (self.fused and len(lv) > 2 and lv[0] == 0 and lv[-1] == 16) else None
+        bounds = None
+        if self.level_groups:
+            off = model.geometry.offset
+            n_xyz = model.xyz_encoder.params.numel()
+            bounds = [0] + [3072 + 2 * int(off[l]) for l in self.level_groups[1:-1]] + [n_xyz]
+            self._lg_begin = (C.c_int * len(lv))(*lv)
+            self._lg_events = [torch.cuda.Event() for _ in range(len(lv) - 1)]
+            for e in self._lg_events:
+                e.record()  # creates the CUDA event handles
+            self._lg_handles = (C.c_void_p * (len(lv) - 1))(*[e.cuda_event for e in self._lg_events])
         self.opt = FusedAdam([(model.xyz_encoder.params, st.cache_xyz), (model.rgb_net.params, st.cache_rgb)], lr,
                              world=self.world, rank=self.rank, shard_min_numel=(1 << 20) if shard_optimizer else (1 << 62),
-                             exchange=exchange)
+                             exchange=exchange, group_bounds=bounds)
         self.global_step = 0
         self._grid_epoch = 0
         self.fork_stage = int(os.environ.get("ARN_FORK_STAGE", "2"))  # where the prefetched march joins the step (arn_train_set_fork):
@@ -314,7 +374,13 @@ class NGPTrainer:
         px = self.opt.pending_zero()
         if px is not None:  # the gradient buffer is being zeroed on a side stream: the MLP backward (first writer) waits for it
             call("arn_train_set_join", 2, C.c_void_p(px.zeroed.cuda_event))
-        call("arn_train_fwbw_marched", C.byref(self._cfg(ms, self._keep_target)), main_h)
+        if self.level_groups:
+            call("arn_train_set_level_groups", len(self._lg_events), self._lg_begin, self._lg_handles)
+        try:
+            call("arn_train_fwbw_marched", C.byref(self._cfg(ms, self._keep_target)), main_h)
+        finally:
+            if self.level_groups:
+                call("arn_train_set_level_groups", 0, None, None)
         if px is not None:
             call("arn_train_set_join", 0, None)
             px.zero_pending = False
@@ -355,7 +421,7 @@ class NGPTrainer:
             next_is_update = update_grid and (self.global_step + 1) % self.update_interval == 0
             loss, results = self._fused_fwbw(rays_o, rays_d, rgb_target, noise, next_rays, next_is_update)
             self.opt.lr = self.lr_at(self.global_step)
-            self.opt.step(inv_grad_scale=1.0 / (self.grad_scale * self.world))
+            self.opt.step(inv_grad_scale=1.0 / (self.grad_scale * self.world), group_events=self._lg_events if self.level_groups else None)
             self.global_step += 1
             return loss, results
         self.opt.wait_zeroed()

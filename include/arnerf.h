@@ -343,6 +343,13 @@ int arn_train_set_fork(int stage, void* cuda_event);
  * in front of stage `stage` (same numbering; 2 = in front of the MLP backward, the first kernel that writes parameter
  * gradients) -- e.g. for a gradient buffer that a side stream zeroes while the forward runs.  NULL switches it off. */
 int arn_train_set_join(int stage, void* cuda_event);
+/* Level-major hash-grid backward: the next field backward calls of this thread (arn_train_fwbw_marched, arn_field_bw_tc[_dyn])
+ * walk the 16 levels in n_groups launches over the level ranges [level_begin[g], level_begin[g+1]) (level_begin[0] = 0,
+ * level_begin[n_groups] = 16) and record cuda_events[g] (cudaEvent_t, may be NULL) on their stream behind group g.  Behind
+ * event g the table gradient of those levels is final -- and behind event 0 the MLP weight gradients as well -- so an
+ * optimizer / multi-GPU exchange for a finished group can run on another stream while the next group is still reducing
+ * (SURVEY 5 "pipeline per hash level"; ar_nerf_b200/trainer.py).  n_groups = 0 restores the single launch. */
+int arn_train_set_level_groups(int n_groups, const int* level_begin_host, void* const* cuda_events_host);
 /* Compositing forward with the NeRFLoss epilogue of the fused step (one launch instead of two; rays_a in canonical ray
  * order).  Same outputs as arn_composite_train_fw followed by arn_nerf_loss. */
 int arn_composite_train_fw_loss(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
@@ -463,7 +470,7 @@ int arn_adam_step2(float* params, float* grads, float* exp_avg, float* exp_avg_s
  *                           fp16 working copy.  params/exp_avg/exp_avg_sq point at this rank's slice (local memory).
  * Flag arrays hold ARN_P2P_FLAG_SLOTS * ARN_P2P_MAX_RANKS uint64 and must come from arn_p2p_alloc (zeroed). */
 #define ARN_P2P_MAX_RANKS 8
-#define ARN_P2P_FLAG_SLOTS 4
+#define ARN_P2P_FLAG_SLOTS 24
 int arn_p2p_alloc(void** ptr_host, int64_t bytes);
 int arn_p2p_free(void* ptr);
 int arn_p2p_export(void* ptr, unsigned char* handle64_host);
@@ -474,6 +481,17 @@ int arn_p2p_wait(const void* my_flags, int n_ranks, int slot, uint64_t value, ar
 /* arn_p2p_signal followed by arn_p2p_wait on the same slot and value, as one launch. */
 int arn_p2p_barrier(void* const* peer_flags_host, const void* my_flags, int n_ranks, int rank, int slot, uint64_t value,
                     arn_stream_t stream);
+/* Waits are bounded spins.  A wait that exceeds the budget (arn_p2p_set_timeout, seconds; default 120 -- ranks may drift apart
+ * by a checkpoint write or a validation pass; call a host-side barrier first if more is expected) does NOT trap: it stores
+ * a non-zero code (0x100 | rank it waited for: arn_p2p_wait, 0x200 | rank: arn_p2p_barrier) into the error word registered
+ * with arn_p2p_set_error_word -- the DEVICE address of a zeroed uint32 in pinned, mapped host memory -- and returns; exchange
+ * kernels launched behind it see the word and update nothing.  The host reads the word whenever it likes (no
+ * synchronisation needed) and decides: raise, or fall back to the NCCL form of the same sharding.
+ * arn_p2p_set_grid: thread blocks per SM of the exchange kernel (default 8); a caller that overlaps the exchange of one level
+ * group with the hash-grid backward of the next (arn_train_set_level_groups) asks for 1-2 so that both hold SM slots. */
+int arn_p2p_set_timeout(double seconds);
+int arn_p2p_set_error_word(void* err_word);
+int arn_p2p_set_grid(int blocks_per_sm);
 int arn_p2p_adam_exchange(void* const* peer_grads_host, void* const* peer_p16_host, int n_ranks, int64_t lo, int64_t count,
                           float* params_slice, float* exp_avg_slice, float* exp_avg_sq_slice, float lr, float beta1,
                           float beta2, float eps, int step, float inv_grad_scale, arn_stream_t stream);

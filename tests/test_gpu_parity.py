@@ -1077,3 +1077,44 @@ def test_mark_invisible_cells_full_size(w1, vren):
     vren.mark_invisible_cells(coords, idx, 128, 0.25, T(oracle.world_to_camera(poses.numpy())), K, (800, 800), 0.01, dens, cnt)
     od, oc = oracle.mark_invisible_cells(N(coords), N(idx), 128, 0.25, poses.numpy(), K.numpy(), (800, 800))
     assert np.array_equal(bits(N(dens)), bits(od)) and np.array_equal(bits(N(cnt)), bits(oc))
+
+
+@pytest.mark.parametrize("groups", ["0,8,16", "0,8,11,13,16", ",".join(str(i) for i in range(17))])
+def test_level_grouped_backward_and_pipelined_adam(groups, w1, monkeypatch):
+    """arn_train_set_level_groups: the hash-grid backward walked group by group (one launch per level range, an event behind
+    each) and, on one GPU, Adam of a finished group on the optimizer stream beside the backward of the next one -- against the
+    single-launch backward + single-launch Adam: same gradients (per entry, against the all-paths L1), same losses over the
+    following steps, same parameters except where Adam's eps = 1e-15 turns rounding noise into a full-size step."""
+    from ar_nerf_b200.trainer import NGPTrainer
+    w = w1
+    model_a, *_ = _field_setup(w.scale, 8, 31, table_amp=1.0)
+    model_b, *_ = _field_setup(w.scale, 8, 31, table_amp=1.0)
+    w.install(model_a); w.install(model_b)
+    monkeypatch.setenv("ARN_LEVEL_GROUPS", groups)
+    ta = NGPTrainer(model_a)
+    monkeypatch.setenv("ARN_LEVEL_GROUPS", "0,16")
+    tb = NGPTrainer(model_b)
+    assert ta.level_groups == [int(x) for x in groups.split(",")] and tb.level_groups is None
+    ro, rd, target, noise = [T(t) for t in w.train_batch(9, 4096)]
+    la, _ = ta._fused_fwbw(ro, rd, target, noise)
+    lb, _ = tb._fused_fwbw(ro, rd, target, noise)
+    torch.cuda.synchronize()
+    assert float(la) == float(lb)
+    geo = oracle.HashGeometry(per_level_scale=model_a.geometry.per_level_scale)
+    o = _oracle_render_train(w, (N(model_a.xyz_encoder.params), N(model_a.rgb_net.params), geo), N(ro), N(rd), N(noise))
+    _, _, l1x, l1c = _oracle_backward(w, o, geo, target.cpu())
+    assert_sum(N(model_a.xyz_encoder.params.grad), N(model_b.xyz_encoder.params.grad), l1x, C_ORDER, rtol=0.0, what=f"grad xyz, level groups {groups}")
+    assert torch.equal(model_a.rgb_net.params.grad, model_b.rgb_net.params.grad)
+    for p in (model_a.xyz_encoder.params, model_a.rgb_net.params, model_b.xyz_encoder.params, model_b.rgb_net.params):
+        p.grad.zero_()
+    for step in range(4):
+        b = [T(t) for t in w.train_batch(20 + step, 4096)]
+        la, _ = ta.train_step(*b[:3], noise=b[3], update_grid=False)
+        lb, _ = tb.train_step(*b[:3], noise=b[3], update_grid=False)
+        assert abs(float(la) - float(lb)) <= 2e-3 * abs(float(lb)), (step, float(la), float(lb))
+    torch.cuda.synchronize()
+    pa, pb = model_a.xyz_encoder.params.detach(), model_b.xyz_encoder.params.detach()
+    assert float(((pa - pb).abs() > 1e-4).float().mean()) < 1e-3
+    assert (model_a.xyz_encoder.params.grad == 0).all()  # every group's Adam zeroed its range
+    h16 = model_a.field_state.cache_xyz.get(model_a.xyz_encoder.params)[:pa.numel()]
+    assert torch.equal(h16, pa.half())                   # ... and refreshed its range of the fp16 working copy

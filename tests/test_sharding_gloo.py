@@ -5,7 +5,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ar_nerf_b200.sharding import (all_gather_shards, allreduce_grads, gather_frame, gather_frame_interleaved, padded_numel,
+from ar_nerf_b200.sharding import (all_gather_shards, allreduce_grads, gather_frame, gather_frame_interleaved, group_runs, padded_numel,
                                    reduce_scatter_sum, shard_bounds, shard_rays, shard_rays_interleaved, shard_size)
 
 
@@ -16,6 +16,26 @@ def test_shard_bounds_cover_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_group_runs_tile_every_level_group():
+    """Ownership of the level-grouped peer exchange (sharding.group_runs): for every group the ranks' runs are disjoint,
+    4-element aligned and cover the group exactly; the packed optimizer state of a rank is the concatenation of its runs."""
+    from ar_nerf_b200.field import HashGeometry
+    geo = HashGeometry()
+    n = 3072 + 2 * geo.total
+    for levels in ([0, 16], [0, 8, 16], [0, 8, 11, 13, 16], list(range(17))):
+        bounds = [0] + [3072 + 2 * int(geo.offset[l]) for l in levels[1:-1]] + [n]
+        for world in (1, 2, 4, 8):
+            owner = torch.full((n,), -1, dtype=torch.int8)
+            for rank in range(world):
+                off_expect = 0
+                for (lo, cnt, off), a, b in zip(group_runs(bounds, world, rank), bounds, bounds[1:]):
+                    assert lo % 4 == 0 and cnt % 4 == 0 and a <= lo and lo + cnt <= b and off == off_expect
+                    assert (owner[lo:lo + cnt] == -1).all()
+                    owner[lo:lo + cnt] = rank
+                    off_expect += cnt
+            assert (owner >= 0).all()
 
 
 def _worker(rank, world, port):
