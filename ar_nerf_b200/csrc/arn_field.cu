@@ -153,104 +153,107 @@ __global__ void __launch_bounds__(256) hash_encode_dx_kernel(const float* __rest
 // SEG consecutive samples of ONE level, keeps the 8 corner gradients of the current cell in registers and issues the
 // red.global.add.v2.f32 only when the cell changes.  lane % 16 = level: a half-warp reads one full 128-byte dfeat row
 // per step and the xyz loads are broadcasts.  (Sums are re-associated relative to the per-sample kernel: same tolerance.)
-template <int SEG, int LPG>
+template <int LPG>
 __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
                                                                   const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
                                                                   float2* __restrict__ table_grad, int level0, int nlevels, int img,
-                                                                  int n_main_blocks, WgradReduce red, int part, int parts) {
+                                                                  int n_main_blocks, int min_run, WgradReduce red, int part, int parts) {
     __shared__ float red_part[8][32];
     if ((int)blockIdx.x >= n_main_blocks) {  // rider blocks: sum of the MLP weight-gradient slabs (independent of the table work)
         wgrad_reduce_block((int)blockIdx.x - n_main_blocks, red.wpart, red.n_slabs, red.with_rgb, red.dWd, red.dWc, red_part);
         return;
     }
     if (n_dev) n = min(n, (int64_t)*n_dev);
-    // LPG consecutive lanes share a sample and take the levels level0 .. level0 + LPG - 1 (LPG = 16: the whole row; smaller
-    // groups when the caller walks the levels group by group so that a finished group's gradient can leave early)
+    // LPG consecutive lanes share a run of samples and take the levels level0 .. level0 + LPG - 1 (LPG = 16: the whole row;
+    // smaller groups when the caller walks the levels group by group so that a finished group's gradient can leave early)
     const int l = level0 + (threadIdx.x & (LPG - 1));
-    const bool active = l < level0 + nlevels && l < ARN_N_LEVELS;
-    const int lc = active ? l : level0;
-    // segments of one of `parts` consecutive ranges of 128-sample tiles (a tile is 128 / SEG segments)
+    if (l >= level0 + nlevels || l >= ARN_N_LEVELS) return;
+    // The samples of this launch (one of `parts` consecutive ranges of 128-sample tiles) are cut into EQUAL contiguous runs, one
+    // per lane group: the grid is one resident wave (launch_hash_bw_runs), so every thread carries the same load -- fixed-length
+    // segments left a last, nearly empty wave (964 blocks on 444 slots: three waves' time for 2.2 waves of work) -- and the runs
+    // are as long as the sample count allows, which is what the aggregation below feeds on.
     const int64_t tiles_all = (n + 127) / 128;
-    const int64_t seg0 = (tiles_all * part / parts) * (128 / SEG);
-    const int64_t n_seg = min((n + SEG - 1) / SEG, (tiles_all * (part + 1) / parts) * (128 / SEG));
-    const uint32_t size = tbl.size[lc], res = tbl.res[lc], mode = tbl.mode[lc];
-    float2* lvl = table_grad + tbl.offset[lc];
+    const int64_t s0 = (tiles_all * part / parts) * 128, s1 = min(n, (tiles_all * (part + 1) / parts) * 128);
+    const int64_t n_tg = ((int64_t)n_main_blocks * blockDim.x) / LPG;
+    int64_t per = (s1 - s0 + n_tg - 1) / n_tg;
+    if (per < min_run) per = min_run;
+    const int64_t tg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPG;
+    const int64_t i0 = s0 + tg * per, i1 = min(s1, i0 + per);
+    if (i0 >= i1) return;
+    const uint32_t size = tbl.size[l], res = tbl.res[l], mode = tbl.mode[l];
+    float2* lvl = table_grad + tbl.offset[l];
     const bool pair_ok = (reinterpret_cast<uintptr_t>(lvl) & 15) == 0;  // 16-byte reductions need the level base aligned
-    const float scale = tbl.scale[lc];
-    for (int64_t seg = seg0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPG); seg < n_seg; seg += ((int64_t)n_main_blocks * blockDim.x) / LPG) {
-        if (!active) continue;
-        const int64_t i0 = seg * SEG, i1 = min(n, i0 + SEG);
-        uint32_t cg[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
-        float2 acc[8];
+    const float scale = tbl.scale[l];
+    uint32_t cg[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+    float2 acc[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) acc[c] = make_float2(0.f, 0.f);
-        bool dirty = false;
-        // The two x-corners of a cell are neighbouring table entries whenever they form an aligned pair (hashed level: x even,
-        // since the hash is x ^ f(y,z); dense level: even linear index): one 16-byte reduction then replaces two 8-byte
-        // ones -- the kernel is bound by the number of reduction sectors the L2 can retire.
-        auto flush = [&]() {
-            uint32_t idx[8];
-            corner_indices(mode, size, res, cg, idx);
+    for (int c = 0; c < 8; c++) acc[c] = make_float2(0.f, 0.f);
+    bool dirty = false;
+    // The two x-corners of a cell are neighbouring table entries whenever they form an aligned pair (hashed level: x even,
+    // since the hash is x ^ f(y,z); dense level: even linear index): one 16-byte reduction then replaces two 8-byte
+    // ones -- the kernel is bound by the number of reduction sectors the L2 can retire.
+    auto flush = [&]() {
+        uint32_t idx[8];
+        corner_indices(mode, size, res, cg, idx);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t i0 = idx[2 * q], i1 = idx[2 * q + 1];
-                if (pair_ok && (i0 ^ i1) == 1u) {
-                    const bool lo0 = (i0 & 1u) == 0u;
-                    const float2 a = lo0 ? acc[2 * q] : acc[2 * q + 1], b = lo0 ? acc[2 * q + 1] : acc[2 * q];
-                    atomicAdd(reinterpret_cast<float4*>(lvl + (i0 & ~1u)), make_float4(a.x, a.y, b.x, b.y));
-                } else {
-                    atomicAdd(lvl + i0, acc[2 * q]); atomicAdd(lvl + i1, acc[2 * q + 1]);
-                }
-                acc[2 * q] = make_float2(0.f, 0.f); acc[2 * q + 1] = make_float2(0.f, 0.f);
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i0 = idx[2 * q], i1 = idx[2 * q + 1];
+            if (pair_ok && (i0 ^ i1) == 1u) {
+                const bool lo0 = (i0 & 1u) == 0u;
+                const float2 a = lo0 ? acc[2 * q] : acc[2 * q + 1], b = lo0 ? acc[2 * q + 1] : acc[2 * q];
+                atomicAdd(reinterpret_cast<float4*>(lvl + (i0 & ~1u)), make_float4(a.x, a.y, b.x, b.y));
+            } else {
+                atomicAdd(lvl + i0, acc[2 * q]); atomicAdd(lvl + i1, acc[2 * q + 1]);
             }
-        };
-        for (int64_t i = i0; i < i1; i++) {
-            const float2 d = dfeat[i * ARN_N_LEVELS + dfeat_col(img, i, l)];
-            float w[3]; uint32_t g[3];
-            level_position(xyzs + 3 * i, box, scale, w, g);
-            if (g[0] != cg[0] || g[1] != cg[1] || g[2] != cg[2]) {
-                if (dirty) { flush(); dirty = false; }
-                cg[0] = g[0]; cg[1] = g[1]; cg[2] = g[2];
-            }
-            if (d.x != 0.0f || d.y != 0.0f) {
-                float wt[8];
-                corner_weights(w, wt);
-#pragma unroll
-                for (int c = 0; c < 8; c++) { acc[c].x += wt[c] * d.x; acc[c].y += wt[c] * d.y; }
-                dirty = true;
-            }
+            acc[2 * q] = make_float2(0.f, 0.f); acc[2 * q + 1] = make_float2(0.f, 0.f);
         }
-        if (dirty) flush();
+    };
+    for (int64_t i = i0; i < i1; i++) {
+        const float2 d = dfeat[i * ARN_N_LEVELS + dfeat_col(img, i, l)];
+        float w[3]; uint32_t g[3];
+        level_position(xyzs + 3 * i, box, scale, w, g);
+        if (g[0] != cg[0] || g[1] != cg[1] || g[2] != cg[2]) {
+            if (dirty) { flush(); dirty = false; }
+            cg[0] = g[0]; cg[1] = g[1]; cg[2] = g[2];
+        }
+        if (d.x != 0.0f || d.y != 0.0f) {
+            float wt[8];
+            corner_weights(w, wt);
+#pragma unroll
+            for (int c = 0; c < 8; c++) { acc[c].x += wt[c] * d.x; acc[c].y += wt[c] * d.y; }
+            dirty = true;
+        }
     }
+    if (dirty) flush();
 }
 
-template <int SEG, int LPG>
-static int launch_hash_bw_runs(const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
+template <int LPG>
+static int launch_hash_bw_runs(int min_run, const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
                                float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red, int part, int parts) {
-    const int64_t threads = ((n + SEG - 1) / SEG) * LPG / parts;
-    const int grid = (int)max((int64_t)1, min((int64_t)148 * 8, (threads + 255) / 256));
+    // one resident wave: blocks per SM from the occupancy calculator (3 at 79 registers), times the SM count
+    static int slots = 0;
+    if (!slots) {
+        int dev = 0, n_sm = 0, per_sm = 0;
+        ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        ARN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_encode_bw_runs_kernel<LPG>, 256, 0));
+        slots = n_sm * (per_sm > 0 ? per_sm : 1);
+    }
+    const int64_t threads = ((n + min_run - 1) / min_run) * LPG / parts;  // an upper bound of n is enough: short runs idle some lanes
+    const int cap = tunable(kTunHashBwBlocks) > 0 ? min(slots, 148 * tunable(kTunHashBwBlocks)) : slots;  // "hash_bw_blocks": blocks per SM (A/B)
+    const int grid = (int)max((int64_t)1, min((int64_t)cap, (threads + 255) / 256));
     const int riders = red.wpart ? kWgradFloats / 32 : 0;
-    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, (hash_encode_bw_runs_kernel<SEG, LPG><<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img, grid, red, part, parts)));
+    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, (hash_encode_bw_runs_kernel<LPG><<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img, grid, min_run, red, part, parts)));
     return check_launch("hash_encode_bw_runs");
 }
-template <int SEG>
-static int hash_bw_runs_lpg(const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
-                            float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red, int part, int parts) {
-    // lanes per sample: the smallest power of two that holds the group's levels
-    if (nlevels > 8) return launch_hash_bw_runs<SEG, 16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-    if (nlevels > 4) return launch_hash_bw_runs<SEG, 8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-    if (nlevels > 2) return launch_hash_bw_runs<SEG, 4>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-    return launch_hash_bw_runs<SEG, 2>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-}
-static int hash_bw_runs(int seg, const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
+// min_run ("hash_bw_mode", 8..64): the shortest run of consecutive samples one lane group takes (small batches)
+static int hash_bw_runs(int min_run, const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
                         float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red = WgradReduce{nullptr, 0, 0, nullptr, nullptr},
                         int part = 0, int parts = 1) {
-    switch (seg) {
-        case 8: return hash_bw_runs_lpg<8>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-        case 16: return hash_bw_runs_lpg<16>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-        case 64: return hash_bw_runs_lpg<64>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-        default: return hash_bw_runs_lpg<32>(xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
-    }
+    // lanes per run: the smallest power of two that holds the group's levels
+    if (nlevels > 8) return launch_hash_bw_runs<16>(min_run, xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+    if (nlevels > 4) return launch_hash_bw_runs<8>(min_run, xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+    if (nlevels > 2) return launch_hash_bw_runs<4>(min_run, xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
+    return launch_hash_bw_runs<2>(min_run, xyzs, n, n_dev, b, t, dfeat, table_grad, level0, nlevels, img, st, red, part, parts);
 }
 
 // ------------------------------------------------------------------------------------------------ SH-4

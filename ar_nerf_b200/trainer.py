@@ -421,7 +421,8 @@ class NGPTrainer:
             next_is_update = update_grid and (self.global_step + 1) % self.update_interval == 0
             loss, results = self._fused_fwbw(rays_o, rays_d, rgb_target, noise, next_rays, next_is_update)
             self.opt.lr = self.lr_at(self.global_step)
-            self.opt.step(inv_grad_scale=1.0 / (self.grad_scale * self.world), group_events=self._lg_events if self.level_groups else None)
+            pipelined = self.level_groups and not os.environ.get("ARN_NO_PIPELINED_OPT")  # A/B: split backward, optimizer behind it as before
+            self.opt.step(inv_grad_scale=1.0 / (self.grad_scale * self.world), group_events=self._lg_events if pipelined else None)
             self.global_step += 1
             return loss, results
         self.opt.wait_zeroed()

@@ -56,9 +56,14 @@ def bits(a):
 
 ALPHA_ATOL = 2.4e-7  # 2 ulp(1.0), see the module docstring
 EPS32 = 2.0 ** -24   # unit roundoff of fp32
-# assert_sum constants, in units of eps32 * L1 (measured by tests/report_field_error.py on a B200, then given ~4x headroom):
-C_ORDER = 16.0       # the same fp16 terms summed in another fp32 order (CUDA-core kernels, kernel variants against each other)
-C_TIES = 64.0        # tensor-core path: additionally, fp16 roundings of G that sit on a tie may fall the other way
+# assert_sum constants, in units of eps32 * L1 (L1 = all-paths mass of the entry).  The contract itself -- fp16 operands, four
+# fp16 roundings along a path of the backward graph -- allows 4 * 2^-11 * L1 = 32768 eps32 L1 between two conforming
+# implementations.  Measured on a B200 (tests/report_field_error.py, report mode of this file): CUDA-core kernels / kernel
+# variants against each other at most 230 (p99.9: 12) -- the same fp16 terms in another fp32 order, plus the rare G element
+# whose fp32 value differs in the last bit (FMA contraction) and rounds to the other fp16 neighbour; tensor-core path at most
+# 2150 (p99.9: 260) -- every G element whose pre-rounding value sits within the MMA's accumulation-order noise of a tie.
+C_ORDER = 1024.0     # 1/8 of ONE fp16 unit roundoff (2^-11) of the entry's L1 mass
+C_TIES = 8192.0      # ONE fp16 unit roundoff of the entry's L1 mass (the contract allows four)
 
 
 REPORT = bool(os.environ.get("ARN_PARITY_REPORT"))  # calibration runs: print "measured / allowed" for every bound (pytest -s)
@@ -1099,12 +1104,12 @@ def test_level_grouped_backward_and_pipelined_adam(groups, w1, monkeypatch):
     la, _ = ta._fused_fwbw(ro, rd, target, noise)
     lb, _ = tb._fused_fwbw(ro, rd, target, noise)
     torch.cuda.synchronize()
-    assert float(la) == float(lb)
+    assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(lb))  # the loss is an order-dependent fp32 atomic sum over blocks
     geo = oracle.HashGeometry(per_level_scale=model_a.geometry.per_level_scale)
     o = _oracle_render_train(w, (N(model_a.xyz_encoder.params), N(model_a.rgb_net.params), geo), N(ro), N(rd), N(noise))
     _, _, l1x, l1c = _oracle_backward(w, o, geo, target.cpu())
     assert_sum(N(model_a.xyz_encoder.params.grad), N(model_b.xyz_encoder.params.grad), l1x, C_ORDER, rtol=0.0, what=f"grad xyz, level groups {groups}")
-    assert torch.equal(model_a.rgb_net.params.grad, model_b.rgb_net.params.grad)
+    assert_sum(N(model_a.rgb_net.params.grad), N(model_b.rgb_net.params.grad), l1c, C_ORDER, rtol=0.0, what=f"grad rgb, level groups {groups}")
     for p in (model_a.xyz_encoder.params, model_a.rgb_net.params, model_b.xyz_encoder.params, model_b.rgb_net.params):
         p.grad.zero_()
     for step in range(4):

@@ -1,36 +1,52 @@
-"""Diagnostics: hash-grid backward variants per level range on the W1 batch (scratch tool)."""
-import os, sys
-import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ar_nerf_b200 import _lib
-from ar_nerf_b200._lib import P, L, I, F, Levels
-from ar_nerf_b200.networks import NGP
-from ar_nerf_b200.rendering import render
-from ar_nerf_b200.workload import Workload
+"""Hash-grid backward on the W1 batch through the public entry point (arn_hash_encode_bw): device time per launch for the
+"hash_bw_mode" (shortest run) x "hash_bw_blocks" (blocks per SM) tunables, with the L2 flushed between launches and with the
+gradient buffer hot, and for level-group splits (arn_train_set_level_groups).  Scratch tool."""
 import ctypes as C
+import os
+import sys
 
-lib = _lib.lib()
-lib.arn_dbg_hash_bw.argtypes = [P, L, P, P, Levels, P, P, I, I, I, P]
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ar_nerf_b200 import _lib, vren
+from ar_nerf_b200.networks import NGP
+from ar_nerf_b200.workload import Workload
+
 dev = torch.device("cuda:0")
 w = Workload("W1"); model = NGP(0.5).to(dev); w.install(model); model.host_box()
 ro, rd, tgt, noise = [t.to(dev) for t in w.train_batch(0)]
-from ar_nerf_b200 import vren
 hits = vren.ray_aabb_near(ro, rd, [0, 0, 0], [0.5] * 3, 0.01)
 out = vren.raymarching_train(ro, rd, hits[:, 0], model.density_bitfield, 1, 0.5, 0.0, noise, 128, 1024)
 xyzs = out[1]; n = xyzs.shape[0]
-print("samples", n)
 st = model.field_state
 dfeat = torch.randn(n, 32, device=dev)
-ref = None
-for name, l0, nl, mode in (("all per-sample", 0, 16, 0), ("all runs 8", 0, 16, 8), ("all runs 16", 0, 16, 16), ("all runs 32", 0, 16, 32), ("all runs 64", 0, 16, 64)):
-    tg = torch.zeros(model.geometry.total * 2, device=dev)
-    for it in range(3):
-        tg.zero_(); torch.cuda.synchronize()
+tg = torch.zeros(model.geometry.total * 2, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+print("samples", n)
+
+
+def run(iters=10, cold=True):
+    ts = []
+    for _ in range(iters):
+        tg.zero_()
+        if cold:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = lib.arn_dbg_hash_bw(xyzs.data_ptr(), n, st.mn, st.mx, st.geometry.c_levels, dfeat.data_ptr(), tg.data_ptr(), l0, nl, mode, _lib.stream())
+        _lib.call("arn_hash_encode_bw", xyzs.data_ptr(), n, st.mn, st.mx, st.geometry.c_levels, None, dfeat.data_ptr(), tg.data_ptr(), None, _lib.stream())
         e1.record(); torch.cuda.synchronize()
-        assert rc == 0
-    print(f"{name:26s} {e0.elapsed_time(e1) * 1e3:8.1f} us")
-    if name == "all per-sample": ref = tg.clone()
-    else: print("   max diff vs per-sample", (tg - ref).abs().max().item(), "max", ref.abs().max().item())
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+for blocks in (0, 1, 2, 3, 4):
+    for mode in (8, 16, 32, 64):
+        _lib.set_tunable("hash_bw_mode", mode); _lib.set_tunable("hash_bw_blocks", blocks)
+        print(f"blocks/SM {blocks} min_run {mode:3d}: cold L2 {run():7.1f} us   warm {run(cold=False):7.1f} us")
+_lib.set_tunable("hash_bw_mode", 16); _lib.set_tunable("hash_bw_blocks", 0)
+for groups in ([0, 16], [0, 8, 16], [0, 8, 11, 13, 16], list(range(17))):
+    arr = (C.c_int * len(groups))(*groups)
+    _lib.call("arn_train_set_level_groups", len(groups) - 1, arr, None)
+    print(f"level groups {groups}: cold {run():7.1f} us  warm {run(cold=False):7.1f} us")
+_lib.call("arn_train_set_level_groups", 0, None, None)
