@@ -158,6 +158,11 @@ def lib():
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
         _lib = l
+        # A/B switches without code changes: ARN_TUNABLES="hash_bw_blocks=2,march_warp=0" (arn_set_tunable names)
+        for kv in filter(None, os.environ.get("ARN_TUNABLES", "").split(",")):
+            name, _, val = kv.partition("=")
+            if l.arn_set_tunable(name.strip().encode(), int(val)) != 0:
+                raise RuntimeError(f"ARN_TUNABLES: {l.arn_last_error().decode()}")
     return _lib
 
 

@@ -168,10 +168,9 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
     // smaller groups when the caller walks the levels group by group so that a finished group's gradient can leave early)
     const int l = level0 + (threadIdx.x & (LPG - 1));
     if (l >= level0 + nlevels || l >= ARN_N_LEVELS) return;
-    // The samples of this launch (one of `parts` consecutive ranges of 128-sample tiles) are cut into EQUAL contiguous runs, one
-    // per lane group: the grid is one resident wave (launch_hash_bw_runs), so every thread carries the same load -- fixed-length
-    // segments left a last, nearly empty wave (964 blocks on 444 slots: three waves' time for 2.2 waves of work) -- and the runs
-    // are as long as the sample count allows, which is what the aggregation below feeds on.
+    // The samples of this launch (one of `parts` consecutive ranges of 128-sample tiles) are cut into EQUAL contiguous runs of
+    // `run` samples (chosen by the host: launch_hash_bw_runs), one per lane group, all resident at once: every thread carries
+    // the same load, and the runs are as long as the machine allows -- the aggregation below feeds on consecutive samples.
     const int64_t tiles_all = (n + 127) / 128;
     const int64_t s0 = (tiles_all * part / parts) * 128, s1 = min(n, (tiles_all * (part + 1) / parts) * 128);
     const int64_t n_tg = ((int64_t)n_main_blocks * blockDim.x) / LPG;
@@ -208,25 +207,40 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
             acc[2 * q] = make_float2(0.f, 0.f); acc[2 * q + 1] = make_float2(0.f, 0.f);
         }
     };
-    for (int64_t i = i0; i < i1; i++) {
-        const float2 d = dfeat[i * ARN_N_LEVELS + dfeat_col(img, i, l)];
-        float w[3]; uint32_t g[3];
-        level_position(xyzs + 3 * i, box, scale, w, g);
-        if (g[0] != cg[0] || g[1] != cg[1] || g[2] != cg[2]) {
-            if (dirty) { flush(); dirty = false; }
-            cg[0] = g[0]; cg[1] = g[1]; cg[2] = g[2];
-        }
-        if (d.x != 0.0f || d.y != 0.0f) {
-            float wt[8];
-            corner_weights(w, wt);
+    // the walk is a chain of dependent steps (load the sample, locate its cell, maybe flush): the loads of four samples are in
+    // flight at a time, so a launch over few levels -- few threads per run -- does not pay the full memory latency per sample
+    constexpr int kAhead = 4;
+    for (int64_t ib = i0; ib < i1; ib += kAhead) {
+        float2 dq[kAhead]; float xq[kAhead][3];
 #pragma unroll
-            for (int c = 0; c < 8; c++) { acc[c].x += wt[c] * d.x; acc[c].y += wt[c] * d.y; }
-            dirty = true;
+        for (int k = 0; k < kAhead; k++) {
+            const int64_t i = min(ib + k, i1 - 1);
+            dq[k] = dfeat[i * ARN_N_LEVELS + dfeat_col(img, i, l)];
+            xq[k][0] = xyzs[3 * i]; xq[k][1] = xyzs[3 * i + 1]; xq[k][2] = xyzs[3 * i + 2];
+        }
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) {
+            if (ib + k >= i1) break;
+            const float2 d = dq[k];
+            float w[3]; uint32_t g[3];
+            level_position(xq[k], box, scale, w, g);
+            if (g[0] != cg[0] || g[1] != cg[1] || g[2] != cg[2]) {
+                if (dirty) { flush(); dirty = false; }
+                cg[0] = g[0]; cg[1] = g[1]; cg[2] = g[2];
+            }
+            if (d.x != 0.0f || d.y != 0.0f) {
+                float wt[8];
+                corner_weights(w, wt);
+#pragma unroll
+                for (int c = 0; c < 8; c++) { acc[c].x += wt[c] * d.x; acc[c].y += wt[c] * d.y; }
+                dirty = true;
+            }
         }
     }
     if (dirty) flush();
 }
 
+constexpr int kFineLevel0 = 11;  // first level whose cells (NGP geometry, b ~ 1.32-1.66) are crossed in about one marching step
 template <int LPG>
 static int launch_hash_bw_runs(int min_run, const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
                                float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red, int part, int parts) {
@@ -238,8 +252,16 @@ static int launch_hash_bw_runs(int min_run, const float* xyzs, int64_t n, const 
         ARN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_encode_bw_runs_kernel<LPG>, 256, 0));
         slots = n_sm * (per_sm > 0 ? per_sm : 1);
     }
-    const int64_t threads = ((n + min_run - 1) / min_run) * LPG / parts;  // an upper bound of n is enough: short runs idle some lanes
+    // Run length: what a full-width launch (16 lanes per run) over the whole machine would give, whatever the group's width --
+    // a launch over fewer levels uses proportionally fewer threads instead of shorter runs (shorter runs flush more often,
+    // and the kernel is bound by the L2's reduction rate, not by its thread count).
     const int cap = tunable(kTunHashBwBlocks) > 0 ? min(slots, 148 * tunable(kTunHashBwBlocks)) : slots;  // "hash_bw_blocks": blocks per SM (A/B)
+    const int64_t n_part = (n + parts - 1) / parts;
+    int64_t run = (n_part + ((int64_t)cap * 256 / 16) - 1) / ((int64_t)cap * 256 / 16);
+    if (run < min_run) run = min_run;
+    // ... except for a group of fine levels only (cells smaller than the sample spacing: nothing to aggregate): short runs, all threads
+    if (level0 >= kFineLevel0 && run > min_run) run = max((int64_t)min_run, (n_part * LPG + (int64_t)cap * 256 - 1) / ((int64_t)cap * 256));
+    const int64_t threads = ((n_part + run - 1) / run) * LPG;
     const int grid = (int)max((int64_t)1, min((int64_t)cap, (threads + 255) / 256));
     const int riders = red.wpart ? kWgradFloats / 32 : 0;
     ARN_LAUNCH("hash_encode_bw_runs_kernel", st, (hash_encode_bw_runs_kernel<LPG><<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img, grid, min_run, red, part, parts)));

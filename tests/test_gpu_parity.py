@@ -85,13 +85,19 @@ def assert_rel(got, ref, rtol=RTOL, what="", atol=0.0, floor=REL_FLOOR):
     assert err.max() <= rtol, f"{what}: max rel err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)} (ref {ref.flat[err.argmax()]:.6e}, got {got.flat[err.argmax()]:.6e})"
 
 
-def assert_sum(got, ref, l1, c, rtol=RTOL, what="", upstream=0.0):
+def assert_sum(got, ref, l1, c, rtol=RTOL, what="", upstream=0.0, flip=0.0):
     """Per-entry bound for entries that are sums: |got - ref| <= rtol * |ref| + (c * eps32 + upstream) * l1, l1 = sum of
     |terms| of the entry.  `upstream`: relative tolerance of the terms themselves when they come out of an earlier stage
-    that is only held to a tolerance (the compositing backward's dL/dsigma in the end-to-end tests)."""
+    that is only held to a tolerance (the compositing backward's dL/dsigma in the end-to-end tests).  `flip` (end-to-end
+    tests, = T_threshold): a ray may cross the termination threshold one sample earlier or later than in the oracle (MUFU
+    exp against exp2f); that sample's transmittance is below T_threshold, so the terms it adds or removes are at most `flip`
+    times the largest terms any sample contributes -- taken as the 99.9 % quantile of the non-zero l1 (fine-level entries
+    are hit by a single sample: their l1 IS one sample's term)."""
     got, ref, l1 = np.asarray(got, np.float64), np.asarray(ref, np.float64), np.asarray(l1, np.float64)
     assert got.shape == ref.shape == l1.shape, (what, got.shape, ref.shape, l1.shape)
     allowed = rtol * np.abs(ref) + (c * EPS32 + upstream) * l1
+    if flip > 0 and (l1 > 0).any():
+        allowed = allowed + flip * np.quantile(l1[l1 > 0], 0.999)
     excess = np.abs(got - ref) - allowed
     _report(what, float(np.max(np.abs(got - ref)[allowed > 0] / allowed[allowed > 0])) if (allowed > 0).any() else 0.0)
     i = int(excess.argmax())
@@ -719,9 +725,9 @@ def test_render_train_end_to_end(kind, impl, w1, w3):
     # relative tolerance of the terms is `upstream`
     c = C_ORDER if impl == "_simt" else C_TIES
     gx = N(model.xyz_encoder.params.grad)
-    assert_sum(N(model.rgb_net.params.grad), o_gc, l1c, c, upstream=tol, what="colour MLP grad")
-    assert_sum(gx[:3072], o_gx[:3072], l1x[:3072], c, upstream=tol, what="density MLP grad")
-    assert_sum(gx[3072:], o_gx[3072:], l1x[3072:], c, upstream=tol, what="hash table grad")
+    assert_sum(N(model.rgb_net.params.grad), o_gc, l1c, c, upstream=tol, flip=1e-4, what="colour MLP grad")
+    assert_sum(gx[:3072], o_gx[:3072], l1x[:3072], c, upstream=tol, flip=1e-4, what="density MLP grad")
+    assert_sum(gx[3072:], o_gx[3072:], l1x[3072:], c, upstream=tol, flip=1e-4, what="hash table grad")
 
 
 @pytest.mark.parametrize("kind", ["W1", "W3"])

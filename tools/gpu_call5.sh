@@ -1,0 +1,6 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 300 python tools/bench_hash_bw.py > gpurun_out/r2_hash_bw_sweep3.log 2>&1; echo "sweep rc=$?"; grep -E "level groups|blocks/SM" gpurun_out/r2_hash_bw_sweep3.log
+timeout 300 python bench.py --steps 64 --warmup 5 --train-only > gpurun_out/r2_t_base.json 2> gpurun_out/r2_t_base.err; echo "base rc=$? $(grep value gpurun_out/r2_t_base.json | cut -c1-200)"
+timeout 900 python -m pytest tests -m gpu -q -k "render_train_end_to_end or level_grouped or hash_backward or fused_train or field_backward" > gpurun_out/r2_pytest_sel.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest_sel.log
