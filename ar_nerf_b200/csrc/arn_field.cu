@@ -240,6 +240,133 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
     if (dirty) flush();
 }
 
+// Hash-grid backward, warp-segmented form (the default).  A warp takes 32 CONSECUTIVE samples and four levels (one 32-byte
+// sector of every sample's dfeat row): each lane owns one sample -- its loads are independent, there is no sequential walk
+// -- and, per level, lanes whose samples fall into the same cell form a segment (samples arrive ordered along their rays, so
+// equal cells are neighbours): a segmented inclusive scan over the 8 corner sums (shuffles; a doubling step is skipped as
+// soon as no segment is longer than its distance) leaves a segment's total in its last lane, which issues the reductions
+// -- aligned x-corner pairs as one red.global.add.v4.f32.  At the fine levels every lane is its own segment and the scan is
+// skipped altogether.  Unlike the run-walking kernel below, whose time is the length of the walk (a launch over ONE level
+// costs 30 us of dependent loads), this kernel's time is its reductions: the levels can be walked group by group
+// (arn_train_set_level_groups) at no extra cost, so a finished group's gradient can leave while the next one is reduced.
+__global__ void __launch_bounds__(256) hash_encode_bw_warp_kernel(const float* __restrict__ xyzs, int64_t n, const int32_t* __restrict__ n_dev, Aabb box,
+                                                                  const __grid_constant__ LevelTable tbl, const float* __restrict__ dfeat,
+                                                                  float2* __restrict__ table_grad, int level0, int nlevels, int img,
+                                                                  int n_main_blocks, WgradReduce red, int part, int parts) {
+    __shared__ float red_part[8][32];
+    if ((int)blockIdx.x >= n_main_blocks) {  // rider blocks: sum of the MLP weight-gradient slabs (independent of the table work)
+        wgrad_reduce_block((int)blockIdx.x - n_main_blocks, red.wpart, red.n_slabs, red.with_rgb, red.dWd, red.dWc, red_part);
+        return;
+    }
+    if (n_dev) n = min(n, (int64_t)*n_dev);
+    const int lane = threadIdx.x & 31;
+    const int q0 = level0 >> 2, nq = ((level0 + nlevels + 3) >> 2) - q0;  // level quads touched by [level0, level0 + nlevels)
+    const int64_t tiles_all = (n + 127) / 128;
+    const int64_t s0 = (tiles_all * part / parts) * 128, s1 = min(n, (tiles_all * (part + 1) / parts) * 128);
+    const int64_t n_items = ((s1 - s0 + 31) / 32) * nq;
+    const int64_t n_warps = ((int64_t)n_main_blocks * blockDim.x) >> 5;
+    for (int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += n_warps) {
+        const int64_t i = s0 + (item / nq) * 32 + lane;
+        const int q = q0 + (int)(item % nq);
+        const bool live = i < s1;
+        float x01[3] = {0.f, 0.f, 0.f};
+        float4 da = make_float4(0.f, 0.f, 0.f, 0.f), db = da;
+        if (live) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const float num = __fsub_rn(xyzs[3 * i + d], box.mn[d]);
+                x01[d] = box.inv[d] != 0.0f ? __fmul_rn(num, box.inv[d]) : __fdiv_rn(num, __fsub_rn(box.mx[d], box.mn[d]));
+            }
+            // levels 4q .. 4q+3 = 16-byte chunks 2q, 2q+1 of the 128-byte row (tile image: permuted inside the row, still one sector)
+            const float4* row = reinterpret_cast<const float4*>(dfeat + i * (2 * ARN_N_LEVELS));
+            da = row[img ? img_chunk128(i, 2u * q) : 2u * q];
+            db = row[img ? img_chunk128(i, 2u * q + 1u) : 2u * q + 1u];
+        }
+        const float2 dl[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y), make_float2(db.z, db.w)};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int l = 4 * q + k;
+            if (l < level0 || l >= level0 + nlevels) continue;  // warp-uniform
+            const float2 d = dl[k];
+            uint32_t g[3]; float w[3];
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                const float pos = __fmaf_rn(tbl.scale[l], x01[e], 0.5f);
+                const float fl = floorf(pos);
+                w[e] = __fsub_rn(pos, fl); g[e] = (uint32_t)(int32_t)fl;
+            }
+            const bool nzero = live && (d.x != 0.0f || d.y != 0.0f);
+            const unsigned any_nz = __ballot_sync(kFull, nzero);
+            if (any_nz == 0u) continue;  // terminated rays: nothing to add for these 32 samples
+            float2 acc[8];
+            {
+                float wt[8];
+                corner_weights(w, wt);
+#pragma unroll
+                for (int c = 0; c < 8; c++) acc[c] = nzero ? make_float2(wt[c] * d.x, wt[c] * d.y) : make_float2(0.f, 0.f);
+            }
+            // segments of equal cells among neighbouring lanes (a dead lane is its own, empty segment)
+            const uint32_t gp0 = __shfl_up_sync(kFull, g[0], 1), gp1 = __shfl_up_sync(kFull, g[1], 1), gp2 = __shfl_up_sync(kFull, g[2], 1);
+            const unsigned livem = __ballot_sync(kFull, live);
+            const bool head = lane == 0 || !live || !((livem >> (lane - 1)) & 1u) || g[0] != gp0 || g[1] != gp1 || g[2] != gp2;
+            const unsigned heads = __ballot_sync(kFull, head);
+            if (heads != kFull) {
+                const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));  // first lane of my segment
+#pragma unroll
+                for (int dist = 1; dist < 32; dist <<= 1) {
+                    const bool take = lane - dist >= start;
+                    if (__ballot_sync(kFull, take) == 0u) break;  // no segment is longer than `dist`
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const float ox = __shfl_up_sync(kFull, acc[c].x, dist), oy = __shfl_up_sync(kFull, acc[c].y, dist);
+                        if (take) { acc[c].x += ox; acc[c].y += oy; }
+                    }
+                }
+            }
+            // the last lane of a segment holds its total
+            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+            const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
+            const unsigned seg_mask = (0xffffffffu >> (31 - lane)) & (0xffffffffu << start);
+            if (tail && (any_nz & seg_mask)) {
+                const uint32_t size = tbl.size[l], res = tbl.res[l], mode = tbl.mode[l];
+                float2* lvl = table_grad + tbl.offset[l];
+                const bool pair_ok = (reinterpret_cast<uintptr_t>(lvl) & 15) == 0;
+                uint32_t idx[8];
+                corner_indices(mode, size, res, g, idx);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const uint32_t a0 = idx[2 * p], a1 = idx[2 * p + 1];
+                    if (pair_ok && (a0 ^ a1) == 1u) {
+                        const bool lo0 = (a0 & 1u) == 0u;
+                        const float2 a = lo0 ? acc[2 * p] : acc[2 * p + 1], b = lo0 ? acc[2 * p + 1] : acc[2 * p];
+                        atomicAdd(reinterpret_cast<float4*>(lvl + (a0 & ~1u)), make_float4(a.x, a.y, b.x, b.y));
+                    } else {
+                        atomicAdd(lvl + a0, acc[2 * p]); atomicAdd(lvl + a1, acc[2 * p + 1]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+static int launch_hash_bw_warp(const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
+                               float* table_grad, int level0, int nlevels, int img, cudaStream_t st, WgradReduce red, int part, int parts) {
+    static int slots = 0;
+    if (!slots) {
+        int dev = 0, n_sm = 0, per_sm = 0;
+        ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        ARN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_encode_bw_warp_kernel, 256, 0));
+        slots = n_sm * (per_sm > 0 ? per_sm : 1);
+    }
+    const int nq = ((level0 + nlevels + 3) >> 2) - (level0 >> 2);
+    const int64_t warps = ((n + 31) / 32) * nq / parts + 1;
+    const int cap = tunable(kTunHashBwBlocks) > 0 ? min(slots, 148 * tunable(kTunHashBwBlocks)) : slots;
+    const int grid = (int)max((int64_t)1, min((int64_t)cap, (warps + 7) / 8));
+    const int riders = red.wpart ? kWgradFloats / 32 : 0;
+    ARN_LAUNCH("hash_encode_bw_warp_kernel", st, hash_encode_bw_warp_kernel<<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, dfeat, (float2*)table_grad, level0, nlevels, img, grid, red, part, parts));
+    return check_launch("hash_encode_bw_warp");
+}
+
 constexpr int kFineLevel0 = 11;  // first level whose cells (NGP geometry, b ~ 1.32-1.66) are crossed in about one marching step
 template <int LPG>
 static int launch_hash_bw_runs(int min_run, const float* xyzs, int64_t n, const int32_t* n_dev, const Aabb& b, const LevelTable& t, const float* dfeat,
@@ -754,7 +881,7 @@ int arn::hash_encode_bw_impl(const float* xyzs, int64_t n, const int32_t* n_dev,
     if (int e = make_box(xyz_min_host, xyz_max_host, b)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     if (table_grad) {
-        const int mode = tunable(kTunHashBwMode);  // 0: one reduction per (sample, level, corner); else: run-aggregating, segment length
+        const int mode = tunable(kTunHashBwMode);  // 0: one reduction per (sample, level, corner); 1: warp-segmented; >= 8: run-walking, shortest run
         if (mode) {
             // arn_train_set_level_groups: the levels are walked group by group, each group one launch, and the caller's event of
             // a group is recorded behind its launch -- the gradient of those levels is final there and may leave (optimizer /
@@ -766,7 +893,9 @@ int arn::hash_encode_bw_impl(const float* xyzs, int64_t n, const int32_t* n_dev,
             const WgradReduce none{nullptr, 0, 0, nullptr, nullptr};
             for (int g = 0; g < ng; g++) {
                 const int l0 = grouped ? lg.begin[g] : 0, l1 = grouped ? lg.begin[g + 1] : ARN_N_LEVELS;
-                if (int e = hash_bw_runs(mode, xyzs, n, n_dev, b, t, dfeat, table_grad, l0, l1 - l0, tile_image, st, g == 0 ? red : none, part, parts)) return e;
+                if (mode == 1) {  // warp-segmented (default)
+                    if (int e = launch_hash_bw_warp(xyzs, n, n_dev, b, t, dfeat, table_grad, l0, l1 - l0, tile_image, st, g == 0 ? red : none, part, parts)) return e;
+                } else if (int e = hash_bw_runs(mode, xyzs, n, n_dev, b, t, dfeat, table_grad, l0, l1 - l0, tile_image, st, g == 0 ? red : none, part, parts)) return e;
                 if (grouped && lg.events[g]) ARN_CUDA(cudaEventRecord((cudaEvent_t)lg.events[g], st));
             }
         } else {

@@ -30,11 +30,15 @@ struct PeerFlags { unsigned long long* p[kMaxRanks]; };
 static long long g_timeout_ticks = (long long)240e9;  // ~120 s at 2 GHz
 static int g_blocks_per_sm = 8;
 static unsigned int* g_err_word = nullptr;
+// device-side copy of the error state: the exchange kernels look at this one (a read of the host word from every block of a
+// 1184-block grid is a PCIe round trip each)
+__device__ unsigned int g_err_dev = 0u;
 __device__ __forceinline__ bool spin_until(const volatile unsigned long long* f, unsigned long long value, long long budget, unsigned int* err, unsigned int code) {
     const long long t0 = clock64();
     while (*f < value) {
         __nanosleep(100);
         if (clock64() - t0 > budget) {
+            atomicExch(&g_err_dev, code);
             if (err) { atomicExch_system(err, code); __threadfence_system(); }
             return false;
         }
@@ -80,44 +84,59 @@ __device__ __forceinline__ uint2 pack_half4_(const float4& a) {
 
 // Elements [lo, lo + 4*n4) of the flat parameter: sum of the ranks' gradients (rank order), Adam (arn_adam_step's
 // arithmetic with inv_gs = 1 / (grad_scale * world)), fp16 result to every rank.  p / m / v point at this rank's slice.
+// U float4 groups per thread and turn, all their peer loads in flight together: with few peers one group per thread leaves
+// the links latency-bound (2 ranks: 16 bytes per thread in flight, 81 us for 23 MB); U * (ranks - 1) >= 8 fills them.
+template <int U, int R>  // R = compile-time bound of n_ranks (register arrays)
 __global__ void __launch_bounds__(256) p2p_adam_exchange_kernel(PeerF32 grads, PeerF16 p16, int n_ranks, int64_t lo, int64_t n4,
                                                                 float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
-                                                                float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_gs,
-                                                                const unsigned int* __restrict__ err) {
+                                                                float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_gs) {
     // a wait in front of this kernel timed out (a peer is gone or far behind): its gradients are not final, update nothing
-    if (err && *reinterpret_cast<const volatile unsigned int*>(err) != 0u) return;
+    if (*reinterpret_cast<const volatile unsigned int*>(&g_err_dev) != 0u) return;
     const float lr_bc1 = lr / bc1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = lo + 4 * i;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 gr[kMaxRanks];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+        float4 gr[U][R];
+        float4 m4[U], v4[U], p4[U];
 #pragma unroll
-        for (int r = 0; r < kMaxRanks; r++)
-            if (r < n_ranks) gr[r] = __ldcs(reinterpret_cast<const float4*>(grads.p[r] + e));  // all peer loads in flight
-        const float4 m4 = __ldcs(m + i), v4 = __ldcs(v + i), p4 = __ldcs(p + i);
+        for (int u = 0; u < U; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i < n4) {
 #pragma unroll
-        for (int r = 0; r < kMaxRanks; r++)
-            if (r < n_ranks) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
-        float pn[4] = {p4.x, p4.y, p4.z, p4.w}, mn[4] = {m4.x, m4.y, m4.z, m4.w}, vn[4] = {v4.x, v4.y, v4.z, v4.w};
-        const float gs[4] = {g.x * inv_gs, g.y * inv_gs, g.z * inv_gs, g.w * inv_gs};
-        bool touched = false;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (gs[k] == 0.0f && mn[k] == 0.0f && vn[k] == 0.0f) continue;  // untouched hash entry: the update is exactly zero
-            touched = true;
-            mn[k] = b1 * mn[k] + (1.0f - b1) * gs[k];
-            vn[k] = b2 * vn[k] + (1.0f - b2) * gs[k] * gs[k];
-            const float denom = sqrtf(vn[k]) / bc2_sqrt + eps;
-            pn[k] = pn[k] - lr_bc1 * (mn[k] / denom);
+                for (int r = 0; r < R; r++)
+                    if (r < n_ranks) gr[u][r] = __ldcs(reinterpret_cast<const float4*>(grads.p[r] + lo + 4 * i));  // all peer loads in flight
+                m4[u] = __ldcs(m + i); v4[u] = __ldcs(v + i); p4[u] = __ldcs(p + i);
+            }
         }
-        if (!touched) continue;  // parameter unchanged: every rank's fp16 copy already holds it
-        __stcs(m + i, make_float4(mn[0], mn[1], mn[2], mn[3])); __stcs(v + i, make_float4(vn[0], vn[1], vn[2], vn[3]));
-        const float4 pnew = make_float4(pn[0], pn[1], pn[2], pn[3]);
-        __stcs(p + i, pnew);
-        const uint2 h = pack_half4_(pnew);
 #pragma unroll
-        for (int r = 0; r < kMaxRanks; r++)
-            if (r < n_ranks) *reinterpret_cast<uint2*>(p16.p[r] + e) = h;
+        for (int u = 0; u < U; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i >= n4) break;
+            const int64_t e = lo + 4 * i;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (r < n_ranks) { g.x += gr[u][r].x; g.y += gr[u][r].y; g.z += gr[u][r].z; g.w += gr[u][r].w; }
+            float pn[4] = {p4[u].x, p4[u].y, p4[u].z, p4[u].w}, mn[4] = {m4[u].x, m4[u].y, m4[u].z, m4[u].w}, vn[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+            const float gs[4] = {g.x * inv_gs, g.y * inv_gs, g.z * inv_gs, g.w * inv_gs};
+            bool touched = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (gs[k] == 0.0f && mn[k] == 0.0f && vn[k] == 0.0f) continue;  // untouched hash entry: the update is exactly zero
+                touched = true;
+                mn[k] = b1 * mn[k] + (1.0f - b1) * gs[k];
+                vn[k] = b2 * vn[k] + (1.0f - b2) * gs[k] * gs[k];
+                const float denom = sqrtf(vn[k]) / bc2_sqrt + eps;
+                pn[k] = pn[k] - lr_bc1 * (mn[k] / denom);
+            }
+            if (!touched) continue;  // parameter unchanged: every rank's fp16 copy already holds it
+            __stcs(m + i, make_float4(mn[0], mn[1], mn[2], mn[3])); __stcs(v + i, make_float4(vn[0], vn[1], vn[2], vn[3]));
+            const float4 pnew = make_float4(pn[0], pn[1], pn[2], pn[3]);
+            __stcs(p + i, pnew);
+            const uint2 h = pack_half4_(pnew);
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (r < n_ranks) *reinterpret_cast<uint2*>(p16.p[r] + e) = h;
+        }
     }
 }
 
@@ -196,11 +215,15 @@ extern "C" ARN_API int arn_p2p_adam_exchange(void* const* peer_grads_host, void*
     const int64_t n4 = count / 4;
     // grid: arn_p2p_set_grid blocks per SM (default 8 = whatever fits); a caller that runs the exchange of one level group
     // beside the hash-grid backward of the next asks for fewer so that both kernels hold SM slots at the same time
-    const int grid = (int)min((int64_t)148 * g_blocks_per_sm, (n4 + 255) / 256);
+    // few ranks: several float4 groups per thread (the unrolled kernels hold their loads in ~140 registers: 128-thread blocks keep
+    // three of them on an SM)
+    const int threads = n_ranks <= 4 ? 128 : 256;
+    const int grid = (int)min((int64_t)148 * g_blocks_per_sm * (256 / threads), (n4 + threads - 1) / threads);
     cudaStream_t st = (cudaStream_t)stream;
-    ARN_LAUNCH("p2p_adam_exchange_kernel", st, p2p_adam_exchange_kernel<<<grid, 256, 0, st>>>(g, h, n_ranks, lo, n4, (float4*)params_slice, (float4*)exp_avg_slice,
-                                                                                             (float4*)exp_avg_sq_slice, lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale,
-                                                                                             g_err_word));
+#define ARN_P2P_EX(U, R) ARN_LAUNCH("p2p_adam_exchange_kernel", st, (p2p_adam_exchange_kernel<U, R><<<grid, threads, 0, st>>>(g, h, n_ranks, lo, n4, (float4*)params_slice, \
+        (float4*)exp_avg_slice, (float4*)exp_avg_sq_slice, lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale)))
+    if (n_ranks <= 2) ARN_P2P_EX(4, 2); else if (n_ranks <= 4) ARN_P2P_EX(2, 4); else ARN_P2P_EX(1, 8);
+#undef ARN_P2P_EX
     return check_launch("p2p_adam_exchange");
 }
 

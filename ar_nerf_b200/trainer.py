@@ -124,10 +124,12 @@ class FusedAdam:
             for i, (p, cache, m, v, st) in enumerate(self.items):
                 if st is None:
                     if group_events is not None:
-                        # the MLP gradients are final behind the first group's event: their all-reduce starts there
+                        # the MLP gradients are final behind the first group's event: their all-reduce starts there (a large
+                        # parameter that is NOT sharded -- shard_optimizer=False -- is final behind the last one)
                         if self.small_stream is None:
                             self.small_stream, self.small_done = torch.cuda.Stream(device=p.device), torch.cuda.Event()
-                        self.small_stream.wait_event(group_events[0])
+                        grouped = self.group_bounds and p.numel() == self.group_bounds[-1]
+                        self.small_stream.wait_event(group_events[-1] if grouped else group_events[0])
                         with torch.cuda.stream(self.small_stream):
                             pending[i] = dist.all_reduce(p.grad, group=self.small_group, async_op=True)
                     else:

@@ -41,9 +41,10 @@ int64_t arn_launch_count(void);
  * line per kernel into buf_host and clears the log.  Keep it disabled during CUDA-graph capture. */
 /* Kernel-variant switch for A/B measurements and for the tests that hold the variants to each other; every variant of
  * a kernel computes the same results.  Names: "march_warp" (1 = warp-per-ray window march, 0 = thread-per-ray loop),
- * "hash_bw_mode" (8/16/32/64 = run-aggregating hash-grid backward, the value being the SHORTEST run of consecutive samples a
- * lane group takes -- the samples are cut into equal runs over one resident wave of blocks; 0 = one reduction per
- * sample and corner), "hash_bw_blocks" (blocks per SM of that wave, 0 = what the occupancy calculator allows), "adam_vec" (1 = 128-bit Adam kernel), "pipeline_parts" (field evaluations of >= 64 K samples are split
+ * "hash_bw_mode" (8/16/32/64 = run-walking hash-grid backward, the value being the SHORTEST run of consecutive samples a lane
+ * group walks -- the samples are cut into equal runs over one resident wave of blocks; 16 is the default; 1 = warp-segmented
+ * backward: a lane per sample, equal cells of neighbouring lanes merged by a segmented warp scan -- measured 98 vs 79 us on the
+ * W1 batch; 0 = one reduction per sample and corner), "hash_bw_blocks" (blocks per SM of that wave, 0 = what the occupancy calculator allows), "adam_vec" (1 = 128-bit Adam kernel), "pipeline_parts" (field evaluations of >= 64 K samples are split
  * into this many consecutive tile ranges, hash-grid and MLP kernels of neighbouring ranges overlapped on two streams; default
  * 1 = off: measured on B200 the overlap loses to the per-launch fixed costs, 0.384 / 0.409 / 0.469 ms per step at 1 / 2 / 3). */
 int arn_set_tunable(const char* name, int value);

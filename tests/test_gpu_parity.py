@@ -575,8 +575,9 @@ def test_hash_encode_linearity_full_size(vren):
 
 @pytest.mark.parametrize("kind", ["W1", "W3"])
 def test_hash_backward_variants_agree(kind, w1, w3, vren):
-    """Run-aggregating hash-grid backward (segment lengths 8..64) against the one-reduction-per-corner kernel on marched
-    samples (consecutive samples of a ray share cells, which is what the aggregation exploits) and against the oracle."""
+    """Aggregating hash-grid backward kernels -- warp-segmented (default) and run-walking (shortest runs 8..64) -- against the
+    one-reduction-per-corner kernel on marched samples (consecutive samples of a ray share cells, which is what the
+    aggregation exploits) and against the oracle; also walked level group by level group (arn_train_set_level_groups)."""
     from ar_nerf_b200 import _lib
     from ar_nerf_b200.field import HashGeometry
     w = workload(kind, w1, w3)
@@ -591,22 +592,38 @@ def test_hash_backward_variants_agree(kind, w1, w3, vren):
     mn = (_lib.F * 3)(*[-w.scale] * 3); mx = (_lib.F * 3)(*[w.scale] * 3)
     res = {}
     try:
-        for mode in (0, 8, 16, 32, 64):
+        for mode in (0, 1, 8, 16, 32, 64):
             _lib.set_tunable("hash_bw_mode", mode)
             tg = torch.zeros(geo.total * 2, device=dev())
             _lib.call("arn_hash_encode_bw", xyzs.data_ptr(), n, mn, mx, geo.c_levels, None, dfeat.data_ptr(), tg.data_ptr(), None, _lib.stream())
             res[mode] = N(tg)
+        # level group by level group (run-walking kernel, then the warp-segmented one): only the launch shapes differ
+        import ctypes as C
+        _lib.set_tunable("hash_bw_mode", 16)
+        for groups in ([0, 11, 16], [0, 3, 5, 6, 13, 16], list(range(17))):
+            _lib.call("arn_train_set_level_groups", len(groups) - 1, (C.c_int * len(groups))(*groups), None)
+            tg = torch.zeros(geo.total * 2, device=dev())
+            _lib.call("arn_hash_encode_bw", xyzs.data_ptr(), n, mn, mx, geo.c_levels, None, dfeat.data_ptr(), tg.data_ptr(), None, _lib.stream())
+            res[tuple(groups)] = N(tg)
+        _lib.set_tunable("hash_bw_mode", 1)
+        _lib.call("arn_train_set_level_groups", 3, (C.c_int * 4)(0, 6, 11, 16), None)
+        tg = torch.zeros(geo.total * 2, device=dev())
+        _lib.call("arn_hash_encode_bw", xyzs.data_ptr(), n, mn, mx, geo.c_levels, None, dfeat.data_ptr(), tg.data_ptr(), None, _lib.stream())
+        res[(0, 6, 11, 16, "warp")] = N(tg)
     finally:
         _lib.set_tunable("hash_bw_mode", 16)
+        _lib.call("arn_train_set_level_groups", 0, None, None)
     x01 = (N(xyzs) - np.float32(-w.scale)) / (np.float32(w.scale) - np.float32(-w.scale))
     o_geo = oracle.HashGeometry(per_level_scale=geo.per_level_scale)
     o_tg, _ = oracle.hash_encode_bw(x01.astype(np.float32), o_geo, np.zeros(geo.total * 2, np.float16), N(dfeat))
     l1, _ = oracle.hash_encode_bw(x01.astype(np.float32), o_geo, np.zeros(geo.total * 2, np.float16), np.abs(N(dfeat)))
     l1 = l1.reshape(-1)
-    for mode in (8, 16, 32, 64):
+    for mode in (1, 8, 16, 32, 64):  # 1 = warp-segmented, >= 8 = run-walking with that shortest run (16 = the default)
         assert_sum(res[mode], res[0], l1, C_ORDER, rtol=0.0, what=f"hash bw runs seg {mode} vs per-sample")
         assert_sum(res[mode], o_tg.reshape(-1), l1, C_ORDER, what=f"hash bw runs seg {mode} vs oracle")
         assert not res[mode][l1 == 0].any()
+    for key in [k for k in res if isinstance(k, tuple)]:
+        assert_sum(res[key], res[1], l1, C_ORDER, rtol=0.0, what=f"hash bw, level groups {key} vs one launch")
 
 
 def test_adam_step_vs_torch(vren):

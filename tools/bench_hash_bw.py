@@ -41,10 +41,10 @@ def run(iters=10, cold=True):
 
 
 for blocks in (0, 2, 3):
-    for mode in (8, 16, 32):
+    for mode in (1, 16):
         _lib.set_tunable("hash_bw_mode", mode); _lib.set_tunable("hash_bw_blocks", blocks)
         print(f"blocks/SM {blocks} min_run {mode:3d}: cold L2 {run():7.1f} us   warm {run(cold=False):7.1f} us")
-_lib.set_tunable("hash_bw_mode", 16); _lib.set_tunable("hash_bw_blocks", 0)
+_lib.set_tunable("hash_bw_mode", 1); _lib.set_tunable("hash_bw_blocks", 0)
 for groups in ([0, 16], [0, 11, 16], [0, 11, 14, 16], [0, 8, 11, 13, 16], [0, 8, 16]):
     arr = (C.c_int * len(groups))(*groups)
     _lib.call("arn_train_set_level_groups", len(groups) - 1, arr, None)

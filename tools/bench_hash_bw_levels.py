@@ -42,11 +42,11 @@ def per_group(groups, iters=7):
     return [sorted(a)[len(a) // 2] for a in acc]
 
 
-for mode in (8, 16, 64):
+for mode in (1, 16):
     _lib.set_tunable("hash_bw_mode", mode)
     t = per_group(list(range(17)))
     print(f"min_run {mode}: per level us:", " ".join(f"{x:5.1f}" for x in t), " sum", round(sum(t), 1))
-_lib.set_tunable("hash_bw_mode", 16)
+_lib.set_tunable("hash_bw_mode", 1)
 for groups in ([0, 16], [0, 11, 16], [0, 8, 16], [0, 4, 8, 12, 16], [0, 11, 14, 16]):
     t = per_group(groups)
     print(f"groups {groups}: us per group:", " ".join(f"{x:5.1f}" for x in t), " sum", round(sum(t), 1))
