@@ -25,8 +25,11 @@ class _Tonemapper(nn.Module):
         self.params = nn.Parameter(p)
 
     def forward(self, x):
+        # tiny-cuda-nn pads the 1-wide input to the 16 columns of W1 with ONES (the padded columns act as a bias) and reads
+        # output 0 of the 16-wide last layer; fp16 weights / activations, fp32 accumulate
         w1 = self.params[:1024].view(64, 16).half().float(); w2 = self.params[1024:].view(16, 64).half().float()
-        hid = torch.relu(x.float() @ w1[:, :1].T).half().float()
+        xin = torch.cat([x.float(), torch.ones(x.shape[0], 15, dtype=torch.float32, device=x.device)], 1).half().float()
+        hid = torch.relu(xin @ w1.T).half().float()
         return torch.sigmoid(hid @ w2[:1].T)
 
 

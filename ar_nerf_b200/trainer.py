@@ -272,11 +272,13 @@ class NGPTrainer:
         st.direct_grad = True
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
-        # Level-major hash-grid backward (arn_train_set_level_groups): the optimizer / the multi-GPU exchange of a level group
-        # starts where that group's gradient is final, beside the backward of the next group.  Coarse levels first: they cost the
-        # backward least per byte of gradient (consecutive samples of a ray share cells), so the exchange -- the longer of the two
-        # pipelines -- starts early.  ARN_LEVEL_GROUPS="0,16" switches the pipelining off.
-        default_groups = "0,8,11,13,16" if self.world > 1 else os.environ.get("ARN_LEVEL_GROUPS_1GPU", "0,16")
+        # Level-major hash-grid backward (arn_train_set_level_groups): the optimizer / the multi-GPU exchange of a level group can
+        # start where that group's gradient is final, beside the backward of the next group.  OFF by default ("0,16"): measured
+        # on B200 the split costs more than the overlap returns -- the backward's levels overlap inside ONE launch (16 single-
+        # level launches take 438 us, the fused launch 79 us), so a second launch adds ~29 us: 8 GPUs 0.429 ms per step
+        # unsplit, 0.462 with "0,11,16"; 2 GPUs 0.376 / 0.405; 1 GPU (Adam per group) 0.332 / 0.352.
+        # ARN_LEVEL_GROUPS="0,11,16" switches it on.
+        default_groups = "0,16"
         lv = [int(x) for x in os.environ.get("ARN_LEVEL_GROUPS", default_groups).split(",")]
         self.level_groups = lv if (self.fused and len(lv) > 2 and lv[0] == 0 and lv[-1] == 16) else None
         bounds = None
@@ -289,7 +291,11 @@ class NGPTrainer:
             for e in self._lg_events:
                 e.record()  # creates the CUDA event handles
             self._lg_handles = (C.c_void_p * (len(lv) - 1))(*[e.cuda_event for e in self._lg_events])
-        self.opt = FusedAdam([(model.xyz_encoder.params, st.cache_xyz), (model.rgb_net.params, st.cache_rgb)], lr,
+        # every parameter of the model is optimised, as train.py:141-146 does (all named parameters except the pose refinement's
+        # dR / dT): in HDR mode that includes the three tonemapper nets (no fp16 working copy: they are evaluated by torch)
+        main_params = {id(model.xyz_encoder.params), id(model.rgb_net.params)}
+        extra = [(p, None) for n_, p in model.named_parameters() if id(p) not in main_params and n_ not in ('dR', 'dT')]
+        self.opt = FusedAdam([(model.xyz_encoder.params, st.cache_xyz), (model.rgb_net.params, st.cache_rgb)] + extra, lr,
                              world=self.world, rank=self.rank, shard_min_numel=(1 << 20) if shard_optimizer else (1 << 62),
                              exchange=exchange, group_bounds=bounds)
         self.global_step = 0
