@@ -66,6 +66,7 @@ SIGNATURES = {
     "arn_last_error": [],
     "arn_launch_count": [],
     "arn_set_tunable": [C.c_char_p, I],
+    "arn_dbg_l2_red_peak": [P, L, L, P],
     "arn_p2p_alloc": [C.POINTER(C.c_void_p), L],
     "arn_p2p_free": [P],
     "arn_p2p_export": [P, C.c_char_p],

@@ -1052,6 +1052,25 @@ __global__ void __launch_bounds__(256) hash_encode_bw_range_kernel(const float* 
 }
 }  // namespace arn
 
+// Measured roof of the hash-grid backward (bench.py "l2_reduction"): red.global.add.v4.f32 to pseudo-random 16-byte aligned
+// addresses of an `n_floats` buffer (46 MB = the table gradient: L2-resident), `per_thread` reductions per thread, no other
+// work -- the rate at which the L2 retires scattered 16-byte reductions.
+__global__ void __launch_bounds__(256) l2_red_peak_kernel(float* __restrict__ buf, uint32_t n_vec4, int per_thread) {
+    uint32_t x = ((uint32_t)blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int k = 0; k < per_thread; k++) {
+        x = x * 1664525u + 1013904223u;  // LCG: a fresh 16-byte slot per reduction, no locality
+        const uint32_t slot = (uint32_t)(((uint64_t)(x >> 4) * n_vec4) >> 28);
+        atomicAdd(reinterpret_cast<float4*>(buf) + (slot < n_vec4 ? slot : 0u), make_float4(1.f, 1.f, 1.f, 1.f));
+    }
+}
+extern "C" ARN_API int arn_dbg_l2_red_peak(float* buf, int64_t n_floats, int64_t n_reductions, arn_stream_t stream) {
+    ARN_REQUIRE(buf && n_floats >= 1024 && n_reductions > 0 && ((uintptr_t)buf & 15) == 0, "bad arguments");
+    const int per_thread = 16;
+    const int64_t threads = (n_reductions + per_thread - 1) / per_thread;
+    ARN_LAUNCH("l2_red_peak_kernel", (cudaStream_t)stream, l2_red_peak_kernel<<<ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(buf, (uint32_t)(n_floats / 4), per_thread));
+    return check_launch("l2_red_peak");
+}
+
 // Diagnostics entry (tools/): mode 0 = per-(sample,level) kernel on levels [level0, level0+nlevels), mode = 8/16/32/64 = run-aggregating
 // kernel with that segment length.
 extern "C" ARN_API int arn_dbg_hash_bw(const float* xyzs, int64_t n, const float* xyz_min_host, const float* xyz_max_host, arn_levels_t levels,

@@ -16,6 +16,8 @@
 //     layer's A tile; the same shared-memory tile is handed to the TMA engine as the saved activation.
 //   Numeric contract: fp16 operands, fp32 accumulate -- identical rounding points to the simt
 //   kernels and the oracle; only the accumulation order inside the MMA differs.
+#include <mutex>
+
 #include "arn_common.cuh"
 #include "arn_field.cuh"
 #include "arn_tc.cuh"
@@ -68,39 +70,46 @@ constexpr int kFwSmemTile64 = 128 * 128;   // 128 rows x 64 halves
 // tensor pipe idles ~90 % of the time with two tiles in flight per SM).  A buffer is overwritten two layers after it was
 // written; its bulk store (issued one layer after the write) has then had a whole layer to read it, and the thread that
 // issues the MMAs waits for that read before it issues the layer whose epilogue overwrites the buffer.
-constexpr int kFwF0 = kWimgBytes, kFwF1 = kFwF0 + kFwSmemTile32, kFwA = kFwF1 + kFwSmemTile32, kFwB = kFwA + kFwSmemTile64;
-constexpr int kFwSmemBytes = kFwB + kFwSmemTile64 + 1024;  // + alignment slack
-constexpr int kFwCtasPerSm = 3;
+// W warpgroups per CTA share ONE weight image; every warpgroup owns the four tile buffers below and walks its own tiles:
+// W = 4 (512 threads, one CTA per SM: 20 + 4 x 48 KB, all 512 TMEM columns) keeps four tiles in flight on an SM instead of
+// the three that three 68 KB CTAs give; W = 1 for launches too small to fill 4 x n_sm tiles.
+constexpr int kFwF0 = 0, kFwF1 = kFwF0 + kFwSmemTile32, kFwA = kFwF1 + kFwSmemTile32, kFwB = kFwA + kFwSmemTile64;  // offsets inside a warpgroup's block
+constexpr int kFwWgBytes = kFwB + kFwSmemTile64;
+template <int W> constexpr int fw_smem_bytes() { return kWimgBytes + W * kFwWgBytes + 1024; }  // + alignment slack
+constexpr int kFwCtasPerSm = 3;  // W = 1
 
-__global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __restrict__ feat, const float* __restrict__ dirs, int64_t n,
+template <int W>
+__global__ void __launch_bounds__(128 * W, 1) field_mlp_fw_tc_kernel(const __half* __restrict__ feat, const float* __restrict__ dirs, int64_t n,
                                                               const int32_t* __restrict__ n_dev, const uint8_t* __restrict__ wimg, int rgb_act, int with_rgb,
                                                               __half* __restrict__ hid, float* __restrict__ h, float* __restrict__ sigmas,
                                                               __half* __restrict__ in32, __half* __restrict__ hid1, __half* __restrict__ hid2,
                                                               float* __restrict__ rgbs, int part, int parts) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[4];
+    __shared__ __align__(8) uint64_t bars[1 + 3 * W];  // weights | per warpgroup: mma, f0, f1
     __shared__ uint32_t tmem_slot;
     if (n_dev) n = min(n, (int64_t)*n_dev);  // fused step: the sample count lives on the device
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzled tiles need 1024-byte alignment
+    const uint32_t base0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzled tiles need 1024-byte alignment
+    const int wg = threadIdx.x >> 7, tid = threadIdx.x & 127, warp = tid >> 5;
+    const uint32_t sW = base0;
+    const uint32_t base = base0 + kWimgBytes + wg * kFwWgBytes;  // this warpgroup's F0 F1 A B
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sW = base;
-    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]), bar_f0 = smem_u32(&bars[2]), bar_f1 = smem_u32(&bars[3]);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1 + 3 * wg]), bar_f0 = smem_u32(&bars[2 + 3 * wg]), bar_f1 = smem_u32(&bars[3 + 3 * wg]);
 
-    if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_mma, 1); mbar_init(bar_f0, 1); mbar_init(bar_f1, 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 1 + 3 * W; k++) mbar_init(smem_u32(&bars[k]), 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 128 * W);
     fence_before_sync(); __syncthreads(); fence_after_sync();
-    const uint32_t tmem = tmem_slot;
+    const uint32_t tmem = tmem_slot + 128 * wg;  // this warpgroup's 128 columns
     const uint32_t wbytes = with_rgb ? kWimgBytes : kWimgC1;
     // this launch owns the tiles [t_begin, n_tiles) of the sample list (one of `parts` consecutive ranges: the host pipelines
     // the hash-grid forward of range p+1 on a second stream under the MLP of range p)
     const int64_t n_tiles_all = (n + 127) / 128;
     const int64_t t_begin = n_tiles_all * part / parts, n_tiles = n_tiles_all * (part + 1) / parts;
-    const int64_t tile0 = t_begin + blockIdx.x;
-    if (tid == 0) {
-        mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w);
-        if (tile0 < n_tiles) { mbar_expect_tx(bar_f0, kFwSmemTile32); bulk_g2s(base + kFwF0, feat + tile0 * 128 * 32, kFwSmemTile32, bar_f0); }
-    }
+    const int64_t tile0 = t_begin + (int64_t)blockIdx.x * W + wg, tile_stride = (int64_t)gridDim.x * W;
+    if (threadIdx.x == 0) { mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w); }
+    if (tid == 0 && tile0 < n_tiles) { mbar_expect_tx(bar_f0, kFwSmemTile32); bulk_g2s(base + kFwF0, feat + tile0 * 128 * 32, kFwSmemTile32, bar_f0); }
     mbar_wait(bar_w, 0);
 
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes; lane == sample row
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
     // free_buf: the epilogue of this layer overwrites a buffer that an earlier bulk store may still be reading; the issuing
     // thread waits for those reads BEFORE it issues the MMAs, and the other threads cannot write before the MMAs commit.
     auto issue_only = [&](uint32_t dcol, uint64_t a, uint64_t b, uint32_t idesc, int ksteps, bool free_buf) {
-        fence_before_sync(); fence_async_smem(); __syncthreads();
+        fence_before_sync(); fence_async_smem(); wg_sync(1 + wg);
         if (tid == 0) {
             fence_after_sync();
             if (free_buf) bulk_wait_read<0>();
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
     };
     fetch_dir(tile0);
     int it = 0;
-    for (int64_t tile = tile0; tile < n_tiles; tile += gridDim.x, it++) {
+    for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, it++) {
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
         const int buf = it & 1;
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
         if (tid == 0) {
             // F[buf^1] held the previous tile's features and then its h staging tile, whose bulk store must have read it
             bulk_wait_read<0>();
-            const int64_t next = tile + gridDim.x;
+            const int64_t next = tile + tile_stride;
             if (next < n_tiles) {
                 const uint32_t bf = buf ? bar_f0 : bar_f1;
                 mbar_expect_tx(bf, kFwSmemTile32);
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
         }
         if (!with_rgb) {
             if (h) {
-                fence_async_smem(); __syncthreads();
+                fence_async_smem(); wg_sync(1 + wg);
                 if (tid == 0) { bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64); bulk_commit(); }
             }
             continue;
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
         // ---- colour layer 3 -> rgb
         issue_only(0, aH2, bC3, kI16, 4, false);
         if (tid == 0 && hid) { bulk_s2g(hid2 + tile * 128 * 64, base + kFwH2, kFwSmemTile64); bulk_commit(); }
-        fetch_dir(tile + gridDim.x);
+        fetch_dir(tile + tile_stride);
         wait_mma();
         {
             float ov[16];
@@ -234,8 +243,11 @@ __global__ void __launch_bounds__(128) field_mlp_fw_tc_kernel(const __half* __re
     }
     if (tid == 0) bulk_wait_read<0>();
     fence_before_sync(); __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (threadIdx.x < 32) tmem_dealloc(tmem_slot, 128 * W);
 }
+
+// One-time, per device: dynamic shared memory limits of every instance of the two kernels.  Returns the SM count.
+int mlp_device_setup(int* n_sm_out);
 
 }  // namespace arn
 
@@ -266,17 +278,16 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
     if (with_rgb) ARN_REQUIRE(params_rgb_f16 && rgbs && (!ws.hid || (ws.in32 && ws.hid1 && ws.hid2)), "null pointer (colour branch)");
     cudaStream_t st = (cudaStream_t)stream;
     const __half* pxyz = (const __half*)params_xyz_f16;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0; ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
-        ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
+    int n_sm = 0;
+    if (int e = arn::mlp_device_setup(&n_sm)) return e;
     // Pipelined over `parts` consecutive ranges of tiles: the hash-grid forward (gathers out of L2) of range p+1 runs on
     // a second stream under the MLP (tensor core + HBM stores) of range p -- the two kernels stress different units.
     const int64_t n_tiles = (n + 127) / 128;
     const int parts = pipeline_parts(n);
-    const int grid = (int)max((int64_t)1, min((int64_t)n_sm * kFwCtasPerSm, (n_tiles + parts - 1) / parts));
+    // four warpgroups per CTA, one CTA per SM, when the launch has the tiles to fill that; else one warpgroup per CTA
+    const bool wide = (n_tiles + parts - 1) / parts >= (int64_t)n_sm * 4 && (tunable(kTunMlpWide) & 1) != 0;
+    const int wgs = wide ? 4 : 1;
+    const int grid = (int)max((int64_t)1, min((int64_t)n_sm * (wide ? 1 : kFwCtasPerSm), ((n_tiles + parts - 1) / parts + wgs - 1) / wgs));
     PipeStreams* ps = nullptr;
     if (parts > 1) {
         if (int e = pipe_streams(&ps)) return e;
@@ -293,9 +304,11 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
     }
     for (int p = 0; p < parts; p++) {
         if (parts > 1) ARN_CUDA(cudaStreamWaitEvent(st, ps->ev[p], 0));
-        ARN_LAUNCH("field_mlp_fw_tc_kernel", st, field_mlp_fw_tc_kernel<<<grid, 128, kFwSmemBytes, st>>>(
-            (const __half*)ws.feat, dirs, n, n_dev, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, (__half*)ws.hid, ws.h, sigmas,
-            (__half*)ws.in32, (__half*)ws.hid1, (__half*)ws.hid2, rgbs, p, parts));
+#define ARN_FW_ARGS (const __half*)ws.feat, dirs, n, n_dev, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, (__half*)ws.hid, ws.h, sigmas, \
+            (__half*)ws.in32, (__half*)ws.hid1, (__half*)ws.hid2, rgbs, p, parts
+        if (wide) ARN_LAUNCH("field_mlp_fw_tc_kernel", st, (field_mlp_fw_tc_kernel<4><<<grid, 512, fw_smem_bytes<4>(), st>>>(ARN_FW_ARGS)));
+        else ARN_LAUNCH("field_mlp_fw_tc_kernel", st, (field_mlp_fw_tc_kernel<1><<<grid, 128, fw_smem_bytes<1>(), st>>>(ARN_FW_ARGS)));
+#undef ARN_FW_ARGS
         if (int e = check_launch("field_mlp_fw_tc")) return e;
     }
     return ARN_OK;
@@ -304,22 +317,27 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
 namespace arn {
 using namespace tc;
 // =====================================================================================================================
-// Backward.  Same CTA shape (128 threads = 128 sample rows, persistent over tiles, 2 CTAs per SM).
+// Backward.  W warpgroups of 128 threads per CTA, each walking its own sequence of 128-sample tiles (thread t of a warpgroup
+// = sample row t), persistent; ONE CTA per SM (W = 3: 384 threads) or, for launches too small to fill that, W = 1.
 // Per layer, walking the net backwards, ONE commit covers two MMA chains that read the same two shared-memory tiles:
 //   dgrad   R[128 x in]  = G (K-major A: rows = samples, K = out)  x  W (MN-major B straight from the forward's weight image)
 //   wgrad   dW[out x in] += G^T X : A = G as MN-major (M = out), B = X as MN-major (N = in), K = the 128 samples of the tile
-// The five weight-gradient accumulators stay in TENSOR MEMORY for the whole kernel (160 columns) and are flushed once
-// per CTA; layers with 16 outputs accumulate the transposed product (M = in = 64, N = 16).
+// The five weight-gradient accumulators stay in TENSOR MEMORY for the whole kernel (160 columns, zero-initialised with
+// tcgen05.st, SHARED by the CTA's warpgroups: the tensor pipe executes their MMAs in issue order) and are flushed once per
+// CTA; layers with 16 outputs accumulate the transposed product (M = in = 64, N = 16).
 // Thread t then pulls row t of R with tcgen05.ld, applies the ReLU mask of its own activation row, scales/rounds to
 // fp16 and writes the next G tile.  Rounding points are those of the simt kernel / oracle (fp16 G, fp32 accumulate).
 // The saved activation tiles X (hid2, hid1, in32, hid, feat -- in this order, 5 per sample tile) stream through a ring of
-// three 16 KB slots: one thread issues each tile as a single bulk (TMA) copy two layers before its MMA, as soon as the
-// slot's previous tile has been consumed; the layer's threads only wait on the slot's mbarrier.  dfeat leaves the same way.
-// TMEM map: [0,64) R | [64,80) dWc3^T | [80,144) dWc2 | [144,176) dWc1 | [176,192) dWd2^T | [192,224) dWd1   (256 allocated)
-constexpr int kBwGa = kWimgBytes, kBwGb = kBwGa + kFwSmemTile64, kBwX0 = kBwGb + kFwSmemTile64;
-constexpr int kBwSmemBytes = kBwX0 + 3 * kFwSmemTile64 + 1024;
+// three 16 KB slots per warpgroup: one thread issues each tile as a single bulk (TMA) copy two layers before its MMA, as
+// soon as the slot's previous tile has been consumed; the layer's threads only wait on the slot's mbarrier.  G lives in ONE
+// 16 KB buffer (the MMA that read G_k has completed before the epilogue writes G_k+1); dfeat is staged in the ring slot the
+// tile's last X (feat) has just left and stored by TMA.  Shared memory: weight image 20 KB + W x 64 KB; the latency chain
+// of a tile (issue -> commit -> tcgen05.ld -> mask -> store, five times) is hidden by the W tiles in flight on the SM --
+// three instead of the two that two 100 KB CTAs gave (the kernel is latency-bound: tensor pipe 13 %, DRAM 31 %).
+// TMEM map: [64 wg, 64 wg + 64) R of warpgroup wg | then dWc3^T (16) dWc2 (64) dWc1 (32) dWd2^T (16) dWd1 (32)
+constexpr int kBwWgBytes = 4 * kFwSmemTile64;  // per warpgroup: G | X0 X1 X2
+template <int W> constexpr int bw_smem_bytes() { return kWimgBytes + W * kBwWgBytes + 1024; }
 constexpr int kMaxBwCtas = ARN_FIELD_SCRATCH_SLABS;
-constexpr uint32_t kColR = 0, kColC3 = 64, kColC2 = 80, kColC1 = 144, kColD2 = 176, kColD1 = 192;
 
 // t[NQ*16] = this thread's row of R; g = fp16(relu'(x) * t) written as a RB=128 row of `gtile`; mask from row of `xtile`.
 __device__ __forceinline__ void epilogue_mask64(uint32_t taddr, const uint8_t* xtile, uint8_t* gtile, int row) {
@@ -341,7 +359,8 @@ __device__ __forceinline__ void epilogue_mask64(uint32_t taddr, const uint8_t* x
     }
 }
 
-__global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const int32_t* __restrict__ n_dev, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
+template <int W>
+__global__ void __launch_bounds__(128 * W, 1) __maxnreg__(W == 3 ? 128 : 192) field_mlp_bw_tc_kernel(int64_t n, const int32_t* __restrict__ n_dev, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
                                                               const float* __restrict__ rgbs, const float* __restrict__ sigmas,
                                                               const __half* __restrict__ feat, const __half* __restrict__ hid,
                                                               const __half* __restrict__ in32, const __half* __restrict__ hid1,
@@ -349,34 +368,46 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                                                               int with_rgb, float loss_scale, float exp_hi, float* __restrict__ dfeat, float* __restrict__ wpart,
                                                               int part, int parts, int slab0) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[5];
+    __shared__ __align__(8) uint64_t bars[1 + 4 * W];  // weights | per warpgroup: mma, x0, x1, x2
     __shared__ uint32_t tmem_slot;
+    constexpr uint32_t kTmemCols = W == 1 ? 256 : 512;
+    constexpr uint32_t kColW = 64 * W, kColC3 = kColW, kColC2 = kColW + 16, kColC1 = kColW + 80, kColD2 = kColW + 112, kColD1 = kColW + 128;
     if (n_dev) n = min(n, (int64_t)*n_dev);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sW = base, sGa = base + kBwGa, sGb = base + kBwGb;
-    uint8_t* pGa = sm + kBwGa; uint8_t* pGb = sm + kBwGb;
-    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wg = threadIdx.x >> 7, tid = threadIdx.x & 127, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sW = base;
+    const uint32_t sWg = base + kWimgBytes + wg * kBwWgBytes;      // this warpgroup's G | X0 X1 X2
+    uint8_t* pWg = sm + kWimgBytes + wg * kBwWgBytes;
+    const uint32_t sG = sWg; uint8_t* pG = pWg;
+    constexpr int kX0 = kFwSmemTile64;
+    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1 + 4 * wg]);
+    auto bar_x = [&](int slot) { return smem_u32(&bars[2 + 4 * wg + slot]); };
 
-    if (tid == 0) {
-        mbar_init(bar_w, 1); mbar_init(bar_mma, 1);
-        for (int k = 0; k < 3; k++) mbar_init(smem_u32(&bars[2 + k]), 1);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 1 + 4 * W; k++) mbar_init(smem_u32(&bars[k]), 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kTmemCols);
     fence_before_sync(); __syncthreads(); fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes; lane == sample row of the warpgroup's tile
+    // zero the weight-gradient accumulators (every warpgroup's MMAs accumulate into them from its first tile on)
+    if (wg == 0) {
+#pragma unroll
+        for (int c = 0; c < 160; c += 16) tmem_st16_fill(trow + kColW + c, 0u);
+        tmem_st_wait();
+    }
     const uint32_t wbytes = with_rgb ? kWimgBytes : kWimgC1;
-    // tiles [t_begin, n_tiles) of the sample list (see the forward kernel)
+    // tiles [t_begin, n_tiles) of the sample list (see the forward kernel); warpgroup wg of CTA b takes t_begin + b W + wg, ...
     const int64_t n_tiles_all = (n + 127) / 128;
     const int64_t t_begin = n_tiles_all * part / parts, n_tiles = n_tiles_all * (part + 1) / parts;
-    const int64_t tile0 = t_begin + blockIdx.x;
+    const int64_t tile0 = t_begin + (int64_t)blockIdx.x * W + wg, tile_stride = (int64_t)gridDim.x * W;
 
-    // ---- activation-tile stream: load j of this CTA = tile (j / L) of its tile sequence, kind (j % L); slot j % 3
+    // ---- activation-tile stream: load j of this warpgroup = tile (j / L) of its tile sequence, kind (j % L); slot j % 3
     const int L = with_rgb ? 5 : 2;
-    auto issue_load = [&](int64_t j) {  // thread 0 only
-        const int64_t t = tile0 + (j / L) * gridDim.x;
+    auto issue_load = [&](int64_t j) {  // the warpgroup's thread 0 only
+        const int64_t t = tile0 + (j / L) * tile_stride;
         if (t >= n_tiles) return;
         const int kind = with_rgb ? (int)(j % 5) : 3 + (int)(j % 2);
         const __half* src; uint32_t bytes;
@@ -388,36 +419,34 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
             default: src = feat + t * 128 * 32; bytes = kFwSmemTile32; break;
         }
         const int slot = (int)(j % 3);
-        const uint32_t bx = smem_u32(&bars[2 + slot]);
-        mbar_expect_tx(bx, bytes);
-        bulk_g2s(base + kBwX0 + slot * kFwSmemTile64, src, bytes, bx);
+        mbar_expect_tx(bar_x(slot), bytes);
+        bulk_g2s(sWg + kX0 + slot * kFwSmemTile64, src, bytes, bar_x(slot));
     };
-    if (tid == 0) {
-        mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w);
-        issue_load(0); issue_load(1);
-    }
+    if (threadIdx.x == 0) { mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w); }
+    if (tid == 0) { issue_load(0); issue_load(1); }
+    fence_before_sync(); __syncthreads(); fence_after_sync();  // the zeroed accumulators are visible to every issuing thread
     mbar_wait(bar_w, 0);
 
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
     const float inv_scale = 1.0f / loss_scale;
     const float exp_lo = 1.0f / exp_hi;
-    uint32_t acc = 0;  // 0 on the CTA's first tile: the wgrad accumulators are initialised by the MMA itself
     int64_t j = 0;     // index of the next activation tile to be consumed
 
     // One layer step: wait for the layer's X tile, publish the G tile, then wgrad (K = 128 samples, 8 MMAs) + dgrad
     // (K = out, ksteps MMAs) under one commit.  After the barrier the slot of the PREVIOUS layer's X tile is free (its MMA
-    // has completed and every thread is past its epilogue), so thread 0 refills it with the tile two layers ahead.
+    // has completed and every thread is past its epilogue), so thread 0 refills it with the tile two layers ahead -- after
+    // the dfeat store that may have been staged there has read it.
     //   g   : G tile (rows = samples, RBG bytes per row)        x : X tile in slot j % 3 (RBX bytes per row)
     //   w   : weight tile of this layer in the image (MN-major B for dgrad), RBW bytes per row (= 2*in)
     //   wgrad M=64: A = (t_out16 ? x : g) MN-major, B = (t_out16 ? g : x) MN-major
     auto layer = [&](uint64_t g_desc, int rbg, int rbx, uint64_t w_desc, int rbw, int n_in, int n_out, uint32_t wcol) -> const uint8_t* {
         const int slot = (int)(j % 3);
-        const uint32_t sX = base + kBwX0 + slot * kFwSmemTile64;
-        mbar_wait(smem_u32(&bars[2 + slot]), (uint32_t)(j / 3) & 1u);
-        fence_before_sync(); fence_async_smem(); __syncthreads();
+        const uint32_t sX = sWg + kX0 + slot * kFwSmemTile64;
+        mbar_wait(bar_x(slot), (uint32_t)(j / 3) & 1u);
+        fence_before_sync(); fence_async_smem(); wg_sync(1 + wg);
         if (tid == 0) {
             fence_after_sync();
+            bulk_wait_read<0>();
             issue_load(j + 2);
             const uint64_t x_desc = rbx == 128 ? smem_desc<128>(sX) : smem_desc<64>(sX);
             const bool t16 = n_out == 16;
@@ -425,21 +454,22 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
             const int rba = t16 ? rbx : rbg, rbb = t16 ? rbg : rbx;
             const uint32_t wi = instr_desc(64, t16 ? 16 : n_in, 1, 1);
             for (int k = 0; k < 8; k++)  // 16 samples per MMA = 16 rows of each tile
-                mma_f16(tmem + wcol, desc_advance(wa, 16 * rba * k), desc_advance(wb, 16 * rbb * k), wi, acc | (uint32_t)(k > 0));
+                mma_f16(tmem + wcol, desc_advance(wa, 16 * rba * k), desc_advance(wb, 16 * rbb * k), wi, 1u);
             const uint32_t di = instr_desc(128, n_in, 0, 1);
             for (int k = 0; k < n_out / 16; k++)  // K = out: 32 B along a G row, 16 rows down the weight tile
-                mma_f16(tmem + kColR, desc_advance(g_desc, 32 * k), desc_advance(w_desc, 16 * rbw * k), di, k > 0);
+                mma_f16(tmem + 64 * wg, desc_advance(g_desc, 32 * k), desc_advance(w_desc, 16 * rbw * k), di, k > 0);
             mma_commit(bar_mma);
         }
         j++;
-        return sm + kBwX0 + slot * kFwSmemTile64;
+        return pWg + kX0 + slot * kFwSmemTile64;
     };
     auto layer_wait = [&]() {
         mbar_wait(bar_mma, phase); phase ^= 1;
         fence_after_sync();
     };
+    const uint32_t tR = trow + 64 * wg;  // this thread's row of the warpgroup's R
 
-    const uint64_t dGa128 = smem_desc<128>(sGa), dGa32 = smem_desc<32>(sGa), dGb128 = smem_desc<128>(sGb), dGb32 = smem_desc<32>(sGb);
+    const uint64_t dG128 = smem_desc<128>(sG), dG32 = smem_desc<32>(sG);
     const uint64_t wD1 = smem_desc<64>(sW + kWimgD1), wD2 = smem_desc<128>(sW + kWimgD2);
     const uint64_t wC1 = smem_desc<64>(sW + kWimgC1), wC2 = smem_desc<128>(sW + kWimgC2), wC3 = smem_desc<128>(sW + kWimgC3);
 
@@ -459,7 +489,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     };
     fetch_scalars(tile0);
 
-    for (int64_t tile = tile0; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
         float tcol[16];  // scaled dL/dh from the colour branch
@@ -467,10 +497,9 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
         for (int k = 0; k < 16; k++) tcol[k] = 0.0f;
         // d sigma / d h0 = exp(clamp(h0, -15, 15)) (custom_functions.py:170-173) = clamp(sigma, e^-15, e^15): exp is monotone
         const float g_sigma = valid ? pre_ds * fminf(fmaxf(pre_sig, exp_lo), exp_hi) * loss_scale : 0.0f;
-        if (tid == 0) bulk_wait_read<0>();  // the previous tile's dfeat has left Gb (ordered before its reuse by the barrier of the first layer)
-        if (!with_rgb) __syncthreads();     // density-only: Gb is written before the first layer's barrier
+        // G was last read by the previous tile's D1 MMA, which has completed (layer_wait); the dfeat staging does not use it
         if (with_rgb) {
-            // ---- colour output layer: g3 (16) -> Ga (RB32), X = hid2
+            // ---- colour output layer: g3 (16) -> G (RB32), X = hid2
             {
                 uint32_t o[8];
 #pragma unroll
@@ -481,21 +510,21 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                     for (int k = 0; k < 3; k++) g[k] = pre_g[k] * (rgb_act ? pre_y[k] * (1.0f - pre_y[k]) : 1.0f) * loss_scale;
                     o[0] = pack2(g[0], g[1]); o[1] = pack2(g[2], 0.0f);
                 }
-                *reinterpret_cast<uint4*>(pGa + swz<32>(tid, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<uint4*>(pGa + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+                *reinterpret_cast<uint4*>(pG + swz<32>(tid, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(pG + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
             }
             const uint8_t* x;
-            x = layer(dGa32, 32, 128, wC3, 128, 64, 16, kColC3);
+            x = layer(dG32, 32, 128, wC3, 128, 64, 16, kColC3);
             layer_wait();
-            epilogue_mask64(trow + kColR, x, pGb, tid);               // g2 -> Gb
-            x = layer(dGb128, 128, 128, wC2, 128, 64, 64, kColC2);
+            epilogue_mask64(tR, x, pG, tid);                           // g2 -> G
+            x = layer(dG128, 128, 128, wC2, 128, 64, 64, kColC2);
             layer_wait();
-            epilogue_mask64(trow + kColR, x, pGa, tid);               // g1 -> Ga
-            layer(dGa128, 128, 64, wC1, 64, 32, 64, kColC1);
+            epilogue_mask64(tR, x, pG, tid);                           // g1 -> G
+            layer(dG128, 128, 64, wC1, 64, 32, 64, kColC1);
             layer_wait();
-            tmem_ld16(trow + kColR + 16, tcol); tmem_ld_wait();        // R[:, 16:32] = scaled dL/dh from the colour branch
+            tmem_ld16(tR + 16, tcol); tmem_ld_wait();                   // R[:, 16:32] = scaled dL/dh from the colour branch
         }
-        // ---- density output layer: gh (16) -> Gb (RB32), X = hid
+        // ---- density output layer: gh (16) -> G (RB32), X = hid
         {
             uint32_t o[8];
             o[0] = pack2(tcol[0] + g_sigma, tcol[1]);
@@ -505,27 +534,28 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
 #pragma unroll
                 for (int k = 0; k < 8; k++) o[k] = 0;
             }
-            // Gb was last read by the C2 MMA, which has completed
-            *reinterpret_cast<uint4*>(pGb + swz<32>(tid, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(pGb + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+            // G was last read by the C1 MMA (or the previous tile's D1 MMA), which has completed
+            *reinterpret_cast<uint4*>(pG + swz<32>(tid, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(pG + swz<32>(tid, 1)) = make_uint4(o[4], o[5], o[6], o[7]);
         }
-        const uint8_t* xh = layer(dGb32, 32, 128, wD2, 128, 64, 16, kColD2);
+        const uint8_t* xh = layer(dG32, 32, 128, wD2, 128, 64, 16, kColD2);
         layer_wait();
-        epilogue_mask64(trow + kColR, xh, pGa, tid);                  // gd -> Ga
-        layer(dGa128, 128, 64, wD1, 64, 32, 64, kColD1);
-        fetch_scalars(tile + gridDim.x);
+        epilogue_mask64(tR, xh, pG, tid);                              // gd -> G
+        const uint8_t* xf = layer(dG128, 128, 64, wD1, 64, 32, 64, kColD1);
+        fetch_scalars(tile + tile_stride);
         layer_wait();
-        {   // dfeat tile: fp32 rows of 128 B, chunk-permuted like a RB128 image; staged in Gb (free since the D2 MMA) and stored by TMA
+        {   // dfeat tile: fp32 rows of 128 B, chunk-permuted like a RB128 image; staged in the ring slot the feature tile has
+            // just left (free until the load two layers ahead, which waits for this store's read) and stored by TMA
+            uint8_t* stage = const_cast<uint8_t*>(xf);
             float v[32];
-            tmem_ld16(trow + kColR, v); tmem_ld16(trow + kColR + 16, v + 16); tmem_ld_wait();
+            tmem_ld16(tR, v); tmem_ld16(tR + 16, v + 16); tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 8; q++)
-                *reinterpret_cast<float4*>(pGb + swz<128>(tid, q)) =
+                *reinterpret_cast<float4*>(stage + swz<128>(tid, q)) =
                     make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale, v[4 * q + 3] * inv_scale);
-            fence_async_smem(); __syncthreads();
-            if (tid == 0) { bulk_s2g(dfeat + tile * 128 * 32, sGb, kFwSmemTile64); bulk_commit(); }
+            fence_async_smem(); wg_sync(1 + wg);
+            if (tid == 0) { bulk_s2g(dfeat + tile * 128 * 32, sWg + kX0 + (uint32_t)(stage - (pWg + kX0)), kFwSmemTile64); bulk_commit(); }
         }
-        acc = 1;
     }
     if (tid == 0) bulk_wait_read<0>();
 
@@ -534,7 +564,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
     // 3072) with plain stores; wgrad_reduce_kernel then sums the slabs in a fixed order.  (296 CTAs reducing onto the same
     // 10240 addresses with atomics serialised in L2 and cost 28 % of this kernel; the slab sum is also deterministic.)
     fence_before_sync(); __syncthreads(); fence_after_sync();
-    {
+    if (wg == 0) {
         float* slab = wpart + (size_t)(slab0 + blockIdx.x) * kWgradFloats;
         const int m = 16 * warp + lane;
         const bool own = lane < 16;
@@ -544,7 +574,7 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                 if (live) { tmem_ld16(trow + col + c0, v); tmem_ld_wait(); }
                 else {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] = 0.0f;
+                    for (int jj = 0; jj < 16; jj++) v[jj] = 0.0f;
                 }
                 if (own) {
                     if (ld_col == 1) {
@@ -554,20 +584,42 @@ __global__ void __launch_bounds__(128) field_mlp_bw_tc_kernel(int64_t n, const i
                                 make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale, v[4 * q + 3] * inv_scale);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; j++) dst[m * ld_row + (c0 + j) * ld_col] = v[j] * inv_scale;
+                        for (int jj = 0; jj < 16; jj++) dst[m * ld_row + (c0 + jj) * ld_col] = v[jj] * inv_scale;
                     }
                 }
             }
         };
-        const bool live_c = acc && with_rgb, live_d = acc != 0;
+        const bool live_c = with_rgb != 0;
         flush(kColC3, 16, slab + 6144, 1, 64, live_c);   // accumulator is [in][out]: dW3[out][in] = acc[in][out]
         flush(kColC2, 64, slab + 2048, 64, 1, live_c);
         flush(kColC1, 32, slab, 32, 1, live_c);
-        flush(kColD2, 16, slab + 7168 + 2048, 1, 64, live_d);
-        flush(kColD1, 32, slab + 7168, 32, 1, live_d);
+        flush(kColD2, 16, slab + 7168 + 2048, 1, 64, true);
+        flush(kColD1, 32, slab + 7168, 32, 1, true);
     }
     fence_before_sync(); __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (threadIdx.x < 32) tmem_dealloc(tmem, kTmemCols);
+}
+
+int mlp_device_setup(int* n_sm_out) {
+    static int n_sm[16] = {};
+    static std::mutex mu;
+    int dev = 0;
+    ARN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { set_error("mlp_device_setup: device index out of range"); return ARN_E_INVALID; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (!n_sm[dev]) {
+        int n = 0;
+        ARN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw_smem_bytes<1>()));
+        ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw_smem_bytes<4>()));
+        ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<1>()));
+        ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<3>()));
+        n_sm[dev] = n;
+    }
+    *n_sm_out = n_sm[dev];
+    return ARN_OK;
 }
 
 // grad += sum over the CTAs' slabs (arn_tc.cuh wgrad_reduce_block), stand-alone launch
@@ -611,27 +663,28 @@ int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, co
         ARN_LAUNCH("pack_mlp_weights_kernel", st, arn::pack_mlp_weights_kernel<<<5, 256, 0, st>>>(pxyz, with_rgb ? (const __half*)params_rgb_f16 : nullptr, (uint8_t*)ws.wimg));
         if (int e = check_launch("pack_mlp_weights")) return e;
     }
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0; ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        ARN_CUDA(cudaFuncSetAttribute(arn::field_mlp_bw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, arn::kBwSmemBytes));
-    }
+    int n_sm = 0;
+    if (int e = arn::mlp_device_setup(&n_sm)) return e;
     // Pipelined like the forward: the hash-grid backward (L2 reductions) of range p runs on a second stream under the MLP
     // backward (tensor core + HBM loads) of range p+1.  Every MLP launch writes its own block of weight-gradient slabs;
-    // the slab sum rides in the LAST hash-grid launch (run-aggregating form), otherwise it is launched on its own.
+    // the slab sum rides in the first hash-grid launch, otherwise it is launched on its own.
     const int64_t n_tiles = (n + 127) / 128;
     const bool runs = tunable(kTunHashBwMode) != 0;
     const int parts = (dL_dxyzs || !runs) ? 1 : pipeline_parts(n);
-    int grid = (int)max((int64_t)1, min((int64_t)n_sm * 2, (n_tiles + parts - 1) / parts));
+    // three warpgroups per CTA, one CTA per SM, when the launch has the tiles to fill that; else one warpgroup per CTA
+    const bool wide = (n_tiles + parts - 1) / parts >= (int64_t)n_sm * 3 && (tunable(kTunMlpWide) & 2) != 0;
+    const int wgs = wide ? 3 : 1;
+    int grid = (int)max((int64_t)1, min((int64_t)n_sm * (wide ? 1 : 2), ((n_tiles + parts - 1) / parts + wgs - 1) / wgs));
     if (grid * parts > arn::kMaxBwCtas) grid = arn::kMaxBwCtas / parts;
     float* wpart = reinterpret_cast<float*>((uint8_t*)ws.wimg + arn::kWimgBytes);  // slabs follow the weight image in the scratch
     PipeStreams* ps = nullptr;
     if (parts > 1) { if (int e = pipe_streams(&ps)) return e; }
     for (int p = 0; p < parts; p++) {
-        ARN_LAUNCH("field_mlp_bw_tc_kernel", st, arn::field_mlp_bw_tc_kernel<<<grid, 128, arn::kBwSmemBytes, st>>>(
-            n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, sigmas, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32,
-            (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, expf(15.0f),
-            dfeat_scratch, wpart, p, parts, p * grid));
+#define ARN_BW_ARGS n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, sigmas, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32, \
+            (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, expf(15.0f), dfeat_scratch, wpart, p, parts, p * grid
+        if (wide) ARN_LAUNCH("field_mlp_bw_tc_kernel", st, (arn::field_mlp_bw_tc_kernel<3><<<grid, 384, arn::bw_smem_bytes<3>(), st>>>(ARN_BW_ARGS)));
+        else ARN_LAUNCH("field_mlp_bw_tc_kernel", st, (arn::field_mlp_bw_tc_kernel<1><<<grid, 128, arn::bw_smem_bytes<1>(), st>>>(ARN_BW_ARGS)));
+#undef ARN_BW_ARGS
         if (int e = check_launch("field_mlp_bw_tc")) return e;
         if (parts > 1) ARN_CUDA(cudaEventRecord(ps->ev[p], st));
     }

@@ -68,6 +68,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16 columns of this warp's 32 lanes <- one value (zero-initialising accumulators several issuing threads add into)
+__device__ __forceinline__ void tmem_st16_fill(uint32_t taddr, uint32_t v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n"
+        :: "r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// barrier among the 128 threads of one warpgroup (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
 
 // Whole warp.  Writes the TMEM base address to *slot (shared memory).
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {

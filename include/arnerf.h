@@ -48,6 +48,10 @@ int64_t arn_launch_count(void);
  * into this many consecutive tile ranges, hash-grid and MLP kernels of neighbouring ranges overlapped on two streams; default
  * 1 = off: measured on B200 the overlap loses to the per-launch fixed costs, 0.384 / 0.409 / 0.469 ms per step at 1 / 2 / 3). */
 int arn_set_tunable(const char* name, int value);
+/* Measurement aid (bench.py): n_reductions red.global.add.v4.f32 to pseudo-random 16-byte slots of buf (n_floats floats, 16-byte
+ * aligned) and nothing else -- timed by the caller, it is the MEASURED rate at which the L2 retires scattered 16-byte
+ * reductions, the roof the hash-grid backward is reported against. */
+int arn_dbg_l2_red_peak(float* buf, int64_t n_floats, int64_t n_reductions, arn_stream_t stream);
 int arn_profile_enable(int on);
 int arn_profile_report(char* buf_host, int capacity);
 
