@@ -23,7 +23,7 @@ struct LaunchTimer {
 };
 
 // Kernel-variant switches for A/B measurements (arn_set_tunable): every variant computes the same results.
-enum Tunable { kTunMarchWarp = 0, kTunHashBwMode, kTunAdamVec, kTunPipelineParts, kTunHashBwBlocks, kTunMlpWide, kTunCount };
+enum Tunable { kTunMarchWarp = 0, kTunHashBwMode, kTunAdamVec, kTunPipelineParts, kTunHashBwBlocks, kTunMlpWide, kTunPdl, kTunCount };
 int tunable(Tunable t);
 
 inline int check_launch(const char* what) {
@@ -44,6 +44,39 @@ constexpr unsigned kFull = 0xffffffffu;
     do {                                          \
         arn::LaunchTimer lt__((name), (st));      \
         __VA_ARGS__;                              \
+    } while (0)
+
+// Programmatic dependent launch for the kernels of the serial chains (training step, test-loop iteration): the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, every block of such a kernel starts with pdl_enter() -- wait until the
+// preceding kernel of the stream has completed and its memory is visible, then allow the NEXT kernel of the stream to be
+// launched -- so that the next kernel's launch latency and block scheduling overlap this kernel's execution instead of
+// following it.  A kernel is launched early only once ALL blocks of its predecessor have started (each has passed its own
+// wait), so nothing it holds can starve the predecessor; results are those of plain stream order.  (Captured into a CUDA
+// graph the attribute becomes a programmatic dependency edge.)  "pdl" tunable, default 0 = plain launches: measured on B200 the
+// early-launched blocks cost the big kernels more than the hidden launch latency returns -- training step 0.333 -> 0.365 ms,
+// 800x800 frame 5.77 -> 6.42 ms; only a rank's 1/8 share of a frame gains (2.00 -> 1.93 ms).
+namespace arn {
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = tunable(kTunPdl) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+}  // namespace arn
+#define ARN_LAUNCH_PDL(name, st, kernel, grid, block, smem, ...)                       \
+    do {                                                                               \
+        arn::LaunchTimer lt__((name), (st));                                           \
+        arn::launch_pdl(kernel, (grid), (block), (smem), (st), __VA_ARGS__);           \
     } while (0)
 
 #define ARN_REQUIRE(cond, msg)                                            \

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) hash_encode_fw_kernel(const float* __rest
                                                              const __half2* __restrict__ table, __half2* __restrict__ feat, int img,
                                                              const __half* __restrict__ pack_wd, const __half* __restrict__ pack_wc,
                                                              uint8_t* __restrict__ pack_img, int part, int parts) {
+    pdl_enter();
     if (n_dev) n = min(n, (int64_t)*n_dev);
     const int grp = blockIdx.y;  // levels [8*grp, 8*grp + 8)
     if (pack_img && grp == 0) {  // rider: the MLP kernels that follow read the weights as a swizzled operand image
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(256) hash_encode_bw_runs_kernel(const float* _
                                                                   const __grid_constant__ LevelTable tbl, const float2* __restrict__ dfeat,
                                                                   float2* __restrict__ table_grad, int level0, int nlevels, int img,
                                                                   int n_main_blocks, int min_run, WgradReduce red, int part, int parts) {
+    pdl_enter();
     __shared__ float red_part[8][32];
     if ((int)blockIdx.x >= n_main_blocks) {  // rider blocks: sum of the MLP weight-gradient slabs (independent of the table work)
         wgrad_reduce_block((int)blockIdx.x - n_main_blocks, red.wpart, red.n_slabs, red.with_rgb, red.dWd, red.dWc, red_part);
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(256) hash_encode_bw_warp_kernel(const float* _
                                                                   const __grid_constant__ LevelTable tbl, const float* __restrict__ dfeat,
                                                                   float2* __restrict__ table_grad, int level0, int nlevels, int img,
                                                                   int n_main_blocks, WgradReduce red, int part, int parts) {
+    pdl_enter();
     __shared__ float red_part[8][32];
     if ((int)blockIdx.x >= n_main_blocks) {  // rider blocks: sum of the MLP weight-gradient slabs (independent of the table work)
         wgrad_reduce_block((int)blockIdx.x - n_main_blocks, red.wpart, red.n_slabs, red.with_rgb, red.dWd, red.dWc, red_part);
@@ -363,7 +366,7 @@ static int launch_hash_bw_warp(const float* xyzs, int64_t n, const int32_t* n_de
     const int cap = tunable(kTunHashBwBlocks) > 0 ? min(slots, 148 * tunable(kTunHashBwBlocks)) : slots;
     const int grid = (int)max((int64_t)1, min((int64_t)cap, (warps + 7) / 8));
     const int riders = red.wpart ? kWgradFloats / 32 : 0;
-    ARN_LAUNCH("hash_encode_bw_warp_kernel", st, hash_encode_bw_warp_kernel<<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, dfeat, (float2*)table_grad, level0, nlevels, img, grid, red, part, parts));
+    ARN_LAUNCH_PDL("hash_encode_bw_warp_kernel", st, (hash_encode_bw_warp_kernel), grid + riders, 256, 0, xyzs, n, n_dev, b, t, dfeat, (float2*)table_grad, level0, nlevels, img, grid, red, part, parts);
     return check_launch("hash_encode_bw_warp");
 }
 
@@ -391,7 +394,7 @@ static int launch_hash_bw_runs(int min_run, const float* xyzs, int64_t n, const 
     const int64_t threads = ((n_part + run - 1) / run) * LPG;
     const int grid = (int)max((int64_t)1, min((int64_t)cap, (threads + 255) / 256));
     const int riders = red.wpart ? kWgradFloats / 32 : 0;
-    ARN_LAUNCH("hash_encode_bw_runs_kernel", st, (hash_encode_bw_runs_kernel<LPG><<<grid + riders, 256, 0, st>>>(xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img, grid, min_run, red, part, parts)));
+    ARN_LAUNCH_PDL("hash_encode_bw_runs_kernel", st, (hash_encode_bw_runs_kernel<LPG>), grid + riders, 256, 0, xyzs, n, n_dev, b, t, (const float2*)dfeat, (float2*)table_grad, level0, nlevels, img, grid, min_run, red, part, parts);
     return check_launch("hash_encode_bw_runs");
 }
 // min_run ("hash_bw_mode", 8..64): the shortest run of consecutive samples one lane group takes (small batches)
@@ -738,6 +741,7 @@ struct AdamRider { float* p; float* g; float* m; float* v; __half* p16; int64_t 
 __global__ void __launch_bounds__(256) adam_vec4_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
                                                         uint2* __restrict__ p16, int64_t n4, float lr, float b1, float b2, float eps,
                                                         float bc1, float bc2_sqrt, float inv_gs, int zero_grad, int n_main_blocks, AdamRider rd) {
+    pdl_enter();
     const float lr_bc1 = lr / bc1;
     if ((int)blockIdx.x >= n_main_blocks) {
         const int64_t i = (int64_t)(blockIdx.x - n_main_blocks) * blockDim.x + threadIdx.x;
@@ -847,8 +851,8 @@ int arn::hash_encode_fw_impl(const float* xyzs, int64_t n, const int32_t* n_dev,
     ARN_REQUIRE(((uintptr_t)feat_f16 & 15) == 0, "feat must be 16-byte aligned");
     ARN_REQUIRE(parts >= 1 && part >= 0 && part < parts, "bad part");
     dim3 grid(max(max(sample_grid(n, n_dev) / parts, 1), pack_img ? ceil_div(kWimgChunks, 256) : 1), ARN_N_LEVELS / 8);
-    ARN_LAUNCH("hash_encode_fw_kernel", (cudaStream_t)stream, hash_encode_fw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyzs, n, n_dev, b, t, (const __half2*)table_f16, (__half2*)feat_f16, tile_image,
-                                                                                                                           pack_wd, pack_wc, pack_img, part, parts));
+    ARN_LAUNCH_PDL("hash_encode_fw_kernel", (cudaStream_t)stream, (hash_encode_fw_kernel), grid, 256, 0, xyzs, n, n_dev, b, t, (const __half2*)table_f16, (__half2*)feat_f16, tile_image,
+                                                                                                                           pack_wd, pack_wc, pack_img, part, parts);
     return check_launch("hash_encode_fw");
 }
 extern "C" ARN_API int arn_hash_encode_fw_dyn(const float* xyzs, int64_t n, const int32_t* n_dev, const float* xyz_min_host, const float* xyz_max_host,
@@ -982,8 +986,8 @@ extern "C" ARN_API int arn_adam_step(float* params, float* grads, float* exp_avg
     if (tunable(kTunAdamVec) && aligned && n % 4 == 0 && n >= 4096) {
         const int64_t n4 = n / 4;
         const int grid = (int)min((int64_t)148 * 16, (n4 + 255) / 256);
-        ARN_LAUNCH("adam_vec4_kernel", st, adam_vec4_kernel<<<grid, 256, 0, st>>>((float4*)params, (float4*)grads, (float4*)exp_avg, (float4*)exp_avg_sq, (uint2*)dst_f16, n4,
-                                                                                  lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad, grid, AdamRider{}));
+        ARN_LAUNCH_PDL("adam_vec4_kernel", st, (adam_vec4_kernel), grid, 256, 0, (float4*)params, (float4*)grads, (float4*)exp_avg, (float4*)exp_avg_sq, (uint2*)dst_f16, n4,
+                                                                                  lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad, grid, AdamRider{});
     } else {
         ARN_LAUNCH("adam_kernel", st, adam_kernel<<<ceil_div(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)dst_f16, n, lr, beta1, beta2,
                                                                                      eps, bc1, bc2_sqrt, inv_grad_scale, zero_grad));
@@ -1005,9 +1009,9 @@ extern "C" ARN_API int arn_adam_step2(float* params, float* grads, float* exp_av
     const int64_t n4 = n / 4;
     const int grid = (int)min((int64_t)148 * 16, (n4 + 255) / 256);
     const AdamRider rd{params2, grads2, exp_avg2, exp_avg_sq2, (__half*)dst2_f16, n2};
-    ARN_LAUNCH("adam_vec4_kernel", st, adam_vec4_kernel<<<grid + ceil_div(n2, 256), 256, 0, st>>>((float4*)params, (float4*)grads, (float4*)exp_avg, (float4*)exp_avg_sq,
+    ARN_LAUNCH_PDL("adam_vec4_kernel", st, (adam_vec4_kernel), grid + ceil_div(n2, 256), 256, 0, (float4*)params, (float4*)grads, (float4*)exp_avg, (float4*)exp_avg_sq,
                                                                                                (uint2*)dst_f16, n4, lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale,
-                                                                                               zero_grad, grid, rd));
+                                                                                               zero_grad, grid, rd);
     return check_launch("adam_step2");
 }
 

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(128 * W, 1) field_mlp_fw_tc_kernel(const __hal
                                                               __half* __restrict__ hid, float* __restrict__ h, float* __restrict__ sigmas,
                                                               __half* __restrict__ in32, __half* __restrict__ hid1, __half* __restrict__ hid2,
                                                               float* __restrict__ rgbs, int part, int parts) {
+    pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[1 + 3 * W];  // weights | per warpgroup: mma, f0, f1
     __shared__ uint32_t tmem_slot;
@@ -306,8 +307,8 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
         if (parts > 1) ARN_CUDA(cudaStreamWaitEvent(st, ps->ev[p], 0));
 #define ARN_FW_ARGS (const __half*)ws.feat, dirs, n, n_dev, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, (__half*)ws.hid, ws.h, sigmas, \
             (__half*)ws.in32, (__half*)ws.hid1, (__half*)ws.hid2, rgbs, p, parts
-        if (wide) ARN_LAUNCH("field_mlp_fw_tc_kernel", st, (field_mlp_fw_tc_kernel<4><<<grid, 512, fw_smem_bytes<4>(), st>>>(ARN_FW_ARGS)));
-        else ARN_LAUNCH("field_mlp_fw_tc_kernel", st, (field_mlp_fw_tc_kernel<1><<<grid, 128, fw_smem_bytes<1>(), st>>>(ARN_FW_ARGS)));
+        if (wide) ARN_LAUNCH_PDL("field_mlp_fw_tc_kernel", st, (field_mlp_fw_tc_kernel<4>), grid, 512, fw_smem_bytes<4>(), ARN_FW_ARGS);
+        else ARN_LAUNCH_PDL("field_mlp_fw_tc_kernel", st, (field_mlp_fw_tc_kernel<1>), grid, 128, fw_smem_bytes<1>(), ARN_FW_ARGS);
 #undef ARN_FW_ARGS
         if (int e = check_launch("field_mlp_fw_tc")) return e;
     }
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(128 * W, 1) __maxnreg__(W == 3 ? 128 : 192) fi
                                                               const __half* __restrict__ hid2, const uint8_t* __restrict__ wimg, int rgb_act,
                                                               int with_rgb, float loss_scale, float exp_hi, float* __restrict__ dfeat, float* __restrict__ wpart,
                                                               int part, int parts, int slab0) {
+    pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[1 + 4 * W];  // weights | per warpgroup: mma, x0, x1, x2
     __shared__ uint32_t tmem_slot;
@@ -682,8 +684,8 @@ int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, co
     for (int p = 0; p < parts; p++) {
 #define ARN_BW_ARGS n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, sigmas, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32, \
             (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, expf(15.0f), dfeat_scratch, wpart, p, parts, p * grid
-        if (wide) ARN_LAUNCH("field_mlp_bw_tc_kernel", st, (arn::field_mlp_bw_tc_kernel<3><<<grid, 384, arn::bw_smem_bytes<3>(), st>>>(ARN_BW_ARGS)));
-        else ARN_LAUNCH("field_mlp_bw_tc_kernel", st, (arn::field_mlp_bw_tc_kernel<1><<<grid, 128, arn::bw_smem_bytes<1>(), st>>>(ARN_BW_ARGS)));
+        if (wide) ARN_LAUNCH_PDL("field_mlp_bw_tc_kernel", st, (arn::field_mlp_bw_tc_kernel<3>), grid, 384, arn::bw_smem_bytes<3>(), ARN_BW_ARGS);
+        else ARN_LAUNCH_PDL("field_mlp_bw_tc_kernel", st, (arn::field_mlp_bw_tc_kernel<1>), grid, 128, arn::bw_smem_bytes<1>(), ARN_BW_ARGS);
 #undef ARN_BW_ARGS
         if (int e = check_launch("field_mlp_bw_tc")) return e;
         if (parts > 1) ARN_CUDA(cudaEventRecord(ps->ev[p], st));

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) intersect_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) aabb_near_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                         int64_t n_rays, float cx, float cy, float cz, float hx, float hy,
                                                         float hz, float near, float2* __restrict__ hits_t) {
+    pdl_enter();
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rays) return;
     const float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
@@ -412,6 +413,7 @@ __global__ void __launch_bounds__(256) march_train_count_warp_kernel(const float
                                                                      const uint8_t* __restrict__ bitfield, ArnMarchConsts c,
                                                                      const float* __restrict__ noise, int64_t* __restrict__ rays_a,
                                                                      float* __restrict__ t_scratch, int32_t* __restrict__ counts) {
+    pdl_enter();
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_rays) return;  // warp-uniform
@@ -484,6 +486,7 @@ __global__ void __launch_bounds__(256) march_train_count_warp_kernel(const float
 // sector throughput: 20 us for 8192 rays.)
 __global__ void __launch_bounds__(1024) rays_scan_compact_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* __restrict__ rays_a,
                                                                  int32_t* __restrict__ counter) {
+    pdl_enter();
     __shared__ int64_t warp_pre[32], warp_inc[32];
     __shared__ int64_t s_start[1024];
     __shared__ int32_t s_cnt[1024];
@@ -576,6 +579,7 @@ __global__ void __launch_bounds__(256) march_train_emit_kernel(const float* __re
                                                                const int32_t* __restrict__ total_dev,
                                                                float* __restrict__ xyzs, float* __restrict__ dirs,
                                                                float* __restrict__ deltas, float* __restrict__ ts) {
+    pdl_enter();
     if (total_dev) total = min(total, (int64_t)*total_dev);  // device-side count (fused step): `total` is the capacity
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (int64_t)gridDim.x * blockDim.x) {
     // largest r with start[r] <= s and N[r] > 0 : starts are non-decreasing, so search the last start <= s
@@ -831,6 +835,7 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
                                                                  float* __restrict__ depth, float* __restrict__ rgb, float* __restrict__ ws,
                                                                  const LossEpilogue L, int64_t n_samples,
                                                                  float* __restrict__ bw_dsigmas, float* __restrict__ bw_drgbs) {
+    pdl_enter();
     __shared__ float s_loss[8];
     if (LOSS && threadIdx.x < 8) s_loss[threadIdx.x] = 0.0f;
     if (LOSS) __syncthreads();
@@ -1188,6 +1193,7 @@ __global__ void __launch_bounds__(128) march_test_all_kernel(const float* __rest
 __global__ void __launch_bounds__(128) neff_test_pre_kernel(const int64_t* __restrict__ alive, const int32_t* __restrict__ state,
                                                             const int32_t* __restrict__ totals, const int32_t* __restrict__ cursor,
                                                             int32_t* __restrict__ n_eff, int32_t* __restrict__ partial) {
+    pdl_enter();
     __shared__ int sm4[4];
     const int64_t n_alive = state[kStN]; const int S = state[kStS];
     for (int64_t base = (int64_t)blockIdx.x * 128; base < n_alive; base += (int64_t)gridDim.x * 128) {
@@ -1210,6 +1216,7 @@ __global__ void __launch_bounds__(256) emit_test_pre_kernel(const float* __restr
                                                             const int32_t* __restrict__ cursor, int64_t n_rays, ArnMarchConsts c,
                                                             float* __restrict__ deltas, float* __restrict__ ts,
                                                             float* __restrict__ xyzs, float* __restrict__ dirs) {
+    pdl_enter();
     const int64_t n_alive = state[kStN]; const int S = state[kStS];
     const int64_t total = n_alive * S;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -1228,6 +1235,7 @@ __global__ void __launch_bounds__(256) emit_test_pre_kernel(const float* __restr
 __global__ void __launch_bounds__(1024) scan_test_dyn_kernel(const int32_t* __restrict__ counts_in, const int32_t* __restrict__ partial,
                                                              const int32_t* __restrict__ state, int64_t* __restrict__ rays_a,
                                                              int32_t* __restrict__ counter) {
+    pdl_enter();
     __shared__ int64_t warp_inc[32];
     __shared__ int64_t s_pre;
     const int64_t n_rays = state[kStN];
@@ -1291,6 +1299,7 @@ __global__ void __launch_bounds__(128) composite_test_dyn_kernel(const float* __
                                                                  float* __restrict__ depth, float* __restrict__ rgb, int32_t* __restrict__ keep,
                                                                  int32_t* __restrict__ partial, unsigned long long* __restrict__ total,
                                                                  int32_t* __restrict__ cursor) {
+    pdl_enter();
     __shared__ int sm4[4];
     const int64_t n_alive = state[kStN]; const int S = state[kStS];
     for (int64_t base = (int64_t)blockIdx.x * 128; base < n_alive; base += (int64_t)gridDim.x * 128) {
@@ -1336,6 +1345,7 @@ __global__ void __launch_bounds__(1024) alive_compact_dyn_kernel(const int64_t* 
                                                                  const int32_t* __restrict__ counts, int64_t* __restrict__ alive_out,
                                                                  int32_t* __restrict__ counts_alive, int32_t* __restrict__ state_out,
                                                                  int64_t n_rays_total, int min_samples, int budget) {
+    pdl_enter();
     __shared__ int64_t warp_inc[32];
     __shared__ int64_t s_pre;
     const int64_t n = state_in[kStN];
@@ -1486,8 +1496,8 @@ extern "C" ARN_API int arn_ray_aabb_near(const float* rays_o, const float* rays_
     ARN_REQUIRE(rays_o && rays_d && center_host && half_size_host && hits_t, "null pointer");
     float ch[6];  // the box is 24 bytes of module state: passed from the host so it travels as kernel arguments
     for (int k = 0; k < 3; k++) { ch[k] = center_host[k]; ch[3 + k] = half_size_host[k]; }
-    ARN_LAUNCH("aabb_near_kernel", (cudaStream_t)stream, aabb_near_kernel<<<ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, n_rays, ch[0], ch[1], ch[2], ch[3],
-                                                                            ch[4], ch[5], near, reinterpret_cast<float2*>(hits_t)));
+    ARN_LAUNCH_PDL("aabb_near_kernel", (cudaStream_t)stream, (aabb_near_kernel), ceil_div(n_rays, 256), 256, 0, rays_o, rays_d, n_rays, ch[0], ch[1], ch[2], ch[3],
+                                                                            ch[4], ch[5], near, reinterpret_cast<float2*>(hits_t));
     return check_launch("ray_aabb_near");
 }
 
@@ -1643,7 +1653,7 @@ extern "C" ARN_API int arn_march_train_count_ex(const float* rays_o, const float
         const bool const_dt = exp_step_factor == 0.0f && c.dt_hi >= 0.0f;  // calc_dt is the constant dt_lo
         const bool fast = cascades == 1 && grid_size <= 256;
         const int grid = ceil_div(n_rays * 32, 256);
-#define ARN_MARCH_WARP(CD, FA) ARN_LAUNCH("march_train_count_warp_kernel", st, (march_train_count_warp_kernel<CD, FA><<<grid, 256, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch, count_scratch)))
+#define ARN_MARCH_WARP(CD, FA) ARN_LAUNCH_PDL("march_train_count_warp_kernel", st, (march_train_count_warp_kernel<CD, FA>), grid, 256, 0, rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, t_scratch, count_scratch)
         if (const_dt && fast) ARN_MARCH_WARP(true, true);
         else if (const_dt) ARN_MARCH_WARP(true, false);
         else if (fast) ARN_MARCH_WARP(false, true);
@@ -1651,7 +1661,7 @@ extern "C" ARN_API int arn_march_train_count_ex(const float* rays_o, const float
 #undef ARN_MARCH_WARP
     }
     if (int e = check_launch("march_train_count")) return e;
-    if (count_scratch) ARN_LAUNCH("rays_scan_compact_kernel", st, rays_scan_compact_kernel<<<ceil_div(n_rays, 1024), 1024, 0, st>>>(count_scratch, n_rays, rays_a, counter));
+    if (count_scratch) ARN_LAUNCH_PDL("rays_scan_compact_kernel", st, (rays_scan_compact_kernel), ceil_div(n_rays, 1024), 1024, 0, count_scratch, n_rays, rays_a, counter);
     else ARN_LAUNCH("rays_scan_kernel", st, rays_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, counter));
     return check_launch("rays_scan");
 }
@@ -1675,7 +1685,7 @@ extern "C" ARN_API int arn_march_train_emit_ex(const float* rays_o, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
     if (t_scratch) {
-        ARN_LAUNCH("march_train_emit_kernel", st, march_train_emit_kernel<<<ceil_div(capacity, 256), 256, 0, st>>>(rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, nullptr, xyzs, dirs, deltas, ts));
+        ARN_LAUNCH_PDL("march_train_emit_kernel", st, (march_train_emit_kernel), ceil_div(capacity, 256), 256, 0, rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, nullptr, xyzs, dirs, deltas, ts);
         return check_launch("march_train_emit");
     }
     ARN_LAUNCH("march_train_remarch_kernel", st, march_train_remarch_kernel<<<ceil_div(n_rays, 128), 128, 0, st>>>(rays_o, rays_d, hits_t, n_rays, density_bitfield, c, noise, rays_a, xyzs, dirs, deltas, ts));
@@ -1693,7 +1703,7 @@ extern "C" ARN_API int arn_march_train_emit_dyn(const float* rays_o, const float
     cudaStream_t st = (cudaStream_t)stream;
     const ArnMarchConsts c = arn_march_consts(cascades, grid_size, scale, scale, exp_step_factor, max_samples);
     const int grid = (int)min((int64_t)148 * 16, (capacity + 255) / 256);
-    ARN_LAUNCH("march_train_emit_kernel", st, march_train_emit_kernel<<<grid, 256, 0, st>>>(rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, counter, xyzs, dirs, deltas, ts));
+    ARN_LAUNCH_PDL("march_train_emit_kernel", st, (march_train_emit_kernel), grid, 256, 0, rays_o, rays_d, n_rays, c, rays_a, t_scratch, capacity, counter, xyzs, dirs, deltas, ts);
     return check_launch("march_train_emit_dyn");
 }
 
@@ -1727,8 +1737,8 @@ extern "C" ARN_API int arn_composite_train_fw(const float* sigmas, const float* 
     if (n_rays == 0) return ARN_OK;
     ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "null pointer");
     ARN_REQUIRE(n_samples == 0 || (sigmas && rgbs && deltas && ts && ws), "null pointer");
-    ARN_LAUNCH("composite_train_fw_kernel", (cudaStream_t)stream, composite_train_fw_kernel<false><<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
-                                                                                          total_samples, opacity, depth, rgb, ws, LossEpilogue{}, n_samples, nullptr, nullptr));
+    ARN_LAUNCH_PDL("composite_train_fw_kernel", (cudaStream_t)stream, (composite_train_fw_kernel<false>), ceil_div(n_rays * 32, 256), 256, 0, sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
+                                                                                          total_samples, opacity, depth, rgb, ws, LossEpilogue{}, n_samples, nullptr, nullptr);
     return check_launch("composite_train_fw");
 }
 
@@ -1762,8 +1772,8 @@ extern "C" int arn_composite_train_fw_loss_ex(const float* sigmas, const float* 
     if (zero_loss) ARN_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
     LossEpilogue L{target, {bg_host[0], bg_host[1], bg_host[2]}, lambda_opacity, lambda_depth, grid_scale, grad_scale, rgb_out, dL_drgb, dL_dopacity,
                    dL_ddepth, loss_out};
-    ARN_LAUNCH("composite_train_fw_loss_kernel", st, composite_train_fw_kernel<true><<<ceil_div(n_rays * 32, 256), 256, 0, st>>>(sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
-                                                                                          total_samples, opacity, depth, rgb, ws, L, n_samples, bw_dsigmas, bw_drgbs));
+    ARN_LAUNCH_PDL("composite_train_fw_loss_kernel", st, (composite_train_fw_kernel<true>), ceil_div(n_rays * 32, 256), 256, 0, sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
+                                                                                          total_samples, opacity, depth, rgb, ws, L, n_samples, bw_dsigmas, bw_drgbs);
     return check_launch("composite_train_fw_loss");
 }
 
@@ -1841,7 +1851,7 @@ extern "C" ARN_API int arn_render_test_iter(const arn_test_iter_t* c, arn_stream
     ARN_LAUNCH("march_test_lite_kernel", st, march_test_lite_kernel<<<ceil_div(n, 128), 128, 0, st>>>(c->rays_o, c->rays_d, c->hits_t, c->alive, n, c->density_bitfield, mc, S,
                                                                                                   c->deltas, c->ts, c->n_eff));
     if (int e = check_launch("march_test_lite")) return e;
-    ARN_LAUNCH("rays_scan_compact_kernel", st, rays_scan_compact_kernel<<<ceil_div(n, 1024), 1024, 0, st>>>(c->n_eff, n, c->rays_a, c->counts));
+    ARN_LAUNCH_PDL("rays_scan_compact_kernel", st, (rays_scan_compact_kernel), ceil_div(n, 1024), 1024, 0, c->n_eff, n, c->rays_a, c->counts);
     if (int e = check_launch("rays_scan")) return e;
     ARN_LAUNCH("emit_test_kernel", st, emit_test_kernel<<<ceil_div(n * S, 256), 256, 0, st>>>(c->rays_o, c->rays_d, c->alive, n, S, c->rays_a, c->ts, c->xyzs, c->dirs));
     if (int e = check_launch("emit_test")) return e;
@@ -1852,7 +1862,7 @@ extern "C" ARN_API int arn_render_test_iter(const arn_test_iter_t* c, arn_stream
                                                                                                                (unsigned long long*)c->total_samples));
     if (int e = check_launch("composite_test_compact")) return e;
     // n_eff now holds the keep flags; the scan reuses rays_a and leaves (rays kept, n) in counts_alive
-    ARN_LAUNCH("rays_scan_compact_kernel", st, rays_scan_compact_kernel<<<ceil_div(n, 1024), 1024, 0, st>>>(c->n_eff, n, c->rays_a, c->counts_alive));
+    ARN_LAUNCH_PDL("rays_scan_compact_kernel", st, (rays_scan_compact_kernel), ceil_div(n, 1024), 1024, 0, c->n_eff, n, c->rays_a, c->counts_alive);
     if (int e = check_launch("rays_scan")) return e;
     ARN_LAUNCH("alive_scatter_kernel", st, alive_scatter_kernel<<<ceil_div(n, 256), 256, 0, st>>>(c->alive, n, c->rays_a, c->alive_out));
     return check_launch("alive_scatter");
@@ -1906,19 +1916,19 @@ extern "C" ARN_API int arn_render_test_step(const arn_test_iter_t* c, const int3
                                                                                                    c->deltas, c->ts, c->n_eff, partial));
         if (int e = check_launch("march_test_dyn")) return e;
     }
-    ARN_LAUNCH("scan_test_dyn_kernel", st, scan_test_dyn_kernel<<<g1024, 1024, 0, st>>>(c->n_eff, warp_march ? nullptr : partial, state_in, c->rays_a, c->counts));
+    ARN_LAUNCH_PDL("scan_test_dyn_kernel", st, (scan_test_dyn_kernel), g1024, 1024, 0, c->n_eff, warp_march ? nullptr : partial, state_in, c->rays_a, c->counts);
     if (int e = check_launch("scan_test_dyn")) return e;
     const int g_emit = (int)min((int64_t)148 * 32, (samples_upper + 255) / 256);
     ARN_LAUNCH("emit_test_dyn_kernel", st, emit_test_dyn_kernel<<<g_emit, 256, 0, st>>>(c->rays_o, c->rays_d, c->alive, state_in, c->rays_a, c->ts, c->xyzs, c->dirs));
     if (int e = check_launch("emit_test_dyn")) return e;
     if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, samples_upper, c->counts, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
                                     c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
-    ARN_LAUNCH("composite_test_dyn_kernel", st, composite_test_dyn_kernel<<<g128, 128, 0, st>>>(c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, state_in, c->T_threshold,
+    ARN_LAUNCH_PDL("composite_test_dyn_kernel", st, (composite_test_dyn_kernel), g128, 128, 0, c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, state_in, c->T_threshold,
                                                                                             c->rays_a, c->opacity, c->depth, c->rgb, c->n_eff, partial,
-                                                                                            (unsigned long long*)c->total_samples, nullptr));
+                                                                                            (unsigned long long*)c->total_samples, nullptr);
     if (int e = check_launch("composite_test_dyn")) return e;
-    ARN_LAUNCH("alive_compact_dyn_kernel", st, alive_compact_dyn_kernel<<<g1024, 1024, 0, st>>>(c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
-                                                                                           c->counts_alive, state_out, c->n_alive, min_samples, budget_samples));
+    ARN_LAUNCH_PDL("alive_compact_dyn_kernel", st, (alive_compact_dyn_kernel), g1024, 1024, 0, c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
+                                                                                           c->counts_alive, state_out, c->n_alive, min_samples, budget_samples);
     return check_launch("alive_compact_dyn");
 }
 
@@ -1953,21 +1963,21 @@ extern "C" ARN_API int arn_render_test_step_pre(const arn_test_iter_t* c, const 
     const int64_t samples_upper = nu * min_samples > c->n_alive ? nu * min_samples : c->n_alive;
     const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
     const int g128 = (int)min((int64_t)148 * 16, (nu + 127) / 128), g1024 = (int)min((int64_t)148 * 4, (nu + 1023) / 1024);  // grid-stride: full residency is enough
-    ARN_LAUNCH("neff_test_pre_kernel", st, neff_test_pre_kernel<<<g128, 128, 0, st>>>(c->alive, state_in, totals, cursor, c->n_eff, partial));
+    ARN_LAUNCH_PDL("neff_test_pre_kernel", st, (neff_test_pre_kernel), g128, 128, 0, c->alive, state_in, totals, cursor, c->n_eff, partial);
     if (int e = check_launch("neff_test_pre")) return e;
-    ARN_LAUNCH("scan_test_dyn_kernel", st, scan_test_dyn_kernel<<<g1024, 1024, 0, st>>>(c->n_eff, partial, state_in, c->rays_a, c->counts));
+    ARN_LAUNCH_PDL("scan_test_dyn_kernel", st, (scan_test_dyn_kernel), g1024, 1024, 0, c->n_eff, partial, state_in, c->rays_a, c->counts);
     if (int e = check_launch("scan_test_dyn")) return e;
     const int g_emit = (int)min((int64_t)148 * 32, (samples_upper + 255) / 256);
-    ARN_LAUNCH("emit_test_pre_kernel", st, emit_test_pre_kernel<<<g_emit, 256, 0, st>>>(c->rays_o, c->rays_d, c->alive, state_in, c->rays_a, ts_all, cursor, c->n_alive, mc,
-                                                                                     c->deltas, c->ts, c->xyzs, c->dirs));
+    ARN_LAUNCH_PDL("emit_test_pre_kernel", st, (emit_test_pre_kernel), g_emit, 256, 0, c->rays_o, c->rays_d, c->alive, state_in, c->rays_a, ts_all, cursor, c->n_alive, mc,
+                                                                                     c->deltas, c->ts, c->xyzs, c->dirs);
     if (int e = check_launch("emit_test_pre")) return e;
     if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, samples_upper, c->counts, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
                                     c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
-    ARN_LAUNCH("composite_test_dyn_kernel", st, composite_test_dyn_kernel<<<g128, 128, 0, st>>>(c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, state_in, c->T_threshold,
+    ARN_LAUNCH_PDL("composite_test_dyn_kernel", st, (composite_test_dyn_kernel), g128, 128, 0, c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, state_in, c->T_threshold,
                                                                                             c->rays_a, c->opacity, c->depth, c->rgb, c->n_eff, partial,
-                                                                                            (unsigned long long*)c->total_samples, cursor));
+                                                                                            (unsigned long long*)c->total_samples, cursor);
     if (int e = check_launch("composite_test_dyn")) return e;
-    ARN_LAUNCH("alive_compact_dyn_kernel", st, alive_compact_dyn_kernel<<<g1024, 1024, 0, st>>>(c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
-                                                                                           c->counts_alive, state_out, c->n_alive, min_samples, budget_samples));
+    ARN_LAUNCH_PDL("alive_compact_dyn_kernel", st, (alive_compact_dyn_kernel), g1024, 1024, 0, c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
+                                                                                           c->counts_alive, state_out, c->n_alive, min_samples, budget_samples);
     return check_launch("alive_compact_dyn");
 }

@@ -46,7 +46,9 @@ int64_t arn_launch_count(void);
  * backward: a lane per sample, equal cells of neighbouring lanes merged by a segmented warp scan -- measured 98 vs 79 us on the
  * W1 batch; 0 = one reduction per sample and corner), "hash_bw_blocks" (blocks per SM of that wave, 0 = what the occupancy calculator allows), "adam_vec" (1 = 128-bit Adam kernel), "pipeline_parts" (field evaluations of >= 64 K samples are split
  * into this many consecutive tile ranges, hash-grid and MLP kernels of neighbouring ranges overlapped on two streams; default
- * 1 = off: measured on B200 the overlap loses to the per-launch fixed costs, 0.384 / 0.409 / 0.469 ms per step at 1 / 2 / 3). */
+ * 1 = off: measured on B200 the overlap loses to the per-launch fixed costs, 0.384 / 0.409 / 0.469 ms per step at 1 / 2 / 3),
+ * "mlp_wide" (bit 0: forward MLP with four warpgroups per CTA sharing one weight image, bit 1: backward with three; default 3),
+ * "pdl" (1 = programmatic dependent launch along the serial kernel chains; default 0: measured slower, see arn_common.cuh). */
 int arn_set_tunable(const char* name, int value);
 /* Measurement aid (bench.py): n_reductions red.global.add.v4.f32 to pseudo-random 16-byte slots of buf (n_floats floats, 16-byte
  * aligned) and nothing else -- timed by the caller, it is the MEASURED rate at which the L2 retires scattered 16-byte
