@@ -11,7 +11,7 @@ w = Workload("W1"); model = NGP(0.5).to(dev); w.install(model)
 ro, rd = w.test_frame(800, 800)
 for world in (1, 2, 4, 8):
     o, d = ro[::world].contiguous().to(dev), rd[::world].contiguous().to(dev)
-    for kw in ({}, {"graph_test_loop": False}):
+    for kw in ({}, {"test_loop_groups": 2}, {"test_loop_groups": 4}, {"test_loop_groups": 8}):
         for _ in range(3):
             render(model, o, d, test_time=True, T_threshold=1e-4, **kw)
         torch.cuda.synchronize()
@@ -21,4 +21,4 @@ for world in (1, 2, 4, 8):
             r = render(model, o, d, test_time=True, T_threshold=1e-4, **kw)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
-        print(f"1/{world} of the frame ({o.shape[0]} rays), {'graphs' if not kw else 'queued'}: {ms:.3f} ms per frame = {1e3 / ms:.0f} frames/s, total samples {int(r['total_samples'])}")
+        print(f"1/{world} of the frame ({o.shape[0]} rays), {kw or 'one loop'}: {ms:.3f} ms per frame = {1e3 / ms:.0f} frames/s, total samples {int(r['total_samples'])}")
