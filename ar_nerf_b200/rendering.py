@@ -131,15 +131,13 @@ def _test_workspace(R, min_samples, device):
 
 
 def _ray_groups(N_rays, kwargs):
-    """How many independent ray groups a frame's loop runs as (graph-driven loop only).  The loop is a chain of ~50 iterations of
-    seven kernels; with few rays every kernel is latency-bound and the GPU idles, so a small frame -- one rank's share of a
-    frame rendered by 8 GPUs -- is cut into interleaved groups (ray i belongs to group i mod G) whose chains are captured as
-    parallel branches of the same CUDA graphs and overlap each other.  A ray's samples and its compositing do not depend on
-    which rays share its launches, so the pixels are those of one group; the reference's schedule N_samples = max(min(N_rays //
-    N_alive, 64), min_samples) is applied per group (each an unbiased sample of the frame's pixels), and total_samples is the sum."""
-    g = kwargs.get('test_loop_groups', 1)  # default 1: the reference's schedule (and total_samples) on the frame as given
-    if g == 'auto':                         # what a renderer of frame SHARES passes (bench.py, workload.ARFrame at world > 1)
-        g = 1 if N_rays > 250_000 else (2 if N_rays > 120_000 else 4)
+    """How many independent ray groups a frame's loop runs as (graph-driven loop only; kwarg test_loop_groups, default 1).  The
+    frame is cut into interleaved groups (ray i belongs to group i mod G) whose chains are captured as parallel branches of
+    the same CUDA graphs.  A ray's samples and its compositing do not depend on which rays share its launches, so the pixels are
+    those of one loop; the schedule N_samples = max(min(N_rays // N_alive, 64), min_samples) is applied per group.
+    Measured on B200 it does NOT pay: a small frame (80 k rays, one rank's share of 8) is bound by the number of kernel launches
+    (~50 iterations x 7 kernels), not by their latency -- 1.94 ms as one loop, 2.10 / 2.25 / 2.71 ms as 2 / 4 / 8 groups."""
+    g = kwargs.get('test_loop_groups', 1)
     return max(1, min(int(g), 8, N_rays))
 
 

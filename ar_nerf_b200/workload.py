@@ -202,8 +202,7 @@ class ARFrame:
         cols = self.shade()                                                                                        # main.py:559-576
         im_bkg = torch.zeros(n, 3, device=self.dev); im_bkg[self.sel] = cols
         mesh_depth = torch.zeros(n, device=self.dev); mesh_depth[self.sel] = self.depth_obj
-        res = render(self.model, self.ro, self.rd, test_time=True, T_threshold=1e-2, max_samples=100, IM_bkg=im_bkg, mesh_depth_map=mesh_depth,
-                     test_loop_groups='auto' if self.world > 1 else 1)  # main.py:646-650
+        res = render(self.model, self.ro, self.rd, test_time=True, T_threshold=1e-2, max_samples=100, IM_bkg=im_bkg, mesh_depth_map=mesh_depth)  # main.py:646-650
         pts = self.ro + self.rd * res["depth"][:, None]                                                            # main.py:493
         smap = self.sg.calc_shadow_factor(self.model_r, pts, self.model_pos, self.lSGs)                             # main.py:501
         return res["rgb"] * smap[:, None]

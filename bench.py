@@ -454,8 +454,7 @@ def run_ours(args):
     fro, frd = fro.to(dev), frd.to(dev)
 
     def frame(i):
-        # a rank that renders a SHARE of the frame runs it as up to four interleaved ray groups whose loops overlap (rendering._ray_groups)
-        r = render(model, fro, frd, test_time=True, T_threshold=1e-4, test_loop_groups='auto' if world > 1 else 1)
+        r = render(model, fro, frd, test_time=True, T_threshold=1e-4)
         gather_frame_interleaved(torch.cat([r["rgb"], r["depth"][:, None], r["opacity"][:, None]], 1), 640000, rank, world)
 
     frame(0); frame(1)
