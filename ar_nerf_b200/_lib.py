@@ -123,6 +123,7 @@ SIGNATURES = {
     "arn_march_test_far_clamp": [P, P, P, L, P, I, I, F, F, I, P],
     "arn_march_test_all": [P, P, P, L, P, I, I, F, F, I, I, P, P, P, P],
     "arn_render_test_step_pre": [C.POINTER(TestIterCfg), P, P, P, P, P, P, I, I, L, P],
+    "arn_render_test_step_fused": [C.POINTER(TestIterCfg), P, P, P, P, P, P, I, I, L, P],
     "arn_render_test_step": [C.POINTER(TestIterCfg), P, P, P, I, I, L, P],
     "arn_train_march": [C.POINTER(TrainCfg), P],
     "arn_train_set_fork": [I, P],

@@ -1393,6 +1393,139 @@ __global__ void __launch_bounds__(1024) alive_compact_dyn_kernel(const int64_t* 
     }
 }
 
+// ---- The pre-marched iteration in FOUR launches (arn_render_test_step_fused): a small frame -- one rank's share of a frame
+// rendered by several GPUs -- is bound by the NUMBER of kernels of its ~50 iterations, not by their work.  The two scans that
+// cost the seven-launch form three kernels are replaced by atomics whose ORDER does not matter:
+//   slice_emit      N_eff of every alive ray, its place in the compact sample list (block scan + ONE atomicAdd per block: the list
+//                   is ordered inside a block of 128 rays, blocks land in arrival order), and the samples themselves
+//   (hash grid, MLP on the compact list; the sample count is read on the device)
+//   composite_keep  compositing + ray kill as before, survivors appended to the next alive list by warp-aggregated atomicAdd,
+//                   the LAST block to finish (ticket) writes the loop's next control state and resets the counters.
+// A ray's samples, its compositing and the counts do not depend on where the ray sits in either list: pixels, kill pattern and
+// total_samples are those of the seven-launch form (tests hold them identical); only the lists' order is scheduling-dependent.
+// sync (4 x int32, zero before the first iteration): {samples of this iteration, -, survivors, ticket}.
+__global__ void __launch_bounds__(128) test_slice_emit_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                              const int64_t* __restrict__ alive, const int32_t* __restrict__ state,
+                                                              const float* __restrict__ ts_all, const int32_t* __restrict__ totals,
+                                                              const int32_t* __restrict__ cursor, int64_t n_rays, ArnMarchConsts c,
+                                                              int32_t* __restrict__ n_eff, int64_t* __restrict__ rays_a, int32_t* __restrict__ sync,
+                                                              float* __restrict__ deltas, float* __restrict__ ts, float* __restrict__ xyzs,
+                                                              float* __restrict__ dirs, int64_t capacity) {
+    __shared__ int s_excl[129];
+    __shared__ int s_warp[4];
+    __shared__ int s_base;
+    const int64_t n_alive = state[kStN]; const int S = state[kStS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int64_t base = (int64_t)blockIdx.x * 128; base < n_alive; base += (int64_t)gridDim.x * 128) {
+        const int64_t n = base + tid;
+        int s = 0;
+        if (n < n_alive) { const int64_t r = alive[n]; s = min(S, totals[r] - cursor[r]); n_eff[n] = s; }
+        int inc = s;  // inclusive scan over the block
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        const int before = (wid > 0 ? s_warp[0] : 0) + (wid > 1 ? s_warp[1] : 0) + (wid > 2 ? s_warp[2] : 0);
+        const int tot = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+        s_excl[tid] = before + inc - s;
+        if (tid == 0) { s_excl[128] = tot; s_base = tot ? atomicAdd(&sync[0], tot) : 0; }
+        __syncthreads();
+        const int64_t blk0 = s_base;
+        if (n < n_alive) { rays_a[3 * n] = n; rays_a[3 * n + 1] = blk0 + s_excl[tid]; rays_a[3 * n + 2] = s; }
+        // the block's samples, one per thread and turn: which ray of the block sample e belongs to = binary search of the offsets
+        for (int e = tid; e < tot; e += 128) {
+            int lo = 0, hi = 127;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_excl[mid] <= e) lo = mid; else hi = mid - 1; }
+            // rays with no samples share their successor's offset: the LAST ray whose offset is <= e owns it (lo), and it has samples
+            const int sl = e - s_excl[lo];
+            const int64_t nj = base + lo, r = alive[nj], o = blk0 + e;
+            const float t = ts_all[(int64_t)(cursor[r] + sl) * n_rays + r];
+            ts[nj * S + sl] = t; deltas[nj * S + sl] = arn_calc_dt(c, t);
+            if (o < capacity) {
+                const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+                xyzs[3 * o] = __fmaf_rn(dx, t, rays_o[3 * r]); xyzs[3 * o + 1] = __fmaf_rn(dy, t, rays_o[3 * r + 1]); xyzs[3 * o + 2] = __fmaf_rn(dz, t, rays_o[3 * r + 2]);
+                dirs[3 * o] = dx; dirs[3 * o + 1] = dy; dirs[3 * o + 2] = dz;
+            }
+        }
+        __syncthreads();  // s_excl / s_base are rewritten by the next turn
+    }
+}
+
+__global__ void __launch_bounds__(128) test_composite_keep_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                  const float* __restrict__ deltas, const float* __restrict__ ts,
+                                                                  const int64_t* __restrict__ alive, const int32_t* __restrict__ state_in, float T_thr,
+                                                                  const int64_t* __restrict__ rays_a, float* __restrict__ opacity,
+                                                                  float* __restrict__ depth, float* __restrict__ rgb,
+                                                                  unsigned long long* __restrict__ total, int32_t* __restrict__ cursor,
+                                                                  int64_t* __restrict__ alive_out, int32_t* __restrict__ sync,
+                                                                  int32_t* __restrict__ counts_alive, int32_t* __restrict__ state_out,
+                                                                  int64_t n_rays_total, int min_samples, int budget) {
+    __shared__ int s_last;
+    const int64_t n_alive = state_in[kStN]; const int S = state_in[kStS];
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * 128; base < n_alive; base += (int64_t)gridDim.x * 128) {
+        const int64_t n = base + threadIdx.x;
+        int ne = 0; bool live = false; int64_t r = 0;
+        if (n < n_alive) {
+            ne = (int)rays_a[3 * n + 2];
+            r = alive[n];
+            if (ne > 0) {
+                live = true;
+                const int64_t c0 = rays_a[3 * n + 1];
+                cursor[r] += ne;  // the ray's next slice starts behind these samples
+                float O = opacity[r];
+                float T = __fsub_rn(1.0f, O);
+                float cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2], D = depth[r];
+                for (int s = 0; s < ne; s++) {
+                    const int64_t o = n * S + s, q = c0 + s;
+                    const float a = alpha_of(sigmas[q], deltas[o]);
+                    const float w = __fmul_rn(a, T);
+                    cr = __fmaf_rn(w, rgbs[3 * q], cr); cg = __fmaf_rn(w, rgbs[3 * q + 1], cg); cb = __fmaf_rn(w, rgbs[3 * q + 2], cb);
+                    D = __fmaf_rn(w, ts[o], D);
+                    O = __fadd_rn(O, w);
+                    T = __fmul_rn(T, __fsub_rn(1.0f, a));
+                    if (T <= T_thr) { live = false; break; }
+                }
+                opacity[r] = O; depth[r] = D; rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+            }
+        }
+        unsigned v = (unsigned)ne;  // effective samples of this iteration: warp sum, one atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (lane == 0 && v) atomicAdd(total, (unsigned long long)v);
+        // survivors: one atomicAdd per warp, the warp's survivors stay in their order
+        const unsigned keep = __ballot_sync(kFull, live);
+        int pos = 0;
+        if (lane == 0 && keep) pos = atomicAdd(&sync[2], __popc(keep));
+        pos = __shfl_sync(kFull, pos, 0);
+        if (live) alive_out[pos + __popc(keep & ((1u << lane) - 1u))] = r;
+    }
+    // the last block to get here writes the loop's next control state (the schedule of rendering.py:184-206) and resets the counters
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&sync[3], 1) == (int)gridDim.x - 1; }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const int64_t n_keep = atomicAdd(&sync[2], 0);
+        const int marched = atomicAdd(&sync[0], 0);
+        counts_alive[0] = (int32_t)n_keep; counts_alive[1] = (int32_t)n_alive;
+        int active = state_in[kStActive], done = state_in[kStDone], Sn = 1;
+        int64_t n_next = 0;
+        if (active && marched == 0) active = 0;                          // rendering.py:206: nothing was marched
+        if (active) { n_next = n_keep; if (n_next == 0 || done >= budget) active = 0; }
+        if (active) {
+            const int64_t q = n_rays_total / n_next;
+            Sn = (int)(q < 64 ? q : 64); if (Sn < min_samples) Sn = min_samples;
+            done += Sn;
+        } else n_next = 0;
+        state_out[kStN] = (int32_t)n_next; state_out[kStS] = Sn; state_out[kStDone] = done; state_out[kStActive] = active;
+        state_out[kStIters] = state_in[kStIters] + 1;
+        state_out[kStLive] = state_in[kStLive] + (state_in[kStActive] ? 1 : 0);
+        sync[0] = 0; sync[2] = 0; sync[3] = 0;
+        __threadfence();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- distortion loss
 // losses.cu:7-59,62-107: one warp per row; inclusive scans kept for the backward, loss reduced in the same pass.
 __global__ void __launch_bounds__(256) distortion_fw_kernel(const float* __restrict__ ws, const float* __restrict__ deltas,
@@ -1980,4 +2113,32 @@ extern "C" ARN_API int arn_render_test_step_pre(const arn_test_iter_t* c, const 
     ARN_LAUNCH_PDL("alive_compact_dyn_kernel", st, (alive_compact_dyn_kernel), g1024, 1024, 0, c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
                                                                                            c->counts_alive, state_out, c->n_alive, min_samples, budget_samples);
     return check_launch("alive_compact_dyn");
+}
+
+
+// arn_render_test_step_pre in four launches (kernels above): sync = 4 x int32 of device scratch, zero before the first iteration
+// of a frame (the last block of every iteration leaves it zero again).  The alive lists and the compact sample list come out in
+// a scheduling-dependent ORDER; every per-ray result, the kill pattern and total_samples are those of the seven-launch form.
+extern "C" ARN_API int arn_render_test_step_fused(const arn_test_iter_t* c, const int32_t* state_in, int32_t* state_out, int32_t* sync,
+                                                  const float* ts_all, const int32_t* totals, int32_t* cursor, int min_samples,
+                                                  int budget_samples, int64_t n_upper, arn_stream_t stream) {
+    ARN_REQUIRE(c && state_in && state_out && sync && ts_all && totals && cursor, "null pointer");
+    ARN_REQUIRE(c->n_alive > 0 && min_samples >= 1 && n_upper >= 0 && n_upper <= c->n_alive, "bad sizes");
+    ARN_REQUIRE(c->capacity >= c->n_alive * (int64_t)min_samples, "capacity must hold N_rays * min_samples samples");
+    if (int e = check_march_cfg(c->cascades, c->grid_size, c->max_samples)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nu = n_upper > 0 ? n_upper : 1;
+    const int64_t samples_upper = nu * min_samples > c->n_alive ? nu * min_samples : c->n_alive;
+    const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
+    const int g128 = (int)min((int64_t)148 * 16, (nu + 127) / 128);
+    ARN_LAUNCH("test_slice_emit_kernel", st, test_slice_emit_kernel<<<g128, 128, 0, st>>>(c->rays_o, c->rays_d, c->alive, state_in, ts_all, totals, cursor, c->n_alive, mc,
+                                                                                         c->n_eff, c->rays_a, sync, c->deltas, c->ts, c->xyzs, c->dirs, c->capacity));
+    if (int e = check_launch("test_slice_emit")) return e;
+    if (int e = arn_field_fw_tc_dyn(c->xyzs, c->dirs, samples_upper, sync, c->xyz_min_host, c->xyz_max_host, c->levels, c->params_xyz_f16,
+                                    c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
+    ARN_LAUNCH("test_composite_keep_kernel", st, test_composite_keep_kernel<<<g128, 128, 0, st>>>(c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, state_in, c->T_threshold,
+                                                                                                 c->rays_a, c->opacity, c->depth, c->rgb, (unsigned long long*)c->total_samples,
+                                                                                                 cursor, c->alive_out, sync, c->counts_alive, state_out, c->n_alive, min_samples,
+                                                                                                 budget_samples));
+    return check_launch("test_composite_keep");
 }

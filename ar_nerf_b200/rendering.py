@@ -116,7 +116,7 @@ def _make_test_ws(R, min_samples, device, own_scratch=False):
                 # graph-driven loop: the frame's inputs / outputs live at fixed addresses
                 g_rays_o=f(R, 3), g_rays_d=f(R, 3), g_hits=f(R, 2), g_opacity=f(R), g_depth=f(R), g_rgb=f(R, 3),
                 g_arange=torch.arange(R, dtype=torch.int64, device=device), g_state0=torch.zeros(8, dtype=torch.int32, device=device),
-                graphs={}, replays_hint=1, n_rays=R)
+                sync=torch.zeros(4, dtype=torch.int32, device=device), graphs={}, replays_hint=1, n_rays=R)
 
 
 def _test_workspace(R, min_samples, device):
@@ -172,7 +172,7 @@ def _test_cfg(model, w, rays_o, rays_d, hits_t2, opacity, depth, rgb, exp_step_f
         ptr(opacity), ptr(depth), ptr(rgb), None, ptr(w['total'])), (p16x, p16c)
 
 
-def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride, n_groups=1):
+def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride, n_groups=1, launches=4):
     """The device-driven loop replayed from CUDA graphs: ONE graph launch covers the frame's prologue (march of every ray,
     state / alive-list / output initialisation) plus the first _GRAPH_ITERS iterations, every further launch _GRAPH_ITERS more
     (an iteration behind the loop's end is a handful of empty kernels).  The frame's inputs are copied to fixed addresses;
@@ -202,7 +202,7 @@ def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_thr
     st = model.field_state
     key = (ptr(model.density_bitfield), model.cascades, model.grid_size, float(model.scale), float(exp_step_factor), float(T_threshold), int(max_samples),
            int(min_samples), int(stride), st.cache_xyz.get(model.xyz_encoder.params).data_ptr(), st.cache_rgb.get(model.rgb_net.params).data_ptr(),
-           tuple(st.mn), tuple(st.mx), id(st.geometry), st.rgb_act, G, tuple(sw['premarch'][0].data_ptr() for sw in subs))
+           tuple(st.mn), tuple(st.mx), id(st.geometry), st.rgb_act, G, launches, tuple(sw['premarch'][0].data_ptr() for sw in subs))
     graphs = w['graphs'].get(key)
     for g, sw in enumerate(subs):
         sw['g_rays_o'].copy_(rays_o[g::G]); sw['g_rays_d'].copy_(rays_d[g::G]); sw['g_hits'].copy_(hits_t2[g::G])
@@ -220,14 +220,20 @@ def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_thr
             call("arn_march_test_all", ptr(sw['g_rays_o']), ptr(sw['g_rays_d']), ptr(sw['g_hits']), sw['n_rays'], ptr(model.density_bitfield), model.cascades,
                  model.grid_size, float(model.scale), float(exp_step_factor), MAX_SAMPLES, stride, ptr(ts_all), ptr(totals), ptr(cursor), stream())
             sw['alive'][0].copy_(sw['g_arange']); sw['state'][0].copy_(sw['g_state0'])
-            sw['total'].zero_(); sw['g_opacity'].zero_(); sw['g_depth'].zero_(); sw['g_rgb'].zero_()
+            sw['total'].zero_(); sw['g_opacity'].zero_(); sw['g_depth'].zero_(); sw['g_rgb'].zero_(); sw['sync'].zero_()
 
         def iterations(sw, cfg, state_ptr):
+            # launches = 4: arn_render_test_step_fused (slice + emit | hash grid | MLP | compositing + survivors + state), the
+            # default; 7: arn_render_test_step_pre (two scans as kernels of their own: ordered lists) -- same pixels, same counts
             ts_all, totals, cursor = sw['premarch']
             for it in range(_GRAPH_ITERS):
                 cfg.alive, cfg.alive_out = sw['alive'][it & 1].data_ptr(), sw['alive'][(it & 1) ^ 1].data_ptr()
-                call("arn_render_test_step_pre", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(sw['partial']), ptr(ts_all), ptr(totals),
-                     ptr(cursor), min_samples, int(max_samples), sw['n_rays'], stream())
+                if launches == 4:
+                    call("arn_render_test_step_fused", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(sw['sync']), ptr(ts_all), ptr(totals),
+                         ptr(cursor), min_samples, int(max_samples), sw['n_rays'], stream())
+                else:
+                    call("arn_render_test_step_pre", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(sw['partial']), ptr(ts_all), ptr(totals),
+                         ptr(cursor), min_samples, int(max_samples), sw['n_rays'], stream())
 
         def run(with_prologue):
             if G == 1:
@@ -312,7 +318,8 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
                 and (n_groups > 1 or _premarch_table(w, stride, N_rays, device) is not None))
     if premarch and use_graph:
         try:
-            return _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride, n_groups)
+            return _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride, n_groups,
+                                      launches=7 if kwargs.get('test_loop_launches', 4) == 7 else 4)
         except torch.cuda.OutOfMemoryError:  # no room for the groups' tables: one loop, marched per iteration if need be
             w.pop('groups', None); w['graphs'].clear()
             premarch = _premarch_table(w, stride, N_rays, device) is not None

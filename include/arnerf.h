@@ -449,6 +449,15 @@ int arn_march_test_all(const float* rays_o, const float* rays_d, const float* hi
 int arn_render_test_step_pre(const arn_test_iter_t* cfg_host, const int32_t* state_in, int32_t* state_out, int32_t* partial,
                              const float* ts_all, const int32_t* totals, int32_t* cursor, int min_samples,
                              int budget_samples, int64_t n_upper, arn_stream_t stream);
+/* The same iteration in FOUR launches instead of seven (slice + emit | hash grid | MLP | compositing + survivors + control
+ * state): the two scans are replaced by atomics whose order does not matter -- the compact sample list and the next alive list
+ * come out in a scheduling-dependent ORDER, every per-ray result, the kill pattern and total_samples are those of
+ * arn_render_test_step_pre.  A small frame (one rank's share of a frame rendered by several GPUs) is bound by the number of
+ * kernels of its ~50 iterations.  sync: 4 x int32 of device scratch, zero before a frame's first iteration (every iteration
+ * leaves it zero); cfg->counts / the `partial` scratch are not used. */
+int arn_render_test_step_fused(const arn_test_iter_t* cfg_host, const int32_t* state_in, int32_t* state_out, int32_t* sync,
+                               const float* ts_all, const int32_t* totals, int32_t* cursor, int min_samples,
+                               int budget_samples, int64_t n_upper, arn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Optimizer step.  Replaces apex FusedAdam(lr, betas=(0.9,0.999), eps=1e-15, weight_decay=0) (train.py:146).

@@ -947,8 +947,10 @@ def test_fused_test_loop_equals_eager_loop(kind, thr, max_samples, w1, w3):
     w.install(model)
     ro, rd = w.test_frame(160, 120)
     kw = dict(test_time=True, T_threshold=thr, max_samples=max_samples, exp_step_factor=w.exp_step_factor)
-    a = render(model, T(ro), T(rd), **kw)                              # frame marched once + arn_render_test_step_pre, replayed from CUDA graphs
+    a = render(model, T(ro), T(rd), **kw)                              # frame marched once + arn_render_test_step_fused (4 launches per iteration), replayed from CUDA graphs
     a2 = render(model, T(ro), T(rd), **kw)                             # second frame: pure replay, the replay count taken from the first
+    g7 = render(model, T(ro), T(rd), test_loop_launches=7, **kw)       # graphs over the seven-launch iteration (ordered lists, scans as kernels)
+    assert int(g7["total_samples"]) == int(a["total_samples"]) and all(torch.equal(g7[k], a[k]) for k in ("opacity", "depth", "rgb"))
     q = render(model, T(ro), T(rd), graph_test_loop=False, **kw)       # the same iterations queued call by call, state read back late
     m = render(model, T(ro), T(rd), premarch_test_loop=False, **kw)    # arn_render_test_step: every iteration marches
     for other in (a2, q, m):
