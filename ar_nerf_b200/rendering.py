@@ -94,14 +94,13 @@ def release_test_workspace():
     _TEST_WS.clear()
 
 
-def _make_test_ws(R, min_samples, device, own_scratch=False):
+def _make_test_ws(R, min_samples, device):
     """Buffers of one device-driven test loop over R rays: every iteration marches at most n_alive * N_samples <=
     R * min_samples samples (N_samples = max(min(R // n_alive, 64), min_samples))."""
     from .field import tile_rows, _scratch
     cap = R * min_samples
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
-    # own_scratch: a loop that runs beside others (ray groups) keeps its own copy of the 20 KB MLP weight image
-    wimg = torch.empty(32768, dtype=torch.uint8, device=device) if own_scratch else _scratch(device)
+    wimg = _scratch(device)
     return dict(cap=cap, deltas=f(cap), ts=f(cap), n_eff=torch.empty(R, dtype=torch.int32, device=device),
                 rays_a=torch.empty(R, 3, dtype=torch.int64, device=device), counts=torch.zeros(4, dtype=torch.int32, device=device),
                 xyzs=f(cap, 3), dirs=f(cap, 3), sigmas=f(cap), rgbs=f(cap, 3),
@@ -128,17 +127,6 @@ def _test_workspace(R, min_samples, device):
         _TEST_WS.clear()
         _TEST_WS[key] = ws
     return ws
-
-
-def _ray_groups(N_rays, kwargs):
-    """How many independent ray groups a frame's loop runs as (graph-driven loop only; kwarg test_loop_groups, default 1).  The
-    frame is cut into interleaved groups (ray i belongs to group i mod G) whose chains are captured as parallel branches of
-    the same CUDA graphs.  A ray's samples and its compositing do not depend on which rays share its launches, so the pixels are
-    those of one loop; the schedule N_samples = max(min(N_rays // N_alive, 64), min_samples) is applied per group.
-    Measured on B200 it does NOT pay: a small frame (80 k rays, one rank's share of 8) is bound by the number of kernel launches
-    (~50 iterations x 7 kernels), not by their latency -- 1.94 ms as one loop, 2.10 / 2.25 / 2.71 ms as 2 / 4 / 8 groups."""
-    g = kwargs.get('test_loop_groups', 1)
-    return max(1, min(int(g), 8, N_rays))
 
 
 def _premarch_table(w, stride, N_rays, device):
@@ -172,120 +160,76 @@ def _test_cfg(model, w, rays_o, rays_d, hits_t2, opacity, depth, rgb, exp_step_f
         ptr(opacity), ptr(depth), ptr(rgb), None, ptr(w['total'])), (p16x, p16c)
 
 
-def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride, n_groups=1, launches=4):
+def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride, launches=7):
     """The device-driven loop replayed from CUDA graphs: ONE graph launch covers the frame's prologue (march of every ray,
     state / alive-list / output initialisation) plus the first _GRAPH_ITERS iterations, every further launch _GRAPH_ITERS more
     (an iteration behind the loop's end is a handful of empty kernels).  The frame's inputs are copied to fixed addresses;
     the host reads the control state once per batch of replays -- as many as the previous frame of this size needed.
-    n_groups > 1: the rays are dealt round-robin to that many independent loops (_ray_groups), captured as parallel branches."""
+    (Measured and dropped: dealing a small frame's rays to 2-8 independent loops captured as parallel graph branches -- 1.94 ms
+    as one loop, 2.10 / 2.25 / 2.71 ms as 2 / 4 / 8 for one rank's eighth of an 800x800 frame.)"""
     import ctypes as C
     from ._lib import call, ptr, stream
     N_rays, device = rays_o.shape[0], rays_o.device
-    G = n_groups
-    if G == 1:
-        subs = [w]
-    else:
-        subs = w.get('groups')
-        if subs is None or len(subs) != G:
-            subs = [_make_test_ws((N_rays - g + G - 1) // G, min_samples, device, own_scratch=True) for g in range(G)]
-            w['groups'] = subs
-            w['graphs'].clear()
-            w['streams'] = [torch.cuda.Stream(device=device) for _ in range(G)]
-    for g, sw in enumerate(subs):
-        if sw.get('premarch') is None or sw['premarch'][0].numel() < stride * sw['n_rays']:
-            if G == 1:
-                pass  # allocated by the caller (_premarch_table)
-            else:
-                sw['premarch'] = (torch.empty(stride * sw['n_rays'], dtype=torch.float32, device=device), torch.empty(sw['n_rays'], dtype=torch.int32, device=device),
-                                  torch.empty(sw['n_rays'], dtype=torch.int32, device=device))
-                w['graphs'].clear()
+    ts_all, totals, cursor = w['premarch']
     st = model.field_state
     key = (ptr(model.density_bitfield), model.cascades, model.grid_size, float(model.scale), float(exp_step_factor), float(T_threshold), int(max_samples),
            int(min_samples), int(stride), st.cache_xyz.get(model.xyz_encoder.params).data_ptr(), st.cache_rgb.get(model.rgb_net.params).data_ptr(),
-           tuple(st.mn), tuple(st.mx), id(st.geometry), st.rgb_act, G, launches, tuple(sw['premarch'][0].data_ptr() for sw in subs))
+           tuple(st.mn), tuple(st.mx), id(st.geometry), st.rgb_act, launches, ts_all.data_ptr())
     graphs = w['graphs'].get(key)
-    for g, sw in enumerate(subs):
-        sw['g_rays_o'].copy_(rays_o[g::G]); sw['g_rays_d'].copy_(rays_d[g::G]); sw['g_hits'].copy_(hits_t2[g::G])
+    w['g_rays_o'].copy_(rays_o); w['g_rays_d'].copy_(rays_d); w['g_hits'].copy_(hits_t2)
     if graphs is None:
+        cfg, keep = _test_cfg(model, w, w['g_rays_o'], w['g_rays_d'], w['g_hits'], w['g_opacity'], w['g_depth'], w['g_rgb'], exp_step_factor, T_threshold)
+        cfg.n_alive = N_rays
+        state_ptr = (w['state'][0].data_ptr(), w['state'][1].data_ptr())
         S0 = max(1, min_samples)
-        plans = []
-        for sw in subs:
-            cfg, keep = _test_cfg(model, sw, sw['g_rays_o'], sw['g_rays_d'], sw['g_hits'], sw['g_opacity'], sw['g_depth'], sw['g_rgb'], exp_step_factor, T_threshold)
-            cfg.n_alive = sw['n_rays']
-            sw['g_state0'].copy_(torch.tensor([sw['n_rays'], S0, S0, 1 if max_samples > 0 else 0, 0, 0, 0, 0], dtype=torch.int32))
-            plans.append((sw, cfg, keep, (sw['state'][0].data_ptr(), sw['state'][1].data_ptr())))
+        w['g_state0'].copy_(torch.tensor([N_rays, S0, S0, 1 if max_samples > 0 else 0, 0, 0, 0, 0], dtype=torch.int32))
 
-        def prologue(sw, cfg):
-            ts_all, totals, cursor = sw['premarch']
-            call("arn_march_test_all", ptr(sw['g_rays_o']), ptr(sw['g_rays_d']), ptr(sw['g_hits']), sw['n_rays'], ptr(model.density_bitfield), model.cascades,
+        def prologue():
+            call("arn_march_test_all", ptr(w['g_rays_o']), ptr(w['g_rays_d']), ptr(w['g_hits']), N_rays, ptr(model.density_bitfield), model.cascades,
                  model.grid_size, float(model.scale), float(exp_step_factor), MAX_SAMPLES, stride, ptr(ts_all), ptr(totals), ptr(cursor), stream())
-            sw['alive'][0].copy_(sw['g_arange']); sw['state'][0].copy_(sw['g_state0'])
-            sw['total'].zero_(); sw['g_opacity'].zero_(); sw['g_depth'].zero_(); sw['g_rgb'].zero_(); sw['sync'].zero_()
+            w['alive'][0].copy_(w['g_arange']); w['state'][0].copy_(w['g_state0'])
+            w['total'].zero_(); w['g_opacity'].zero_(); w['g_depth'].zero_(); w['g_rgb'].zero_(); w['sync'].zero_()
 
-        def iterations(sw, cfg, state_ptr):
-            # launches = 4: arn_render_test_step_fused (slice + emit | hash grid | MLP | compositing + survivors + state), the
-            # default; 7: arn_render_test_step_pre (two scans as kernels of their own: ordered lists) -- same pixels, same counts
-            ts_all, totals, cursor = sw['premarch']
+        def iterations():
+            # launches = 7: arn_render_test_step_pre (the default: ordered lists, the two scans as kernels of their own); 4:
+            # arn_render_test_step_fused (slice + emit | hash grid | MLP | compositing + survivors + state) -- same pixels, same
+            # counts, lists in arrival order.  Measured equal (800x800: 5.48 / 5.52 ms; an eighth of it: 2.00 / 1.95 ms): inside a
+            # graph the three small kernels cost next to nothing, an iteration is the latency of its hash-grid and MLP launches
             for it in range(_GRAPH_ITERS):
-                cfg.alive, cfg.alive_out = sw['alive'][it & 1].data_ptr(), sw['alive'][(it & 1) ^ 1].data_ptr()
+                cfg.alive, cfg.alive_out = w['alive'][it & 1].data_ptr(), w['alive'][(it & 1) ^ 1].data_ptr()
                 if launches == 4:
-                    call("arn_render_test_step_fused", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(sw['sync']), ptr(ts_all), ptr(totals),
-                         ptr(cursor), min_samples, int(max_samples), sw['n_rays'], stream())
+                    call("arn_render_test_step_fused", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(w['sync']), ptr(ts_all), ptr(totals),
+                         ptr(cursor), min_samples, int(max_samples), N_rays, stream())
                 else:
-                    call("arn_render_test_step_pre", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(sw['partial']), ptr(ts_all), ptr(totals),
-                         ptr(cursor), min_samples, int(max_samples), sw['n_rays'], stream())
-
-        def run(with_prologue):
-            if G == 1:
-                sw, cfg, _, sp = plans[0]
-                if with_prologue:
-                    prologue(sw, cfg)
-                iterations(sw, cfg, sp)
-                return
-            main = torch.cuda.current_stream()
-            for (sw, cfg, _, sp), side in zip(plans, w['streams']):  # fork: every group's chain on its own stream
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    if with_prologue:
-                        prologue(sw, cfg)
-                    iterations(sw, cfg, sp)
-            for side in w['streams']:                                  # join
-                main.wait_stream(side)
+                    call("arn_render_test_step_pre", C.byref(cfg), state_ptr[it & 1], state_ptr[(it & 1) ^ 1], ptr(w['partial']), ptr(ts_all), ptr(totals),
+                         ptr(cursor), min_samples, int(max_samples), N_rays, stream())
 
         # one eager pass first: module loading and the kernels' one-time attribute calls are not capturable
-        run(True)
+        prologue(); iterations()
         torch.cuda.current_stream().synchronize()
         first, more = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(first, capture_error_mode="thread_local"):
-            run(True)
+            prologue(); iterations()
         with torch.cuda.graph(more, capture_error_mode="thread_local"):
-            run(False)
-        graphs = (first, more, plans)
+            iterations()
+        graphs = (first, more, keep)
         w['graphs'].clear()  # one configuration at a time
         w['graphs'][key] = graphs
     first, more, _ = graphs
     first.replay()
     queued, want = 1, max(1, w['replays_hint'])
-    cur = torch.cuda.current_stream()
     while True:
         while queued < want:
             more.replay(); queued += 1
-        for sw in subs:
-            sw['state_host'][0].copy_(sw['state'][0], non_blocking=True)   # _GRAPH_ITERS is even: the last state written is state[0]
-        w['state_ev'][0].record(cur)
+        w['state_host'][0].copy_(w['state'][0], non_blocking=True)   # _GRAPH_ITERS is even: the last state written is state[0]
+        w['state_ev'][0].record(torch.cuda.current_stream())
         w['state_ev'][0].synchronize()
-        active = any(int(sw['state_host'][0][3]) for sw in subs)
-        live_iters = max(int(sw['state_host'][0][5]) for sw in subs)
+        active, live_iters = int(w['state_host'][0][3]), int(w['state_host'][0][5])
         if not active or queued * _GRAPH_ITERS > int(max_samples):  # every live iteration requests at least one sample
             break
         want = queued + 1
     w['replays_hint'] = max(1, -(-live_iters // _GRAPH_ITERS))
-    if G == 1:
-        return w['g_opacity'].clone(), w['g_depth'].clone(), w['g_rgb'].clone(), w['total'][0].clone()
-    opacity = torch.empty(N_rays, device=device); depth = torch.empty(N_rays, device=device); rgb = torch.empty(N_rays, 3, device=device)
-    for g, sw in enumerate(subs):
-        opacity[g::G] = sw['g_opacity']; depth[g::G] = sw['g_depth']; rgb[g::G] = sw['g_rgb']
-    return opacity, depth, rgb, torch.stack([sw['total'][0] for sw in subs]).sum()
+    return w['g_opacity'].clone(), w['g_depth'].clone(), w['g_rgb'].clone(), w['total'][0].clone()
 
 
 @torch.no_grad()
@@ -312,17 +256,11 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
     # The frame's samples are marched once, in front of the loop (arn_march_test_all), when their table fits: the loop never
     # asks a ray for more than max_samples + 63 samples.  Otherwise the iterations march (far-clamped rays).
     stride = int(max(1, max_samples)) + 64
-    use_graph = kwargs.get('graph_test_loop', True) and not torch.cuda.is_current_stream_capturing()
-    n_groups = _ray_groups(N_rays, kwargs) if use_graph else 1
     premarch = (not host_driven and kwargs.get('premarch_test_loop', True) and max_samples > 0 and stride * N_rays * 4 <= _PREMARCH_MAX_BYTES
-                and (n_groups > 1 or _premarch_table(w, stride, N_rays, device) is not None))
-    if premarch and use_graph:
-        try:
-            return _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride, n_groups,
-                                      launches=7 if kwargs.get('test_loop_launches', 4) == 7 else 4)
-        except torch.cuda.OutOfMemoryError:  # no room for the groups' tables: one loop, marched per iteration if need be
-            w.pop('groups', None); w['graphs'].clear()
-            premarch = _premarch_table(w, stride, N_rays, device) is not None
+                and _premarch_table(w, stride, N_rays, device) is not None)
+    if premarch and kwargs.get('graph_test_loop', True) and not torch.cuda.is_current_stream_capturing():
+        return _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride,
+                                  launches=4 if kwargs.get('test_loop_launches', 7) == 4 else 7)
     opacity = torch.zeros(N_rays, device=device)
     depth = torch.zeros(N_rays, device=device)
     rgb = torch.zeros(N_rays, 3, device=device)

@@ -11,7 +11,7 @@ w = Workload("W1"); model = NGP(0.5).to(dev); w.install(model)
 ro, rd = w.test_frame(800, 800)
 for world in (1, 2, 4, 8):
     o, d = ro[::world].contiguous().to(dev), rd[::world].contiguous().to(dev)
-    for kw in ({}, {"test_loop_launches": 7}, {"graph_test_loop": False}):
+    for kw in ({}, {"test_loop_launches": 4}, {"graph_test_loop": False}):
         for _ in range(3):
             render(model, o, d, test_time=True, T_threshold=1e-4, **kw)
         torch.cuda.synchronize()
