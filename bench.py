@@ -517,8 +517,9 @@ def run_ours(args):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": BATCH, "samples_per_step_per_gpu": N,
-                           "parallelism": f"dp{world} (rays sharded; hash-table gradient reduce-scatter + sharded Adam + all-gather as peer-memory kernels over NVLink, "
-                                          f"pipelined per level group behind the hash-grid backward; NCCL all-reduce of the MLP gradients)" if world > 1 else "dp1",
+                           "parallelism": f"dp{world} (rays sharded; hash-table gradient reduce-scatter + sharded Adam + all-gather as ONE peer-memory kernel over NVLink"
+                                          f"{' per level group ' + str(trainer.level_groups) + ', behind the level-major hash-grid backward' if trainer.level_groups else ''}; "
+                                          f"NCCL all-reduce of the MLP gradients)" if world > 1 else "dp1",
                            "l2_policy": "no explicit flush: one step streams ~350 MB (fp32 master + Adam moments + gradients 206 MB, activations ~140 MB) > 126 MB L2",
                            "grid_update": "every 16 steps inside the timed region (steady-state form of steps >= 256: G^3/4 uniform + G^3/4 occupied cells)",
                            "timing": f"{windows} window(s) of {args.steps} steps each, starting at phases 0,2,..,14 of the 16-step refresh cycle; value = mean window"},
