@@ -145,7 +145,8 @@ def test_frame_stages(model, rays_o, rays_d, T_threshold=1e-4):
     saved = rendering.vren
     try:
         for name, v in (("reference", ref), ("ours", ours)):
-            for rep in range(2):  # the second pass is the timed one
+            best = None
+            for rep in range(4):  # one untimed pass, then the best of three (the loop's host syncs make single passes noisy)
                 sw = Swap(v)
                 rendering.vren = sw
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -153,7 +154,10 @@ def test_frame_stages(model, rays_o, rays_d, T_threshold=1e-4):
                 out = rendering.render(model, rays_o, rays_d, test_time=True, T_threshold=T_threshold, eager_test_loop=True)
                 f1.record()
                 torch.cuda.synchronize()
-            res[name] = {"ms": sum(a.elapsed_time(b) for a, b in sw.ev), "calls": len(sw.ev), "rgb": out["rgb"], "frame_ms": f0.elapsed_time(f1)}
+                cur = {"ms": sum(a.elapsed_time(b) for a, b in sw.ev), "calls": len(sw.ev), "rgb": out["rgb"], "frame_ms": f0.elapsed_time(f1)}
+                if rep > 0 and (best is None or cur["ms"] < best["ms"]):
+                    best = cur
+            res[name] = best
     finally:
         rendering.vren = saved
     same = bool(torch.equal(res["reference"]["rgb"], res["ours"]["rgb"]))
