@@ -76,6 +76,7 @@ SIGNATURES = {
     "arn_p2p_wait": [P, I, I, C.c_uint64, P],
     "arn_p2p_barrier": [C.POINTER(C.c_void_p), P, I, I, I, C.c_uint64, P],
     "arn_p2p_adam_exchange": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), I, L, L, P, P, P, F, F, F, F, I, F, P],
+    "arn_p2p_adam_exchange_mc": [P, P, L, L, P, P, P, F, F, F, F, I, F, P],
     "arn_p2p_set_timeout": [C.c_double],
     "arn_p2p_set_error_word": [P],
     "arn_p2p_set_grid": [I],

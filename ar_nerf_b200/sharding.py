@@ -174,25 +174,58 @@ class PeerExchange:
             _lib.call("arn_p2p_export", ptr, buf)
             return buf.raw
 
-        with torch.cuda.device(device):
-            self.g_ptr, self.h_ptr, self.f_ptr = alloc(self.P * 4), alloc(self.P * 2), alloc(4096)
-            mine = (export(self.g_ptr), export(self.h_ptr), export(self.f_ptr))
-            everyone = [None] * world
-            dist.all_gather_object(everyone, mine)
-            arrs = []
-            for k, own in enumerate((self.g_ptr, self.h_ptr, self.f_ptr)):
-                ptrs = []
-                for r in range(world):
-                    if r == rank:
-                        ptrs.append(own)
-                    else:
-                        out = C.c_void_p()
-                        _lib.call("arn_p2p_open", everyone[r][k], C.byref(out))
-                        ptrs.append(out.value)
-                arrs.append((C.c_void_p * world)(*ptrs))
-            self.G, self.H, self.F = arrs
-        self.grad = torch.as_tensor(_RawCuda(self.g_ptr, self.P, "<f4"), device=device)
-        self.p16 = torch.as_tensor(_RawCuda(self.h_ptr, self.P, "<f2"), device=device)
+        # Buffers every rank can address: torch symmetric memory when it rendezvouses (it also hands out MULTICAST addresses of
+        # the ranks' buffers -- NVLS: the switch reduces and replicates, arn_p2p_adam_exchange_mc), else cudaMalloc + CUDA IPC
+        # handles (peer loads / stores only).  ARN_P2P_BACKEND=ipc forces the latter.  Every rank must take the same branch.
+        self.mc_grad = self.mc_p16 = None
+        self._symm = None
+        ok = torch.zeros(1, device=device)
+        if os.environ.get("ARN_P2P_BACKEND", "symm") == "symm":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                gname = dist.group.WORLD.group_name
+                with torch.cuda.device(device):
+                    g = symm.empty(self.P, dtype=torch.float32, device=device)
+                    h = symm.empty(self.P, dtype=torch.float16, device=device)
+                    f = symm.empty(1024, dtype=torch.int32, device=device)
+                    g.zero_(); h.zero_(); f.zero_()
+                    hg, hh, hf = symm.rendezvous(g, gname), symm.rendezvous(h, gname), symm.rendezvous(f, gname)
+                self._symm = (g, h, f, hg, hh, hf)
+                ok.fill_(1.0)
+            except Exception as e:  # noqa: BLE001 -- any failure means "use IPC"
+                print(f"[ar_nerf_b200] symmetric memory unavailable on rank {rank} ({type(e).__name__}: {e}); using CUDA IPC")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 1.0:
+            g, h, f, hg, hh, hf = self._symm
+            self.grad, self.p16 = g, h
+            self.g_ptr, self.h_ptr, self.f_ptr = g.data_ptr(), h.data_ptr(), f.data_ptr()
+            self.G = (C.c_void_p * world)(*[int(x) for x in hg.buffer_ptrs])
+            self.H = (C.c_void_p * world)(*[int(x) for x in hh.buffer_ptrs])
+            self.F = (C.c_void_p * world)(*[int(x) for x in hf.buffer_ptrs])
+            mg, mh = int(getattr(hg, "multicast_ptr", 0) or 0), int(getattr(hh, "multicast_ptr", 0) or 0)
+            if mg and mh and not os.environ.get("ARN_P2P_NO_MULTICAST"):
+                self.mc_grad, self.mc_p16 = mg, mh
+        else:
+            self._symm = None
+            with torch.cuda.device(device):
+                self.g_ptr, self.h_ptr, self.f_ptr = alloc(self.P * 4), alloc(self.P * 2), alloc(4096)
+                mine = (export(self.g_ptr), export(self.h_ptr), export(self.f_ptr))
+                everyone = [None] * world
+                dist.all_gather_object(everyone, mine)
+                arrs = []
+                for k, own in enumerate((self.g_ptr, self.h_ptr, self.f_ptr)):
+                    ptrs = []
+                    for r in range(world):
+                        if r == rank:
+                            ptrs.append(own)
+                        else:
+                            out = C.c_void_p()
+                            _lib.call("arn_p2p_open", everyone[r][k], C.byref(out))
+                            ptrs.append(out.value)
+                    arrs.append((C.c_void_p * world)(*ptrs))
+                self.G, self.H, self.F = arrs
+            self.grad = torch.as_tensor(_RawCuda(self.g_ptr, self.P, "<f4"), device=device)
+            self.p16 = torch.as_tensor(_RawCuda(self.h_ptr, self.P, "<f2"), device=device)
         self.zero_stream = torch.cuda.Stream(device=device)
         # the exchange runs on its own high-priority stream: its blocks take the SM slots the hash-grid backward's blocks free
         self.x_stream = torch.cuda.Stream(device=device, priority=-1)
@@ -218,7 +251,10 @@ class PeerExchange:
     def _exchange_group(self, g, p_flat, m, v, hyper, cuda_stream):
         from ._lib import call, ptr
         lo, cnt, off = self.groups[g]
-        if cnt > 0:
+        if cnt > 0 and self.mc_grad is not None:
+            call("arn_p2p_adam_exchange_mc", self.mc_grad, self.mc_p16, lo, cnt, ptr(p_flat[lo:lo + cnt]), ptr(m[off:off + cnt]), ptr(v[off:off + cnt]),
+                 *hyper, cuda_stream)
+        elif cnt > 0:
             call("arn_p2p_adam_exchange", self.G, self.H, self.world, lo, cnt, ptr(p_flat[lo:lo + cnt]), ptr(m[off:off + cnt]), ptr(v[off:off + cnt]),
                  *hyper, cuda_stream)
 

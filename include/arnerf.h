@@ -506,6 +506,13 @@ int arn_p2p_barrier(void* const* peer_flags_host, const void* my_flags, int n_ra
  * synchronisation needed) and decides: raise, or fall back to the NCCL form of the same sharding.
  * arn_p2p_set_grid: thread blocks per SM of the exchange kernel (default 8); a caller that overlaps the exchange of one level
  * group with the hash-grid backward of the next (arn_train_set_level_groups) asks for 1-2 so that both hold SM slots. */
+/* arn_p2p_adam_exchange through the NVSwitch's multicast (NVLS): mc_grads / mc_p16 are MULTICAST addresses of the ranks'
+ * gradient / fp16 buffers (same offsets on every rank; torch symmetric memory hands them out).  The gradient sum of a float4
+ * group is ONE multimem.ld_reduce (the switch adds the ranks' copies: the reduction order is the fabric's), the fp16 result
+ * ONE multimem.st into every rank's copy -- 43 / 26 MB per link direction and step at 8 ranks instead of 60 / 60. */
+int arn_p2p_adam_exchange_mc(const void* mc_grads, void* mc_p16, int64_t lo, int64_t count, float* params_slice,
+                             float* exp_avg_slice, float* exp_avg_sq_slice, float lr, float beta1, float beta2, float eps,
+                             int step, float inv_grad_scale, arn_stream_t stream);
 int arn_p2p_set_timeout(double seconds);
 int arn_p2p_set_error_word(void* err_word);
 int arn_p2p_set_grid(int blocks_per_sm);
