@@ -392,11 +392,19 @@ def run_ours(args):
             ach = model_flops[top] / launches_per_step / per_launch_s / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": traffic.get(top),
                     "peak_source": peak_src + " (sustained bf16)", "ms_per_launch": per_launch_s * 1e3}
-        elif top == "p2p_adam_exchange_kernel":
-            ach = nvlink_bytes / launches_per_step / per_launch_s / 1e9
+        elif top in ("p2p_adam_exchange_kernel", "p2p_adam_exchange_mc_kernel"):
+            if top.endswith("_mc_kernel"):
+                # NVLS: the switch reads this rank's gradient for the other ranks' slices and this rank multicasts its fp16 slice once
+                # (outbound); the reduced gradient of the own slice and the other ranks' fp16 slices come in.  Outbound is the larger.
+                nv_bytes = 4.0 * n_table * (world - 1) / world + 2.0 * n_table / world
+                what = ("busier link direction (outbound) per rank: the switch's reads of this rank's fp32 gradient for the other ranks' slices + one multicast "
+                        "store of the own fp16 slice; inbound carries the reduced own slice + the other ranks' fp16 slices")
+            else:
+                nv_bytes = nvlink_bytes
+                what = "bytes per rank and direction over NVLink: fp32 gradient slices of the other ranks in, fp16 table slices of the other ranks in (and the same out)"
+            ach = nv_bytes / launches_per_step / per_launch_s / 1e9
             roof = {"kernel": top, "bound": "nvlink", "achieved": ach, "peak": PEER_COPY_GBS, "unit": "GB/s", "frac": ach / PEER_COPY_GBS, "traffic": None,
-                    "peak_source": "measured peer copy per direction (B200_PROFILING.md)", "ms_per_launch": per_launch_s * 1e3,
-                    "note": "bytes per rank and direction over NVLink: fp32 gradient slices of the other ranks in, fp16 table slices of the other ranks in (and the same out)"}
+                    "peak_source": "measured peer copy per direction (B200_PROFILING.md)", "ms_per_launch": per_launch_s * 1e3, "note": what}
         else:
             ach = model_bytes.get(top, 0.0) / launches_per_step / per_launch_s / 1e9
             roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic.get(top),
@@ -517,7 +525,7 @@ def run_ours(args):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": BATCH, "samples_per_step_per_gpu": N,
-                           "parallelism": f"dp{world} (rays sharded; hash-table gradient reduce-scatter + sharded Adam + all-gather as ONE peer-memory kernel over NVLink"
+                           "parallelism": f"dp{world} (rays sharded; hash-table gradient reduce-scatter + sharded Adam + all-gather as ONE kernel over NVLink -- through the NVSwitch's multicast (multimem.ld_reduce / multimem.st) where symmetric memory provides it, peer loads / stores otherwise"
                                           f"{' per level group ' + str(trainer.level_groups) + ', behind the level-major hash-grid backward' if trainer.level_groups else ''}; "
                                           f"NCCL all-reduce of the MLP gradients)" if world > 1 else "dp1",
                            "l2_policy": "no explicit flush: one step streams ~350 MB (fp32 master + Adam moments + gradients 206 MB, activations ~140 MB) > 126 MB L2",
