@@ -23,7 +23,7 @@ struct LaunchTimer {
 };
 
 // Kernel-variant switches for A/B measurements (arn_set_tunable): every variant computes the same results.
-enum Tunable { kTunMarchWarp = 0, kTunHashBwMode, kTunAdamVec, kTunPipelineParts, kTunHashBwBlocks, kTunMlpWide, kTunPdl, kTunCount };
+enum Tunable { kTunMarchWarp = 0, kTunHashBwMode, kTunAdamVec, kTunPipelineParts, kTunHashBwBlocks, kTunMlpWide, kTunPdl, kTunP2pMc, kTunCount };
 int tunable(Tunable t);
 
 inline int check_launch(const char* what) {

@@ -22,8 +22,8 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- kernel-variant switches
-static std::atomic<int> g_tun[kTunCount] = {{1}, {16}, {1}, {1}, {0}, {3}, {0}};
-static const char* const g_tun_names[kTunCount] = {"march_warp", "hash_bw_mode", "adam_vec", "pipeline_parts", "hash_bw_blocks", "mlp_wide", "pdl"};
+static std::atomic<int> g_tun[kTunCount] = {{1}, {16}, {1}, {1}, {0}, {3}, {0}, {4256}};
+static const char* const g_tun_names[kTunCount] = {"march_warp", "hash_bw_mode", "adam_vec", "pipeline_parts", "hash_bw_blocks", "mlp_wide", "pdl", "p2p_mc"};
 int tunable(Tunable t) { return g_tun[t].load(std::memory_order_relaxed); }
 
 // ---- side stream + events for the pipelined field evaluation, one set per device

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) p2p_adam_exchange_kernel(PeerF32 grads, P
 // / 26 MB per direction instead of 60 / 60.  mc_grad / mc_p16: multicast addresses of the ranks' gradient / fp16 buffers
 // (torch symmetric memory: sharding.PeerExchange).  The reduction order is the switch's (fixed by the fabric), not rank order.
 template <int U>
-__global__ void __launch_bounds__(256) p2p_adam_exchange_mc_kernel(const float* __restrict__ mc_grad, __half* __restrict__ mc_p16, int64_t lo, int64_t n4,
+__global__ void __launch_bounds__(U >= 8 ? 128 : (U >= 4 ? 256 : 512)) p2p_adam_exchange_mc_kernel(const float* __restrict__ mc_grad, __half* __restrict__ mc_p16, int64_t lo, int64_t n4,
                                                                    float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
                                                                    float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float inv_gs) {
     if (*reinterpret_cast<const volatile unsigned int*>(&g_err_dev) != 0u) return;
@@ -307,9 +307,15 @@ extern "C" ARN_API int arn_p2p_adam_exchange_mc(const void* mc_grads, void* mc_p
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
     const int64_t n4 = count / 4;
-    const int grid = (int)min((int64_t)148 * g_blocks_per_sm, (n4 + 255) / 256);
+    // "p2p_mc" tunable = 1000 * (float4 groups per thread) + threads per block (A/B: how many multimem.ld_reduce are in flight)
+    const int var = tunable(kTunP2pMc), U = var / 1000, threads = var % 1000;
+    ARN_REQUIRE((U == 1 || U == 2 || U == 4 || U == 8) && (threads == 128 || threads == 256 || threads == 512), "bad p2p_mc variant");
+    ARN_REQUIRE(threads <= (U >= 8 ? 128 : (U >= 4 ? 256 : 512)), "p2p_mc: too many threads for that many groups per thread");
+    const int grid = (int)min((int64_t)148 * g_blocks_per_sm * (256 / min(threads, 256)), (n4 + threads - 1) / threads);
     cudaStream_t st = (cudaStream_t)stream;
-    ARN_LAUNCH("p2p_adam_exchange_mc_kernel", st, (p2p_adam_exchange_mc_kernel<4><<<grid, 256, 0, st>>>((const float*)mc_grads, (__half*)mc_p16, lo, n4, (float4*)params_slice,
-               (float4*)exp_avg_slice, (float4*)exp_avg_sq_slice, lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale)));
+#define ARN_MC(UU) ARN_LAUNCH("p2p_adam_exchange_mc_kernel", st, (p2p_adam_exchange_mc_kernel<UU><<<grid, threads, 0, st>>>((const float*)mc_grads, (__half*)mc_p16, lo, n4, \
+        (float4*)params_slice, (float4*)exp_avg_slice, (float4*)exp_avg_sq_slice, lr, beta1, beta2, eps, bc1, bc2_sqrt, inv_grad_scale)))
+    if (U == 1) ARN_MC(1); else if (U == 2) ARN_MC(2); else if (U == 4) ARN_MC(4); else ARN_MC(8);
+#undef ARN_MC
     return check_launch("p2p_adam_exchange_mc");
 }

@@ -31,8 +31,16 @@ def timeit(fn, iters=100):
     t = torch.tensor([e0.elapsed_time(e1) / iters * 1e3], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t)
+from ar_nerf_b200 import _lib
 t_full = timeit(full)
 t_bar = timeit(barrier_only, 300)
 if rank == 0:
-    print(f"world {world}: exchange step (barrier + kernel + barrier + zeroing, no skew) {t_full:.1f} us; bare barrier {t_bar:.1f} us; table {n * 4 / 1e6:.1f} MB")
+    print(f"world {world}: exchange step (barrier + kernel + barrier + zeroing, no skew) {t_full:.1f} us; bare barrier {t_bar:.1f} us; table {n * 4 / 1e6:.1f} MB; multicast {px.mc_grad is not None}")
+if px.mc_grad is not None and os.environ.get("SWEEP"):
+    for var in (1256, 1512, 2256, 2512, 4128, 4256, 8128):
+        for g in (2, 4, 8):
+            _lib.set_tunable("p2p_mc", var); px.grid_tail = g
+            t = timeit(full, 60)
+            if rank == 0:
+                print(f"   p2p_mc {var} blocks/SM cap {g}: {t:.1f} us")
 dist.destroy_process_group()
