@@ -203,7 +203,10 @@ class PeerExchange:
             self.H = (C.c_void_p * world)(*[int(x) for x in hh.buffer_ptrs])
             self.F = (C.c_void_p * world)(*[int(x) for x in hf.buffer_ptrs])
             mg, mh = int(getattr(hg, "multicast_ptr", 0) or 0), int(getattr(hh, "multicast_ptr", 0) or 0)
-            if mg and mh and not os.environ.get("ARN_P2P_NO_MULTICAST"):
+            # the multicast form pays from 8 ranks on (0.430 -> 0.399 ms per step); at 4 it measures equal (0.407), at 2 the
+            # switch's read of both copies costs more than the one peer load it replaces (0.379 -> 0.415): peer loads / stores there
+            want_mc = os.environ.get("ARN_P2P_MULTICAST", "1" if world >= 8 else "0") == "1" and not os.environ.get("ARN_P2P_NO_MULTICAST")
+            if mg and mh and want_mc:
                 self.mc_grad, self.mc_p16 = mg, mh
         else:
             self._symm = None
