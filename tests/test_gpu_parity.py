@@ -1148,3 +1148,55 @@ def test_level_grouped_backward_and_pipelined_adam(groups, w1, monkeypatch):
     assert (model_a.xyz_encoder.params.grad == 0).all()  # every group's Adam zeroed its range
     h16 = model_a.field_state.cache_xyz.get(model_a.xyz_encoder.params)[:pa.numel()]
     assert torch.equal(h16, pa.half())                   # ... and refreshed its range of the fp16 working copy
+
+
+def test_gather_batch_and_feeder(vren):
+    """arn_gather_batch (rays + the batch's pixels from the device-resident images, datasets/base.py:32 + train.py:121-126) against
+    the torch expressions, and trainer.BatchFeeder's slots (indices copied host -> device, batches built on the copy stream)."""
+    from ar_nerf_b200.trainer import BatchFeeder, DeviceDataset
+    from ar_nerf_b200.workload import get_rays, intrinsics, look_at_poses, ray_directions
+    K = intrinsics(64, 48)
+    directions = ray_directions(48, 64, K)
+    poses = look_at_poses(5, 1.5, 3)
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand(5, 64 * 48, 4, generator=g)  # rgb + exposure (HDR-NeRF data)
+    ds = DeviceDataset(poses, images, directions, dev())
+    n = 1000
+    img = torch.randint(5, (n,), generator=g); pix = torch.randint(64 * 48, (n,), generator=g)
+    ro, rd, px = vren.gather_batch(ds.poses, T(img), T(pix), ds.images, directions=ds.directions)
+    want_o, want_d = get_rays(directions[pix], poses[img])
+    assert torch.equal(ro.cpu(), want_o) and torch.equal(px.cpu(), images[img, pix])
+    assert_rel(N(rd), want_d.numpy(), rtol=1e-6, what="rays_d")
+    feeder = BatchFeeder(DeviceDataset(poses, images[:, :, :3].contiguous(), directions, dev()), n)
+    idx = [torch.stack([torch.randint(5, (n,), generator=g), torch.randint(64 * 48, (n,), generator=g)]).pin_memory() for _ in range(7)]
+    for i in range(7):
+        feeder.stage(i, idx[i])
+        if i + 1 < 7:
+            feeder.stage(i + 1, idx[i + 1])
+        o, d, c = feeder.get(i)
+        torch.cuda.current_stream().synchronize()
+        wo, _ = get_rays(directions[idx[i][1]], poses[idx[i][0]])
+        assert torch.equal(o.cpu(), wo) and torch.equal(c.cpu(), images[idx[i][0], idx[i][1], :3]), i
+        feeder.done(i)
+
+
+def test_hdr_mode_trains_every_parameter(w1):
+    """rgb_act='None' (HDR-NeRF mode, networks.py:80-93,110-131): the eager step optimises the three tonemapper nets with the
+    field's parameters, as train.py:141-146 does, and zeroes their gradients."""
+    from ar_nerf_b200.networks import NGP
+    from ar_nerf_b200.trainer import NGPTrainer
+    torch.manual_seed(0)
+    model = NGP(w1.scale, rgb_act='None').to(dev())
+    w1.install(model)
+    tr = NGPTrainer(model)
+    assert not tr.fused and len(tr.opt.items) == 5
+    before = [getattr(model, f"tonemapper_net_{i}").params.detach().clone() for i in range(3)]
+    px = model.xyz_encoder.params.detach().clone()
+    for step in range(2):
+        ro, rd, target, noise = [T(t) for t in w1.train_batch(step, 1024)]
+        loss, _ = tr.train_step(ro, rd, target, noise=noise, update_grid=False)
+        assert torch.isfinite(loss)
+    for i in range(3):
+        p = getattr(model, f"tonemapper_net_{i}").params
+        assert not torch.equal(p.detach(), before[i]) and float(p.grad.abs().max()) == 0.0
+    assert not torch.equal(model.xyz_encoder.params.detach(), px)
