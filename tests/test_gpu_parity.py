@@ -1166,7 +1166,7 @@ def test_gather_batch_and_feeder(vren):
     ro, rd, px = vren.gather_batch(ds.poses, T(img), T(pix), ds.images, directions=ds.directions)
     want_o, want_d = get_rays(directions[pix], poses[img])
     assert torch.equal(ro.cpu(), want_o) and torch.equal(px.cpu(), images[img, pix])
-    assert_rel(N(rd), want_d.numpy(), rtol=1e-6, what="rays_d")
+    assert_rel(N(rd), want_d.numpy(), rtol=4e-6, what="rays_d")  # three-term dot products: fp32 order against torch bmm (the sibling test uses 2e-6)
     feeder = BatchFeeder(DeviceDataset(poses, images[:, :, :3].contiguous(), directions, dev()), n)
     idx = [torch.stack([torch.randint(5, (n,), generator=g), torch.randint(64 * 48, (n,), generator=g)]).pin_memory() for _ in range(7)]
     for i in range(7):
