@@ -14,6 +14,9 @@
  *   - outputs are written completely by the kernels (no pre-zeroing by the caller is needed) unless stated.
  *   - "in place" tensors keep the reference's in-place semantics: density_bitfield, hits_t (test march),
  *     alive_indices, opacity/depth/rgb (test compositing).
+ *   - one process per GPU, one calling thread per device: the side stream / event pool of the pipelined field evaluation, the
+ *     arn_train_set_* switches (thread-local) and the peer-exchange settings are per process, not per calling stream.  Kernel
+ *     attributes that depend on the device (shared-memory limits of the MLP kernels) are set per device on first use.
  */
 #ifndef ARNERF_H_
 #define ARNERF_H_
@@ -24,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ARN_VERSION 100 /* round 1 */
+#define ARN_VERSION 200 /* round 2 */
 
 #define ARN_OK 0
 #define ARN_E_INVALID (-1) /* bad argument (null pointer, negative size, unsupported configuration) */

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/arnerf.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in ar_nerf_b200/_lib.py"
-    assert _lib.lib().arn_version() == 100
+    assert _lib.lib().arn_version() == 200
     assert _lib.lib().arn_last_error() == b""
 
 
