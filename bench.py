@@ -16,6 +16,8 @@ import subprocess
 import sys
 import time
 
+_STDOUT = sys.stdout
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -181,7 +183,7 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
             "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_STDOUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
@@ -287,7 +289,8 @@ def run_ours(args):
     if args.train_only:
         if rank == 0:
             print(json.dumps({"metric": "train_Mrays_per_s", "value": value, "ms_per_step": ms_total / args.steps, "train_only": True,
-                              "ms_per_step_no_refresh": ms_norefresh, "refresh_ms": refresh_ms, "window_ms_per_step": [m / args.steps for m in win_ms]}))
+                              "ms_per_step_no_refresh": ms_norefresh, "refresh_ms": refresh_ms, "window_ms_per_step": [m / args.steps for m in win_ms]}),
+                  file=_STDOUT, flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -541,7 +544,7 @@ def run_ours(args):
                 "frames_per_s_800x800": fps, "frames_timed": n_frames, "hash_encode_GBps": hash_gbs, "other_configs": other, "multi_gpu_check": mg,
                 "kernel_ms_per_step": {k: round(v, 5) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
                 "refresh_kernel_ms": {k: round(ms / 4, 5) for k, (c, ms) in sorted(prof_refresh.items(), key=lambda kv: -kv[1][1])}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -598,6 +601,11 @@ def main():
     ap.add_argument("--train-only", action="store_true", help="profiling runs: skip the e2e, test-frame and CPU legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries the ONE JSON line and nothing else: the package mirrors the reference's construction-time prints
+    # (networks.py:36), which go to stderr here.
+    global _STDOUT
+    _STDOUT = sys.stdout
+    sys.stdout = sys.stderr
     if args.impl == "reference":
         run_reference(args)
     else:
