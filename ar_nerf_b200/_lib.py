@@ -50,7 +50,7 @@ class TestIterCfg(C.Structure):
                 ("xyz_min_host", P), ("xyz_max_host", P), ("levels", Levels), ("params_xyz_f16", P), ("params_rgb_f16", P), ("rgb_act", I),
                 ("capacity", L), ("deltas", P), ("ts", P), ("n_eff", P), ("rays_a", P), ("counts", P), ("counts_alive", P),
                 ("xyzs", P), ("dirs", P), ("sigmas", P), ("rgbs", P), ("ws", FieldWs),
-                ("opacity", P), ("depth", P), ("rgb", P), ("alive_out", P), ("total_samples", P)]
+                ("opacity", P), ("depth", P), ("rgb", P), ("alive_out", P), ("total_samples", P), ("schedule_rays", L)]
 
 
 class SgTables(C.Structure):

@@ -2018,17 +2018,22 @@ extern "C" ARN_API int arn_march_test_far_clamp(const float* rays_o, const float
     return check_launch("march_test_far_clamp");
 }
 
+// Numerator of the device-driven loop's schedule: the frame's ray count (the reference's N_rays // N_alive) unless the caller
+// asks for more samples per iteration (cfg->schedule_rays > N_rays; pixels do not depend on the slicing).
+static inline int64_t schedule_rays(const arn_test_iter_t* c) { return c->schedule_rays > c->n_alive ? c->schedule_rays : c->n_alive; }
+
 // The iteration above with the loop control on the device (kernels: "test loop, device-driven").  c->n_alive = N_rays of the
 // frame (the numerator of the schedule), c->n_samples is ignored; n_upper bounds the device-side n_alive (grid sizing only).
 extern "C" ARN_API int arn_render_test_step(const arn_test_iter_t* c, const int32_t* state_in, int32_t* state_out, int32_t* partial,
                                             int min_samples, int budget_samples, int64_t n_upper, arn_stream_t stream) {
     ARN_REQUIRE(c && state_in && state_out && partial, "null pointer");
     ARN_REQUIRE(c->n_alive > 0 && min_samples >= 1 && n_upper >= 0 && n_upper <= c->n_alive, "bad sizes");
-    ARN_REQUIRE(c->capacity >= c->n_alive * (int64_t)min_samples, "capacity must hold N_rays * min_samples samples");
+    ARN_REQUIRE(c->capacity >= c->n_alive * (int64_t)min_samples && c->capacity >= schedule_rays(c), "capacity must hold max(N_rays * min_samples, schedule_rays) samples");
     if (int e = check_march_cfg(c->cascades, c->grid_size, c->max_samples)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nu = n_upper > 0 ? n_upper : 1;
-    const int64_t samples_upper = nu * min_samples > c->n_alive ? nu * min_samples : c->n_alive;  // n * S <= max(N_rays, n * min_samples)
+    const int64_t sched = schedule_rays(c);
+    const int64_t samples_upper = nu * min_samples > sched ? nu * min_samples : sched;  // n * S <= max(schedule_rays, n * min_samples)
     const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
     const int g128 = (int)min((int64_t)148 * 16, (nu + 127) / 128), g1024 = (int)min((int64_t)148 * 4, (nu + 1023) / 1024);  // grid-stride: full residency is enough
     // few rays, many samples each (N_samples >= 9 once n_alive <= N_rays / 9): one warp per ray
@@ -2061,7 +2066,7 @@ extern "C" ARN_API int arn_render_test_step(const arn_test_iter_t* c, const int3
                                                                                             (unsigned long long*)c->total_samples, nullptr);
     if (int e = check_launch("composite_test_dyn")) return e;
     ARN_LAUNCH_PDL("alive_compact_dyn_kernel", st, (alive_compact_dyn_kernel), g1024, 1024, 0, c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
-                                                                                           c->counts_alive, state_out, c->n_alive, min_samples, budget_samples);
+                                                                                           c->counts_alive, state_out, sched, min_samples, budget_samples);
     return check_launch("alive_compact_dyn");
 }
 
@@ -2089,11 +2094,12 @@ extern "C" ARN_API int arn_render_test_step_pre(const arn_test_iter_t* c, const 
                                                 int budget_samples, int64_t n_upper, arn_stream_t stream) {
     ARN_REQUIRE(c && state_in && state_out && partial && ts_all && totals && cursor, "null pointer");
     ARN_REQUIRE(c->n_alive > 0 && min_samples >= 1 && n_upper >= 0 && n_upper <= c->n_alive, "bad sizes");
-    ARN_REQUIRE(c->capacity >= c->n_alive * (int64_t)min_samples, "capacity must hold N_rays * min_samples samples");
+    ARN_REQUIRE(c->capacity >= c->n_alive * (int64_t)min_samples && c->capacity >= schedule_rays(c), "capacity must hold max(N_rays * min_samples, schedule_rays) samples");
     if (int e = check_march_cfg(c->cascades, c->grid_size, c->max_samples)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nu = n_upper > 0 ? n_upper : 1;
-    const int64_t samples_upper = nu * min_samples > c->n_alive ? nu * min_samples : c->n_alive;
+    const int64_t sched = schedule_rays(c);
+    const int64_t samples_upper = nu * min_samples > sched ? nu * min_samples : sched;  // n * S <= max(schedule_rays, n * min_samples)
     const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
     const int g128 = (int)min((int64_t)148 * 16, (nu + 127) / 128), g1024 = (int)min((int64_t)148 * 4, (nu + 1023) / 1024);  // grid-stride: full residency is enough
     ARN_LAUNCH_PDL("neff_test_pre_kernel", st, (neff_test_pre_kernel), g128, 128, 0, c->alive, state_in, totals, cursor, c->n_eff, partial);
@@ -2111,7 +2117,7 @@ extern "C" ARN_API int arn_render_test_step_pre(const arn_test_iter_t* c, const 
                                                                                             (unsigned long long*)c->total_samples, cursor);
     if (int e = check_launch("composite_test_dyn")) return e;
     ARN_LAUNCH_PDL("alive_compact_dyn_kernel", st, (alive_compact_dyn_kernel), g1024, 1024, 0, c->alive, c->n_eff, partial, state_in, c->counts, c->alive_out,
-                                                                                           c->counts_alive, state_out, c->n_alive, min_samples, budget_samples);
+                                                                                           c->counts_alive, state_out, sched, min_samples, budget_samples);
     return check_launch("alive_compact_dyn");
 }
 
@@ -2124,11 +2130,12 @@ extern "C" ARN_API int arn_render_test_step_fused(const arn_test_iter_t* c, cons
                                                   int budget_samples, int64_t n_upper, arn_stream_t stream) {
     ARN_REQUIRE(c && state_in && state_out && sync && ts_all && totals && cursor, "null pointer");
     ARN_REQUIRE(c->n_alive > 0 && min_samples >= 1 && n_upper >= 0 && n_upper <= c->n_alive, "bad sizes");
-    ARN_REQUIRE(c->capacity >= c->n_alive * (int64_t)min_samples, "capacity must hold N_rays * min_samples samples");
+    ARN_REQUIRE(c->capacity >= c->n_alive * (int64_t)min_samples && c->capacity >= schedule_rays(c), "capacity must hold max(N_rays * min_samples, schedule_rays) samples");
     if (int e = check_march_cfg(c->cascades, c->grid_size, c->max_samples)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nu = n_upper > 0 ? n_upper : 1;
-    const int64_t samples_upper = nu * min_samples > c->n_alive ? nu * min_samples : c->n_alive;
+    const int64_t sched = schedule_rays(c);
+    const int64_t samples_upper = nu * min_samples > sched ? nu * min_samples : sched;  // n * S <= max(schedule_rays, n * min_samples)
     const ArnMarchConsts mc = arn_march_consts(c->cascades, c->grid_size, c->scale, (float)c->cascades, c->exp_step_factor, c->max_samples);
     const int g128 = (int)min((int64_t)148 * 16, (nu + 127) / 128);
     ARN_LAUNCH("test_slice_emit_kernel", st, test_slice_emit_kernel<<<g128, 128, 0, st>>>(c->rays_o, c->rays_d, c->alive, state_in, ts_all, totals, cursor, c->n_alive, mc,
@@ -2138,7 +2145,7 @@ extern "C" ARN_API int arn_render_test_step_fused(const arn_test_iter_t* c, cons
                                     c->params_rgb_f16, c->rgb_act, c->ws, c->sigmas, c->rgbs, stream)) return e;
     ARN_LAUNCH("test_composite_keep_kernel", st, test_composite_keep_kernel<<<g128, 128, 0, st>>>(c->sigmas, c->rgbs, c->deltas, c->ts, c->alive, state_in, c->T_threshold,
                                                                                                  c->rays_a, c->opacity, c->depth, c->rgb, (unsigned long long*)c->total_samples,
-                                                                                                 cursor, c->alive_out, sync, c->counts_alive, state_out, c->n_alive, min_samples,
+                                                                                                 cursor, c->alive_out, sync, c->counts_alive, state_out, sched, min_samples,
                                                                                                  budget_samples));
     return check_launch("test_composite_keep");
 }

@@ -83,6 +83,7 @@ def render(model, rays_o, rays_d, **kwargs):
 
 
 _TEST_WS = {}
+_BOOST_SAMPLES = 2_560_000  # samples per iteration the boosted schedule aims at (see _render_rays_test_fused)
 _STATE_RING = 4   # read-back slots of the device-driven test loop
 _STATE_LAG = 2    # the host looks at the control state of the iteration queued this many calls earlier
 _PREMARCH_MAX_BYTES = 12 << 30  # largest per-frame sample table (stride x N_rays floats) the fused test loop allocates
@@ -94,11 +95,11 @@ def release_test_workspace():
     _TEST_WS.clear()
 
 
-def _make_test_ws(R, min_samples, device):
+def _make_test_ws(R, min_samples, device, boost=1):
     """Buffers of one device-driven test loop over R rays: every iteration marches at most n_alive * N_samples <=
-    R * min_samples samples (N_samples = max(min(R // n_alive, 64), min_samples))."""
+    R * max(min_samples, boost) samples (N_samples = max(min(boost * R // n_alive, 64), min_samples))."""
     from .field import tile_rows, _scratch
-    cap = R * min_samples
+    cap = R * max(min_samples, boost)
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
     wimg = _scratch(device)
     return dict(cap=cap, deltas=f(cap), ts=f(cap), n_eff=torch.empty(R, dtype=torch.int32, device=device),
@@ -118,12 +119,12 @@ def _make_test_ws(R, min_samples, device):
                 sync=torch.zeros(4, dtype=torch.int32, device=device), graphs={}, replays_hint=1, n_rays=R)
 
 
-def _test_workspace(R, min_samples, device):
-    """The fused test loop's buffers, kept per (rays, min_samples, device) -- one frame size at a time."""
-    key = (R, min_samples, device.type, device.index)
+def _test_workspace(R, min_samples, device, boost=1):
+    """The fused test loop's buffers, kept per (rays, min_samples, samples_boost, device) -- one frame size at a time."""
+    key = (R, min_samples, boost, device.type, device.index)
     ws = _TEST_WS.get(key)
     if ws is None:
-        ws = _make_test_ws(R, min_samples, device)
+        ws = _make_test_ws(R, min_samples, device, boost)
         _TEST_WS.clear()
         _TEST_WS[key] = ws
     return ws
@@ -142,7 +143,7 @@ def _premarch_table(w, stride, N_rays, device):
     return pm
 
 
-def _test_cfg(model, w, rays_o, rays_d, hits_t2, opacity, depth, rgb, exp_step_factor, T_threshold):
+def _test_cfg(model, w, rays_o, rays_d, hits_t2, opacity, depth, rgb, exp_step_factor, T_threshold, schedule_rays=0):
     """arn_test_iter_t over the given frame buffers (alive lists / n_alive are filled in per call)."""
     import ctypes as C
     from ._lib import FieldWs, TestIterCfg, ptr
@@ -157,10 +158,10 @@ def _test_cfg(model, w, rays_o, rays_d, hits_t2, opacity, depth, rgb, exp_step_f
         w['cap'], ptr(w['deltas']), ptr(w['ts']), ptr(w['n_eff']), ptr(w['rays_a']), w['counts'].data_ptr(), w['counts'].data_ptr() + 8,
         ptr(w['xyzs']), ptr(w['dirs']), ptr(w['sigmas']), ptr(w['rgbs']),
         FieldWs(ptr(w['feat']), None, None, None, None, None, ptr(w['wimg'])),
-        ptr(opacity), ptr(depth), ptr(rgb), None, ptr(w['total'])), (p16x, p16c)
+        ptr(opacity), ptr(depth), ptr(rgb), None, ptr(w['total']), int(schedule_rays)), (p16x, p16c)
 
 
-def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride, launches=7):
+def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride, launches=7, boost=1):
     """The device-driven loop replayed from CUDA graphs: ONE graph launch covers the frame's prologue (march of every ray,
     state / alive-list / output initialisation) plus the first _GRAPH_ITERS iterations, every further launch _GRAPH_ITERS more
     (an iteration behind the loop's end is a handful of empty kernels).  The frame's inputs are copied to fixed addresses;
@@ -174,14 +175,15 @@ def _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_thr
     st = model.field_state
     key = (ptr(model.density_bitfield), model.cascades, model.grid_size, float(model.scale), float(exp_step_factor), float(T_threshold), int(max_samples),
            int(min_samples), int(stride), st.cache_xyz.get(model.xyz_encoder.params).data_ptr(), st.cache_rgb.get(model.rgb_net.params).data_ptr(),
-           tuple(st.mn), tuple(st.mx), id(st.geometry), st.rgb_act, launches, ts_all.data_ptr())
+           tuple(st.mn), tuple(st.mx), id(st.geometry), st.rgb_act, launches, ts_all.data_ptr(), boost)
     graphs = w['graphs'].get(key)
     w['g_rays_o'].copy_(rays_o); w['g_rays_d'].copy_(rays_d); w['g_hits'].copy_(hits_t2)
     if graphs is None:
-        cfg, keep = _test_cfg(model, w, w['g_rays_o'], w['g_rays_d'], w['g_hits'], w['g_opacity'], w['g_depth'], w['g_rgb'], exp_step_factor, T_threshold)
+        cfg, keep = _test_cfg(model, w, w['g_rays_o'], w['g_rays_d'], w['g_hits'], w['g_opacity'], w['g_depth'], w['g_rgb'], exp_step_factor, T_threshold,
+                              schedule_rays=boost * N_rays)
         cfg.n_alive = N_rays
         state_ptr = (w['state'][0].data_ptr(), w['state'][1].data_ptr())
-        S0 = max(1, min_samples)
+        S0 = max(min(boost, 64), min_samples)
         w['g_state0'].copy_(torch.tensor([N_rays, S0, S0, 1 if max_samples > 0 else 0, 0, 0, 0, 0], dtype=torch.int32))
 
         def prologue():
@@ -245,14 +247,27 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
     max_samples = kwargs.get('max_samples', MAX_SAMPLES)
     N_rays, device = len(rays_o), rays_o.device
     min_samples = 1 if exp_step_factor == 0 else 4
-    w = _test_workspace(N_rays, min_samples, device)
+    host_driven = kwargs.get('host_driven_test_loop', False)
+    # samples_boost = k: the device-driven loop takes N_samples = max(min(k * N_rays // N_alive, 64), min_samples) per iteration
+    # instead of the reference's k = 1 (whose N_rays samples per iteration bound ITS memory): fewer, larger iterations for a
+    # loop that is bound by the NUMBER of its iterations (800x800: 41 -> 13 at k = 4, 6 at k = 16).  A ray's samples do not
+    # depend on the slicing; its compositing does in the last bit (composite_test_fw restarts each iteration from
+    # T = 1 - opacity instead of the running product: measured max |d rgb| 1.2e-7), and a ray that ends inside a slice has the
+    # rest of that slice evaluated for nothing (total_samples counts them, as the reference's does).  k = 1 is the
+    # reference's slicing bit for bit.  Default: k = 1 wherever the sample budget can bind (max_samples below the march's own
+    # 1024, or exp_step_factor > 0: WHICH samples a ray gets then depends on the schedule); otherwise (the reference's
+    # bounded-scene test frame) k = what keeps an iteration's buffers inside L2, ~2.5 M samples, at most 16.
+    boost = kwargs.get('samples_boost')
+    if boost is None:
+        boost = min(16, _BOOST_SAMPLES // max(1, N_rays)) if (exp_step_factor == 0 and max_samples >= MAX_SAMPLES) else 1
+    boost = 1 if host_driven else max(1, min(64, int(boost)))
+    w = _test_workspace(N_rays, min_samples, device, boost)
     model.host_box()
     hits_t2 = hits_t[:, 0]
     if not hits_t2.is_contiguous():
         raise RuntimeError("hits_t must be contiguous")
     rays_o = rays_o.contiguous().float(); rays_d = rays_d.contiguous().float()
     s_ = stream()
-    host_driven = kwargs.get('host_driven_test_loop', False)
     # The frame's samples are marched once, in front of the loop (arn_march_test_all), when their table fits: the loop never
     # asks a ray for more than max_samples + 63 samples.  Otherwise the iterations march (far-clamped rays).
     stride = int(max(1, max_samples)) + 64
@@ -260,14 +275,14 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
                 and _premarch_table(w, stride, N_rays, device) is not None)
     if premarch and kwargs.get('graph_test_loop', True) and not torch.cuda.is_current_stream_capturing():
         return _render_test_graph(model, w, rays_o, rays_d, hits_t2, exp_step_factor, T_threshold, max_samples, min_samples, stride,
-                                  launches=4 if kwargs.get('test_loop_launches', 7) == 4 else 7)
+                                  launches=4 if kwargs.get('test_loop_launches', 7) == 4 else 7, boost=boost)
     opacity = torch.zeros(N_rays, device=device)
     depth = torch.zeros(N_rays, device=device)
     rgb = torch.zeros(N_rays, 3, device=device)
     cur = 0
     torch.arange(N_rays, out=w['alive'][0])
     w['total'].zero_()
-    cfg, _keep = _test_cfg(model, w, rays_o, rays_d, hits_t2, opacity, depth, rgb, exp_step_factor, T_threshold)
+    cfg, _keep = _test_cfg(model, w, rays_o, rays_d, hits_t2, opacity, depth, rgb, exp_step_factor, T_threshold, schedule_rays=boost * N_rays)
     if not host_driven:
         # Loop control on the device: iterations are queued without waiting for their counts; the control state comes back
         # through pinned memory and is looked at _STATE_LAG iterations late (an iteration queued after the loop has ended
@@ -279,7 +294,7 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
         elif kwargs.get('far_clamp', True):
             call("arn_march_test_far_clamp", ptr(rays_o), ptr(rays_d), ptr(hits_t2), N_rays, ptr(model.density_bitfield), model.cascades,
                  model.grid_size, float(model.scale), float(exp_step_factor), MAX_SAMPLES, s_)
-        S0 = max(1, min_samples)
+        S0 = max(min(boost, 64), min_samples)
         w['state_init'][:5] = torch.tensor([N_rays, S0, S0, 1 if max_samples > 0 else 0, 0], dtype=torch.int32)
         w['state'][0].copy_(w['state_init'], non_blocking=True)
         cfg.n_alive = N_rays

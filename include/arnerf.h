@@ -414,6 +414,11 @@ typedef struct {
     float* xyzs; float* dirs; float* sigmas; float* rgbs; arn_field_ws_t ws;
     /* in/out */
     float* opacity; float* depth; float* rgb; int64_t* alive_out; int64_t* total_samples;
+    /* device-driven loop only: numerator of the schedule N_samples = max(min(schedule_rays // N_alive, 64), min_samples).
+     * 0 (or anything <= N_rays) = N_rays, the reference's schedule; k * N_rays asks for k times the samples per iteration --
+     * fewer, larger iterations, the same per-ray results (a ray's samples and their compositing order do not depend on the
+     * slicing), more samples evaluated behind the point where a ray terminates.  capacity >= schedule_rays. */
+    int64_t schedule_rays;
 } arn_test_iter_t;
 int arn_render_test_iter(const arn_test_iter_t* cfg_host, arn_stream_t stream);
 /* Far clamp of a frame's rays, once, in front of the test loop: every ray is marched to its end with the test march's

@@ -885,12 +885,15 @@ def test_nerf_loss_kernel_vs_autograd():
         assert_rel(N(outs[3]), N(d_.grad), rtol=1e-4, what="dL_ddepth")
 
 
-@pytest.mark.parametrize("impl", ["_simt", ""])
-def test_render_test_end_to_end(impl, w1):
+@pytest.mark.parametrize("impl,max_samples", [("_simt", 100), ("", 100), ("", 1024)])
+def test_render_test_end_to_end(impl, max_samples, w1):
     """rendering.render(test_time=True) against the same loop driven by the oracle: the CUDA-core field through the eager
     loop (bit-comparable field, 1e-4), and the PRODUCTION path -- tensor-core field, fused device-driven loop replayed from
     CUDA graphs -- whose field carries the tie-rounding spread of test_field_forward: a ray may then cross the termination
-    threshold one sample earlier or later than in the oracle, which moves its pixel by at most T_threshold."""
+    threshold one sample earlier or later than in the oracle, which moves its pixel by at most T_threshold.  With the march's
+    own budget (max_samples = 1024, the reference's default) the production path also takes its larger slices per iteration
+    (samples_boost, rendering.py) while the oracle loop below keeps the reference's schedule: same pixels, and samples that the
+    reference would not have evaluated behind a ray's termination are the only difference in total_samples."""
     from ar_nerf_b200.rendering import render
     w = w1
     model, geo, _, _, _, pxyz, prgb = _field_setup(w.scale, 8, 22, table_amp=4.0)
@@ -898,14 +901,14 @@ def test_render_test_end_to_end(impl, w1):
     w.install(model)
     ro, rd = w.test_frame(100, 100)
     thr = 1e-2
-    res = render(model, T(ro), T(rd), test_time=True, T_threshold=thr, max_samples=100, val_batch_size=2 ** 20)  # show_gui.py:89's kwargs
+    res = render(model, T(ro), T(rd), test_time=True, T_threshold=thr, max_samples=max_samples, val_batch_size=2 ** 20)  # show_gui.py:89's kwargs
     ro_n, rd_n = ro.numpy(), rd.numpy()
     hits = scene_hits(w, ro_n, rd_n)
     R = len(ro_n)
     opacity, depth, rgb = np.zeros(R, np.float32), np.zeros(R, np.float32), np.zeros((R, 3), np.float32)
     alive = np.arange(R, dtype=np.int64); samples = 0; total = 0
     mn, mx = np.full(3, -w.scale, np.float32), np.full(3, w.scale, np.float32)
-    while samples < 100 and len(alive):
+    while samples < max_samples and len(alive):
         S = max(min(R // len(alive), 64), 1); samples += S
         x, d, dl, t, neff = oracle.raymarching_test(ro_n, rd_n, hits, alive, w.bitfield.numpy(), 1, 0.5, 0.0, 128, 1024, S)
         total += int(neff.sum())
@@ -932,7 +935,10 @@ def test_render_test_end_to_end(impl, w1):
             f"max |d opacity| {d_op[~flipped].max():.2e}, max |d rgb| {d_rgb[~flipped].max():.2e} on the others", float(flipped.mean()) / 2e-3)
     assert flipped.mean() <= 2e-3
     assert d_op[flipped].max(initial=0.0) <= 2 * thr and d_rgb[flipped].max(initial=0.0) <= 2 * thr
-    assert abs(int(res["total_samples"]) - total) <= 64 * max(1, int(flipped.sum())) + 2e-3 * total
+    if max_samples < 1024:
+        assert abs(int(res["total_samples"]) - total) <= 64 * max(1, int(flipped.sum())) + 2e-3 * total
+    else:  # boosted slices: a terminated ray's slice is evaluated to its end, up to 63 samples more than the reference's schedule
+        assert total * (1 - 2e-3) - 64 * int(flipped.sum()) <= int(res["total_samples"]) <= total + 64 * R
     far = float(np.abs(depth).max())
     assert_rel(N(res["depth"])[~flipped], depth[~flipped], rtol=2e-3, what="depth", atol=2e-3 * far)
 
@@ -946,7 +952,7 @@ def test_fused_test_loop_equals_eager_loop(kind, thr, max_samples, w1, w3):
     model, *_ = _field_setup(w.scale, 8, 23, table_amp=4.0)
     w.install(model)
     ro, rd = w.test_frame(160, 120)
-    kw = dict(test_time=True, T_threshold=thr, max_samples=max_samples, exp_step_factor=w.exp_step_factor)
+    kw = dict(test_time=True, T_threshold=thr, max_samples=max_samples, exp_step_factor=w.exp_step_factor, samples_boost=1)  # the reference's slicing
     a = render(model, T(ro), T(rd), **kw)                              # frame marched once + arn_render_test_step_pre, replayed from CUDA graphs
     a2 = render(model, T(ro), T(rd), **kw)                             # second frame: pure replay, the replay count taken from the first
     g4 = render(model, T(ro), T(rd), test_loop_launches=4, **kw)       # graphs over the four-launch iteration (arn_render_test_step_fused: lists in arrival order)
@@ -965,6 +971,18 @@ def test_fused_test_loop_equals_eager_loop(kind, thr, max_samples, w1, w3):
     assert int(a["total_samples"]) == int(h["total_samples"]) == int(b["total_samples"]) > 0
     for k in ("opacity", "depth", "rgb"):
         assert torch.equal(a[k], b[k]) and torch.equal(h[k], b[k]), k
+    # larger slices per iteration (samples_boost; the default where no sample budget can bind): the same samples per ray,
+    # compositing restarted at other sample indices -- pixels equal to the last bits, never fewer samples evaluated
+    kwd = {k: v for k, v in kw.items() if k != 'samples_boost'}
+    dflt = render(model, T(ro), T(rd), **kwd)
+    auto = 16 if (w.exp_step_factor == 0 and max_samples >= 1024) else 1
+    for k_, r_ in [(auto, dflt)] + [(k_, render(model, T(ro), T(rd), **dict(kw, samples_boost=k_))) for k_ in (4, 16, 64)]:
+        if k_ == auto:
+            assert all(torch.equal(r_[k], dflt[k]) for k in ("opacity", "depth", "rgb")) and int(r_["total_samples"]) == int(dflt["total_samples"])
+        if w.exp_step_factor == 0 and max_samples >= 1024:
+            assert int(r_["total_samples"]) >= int(a["total_samples"])
+            for k in ("opacity", "depth", "rgb"):
+                assert float((r_[k] - a[k]).abs().max()) <= 2e-6 * max(1.0, float(a[k].abs().max())), (k_, k)
     # a frame whose rays all miss, a one-ray frame and an exhausted sample budget end the device-driven loop as well
     far = T(ro) + 100.0
     z = render(model, far, T(rd), **kw)
