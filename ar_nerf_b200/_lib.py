@@ -84,6 +84,8 @@ SIGNATURES = {
     "arn_gather_batch": [P, P, I, P, P, L, P, L, P, L, I, P, P, P, P],
     "arn_grid_cell_positions": [P, P, L, I, F, P, P],
     "arn_grid_sample_cells": [P, F, I, F, P, P, L, P, P, P, P, P],
+    "arn_grid_sample_cells_sorted": [P, F, I, F, P, P, L, P, P, P, P, P],
+    "arn_grid_scatter": [P, L, P, P, L, P],
     "arn_density_grid_update": [P, P, P, F, F, L, P, P, P],
     "arn_mark_invisible_cells": [P, P, L, I, F, P, I, P, F, F, F, P, P, P],
     "arn_profile_enable": [I],

@@ -63,19 +63,24 @@ inline int pipeline_parts(int64_t n) {
 
 constexpr int kFwSmemTile32 = 128 * 64;    // 128 rows x 32 halves
 constexpr int kFwSmemTile64 = 128 * 128;   // 128 rows x 64 halves
-// Shared-memory map of the forward (offsets from the 1024-aligned base): weight image | F0 F1 (feature tiles, double
-// buffered) | A B (two 16 KB activation buffers used in turn: hid -> A, in32 -> B, hid1 -> A, hid2 -> B).  The h staging
-// tile (128 x 16 f32) reuses the current feature buffer, free once the first MMA has read it.  68 KB + slack: THREE CTAs
-// per SM (the kernel is a chain of short latencies per tile -- MMA completion, TMEM load, shared-memory fence -- and the
-// tensor pipe idles ~90 % of the time with two tiles in flight per SM).  A buffer is overwritten two layers after it was
-// written; its bulk store (issued one layer after the write) has then had a whole layer to read it, and the thread that
-// issues the MMAs waits for that read before it issues the layer whose epilogue overwrites the buffer.
-// W warpgroups per CTA share ONE weight image; every warpgroup owns the four tile buffers below and walks its own tiles:
-// W = 4 (512 threads, one CTA per SM: 20 + 4 x 48 KB, all 512 TMEM columns) keeps four tiles in flight on an SM instead of
-// the three that three 68 KB CTAs give; W = 1 for launches too small to fill 4 x n_sm tiles.
-constexpr int kFwF0 = 0, kFwF1 = kFwF0 + kFwSmemTile32, kFwA = kFwF1 + kFwSmemTile32, kFwB = kFwA + kFwSmemTile64;  // offsets inside a warpgroup's block
+// Shared-memory map of the forward (offsets from the 1024-aligned base): weight image | per warpgroup: F (the tile's
+// features) | A B (two 16 KB activation buffers used in turn: hid -> A, in32 -> B, hid1 -> A, hid2 -> B).  The h staging
+// tile (128 x 16 f32, 8 KB) sits in the upper half of B beside in32 (8 KB): both are gone when hid2 arrives.  F is free as
+// soon as the first MMA of a tile has read it: the NEXT tile's features are requested then and have four layers to arrive.
+// A buffer is overwritten two layers after it was written; its bulk store (issued one layer after the write) has then had
+// a whole layer to read it, and the thread that issues the MMAs waits for that read before it issues the layer whose
+// epilogue overwrites the buffer.
+// The kernel is a chain of short latencies per tile (MMA completion, TMEM load, shared-memory fence: issue slots 30 % busy,
+// tensor pipe 10 %), so what counts is the number of tiles in flight on an SM and the number of ROUNDS a launch takes:
+// W warpgroups per CTA share ONE weight image, every warpgroup owns the three tile buffers above (40 KB) and 64 TMEM
+// columns (a layer's accumulator has been pulled before the next layer is issued) and walks its own tiles.
+// W = 5 (640 threads, one CTA per SM: 20 + 5 x 40 KB): a training step's 1920 tiles take 3 rounds over 740 warpgroups where
+// four warpgroups of 48 KB took 4 over 592; W = 1 (three CTAs per SM) for launches too small to fill 5 x n_sm tiles.
+constexpr int kFwF = 0, kFwA = kFwF + kFwSmemTile32, kFwB = kFwA + kFwSmemTile64;  // offsets inside a warpgroup's block
 constexpr int kFwWgBytes = kFwB + kFwSmemTile64;
+constexpr int kFwWide = 5;
 template <int W> constexpr int fw_smem_bytes() { return kWimgBytes + W * kFwWgBytes + 1024; }  // + alignment slack
+template <int W> constexpr int fw_tmem_cols() { return W == 1 ? 64 : 512; }                     // 64 per warpgroup, a power of two
 constexpr int kFwCtasPerSm = 3;  // W = 1
 
 template <int W>
@@ -86,23 +91,23 @@ __global__ void __launch_bounds__(128 * W, 1) field_mlp_fw_tc_kernel(const __hal
                                                               float* __restrict__ rgbs, int part, int parts) {
     pdl_enter();
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[1 + 3 * W];  // weights | per warpgroup: mma, f0, f1
+    __shared__ __align__(8) uint64_t bars[1 + 2 * W];  // weights | per warpgroup: mma, features
     __shared__ uint32_t tmem_slot;
     if (n_dev) n = min(n, (int64_t)*n_dev);  // fused step: the sample count lives on the device
     const uint32_t base0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzled tiles need 1024-byte alignment
     const int wg = threadIdx.x >> 7, tid = threadIdx.x & 127, warp = tid >> 5;
     const uint32_t sW = base0;
-    const uint32_t base = base0 + kWimgBytes + wg * kFwWgBytes;  // this warpgroup's F0 F1 A B
+    const uint32_t base = base0 + kWimgBytes + wg * kFwWgBytes;  // this warpgroup's F A B
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1 + 3 * wg]), bar_f0 = smem_u32(&bars[2 + 3 * wg]), bar_f1 = smem_u32(&bars[3 + 3 * wg]);
+    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1 + 2 * wg]), bar_f = smem_u32(&bars[2 + 2 * wg]);
 
     if (threadIdx.x == 0) {
-        for (int k = 0; k < 1 + 3 * W; k++) mbar_init(smem_u32(&bars[k]), 1);
+        for (int k = 0; k < 1 + 2 * W; k++) mbar_init(smem_u32(&bars[k]), 1);
         mbar_fence_init();
     }
-    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 128 * W);
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, fw_tmem_cols<W>());
     fence_before_sync(); __syncthreads(); fence_after_sync();
-    const uint32_t tmem = tmem_slot + 128 * wg;  // this warpgroup's 128 columns
+    const uint32_t tmem = tmem_slot + 64 * wg;  // this warpgroup's 64 columns
     const uint32_t wbytes = with_rgb ? kWimgBytes : kWimgC1;
     // this launch owns the tiles [t_begin, n_tiles) of the sample list (one of `parts` consecutive ranges: the host pipelines
     // the hash-grid forward of range p+1 on a second stream under the MLP of range p)
@@ -110,29 +115,31 @@ __global__ void __launch_bounds__(128 * W, 1) field_mlp_fw_tc_kernel(const __hal
     const int64_t t_begin = n_tiles_all * part / parts, n_tiles = n_tiles_all * (part + 1) / parts;
     const int64_t tile0 = t_begin + (int64_t)blockIdx.x * W + wg, tile_stride = (int64_t)gridDim.x * W;
     if (threadIdx.x == 0) { mbar_expect_tx(bar_w, wbytes); bulk_g2s(sW, wimg, wbytes, bar_w); }
-    if (tid == 0 && tile0 < n_tiles) { mbar_expect_tx(bar_f0, kFwSmemTile32); bulk_g2s(base + kFwF0, feat + tile0 * 128 * 32, kFwSmemTile32, bar_f0); }
+    if (tid == 0 && tile0 < n_tiles) { mbar_expect_tx(bar_f, kFwSmemTile32); bulk_g2s(base + kFwF, feat + tile0 * 128 * 32, kFwSmemTile32, bar_f); }
     mbar_wait(bar_w, 0);
 
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes; lane == sample row
-    const uint64_t aF0 = smem_desc<64>(base + kFwF0), aF1 = smem_desc<64>(base + kFwF1);
+    const uint64_t aF = smem_desc<64>(base + kFwF);
     const uint64_t aI = smem_desc<64>(base + kFwB);
     const uint64_t aH0 = smem_desc<128>(base + kFwA), aH1 = smem_desc<128>(base + kFwA), aH2 = smem_desc<128>(base + kFwB);
     constexpr int kFwH0 = kFwA, kFwI = kFwB, kFwH1 = kFwA, kFwH2 = kFwB;
+    constexpr int kFwHS = kFwB + kFwSmemTile32;  // h staging: upper half of B, beside in32
     const uint64_t bD1 = smem_desc<64>(sW + kWimgD1), bD2 = smem_desc<128>(sW + kWimgD2);
     const uint64_t bC1 = smem_desc<64>(sW + kWimgC1), bC2 = smem_desc<128>(sW + kWimgC2), bC3 = smem_desc<128>(sW + kWimgC3);
     constexpr uint32_t kI64 = instr_desc(128, 64, 0, 0), kI16 = instr_desc(128, 16, 0, 0);
     uint32_t phase = 0;
 
     // issue one layer: D[tmem cols] = A (128 x K) * W^T, K = 16 * ksteps; then commit.  The barrier in front publishes the
-    // A tile the threads have just written (generic proxy -> async proxy) to the tensor core AND to the TMA engine.
+    // A tile the threads have just written (generic proxy -> async proxy) to the tensor core AND to the TMA engine, and
+    // orders the threads' tcgen05.ld of the previous accumulator before the MMAs that overwrite it.
     // free_buf: the epilogue of this layer overwrites a buffer that an earlier bulk store may still be reading; the issuing
     // thread waits for those reads BEFORE it issues the MMAs, and the other threads cannot write before the MMAs commit.
-    auto issue_only = [&](uint32_t dcol, uint64_t a, uint64_t b, uint32_t idesc, int ksteps, bool free_buf) {
+    auto issue_only = [&](uint64_t a, uint64_t b, uint32_t idesc, int ksteps, bool free_buf) {
         fence_before_sync(); fence_async_smem(); wg_sync(1 + wg);
         if (tid == 0) {
             fence_after_sync();
             if (free_buf) bulk_wait_read<0>();
-            for (int k = 0; k < ksteps; k++) mma_f16(tmem + dcol, desc_advance(a, 32 * k), desc_advance(b, 32 * k), idesc, k > 0);
+            for (int k = 0; k < ksteps; k++) mma_f16(tmem, desc_advance(a, 32 * k), desc_advance(b, 32 * k), idesc, k > 0);
             mma_commit(bar_mma);
         }
     };
@@ -140,12 +147,20 @@ __global__ void __launch_bounds__(128 * W, 1) field_mlp_fw_tc_kernel(const __hal
         mbar_wait(bar_mma, phase); phase ^= 1;
         fence_after_sync();
     };
-    // epilogue of a 64-wide hidden layer: ReLU, fp16, this thread's row of the next A tile
-    auto hidden_row = [&](uint32_t taddr, uint8_t* tile) {
-        uint32_t o[32];
-        epilogue_row_f16<4, true>(taddr, o);
+    // epilogue of a 64-wide hidden layer: ReLU, fp16, this thread's row of the next A tile (two halves of 32 columns: the
+    // first half's conversions and stores run under the second half's TMEM load)
+    auto hidden_row = [&](uint8_t* tile) {
+        float v[64];
 #pragma unroll
-        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(tile + swz<128>(tid, c)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        for (int q = 0; q < 4; q++) tmem_ld16(trow + 16 * q, v + 16 * q);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = pack2(fmaxf(v[8 * c + 2 * j], 0.0f), fmaxf(v[8 * c + 2 * j + 1], 0.0f));
+            *reinterpret_cast<uint4*>(tile + swz<128>(tid, c)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     };
 
     // ray direction of this thread's sample, requested one tile ahead (between an MMA issue and its completion)
@@ -160,36 +175,28 @@ __global__ void __launch_bounds__(128 * W, 1) field_mlp_fw_tc_kernel(const __hal
     for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, it++) {
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
-        const int buf = it & 1;
-        const int kFwHS = buf ? kFwF1 : kFwF0;  // h staging: the feature buffer of this tile, once the first MMA has read it
-        uint8_t* pF = sm + (buf ? kFwF1 : kFwF0);
-        if (tid == 0) {
-            // F[buf^1] held the previous tile's features and then its h staging tile, whose bulk store must have read it
-            bulk_wait_read<0>();
-            const int64_t next = tile + tile_stride;
-            if (next < n_tiles) {
-                const uint32_t bf = buf ? bar_f0 : bar_f1;
-                mbar_expect_tx(bf, kFwSmemTile32);
-                bulk_g2s(base + (buf ? kFwF0 : kFwF1), feat + next * 128 * 32, kFwSmemTile32, bf);
-            }
-        }
-        mbar_wait(buf ? bar_f1 : bar_f0, (uint32_t)(it >> 1) & 1u);
+        uint8_t* pF = sm + kFwF;
+        mbar_wait(bar_f, (uint32_t)it & 1u);
         if (!valid) {  // rows past the sample count: zero features keep every saved activation of the pad rows finite
 #pragma unroll
             for (int c = 0; c < 4; c++) *reinterpret_cast<uint4*>(pF + swz<64>(tid, c)) = make_uint4(0, 0, 0, 0);
         }
         const float dcur[3] = {dr[0], dr[1], dr[2]};
         // ---- density layer 1: A = feature tile
-        issue_only(0, buf ? aF1 : aF0, bD1, kI64, 2, true);    // epilogue -> A (previous tile's hid1)
+        issue_only(aF, bD1, kI64, 2, true);                      // epilogue -> A (previous tile's hid1)
         wait_mma();
-        hidden_row(trow + 0, sm + kFwH0);
+        if (tid == 0) {  // F has been read: the next tile's features may land in it
+            const int64_t next = tile + tile_stride;
+            if (next < n_tiles) { mbar_expect_tx(bar_f, kFwSmemTile32); bulk_g2s(base + kFwF, feat + next * 128 * 32, kFwSmemTile32, bar_f); }
+        }
+        hidden_row(sm + kFwH0);
         // ---- density layer 2 -> h (16, fp32), sigma
-        issue_only(64, aH0, bD2, kI16, 4, true);                 // epilogue -> B (previous tile's hid2), h staging
+        issue_only(aH0, bD2, kI16, 4, true);                     // epilogue -> B (previous tile's hid2): in32 and the h staging tile
         if (tid == 0 && hid) { bulk_s2g(hid + tile * 128 * 64, base + kFwH0, kFwSmemTile64); bulk_commit(); }
         wait_mma();
         {
             float hv[16];
-            tmem_ld16(trow + 64, hv); tmem_ld_wait();
+            tmem_ld16(trow, hv); tmem_ld_wait();
             if (valid) sigmas[i] = expf(hv[0]);
             // h tile staging: plain row-major 128 x 16 f32, the public layout of h
             if (h) {
@@ -209,33 +216,33 @@ __global__ void __launch_bounds__(128 * W, 1) field_mlp_fw_tc_kernel(const __hal
         }
         if (!with_rgb) {
             if (h) {
-                fence_async_smem(); wg_sync(1 + wg);
+                fence_before_sync(); fence_async_smem(); wg_sync(1 + wg);
                 if (tid == 0) { bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64); bulk_commit(); }
             }
             continue;
         }
         // ---- colour layer 1
-        issue_only(0, aI, bC1, kI64, 2, true);                   // epilogue -> A (hid)
+        issue_only(aI, bC1, kI64, 2, true);                      // epilogue -> A (hid)
         if (tid == 0) {
             if (hid) bulk_s2g(in32 + tile * 128 * 32, base + kFwI, kFwSmemTile32);
             if (h) bulk_s2g(h + tile * 128 * 16, base + kFwHS, 128 * 64);
             bulk_commit();
         }
         wait_mma();
-        hidden_row(trow + 0, sm + kFwH1);
+        hidden_row(sm + kFwH1);
         // ---- colour layer 2
-        issue_only(64, aH1, bC2, kI64, 4, true);                 // epilogue -> B (in32)
+        issue_only(aH1, bC2, kI64, 4, true);                     // epilogue -> B (in32, h staging)
         if (tid == 0 && hid) { bulk_s2g(hid1 + tile * 128 * 64, base + kFwH1, kFwSmemTile64); bulk_commit(); }
         wait_mma();
-        hidden_row(trow + 64, sm + kFwH2);
+        hidden_row(sm + kFwH2);
         // ---- colour layer 3 -> rgb
-        issue_only(0, aH2, bC3, kI16, 4, false);
+        issue_only(aH2, bC3, kI16, 4, false);
         if (tid == 0 && hid) { bulk_s2g(hid2 + tile * 128 * 64, base + kFwH2, kFwSmemTile64); bulk_commit(); }
         fetch_dir(tile + tile_stride);
         wait_mma();
         {
             float ov[16];
-            tmem_ld16(trow + 0, ov); tmem_ld_wait();
+            tmem_ld16(trow, ov); tmem_ld_wait();
             if (valid) {
 #pragma unroll
                 for (int j = 0; j < 3; j++) rgbs[3 * i + j] = rgb_act ? 1.0f / (1.0f + expf(-ov[j])) : ov[j];
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(128 * W, 1) field_mlp_fw_tc_kernel(const __hal
     }
     if (tid == 0) bulk_wait_read<0>();
     fence_before_sync(); __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem_slot, 128 * W);
+    if (threadIdx.x < 32) tmem_dealloc(tmem_slot, fw_tmem_cols<W>());
 }
 
 // One-time, per device: dynamic shared memory limits of every instance of the two kernels.  Returns the SM count.
@@ -285,9 +292,9 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
     // a second stream under the MLP (tensor core + HBM stores) of range p -- the two kernels stress different units.
     const int64_t n_tiles = (n + 127) / 128;
     const int parts = pipeline_parts(n);
-    // four warpgroups per CTA, one CTA per SM, when the launch has the tiles to fill that; else one warpgroup per CTA
-    const bool wide = (n_tiles + parts - 1) / parts >= (int64_t)n_sm * 4 && (tunable(kTunMlpWide) & 1) != 0;
-    const int wgs = wide ? 4 : 1;
+    // kFwWide warpgroups per CTA, one CTA per SM, when the launch has the tiles to fill that; else one warpgroup per CTA
+    const bool wide = (n_tiles + parts - 1) / parts >= (int64_t)n_sm * kFwWide && (tunable(kTunMlpWide) & 1) != 0;
+    const int wgs = wide ? kFwWide : 1;
     const int grid = (int)max((int64_t)1, min((int64_t)n_sm * (wide ? 1 : kFwCtasPerSm), ((n_tiles + parts - 1) / parts + wgs - 1) / wgs));
     PipeStreams* ps = nullptr;
     if (parts > 1) {
@@ -307,7 +314,7 @@ extern "C" ARN_API int arn_field_fw_tc_dyn(const float* xyzs, const float* dirs,
         if (parts > 1) ARN_CUDA(cudaStreamWaitEvent(st, ps->ev[p], 0));
 #define ARN_FW_ARGS (const __half*)ws.feat, dirs, n, n_dev, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, (__half*)ws.hid, ws.h, sigmas, \
             (__half*)ws.in32, (__half*)ws.hid1, (__half*)ws.hid2, rgbs, p, parts
-        if (wide) ARN_LAUNCH_PDL("field_mlp_fw_tc_kernel", st, (field_mlp_fw_tc_kernel<4>), grid, 512, fw_smem_bytes<4>(), ARN_FW_ARGS);
+        if (wide) ARN_LAUNCH_PDL("field_mlp_fw_tc_kernel", st, (field_mlp_fw_tc_kernel<kFwWide>), grid, 128 * kFwWide, fw_smem_bytes<kFwWide>(), ARN_FW_ARGS);
         else ARN_LAUNCH_PDL("field_mlp_fw_tc_kernel", st, (field_mlp_fw_tc_kernel<1>), grid, 128, fw_smem_bytes<1>(), ARN_FW_ARGS);
 #undef ARN_FW_ARGS
         if (int e = check_launch("field_mlp_fw_tc")) return e;
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(128 * W, 1) __maxnreg__(W == 3 ? 128 : 192) fi
                                                               const __half* __restrict__ in32, const __half* __restrict__ hid1,
                                                               const __half* __restrict__ hid2, const uint8_t* __restrict__ wimg, int rgb_act,
                                                               int with_rgb, float loss_scale, float exp_hi, float* __restrict__ dfeat, float* __restrict__ wpart,
-                                                              int part, int parts, int slab0) {
+                                                              int part, int parts, int slab0, int reverse) {
     pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[1 + 4 * W];  // weights | per warpgroup: mma, x0, x1, x2
@@ -405,12 +412,16 @@ __global__ void __launch_bounds__(128 * W, 1) __maxnreg__(W == 3 ? 128 : 192) fi
     const int64_t n_tiles_all = (n + 127) / 128;
     const int64_t t_begin = n_tiles_all * part / parts, n_tiles = n_tiles_all * (part + 1) / parts;
     const int64_t tile0 = t_begin + (int64_t)blockIdx.x * W + wg, tile_stride = (int64_t)gridDim.x * W;
+    // reverse: position t of the walk is the tile n_tiles - 1 - (t - t_begin) -- the forward's LAST tiles first, whose saved
+    // activations are the ones still in L2 (the forward wrote 110 MB through a 126 MB cache in tile order)
+    auto phys = [&](int64_t t) { return reverse ? n_tiles - 1 - (t - t_begin) : t; };
 
     // ---- activation-tile stream: load j of this warpgroup = tile (j / L) of its tile sequence, kind (j % L); slot j % 3
     const int L = with_rgb ? 5 : 2;
     auto issue_load = [&](int64_t j) {  // the warpgroup's thread 0 only
-        const int64_t t = tile0 + (j / L) * tile_stride;
+        int64_t t = tile0 + (j / L) * tile_stride;
         if (t >= n_tiles) return;
+        t = phys(t);
         const int kind = with_rgb ? (int)(j % 5) : 3 + (int)(j % 2);
         const __half* src; uint32_t bytes;
         switch (kind) {
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(128 * W, 1) __maxnreg__(W == 3 ? 128 : 192) fi
     // of a basic block but not across the bar.sync; a use placed after younger loads would wait for those as well)
     float pre_y[3] = {0.f, 0.f, 0.f}, pre_g[3] = {0.f, 0.f, 0.f}, pre_ds = 0.f, pre_sig = 1.f;
     auto fetch_scalars = [&](int64_t t) {
-        const int64_t i = t * 128 + tid;
+        const int64_t i = phys(t) * 128 + tid;
         const bool ok = t < n_tiles && i < n;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -491,7 +502,8 @@ __global__ void __launch_bounds__(128 * W, 1) __maxnreg__(W == 3 ? 128 : 192) fi
     };
     fetch_scalars(tile0);
 
-    for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+    for (int64_t pos = tile0; pos < n_tiles; pos += tile_stride) {
+        const int64_t tile = phys(pos);
         const int64_t i = tile * 128 + tid;
         const bool valid = i < n;
         float tcol[16];  // scaled dL/dh from the colour branch
@@ -544,7 +556,7 @@ __global__ void __launch_bounds__(128 * W, 1) __maxnreg__(W == 3 ? 128 : 192) fi
         layer_wait();
         epilogue_mask64(tR, xh, pG, tid);                              // gd -> G
         const uint8_t* xf = layer(dG128, 128, 64, wD1, 64, 32, 64, kColD1);
-        fetch_scalars(tile + tile_stride);
+        fetch_scalars(pos + tile_stride);
         layer_wait();
         {   // dfeat tile: fp32 rows of 128 B, chunk-permuted like a RB128 image; staged in the ring slot the feature tile has
             // just left (free until the load two layers ahead, which waits for this store's read) and stored by TMA
@@ -614,7 +626,7 @@ int mlp_device_setup(int* n_sm_out) {
         ARN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
         ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw_smem_bytes<1>()));
         ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw_smem_bytes<4>()));
+        ARN_CUDA(cudaFuncSetAttribute(field_mlp_fw_tc_kernel<kFwWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, fw_smem_bytes<kFwWide>()));
         ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<1>()));
         ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bw_smem_bytes<3>()));
@@ -683,7 +695,7 @@ int arn::field_bw_tc_impl(const float* xyzs, int64_t n, const int32_t* n_dev, co
     if (parts > 1) { if (int e = pipe_streams(&ps)) return e; }
     for (int p = 0; p < parts; p++) {
 #define ARN_BW_ARGS n, n_dev, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, sigmas, (const __half*)ws.feat, (const __half*)ws.hid, (const __half*)ws.in32, \
-            (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, expf(15.0f), dfeat_scratch, wpart, p, parts, p * grid
+            (const __half*)ws.hid1, (const __half*)ws.hid2, (const uint8_t*)ws.wimg, rgb_act, with_rgb ? 1 : 0, loss_scale, expf(15.0f), dfeat_scratch, wpart, p, parts, p * grid, (tunable(kTunMlpWide) & 4) ? 1 : 0
         if (wide) ARN_LAUNCH_PDL("field_mlp_bw_tc_kernel", st, (arn::field_mlp_bw_tc_kernel<3>), grid, 384, arn::bw_smem_bytes<3>(), ARN_BW_ARGS);
         else ARN_LAUNCH_PDL("field_mlp_bw_tc_kernel", st, (arn::field_mlp_bw_tc_kernel<1>), grid, 128, arn::bw_smem_bytes<1>(), ARN_BW_ARGS);
 #undef ARN_BW_ARGS

@@ -237,9 +237,11 @@ __global__ void __launch_bounds__(256) mark_invisible_kernel(const int32_t* __re
 // occupied cell is found through occupancy bit masks (one word per 32 cells) and a prefix over 1024-cell chunks -- a binary
 // search in shared memory and one 128-byte read of the chunk's masks -- instead of cumsum + searchsorted over the whole
 // grid; the jittered position of the cell (networks.py:263-267) is written by the same thread.
-// (Measured and dropped: ordering the selected cells along the morton curve with a counting sort over the chunks.  The
-// density evaluation that follows does get cheaper -- 293 -> 200 us of hash-grid gathers for the 1 M cells -- but the
-// histogram and the scatter cost more than that.)
+// arn_grid_sample_cells_sorted returns the same cells ordered along the morton curve (a counting sort over the cells: the
+// density evaluation that follows gathers 1 M cells' hash-grid corners in 167 us instead of 295 when neighbours in the list are
+// neighbours in space).  The sort costs about what it saves, so it only pays where the selection is computed AHEAD of the
+// refresh, off the step's critical path: it depends on the previous refresh's density_grid and on random draws only
+// (NGP.update_density_grid prefetches it on a side stream).
 constexpr int kCellChunk = 1024;  // cells per chunk = 32 mask words
 constexpr int kMaxChunks = 4096;
 __global__ void __launch_bounds__(256) occ_mask_kernel(const float* __restrict__ grid, float thr, int64_t n_cells, uint32_t* __restrict__ masks,
@@ -281,11 +283,25 @@ __global__ void __launch_bounds__(1024) small_scan_kernel(const int32_t* __restr
     for (int k = 0; k < 4; k++) { const int i = threadIdx.x * 4 + k; if (i < n) out[i] = run; run += v[k]; }
     if (threadIdx.x == 0) out[n] = warp_tot[31];
 }
-// cell index + jittered position of every draw (j < M: uniform; j >= M: k-th occupied)
+// jittered position of a cell (networks.py:263-267), bit-identical with the torch expression
+__device__ __forceinline__ void cell_position(uint32_t idx, const float* __restrict__ rnd3, float inv_gm1, float s_minus_half, float half,
+                                              float* __restrict__ out3) {
+    const uint32_t c[3] = {arn_morton3d_invert(idx), arn_morton3d_invert(idx >> 1), arn_morton3d_invert(idx >> 2)};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float cc = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)(int32_t)c[d], inv_gm1), 2.0f), 1.0f), s_minus_half);
+        const float jj = __fmul_rn(__fsub_rn(__fmul_rn(rnd3[d], 2.0f), 1.0f), half);
+        out3[d] = __fadd_rn(cc, jj);
+    }
+}
+// cell index + jittered position of every draw (j < M: uniform; j >= M: k-th occupied).  SORTED: the index goes to idx_tmp
+// and into the histogram over the cells instead (place_cells_kernel writes the outputs in curve order).
+template <bool SORTED>
 __global__ void __launch_bounds__(256) pick_cells_kernel(const int32_t* __restrict__ coords1, const int64_t* __restrict__ u, int64_t M,
                                                          const uint32_t* __restrict__ masks, const int32_t* __restrict__ chunk_prefix, int n_chunks,
                                                          const float* __restrict__ rnd, float inv_gm1, float s_minus_half, float half,
-                                                         int64_t* __restrict__ indices, float* __restrict__ xyzs) {
+                                                         int64_t* __restrict__ indices, float* __restrict__ xyzs,
+                                                         uint32_t* __restrict__ idx_tmp, int32_t* __restrict__ hist) {
     __shared__ int s_prefix[kMaxChunks + 1];
     const bool occupied_half = (int64_t)blockIdx.x * blockDim.x >= M;  // M is a multiple of the block size (checked by the host)
     if (occupied_half) {
@@ -316,14 +332,60 @@ __global__ void __launch_bounds__(256) pick_cells_kernel(const int32_t* __restri
         const int bit = (total > 0 && found) ? (int)__fns(word, 0, rem + 1) : 0;  // (an empty grid degenerates to one cell, harmless: see networks.py)
         idx = (uint32_t)lo * kCellChunk + (uint32_t)w * 32u + (uint32_t)(bit & 31);
     }
-    indices[j] = (int64_t)idx;
-    const uint32_t c[3] = {arn_morton3d_invert(idx), arn_morton3d_invert(idx >> 1), arn_morton3d_invert(idx >> 2)};
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        const float cc = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)(int32_t)c[d], inv_gm1), 2.0f), 1.0f), s_minus_half);
-        const float jj = __fmul_rn(__fsub_rn(__fmul_rn(rnd[3 * j + d], 2.0f), 1.0f), half);
-        xyzs[3 * j + d] = __fadd_rn(cc, jj);
+    if (SORTED) {
+        idx_tmp[j] = idx;
+        atomicAdd(hist + idx, 1);
+        return;
     }
+    indices[j] = (int64_t)idx;
+    cell_position(idx, rnd + 3 * j, inv_gm1, s_minus_half, half, xyzs + 3 * j);
+}
+// counting sort over the cells, pass 2: totals of the histogram's 1024-cell chunks (one warp per chunk) ...
+__global__ void __launch_bounds__(256) hist_chunk_sum_kernel(const int32_t* __restrict__ hist, int64_t n_cells, int n_chunks, int32_t* __restrict__ chunk_tot) {
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    int sum = 0;
+    for (int w = 0; w < 32; w++) { const int64_t i = chunk * kCellChunk + w * 32 + lane; sum += i < n_cells ? hist[i] : 0; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+    if (lane == 0) chunk_tot[chunk] = sum;
+}
+// ... pass 3: the histogram becomes the table of first output slots (exclusive prefix inside the chunk + the chunk's base) ...
+__global__ void __launch_bounds__(256) hist_chunk_scan_kernel(int32_t* __restrict__ hist, int64_t n_cells, int n_chunks, const int32_t* __restrict__ chunk_base) {
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    int run = chunk_base[chunk];
+    for (int w = 0; w < 32; w++) {
+        const int64_t i = chunk * kCellChunk + w * 32 + lane;
+        const int v = i < n_cells ? hist[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+        if (i < n_cells) hist[i] = run + inc - v;
+        run += __shfl_sync(kFull, inc, 31);
+    }
+}
+// ... pass 4: every draw takes the next slot of its cell (draws of one cell land next to each other in arbitrary order, each with
+// the jitter of its own draw)
+__global__ void __launch_bounds__(256) place_cells_kernel(const uint32_t* __restrict__ idx_tmp, int32_t* __restrict__ cursor, int64_t n,
+                                                          const float* __restrict__ rnd, float inv_gm1, float s_minus_half, float half,
+                                                          int64_t* __restrict__ indices, float* __restrict__ xyzs) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t idx = idx_tmp[j];
+    const int64_t p = atomicAdd(cursor + idx, 1);
+    indices[p] = (int64_t)idx;
+    cell_position(idx, rnd + 3 * j, inv_gm1, s_minus_half, half, xyzs + 3 * p);
+}
+// dst[indices[i]] = src[i] (density_grid_tmp[c, indices] = density of networks.py:268; a cell drawn twice keeps one of its values)
+__global__ void __launch_bounds__(256) scatter_f32_kernel(float* __restrict__ dst, const int64_t* __restrict__ indices, const float* __restrict__ src, int64_t n,
+                                                          int64_t n_dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t o = indices[i];
+    if (o >= 0 && o < n_dst) dst[o] = src[i];
 }
 
 // networks.py:273-279: grid = where(grid < 0, grid, max(grid * decay, tmp)) in place, plus the sum / count of the positive
@@ -1717,9 +1779,9 @@ extern "C" ARN_API int arn_mark_invisible_cells(const int32_t* coords, const int
     return check_launch("mark_invisible_cells");
 }
 
-extern "C" ARN_API int arn_grid_sample_cells(const float* density_grid, float density_threshold, int grid_size, float s, const int32_t* coords1,
-                                             const int64_t* u, int64_t M, const float* rnd, void* scratch, int64_t* indices, float* xyzs,
-                                             arn_stream_t stream) {
+static int grid_sample_cells_impl(const float* density_grid, float density_threshold, int grid_size, float s, const int32_t* coords1,
+                                  const int64_t* u, int64_t M, const float* rnd, void* scratch, int64_t* indices, float* xyzs, bool sorted,
+                                  arn_stream_t stream) {
     ARN_REQUIRE(grid_size >= 2 && grid_size <= 1024 && M > 0 && M % 256 == 0, "bad sizes (M must be a positive multiple of 256)");
     ARN_REQUIRE(density_grid && coords1 && u && rnd && scratch && indices && xyzs, "null pointer");
     const int64_t n_cells = (int64_t)grid_size * grid_size * grid_size;
@@ -1727,19 +1789,56 @@ extern "C" ARN_API int arn_grid_sample_cells(const float* density_grid, float de
     ARN_REQUIRE(n_chunks <= kMaxChunks - 1, "grid too large for the single-CTA chunk scan (grid_size <= 160)");
     ARN_REQUIRE(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    // scratch: masks (32 per chunk) | chunk_count (n_chunks) | chunk_prefix (n_chunks + 1)
+    // scratch: masks (32 per chunk) | chunk_count (n_chunks) | chunk_prefix (n_chunks + 1) | pad | sorted only: chunk_tot (n_chunks) |
+    // chunk_base (n_chunks + 1) | hist (n_cells) | idx_tmp (2 M)
     uint32_t* masks = (uint32_t*)scratch;
     int32_t* chunk_count = (int32_t*)(masks + (size_t)n_chunks * 32);
     int32_t* chunk_prefix = chunk_count + n_chunks;
+    int32_t* chunk_tot = (int32_t*)scratch + (size_t)n_chunks * 34 + 4;
+    int32_t* chunk_base = chunk_tot + n_chunks;
+    int32_t* hist = chunk_base + n_chunks + 4;
+    uint32_t* idx_tmp = (uint32_t*)(hist + n_cells);
     ARN_LAUNCH("occ_mask_kernel", st, occ_mask_kernel<<<ceil_div((int64_t)n_chunks * 32, 256), 256, 0, st>>>(density_grid, density_threshold, n_cells, masks, chunk_count));
     if (int e = check_launch("occ_mask")) return e;
     ARN_LAUNCH("small_scan_kernel", st, small_scan_kernel<<<1, 1024, 0, st>>>(chunk_count, n_chunks, chunk_prefix));
     if (int e = check_launch("small_scan")) return e;
     const float s_minus_half = (float)((double)s - (double)s / (double)grid_size);
     const float half_f = (float)((double)s / (double)grid_size);
-    ARN_LAUNCH("pick_cells_kernel", st, pick_cells_kernel<<<ceil_div(2 * M, 256), 256, 0, st>>>(coords1, u, M, masks, chunk_prefix, n_chunks, rnd,
-                                                                                              1.0f / (float)(grid_size - 1), s_minus_half, half_f, indices, xyzs));
-    return check_launch("pick_cells");
+    const float inv_gm1 = 1.0f / (float)(grid_size - 1);
+    if (!sorted) {
+        ARN_LAUNCH("pick_cells_kernel", st, pick_cells_kernel<false><<<ceil_div(2 * M, 256), 256, 0, st>>>(coords1, u, M, masks, chunk_prefix, n_chunks, rnd,
+                   inv_gm1, s_minus_half, half_f, indices, xyzs, nullptr, nullptr));
+        return check_launch("pick_cells");
+    }
+    ARN_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_cells * sizeof(int32_t), st));
+    ARN_LAUNCH("pick_cells_kernel", st, pick_cells_kernel<true><<<ceil_div(2 * M, 256), 256, 0, st>>>(coords1, u, M, masks, chunk_prefix, n_chunks, rnd,
+               inv_gm1, s_minus_half, half_f, nullptr, nullptr, idx_tmp, hist));
+    if (int e = check_launch("pick_cells (sorted)")) return e;
+    ARN_LAUNCH("hist_chunk_sum_kernel", st, hist_chunk_sum_kernel<<<ceil_div((int64_t)n_chunks * 32, 256), 256, 0, st>>>(hist, n_cells, n_chunks, chunk_tot));
+    if (int e = check_launch("hist_chunk_sum")) return e;
+    ARN_LAUNCH("small_scan_kernel", st, small_scan_kernel<<<1, 1024, 0, st>>>(chunk_tot, n_chunks, chunk_base));
+    if (int e = check_launch("small_scan")) return e;
+    ARN_LAUNCH("hist_chunk_scan_kernel", st, hist_chunk_scan_kernel<<<ceil_div((int64_t)n_chunks * 32, 256), 256, 0, st>>>(hist, n_cells, n_chunks, chunk_base));
+    if (int e = check_launch("hist_chunk_scan")) return e;
+    ARN_LAUNCH("place_cells_kernel", st, place_cells_kernel<<<ceil_div(2 * M, 256), 256, 0, st>>>(idx_tmp, hist, 2 * M, rnd, inv_gm1, s_minus_half, half_f, indices, xyzs));
+    return check_launch("place_cells");
+}
+extern "C" ARN_API int arn_grid_sample_cells(const float* density_grid, float density_threshold, int grid_size, float s, const int32_t* coords1,
+                                             const int64_t* u, int64_t M, const float* rnd, void* scratch, int64_t* indices, float* xyzs,
+                                             arn_stream_t stream) {
+    return grid_sample_cells_impl(density_grid, density_threshold, grid_size, s, coords1, u, M, rnd, scratch, indices, xyzs, false, stream);
+}
+extern "C" ARN_API int arn_grid_sample_cells_sorted(const float* density_grid, float density_threshold, int grid_size, float s, const int32_t* coords1,
+                                                    const int64_t* u, int64_t M, const float* rnd, void* scratch, int64_t* indices, float* xyzs,
+                                                    arn_stream_t stream) {
+    return grid_sample_cells_impl(density_grid, density_threshold, grid_size, s, coords1, u, M, rnd, scratch, indices, xyzs, true, stream);
+}
+extern "C" ARN_API int arn_grid_scatter(float* dst, int64_t n_dst, const int64_t* indices, const float* src, int64_t n, arn_stream_t stream) {
+    ARN_REQUIRE(n >= 0 && n_dst >= 0, "bad size");
+    if (n == 0) return ARN_OK;
+    ARN_REQUIRE(dst && indices && src, "null pointer");
+    ARN_LAUNCH("scatter_f32_kernel", (cudaStream_t)stream, scatter_f32_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dst, indices, src, n, n_dst));
+    return check_launch("grid_scatter");
 }
 
 extern "C" ARN_API int arn_density_grid_update(float* density_grid, const float* density_tmp, const float* decay_cells, float decay,

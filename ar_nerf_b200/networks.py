@@ -191,36 +191,99 @@ class NGP(nn.Module):
         for c, (indices, coords) in enumerate(self.get_all_cells()):
             vren.mark_invisible_cells(coords, indices, self.grid_size, min(2 ** (c - 1), self.scale), w2c, K, img_wh, NEAR_DISTANCE,
                                       self.density_grid[c], self.count_grid[c])
+        self._grid_version = getattr(self, '_grid_version', 0) + 1  # a cell selection computed ahead of this call is stale
+
+    # ---- steady-state cell selection, one refresh ahead.  Which cells a refresh samples depends on the density grid the PREVIOUS
+    # refresh left behind and on random draws -- not on the weights -- so the draws, the selection (arn_grid_sample_cells_sorted:
+    # cells in curve order, which makes the density evaluation's hash-grid gathers 1.8x cheaper) and the zero fill of the scratch
+    # grid run on a side stream right behind a refresh, under the training steps that follow; the next refresh finds them done.
+    def _grid_key(self, density_threshold):
+        g = self.density_grid
+        return (g.data_ptr(), g._version, getattr(self, '_grid_version', 0), float(density_threshold), self.grid_size, self.cascades, float(self.scale))
+
+    def _refresh_buffers(self):
+        G, dev = self.grid_size, self.density_grid.device
+        M = G ** 3 // 4
+        b = getattr(self, '_refresh_ws', None)
+        if b is None or b['key'] != (G, self.cascades, dev):
+            b = self._refresh_ws = dict(
+                key=(G, self.cascades, dev), tmp=torch.zeros_like(self.density_grid), tmp_clean=True,
+                cells=[(torch.empty(2 * M, dtype=torch.int64, device=dev), torch.empty(2 * M, 3, device=dev)) for _ in range(self.cascades)],
+                side=torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None, ready=None, ready_key=None)
+        return b
+
+    def _draw_and_select(self, b, density_threshold, sort):
+        """The two randint draws of sample_uniform_and_occupied_cells, cascade by cascade, in the reference's order, then the
+        rand draw of the positions and the native selection (k-th occupied cell through bit masks) per cascade."""
+        G, dev = self.grid_size, self.density_grid.device
+        M = G ** 3 // 4
+        draws = [(torch.randint(G, (M, 3), dtype=torch.int32, device=dev), torch.randint(2 ** 31 - 1, (M,), device=dev))
+                 for _ in range(self.cascades)]
+        for c in range(self.cascades):
+            rnd = torch.rand((2 * M, 3), dtype=torch.float32, device=dev)
+            vren.grid_sample_cells(self.density_grid[c], density_threshold, G, min(2 ** (c - 1), self.scale), *draws[c], rnd, sort=sort, out=b['cells'][c])
+
+    def _prefetch_refresh(self, b, density_threshold):
+        main = torch.cuda.current_stream()
+        done = torch.cuda.Event(); done.record(main)       # this refresh has consumed the cells and the scratch grid
+        with torch.cuda.stream(b['side']):
+            b['side'].wait_event(done)
+            b['tmp'].zero_(); b['tmp_clean'] = True
+            self._draw_and_select(b, density_threshold, sort=True)
+            b['ready'] = torch.cuda.Event(); b['ready'].record(b['side'])
+        b['ready_key'] = self._grid_key(density_threshold)
 
     @torch.no_grad()
-    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):
-        """networks.py:252-281."""
-        density_grid_tmp = torch.zeros_like(self.density_grid)
+    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False, prefetch_next=None):
+        """networks.py:252-281.  prefetch_next: whether the NEXT call will be a steady-state refresh (warmup=False) with the same
+        threshold, so that its cell selection can be computed ahead (default: the kind of this call)."""
         G, dev = self.grid_size, self.density_grid.device
-        native_sampling = not warmup and G <= 160 and (G ** 3 // 4) % 256 == 0 and self.density_grid.is_cuda
+        native_sampling = G <= 160 and (G ** 3 // 4) % 256 == 0 and self.density_grid.is_cuda
+        if not native_sampling:
+            return self._update_density_grid_torch(density_threshold, warmup, decay, erode)
+        b = self._refresh_buffers()
+        main = torch.cuda.current_stream()
+        if b['ready'] is not None:
+            main.wait_event(b['ready'])   # (also orders the side stream's zero fill in front of the writes below)
+        prefetched = b['ready'] is not None and not warmup and b['ready_key'] == self._grid_key(density_threshold)
+        b['ready'] = None
+        if not b['tmp_clean']:
+            b['tmp'].zero_()
         if warmup:
             cells = self.get_all_cells()
-        elif native_sampling:
-            # the two randint draws of sample_uniform_and_occupied_cells, cascade by cascade, in the reference's order
-            M = G ** 3 // 4
-            draws = [(torch.randint(G, (M, 3), dtype=torch.int32, device=dev), torch.randint(2 ** 31 - 1, (M,), device=dev))
-                     for _ in range(self.cascades)]
-        else:
-            cells = self.sample_uniform_and_occupied_cells(G ** 3 // 4, density_threshold)
+        elif not prefetched:
+            self._draw_and_select(b, density_threshold, sort=False)
         for c in range(self.cascades):
-            s = min(2 ** (c - 1), self.scale)
-            if native_sampling:
-                # selection (k-th occupied cell through bit masks) and positions in one native call
-                rnd = torch.rand((2 * M, 3), dtype=torch.float32, device=dev)
-                indices, xyzs_w = vren.grid_sample_cells(self.density_grid[c], density_threshold, G, s, *draws[c], rnd)
-            else:
+            if warmup:
                 indices, coords = cells[c]
                 # xyzs_w = (coords/(G-1)*2-1)*(s - s/G) + (rand*2-1)*(s/G): one kernel, same torch.rand_like draw, same bits
                 rnd = torch.rand(coords.shape, dtype=torch.float32, device=coords.device)
-                xyzs_w = vren.grid_cell_positions(coords, rnd, self.grid_size, s)
-            density_grid_tmp[c, indices] = self.density(xyzs_w)
+                xyzs_w = vren.grid_cell_positions(coords, rnd, G, min(2 ** (c - 1), self.scale))
+            else:
+                indices, xyzs_w = b['cells'][c]
+            vren.grid_scatter(b['tmp'][c], indices, self.density(xyzs_w))  # density_grid_tmp[c, indices] = density (:268)
+        b['tmp_clean'] = False
         decay_cells = None
         if erode:
             decay_cells = torch.clamp(decay ** (1 / self.count_grid), 0.1, 0.95).float().contiguous()
         # where(grid < 0, grid, max(grid*decay, tmp)) in place, mean of the positive cells, threshold, packbits: no host sync
+        vren.density_grid_update(self.density_grid, b['tmp'], decay_cells, decay, density_threshold, self.density_bitfield)
+        self._grid_version = getattr(self, '_grid_version', 0) + 1
+        if (not warmup) if prefetch_next is None else prefetch_next:
+            self._prefetch_refresh(b, density_threshold)
+
+    @torch.no_grad()
+    def _update_density_grid_torch(self, density_threshold, warmup=False, decay=0.95, erode=False):
+        """The same refresh where the native cell selection does not apply (grid_size > 160, odd sizes, CPU tensors)."""
+        density_grid_tmp = torch.zeros_like(self.density_grid)
+        cells = self.get_all_cells() if warmup else self.sample_uniform_and_occupied_cells(self.grid_size ** 3 // 4, density_threshold)
+        for c in range(self.cascades):
+            s = min(2 ** (c - 1), self.scale)
+            indices, coords = cells[c]
+            rnd = torch.rand(coords.shape, dtype=torch.float32, device=coords.device)
+            xyzs_w = vren.grid_cell_positions(coords, rnd, self.grid_size, s)
+            density_grid_tmp[c, indices] = self.density(xyzs_w)
+        decay_cells = None
+        if erode:
+            decay_cells = torch.clamp(decay ** (1 / self.count_grid), 0.1, 0.95).float().contiguous()
         vren.density_grid_update(self.density_grid, density_grid_tmp, decay_cells, decay, density_threshold, self.density_bitfield)

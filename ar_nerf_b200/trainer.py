@@ -242,7 +242,7 @@ class _FusedWorkspace:
         self.dL_dopacity, self.dL_ddepth, self.dL_drgb = f(R), f(R), f(R, 3)
         self.sigmas, self.rgbs, self.ws_out = f(N), f(N, 3), f(N)
         self.dL_dsigmas, self.dL_drgbs, self.dfeat = f(N), f(N, 3), f(N, 32)
-        self.feat, self.hid, self.h = h(N, 32), h(N, 64), f(N, 16)
+        self.feat, self.hid = h(N, 32), h(N, 64)  # no fp32 h: the tensor-core backward reads fp16(h) out of in32
         self.in32, self.hid1, self.hid2 = h(N, 32), h(N, 64), h(N, 64)
         self.wimg = torch.empty(FIELD_SCRATCH_BYTES, dtype=torch.uint8, device=device)
         self.marched = torch.cuda.Event()
@@ -338,7 +338,7 @@ class NGPTrainer:
                 ptr(w.opacity), ptr(w.depth), ptr(w.rgb), ptr(w.rgb_final), ptr(w.dL_dopacity), ptr(w.dL_ddepth), ptr(w.dL_drgb),
                 w.capacity, ptr(ms.xyzs), ptr(ms.dirs), ptr(ms.deltas), ptr(ms.ts), ptr(w.sigmas), ptr(w.rgbs), ptr(w.ws_out),
                 ptr(w.dL_dsigmas), ptr(w.dL_drgbs), ptr(w.dfeat),
-                FieldWs(ptr(w.feat), ptr(w.hid), ptr(w.h), ptr(w.in32), ptr(w.hid1), ptr(w.hid2), ptr(w.wimg)),
+                FieldWs(ptr(w.feat), ptr(w.hid), None, ptr(w.in32), ptr(w.hid1), ptr(w.hid2), ptr(w.wimg)),
                 ptr(m.xyz_encoder.params.grad), ptr(m.rgb_net.params.grad), ptr(ms.loss))
             ms.cfg_key = key
         c = ms.cfg
@@ -423,7 +423,10 @@ class NGPTrainer:
         them on the device: their ray march is then overlapped with this step (pass the very same tensors next time)."""
         m = self.model
         if update_grid and self.global_step % self.update_interval == 0:
-            m.update_density_grid(0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=self.global_step < self.warmup_steps)
+            # (the refresh after this one is a steady-state refresh as soon as it lies behind the warm-up: its cell selection
+            # is then computed ahead, under the steps in between -- NGP.update_density_grid)
+            m.update_density_grid(0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=self.global_step < self.warmup_steps,
+                                  prefetch_next=self.global_step + self.update_interval >= self.warmup_steps)
             self._grid_epoch += 1
         if self.fused:
             next_is_update = update_grid and (self.global_step + 1) % self.update_interval == 0

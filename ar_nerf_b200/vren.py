@@ -169,27 +169,45 @@ def grid_cell_positions(coords, rnd, grid_size, s):
 _SAMPLE_SCRATCH = {}
 
 
-def grid_sample_cells(density_grid_c, density_threshold, grid_size, s, coords1, u, rnd):
+def grid_sample_cells(density_grid_c, density_threshold, grid_size, s, coords1, u, rnd, sort=False, out=None):
     """Steady-state cell selection of ONE cascade (networks.py:181-207 + :263-267) without torch glue: coords1 (M,3) i32 and
     u (M,) i64 are the caller's two randint draws, rnd (2M,3) its rand draw.  Returns (indices (2M,) i64, xyzs_w (2M,3)) in
-    draw order (uniform half first)."""
+    draw order (uniform half first) or, sort=True, along the morton curve (arn_grid_sample_cells_sorted).  out = (indices,
+    xyzs) to write into."""
     check_tensor(density_grid_c, "density_grid", torch.float32, 1)
     check_tensor(coords1, "coords1", torch.int32, 2, 3); check_tensor(u, "u", torch.int64, 1); check_tensor(rnd, "rnd", torch.float32, 2, 3)
     M = coords1.shape[0]
     if u.shape[0] != M or rnd.shape[0] != 2 * M or density_grid_c.numel() != grid_size ** 3:
         raise RuntimeError("grid_sample_cells: inconsistent sizes")
     dev = density_grid_c.device
-    need = ((grid_size ** 3 + 1023) // 1024) * 34 + 4  # ARN_GRID_SAMPLE_SCRATCH_INTS
-    key = (dev.index, need)
+    chunks = (grid_size ** 3 + 1023) // 1024
+    # ARN_GRID_SAMPLE_SCRATCH_INTS / ARN_GRID_SAMPLE_SORTED_SCRATCH_INTS
+    need = chunks * 36 + 12 + grid_size ** 3 + 2 * M if sort else chunks * 34 + 4
+    key = (dev.index, need, bool(sort))
     scratch = _SAMPLE_SCRATCH.get(key)
     if scratch is None:
-        _SAMPLE_SCRATCH.clear()
+        for k in [k for k in _SAMPLE_SCRATCH if k[2] == bool(sort)]:
+            del _SAMPLE_SCRATCH[k]
         scratch = _SAMPLE_SCRATCH[key] = torch.empty(need, dtype=torch.int32, device=dev)
-    indices = torch.empty(2 * M, dtype=torch.int64, device=dev)
-    xyzs = torch.empty(2 * M, 3, dtype=torch.float32, device=dev)
-    call("arn_grid_sample_cells", ptr(density_grid_c), float(density_threshold), int(grid_size), float(s), ptr(coords1), ptr(u), M, ptr(rnd),
-         ptr(scratch), ptr(indices), ptr(xyzs), stream())
+    if out is None:
+        indices = torch.empty(2 * M, dtype=torch.int64, device=dev)
+        xyzs = torch.empty(2 * M, 3, dtype=torch.float32, device=dev)
+    else:
+        indices, xyzs = out
+        check_tensor(indices, "indices", torch.int64, 1); check_tensor(xyzs, "xyzs", torch.float32, 2, 3)
+        if indices.shape[0] != 2 * M or xyzs.shape[0] != 2 * M:
+            raise RuntimeError("grid_sample_cells: out tensors must hold 2M cells")
+    call("arn_grid_sample_cells_sorted" if sort else "arn_grid_sample_cells", ptr(density_grid_c), float(density_threshold), int(grid_size), float(s),
+         ptr(coords1), ptr(u), M, ptr(rnd), ptr(scratch), ptr(indices), ptr(xyzs), stream())
     return indices, xyzs
+
+
+def grid_scatter(dst, indices, src):
+    """dst[indices] = src for 1-D f32 dst / src and i64 indices (networks.py:268), one native launch."""
+    check_tensor(dst, "dst", torch.float32, 1); check_tensor(indices, "indices", torch.int64, 1); check_tensor(src, "src", torch.float32, 1)
+    if indices.shape[0] != src.shape[0]:
+        raise RuntimeError("grid_scatter: indices and src must have the same length")
+    call("arn_grid_scatter", ptr(dst), dst.numel(), ptr(indices), ptr(src), src.shape[0], stream())
 
 
 _GRID_SCRATCH = {}

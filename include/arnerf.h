@@ -127,6 +127,18 @@ int arn_grid_cell_positions(const int32_t* coords, const float* rnd, int64_t n_c
 int arn_grid_sample_cells(const float* density_grid, float density_threshold, int grid_size, float s, const int32_t* coords1,
                           const int64_t* u, int64_t M, const float* rnd, void* scratch, int64_t* indices, float* xyzs,
                           arn_stream_t stream);
+/* The same selection with the 2M cells ordered along the morton curve (counting sort over the cells; the draws of one cell are
+ * neighbours in arbitrary order, each with the jitter of its own draw): the density evaluation that follows gathers neighbouring
+ * cells' hash-grid corners together (1 M cells: 167 us instead of 295).  The sort costs about what it saves, so it pays where the
+ * selection is computed AHEAD of the refresh -- it depends on the previous refresh's density_grid and the draws only.
+ * scratch: ARN_GRID_SAMPLE_SORTED_SCRATCH_INTS(G^3, M) int32, 16-byte aligned. */
+#define ARN_GRID_SAMPLE_SORTED_SCRATCH_INTS(n_cells, M) ((((n_cells) + 1023) / 1024) * 36 + 12 + (n_cells) + 2 * (M))
+int arn_grid_sample_cells_sorted(const float* density_grid, float density_threshold, int grid_size, float s, const int32_t* coords1,
+                                 const int64_t* u, int64_t M, const float* rnd, void* scratch, int64_t* indices, float* xyzs,
+                                 arn_stream_t stream);
+/* dst[indices[i]] = src[i], i < n (density_grid_tmp[c, indices] = density, networks.py:268): an index outside [0, n_dst) is
+ * skipped, a cell that occurs twice keeps one of its values (as index_put_ does). */
+int arn_grid_scatter(float* dst, int64_t n_dst, const int64_t* indices, const float* src, int64_t n, arn_stream_t stream);
 int arn_density_grid_update(float* density_grid, const float* density_tmp, const float* decay_cells, float decay,
                             float density_threshold, int64_t n_cells, uint8_t* density_bitfield, void* scratch,
                             arn_stream_t stream);

@@ -1075,7 +1075,35 @@ def test_density_grid_update_bits(w1):
     want = torch.cat([v.morton3D(coords1).long(), want2])
     assert torch.equal(n_idx, want)
     assert torch.equal(n_xyz, v.grid_cell_positions(v.morton3D_invert(n_idx.int()), rnd, G, 0.5))  # same bits as the torch expression
-    model.update_density_grid(5.912, warmup=False)
+    # the same selection in curve order (arn_grid_sample_cells_sorted, what a refresh computes ahead): the same (cell, position)
+    # pairs, cells ascending, draws of one cell next to each other in arbitrary order
+    s_idx, s_xyz = v.grid_sample_cells(model.density_grid[0], 5.912, G, 0.5, coords1, u, rnd, sort=True)
+    assert bool((s_idx[1:] >= s_idx[:-1]).all())
+    canon = lambda i, x: torch.stack([i.double(), x[:, 0].double(), x[:, 1].double(), x[:, 2].double()], 1).unique(dim=0, sorted=True)
+    a_, b_ = canon(n_idx, n_xyz), canon(s_idx, s_xyz)
+    assert a_.shape == b_.shape and torch.equal(a_, b_)
+    assert torch.equal(torch.bincount(s_idx, minlength=G ** 3), torch.bincount(n_idx, minlength=G ** 3))
+    # arn_grid_scatter: density_grid_tmp[c, indices] = values
+    vals = torch.rand(2 * M, device=dev())
+    once = torch.bincount(n_idx, minlength=G ** 3) == 1
+    got = torch.zeros(G ** 3, device=dev()); v.grid_scatter(got, n_idx, vals)
+    want_s = torch.zeros(G ** 3, device=dev()); want_s[n_idx] = vals
+    assert torch.equal(got[once], want_s[once]) and bool((got[~once & (torch.bincount(n_idx, minlength=G ** 3) == 0)] == 0).all())
+    # a refresh whose selection was computed ahead (side stream, curve order) against the same refresh computed in one go from
+    # the same random draws: the same cells get the same densities (a cell drawn twice keeps either draw's), the same bits
+    model.update_density_grid(5.912, warmup=False, prefetch_next=False)
+    grids = []
+    for ahead in (True, False):
+        m2 = NGP(0.5).to(dev()); w1.install(m2)
+        m2.load_state_dict(model.state_dict(), strict=False)
+        torch.manual_seed(11)
+        m2.update_density_grid(5.912, warmup=False, prefetch_next=ahead)
+        m2.update_density_grid(5.912, warmup=False, prefetch_next=False)
+        torch.cuda.synchronize()
+        grids.append((m2.density_grid.clone(), m2.density_bitfield.clone()))
+    assert torch.equal(grids[0][1], grids[1][1])
+    same = grids[0][0] == grids[1][0]
+    assert float(same.float().mean()) > 0.7 and abs(float(grids[0][0].clamp(min=0).mean()) - float(grids[1][0].clamp(min=0).mean())) < 1e-2 * float(grids[1][0].clamp(min=0).mean())
     assert model.density_grid.shape == (1, 128 ** 3)
 
 
