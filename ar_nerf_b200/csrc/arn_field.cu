@@ -5,6 +5,7 @@
 // MLP kernels.  The simt MLP follows the oracle's operation order exactly (k-ascending fmaf), which makes the whole
 // forward bit-comparable with oracle/oracle_field.c; the tensor-core MLP (arn_mlp_tc.cu) is validated against it.
 #include "arn_common.cuh"
+#include <atomic>
 #include "arn_field.cuh"
 #include "arn_tc.cuh"
 
@@ -958,11 +959,18 @@ extern "C" ARN_API int arn_field_bw_simt(const float* xyzs, int64_t n, const flo
     if (with_rgb) ARN_REQUIRE(ws.in32 && ws.hid1 && ws.hid2 && rgbs && grad_params_rgb, "null pointer (colour branch)");
     cudaStream_t st = (cudaStream_t)stream;
     const __half* pxyz = (const __half*)params_xyz_f16;
-    static int n_sm = 0;
-    if (!n_sm) { int dev = 0; ARN_CUDA(cudaGetDevice(&dev)); ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
     const int smem = (7168 + 3072 + 2 * 128 * 64) * (int)sizeof(__half);  // 53,248 B
-    static bool attr_set = false;
-    if (!attr_set) { ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+    // per device, once: SM count and the kernel's dynamic shared memory limit (function attributes are per device)
+    static std::atomic<int> n_sm_dev[16] = {};
+    int dev = 0;
+    ARN_CUDA(cudaGetDevice(&dev));
+    ARN_REQUIRE(dev >= 0 && dev < 16, "device index out of range");
+    int n_sm = n_sm_dev[dev].load(std::memory_order_acquire);
+    if (!n_sm) {
+        ARN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        ARN_CUDA(cudaFuncSetAttribute(field_mlp_bw_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        n_sm_dev[dev].store(n_sm, std::memory_order_release);
+    }
     const int64_t n_tiles = (n + 127) / 128;
     const int grid = (int)min((int64_t)n_sm * 4, n_tiles);
     ARN_LAUNCH("field_mlp_bw_simt_kernel", (cudaStream_t)stream, field_mlp_bw_simt_kernel<<<grid, 128, smem, st>>>(n, dL_dsigmas, with_rgb ? dL_drgbs : nullptr, rgbs, ws.h, (const __half*)ws.feat,
