@@ -209,27 +209,41 @@ class NGP(nn.Module):
             b = self._refresh_ws = dict(
                 key=(G, self.cascades, dev), tmp=torch.zeros_like(self.density_grid), tmp_clean=True,
                 cells=[(torch.empty(2 * M, dtype=torch.int64, device=dev), torch.empty(2 * M, 3, device=dev)) for _ in range(self.cascades)],
-                side=torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None, ready=None, ready_key=None)
+                side=torch.cuda.Stream(device=dev), ready=None, ready_key=None, gen=None, rng_delta=None)
         return b
 
-    def _draw_and_select(self, b, density_threshold, sort):
+    def _draw_and_select(self, b, density_threshold, sort, generator=None):
         """The two randint draws of sample_uniform_and_occupied_cells, cascade by cascade, in the reference's order, then the
         rand draw of the positions and the native selection (k-th occupied cell through bit masks) per cascade."""
         G, dev = self.grid_size, self.density_grid.device
         M = G ** 3 // 4
-        draws = [(torch.randint(G, (M, 3), dtype=torch.int32, device=dev), torch.randint(2 ** 31 - 1, (M,), device=dev))
-                 for _ in range(self.cascades)]
+        draws = [(torch.randint(G, (M, 3), dtype=torch.int32, device=dev, generator=generator),
+                  torch.randint(2 ** 31 - 1, (M,), device=dev, generator=generator)) for _ in range(self.cascades)]
         for c in range(self.cascades):
-            rnd = torch.rand((2 * M, 3), dtype=torch.float32, device=dev)
+            rnd = torch.rand((2 * M, 3), dtype=torch.float32, device=dev, generator=generator)
             vren.grid_sample_cells(self.density_grid[c], density_threshold, G, min(2 ** (c - 1), self.scale), *draws[c], rnd, sort=sort, out=b['cells'][c])
 
     def _prefetch_refresh(self, b, density_threshold):
+        """Queue the NEXT refresh's draws + selection (+ the zero fill of the scratch grid) on the side stream.  Its draws come
+        from a private generator seeded from the global seed; the refresh that uses them moves the global CUDA generator past the
+        draws it would have made itself (b['rng_delta'], measured once on the global generator and rewound), so every OTHER draw
+        of a seeded run -- the marcher's noise, a random background -- sits where it sits without the prefetch."""
+        dev = self.density_grid.device
+        glob = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+        if b['gen'] is None:
+            b['gen'] = torch.Generator(device=dev)
+            b['gen'].manual_seed((glob.initial_seed() + 0x9E3779B97F4A7C15) % (2 ** 63))
+        if b['rng_delta'] is None:
+            off = glob.get_offset()
+            self._draw_and_select(b, density_threshold, sort=False)   # (the cells it selects are overwritten below)
+            b['rng_delta'] = glob.get_offset() - off
+            glob.set_offset(off)
         main = torch.cuda.current_stream()
         done = torch.cuda.Event(); done.record(main)       # this refresh has consumed the cells and the scratch grid
         with torch.cuda.stream(b['side']):
             b['side'].wait_event(done)
             b['tmp'].zero_(); b['tmp_clean'] = True
-            self._draw_and_select(b, density_threshold, sort=True)
+            self._draw_and_select(b, density_threshold, sort=True, generator=b['gen'])
             b['ready'] = torch.cuda.Event(); b['ready'].record(b['side'])
         b['ready_key'] = self._grid_key(density_threshold)
 
@@ -253,6 +267,9 @@ class NGP(nn.Module):
             cells = self.get_all_cells()
         elif not prefetched:
             self._draw_and_select(b, density_threshold, sort=False)
+        else:  # the global generator moves as if this refresh had drawn its cells here
+            glob = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+            glob.set_offset(glob.get_offset() + b['rng_delta'])
         for c in range(self.cascades):
             if warmup:
                 indices, coords = cells[c]
