@@ -795,7 +795,7 @@ struct LossEpilogue {
 };
 // store: this lane writes the per-ray results; every calling lane gets the gradients (g_rgb, g_op, g_d) back
 __device__ __forceinline__ float ray_loss(const LossEpilogue& L, int64_t r, int64_t n_rays, const float c[3], float o, float dep, bool store,
-                                          float g_rgb[3], float& g_op, float& g_d) {
+                                          const float tgt[3], float g_rgb[3], float& g_op, float& g_d) {
     const float inv_r = 1.0f / (float)n_rays, inv_3r = inv_r / 3.0f;
     float loss = 0.0f;
     g_op = 0.0f;
@@ -804,7 +804,7 @@ __device__ __forceinline__ float ray_loss(const LossEpilogue& L, int64_t r, int6
         const float est = c[k] + L.bg[k] * (1.0f - o);
         if (store && L.rgb_out) L.rgb_out[3 * r + k] = est;
         const float den = est + 1e-3f;
-        const float e = (est - L.target[3 * r + k]) / den;
+        const float e = (est - tgt[k]) / den;
         loss += e * e * inv_3r;
         const float g = 2.0f * e / den * inv_3r * L.grad_scale;
         g_rgb[k] = g;
@@ -825,6 +825,17 @@ __device__ __forceinline__ float ray_loss(const LossEpilogue& L, int64_t r, int6
     return loss;
 }
 
+// Samples per lane and per turn of the training compositing loops: a warp takes kSPL * 32 consecutive samples of its ray at
+// once -- lane l the samples kSPL*l .. kSPL*l + kSPL-1, scanned inside the lane, the lanes' totals by ONE warp scan per quantity.
+// A batch's rays are few and long (W1: 2 000 of 8 192 rays hit the object, 120 samples each on average, 437 at most) and a turn
+// is a chain of dependent shuffles.  Measured on W1 (fused forward + loss + backward launch, 64-thread blocks): kSPL = 1 / 2 / 4 / 8
+// -> 25.3 / 20.2 / 21.4 / 29.1 us (more samples per lane = fewer turns but more registers = fewer rays resident).
+constexpr int kSPL = 2;
+// ... and the blocks are SMALL (two rays): a zero-sample ray's warp is gone at once, but its block holds its registers until the
+// block's longest ray is done -- with eight rays per block three quarters of the resident warps were such idle ones
+// (256 / 64 / 32 threads per block at kSPL = 4: 28.9 / 21.4 / 24.1 us).
+constexpr int kCompBlock = 64;
+
 // volumerendering.cu:86-150 for one ray, by one warp.  The reference's in-kernel serial thrust scan of dL_dws*ws (:118-121)
 // becomes a warp reduction (total) plus a running warp scan.  Shared by composite_train_bw_kernel and by the fused
 // forward + loss + backward of the training step.
@@ -841,56 +852,76 @@ __device__ __forceinline__ void composite_bw_ray(int lane, int64_t start, int N,
     }
     float T = 1.0f, r = 0.f, g = 0.f, b = 0.f, d = 0.f, ww = 0.f;
     bool done = false; int base = 0;
-    float n_sg = 0.f, n_dl = 0.f, n_cr = 0.f, n_cg = 0.f, n_cb = 0.f, n_ct = 0.f, n_gw = 0.f, n_ws = 0.f;  // prefetched chunk (see the forward)
-    if (lane < N) {
-        const int64_t s = start + lane;
-        n_sg = sigmas[s]; n_dl = deltas[s]; n_cr = rgbs[3 * s]; n_cg = rgbs[3 * s + 1]; n_cb = rgbs[3 * s + 2]; n_ct = ts[s];
-        if (dL_dws) { n_gw = dL_dws[s]; n_ws = ws[s]; }
-    }
-    for (; base < N && !done; base += 32) {
-        const int i = base + lane; const bool in = i < N; const int64_t s = start + i;
-        float sg = 0.f, dl = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, ct = 0.f, gw = 0.f, wsv = 0.f;
-        if (in) { sg = n_sg; dl = n_dl; cr = n_cr; cg = n_cg; cb = n_cb; ct = n_ct; gw = n_gw; wsv = n_ws; }
-        if (i + 32 < N) {
-            const int64_t q = s + 32;
-            n_sg = sigmas[q]; n_dl = deltas[q]; n_cr = rgbs[3 * q]; n_cg = rgbs[3 * q + 1]; n_cb = rgbs[3 * q + 2]; n_ct = ts[q];
-            if (dL_dws) { n_gw = dL_dws[q]; n_ws = ws[q]; }
+    for (; base < N && !done; base += 32 * kSPL) {
+        const int i0 = base + kSPL * lane;
+        float sg[kSPL], dl[kSPL], cr[kSPL], cg[kSPL], cb[kSPL], ct[kSPL], gw[kSPL], wsv[kSPL];
+#pragma unroll
+        for (int k = 0; k < kSPL; k++) {
+            const bool in = i0 + k < N; const int64_t q = start + i0 + k;
+            sg[k] = in ? sigmas[q] : 0.f; dl[k] = in ? deltas[q] : 0.f; ct[k] = in ? ts[q] : 0.f;
+            cr[k] = in ? rgbs[3 * q] : 0.f; cg[k] = in ? rgbs[3 * q + 1] : 0.f; cb[k] = in ? rgbs[3 * q + 2] : 0.f;
+            gw[k] = (in && dL_dws) ? dL_dws[q] : 0.f; wsv[k] = (in && dL_dws) ? ws[q] : 0.f;
         }
-        const float a = in ? alpha_of(sg, dl) : 0.0f;
-        const float incl = warp_incl_prod(__fsub_rn(1.0f, a), lane);
+        float al[kSPL], pp[kSPL];  // alpha, product of (1 - alpha) over the lane's samples up to and including k
+#pragma unroll
+        for (int k = 0; k < kSPL; k++) {
+            al[k] = i0 + k < N ? alpha_of(sg[k], dl[k]) : 0.0f;
+            const float om = __fsub_rn(1.0f, al[k]);
+            pp[k] = k ? pp[k - 1] * om : om;
+        }
+        const float incl = warp_incl_prod(pp[kSPL - 1], lane);
         float excl = __shfl_up_sync(kFull, incl, 1); if (lane == 0) excl = 1.0f;
-        const float T_before = T * excl, T_after = T * incl;
-        const unsigned term = __ballot_sync(kFull, in && (T_after <= T_thr));
-        const int last = term ? __ffs(term) - 1 : 31;
-        const bool use = in && lane <= last;
-        const float w = use ? a * T_before : 0.0f;
-        const float pr = r + warp_incl_sum(w * cr, lane), pg = g + warp_incl_sum(w * cg, lane);
-        const float pb = b + warp_incl_sum(w * cb, lane), pd = d + warp_incl_sum(w * ct, lane);
-        const float pww = ww + warp_incl_sum(gw * wsv, lane);
-        if (in) {
+        const float Tl = T * excl;  // transmittance in front of the lane's first sample
+        float Tb[kSPL], Ta[kSPL]; int first = kSPL;
+#pragma unroll
+        for (int k = kSPL - 1; k >= 0; k--) {
+            Tb[k] = k ? Tl * pp[k - 1] : Tl; Ta[k] = Tl * pp[k];
+            if (i0 + k < N && Ta[k] <= T_thr) first = k;
+        }
+        const unsigned term = __ballot_sync(kFull, first < kSPL);
+        int last = 32 * kSPL - 1;
+        if (term) { const int tl = __ffs(term) - 1; last = kSPL * tl + __shfl_sync(kFull, first, tl); }
+        float w[kSPL], s_r[kSPL], s_g[kSPL], s_b[kSPL], s_d[kSPL], s_w[kSPL];  // in-lane inclusive sums
+#pragma unroll
+        for (int k = 0; k < kSPL; k++) {
+            const bool use = i0 + k < N && kSPL * lane + k <= last;
+            w[k] = use ? al[k] * Tb[k] : 0.0f;
+            s_r[k] = (k ? s_r[k - 1] : 0.f) + w[k] * cr[k]; s_g[k] = (k ? s_g[k - 1] : 0.f) + w[k] * cg[k];
+            s_b[k] = (k ? s_b[k - 1] : 0.f) + w[k] * cb[k]; s_d[k] = (k ? s_d[k - 1] : 0.f) + w[k] * ct[k];
+            s_w[k] = (k ? s_w[k - 1] : 0.f) + gw[k] * wsv[k];
+        }
+        const float i_r = warp_incl_sum(s_r[kSPL - 1], lane), i_g = warp_incl_sum(s_g[kSPL - 1], lane), i_b = warp_incl_sum(s_b[kSPL - 1], lane);
+        const float i_d = warp_incl_sum(s_d[kSPL - 1], lane), i_w = dL_dws ? warp_incl_sum(s_w[kSPL - 1], lane) : 0.0f;
+        const float e_r = r + (i_r - s_r[kSPL - 1]), e_g = g + (i_g - s_g[kSPL - 1]), e_b = b + (i_b - s_b[kSPL - 1]);
+        const float e_d = d + (i_d - s_d[kSPL - 1]), e_w = ww + (i_w - s_w[kSPL - 1]);
+#pragma unroll
+        for (int k = 0; k < kSPL; k++) {
+            if (i0 + k >= N) continue;
+            const int64_t q = start + i0 + k;
             float o_r = 0.f, o_g = 0.f, o_b = 0.f, o_s = 0.f;
-            if (use) {
-                o_r = gR * w; o_g = gG * w; o_b = gB * w;
-                o_s = dl * (gR * (cr * T_after - (R - pr)) + gG * (cg * T_after - (G - pg)) + gB * (cb * T_after - (B - pb)) +
-                            gO * (1.0f - O) + gD * (ct * T_after - (D - pd)) + T_after * gw - (ww_total - pww));
+            if (kSPL * lane + k <= last) {
+                const float pr = e_r + s_r[k], pg = e_g + s_g[k], pb = e_b + s_b[k], pd = e_d + s_d[k], pww = e_w + s_w[k];
+                o_r = gR * w[k]; o_g = gG * w[k]; o_b = gB * w[k];
+                o_s = dl[k] * (gR * (cr[k] * Ta[k] - (R - pr)) + gG * (cg[k] * Ta[k] - (G - pg)) + gB * (cb[k] * Ta[k] - (B - pb)) +
+                               gO * (1.0f - O) + gD * (ct[k] * Ta[k] - (D - pd)) + Ta[k] * gw[k] - (ww_total - pww));
             }
-            dL_drgbs[3 * s] = o_r; dL_drgbs[3 * s + 1] = o_g; dL_drgbs[3 * s + 2] = o_b;
-            dL_dsigmas[s] = o_s;
+            dL_drgbs[3 * q] = o_r; dL_drgbs[3 * q + 1] = o_g; dL_drgbs[3 * q + 2] = o_b;
+            dL_dsigmas[q] = o_s;
         }
         if (term) done = true;
-        T = __shfl_sync(kFull, T_after, 31);
-        r = __shfl_sync(kFull, pr, 31); g = __shfl_sync(kFull, pg, 31); b = __shfl_sync(kFull, pb, 31);
-        d = __shfl_sync(kFull, pd, 31); ww = __shfl_sync(kFull, pww, 31);
+        T = __shfl_sync(kFull, Ta[kSPL - 1], 31);
+        r += __shfl_sync(kFull, i_r, 31); g += __shfl_sync(kFull, i_g, 31); b += __shfl_sync(kFull, i_b, 31);
+        d += __shfl_sync(kFull, i_d, 31); ww += __shfl_sync(kFull, i_w, 31);
     }
     for (int i = base + lane; i < N; i += 32) {  // zero-init in the reference (:171-172)
-        const int64_t s = start + i;
-        dL_drgbs[3 * s] = 0.f; dL_drgbs[3 * s + 1] = 0.f; dL_drgbs[3 * s + 2] = 0.f; dL_dsigmas[s] = 0.f;
+        const int64_t q = start + i;
+        dL_drgbs[3 * q] = 0.f; dL_drgbs[3 * q + 1] = 0.f; dL_drgbs[3 * q + 2] = 0.f; dL_dsigmas[q] = 0.f;
     }
 }
 
 // volumerendering.cu:5-44, one warp per rays_a row.
 template <bool LOSS>
-__global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+__global__ void __launch_bounds__(kCompBlock) composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                                  const float* __restrict__ deltas, const float* __restrict__ ts,
                                                                  const int64_t* __restrict__ rays_a, int64_t n_rays, float T_thr,
                                                                  int64_t* __restrict__ total_samples, float* __restrict__ opacity,
@@ -898,8 +929,8 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
                                                                  const LossEpilogue L, int64_t n_samples,
                                                                  float* __restrict__ bw_dsigmas, float* __restrict__ bw_drgbs) {
     pdl_enter();
-    __shared__ float s_loss[8];
-    if (LOSS && threadIdx.x < 8) s_loss[threadIdx.x] = 0.0f;
+    __shared__ float s_loss[kCompBlock / 32];
+    if (LOSS && threadIdx.x < kCompBlock / 32) s_loss[threadIdx.x] = 0.0f;
     if (LOSS) __syncthreads();
     const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -914,29 +945,41 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
     float T = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
     int64_t samples = N; bool done = false;
     int base = 0;
-    // the next 32 samples are requested before the current 32 go through the scans: a long ray no longer pays one
-    // exposed load latency per chunk
-    float n_sg = 0.f, n_dl = 0.f, n_cr = 0.f, n_cg = 0.f, n_cb = 0.f, n_ct = 0.f;
-    if (lane < N) { const int64_t s = start + lane; n_sg = sigmas[s]; n_dl = deltas[s]; n_cr = rgbs[3 * s]; n_cg = rgbs[3 * s + 1]; n_cb = rgbs[3 * s + 2]; n_ct = ts[s]; }
-    for (; base < N && !done; base += 32) {
-        const int i = base + lane; const bool in = i < N; const int64_t s = start + i;
-        const float c_sg = n_sg, c_dl = n_dl, c_cr = n_cr, c_cg = n_cg, c_cb = n_cb, c_ct = n_ct;
-        if (i + 32 < N) { const int64_t q = s + 32; n_sg = sigmas[q]; n_dl = deltas[q]; n_cr = rgbs[3 * q]; n_cg = rgbs[3 * q + 1]; n_cb = rgbs[3 * q + 2]; n_ct = ts[q]; }
-        const float a = in ? alpha_of(c_sg, c_dl) : 0.0f;
-        const float incl = warp_incl_prod(__fsub_rn(1.0f, a), lane);
+    float tgt[3] = {0.f, 0.f, 0.f};  // the ray's target colour, requested in front of the sample loop (used by the loss behind it)
+    if (LOSS && live) { tgt[0] = L.target[3 * ray_idx]; tgt[1] = L.target[3 * ray_idx + 1]; tgt[2] = L.target[3 * ray_idx + 2]; }
+    for (; base < N && !done; base += 32 * kSPL) {
+        const int i0 = base + kSPL * lane;
+        float al[kSPL], pp[kSPL], cr[kSPL], cg[kSPL], cb[kSPL], ct[kSPL];
+#pragma unroll
+        for (int k = 0; k < kSPL; k++) {
+            const bool in = i0 + k < N; const int64_t q = start + i0 + k;
+            const float sg = in ? sigmas[q] : 0.f, dl = in ? deltas[q] : 0.f;
+            ct[k] = in ? ts[q] : 0.f; cr[k] = in ? rgbs[3 * q] : 0.f; cg[k] = in ? rgbs[3 * q + 1] : 0.f; cb[k] = in ? rgbs[3 * q + 2] : 0.f;
+            al[k] = in ? alpha_of(sg, dl) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < kSPL; k++) { const float om = __fsub_rn(1.0f, al[k]); pp[k] = k ? pp[k - 1] * om : om; }
+        const float incl = warp_incl_prod(pp[kSPL - 1], lane);
         float excl = __shfl_up_sync(kFull, incl, 1); if (lane == 0) excl = 1.0f;
-        const float T_before = T * excl, T_after = T * incl;
-        const unsigned term = __ballot_sync(kFull, in && (T_after <= T_thr));
-        const int last = term ? __ffs(term) - 1 : 31;  // the terminating sample still contributes (:37-40)
-        const bool use = in && lane <= last;
-        const float w = use ? a * T_before : 0.0f;
-        if (in) ws[s] = w;
-        float cr = 0.f, cg = 0.f, cb = 0.f, ct = 0.f;
-        if (use) { cr = c_cr; cg = c_cg; cb = c_cb; ct = c_ct; }
-        acc_r += warp_sum(w * cr); acc_g += warp_sum(w * cg); acc_b += warp_sum(w * cb);
-        acc_d += warp_sum(w * ct); acc_o += warp_sum(w);
+        const float Tl = T * excl;  // transmittance in front of the lane's first sample
+        int first = kSPL;
+#pragma unroll
+        for (int k = kSPL - 1; k >= 0; k--) if (i0 + k < N && Tl * pp[k] <= T_thr) first = k;
+        const unsigned term = __ballot_sync(kFull, first < kSPL);
+        int last = 32 * kSPL - 1;  // the terminating sample still contributes (:37-40)
+        if (term) { const int tl = __ffs(term) - 1; last = kSPL * tl + __shfl_sync(kFull, first, tl); }
+        float p_r = 0.f, p_g = 0.f, p_b = 0.f, p_d = 0.f, p_o = 0.f;
+#pragma unroll
+        for (int k = 0; k < kSPL; k++) {
+            const bool in = i0 + k < N;
+            const float w = (in && kSPL * lane + k <= last) ? al[k] * (k ? Tl * pp[k - 1] : Tl) : 0.0f;
+            if (in) ws[start + i0 + k] = w;
+            p_r += w * cr[k]; p_g += w * cg[k]; p_b += w * cb[k]; p_d += w * ct[k]; p_o += w;
+        }
+        acc_r += warp_sum(p_r); acc_g += warp_sum(p_g); acc_b += warp_sum(p_b);
+        acc_d += warp_sum(p_d); acc_o += warp_sum(p_o);
         if (term) { done = true; samples = base + last; }  // break happens before samples++ (:40-41)
-        T = __shfl_sync(kFull, T_after, 31);
+        T = __shfl_sync(kFull, Tl * pp[kSPL - 1], 31);
     }
     for (int i = base + lane; i < N; i += 32) ws[start + i] = 0.0f;  // after termination (reference: zero-init, :59)
     if (lane == 0 && live) {
@@ -950,18 +993,18 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
         // training step needs no second compositing launch and no re-read of rays_a / the per-ray outputs
         const float c[3] = {acc_r, acc_g, acc_b};
         float g_rgb[3], g_op, g_d;
-        const float l = ray_loss(L, ray_idx, n_rays, c, acc_o, acc_d, lane == 0, g_rgb, g_op, g_d);
+        const float l = ray_loss(L, ray_idx, n_rays, c, acc_o, acc_d, lane == 0, tgt, g_rgb, g_op, g_d);
         if (lane == 0) s_loss[threadIdx.x >> 5] = l;
         if (bw_dsigmas && N > 0)
             composite_bw_ray(lane, start, N, acc_r, acc_g, acc_b, acc_o, acc_d, g_rgb[0], g_rgb[1], g_rgb[2], g_op, g_d, nullptr, sigmas, rgbs, ws, deltas, ts,
                              T_thr, bw_dsigmas, bw_drgbs);
     }
-    if (LOSS) {  // one atomic per CTA (8 rays)
+    if (LOSS) {  // one atomic per CTA
         __syncthreads();
         if (threadIdx.x == 0) {
             float v = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 8; k++) v += s_loss[k];
+            for (int k = 0; k < kCompBlock / 32; k++) v += s_loss[k];
             atomicAdd(L.loss_out, v);
         }
     }
@@ -969,7 +1012,7 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(const float* __
 
 // volumerendering.cu:86-150, one warp per row.  The reference's in-kernel serial thrust scan of dL_dws*ws (:118-121)
 // becomes a warp reduction (total) plus a running warp scan.
-__global__ void __launch_bounds__(256) composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __restrict__ dL_ddepth,
+__global__ void __launch_bounds__(kCompBlock) composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __restrict__ dL_ddepth,
                                                                  const float* __restrict__ dL_drgb, const float* __restrict__ dL_dws,
                                                                  const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                                  const float* __restrict__ ws, const float* __restrict__ deltas,
@@ -1969,7 +2012,7 @@ extern "C" ARN_API int arn_composite_train_fw(const float* sigmas, const float* 
     if (n_rays == 0) return ARN_OK;
     ARN_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "null pointer");
     ARN_REQUIRE(n_samples == 0 || (sigmas && rgbs && deltas && ts && ws), "null pointer");
-    ARN_LAUNCH_PDL("composite_train_fw_kernel", (cudaStream_t)stream, (composite_train_fw_kernel<false>), ceil_div(n_rays * 32, 256), 256, 0, sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
+    ARN_LAUNCH_PDL("composite_train_fw_kernel", (cudaStream_t)stream, (composite_train_fw_kernel<false>), ceil_div(n_rays * 32, kCompBlock), kCompBlock, 0, sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
                                                                                           total_samples, opacity, depth, rgb, ws, LossEpilogue{}, n_samples, nullptr, nullptr);
     return check_launch("composite_train_fw");
 }
@@ -2004,7 +2047,7 @@ extern "C" int arn_composite_train_fw_loss_ex(const float* sigmas, const float* 
     if (zero_loss) ARN_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
     LossEpilogue L{target, {bg_host[0], bg_host[1], bg_host[2]}, lambda_opacity, lambda_depth, grid_scale, grad_scale, rgb_out, dL_drgb, dL_dopacity,
                    dL_ddepth, loss_out};
-    ARN_LAUNCH_PDL("composite_train_fw_loss_kernel", st, (composite_train_fw_kernel<true>), ceil_div(n_rays * 32, 256), 256, 0, sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
+    ARN_LAUNCH_PDL("composite_train_fw_loss_kernel", st, (composite_train_fw_kernel<true>), ceil_div(n_rays * 32, kCompBlock), kCompBlock, 0, sigmas, rgbs, deltas, ts, rays_a, n_rays, T_threshold,
                                                                                           total_samples, opacity, depth, rgb, ws, L, n_samples, bw_dsigmas, bw_drgbs);
     return check_launch("composite_train_fw_loss");
 }
@@ -2018,7 +2061,7 @@ extern "C" ARN_API int arn_composite_train_bw(const float* dL_dopacity, const fl
     if (n_rays == 0 || n_samples == 0) return ARN_OK;
     ARN_REQUIRE(dL_dopacity && dL_ddepth && dL_drgb && sigmas && rgbs && ws && deltas && ts && rays_a && opacity && depth && rgb && dL_dsigmas && dL_drgbs,
                 "null pointer");
-    ARN_LAUNCH("composite_train_bw_kernel", (cudaStream_t)stream, composite_train_bw_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws,
+    ARN_LAUNCH("composite_train_bw_kernel", (cudaStream_t)stream, composite_train_bw_kernel<<<ceil_div(n_rays * 32, kCompBlock), kCompBlock, 0, (cudaStream_t)stream>>>(dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws,
                                                                                           deltas, ts, rays_a, opacity, depth, rgb, n_rays,
                                                                                           T_threshold, dL_dsigmas, dL_drgbs, n_samples));
     return check_launch("composite_train_bw");
