@@ -3,7 +3,6 @@
 show_gui.py:94 and insert/main.py:126,645 can call it unchanged.  The kernels underneath are libarnerf.so."""
 import torch
 import torch.nn.functional as F
-from einops import rearrange
 
 from . import vren
 from .custom_functions import RayAABBIntersector, RayMarcher, VolumeRenderer
@@ -353,105 +352,72 @@ def __render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     if fused:
         opacity, depth, rgb, total_samples = _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs)
         return _finish_test(results, opacity, depth, rgb, total_samples, rays_d, **kwargs)
-    opacity = torch.zeros(N_rays, device=device)
-    depth = torch.zeros(N_rays, device=device)
-    rgb = torch.zeros(N_rays, 3, device=device)
-
-    samples = total_samples = 0
-    alive_indices = torch.arange(N_rays, device=device)
-    min_samples = 1 if exp_step_factor == 0 else 4
-    hits_t2 = hits_t[:, 0]  # (R,2) view, marched in place
-
-    while samples < kwargs.get('max_samples', MAX_SAMPLES):
-        N_alive = len(alive_indices)
-        if N_alive == 0: break
-
-        N_samples = max(min(N_rays // N_alive, 64), min_samples)
-        samples += N_samples
-
-        xyzs, dirs, deltas, ts, N_eff_samples = \
-            vren.raymarching_test(rays_o, rays_d, hits_t2, alive_indices, model.density_bitfield, model.cascades,
-                                  model.scale, exp_step_factor, model.grid_size, MAX_SAMPLES, N_samples)
-        total_samples += N_eff_samples.sum()
-        xyzs = rearrange(xyzs, 'n1 n2 c -> (n1 n2) c')
-        dirs = rearrange(dirs, 'n1 n2 c -> (n1 n2) c')
-        valid_mask = ~torch.all(dirs == 0, dim=1)
-        if valid_mask.sum() == 0: break
-
-        sigmas = torch.zeros(len(xyzs), device=device)
-        rgbs = torch.zeros(len(xyzs), 3, device=device)
-
-        xyzs = xyzs[valid_mask]; dirs = dirs[valid_mask]
-        pts_num = xyzs.shape[0]
-        val_batch_size = kwargs.get('val_batch_size', pts_num)
-        sigma_bat_res = []; rgb_bat_res = []
-        for i in range(0, pts_num, val_batch_size):
-            sigma_bat, rgb_bat = model(xyzs[i:i + val_batch_size], dirs[i:i + val_batch_size], **kwargs)
-            sigma_bat_res.append(sigma_bat)
-            rgb_bat_res.append(rgb_bat)
-        sigmas[valid_mask] = torch.concat(sigma_bat_res, 0)
-        rgbs[valid_mask] = torch.concat(rgb_bat_res, 0).float()
-
-        sigmas = rearrange(sigmas, '(n1 n2) -> n1 n2', n2=N_samples)
-        rgbs = rearrange(rgbs, '(n1 n2) c -> n1 n2 c', n2=N_samples)
-
-        vren.composite_test_fw(sigmas, rgbs, deltas, ts, hits_t2, alive_indices, kwargs.get('T_threshold', 1e-4),
-                               N_eff_samples, opacity, depth, rgb)
-        alive_indices = alive_indices[alive_indices >= 0]  # remove converged rays
-
+    # ---- the reference's loop op by op (the cross-check of the fused loop, and the path of the HDR / CUDA-core field variants)
+    opacity, depth, rgb = (torch.zeros(N_rays, *tail, device=device) for tail in ((), (), (3,)))
+    alive = torch.arange(N_rays, device=device)
+    hits_near_far = hits_t[:, 0]                       # (R,2) view, marched in place
+    budget, threshold = kwargs.get('max_samples', MAX_SAMPLES), kwargs.get('T_threshold', 1e-4)
+    fewest = 1 if exp_step_factor == 0 else 4
+    requested, total_samples = 0, 0
+    while requested < budget and alive.numel() > 0:
+        per_ray = max(min(N_rays // alive.numel(), 64), fewest)   # few alive rays -> many samples each (rendering.py:197-199)
+        requested += per_ray
+        xyzs, dirs, deltas, ts, n_eff = vren.raymarching_test(rays_o, rays_d, hits_near_far, alive, model.density_bitfield, model.cascades,
+                                                             model.scale, exp_step_factor, model.grid_size, MAX_SAMPLES, per_ray)
+        total_samples = total_samples + n_eff.sum()
+        xyzs, dirs = xyzs.reshape(-1, 3), dirs.reshape(-1, 3)
+        real = (dirs != 0).any(dim=1)                  # padding slots carry a zero direction
+        if not bool(real.any()):
+            break
+        sigmas, rgbs = _field_on_real_samples(model, xyzs, dirs, real, kwargs)
+        vren.composite_test_fw(sigmas.view(-1, per_ray), rgbs.view(-1, per_ray, 3), deltas, ts, hits_near_far, alive, threshold,
+                               n_eff, opacity, depth, rgb)
+        alive = alive[alive >= 0]                      # composite_test_fw marks the rays it has finished with -1
     return _finish_test(results, opacity, depth, rgb, total_samples, rays_d, **kwargs)
 
 
-def _finish_test(results, opacity, depth, rgb, total_samples, rays_d, **kwargs):
-    """rendering.py:238-253: result dict and background blend."""
-    device = rgb.device
-    results['opacity'] = opacity
-    results['depth'] = depth
-    results['rgb'] = rgb
-    results['total_samples'] = total_samples  # total samples for all rays
+def _field_on_real_samples(model, xyzs, dirs, real, kwargs):
+    """(sigmas (n), rgbs (n,3)) over the padded sample list: the field where `real`, zeros elsewhere; at most `val_batch_size`
+    samples per field call (rendering.py:209-219)."""
+    pts, views = xyzs[real], dirs[real]
+    step = kwargs.get('val_batch_size', pts.shape[0])
+    parts = [model(pts[i:i + step], views[i:i + step], **kwargs) for i in range(0, pts.shape[0], step)]
+    sigmas, rgbs = xyzs.new_zeros(xyzs.shape[0]), xyzs.new_zeros(xyzs.shape[0], 3)
+    sigmas[real] = torch.cat([p[0] for p in parts], 0)
+    rgbs[real] = torch.cat([p[1] for p in parts], 0).float()
+    return sigmas, rgbs
 
-    rgb_bg = torch.zeros(3, device=device)
-    SH_bkg = kwargs.get('SH_bkg', None)
-    if SH_bkg is not None:
-        rgb_bg = get_SH_val(SH_bkg, rays_d, clamp_postive=True)
-    IM_bkg = kwargs.get('IM_bkg', None)
-    if IM_bkg is not None:
-        rgb_bg = IM_bkg
+
+def _finish_test(results, opacity, depth, rgb, total_samples, rays_d, **kwargs):
+    """rendering.py:238-253: the result dict; the background behind the rays -- an image (IM_bkg) before a spherical-harmonics
+    environment (SH_bkg) before black -- is blended in unless blend_bkg=False."""
+    background = kwargs.get('IM_bkg')
+    if background is None:
+        sh = kwargs.get('SH_bkg')
+        background = torch.zeros(3, device=rgb.device) if sh is None else get_SH_val(sh, rays_d, clamp_postive=True)
     if kwargs.get('blend_bkg', True):
-        results['rgb'] += rgb_bg * rearrange(1 - opacity, 'n -> n 1')
+        rgb += background * (1 - opacity)[:, None]
+    results.update(opacity=opacity, depth=depth, rgb=rgb, total_samples=total_samples)
     return results
 
 
 def __render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):
-    """rendering.py:255-298: march -> field -> composite, background blend (Q9)."""
-    exp_step_factor = kwargs.get('exp_step_factor', 0.)
-    results = {}
-
-    (rays_a, xyzs, dirs, results['deltas'], results['ts'], results['rm_samples']) = \
-        RayMarcher.apply(rays_o, rays_d, hits_t[:, 0], model.density_bitfield, model.cascades, model.scale,
-                         exp_step_factor, model.grid_size, MAX_SAMPLES, kwargs.get('noise', None))
-
-    for k, v in kwargs.items():  # supply additional inputs, repeated per ray
-        if isinstance(v, torch.Tensor) and k != 'noise':
-            kwargs[k] = torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0)
+    """rendering.py:255-298: march -> field -> composite, then the background behind what is left of each ray (Q9)."""
+    step_factor = kwargs.get('exp_step_factor', 0.)
+    rays_a, xyzs, dirs, deltas, ts, marched = RayMarcher.apply(rays_o, rays_d, hits_t[:, 0], model.density_bitfield, model.cascades, model.scale,
+                                                             step_factor, model.grid_size, MAX_SAMPLES, kwargs.get('noise', None))
+    # per-ray tensors among the keyword arguments (exposure ...) follow their ray's samples (rendering.py:266-268)
+    for name, value in kwargs.items():
+        if torch.is_tensor(value) and name != 'noise':
+            kwargs[name] = value[rays_a[:, 0]].repeat_interleave(rays_a[:, 2], 0)
     sigmas, rgbs = model(xyzs, dirs, **kwargs)
-
-    (results['vr_samples'], results['opacity'], results['depth'], results['rgb'], results['ws']) = \
-        VolumeRenderer.apply(sigmas, rgbs.contiguous(), results['deltas'], results['ts'], rays_a,
-                             kwargs.get('T_threshold', 1e-4))
-    results['rays_a'] = rays_a
-
+    composited, opacity, depth, rgb, ws = VolumeRenderer.apply(sigmas, rgbs.contiguous(), deltas, ts, rays_a, kwargs.get('T_threshold', 1e-4))
     if kwargs.get('random_bg', False):
-        rgb_bg = torch.rand(3, device=rays_o.device)
-    else:
-        if exp_step_factor == 0:  # synthetic
-            rgb_bg = torch.ones(3, device=rays_o.device)
-        else:  # real
-            rgb_bg = torch.zeros(3, device=rays_o.device)
-
-    results['rgb'] = results['rgb'] + rgb_bg * rearrange(1 - results['opacity'], 'n -> n 1')
-    del rgb_bg
-    return results
+        background = torch.rand(3, device=rays_o.device)
+    else:  # white behind synthetic scenes (fixed step), black behind real ones
+        background = torch.full((3,), 1.0 if step_factor == 0 else 0.0, device=rays_o.device)
+    return {'deltas': deltas, 'ts': ts, 'rm_samples': marched, 'vr_samples': composited, 'opacity': opacity, 'depth': depth,
+            'rgb': rgb + background * (1 - opacity)[:, None], 'ws': ws, 'rays_a': rays_a}
 
 
 @torch.enable_grad()
