@@ -209,6 +209,8 @@ class NGP(nn.Module):
             b = self._refresh_ws = dict(
                 key=(G, self.cascades, dev), tmp=torch.zeros_like(self.density_grid), tmp_clean=True,
                 cells=[(torch.empty(2 * M, dtype=torch.int64, device=dev), torch.empty(2 * M, 3, device=dev)) for _ in range(self.cascades)],
+                # the side stream's selection has its own scratch: another model's refresh may run beside it
+                scratch=torch.empty(vren.grid_sample_scratch_ints(G, M, sort=True), dtype=torch.int32, device=dev),
                 side=torch.cuda.Stream(device=dev), ready=None, ready_key=None, gen=None, rng_delta=None)
         return b
 
@@ -221,7 +223,8 @@ class NGP(nn.Module):
                   torch.randint(2 ** 31 - 1, (M,), device=dev, generator=generator)) for _ in range(self.cascades)]
         for c in range(self.cascades):
             rnd = torch.rand((2 * M, 3), dtype=torch.float32, device=dev, generator=generator)
-            vren.grid_sample_cells(self.density_grid[c], density_threshold, G, min(2 ** (c - 1), self.scale), *draws[c], rnd, sort=sort, out=b['cells'][c])
+            vren.grid_sample_cells(self.density_grid[c], density_threshold, G, min(2 ** (c - 1), self.scale), *draws[c], rnd, sort=sort, out=b['cells'][c],
+                                   scratch=b['scratch'])
 
     def _prefetch_refresh(self, b, density_threshold):
         """Queue the NEXT refresh's draws + selection (+ the zero fill of the scratch grid) on the side stream.  Its draws come

@@ -169,26 +169,35 @@ def grid_cell_positions(coords, rnd, grid_size, s):
 _SAMPLE_SCRATCH = {}
 
 
-def grid_sample_cells(density_grid_c, density_threshold, grid_size, s, coords1, u, rnd, sort=False, out=None):
+def grid_sample_scratch_ints(grid_size, M, sort=False):
+    """ARN_GRID_SAMPLE_SCRATCH_INTS / ARN_GRID_SAMPLE_SORTED_SCRATCH_INTS (include/arnerf.h)."""
+    chunks = (grid_size ** 3 + 1023) // 1024
+    return chunks * 36 + 12 + grid_size ** 3 + 2 * M if sort else chunks * 34 + 4
+
+
+def grid_sample_cells(density_grid_c, density_threshold, grid_size, s, coords1, u, rnd, sort=False, out=None, scratch=None):
     """Steady-state cell selection of ONE cascade (networks.py:181-207 + :263-267) without torch glue: coords1 (M,3) i32 and
     u (M,) i64 are the caller's two randint draws, rnd (2M,3) its rand draw.  Returns (indices (2M,) i64, xyzs_w (2M,3)) in
     draw order (uniform half first) or, sort=True, along the morton curve (arn_grid_sample_cells_sorted).  out = (indices,
-    xyzs) to write into."""
+    xyzs) to write into; scratch = the caller's own int32 workspace (grid_sample_scratch_ints) instead of the shared one."""
     check_tensor(density_grid_c, "density_grid", torch.float32, 1)
     check_tensor(coords1, "coords1", torch.int32, 2, 3); check_tensor(u, "u", torch.int64, 1); check_tensor(rnd, "rnd", torch.float32, 2, 3)
     M = coords1.shape[0]
     if u.shape[0] != M or rnd.shape[0] != 2 * M or density_grid_c.numel() != grid_size ** 3:
         raise RuntimeError("grid_sample_cells: inconsistent sizes")
     dev = density_grid_c.device
-    chunks = (grid_size ** 3 + 1023) // 1024
-    # ARN_GRID_SAMPLE_SCRATCH_INTS / ARN_GRID_SAMPLE_SORTED_SCRATCH_INTS
-    need = chunks * 36 + 12 + grid_size ** 3 + 2 * M if sort else chunks * 34 + 4
-    key = (dev.index, need, bool(sort))
-    scratch = _SAMPLE_SCRATCH.get(key)
-    if scratch is None:
-        for k in [k for k in _SAMPLE_SCRATCH if k[2] == bool(sort)]:
-            del _SAMPLE_SCRATCH[k]
-        scratch = _SAMPLE_SCRATCH[key] = torch.empty(need, dtype=torch.int32, device=dev)
+    need = grid_sample_scratch_ints(grid_size, M, sort)
+    if scratch is not None:  # the caller's own (calls that may overlap on different streams must not share one)
+        check_tensor(scratch, "scratch", torch.int32, 1)
+        if scratch.numel() < need:
+            raise RuntimeError("grid_sample_cells: scratch too small")
+    else:
+        key = (dev.index, need, bool(sort))
+        scratch = _SAMPLE_SCRATCH.get(key)
+        if scratch is None:
+            for k in [k for k in _SAMPLE_SCRATCH if k[2] == bool(sort)]:
+                del _SAMPLE_SCRATCH[k]
+            scratch = _SAMPLE_SCRATCH[key] = torch.empty(need, dtype=torch.int32, device=dev)
     if out is None:
         indices = torch.empty(2 * M, dtype=torch.int64, device=dev)
         xyzs = torch.empty(2 * M, 3, dtype=torch.float32, device=dev)
