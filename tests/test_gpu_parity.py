@@ -834,7 +834,7 @@ def test_pipelined_field_evaluation_is_the_same_step(w1):
             _lib.set_tunable("pipeline_parts", 1)
         assert int(res["rm_samples"]) > 64 * 1024  # large enough for the split to be taken
         losses.append(float(loss)); grads.append((N(model.xyz_encoder.params.grad), N(model.rgb_net.params.grad)))
-    assert abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[0])
+    assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[0])  # order-dependent fp32 atomic sum over 4096 two-ray blocks
     assert_sum(grads[1][0], grads[0][0], l1[0], C_TIES, rtol=0.0, what="xyz grad, pipelined vs plain")
     assert_sum(grads[1][1], grads[0][1], l1[1], C_TIES, rtol=0.0, what="rgb grad, pipelined vs plain")
 
@@ -1187,7 +1187,9 @@ def test_level_grouped_backward_and_pipelined_adam(groups, w1, monkeypatch):
     la, _ = ta._fused_fwbw(ro, rd, target, noise)
     lb, _ = tb._fused_fwbw(ro, rd, target, noise)
     torch.cuda.synchronize()
-    assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(lb))  # the loss is an order-dependent fp32 atomic sum over blocks
+    # the loss is an order-dependent fp32 atomic sum over the compositing kernel's two-ray blocks (2048 partial sums here): two runs
+    # of the SAME launch differ by a few 1e-7 relative (measured up to 1.0e-6); the gradients do not depend on it
+    assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(lb))
     geo = oracle.HashGeometry(per_level_scale=model_a.geometry.per_level_scale)
     o = _oracle_render_train(w, (N(model_a.xyz_encoder.params), N(model_a.rgb_net.params), geo), N(ro), N(rd), N(noise))
     _, _, l1x, l1c = _oracle_backward(w, o, geo, target.cpu())
