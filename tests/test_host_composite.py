@@ -113,3 +113,70 @@ def test_turn_structure_matches_sequential_compositing(sigma_max, thr):
     for ray_idx, start, N in rays_a:
         used = int(want[0][ray_idx])
         assert not got[4][start + used + 1:start + N].any()
+
+
+def emulate_bw(g_op, g_dep, g_rgb, sigmas, rgbs, deltas, ts, rays_a, opacity, depth, rgb, thr):
+    """composite_bw_ray without a dL_dws input (the fused training step's form): in-lane inclusive sums, one warp scan of the
+    lanes' totals per quantity, running carries across turns."""
+    dsig = np.zeros(len(sigmas), F); drgbs = np.zeros((len(sigmas), 3), F)
+    chunk = 32 * K_SPL
+    for ray_idx, start, N in rays_a:
+        R_, G_, B_ = (F(v) for v in rgb[ray_idx]); O_, D_ = F(opacity[ray_idx]), F(depth[ray_idx])
+        gR, gG, gB = (F(v) for v in g_rgb[ray_idx]); gO, gD = F(g_op[ray_idx]), F(g_dep[ray_idx])
+        T = F(1.0); carry = np.zeros(4, F); done = False; base = 0
+        while base < N and not done:
+            idx = base + np.arange(chunk); inside = idx < N
+            q = start + np.minimum(idx, max(N - 1, 0))
+            shape = (32, K_SPL)
+            dl = np.where(inside, deltas[q], F(0)).astype(F).reshape(shape)
+            al = np.where(inside, _alpha(sigmas[q], deltas[q]), F(0)).astype(F).reshape(shape)
+            om = (F(1.0) - al).astype(F)
+            pp = np.empty_like(om); pp[:, 0] = om[:, 0]
+            for k in range(1, K_SPL):
+                pp[:, k] = (pp[:, k - 1] * om[:, k]).astype(F)
+            incl = _warp_incl(pp[:, -1], np.multiply)
+            Tl = (T * np.concatenate([[F(1.0)], incl[:-1]]).astype(F)).astype(F)
+            Ta = (Tl[:, None] * pp).astype(F)
+            Tb = np.empty_like(Ta); Tb[:, 0] = Tl; Tb[:, 1:] = (Tl[:, None] * pp[:, :-1]).astype(F)
+            term = inside.reshape(shape) & (Ta <= F(thr))
+            last = int(np.argmax(term.reshape(-1))) if term.any() else chunk - 1
+            use = (inside & (np.arange(chunk) <= last)).reshape(shape)
+            w = np.where(use, (al * Tb).astype(F), F(0)).astype(F)
+            cols = [np.where(inside, c[q], F(0)).astype(F).reshape(shape) for c in (rgbs[:, 0], rgbs[:, 1], rgbs[:, 2], ts)]
+            pre = []                                                   # per-sample inclusive prefix of w*c over the whole ray
+            for j, c in enumerate(cols):
+                loc = np.cumsum((w * c).astype(F), axis=1, dtype=F)    # in-lane, sequential in float32
+                tot = _warp_incl(loc[:, -1], np.add)
+                excl = (carry[j] + (tot - loc[:, -1]).astype(F)).astype(F)
+                pre.append((excl[:, None] + loc).astype(F))
+                carry[j] = F(carry[j] + tot[31])
+            pr, pg, pb, pd = pre
+            cr, cg, cb, ct = cols
+            o_s = (dl * (gR * (cr * Ta - (R_ - pr)) + gG * (cg * Ta - (G_ - pg)) + gB * (cb * Ta - (B_ - pb))
+                         + gO * (F(1.0) - O_) + gD * (ct * Ta - (D_ - pd)))).astype(F)
+            sel = inside.reshape(shape)
+            dsig[start + idx[inside]] = np.where(use, o_s, F(0))[sel]
+            for c_, g_ in enumerate((gR, gG, gB)):
+                drgbs[start + idx[inside], c_] = np.where(use, (g_ * w).astype(F), F(0))[sel]
+            if term.any():
+                done = True
+            T = F(Ta[31, -1])
+            base += chunk
+    return dsig, drgbs
+
+
+@pytest.mark.parametrize("sigma_max,thr", [(40.0, 1e-4), (4000.0, 1e-2)])
+def test_turn_structure_matches_sequential_backward(sigma_max, thr):
+    rng = np.random.default_rng(9)
+    counts = [0, 1, 33, 64, 65, 128, 200, 437, 5]
+    sigmas, rgbs, deltas, ts, rays_a = _rays(rng, counts, sigma_max)
+    _, opacity, depth, rgb, ws = oracle.composite_train_fw(sigmas, rgbs, deltas, ts, rays_a, thr)
+    R = len(rays_a)
+    g_op, g_dep, g_rgb = rng.standard_normal(R).astype(F), rng.standard_normal(R).astype(F), rng.standard_normal((R, 3)).astype(F)
+    want_s, want_c = oracle.composite_train_bw(g_op, g_dep, g_rgb, np.zeros(len(sigmas), F), sigmas, rgbs, ws, deltas, ts, rays_a,
+                                               opacity, depth, rgb, thr)
+    got_s, got_c = emulate_bw(g_op, g_dep, g_rgb, sigmas, rgbs, deltas, ts, rays_a, opacity, depth, rgb, thr)
+    assert np.all(np.abs(got_c.astype(np.float64) - want_c) <= 2e-6 * np.abs(want_c) + 1e-6), "dL_drgbs"
+    # dL_dsigma is a difference of ray-sized sums scaled by delta: judged against the size of its terms, not of the result
+    scale = deltas * (np.abs(g_rgb).sum(1).max() * 4 + np.abs(g_op).max() + np.abs(g_dep).max() * ts.max(initial=1.0))
+    assert np.all(np.abs(got_s.astype(np.float64) - want_s) <= 1e-4 * np.abs(want_s) + 4e-6 * scale), "dL_dsigmas"
